@@ -1,0 +1,352 @@
+#!/usr/bin/env python
+"""Benchmark of the cooperative-training hot path (BASELINE.json metric:
+"cooperative-training samples/sec at 1/2/4/8 B200; masking-kernel HBM GB/s").
+
+    python bench.py --gpus N --steps K --warmup W            # this build, one rank per GPU
+    python bench.py --impl reference --gpus N --steps K ...  # the reference's CPU path (oracle port)
+    torchrun --nproc-per-node N bench.py --gpus N ...        # N > 1
+
+Workload (config.workload): BASELINE.json configs[1] -- ACDC cooperative_training config, synthetic
+1x224x224 slices, 4 classes, batch 64 PER GPU, bf16, channel(image code)+spatial(shape code) targeted
+soft masking with random thresholds.  A "step" is one full cooperative step (three passes + hard-example
+generation + backward + gradient all-reduce + Adam) over one batch.  Weak scaling: per-GPU batch is fixed.
+
+One JSON line on stdout (rank 0).  See DESIGN.md section 6 for how each field is measured.
+"""
+import argparse
+import json
+import os
+import random
+import statistics
+import subprocess
+import sys
+import tempfile
+import time
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+GF_PER_SAMPLE = {224: 64.01, 256: 83.61, 192: 47.03}      # conv GFLOP per sample-step
+IMAGE_CFG = {"loss_name": "mse", "mask_type": "channel", "max_threshold": 0.5, "random_threshold": True,
+             "if_soft": True}
+SEG_CFG = {"loss_name": "ce", "mask_type": "spatial", "max_threshold": 0.5, "random_threshold": True,
+           "if_soft": True}
+
+
+def measured_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            d = json.load(f)
+        return {"hbm_gbs": float(d["hbm_gbs"]), "bf16_tflops": float(d["bf16_tflops"]),
+                "bf16_tflops_sustained": float(d.get("bf16_tflops_sustained", d["bf16_tflops"])), "source": "measured"}
+    return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0, "source": "fallback"}
+
+
+def synthetic_batch(n, size, seed, device=None, pin=False):
+    """images U[0,1) f32 [n,1,H,W], labels randint{0..3} i64 [n,H,W]."""
+    g = torch.Generator().manual_seed(seed)
+    img = torch.rand((n, 1, size, size), generator=g, dtype=torch.float32)
+    lab = torch.randint(0, 4, (n, size, size), generator=g, dtype=torch.int64)
+    if pin:
+        img, lab = img.pin_memory(), lab.pin_memory()
+    if device is not None:
+        img, lab = img.to(device), lab.to(device)
+    return img, lab
+
+
+# ------------------------------------------------------------------------------------------------ clocks
+class ClockSampler:
+    QUERY = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+             "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.gpu_index = gpu_index
+        self.proc = None
+        self.path = None
+
+    def start(self):
+        try:
+            fd, self.path = tempfile.mkstemp(suffix=".csv")
+            os.close(fd)
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", "-i", str(self.gpu_index), "--query-gpu=" + self.QUERY, "--format=csv,noheader,nounits",
+                 "-lms", "200"], stdout=open(self.path, "w"), stderr=subprocess.DEVNULL)
+        except Exception:  # noqa: BLE001
+            self.proc = None
+
+    def stop(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": []}
+        if self.proc is None:
+            return out
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:  # noqa: BLE001
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        try:
+            for line in open(self.path):
+                parts = [p.strip() for p in line.split(",")]
+                if len(parts) < 9:
+                    continue
+                try:
+                    sm.append(float(parts[1]))
+                    mx.append(float(parts[2]))
+                except ValueError:
+                    continue
+                for name, val in zip(names, parts[5:9]):
+                    if val.lower().startswith("active"):
+                        reasons.add(name)
+            os.unlink(self.path)
+        except Exception:  # noqa: BLE001
+            pass
+        if sm:
+            out = {"sm_mhz": statistics.median(sm), "sm_max_mhz": max(mx), "reasons": sorted(reasons),
+                   "samples": len(sm)}
+        return out
+
+
+# ------------------------------------------------------------------------------------------------ CPU arm
+def cpu_reference_steps(steps, warmup, batch, size, threads):
+    """The reference's own CPU path (oracle/model_oracle.py restates it; the reference is Python and cannot
+    travel to the GPU box) on a bounded sample of the workload: same step, same mask config, batch `batch`."""
+    from oracle import model_oracle
+    torch.set_num_threads(threads)
+    random.seed(0)
+    np.random.seed(0)
+    torch.manual_seed(0)
+    solver = model_oracle.OracleSolver(num_classes=4, learning_rate=1e-4, seed=0)
+    img, lab = synthetic_batch(batch, size, seed=0)
+    for _ in range(warmup):
+        solver.cooperative_step(img, lab, IMAGE_CFG, SEG_CFG)
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        solver.cooperative_step(img, lab, IMAGE_CFG, SEG_CFG)
+    dt = time.perf_counter() - t0
+    return batch * steps / dt, dt
+
+
+def run_reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    threads = os.cpu_count() or 1
+    batch = args.ref_batch
+    value, dt = cpu_reference_steps(args.steps, args.warmup, batch, args.size, threads)
+    line = {
+        "impl": "reference", "metric": "cooperative-training samples/sec", "value": value, "unit": "samples/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": workload_config(args, batch_per_gpu=args.batch),
+        "cpu_baseline": {"value": value, "unit": "samples/s", "cores": threads, "kind": "port",
+                         "sample": "oracle/model_oracle.py (torch fp32 CPU restatement of the reference step), batch "
+                                   "%d of 1x%dx%d per step, %d timed steps" % (batch, args.size, args.size, args.steps)},
+        "e2e": {"value": value, "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def workload_config(args, batch_per_gpu):
+    return {"workload": "BASELINE.json configs[1]: ACDC cooperative_training step, synthetic 1x%dx%d slices, 4 classes, "
+                        "batch %d per GPU, channel(image code)+spatial(shape code) targeted soft masking, random "
+                        "thresholds (max 0.5)" % (args.size, args.size, batch_per_gpu),
+            "batch_per_gpu": batch_per_gpu, "global_batch": batch_per_gpu * args.gpus, "image": [1, args.size, args.size],
+            "num_classes": 4, "precision": args.precision, "parallelism": "dp%d" % args.gpus,
+            "l2_policy": "inputs larger than L2: one step touches several GB of activations (126 MB L2); the masking "
+                         "microbench reads/writes 308 MB per call and additionally flushes L2 between iterations"}
+
+
+# ------------------------------------------------------------------------------------------------ masking microbench
+def masking_microbench(pkg, peaks, iters=20):
+    """BASELINE.json configs[3]: [512,64,28,28] fp32 latent codes.  Times the K1+K2 pair (one fused C-ABI call,
+    two kernels) with CUDA events on the launching stream, L2 flushed between iterations."""
+    N, C, H, W = 512, 64, 28, 28
+    gen = torch.Generator(device="cuda").manual_seed(0)
+    z = torch.relu(torch.randn(N, C, H, W, device="cuda", generator=gen))
+    g = 1e-5 * torch.randn(N, C, H, W, device="cuda", generator=gen)
+    flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device="cuda")
+    numel = N * C * H * W
+    out = {}
+
+    def timed(fn, n_iter):
+        ts = []
+        for _ in range(3):
+            fn()
+        for _ in range(n_iter):
+            flush.zero_()
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            fn()
+            b.record()
+            torch.cuda.synchronize()
+            ts.append(a.elapsed_time(b) * 1e-3)
+        return statistics.mean(ts), min(ts)
+
+    rng = pkg.ops.NativeRNG(0)
+    for name, mode, n in (("channel", pkg.ops.MODE_CHANNEL, C), ("spatial", pkg.ops.MODE_SPATIAL, H * W)):
+        for p in (0.1, 0.3, 0.5):
+            k = int(n * p)
+            mean_t, best_t = timed(lambda: pkg.ops.saliency_mask_apply(g, z, mode, k, soft=True, rng=rng), iters)
+            algo = 12.0 * numel + 8.0 * N * n                     # g + z read, z~ written (fp32) + s, mask
+            out["%s_p%02d" % (name, int(p * 100))] = {"us": mean_t * 1e6, "best_us": best_t * 1e6,
+                                                     "GBps": algo / mean_t / 1e9, "algo_bytes": algo}
+    s = pkg.ops.saliency_reduce(g, pkg.ops.MODE_CHANNEL)
+    mean_t, _ = timed(lambda: pkg.ops.saliency_reduce(g, pkg.ops.MODE_CHANNEL), iters)
+    out["k1_channel"] = {"us": mean_t * 1e6, "GBps": 4.0 * numel / mean_t / 1e9}
+    mean_t, _ = timed(lambda: pkg.ops.saliency_reduce(g, pkg.ops.MODE_SPATIAL), iters)
+    out["k1_spatial"] = {"us": mean_t * 1e6, "GBps": 4.0 * numel / mean_t / 1e9}
+    mean_t, _ = timed(lambda: pkg.ops.topp_mask_apply(s, z, pkg.ops.MODE_CHANNEL, 19, soft=True, rng=rng), iters)
+    out["k2_channel"] = {"us": mean_t * 1e6, "GBps": 8.0 * numel / mean_t / 1e9}
+    mean_t, _ = timed(lambda: pkg.ops.channel_dropout(z, 0.5, rng=rng, want_mask=False), iters)
+    out["dropout_p50"] = {"us": mean_t * 1e6, "GBps": 8.0 * numel / mean_t / 1e9}
+    mean_t, _ = timed(lambda: pkg.ops.channel_dropout(z, 0.5, rng=rng, want_mask=True), iters)
+    out["dropout_p50_with_quirk_mask"] = {"us": mean_t * 1e6, "GBps": 12.0 * numel / mean_t / 1e9}
+    head = out["channel_p30"]
+    roofline = {"kernel": "ctl_saliency_mask_apply (K1 saliency_channel + K2 topp_mask_apply), [512,64,28,28] fp32, "
+                          "channel mode, p=0.3, soft, native Philox",
+                "bound": "hbm", "achieved": head["GBps"], "peak": peaks["hbm_gbs"], "unit": "GB/s",
+                "frac": head["GBps"] / peaks["hbm_gbs"], "traffic": None,
+                "algorithmic_bytes_per_launch": head["algo_bytes"], "peak_source": peaks["source"] + " (burst copy)",
+                "avg_launch_us": head["us"]}
+    return roofline, out
+
+
+# ------------------------------------------------------------------------------------------------ GPU arm
+def run_gpu_arm(args):
+    import torch.distributed as dist
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device -- this build has no CPU fallback (use --impl reference for the "
+                         "CPU baseline)")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    if world != args.gpus and rank == 0:
+        print("bench.py: warning: --gpus %d but WORLD_SIZE %d" % (args.gpus, world), file=sys.stderr)
+    args.gpus = world
+
+    import cooperative_training_and_latent_space_data_augmentation_b200 as pkg
+    from cooperative_training_and_latent_space_data_augmentation_b200 import _lib
+    pkg.conv_blocks.set_precision(args.precision)
+    torch.manual_seed(0)
+    solver = pkg.AdvancedTripletReconSegmentationModel('FCN_16_standard', num_classes=4, learning_rate=1e-4)
+    global_batch = args.batch * world
+    trainer = pkg.CooperativeTrainer(solver, global_batch, seed=0, image_cfg=IMAGE_CFG, seg_cfg=SEG_CFG)
+
+    # every rank draws its own slice of the global synthetic batch
+    img_h, lab_h = synthetic_batch(args.batch, args.size, seed=1000 + rank, pin=True)
+    img_d, lab_d = img_h.cuda(non_blocking=True), lab_h.cuda(non_blocking=True)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def device_step():
+        return trainer.step(img_d, lab_d)
+
+    def e2e_step():
+        a = img_h.cuda(non_blocking=True)
+        b = lab_h.cuda(non_blocking=True)
+        out = trainer.step(a, b)
+        return float(out['loss'].item())            # D2H read of the step's result
+
+    def timed_loop(fn, steps):
+        barrier()
+        start, stop = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        start.record()
+        for _ in range(steps):
+            last = fn()
+        stop.record()
+        barrier()
+        ms = start.elapsed_time(stop)
+        t = torch.tensor([ms], device="cuda", dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item()) * 1e-3, last
+
+    for _ in range(max(args.warmup, 3)):
+        device_step()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    launches0 = _lib.LAUNCHES["count"]
+    t_dev, _ = timed_loop(device_step, args.steps)
+    launches = _lib.LAUNCHES["count"] - launches0
+    for _ in range(2):
+        e2e_step()
+    t_e2e, last_loss = timed_loop(e2e_step, args.steps)
+    clocks = sampler.stop() if rank == 0 else None
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    peaks = measured_peaks()
+    value = global_batch * args.steps / t_dev
+    e2e_value = global_batch * args.steps / t_e2e
+    roofline, sweep = masking_microbench(pkg, peaks)
+    gf = GF_PER_SAMPLE.get(args.size)
+    cpu = None
+    if world == 1 and not args.no_cpu_baseline:
+        threads = os.cpu_count() or 1
+        v, dt = cpu_reference_steps(3, 1, args.ref_batch, args.size, threads)
+        cpu = {"value": v, "unit": "samples/s", "cores": threads, "kind": "port",
+               "sample": "oracle/model_oracle.py cooperative step, batch %d of 1x%dx%d, 1 warm-up + 3 timed steps "
+                         "(%.1f s)" % (args.ref_batch, args.size, args.size, dt)}
+    line = {
+        "metric": "cooperative-training samples/sec", "value": value, "unit": "samples/s", "n_gpus": world,
+        "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": 1e3 * t_dev / args.steps,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "bf16" if args.precision == "bf16" else "f32", "data": "synthetic",
+        "config": workload_config(args, args.batch),
+        "e2e": {"value": e2e_value, "unit": "samples/s",
+                "h2d_bytes_per_step": int(img_h.numel() * 4 + lab_h.numel() * 8) * world,
+                "d2h_bytes_per_step": 4 * world, "ms_per_step": 1e3 * t_e2e / args.steps,
+                "api": "CooperativeTrainer.step on pinned host tensors + loss.item()"},
+        "gpu_launches": launches,
+        "roofline": roofline,
+        "masking_GBps": {k: round(v["GBps"], 1) for k, v in sweep.items()},
+        "masking_us": {k: round(v["us"], 2) for k, v in sweep.items()},
+        "step_tensor_frac": (value * gf * 1e9 / (world * peaks["bf16_tflops_sustained"] * 1e12)) if gf else None,
+        "cpu_baseline": cpu,
+        "clocks": clocks,
+        "last_loss": last_loss,
+    }
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--batch", type=int, default=64, help="batch per GPU (configs[1]: 64)")
+    ap.add_argument("--size", type=int, default=224, help="slice height = width (configs[1]: 224)")
+    ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32"])
+    ap.add_argument("--ref-batch", type=int, default=8, help="bounded CPU sample: batch per CPU step")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference_arm(args)
+    else:
+        run_gpu_arm(args)
+
+
+if __name__ == "__main__":
+    main()

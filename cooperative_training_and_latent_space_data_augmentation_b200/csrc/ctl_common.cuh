@@ -1,0 +1,130 @@
+// Shared host/device helpers for the ctl_b200 kernels (sm_100a only).
+#pragma once
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/ctl_b200.h"
+
+namespace ctl {
+
+// ---- host side ---------------------------------------------------------------------------------
+void set_error(const char* fmt, ...);
+int cuda_fail(cudaError_t e, const char* what);   // records the message, returns CTL_ERR_CUDA
+int sm_count();                                   // cached per device; <0 on error
+
+#define CTL_CUDA_OK(expr, what)                         \
+  do {                                                  \
+    cudaError_t e__ = (expr);                           \
+    if (e__ != cudaSuccess) return ::ctl::cuda_fail(e__, what); \
+  } while (0)
+
+#define CTL_REQUIRE(cond, code, ...)  \
+  do {                                \
+    if (!(cond)) {                    \
+      ::ctl::set_error(__VA_ARGS__);  \
+      return (code);                  \
+    }                                 \
+  } while (0)
+
+static inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+static inline int64_t ceil_div(int64_t a, int64_t b) { return (a + b - 1) / b; }
+
+// ---- device side: 16-byte streaming access -----------------------------------------------------
+template <typename T>
+struct Elems16 { static constexpr int value = 16 / sizeof(T); };
+
+// load VEC consecutive elements as floats.  VEC == Elems16<T> -> one 128-bit load; VEC == 1 -> scalar.
+template <typename T, int VEC>
+__device__ __forceinline__ void load_as_float(const T* __restrict__ p, float (&out)[VEC]);
+
+template <>
+__device__ __forceinline__ void load_as_float<float, 4>(const float* __restrict__ p, float (&out)[4]) {
+  const float4 v = __ldcs(reinterpret_cast<const float4*>(p));
+  out[0] = v.x; out[1] = v.y; out[2] = v.z; out[3] = v.w;
+}
+template <>
+__device__ __forceinline__ void load_as_float<float, 1>(const float* __restrict__ p, float (&out)[1]) {
+  out[0] = __ldcs(p);
+}
+template <>
+__device__ __forceinline__ void load_as_float<__nv_bfloat16, 8>(const __nv_bfloat16* __restrict__ p,
+                                                                float (&out)[8]) {
+  const uint4 v = __ldcs(reinterpret_cast<const uint4*>(p));
+  const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    out[2 * i] = __uint_as_float(w[i] << 16);
+    out[2 * i + 1] = __uint_as_float(w[i] & 0xffff0000u);
+  }
+}
+template <>
+__device__ __forceinline__ void load_as_float<__nv_bfloat16, 1>(const __nv_bfloat16* __restrict__ p,
+                                                                float (&out)[1]) {
+  out[0] = __bfloat162float(*p);
+}
+
+// store VEC floats as VEC elements of T (round-to-nearest-even for bf16)
+template <typename T, int VEC>
+__device__ __forceinline__ void store_from_float(T* __restrict__ p, const float (&in)[VEC]);
+
+template <>
+__device__ __forceinline__ void store_from_float<float, 4>(float* __restrict__ p, const float (&in)[4]) {
+  *reinterpret_cast<float4*>(p) = make_float4(in[0], in[1], in[2], in[3]);
+}
+template <>
+__device__ __forceinline__ void store_from_float<float, 8>(float* __restrict__ p, const float (&in)[8]) {
+  reinterpret_cast<float4*>(p)[0] = make_float4(in[0], in[1], in[2], in[3]);
+  reinterpret_cast<float4*>(p)[1] = make_float4(in[4], in[5], in[6], in[7]);
+}
+template <>
+__device__ __forceinline__ void store_from_float<float, 1>(float* __restrict__ p, const float (&in)[1]) {
+  *p = in[0];
+}
+template <>
+__device__ __forceinline__ void store_from_float<__nv_bfloat16, 8>(__nv_bfloat16* __restrict__ p,
+                                                                   const float (&in)[8]) {
+  uint32_t w[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const __nv_bfloat162 h = __floats2bfloat162_rn(in[2 * i], in[2 * i + 1]);
+    w[i] = *reinterpret_cast<const uint32_t*>(&h);
+  }
+  *reinterpret_cast<uint4*>(p) = make_uint4(w[0], w[1], w[2], w[3]);
+}
+template <>
+__device__ __forceinline__ void store_from_float<__nv_bfloat16, 4>(__nv_bfloat16* __restrict__ p,
+                                                                   const float (&in)[4]) {
+  uint32_t w[2];
+#pragma unroll
+  for (int i = 0; i < 2; ++i) {
+    const __nv_bfloat162 h = __floats2bfloat162_rn(in[2 * i], in[2 * i + 1]);
+    w[i] = *reinterpret_cast<const uint32_t*>(&h);
+  }
+  *reinterpret_cast<uint2*>(p) = make_uint2(w[0], w[1]);
+}
+template <>
+__device__ __forceinline__ void store_from_float<__nv_bfloat16, 1>(__nv_bfloat16* __restrict__ p,
+                                                                   const float (&in)[1]) {
+  *p = __float2bfloat16_rn(in[0]);
+}
+
+// value a float takes after a round trip through T (used for the dropout "masked == z" compare)
+template <typename T> __device__ __forceinline__ float round_through(float v);
+template <> __device__ __forceinline__ float round_through<float>(float v) { return v; }
+template <> __device__ __forceinline__ float round_through<__nv_bfloat16>(float v) {
+  return __bfloat162float(__float2bfloat16_rn(v));
+}
+
+// lanes-of-a-row group mask for sub-warp shuffles
+template <int L>
+__device__ __forceinline__ unsigned group_mask() {
+  if constexpr (L >= 32) {
+    return 0xffffffffu;
+  } else {
+    const unsigned lane = threadIdx.x & 31u;
+    return ((1u << L) - 1u) << (lane & ~(unsigned)(L - 1));
+  }
+}
+
+}  // namespace ctl

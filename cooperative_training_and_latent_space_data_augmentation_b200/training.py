@@ -1,0 +1,192 @@
+"""One cooperative training step (the reference's loop body,
+medseg/train_adv_supervised_segmentation_triplet.py:171-237) and its batch-sharded data-parallel
+form over NCCL (the reference has no distributed code).
+
+Step = clean pass (standard_training) -> hard-example generation (latent masking, K1/K2) ->
+corrupted-image and corrupted-shape passes (hard_example_training) -> backward -> gradient
+all-reduce (one flat fp32 bucket, 2,528,953 elements) -> Adam.
+
+Differences from the reference loop that do not change results: losses stay on the device (the
+reference calls .item() nine times per step), no gc.collect()/empty_cache().
+
+Data parallel contract (8e):
+  * the batch is split in contiguous per-rank slices; no collective inside the masking kernels
+  * host RNG draws (mask type via python `random`, percentile via numpy) must be identical on all
+    ranks -> `seed_host_rng` seeds both the same way everywhere
+  * device RNG uses the native Philox mode keyed by the GLOBAL sample index, so a shard draws what
+    the full batch would
+  * BatchNorm uses per-rank batch statistics (equals the reference at the per-rank batch size;
+    no SyncBN); running statistics are therefore per-rank and rank 0's are the ones checkpointed
+  * gradients are averaged over ranks (each rank's losses are means over its own slice)
+"""
+import random as _pyrandom
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+from . import model_util
+
+LOSS_KEYS = ('loss/standard/total', 'loss/standard/seg', 'loss/standard/image', 'loss/standard/shape',
+             'loss/standard/gt_shape', 'loss/hard/total', 'loss/hard/seg', 'loss/hard/image', 'loss/hard/shape')
+
+DEFAULT_IMAGE_CFG = {"loss_name": "mse", "mask_type": "random", "max_threshold": 0.5, "random_threshold": True,
+                     "if_soft": True}
+DEFAULT_SEG_CFG = {"loss_name": "ce", "mask_type": "random", "max_threshold": 0.5, "random_threshold": True,
+                   "if_soft": True}
+
+
+def seed_host_rng(seed):
+    """python `random` + numpy global generator: the two host streams the hot path consumes."""
+    _pyrandom.seed(seed)
+    np.random.seed(seed)
+
+
+def latent_da_configs(experiment_opt):
+    """Reads the `latent_DA` block of config/ACDC/cooperative_training.json verbatim
+    (train...triplet.py:125-142).  Returns (gen_image, image_cfg, gen_seg, seg_cfg)."""
+    if not experiment_opt.get('learning', {}).get('latent_DA', False):
+        return False, None, False, None
+    block = experiment_opt['latent_DA']
+    scope = block['mask_scope']
+    gi, gs = 'image code' in scope, 'shape code' in scope
+    return gi, block['image code'] if gi else None, gs, block['shape code'] if gs else None
+
+
+def cooperative_step(solver, clean_image_l, label_l, corrupted_image_DA_config=None, corrupted_seg_DA_config=None,
+                     gen_corrupted_image=True, gen_corrupted_seg=True, latent_DA=True, separate_training=False,
+                     noise=None, grad_sync=None, optimize=True):
+    """Runs the loop body once.  Returns a dict of 0-d DEVICE tensors keyed like the reference's loss_dict
+    plus 'loss' (nothing is synchronised; call .item() on what you want to log)."""
+    icfg = corrupted_image_DA_config or DEFAULT_IMAGE_CFG
+    scfg = corrupted_seg_DA_config or DEFAULT_SEG_CFG
+    solver.train()
+    solver.reset_all_optimizers()
+    if noise is None:
+        noise = 0.05 * torch.randn_like(clean_image_l)
+    image_l = torch.clamp(clean_image_l + noise, 0, 1)
+
+    seg_loss, image_recon_loss, gt_recon_loss, shape_recon_loss = solver.standard_training(
+        clean_image_l, label_l, perturbed_image=image_l, separate_training=separate_training)
+    standard_loss = seg_loss + image_recon_loss + shape_recon_loss + gt_recon_loss
+    out = {'loss/standard/total': standard_loss.detach(), 'loss/standard/seg': seg_loss.detach(),
+           'loss/standard/image': image_recon_loss.detach(), 'loss/standard/shape': shape_recon_loss.detach(),
+           'loss/standard/gt_shape': gt_recon_loss.detach()}
+
+    if latent_DA:
+        p_img, p_seg = solver.hard_example_generation(
+            clean_image_l.detach(), label_l.detach(), gen_corrupted_seg=gen_corrupted_seg,
+            gen_corrupted_image=gen_corrupted_image, corrupted_image_DA_config=icfg, corrupted_seg_DA_config=scfg)
+        h_seg, h_img, h_shape2, h_cshape = solver.hard_example_training(
+            perturbed_image=p_img, perturbed_seg=p_seg, clean_image_l=clean_image_l, label_l=label_l,
+            separate_training=separate_training)
+        hard_loss = h_seg + h_img + h_shape2 + h_cshape
+        out.update({'loss/hard/total': hard_loss.detach(), 'loss/hard/seg': h_seg.detach(),
+                    'loss/hard/image': h_img.detach(), 'loss/hard/shape': (h_shape2 + h_cshape).detach(),
+                    'perturbed_image': p_img, 'perturbed_seg': p_seg})
+    else:
+        hard_loss = torch.zeros((), device=clean_image_l.device)
+        out.update({'loss/hard/total': hard_loss, 'loss/hard/seg': hard_loss, 'loss/hard/image': hard_loss,
+                    'loss/hard/shape': hard_loss})
+
+    loss = standard_loss + hard_loss
+    solver.reset_all_optimizers()
+    loss.backward()
+    if grad_sync is not None:
+        grad_sync()
+    if optimize:
+        solver.optimize_all_params()
+    out['loss'] = loss.detach()
+    return out
+
+
+class FlatGradBucket:
+    """All gradients of a parameter list as views of ONE flat fp32 buffer, so the data-parallel
+    exchange is a single all-reduce (10.1 MB for FCN_16_standard; latency-bound on NVLink 5 /
+    NVSwitch, hence one bucket rather than many).  Device-agnostic: the CPU tests drive it over gloo."""
+
+    def __init__(self, params):
+        self.params = [p for p in params]
+        if not self.params:
+            raise ValueError("no parameters")
+        dev, dt = self.params[0].device, self.params[0].dtype
+        self.numel = sum(p.numel() for p in self.params)
+        self.flat = torch.zeros(self.numel, device=dev, dtype=dt)
+        off = 0
+        for p in self.params:
+            n = p.numel()
+            p.grad = self.flat[off:off + n].view_as(p)
+            off += n
+
+    def zero(self):
+        self.flat.zero_()
+
+    def reattach(self):
+        """If something replaced a .grad (e.g. zero_grad(set_to_none=True)), fold it back into the bucket."""
+        off = 0
+        for p in self.params:
+            n = p.numel()
+            view = self.flat[off:off + n].view_as(p)
+            if p.grad is None:
+                view.zero_()
+                p.grad = view
+            elif p.grad.data_ptr() != view.data_ptr():
+                view.copy_(p.grad)
+                p.grad = view
+            off += n
+
+    def all_reduce_mean(self, group=None):
+        if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
+            self.reattach()
+            dist.all_reduce(self.flat, op=dist.ReduceOp.SUM, group=group)
+            self.flat.div_(dist.get_world_size(group))
+
+
+def shard_bounds(global_batch, world_size, rank):
+    """Contiguous N/world slices (8e).  The global batch must divide evenly."""
+    if global_batch % world_size:
+        raise ValueError("global batch %d is not divisible by world size %d" % (global_batch, world_size))
+    per = global_batch // world_size
+    return rank * per, (rank + 1) * per
+
+
+def broadcast_module_state(modules, src=0, group=None):
+    """Parameters and buffers of rank `src` to everyone (identical initial weights)."""
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
+        return
+    for m in modules:
+        for t in list(m.parameters()) + list(m.buffers()):
+            dist.broadcast(t.data, src=src, group=group)
+
+
+class CooperativeTrainer:
+    """Batch-sharded cooperative training: one process per GPU, NCCL all-reduce of one flat bucket."""
+
+    def __init__(self, solver, global_batch, seed=0, image_cfg=None, seg_cfg=None, group=None):
+        self.solver = solver
+        self.group = group
+        self.world = dist.get_world_size(group) if dist.is_available() and dist.is_initialized() else 1
+        self.rank = dist.get_rank(group) if self.world > 1 else 0
+        self.global_batch = global_batch
+        self.lo, self.hi = shard_bounds(global_batch, self.world, self.rank)
+        self.image_cfg = image_cfg or DEFAULT_IMAGE_CFG
+        self.seg_cfg = seg_cfg or DEFAULT_SEG_CFG
+        self.seed = seed
+        self.step_index = 0
+        broadcast_module_state(solver.model.values(), 0, group)
+        self.bucket = FlatGradBucket(list(solver.parameters()))
+        solver._grads_set_to_none = False          # keep .grad views of the flat bucket alive
+        seed_host_rng(seed)                         # identical host draws on every rank
+        model_util.set_rng_mode("philox", seed=seed, first_sample=self.lo)
+
+    def local_slice(self, global_tensor):
+        return global_tensor[self.lo:self.hi]
+
+    def step(self, clean_local, label_local, noise_local=None):
+        """`clean_local` / `label_local` are this rank's slice of the global batch."""
+        # Philox stream: advance first_sample by the global batch per step so no (sample, step) pair repeats
+        model_util.native_rng().first_sample = self.step_index * self.global_batch + self.lo
+        out = cooperative_step(self.solver, clean_local, label_local, self.image_cfg, self.seg_cfg,
+                               noise=noise_local, grad_sync=lambda: self.bucket.all_reduce_mean(self.group))
+        self.step_index += 1
+        return out

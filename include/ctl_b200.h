@@ -1,0 +1,101 @@
+/*
+ * ctl_b200.h -- C ABI of the B200-native cooperative-training hot path.
+ *
+ * Drop-in boundary.  The reference has no FFI: its boundary is four Python
+ * callables.  This library exports the device work those callables perform; the Python mirror in
+ * cooperative_training_and_latent_space_data_augmentation_b200/ binds it with ctypes and keeps the
+ * reference's names, argument order, defaults and exceptions.  INTEGRATION.md shows the stub a
+ * maintainer of the reference would add.
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer unless the name ends in _host; buffers are caller-allocated
+ *   - `stream` is a cudaStream_t passed as void* (0 = legacy default stream); calls are asynchronous
+ *   - return value: CTL_OK or an error code; ctl_last_error() gives a thread-local message
+ *   - no allocation, no global state, no CPU fallback: without a CUDA device every compute entry
+ *     point returns CTL_ERR_CUDA
+ *   - tensors are dense NCHW (masking) exactly as the reference passes them
+ */
+#ifndef CTL_B200_H_
+#define CTL_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define CTL_B200_VERSION 100 /* 0.1.0 */
+
+enum ctl_status {
+  CTL_OK = 0,
+  CTL_ERR_INVALID = 1,     /* bad argument (NULL pointer, non-positive size, unknown enum)          */
+  CTL_ERR_INDEX = 2,       /* k >= n: the reference raises IndexError (model_util.py:231-232)        */
+  CTL_ERR_UNSUPPORTED = 3, /* shape outside what the kernels handle (documented per entry point)     */
+  CTL_ERR_CUDA = 4         /* CUDA runtime error (message in ctl_last_error)                         */
+};
+
+enum ctl_dtype { CTL_F32 = 0, CTL_BF16 = 1 };
+enum ctl_mode { CTL_MODE_CHANNEL = 0, CTL_MODE_SPATIAL = 1 };
+
+int ctl_version(void);
+const char* ctl_last_error(void);
+/* number of SMs of the current device (grid sizing is derived from it); <0 on error */
+int ctl_device_sm_count(void);
+
+/* ---------------------------------------------------------------------------------------------
+ * K1 -- latent saliency.  Replaces
+ *   torch.mean(gradient.view(N, C, -1), dim=2)              medseg/models/model_util.py:224-225
+ *   torch.mean(gradient, dim=1, keepdim=True).squeeze()...  medseg/models/model_util.py:285-286
+ * g: [N,C,HW] (g_dtype), s_out: fp32 [N,C] (channel) or [N,HW] (spatial).
+ * Accumulates in fp64 and rounds once (order-independent; see oracle/masking_oracle.py).
+ */
+int ctl_saliency_reduce(const void* g, int g_dtype, int64_t N, int64_t C, int64_t HW, int mode,
+                        float* s_out, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * K2 -- per-sample top-p threshold, mask build and 128-bit apply.  Replaces
+ *   torch.sort(s, descending=True)[0][:, k]; torch.where(s > thr, 0.5*rand_like(s) | 0, 1);
+ *   code * mask.view(N,C,1,1) | (N,1,H,W)       medseg/models/model_util.py:231-249, :293-312
+ * s: fp32 [N,n], n = C (channel) or HW (spatial).  k = int(n*p) is computed by the caller on the host
+ * exactly as the reference does; k >= n returns CTL_ERR_INDEX, k < 0 CTL_ERR_INVALID.
+ * soft != 0: masked entries get 0.5*u with u = rand[i,j] when `rand` is non-NULL (the caller's
+ * torch.rand_like(s) draw -- reference-compatible mode), else u = Philox4x32-10(seed, offset,
+ * (first_sample+i)*n + j) (native, shard-invariant mode; first_sample = global index of row 0).
+ * mask_out: fp32 [N,n] (viewed by the caller as [N,C,1,1] or [N,1,H,W]); thr_out: fp32 [N] or NULL.
+ * z: [N,C,HW] (z_dtype) -> z_out same shape (out_dtype; the reference always produces fp32).
+ * Spatial mode keeps one sample's mask in shared memory: HW <= 51200, else CTL_ERR_UNSUPPORTED.
+ */
+int ctl_topp_mask_apply(const float* s, const void* z, int z_dtype, int64_t N, int64_t C, int64_t HW,
+                        int mode, int64_t k, int soft, const float* rand, uint64_t seed,
+                        uint64_t offset, int64_t first_sample, float* mask_out, float* thr_out,
+                        void* z_out, int out_dtype, void* stream);
+
+/* K1 + K2 back to back on `stream` (s_scratch: fp32 [N,n] caller scratch, holds s afterwards). */
+int ctl_saliency_mask_apply(const void* g, int g_dtype, const void* z, int z_dtype, int64_t N,
+                            int64_t C, int64_t HW, int mode, int64_t k, int soft, const float* rand,
+                            uint64_t seed, uint64_t offset, int64_t first_sample, float* s_scratch,
+                            float* mask_out, float* thr_out, void* z_out, int out_dtype,
+                            void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Random channel dropout.  Replaces F.dropout2d(z, p) + the full-size `where(masked == z, 1, 0)`
+ *   medseg/models/advanced_triplet_recon_segmentation_model.py:332-336
+ * keep: fp32 [N,C] of 0/1 (the caller's bernoulli_(1-p) draw) or NULL for native Philox
+ * (keep <=> u >= p).  z_out = z * (keep * scale), scale = fp32(1/(1-p)) supplied by the caller so the
+ * host controls the rounding (p == 1: scale 0; p == 0: pass scale 1 and keep NULL/ones).
+ * mask_out: fp32 [N,C,HW] = (z_out == z) or NULL to skip the reference's quirk mask.
+ * keep_out: fp32 [N,C] or NULL (the drawn pattern, for tests).
+ */
+int ctl_channel_dropout(const void* z, int z_dtype, int64_t N, int64_t C, int64_t HW, float p,
+                        float scale, const float* keep, uint64_t seed, uint64_t offset,
+                        int64_t first_sample, void* z_out, int out_dtype, float* mask_out,
+                        float* keep_out, void* stream);
+
+/* Philox4x32-10 uniform draw, exposed for parity tests of the native RNG: out[i] = u(first_index+i). */
+int ctl_philox_uniform(uint64_t seed, uint64_t offset, uint64_t first_index, int64_t count,
+                       float* out, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CTL_B200_H_ */
