@@ -276,7 +276,8 @@ def run_gpu_arm(args):
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item()) * 1e-3, last
 
-    for _ in range(max(args.warmup, 3)):
+    n_warm = args.warmup if args.profile else max(args.warmup, 3)
+    for _ in range(n_warm):
         device_step()
     sampler = ClockSampler(local_rank)
     if rank == 0:
@@ -284,6 +285,13 @@ def run_gpu_arm(args):
     launches0 = _lib.LAUNCHES["count"]
     t_dev, _ = timed_loop(device_step, args.steps)
     launches = _lib.LAUNCHES["count"] - launches0
+    if args.profile:                        # ncu launch-list pass: the device loop only
+        if rank == 0:
+            sampler.stop()
+            print(json.dumps({"profile_only": True, "ms_per_step": 1e3 * t_dev / args.steps}), flush=True)
+        if world > 1:
+            dist.destroy_process_group()
+        return
     for _ in range(2):
         e2e_step()
     t_e2e, last_loss = timed_loop(e2e_step, args.steps)
@@ -341,6 +349,7 @@ def main():
     ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32"])
     ap.add_argument("--ref-batch", type=int, default=8, help="bounded CPU sample: batch per CPU step")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--profile", action="store_true", help="device loop only, honour --warmup < 3 (for ncu)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference_arm(args)

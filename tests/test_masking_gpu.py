@@ -253,7 +253,9 @@ def test_full_size_properties(pkg):
     g = 1e-5 * torch.randn(N, C, H, W, device="cuda", generator=gen)
     for mode, n in ((mo.MODE_CHANNEL, C), (mo.MODE_SPATIAL, H * W)):
         s = pkg.ops.saliency_reduce(g, mode)
-        ref = g.double().mean(dim=(2, 3)) if mode == mo.MODE_CHANNEL else g.double().mean(dim=1).view(N, -1)
+        # float64 sum, ONE division, one rounding (torch's own double mean multiplies by 1/n instead)
+        ref = g.double().sum(dim=(2, 3)) / (H * W) if mode == mo.MODE_CHANNEL else \
+            (g.double().sum(dim=1) / C).view(N, -1)
         assert_equal_or_one_ulp(s.cpu().numpy(), ref.float().cpu().numpy())
         assert torch.equal(pkg.ops.saliency_reduce(g * 4, mode), s * 4)
         for p in (0.1, 0.3, 0.5):
