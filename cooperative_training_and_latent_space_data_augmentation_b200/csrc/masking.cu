@@ -24,47 +24,66 @@ namespace {
 constexpr int kThreads = 256;
 
 // ------------------------------------------------------------------------------------------------
-// K1, channel mode: one L-lane group per row, fp64 accumulation, shuffle reduction.
+// Streaming building block: a group of L lanes owns one row; each lane issues up to U independent
+// 128-bit loads before it touches any of them (U*16 bytes in flight per lane).
+// ------------------------------------------------------------------------------------------------
+constexpr int kU = 8;
+
+template <typename T, int VEC, int L>
+__device__ __forceinline__ void load_batch(const T* __restrict__ row, int base, int lane, int nv,
+                                           float (&a)[kU][VEC]) {
+#pragma unroll
+  for (int j = 0; j < kU; ++j) {
+    const int v = base + j * L + lane;
+    if (v < nv) {
+      load_as_float<T, VEC>(row + (int64_t)v * VEC, a[j]);
+    } else {
+#pragma unroll
+      for (int i = 0; i < VEC; ++i) a[j][i] = 0.0f;
+    }
+  }
+}
+
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
+// ------------------------------------------------------------------------------------------------
+// K1, channel mode: one L-lane group per (n,c) row, fp64 accumulation, shuffle reduction.
 // ------------------------------------------------------------------------------------------------
 template <typename T, int VEC, int L>
 __global__ void __launch_bounds__(kThreads)
 saliency_channel_kernel(const T* __restrict__ g, float* __restrict__ s, int64_t rows, int HW, int nv) {
+  pdl_launch_dependents();
   const int lane = threadIdx.x & (L - 1);
   const unsigned gmask = group_mask<L>();
-  const int64_t ngroups = (int64_t)gridDim.x * (kThreads / L);
-  const double inv_den = (double)HW;
-  for (int64_t row = (int64_t)blockIdx.x * (kThreads / L) + threadIdx.x / L; row < rows; row += ngroups) {
-    const T* __restrict__ p = g + row * HW;
-    double acc0 = 0.0, acc1 = 0.0;
-    int v = lane;
-    // two independent 128-bit loads in flight per lane per trip
-    for (; v + L < nv; v += 2 * L) {
-      float a[VEC], b[VEC];
-      load_as_float<T, VEC>(p + (int64_t)v * VEC, a);
-      load_as_float<T, VEC>(p + (int64_t)(v + L) * VEC, b);
+  const int64_t row = (int64_t)blockIdx.x * (kThreads / L) + threadIdx.x / L;
+  if (row >= rows) return;                     // whole group leaves together
+  const T* __restrict__ p = g + row * HW;
+  double acc0 = 0.0, acc1 = 0.0;
+  for (int base = 0; base < nv; base += kU * L) {
+    float a[kU][VEC];
+    load_batch<T, VEC, L>(p, base, lane, nv, a);
 #pragma unroll
-      for (int i = 0; i < VEC; ++i) { acc0 += (double)a[i]; acc1 += (double)b[i]; }
+    for (int j = 0; j < kU; j += 2) {
+#pragma unroll
+      for (int i = 0; i < VEC; ++i) { acc0 += (double)a[j][i]; acc1 += (double)a[j + 1][i]; }
     }
-    if (v < nv) {
-      float a[VEC];
-      load_as_float<T, VEC>(p + (int64_t)v * VEC, a);
-#pragma unroll
-      for (int i = 0; i < VEC; ++i) acc0 += (double)a[i];
-    }
-    double acc = acc0 + acc1;
-#pragma unroll
-    for (int o = L / 2; o > 0; o >>= 1) acc += __shfl_xor_sync(gmask, acc, o);
-    if (lane == 0) s[row] = (float)(acc / inv_den);
   }
+  double acc = acc0 + acc1;
+#pragma unroll
+  for (int o = L / 2; o > 0; o >>= 1) acc += __shfl_xor_sync(gmask, acc, o);
+  if (lane == 0) s[row] = (float)(acc / (double)HW);
 }
 
 // ------------------------------------------------------------------------------------------------
-// K1, spatial mode: CTA = (X vector columns) x (Y channel slices) of one sample.  Every row
-// segment a warp touches is X*16 contiguous bytes; the Y partial sums meet in shared memory.
+// K1, spatial mode: CTA = X vector columns x Y channel slices of one sample.  A warp reads X*16
+// contiguous bytes of one channel row; each thread keeps kU channel rows in flight; the Y partial
+// sums meet in shared memory (fp64).
 // ------------------------------------------------------------------------------------------------
 template <typename T, int VEC, int X, int Y>
 __global__ void __launch_bounds__(X * Y)
 saliency_spatial_kernel(const T* __restrict__ g, float* __restrict__ s, int C, int HW, int nv) {
+  pdl_launch_dependents();
   __shared__ double red[Y][X * VEC + 1];
   const int x = threadIdx.x % X, y = threadIdx.x / X;
   const int64_t n = blockIdx.y;
@@ -74,19 +93,23 @@ saliency_spatial_kernel(const T* __restrict__ g, float* __restrict__ s, int C, i
   for (int i = 0; i < VEC; ++i) acc[i] = 0.0;
   if (v < nv) {
     const T* __restrict__ p = g + n * (int64_t)C * HW + (int64_t)v * VEC;
-    int c = y;
-    for (; c + Y < C; c += 2 * Y) {
-      float a[VEC], b[VEC];
-      load_as_float<T, VEC>(p + (int64_t)c * HW, a);
-      load_as_float<T, VEC>(p + (int64_t)(c + Y) * HW, b);
+    for (int c0 = y; c0 < C; c0 += kU * Y) {
+      float a[kU][VEC];
 #pragma unroll
-      for (int i = 0; i < VEC; ++i) acc[i] += (double)a[i] + (double)b[i];
-    }
-    if (c < C) {
-      float a[VEC];
-      load_as_float<T, VEC>(p + (int64_t)c * HW, a);
+      for (int j = 0; j < kU; ++j) {
+        const int c = c0 + j * Y;
+        if (c < C) {
+          load_as_float<T, VEC>(p + (int64_t)c * HW, a[j]);
+        } else {
 #pragma unroll
-      for (int i = 0; i < VEC; ++i) acc[i] += (double)a[i];
+          for (int i = 0; i < VEC; ++i) a[j][i] = 0.0f;
+        }
+      }
+#pragma unroll
+      for (int j = 0; j < kU; ++j) {
+#pragma unroll
+        for (int i = 0; i < VEC; ++i) acc[i] += (double)a[j][i];
+      }
     }
   }
 #pragma unroll
@@ -96,7 +119,7 @@ saliency_spatial_kernel(const T* __restrict__ g, float* __restrict__ s, int C, i
     const int64_t hw = (int64_t)blockIdx.x * X * VEC + e;
     if (hw < HW) {
       double t = 0.0;
-#pragma unroll 8
+#pragma unroll
       for (int j = 0; j < Y; ++j) t += red[j][e];
       s[n * HW + hw] = (float)(t / (double)C);
     }
@@ -117,16 +140,17 @@ __device__ __forceinline__ float key_to_float(uint32_t k) {
   return __uint_as_float((k & 0x80000000u) ? (k & 0x7fffffffu) : ~k);
 }
 
-// All threads of the CTA call this; returns the k-th (0-based) largest value of srow[0..n).
-__device__ float block_kth_largest(const float* __restrict__ srow, int n, int k, uint32_t* hist /*[256]*/,
-                                   uint32_t* sel /*[2]*/) {
+// All threads of the CTA call this; keys[0..n) live in shared memory.  Returns the key of the
+// k-th (0-based) largest element.
+__device__ uint32_t block_kth_largest_key(const uint32_t* __restrict__ keys, int n, int k,
+                                          uint32_t* hist /*[256]*/, uint32_t* sel /*[2]*/) {
   uint32_t prefix = 0, known = 0, krem = (uint32_t)k;
 #pragma unroll 1
   for (int shift = 24; shift >= 0; shift -= 8) {
     for (int i = threadIdx.x; i < 256; i += blockDim.x) hist[i] = 0;
     __syncthreads();
     for (int j = threadIdx.x; j < n; j += blockDim.x) {
-      const uint32_t key = order_key(srow[j]);
+      const uint32_t key = keys[j];
       if ((key & known) == prefix) atomicAdd(&hist[(key >> shift) & 255u], 1u);
     }
     __syncthreads();
@@ -161,7 +185,7 @@ __device__ float block_kth_largest(const float* __restrict__ srow, int n, int k,
     known |= 255u << shift;
     krem = sel[1];
   }
-  return key_to_float(prefix);
+  return prefix;
 }
 
 __device__ __forceinline__ float mask_value(float sv, float thr, int soft, const float* __restrict__ rand,
@@ -172,65 +196,67 @@ __device__ __forceinline__ float mask_value(float sv, float thr, int soft, const
   return 0.5f * u;
 }
 
-template <typename ZT, typename OT, int VEC, int L, int MODE>
+template <int VEC, int MODE>
+__device__ __forceinline__ void scale_vec(float (&a)[VEC], float mrow, const float* __restrict__ mask_sm, int v) {
+#pragma unroll
+  for (int i = 0; i < VEC; ++i) a[i] *= (MODE == CTL_MODE_CHANNEL) ? mrow : mask_sm[v * VEC + i];
+}
+
+// CTA = rows [c0, c0+rows_per_cta) of one sample; group gi (L lanes) owns rows c0+gi, c0+gi+G, ...
+// The first row's data is requested BEFORE the dependency wait / select: z does not depend on K1.
+template <typename ZT, typename OT, int VEC, int L, int MODE, bool PDL>
 __global__ void __launch_bounds__(kThreads)
 topp_mask_apply_kernel(const float* __restrict__ s, const ZT* __restrict__ z, OT* __restrict__ z_out,
                        float* __restrict__ mask_out, float* __restrict__ thr_out,
                        const float* __restrict__ rand, PhiloxKey key, int C, int HW, int nv, int k, int soft,
                        int rows_per_cta, int64_t first_sample) {
-  extern __shared__ float mask_sm[];          // channel: rows_per_cta floats; spatial: HW floats
+  extern __shared__ float mask_sm[];          // n floats: first the keys of s, then (in place) the mask
   __shared__ uint32_t hist[256];
   __shared__ uint32_t sel[2];
+  constexpr int G = kThreads / L;
   const int64_t sample = blockIdx.y;
   const int n = (MODE == CTL_MODE_CHANNEL) ? C : HW;
-  const float* __restrict__ srow = s + sample * n;
-  const float thr = block_kth_largest(srow, n, k, hist, sel);
-  if (thr_out && blockIdx.x == 0 && threadIdx.x == 0) thr_out[sample] = thr;
-
   const int c0 = blockIdx.x * rows_per_cta;
   const int crows = min(rows_per_cta, C - c0);
+  const int lane = threadIdx.x & (L - 1);
+  const int gi = threadIdx.x / L;
+  const int64_t base = (sample * C + c0) * (int64_t)HW;
+
+  float a[kU][VEC];
+  if (gi < crows) load_batch<ZT, VEC, L>(z + base + (int64_t)gi * HW, 0, lane, nv, a);
+
+  if (PDL) pdl_wait();                        // s is produced by the preceding K1 launch
+
+  const float* __restrict__ srow = s + sample * n;
+  uint32_t* keys = reinterpret_cast<uint32_t*>(mask_sm);
+  for (int j = threadIdx.x; j < n; j += kThreads) keys[j] = order_key(srow[j]);
+  const float thr = key_to_float(block_kth_largest_key(keys, n, k, hist, sel));   // syncs inside
+  if (thr_out && blockIdx.x == 0 && threadIdx.x == 0) thr_out[sample] = thr;
+
   const uint64_t gbase = (uint64_t)(first_sample + sample) * (uint64_t)n;
-  if (MODE == CTL_MODE_CHANNEL) {
-    for (int j = threadIdx.x; j < crows; j += kThreads) {
-      const int c = c0 + j;
-      const float m = mask_value(srow[c], thr, soft, rand, key, gbase + c, sample * n + c);
-      mask_sm[j] = m;
-      mask_out[sample * n + c] = m;
-    }
-  } else {
-    for (int j = threadIdx.x; j < n; j += kThreads) {
-      const float m = mask_value(srow[j], thr, soft, rand, key, gbase + j, sample * n + j);
-      mask_sm[j] = m;
-      if (blockIdx.x == 0) mask_out[sample * n + j] = m;
-    }
+  for (int j = threadIdx.x; j < n; j += kThreads) {
+    // same thread reads keys[j] and overwrites it with the mask value: no hazard
+    const float m = mask_value(key_to_float(keys[j]), thr, soft, rand, key, gbase + j, sample * n + j);
+    mask_sm[j] = m;
+    const bool mine = (MODE == CTL_MODE_CHANNEL) ? (j >= c0 && j < c0 + crows) : (blockIdx.x == 0);
+    if (mine) mask_out[sample * n + j] = m;
   }
   __syncthreads();
 
-  const int lane = threadIdx.x & (L - 1);
-  const int64_t base = (sample * C + c0) * (int64_t)HW;
-  for (int r = threadIdx.x / L; r < crows; r += kThreads / L) {
+  for (int r = gi; r < crows; r += G) {
     const ZT* __restrict__ zi = z + base + (int64_t)r * HW;
     OT* __restrict__ zo = z_out + base + (int64_t)r * HW;
-    const float mrow = (MODE == CTL_MODE_CHANNEL) ? mask_sm[r] : 1.0f;
-    int v = lane;
-    for (; v + L < nv; v += 2 * L) {
-      float a[VEC], b[VEC];
-      load_as_float<ZT, VEC>(zi + (int64_t)v * VEC, a);
-      load_as_float<ZT, VEC>(zi + (int64_t)(v + L) * VEC, b);
+    const float mrow = (MODE == CTL_MODE_CHANNEL) ? mask_sm[c0 + r] : 1.0f;
+    for (int vb = 0; vb < nv; vb += kU * L) {
+      if (r != gi || vb != 0) load_batch<ZT, VEC, L>(zi, vb, lane, nv, a);
 #pragma unroll
-      for (int i = 0; i < VEC; ++i) {
-        a[i] *= (MODE == CTL_MODE_CHANNEL) ? mrow : mask_sm[v * VEC + i];
-        b[i] *= (MODE == CTL_MODE_CHANNEL) ? mrow : mask_sm[(v + L) * VEC + i];
+      for (int j = 0; j < kU; ++j) {
+        const int v = vb + j * L + lane;
+        if (v < nv) {
+          scale_vec<VEC, MODE>(a[j], mrow, mask_sm, v);
+          store_from_float<OT, VEC>(zo + (int64_t)v * VEC, a[j]);
+        }
       }
-      store_from_float<OT, VEC>(zo + (int64_t)v * VEC, a);
-      store_from_float<OT, VEC>(zo + (int64_t)(v + L) * VEC, b);
-    }
-    if (v < nv) {
-      float a[VEC];
-      load_as_float<ZT, VEC>(zi + (int64_t)v * VEC, a);
-#pragma unroll
-      for (int i = 0; i < VEC; ++i) a[i] *= (MODE == CTL_MODE_CHANNEL) ? mrow : mask_sm[v * VEC + i];
-      store_from_float<OT, VEC>(zo + (int64_t)v * VEC, a);
     }
   }
 }
@@ -244,24 +270,31 @@ channel_dropout_kernel(const ZT* __restrict__ z, OT* __restrict__ z_out, float* 
                        const float* __restrict__ keep, float* __restrict__ keep_out, PhiloxKey key,
                        int64_t rows, int HW, int nv, float p, float scale, uint64_t first_row) {
   const int lane = threadIdx.x & (L - 1);
-  const int64_t ngroups = (int64_t)gridDim.x * (kThreads / L);
-  for (int64_t row = (int64_t)blockIdx.x * (kThreads / L) + threadIdx.x / L; row < rows; row += ngroups) {
-    const float kf = keep ? keep[row] : (philox_uniform(key, first_row + (uint64_t)row) >= p ? 1.0f : 0.0f);
-    if (keep_out && lane == 0) keep_out[row] = kf;
-    const float noise = round_through<ZT>(kf * scale);   // the reference's noise tensor has z's dtype
-    const ZT* __restrict__ zi = z + row * HW;
-    OT* __restrict__ zo = z_out + row * HW;
-    float* __restrict__ mo = mask_out ? mask_out + row * HW : nullptr;
-    for (int v = lane; v < nv; v += L) {
-      float a[VEC], o[VEC], m[VEC];
-      load_as_float<ZT, VEC>(zi + (int64_t)v * VEC, a);
+  const int64_t row = (int64_t)blockIdx.x * (kThreads / L) + threadIdx.x / L;
+  if (row >= rows) return;
+  const ZT* __restrict__ zi = z + row * HW;
+  OT* __restrict__ zo = z_out + row * HW;
+  float* __restrict__ mo = mask_out ? mask_out + row * HW : nullptr;
+  float a[kU][VEC];
+  load_batch<ZT, VEC, L>(zi, 0, lane, nv, a);            // in flight while the Philox draw is computed
+  const float kf = keep ? keep[row] : (philox_uniform(key, first_row + (uint64_t)row) >= p ? 1.0f : 0.0f);
+  if (keep_out && lane == 0) keep_out[row] = kf;
+  const float noise = round_through<ZT>(kf * scale);     // the reference's noise tensor has z's dtype
+  for (int vb = 0; vb < nv; vb += kU * L) {
+    if (vb != 0) load_batch<ZT, VEC, L>(zi, vb, lane, nv, a);
 #pragma unroll
-      for (int i = 0; i < VEC; ++i) {
-        o[i] = a[i] * noise;
-        m[i] = (round_through<OT>(o[i]) == a[i]) ? 1.0f : 0.0f;
+    for (int j = 0; j < kU; ++j) {
+      const int v = vb + j * L + lane;
+      if (v < nv) {
+        float o[VEC], m[VEC];
+#pragma unroll
+        for (int i = 0; i < VEC; ++i) {
+          o[i] = a[j][i] * noise;
+          m[i] = (round_through<OT>(o[i]) == a[j][i]) ? 1.0f : 0.0f;
+        }
+        store_from_float<OT, VEC>(zo + (int64_t)v * VEC, o);
+        if (mo) store_from_float<float, VEC>(mo + (int64_t)v * VEC, m);
       }
-      store_from_float<OT, VEC>(zo + (int64_t)v * VEC, o);
-      if (mo) store_from_float<float, VEC>(mo + (int64_t)v * VEC, m);
     }
   }
 }
@@ -272,14 +305,16 @@ __global__ void philox_uniform_kernel(PhiloxKey key, uint64_t first, int64_t cou
 }
 
 // ---- launch helpers ------------------------------------------------------------------------------
+// lanes per row: enough rows in flight per CTA, yet most of a row covered by one kU-deep batch
 inline int pick_lanes(int nv) { return nv >= 128 ? 32 : nv >= 64 ? 16 : nv >= 16 ? 8 : 4; }
 
 template <typename T, int VEC>
 int launch_saliency_channel(const T* g, float* s, int64_t rows, int HW, cudaStream_t st) {
   const int nv = HW / VEC;
   const int L = pick_lanes(nv);
-  const int64_t want = ceil_div(rows * L, kThreads);
-  const int grid = (int)std::min<int64_t>(want, (int64_t)sm_count() * 16);
+  const int64_t grid64 = ceil_div(rows, kThreads / L);
+  CTL_REQUIRE(grid64 <= 0x7fffffff, CTL_ERR_UNSUPPORTED, "too many rows for one launch");
+  const unsigned grid = (unsigned)grid64;
   switch (L) {
     case 32: saliency_channel_kernel<T, VEC, 32><<<grid, kThreads, 0, st>>>(g, s, rows, HW, nv); break;
     case 16: saliency_channel_kernel<T, VEC, 16><<<grid, kThreads, 0, st>>>(g, s, rows, HW, nv); break;
@@ -293,64 +328,77 @@ int launch_saliency_channel(const T* g, float* s, int64_t rows, int HW, cudaStre
 template <typename T, int VEC>
 int launch_saliency_spatial(const T* g, float* s, int64_t N, int C, int HW, cudaStream_t st) {
   const int nv = HW / VEC;
-  if (VEC > 1) {
-    constexpr int X = 8, Y = 32;
-    dim3 grid((unsigned)ceil_div(nv, X), (unsigned)N);
-    saliency_spatial_kernel<T, VEC, X, Y><<<grid, X * Y, 0, st>>>(g, s, C, HW, nv);
-  } else {
-    constexpr int X = 32, Y = 8;
-    dim3 grid((unsigned)ceil_div(nv, X), (unsigned)N);
-    saliency_spatial_kernel<T, 1, X, Y><<<grid, X * Y, 0, st>>>(g, s, C, HW, nv);
-  }
+  constexpr int X = 32, Y = 8;
+  dim3 grid((unsigned)ceil_div(nv, X), (unsigned)N);
+  saliency_spatial_kernel<T, VEC, X, Y><<<grid, X * Y, 0, st>>>(g, s, C, HW, nv);
   CTL_CUDA_OK(cudaGetLastError(), "saliency_spatial launch");
   return CTL_OK;
 }
 
-template <typename ZT, typename OT, int VEC, int MODE>
+template <typename ZT, typename OT, int VEC, int L, int MODE, bool PDL>
+int launch_topp_kernel(dim3 grid, size_t smem, cudaStream_t st, const float* s, const ZT* z, OT* z_out,
+                       float* mask_out, float* thr_out, const float* rand, PhiloxKey key, int C, int HW, int nv, int k,
+                       int soft, int rows_per_cta, int64_t first_sample) {
+  auto kern = topp_mask_apply_kernel<ZT, OT, VEC, L, MODE, PDL>;
+  if (smem > 48 * 1024)
+    CTL_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem),
+                "topp smem attribute");
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = dim3(kThreads);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = PDL ? 1 : 0;
+  CTL_CUDA_OK(cudaLaunchKernelEx(&cfg, kern, s, z, z_out, mask_out, thr_out, rand, key, C, HW, nv, k, soft,
+                                 rows_per_cta, first_sample),
+              "topp_mask_apply launch");
+  return CTL_OK;
+}
+
+template <typename ZT, typename OT, int VEC, int MODE, bool PDL>
 int launch_topp(const float* s, const ZT* z, OT* z_out, float* mask_out, float* thr_out, const float* rand,
                 PhiloxKey key, int64_t N, int C, int HW, int k, int soft, int64_t first_sample, cudaStream_t st) {
   const int nv = HW / VEC;
   const int L = pick_lanes(nv);
-  // ~32 KB of z per CTA amortises the redundant per-CTA select; shrink while the grid under-fills the chip
-  int rows_per_cta = (int)std::max<int64_t>(1, std::min<int64_t>(C, (32 * 1024) / ((int64_t)HW * sizeof(ZT))));
-  int chunks = (int)ceil_div(C, rows_per_cta);
-  while (N * chunks < 2 * (int64_t)sm_count() && rows_per_cta > 1) {
-    rows_per_cta = (rows_per_cta + 1) / 2;
-    chunks = (int)ceil_div(C, rows_per_cta);
-  }
-  rows_per_cta = (int)ceil_div(C, chunks);
-  chunks = (int)ceil_div(C, rows_per_cta);
-  const size_t smem = sizeof(float) * (size_t)(MODE == CTL_MODE_CHANNEL ? rows_per_cta : HW);
+  const int G = kThreads / L;
+  // one row per group per CTA keeps every lane busy and the per-CTA select cheap relative to its stream;
+  // take more rows per group only when the rows are short (< 4 KB) and the grid stays >= 4 waves
+  int rows_per_cta = G;
+  while ((int64_t)rows_per_cta * HW * (int64_t)sizeof(ZT) < 16 * 1024 && rows_per_cta < C &&
+         N * ceil_div(C, 2 * rows_per_cta) >= 8 * (int64_t)sm_count())
+    rows_per_cta *= 2;
+  rows_per_cta = std::min(rows_per_cta, C);
+  const int chunks = (int)ceil_div(C, rows_per_cta);
+  const int n = MODE == CTL_MODE_CHANNEL ? C : HW;
+  const size_t smem = sizeof(float) * (size_t)n;
   dim3 grid((unsigned)chunks, (unsigned)N);
-#define CTL_LAUNCH_TOPP(LL)                                                                                 \
-  do {                                                                                                      \
-    auto kern = topp_mask_apply_kernel<ZT, OT, VEC, LL, MODE>;                                              \
-    if (smem > 48 * 1024)                                                                                   \
-      CTL_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem),       \
-                  "topp smem attribute");                                                                   \
-    kern<<<grid, kThreads, smem, st>>>(s, z, z_out, mask_out, thr_out, rand, key, C, HW, nv, k, soft,       \
-                                       rows_per_cta, first_sample);                                         \
-  } while (0)
+#define CTL_LAUNCH_TOPP(LL)                                                                                      \
+  return launch_topp_kernel<ZT, OT, VEC, LL, MODE, PDL>(grid, smem, st, s, z, z_out, mask_out, thr_out, rand, key, C, \
+                                                        HW, nv, k, soft, rows_per_cta, first_sample)
   switch (L) {
-    case 32: CTL_LAUNCH_TOPP(32); break;
-    case 16: CTL_LAUNCH_TOPP(16); break;
-    case 8: CTL_LAUNCH_TOPP(8); break;
-    default: CTL_LAUNCH_TOPP(4); break;
+    case 32: CTL_LAUNCH_TOPP(32);
+    case 16: CTL_LAUNCH_TOPP(16);
+    case 8: CTL_LAUNCH_TOPP(8);
+    default: CTL_LAUNCH_TOPP(4);
   }
 #undef CTL_LAUNCH_TOPP
-  CTL_CUDA_OK(cudaGetLastError(), "topp_mask_apply launch");
-  return CTL_OK;
 }
 
 template <typename ZT, typename OT, int VEC>
-int launch_topp_mode(int mode, const float* s, const ZT* z, OT* z_out, float* mask_out, float* thr_out,
+int launch_topp_mode(int mode, bool pdl, const float* s, const ZT* z, OT* z_out, float* mask_out, float* thr_out,
                      const float* rand, PhiloxKey key, int64_t N, int C, int HW, int k, int soft,
                      int64_t first_sample, cudaStream_t st) {
+#define CTL_ARGS s, z, z_out, mask_out, thr_out, rand, key, N, C, HW, k, soft, first_sample, st
   if (mode == CTL_MODE_CHANNEL)
-    return launch_topp<ZT, OT, VEC, CTL_MODE_CHANNEL>(s, z, z_out, mask_out, thr_out, rand, key, N, C, HW, k, soft,
-                                                      first_sample, st);
-  return launch_topp<ZT, OT, VEC, CTL_MODE_SPATIAL>(s, z, z_out, mask_out, thr_out, rand, key, N, C, HW, k, soft,
-                                                    first_sample, st);
+    return pdl ? launch_topp<ZT, OT, VEC, CTL_MODE_CHANNEL, true>(CTL_ARGS)
+               : launch_topp<ZT, OT, VEC, CTL_MODE_CHANNEL, false>(CTL_ARGS);
+  return pdl ? launch_topp<ZT, OT, VEC, CTL_MODE_SPATIAL, true>(CTL_ARGS)
+             : launch_topp<ZT, OT, VEC, CTL_MODE_SPATIAL, false>(CTL_ARGS);
+#undef CTL_ARGS
 }
 
 template <typename ZT, typename OT, int VEC>
@@ -358,8 +406,9 @@ int launch_dropout(const ZT* z, OT* z_out, float* mask_out, const float* keep, f
                    int64_t rows, int HW, float p, float scale, uint64_t first_row, cudaStream_t st) {
   const int nv = HW / VEC;
   const int L = pick_lanes(nv);
-  const int64_t want = ceil_div(rows * L, kThreads);
-  const int grid = (int)std::min<int64_t>(want, (int64_t)sm_count() * 16);
+  const int64_t grid64 = ceil_div(rows, kThreads / L);
+  CTL_REQUIRE(grid64 <= 0x7fffffff, CTL_ERR_UNSUPPORTED, "too many rows for one launch");
+  const unsigned grid = (unsigned)grid64;
   switch (L) {
     case 32: channel_dropout_kernel<ZT, OT, VEC, 32><<<grid, kThreads, 0, st>>>(z, z_out, mask_out, keep, keep_out, key, rows, HW, nv, p, scale, first_row); break;
     case 16: channel_dropout_kernel<ZT, OT, VEC, 16><<<grid, kThreads, 0, st>>>(z, z_out, mask_out, keep, keep_out, key, rows, HW, nv, p, scale, first_row); break;
@@ -409,10 +458,10 @@ extern "C" int ctl_saliency_reduce(const void* g, int g_dtype, int64_t N, int64_
              : launch_saliency_spatial<__nv_bfloat16, 1>((const __nv_bfloat16*)g, s_out, N, (int)C, (int)HW, st);
 }
 
-extern "C" int ctl_topp_mask_apply(const float* s, const void* z, int z_dtype, int64_t N, int64_t C, int64_t HW,
-                                   int mode, int64_t k, int soft, const float* rand, uint64_t seed, uint64_t offset,
-                                   int64_t first_sample, float* mask_out, float* thr_out, void* z_out, int out_dtype,
-                                   void* stream) {
+static int topp_impl(bool pdl, const float* s, const void* z, int z_dtype, int64_t N, int64_t C, int64_t HW,
+                     int mode, int64_t k, int soft, const float* rand, uint64_t seed, uint64_t offset,
+                     int64_t first_sample, float* mask_out, float* thr_out, void* z_out, int out_dtype,
+                     void* stream) {
   CTL_REQUIRE(s && z && mask_out && z_out, CTL_ERR_INVALID, "ctl_topp_mask_apply: NULL pointer");
   CTL_REQUIRE(valid_dtype(z_dtype) && valid_dtype(out_dtype), CTL_ERR_INVALID, "ctl_topp_mask_apply: unknown dtype");
   CTL_REQUIRE(mode == CTL_MODE_CHANNEL || mode == CTL_MODE_SPATIAL, CTL_ERR_INVALID, "unknown mode %d", mode);
@@ -422,8 +471,8 @@ extern "C" int ctl_topp_mask_apply(const float* s, const void* z, int z_dtype, i
   CTL_REQUIRE(k < n, CTL_ERR_INDEX, "index %lld is out of bounds for dimension 1 with size %lld", (long long)k,
               (long long)n);
   CTL_REQUIRE(first_sample >= 0, CTL_ERR_INVALID, "first_sample must be >= 0");
-  CTL_REQUIRE(mode == CTL_MODE_CHANNEL || HW <= 51200, CTL_ERR_UNSUPPORTED,
-              "spatial mode keeps the sample mask in shared memory: HW=%lld > 51200", (long long)HW);
+  CTL_REQUIRE(n <= 51200, CTL_ERR_UNSUPPORTED,
+              "one sample's saliency row is kept in shared memory: n=%lld > 51200", (long long)n);
   if (sm_count() < 0) return CTL_ERR_CUDA;
   cudaStream_t st = (cudaStream_t)stream;
   const PhiloxKey key{seed, offset};
@@ -432,13 +481,22 @@ extern "C" int ctl_topp_mask_apply(const float* s, const void* z, int z_dtype, i
   const bool vec = (HW % vw == 0) && aligned16(z) && aligned16(z_out);
   const int Ci = (int)C, HWi = (int)HW, ki = (int)k;
 #define CTL_TOPP(ZT, OT, V) \
-  return launch_topp_mode<ZT, OT, V>(mode, s, (const ZT*)z, (OT*)z_out, mask_out, thr_out, rand, key, N, Ci, HWi, ki, \
-                                     soft != 0, first_sample, st)
+  return launch_topp_mode<ZT, OT, V>(mode, pdl, s, (const ZT*)z, (OT*)z_out, mask_out, thr_out, rand, key, N, Ci, HWi, \
+                                     ki, soft != 0, first_sample, st)
   if (zf && of) { if (vec) CTL_TOPP(float, float, 4); else CTL_TOPP(float, float, 1); }
   if (zf && !of) { if (vec) CTL_TOPP(float, __nv_bfloat16, 4); else CTL_TOPP(float, __nv_bfloat16, 1); }
   if (!zf && of) { if (vec) CTL_TOPP(__nv_bfloat16, float, 8); else CTL_TOPP(__nv_bfloat16, float, 1); }
   if (vec) CTL_TOPP(__nv_bfloat16, __nv_bfloat16, 8); else CTL_TOPP(__nv_bfloat16, __nv_bfloat16, 1);
 #undef CTL_TOPP
+}
+
+extern "C" int ctl_topp_mask_apply(const float* s, const void* z, int z_dtype, int64_t N, int64_t C, int64_t HW,
+                                   int mode, int64_t k, int soft, const float* rand, uint64_t seed, uint64_t offset,
+                                   int64_t first_sample, float* mask_out, float* thr_out, void* z_out, int out_dtype,
+                                   void* stream) {
+  // stand-alone: z may have been written by the kernel just before us in the stream -> ordinary launch
+  return topp_impl(false, s, z, z_dtype, N, C, HW, mode, k, soft, rand, seed, offset, first_sample, mask_out, thr_out,
+                   z_out, out_dtype, stream);
 }
 
 extern "C" int ctl_saliency_mask_apply(const void* g, int g_dtype, const void* z, int z_dtype, int64_t N, int64_t C,
@@ -450,9 +508,15 @@ extern "C" int ctl_saliency_mask_apply(const void* g, int g_dtype, const void* z
   CTL_REQUIRE(k >= 0, CTL_ERR_INVALID, "k must be >= 0 (got %lld)", (long long)k);
   CTL_REQUIRE(k < n, CTL_ERR_INDEX, "index %lld is out of bounds for dimension 1 with size %lld", (long long)k,
               (long long)n);
+  CTL_REQUIRE(n <= 51200, CTL_ERR_UNSUPPORTED,
+              "one sample's saliency row is kept in shared memory: n=%lld > 51200", (long long)n);
+  CTL_REQUIRE(s_scratch && z && mask_out && z_out, CTL_ERR_INVALID, "ctl_saliency_mask_apply: NULL pointer");
   if (int rc = ctl_saliency_reduce(g, g_dtype, N, C, HW, mode, s_scratch, stream)) return rc;
-  return ctl_topp_mask_apply(s_scratch, z, z_dtype, N, C, HW, mode, k, soft, rand, seed, offset, first_sample,
-                             mask_out, thr_out, z_out, out_dtype, stream);
+  // K2 is launched with programmatic stream serialization: its CTAs become resident while K1 drains, request
+  // their first rows of z (K1 never writes z; everything older than K1 has completed because K1 itself was an
+  // ordinary launch) and only then wait for K1's s.
+  return topp_impl(true, s_scratch, z, z_dtype, N, C, HW, mode, k, soft, rand, seed, offset, first_sample, mask_out,
+                   thr_out, z_out, out_dtype, stream);
 }
 
 extern "C" int ctl_channel_dropout(const void* z, int z_dtype, int64_t N, int64_t C, int64_t HW, float p, float scale,

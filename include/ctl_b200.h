@@ -63,7 +63,7 @@ int ctl_saliency_reduce(const void* g, int g_dtype, int64_t N, int64_t C, int64_
  * (first_sample+i)*n + j) (native, shard-invariant mode; first_sample = global index of row 0).
  * mask_out: fp32 [N,n] (viewed by the caller as [N,C,1,1] or [N,1,H,W]); thr_out: fp32 [N] or NULL.
  * z: [N,C,HW] (z_dtype) -> z_out same shape (out_dtype; the reference always produces fp32).
- * Spatial mode keeps one sample's mask in shared memory: HW <= 51200, else CTL_ERR_UNSUPPORTED.
+ * One sample's saliency row is staged in shared memory: n <= 51200, else CTL_ERR_UNSUPPORTED.
  */
 int ctl_topp_mask_apply(const float* s, const void* z, int z_dtype, int64_t N, int64_t C, int64_t HW,
                         int mode, int64_t k, int soft, const float* rand, uint64_t seed,
