@@ -48,31 +48,158 @@ __device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepc
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 
 // ------------------------------------------------------------------------------------------------
-// K1, channel mode: one L-lane group per (n,c) row, fp64 accumulation, shuffle reduction.
+// Per-sample selection: k-th largest of s[0..n) by radix select on order-preserving keys, then the
+// mask row.  Called by ONE CTA per sample (the last K1 CTA to arrive, or the stand-alone select kernel).
 // ------------------------------------------------------------------------------------------------
-template <typename T, int VEC, int L>
-__global__ void __launch_bounds__(kThreads)
-saliency_channel_kernel(const T* __restrict__ g, float* __restrict__ s, int64_t rows, int HW, int nv) {
+constexpr int kSelKeys = 2048;     // rows up to this long are staged in shared memory (8 KB)
+
+__device__ __forceinline__ uint32_t order_key(float f) {
+  // larger float -> larger key; NaN sorts first in torch.sort(descending=True) -> largest key
+  if (f != f) return 0xffffffffu;
+  const uint32_t u = __float_as_uint(f);
+  return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+__device__ __forceinline__ float key_to_float(uint32_t k) {
+  if (k == 0xffffffffu) return __uint_as_float(0x7fc00000u);
+  return __uint_as_float((k & 0x80000000u) ? (k & 0x7fffffffu) : ~k);
+}
+
+struct SelectSmem {
+  uint32_t keys[kSelKeys];
+  uint32_t hist[256];
+  uint32_t sel[2];
+  int flag;
+};
+
+__device__ __forceinline__ float mask_value(float sv, float thr, int soft, const float* __restrict__ rand,
+                                            PhiloxKey key, uint64_t gidx, int64_t lidx) {
+  if (!(sv > thr)) return 1.0f;
+  if (!soft) return 0.0f;
+  const float u = rand ? rand[lidx] : philox_uniform(key, gidx);
+  return 0.5f * u;
+}
+
+// srow is read through L2 (__ldcg): it may have been written by other CTAs of the same launch.
+__device__ void select_and_build_mask(const float* srow, int n, int k, int soft, const float* __restrict__ rand,
+                                      PhiloxKey key, uint64_t gbase, int64_t lbase, float* __restrict__ mask_row,
+                                      float* thr_ptr, SelectSmem& sm) {
+  const bool staged = n <= kSelKeys;
+  if (staged)
+    for (int j = threadIdx.x; j < n; j += blockDim.x) sm.keys[j] = order_key(__ldcg(srow + j));
+  uint32_t prefix = 0, known = 0, krem = (uint32_t)k;
+#pragma unroll 1
+  for (int shift = 24; shift >= 0; shift -= 8) {
+    for (int i = threadIdx.x; i < 256; i += blockDim.x) sm.hist[i] = 0;
+    __syncthreads();
+    for (int j = threadIdx.x; j < n; j += blockDim.x) {
+      const uint32_t kk = staged ? sm.keys[j] : order_key(__ldcg(srow + j));
+      if ((kk & known) == prefix) atomicAdd(&sm.hist[(kk >> shift) & 255u], 1u);
+    }
+    __syncthreads();
+    if (threadIdx.x < 32) {
+      // lane l owns bins [255-8l-7, 255-8l], walked from the top
+      const int lane = threadIdx.x;
+      uint32_t local = 0;
+#pragma unroll
+      for (int b = 0; b < 8; ++b) local += sm.hist[255 - 8 * lane - b];
+      uint32_t incl = local;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const uint32_t t = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += t;
+      }
+      const uint32_t before = incl - local;          // elements in strictly higher bins (other lanes)
+      if (krem >= before && krem < incl) {           // exactly one lane
+        uint32_t cum = before;
+        for (int b = 0; b < 8; ++b) {
+          const uint32_t h = sm.hist[255 - 8 * lane - b];
+          if (krem < cum + h) {
+            sm.sel[0] = (uint32_t)(255 - 8 * lane - b);
+            sm.sel[1] = krem - cum;
+            break;
+          }
+          cum += h;
+        }
+      }
+    }
+    __syncthreads();
+    prefix |= sm.sel[0] << shift;
+    known |= 255u << shift;
+    krem = sm.sel[1];
+  }
+  const float thr = key_to_float(prefix);
+  if (thr_ptr && threadIdx.x == 0) *thr_ptr = thr;
+  for (int j = threadIdx.x; j < n; j += blockDim.x) {
+    const float sv = staged ? key_to_float(sm.keys[j]) : __ldcg(srow + j);
+    mask_row[j] = mask_value(sv, thr, soft, rand, key, gbase + j, lbase + j);
+  }
+}
+
+struct SelectArgs {          // everything the fused tail of K1 needs; counters == nullptr -> plain K1
+  int* counters;             // [N] arrival counters, zero on entry, zero again on exit
+  float* mask_out;           // [N,n]
+  float* thr_out;            // [N] or nullptr
+  const float* rand;         // [N,n] or nullptr
+  PhiloxKey key;
+  int64_t first_sample;
+  int k;
+  int soft;
+};
+
+// All threads of the CTA call this after their s values are written.  Exactly one CTA per sample
+// (the last to arrive) runs the selection.
+__device__ __forceinline__ void arrive_and_maybe_select(const SelectArgs& sa, const float* s, int64_t sample, int n,
+                                                        int ctas_per_sample, SelectSmem& sm) {
+  __syncthreads();                                   // writers fenced their s stores before this
+  if (threadIdx.x == 0) {
+    const int old = atomicAdd(&sa.counters[sample], 1);
+    const int last = (old == ctas_per_sample - 1);
+    if (last) sa.counters[sample] = 0;               // self-cleaning for the next call
+    sm.flag = last;
+  }
+  __syncthreads();
+  if (sm.flag) {
+    __threadfence();
+    select_and_build_mask(s + sample * n, n, sa.k, sa.soft, sa.rand, sa.key,
+                          (uint64_t)(sa.first_sample + sample) * (uint64_t)n, sample * (int64_t)n,
+                          sa.mask_out + sample * (int64_t)n, sa.thr_out ? sa.thr_out + sample : nullptr, sm);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// K1, channel mode: grid (row chunks, N); one L-lane group per (n,c) row, fp64 accumulation,
+// shuffle reduction; optional fused per-sample selection in the last CTA of each sample.
+// ------------------------------------------------------------------------------------------------
+template <typename T, int VEC, int L, bool SELECT>
+__global__ void __launch_bounds__(kThreads, 4)
+saliency_channel_kernel(const T* __restrict__ g, float* __restrict__ s, int C, int HW, int nv, SelectArgs sa) {
   pdl_launch_dependents();
+  __shared__ SelectSmem sm;
   const int lane = threadIdx.x & (L - 1);
   const unsigned gmask = group_mask<L>();
-  const int64_t row = (int64_t)blockIdx.x * (kThreads / L) + threadIdx.x / L;
-  if (row >= rows) return;                     // whole group leaves together
-  const T* __restrict__ p = g + row * HW;
-  double acc0 = 0.0, acc1 = 0.0;
-  for (int base = 0; base < nv; base += kU * L) {
-    float a[kU][VEC];
-    load_batch<T, VEC, L>(p, base, lane, nv, a);
+  const int64_t sample = blockIdx.y;
+  const int c = blockIdx.x * (kThreads / L) + threadIdx.x / L;
+  if (c < C) {                                         // group-uniform
+    const T* __restrict__ p = g + (sample * C + c) * (int64_t)HW;
+    double acc0 = 0.0, acc1 = 0.0;
+    for (int base = 0; base < nv; base += kU * L) {
+      float a[kU][VEC];
+      load_batch<T, VEC, L>(p, base, lane, nv, a);
 #pragma unroll
-    for (int j = 0; j < kU; j += 2) {
+      for (int j = 0; j < kU; j += 2) {
 #pragma unroll
-      for (int i = 0; i < VEC; ++i) { acc0 += (double)a[j][i]; acc1 += (double)a[j + 1][i]; }
+        for (int i = 0; i < VEC; ++i) { acc0 += (double)a[j][i]; acc1 += (double)a[j + 1][i]; }
+      }
+    }
+    double acc = acc0 + acc1;
+#pragma unroll
+    for (int o = L / 2; o > 0; o >>= 1) acc += __shfl_xor_sync(gmask, acc, o);
+    if (lane == 0) {
+      s[sample * C + c] = (float)(acc / (double)HW);
+      if (SELECT) __threadfence();
     }
   }
-  double acc = acc0 + acc1;
-#pragma unroll
-  for (int o = L / 2; o > 0; o >>= 1) acc += __shfl_xor_sync(gmask, acc, o);
-  if (lane == 0) s[row] = (float)(acc / (double)HW);
+  if (SELECT) arrive_and_maybe_select(sa, s, sample, C, gridDim.x, sm);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -80,11 +207,12 @@ saliency_channel_kernel(const T* __restrict__ g, float* __restrict__ s, int64_t 
 // contiguous bytes of one channel row; each thread keeps kU channel rows in flight; the Y partial
 // sums meet in shared memory (fp64).
 // ------------------------------------------------------------------------------------------------
-template <typename T, int VEC, int X, int Y>
-__global__ void __launch_bounds__(X * Y)
-saliency_spatial_kernel(const T* __restrict__ g, float* __restrict__ s, int C, int HW, int nv) {
+template <typename T, int VEC, int X, int Y, bool SELECT>
+__global__ void __launch_bounds__(X * Y, 3)
+saliency_spatial_kernel(const T* __restrict__ g, float* __restrict__ s, int C, int HW, int nv, SelectArgs sa) {
   pdl_launch_dependents();
   __shared__ double red[Y][X * VEC + 1];
+  __shared__ SelectSmem sm;
   const int x = threadIdx.x % X, y = threadIdx.x / X;
   const int64_t n = blockIdx.y;
   const int v = blockIdx.x * X + x;
@@ -122,140 +250,75 @@ saliency_spatial_kernel(const T* __restrict__ g, float* __restrict__ s, int C, i
 #pragma unroll
       for (int j = 0; j < Y; ++j) t += red[j][e];
       s[n * HW + hw] = (float)(t / (double)C);
+      if (SELECT) __threadfence();
     }
   }
+  if (SELECT) arrive_and_maybe_select(sa, s, n, HW, gridDim.x, sm);
 }
 
-// ------------------------------------------------------------------------------------------------
-// K2: per-sample k-th largest (radix select on order-preserving keys), mask build, apply.
-// ------------------------------------------------------------------------------------------------
-__device__ __forceinline__ uint32_t order_key(float f) {
-  // larger float -> larger key; NaN sorts first in torch.sort(descending=True) -> largest key
-  if (f != f) return 0xffffffffu;
-  const uint32_t u = __float_as_uint(f);
-  return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
-}
-__device__ __forceinline__ float key_to_float(uint32_t k) {
-  if (k == 0xffffffffu) return __uint_as_float(0x7fc00000u);
-  return __uint_as_float((k & 0x80000000u) ? (k & 0x7fffffffu) : ~k);
-}
-
-// All threads of the CTA call this; keys[0..n) live in shared memory.  Returns the key of the
-// k-th (0-based) largest element.
-__device__ uint32_t block_kth_largest_key(const uint32_t* __restrict__ keys, int n, int k,
-                                          uint32_t* hist /*[256]*/, uint32_t* sel /*[2]*/) {
-  uint32_t prefix = 0, known = 0, krem = (uint32_t)k;
-#pragma unroll 1
-  for (int shift = 24; shift >= 0; shift -= 8) {
-    for (int i = threadIdx.x; i < 256; i += blockDim.x) hist[i] = 0;
-    __syncthreads();
-    for (int j = threadIdx.x; j < n; j += blockDim.x) {
-      const uint32_t key = keys[j];
-      if ((key & known) == prefix) atomicAdd(&hist[(key >> shift) & 255u], 1u);
-    }
-    __syncthreads();
-    if (threadIdx.x < 32) {
-      // lane l owns bins [255-8l-7, 255-8l], walked from the top
-      const int lane = threadIdx.x;
-      uint32_t local = 0;
-#pragma unroll
-      for (int b = 0; b < 8; ++b) local += hist[255 - 8 * lane - b];
-      uint32_t incl = local;
-#pragma unroll
-      for (int o = 1; o < 32; o <<= 1) {
-        const uint32_t t = __shfl_up_sync(0xffffffffu, incl, o);
-        if (lane >= o) incl += t;
-      }
-      const uint32_t before = incl - local;          // elements in strictly higher bins (other lanes)
-      if (krem >= before && krem < incl) {           // exactly one lane
-        uint32_t cum = before;
-        for (int b = 0; b < 8; ++b) {
-          const uint32_t h = hist[255 - 8 * lane - b];
-          if (krem < cum + h) {
-            sel[0] = (uint32_t)(255 - 8 * lane - b);
-            sel[1] = krem - cum;
-            break;
-          }
-          cum += h;
-        }
-      }
-    }
-    __syncthreads();
-    prefix |= sel[0] << shift;
-    known |= 255u << shift;
-    krem = sel[1];
-  }
-  return prefix;
-}
-
-__device__ __forceinline__ float mask_value(float sv, float thr, int soft, const float* __restrict__ rand,
-                                            PhiloxKey key, uint64_t gidx, int64_t lidx) {
-  if (!(sv > thr)) return 1.0f;
-  if (!soft) return 0.0f;
-  const float u = rand ? rand[lidx] : philox_uniform(key, gidx);
-  return 0.5f * u;
-}
-
-template <int VEC, int MODE>
-__device__ __forceinline__ void scale_vec(float (&a)[VEC], float mrow, const float* __restrict__ mask_sm, int v) {
-#pragma unroll
-  for (int i = 0; i < VEC; ++i) a[i] *= (MODE == CTL_MODE_CHANNEL) ? mrow : mask_sm[v * VEC + i];
-}
-
-// CTA = rows [c0, c0+rows_per_cta) of one sample; group gi (L lanes) owns rows c0+gi, c0+gi+G, ...
-// The first row's data is requested BEFORE the dependency wait / select: z does not depend on K1.
-template <typename ZT, typename OT, int VEC, int L, int MODE, bool PDL>
+// stand-alone selection for ctl_topp_mask_apply (s supplied by the caller): one CTA per sample
 __global__ void __launch_bounds__(kThreads)
-topp_mask_apply_kernel(const float* __restrict__ s, const ZT* __restrict__ z, OT* __restrict__ z_out,
-                       float* __restrict__ mask_out, float* __restrict__ thr_out,
-                       const float* __restrict__ rand, PhiloxKey key, int C, int HW, int nv, int k, int soft,
-                       int rows_per_cta, int64_t first_sample) {
-  extern __shared__ float mask_sm[];          // n floats: first the keys of s, then (in place) the mask
-  __shared__ uint32_t hist[256];
-  __shared__ uint32_t sel[2];
-  constexpr int G = kThreads / L;
-  const int64_t sample = blockIdx.y;
-  const int n = (MODE == CTL_MODE_CHANNEL) ? C : HW;
-  const int c0 = blockIdx.x * rows_per_cta;
-  const int crows = min(rows_per_cta, C - c0);
-  const int lane = threadIdx.x & (L - 1);
-  const int gi = threadIdx.x / L;
-  const int64_t base = (sample * C + c0) * (int64_t)HW;
+select_mask_kernel(const float* __restrict__ s, int n, SelectArgs sa) {
+  pdl_launch_dependents();
+  __shared__ SelectSmem sm;
+  const int64_t sample = blockIdx.x;
+  select_and_build_mask(s + sample * n, n, sa.k, sa.soft, sa.rand, sa.key,
+                        (uint64_t)(sa.first_sample + sample) * (uint64_t)n, sample * (int64_t)n,
+                        sa.mask_out + sample * (int64_t)n, sa.thr_out ? sa.thr_out + sample : nullptr, sm);
+}
 
-  float a[kU][VEC];
-  if (gi < crows) load_batch<ZT, VEC, L>(z + base + (int64_t)gi * HW, 0, lane, nv, a);
-
-  if (PDL) pdl_wait();                        // s is produced by the preceding K1 launch
-
-  const float* __restrict__ srow = s + sample * n;
-  uint32_t* keys = reinterpret_cast<uint32_t*>(mask_sm);
-  for (int j = threadIdx.x; j < n; j += kThreads) keys[j] = order_key(srow[j]);
-  const float thr = key_to_float(block_kth_largest_key(keys, n, k, hist, sel));   // syncs inside
-  if (thr_out && blockIdx.x == 0 && threadIdx.x == 0) thr_out[sample] = thr;
-
-  const uint64_t gbase = (uint64_t)(first_sample + sample) * (uint64_t)n;
-  for (int j = threadIdx.x; j < n; j += kThreads) {
-    // same thread reads keys[j] and overwrites it with the mask value: no hazard
-    const float m = mask_value(key_to_float(keys[j]), thr, soft, rand, key, gbase + j, sample * n + j);
-    mask_sm[j] = m;
-    const bool mine = (MODE == CTL_MODE_CHANNEL) ? (j >= c0 && j < c0 + crows) : (blockIdx.x == 0);
-    if (mine) mask_out[sample * n + j] = m;
-  }
-  __syncthreads();
-
-  for (int r = gi; r < crows; r += G) {
-    const ZT* __restrict__ zi = z + base + (int64_t)r * HW;
-    OT* __restrict__ zo = z_out + base + (int64_t)r * HW;
-    const float mrow = (MODE == CTL_MODE_CHANNEL) ? mask_sm[c0 + r] : 1.0f;
-    for (int vb = 0; vb < nv; vb += kU * L) {
-      if (r != gi || vb != 0) load_batch<ZT, VEC, L>(zi, vb, lane, nv, a);
+// coherent (ld.global, not ld.global.nc) vector read of mask values: under programmatic dependent launch
+// this kernel is already resident while K1 still writes the mask, so the read-only path must not be used
+template <int VEC>
+__device__ __forceinline__ void load_mask(const float* p, float (&m)[VEC]) {
+  if constexpr (VEC % 4 == 0) {
 #pragma unroll
-      for (int j = 0; j < kU; ++j) {
-        const int v = vb + j * L + lane;
-        if (v < nv) {
-          scale_vec<VEC, MODE>(a[j], mrow, mask_sm, v);
-          store_from_float<OT, VEC>(zo + (int64_t)v * VEC, a[j]);
+    for (int q = 0; q < VEC / 4; ++q) {
+      const float4 t = __ldcg(reinterpret_cast<const float4*>(p) + q);
+      m[4 * q] = t.x; m[4 * q + 1] = t.y; m[4 * q + 2] = t.z; m[4 * q + 3] = t.w;
+    }
+  } else {
+#pragma unroll
+    for (int i = 0; i < VEC; ++i) m[i] = __ldcg(p + i);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// K2: z~ = z * mask.  Pure streaming: one L-lane group per (n,c) row, kU 128-bit loads in flight per
+// lane.  The row's data is requested BEFORE the dependency wait -- z does not depend on K1, the mask does.
+// ------------------------------------------------------------------------------------------------
+template <typename ZT, typename OT, int VEC, int L, int MODE>
+__global__ void __launch_bounds__(kThreads, 4)
+mask_apply_kernel(const ZT* __restrict__ z, OT* __restrict__ z_out, const float* mask, int64_t rows, int C, int HW,
+                  int nv) {
+  const int lane = threadIdx.x & (L - 1);
+  const int64_t row = (int64_t)blockIdx.x * (kThreads / L) + threadIdx.x / L;
+  const bool active = row < rows;
+  const ZT* __restrict__ zi = z + row * HW;
+  OT* __restrict__ zo = z_out + row * HW;
+  float a[kU][VEC];
+  if (active) load_batch<ZT, VEC, L>(zi, 0, lane, nv, a);
+  pdl_wait();                                            // the mask comes from the preceding launch
+  if (!active) return;
+  const int64_t sample = row / C;
+  const float mrow = (MODE == CTL_MODE_CHANNEL) ? __ldcg(mask + row) : 1.0f;
+  const float* mvec = mask + sample * HW;
+  for (int vb = 0; vb < nv; vb += kU * L) {
+    if (vb != 0) load_batch<ZT, VEC, L>(zi, vb, lane, nv, a);
+#pragma unroll
+    for (int j = 0; j < kU; ++j) {
+      const int v = vb + j * L + lane;
+      if (v < nv) {
+        if (MODE == CTL_MODE_CHANNEL) {
+#pragma unroll
+          for (int i = 0; i < VEC; ++i) a[j][i] *= mrow;
+        } else {
+          float m[VEC];
+          load_mask<VEC>(mvec + v * VEC, m);
+#pragma unroll
+          for (int i = 0; i < VEC; ++i) a[j][i] *= m[i];
         }
+        store_from_float<OT, VEC>(zo + (int64_t)v * VEC, a[j]);
       }
     }
   }
@@ -309,96 +372,111 @@ __global__ void philox_uniform_kernel(PhiloxKey key, uint64_t first, int64_t cou
 inline int pick_lanes(int nv) { return nv >= 128 ? 32 : nv >= 64 ? 16 : nv >= 16 ? 8 : 4; }
 
 template <typename T, int VEC>
-int launch_saliency_channel(const T* g, float* s, int64_t rows, int HW, cudaStream_t st) {
+int launch_saliency_channel(const T* g, float* s, int64_t N, int C, int HW, const SelectArgs* sa, cudaStream_t st) {
   const int nv = HW / VEC;
   const int L = pick_lanes(nv);
-  const int64_t grid64 = ceil_div(rows, kThreads / L);
-  CTL_REQUIRE(grid64 <= 0x7fffffff, CTL_ERR_UNSUPPORTED, "too many rows for one launch");
-  const unsigned grid = (unsigned)grid64;
+  dim3 grid((unsigned)ceil_div(C, kThreads / L), (unsigned)N);
+  const SelectArgs none = {};
+#define CTL_K1C(LL)                                                                                    \
+  do {                                                                                                 \
+    if (sa) saliency_channel_kernel<T, VEC, LL, true><<<grid, kThreads, 0, st>>>(g, s, C, HW, nv, *sa); \
+    else saliency_channel_kernel<T, VEC, LL, false><<<grid, kThreads, 0, st>>>(g, s, C, HW, nv, none);  \
+  } while (0)
   switch (L) {
-    case 32: saliency_channel_kernel<T, VEC, 32><<<grid, kThreads, 0, st>>>(g, s, rows, HW, nv); break;
-    case 16: saliency_channel_kernel<T, VEC, 16><<<grid, kThreads, 0, st>>>(g, s, rows, HW, nv); break;
-    case 8: saliency_channel_kernel<T, VEC, 8><<<grid, kThreads, 0, st>>>(g, s, rows, HW, nv); break;
-    default: saliency_channel_kernel<T, VEC, 4><<<grid, kThreads, 0, st>>>(g, s, rows, HW, nv); break;
+    case 32: CTL_K1C(32); break;
+    case 16: CTL_K1C(16); break;
+    case 8: CTL_K1C(8); break;
+    default: CTL_K1C(4); break;
   }
+#undef CTL_K1C
   CTL_CUDA_OK(cudaGetLastError(), "saliency_channel launch");
   return CTL_OK;
 }
 
 template <typename T, int VEC>
-int launch_saliency_spatial(const T* g, float* s, int64_t N, int C, int HW, cudaStream_t st) {
+int launch_saliency_spatial(const T* g, float* s, int64_t N, int C, int HW, const SelectArgs* sa, cudaStream_t st) {
   const int nv = HW / VEC;
   constexpr int X = 32, Y = 8;
   dim3 grid((unsigned)ceil_div(nv, X), (unsigned)N);
-  saliency_spatial_kernel<T, VEC, X, Y><<<grid, X * Y, 0, st>>>(g, s, C, HW, nv);
+  const SelectArgs none = {};
+  if (sa) saliency_spatial_kernel<T, VEC, X, Y, true><<<grid, X * Y, 0, st>>>(g, s, C, HW, nv, *sa);
+  else saliency_spatial_kernel<T, VEC, X, Y, false><<<grid, X * Y, 0, st>>>(g, s, C, HW, nv, none);
   CTL_CUDA_OK(cudaGetLastError(), "saliency_spatial launch");
   return CTL_OK;
 }
 
-template <typename ZT, typename OT, int VEC, int L, int MODE, bool PDL>
-int launch_topp_kernel(dim3 grid, size_t smem, cudaStream_t st, const float* s, const ZT* z, OT* z_out,
-                       float* mask_out, float* thr_out, const float* rand, PhiloxKey key, int C, int HW, int nv, int k,
-                       int soft, int rows_per_cta, int64_t first_sample) {
-  auto kern = topp_mask_apply_kernel<ZT, OT, VEC, L, MODE, PDL>;
-  if (smem > 48 * 1024)
-    CTL_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem),
-                "topp smem attribute");
+int launch_saliency(const void* g, int g_dtype, int64_t N, int64_t C, int64_t HW, int mode, float* s,
+                    const SelectArgs* sa, cudaStream_t st) {
+  const bool f32 = g_dtype == CTL_F32;
+  const int vw = f32 ? 4 : 8;
+  const bool vec = (HW % vw == 0) && aligned16(g);
+  const int Ci = (int)C, HWi = (int)HW;
+  if (mode == CTL_MODE_CHANNEL) {
+    if (f32) return vec ? launch_saliency_channel<float, 4>((const float*)g, s, N, Ci, HWi, sa, st)
+                        : launch_saliency_channel<float, 1>((const float*)g, s, N, Ci, HWi, sa, st);
+    return vec ? launch_saliency_channel<__nv_bfloat16, 8>((const __nv_bfloat16*)g, s, N, Ci, HWi, sa, st)
+               : launch_saliency_channel<__nv_bfloat16, 1>((const __nv_bfloat16*)g, s, N, Ci, HWi, sa, st);
+  }
+  if (f32) return vec ? launch_saliency_spatial<float, 4>((const float*)g, s, N, Ci, HWi, sa, st)
+                      : launch_saliency_spatial<float, 1>((const float*)g, s, N, Ci, HWi, sa, st);
+  return vec ? launch_saliency_spatial<__nv_bfloat16, 8>((const __nv_bfloat16*)g, s, N, Ci, HWi, sa, st)
+             : launch_saliency_spatial<__nv_bfloat16, 1>((const __nv_bfloat16*)g, s, N, Ci, HWi, sa, st);
+}
+
+// K2 is always launched with programmatic stream serialization: its CTAs become resident while the
+// producer of the mask (K1 or the select kernel) drains, request their rows of z and only then wait.
+// Safe because that producer is an ordinary launch: everything older (including whatever wrote z) has
+// completed before it started, and it never writes z.
+template <typename ZT, typename OT, int VEC, int L, int MODE>
+int launch_apply_kernel(const ZT* z, OT* z_out, const float* mask, int64_t rows, int C, int HW, int nv,
+                        cudaStream_t st) {
+  const int64_t grid64 = ceil_div(rows, kThreads / L);
+  CTL_REQUIRE(grid64 <= 0x7fffffff, CTL_ERR_UNSUPPORTED, "too many rows for one launch");
   cudaLaunchConfig_t cfg = {};
-  cfg.gridDim = grid;
+  cfg.gridDim = dim3((unsigned)grid64);
   cfg.blockDim = dim3(kThreads);
-  cfg.dynamicSmemBytes = smem;
+  cfg.dynamicSmemBytes = 0;
   cfg.stream = st;
   cudaLaunchAttribute attr[1];
   attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
   attr[0].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
-  cfg.numAttrs = PDL ? 1 : 0;
-  CTL_CUDA_OK(cudaLaunchKernelEx(&cfg, kern, s, z, z_out, mask_out, thr_out, rand, key, C, HW, nv, k, soft,
-                                 rows_per_cta, first_sample),
-              "topp_mask_apply launch");
+  cfg.numAttrs = 1;
+  CTL_CUDA_OK(cudaLaunchKernelEx(&cfg, mask_apply_kernel<ZT, OT, VEC, L, MODE>, z, z_out, mask, rows, C, HW, nv),
+              "mask_apply launch");
   return CTL_OK;
 }
 
-template <typename ZT, typename OT, int VEC, int MODE, bool PDL>
-int launch_topp(const float* s, const ZT* z, OT* z_out, float* mask_out, float* thr_out, const float* rand,
-                PhiloxKey key, int64_t N, int C, int HW, int k, int soft, int64_t first_sample, cudaStream_t st) {
+template <typename ZT, typename OT, int VEC>
+int launch_apply(int mode, const ZT* z, OT* z_out, const float* mask, int64_t N, int C, int HW, cudaStream_t st) {
   const int nv = HW / VEC;
   const int L = pick_lanes(nv);
-  const int G = kThreads / L;
-  // one row per group per CTA keeps every lane busy and the per-CTA select cheap relative to its stream;
-  // take more rows per group only when the rows are short (< 4 KB) and the grid stays >= 4 waves
-  int rows_per_cta = G;
-  while ((int64_t)rows_per_cta * HW * (int64_t)sizeof(ZT) < 16 * 1024 && rows_per_cta < C &&
-         N * ceil_div(C, 2 * rows_per_cta) >= 8 * (int64_t)sm_count())
-    rows_per_cta *= 2;
-  rows_per_cta = std::min(rows_per_cta, C);
-  const int chunks = (int)ceil_div(C, rows_per_cta);
-  const int n = MODE == CTL_MODE_CHANNEL ? C : HW;
-  const size_t smem = sizeof(float) * (size_t)n;
-  dim3 grid((unsigned)chunks, (unsigned)N);
-#define CTL_LAUNCH_TOPP(LL)                                                                                      \
-  return launch_topp_kernel<ZT, OT, VEC, LL, MODE, PDL>(grid, smem, st, s, z, z_out, mask_out, thr_out, rand, key, C, \
-                                                        HW, nv, k, soft, rows_per_cta, first_sample)
+  const int64_t rows = N * C;
+#define CTL_K2(LL)                                                                                              \
+  return mode == CTL_MODE_CHANNEL                                                                               \
+             ? launch_apply_kernel<ZT, OT, VEC, LL, CTL_MODE_CHANNEL>(z, z_out, mask, rows, C, HW, nv, st)       \
+             : launch_apply_kernel<ZT, OT, VEC, LL, CTL_MODE_SPATIAL>(z, z_out, mask, rows, C, HW, nv, st)
   switch (L) {
-    case 32: CTL_LAUNCH_TOPP(32);
-    case 16: CTL_LAUNCH_TOPP(16);
-    case 8: CTL_LAUNCH_TOPP(8);
-    default: CTL_LAUNCH_TOPP(4);
+    case 32: CTL_K2(32);
+    case 16: CTL_K2(16);
+    case 8: CTL_K2(8);
+    default: CTL_K2(4);
   }
-#undef CTL_LAUNCH_TOPP
+#undef CTL_K2
 }
 
-template <typename ZT, typename OT, int VEC>
-int launch_topp_mode(int mode, bool pdl, const float* s, const ZT* z, OT* z_out, float* mask_out, float* thr_out,
-                     const float* rand, PhiloxKey key, int64_t N, int C, int HW, int k, int soft,
-                     int64_t first_sample, cudaStream_t st) {
-#define CTL_ARGS s, z, z_out, mask_out, thr_out, rand, key, N, C, HW, k, soft, first_sample, st
-  if (mode == CTL_MODE_CHANNEL)
-    return pdl ? launch_topp<ZT, OT, VEC, CTL_MODE_CHANNEL, true>(CTL_ARGS)
-               : launch_topp<ZT, OT, VEC, CTL_MODE_CHANNEL, false>(CTL_ARGS);
-  return pdl ? launch_topp<ZT, OT, VEC, CTL_MODE_SPATIAL, true>(CTL_ARGS)
-             : launch_topp<ZT, OT, VEC, CTL_MODE_SPATIAL, false>(CTL_ARGS);
-#undef CTL_ARGS
+int launch_apply_any(int mode, const void* z, int z_dtype, void* z_out, int out_dtype, const float* mask, int64_t N,
+                     int64_t C, int64_t HW, cudaStream_t st) {
+  const bool zf = z_dtype == CTL_F32, of = out_dtype == CTL_F32;
+  const int vw = zf ? 4 : 8;
+  const bool vec = (HW % vw == 0) && aligned16(z) && aligned16(z_out) && aligned16(mask);
+  const int Ci = (int)C, HWi = (int)HW;
+#define CTL_APPLY(ZT, OT, V) return launch_apply<ZT, OT, V>(mode, (const ZT*)z, (OT*)z_out, mask, N, Ci, HWi, st)
+  if (zf && of) { if (vec) CTL_APPLY(float, float, 4); else CTL_APPLY(float, float, 1); }
+  if (zf && !of) { if (vec) CTL_APPLY(float, __nv_bfloat16, 4); else CTL_APPLY(float, __nv_bfloat16, 1); }
+  if (!zf && of) { if (vec) CTL_APPLY(__nv_bfloat16, float, 8); else CTL_APPLY(__nv_bfloat16, float, 1); }
+  if (vec) CTL_APPLY(__nv_bfloat16, __nv_bfloat16, 8); else CTL_APPLY(__nv_bfloat16, __nv_bfloat16, 1);
+#undef CTL_APPLY
 }
 
 template <typename ZT, typename OT, int VEC>
@@ -430,10 +508,20 @@ int check_shape(int64_t N, int64_t C, int64_t HW) {
   return CTL_OK;
 }
 
+int check_select(int64_t n, int64_t k, int64_t first_sample) {
+  CTL_REQUIRE(k >= 0, CTL_ERR_INVALID, "k must be >= 0 (got %lld)", (long long)k);
+  CTL_REQUIRE(k < n, CTL_ERR_INDEX, "index %lld is out of bounds for dimension 1 with size %lld", (long long)k,
+              (long long)n);
+  CTL_REQUIRE(first_sample >= 0, CTL_ERR_INVALID, "first_sample must be >= 0");
+  return CTL_OK;
+}
+
 }  // namespace
 }  // namespace ctl
 
 using namespace ctl;
+
+extern "C" size_t ctl_masking_workspace_bytes(int64_t N) { return N > 0 ? (size_t)N * sizeof(int) : 0; }
 
 extern "C" int ctl_saliency_reduce(const void* g, int g_dtype, int64_t N, int64_t C, int64_t HW, int mode,
                                    float* s_out, void* stream) {
@@ -442,81 +530,45 @@ extern "C" int ctl_saliency_reduce(const void* g, int g_dtype, int64_t N, int64_
   CTL_REQUIRE(mode == CTL_MODE_CHANNEL || mode == CTL_MODE_SPATIAL, CTL_ERR_INVALID, "unknown mode %d", mode);
   if (int rc = check_shape(N, C, HW)) return rc;
   if (sm_count() < 0) return CTL_ERR_CUDA;
-  cudaStream_t st = (cudaStream_t)stream;
-  const bool f32 = g_dtype == CTL_F32;
-  const int vw = f32 ? 4 : 8;
-  const bool vec = (HW % vw == 0) && aligned16(g);
-  if (mode == CTL_MODE_CHANNEL) {
-    if (f32) return vec ? launch_saliency_channel<float, 4>((const float*)g, s_out, N * C, (int)HW, st)
-                        : launch_saliency_channel<float, 1>((const float*)g, s_out, N * C, (int)HW, st);
-    return vec ? launch_saliency_channel<__nv_bfloat16, 8>((const __nv_bfloat16*)g, s_out, N * C, (int)HW, st)
-               : launch_saliency_channel<__nv_bfloat16, 1>((const __nv_bfloat16*)g, s_out, N * C, (int)HW, st);
-  }
-  if (f32) return vec ? launch_saliency_spatial<float, 4>((const float*)g, s_out, N, (int)C, (int)HW, st)
-                      : launch_saliency_spatial<float, 1>((const float*)g, s_out, N, (int)C, (int)HW, st);
-  return vec ? launch_saliency_spatial<__nv_bfloat16, 8>((const __nv_bfloat16*)g, s_out, N, (int)C, (int)HW, st)
-             : launch_saliency_spatial<__nv_bfloat16, 1>((const __nv_bfloat16*)g, s_out, N, (int)C, (int)HW, st);
-}
-
-static int topp_impl(bool pdl, const float* s, const void* z, int z_dtype, int64_t N, int64_t C, int64_t HW,
-                     int mode, int64_t k, int soft, const float* rand, uint64_t seed, uint64_t offset,
-                     int64_t first_sample, float* mask_out, float* thr_out, void* z_out, int out_dtype,
-                     void* stream) {
-  CTL_REQUIRE(s && z && mask_out && z_out, CTL_ERR_INVALID, "ctl_topp_mask_apply: NULL pointer");
-  CTL_REQUIRE(valid_dtype(z_dtype) && valid_dtype(out_dtype), CTL_ERR_INVALID, "ctl_topp_mask_apply: unknown dtype");
-  CTL_REQUIRE(mode == CTL_MODE_CHANNEL || mode == CTL_MODE_SPATIAL, CTL_ERR_INVALID, "unknown mode %d", mode);
-  if (int rc = check_shape(N, C, HW)) return rc;
-  const int64_t n = mode == CTL_MODE_CHANNEL ? C : HW;
-  CTL_REQUIRE(k >= 0, CTL_ERR_INVALID, "k must be >= 0 (got %lld)", (long long)k);
-  CTL_REQUIRE(k < n, CTL_ERR_INDEX, "index %lld is out of bounds for dimension 1 with size %lld", (long long)k,
-              (long long)n);
-  CTL_REQUIRE(first_sample >= 0, CTL_ERR_INVALID, "first_sample must be >= 0");
-  CTL_REQUIRE(n <= 51200, CTL_ERR_UNSUPPORTED,
-              "one sample's saliency row is kept in shared memory: n=%lld > 51200", (long long)n);
-  if (sm_count() < 0) return CTL_ERR_CUDA;
-  cudaStream_t st = (cudaStream_t)stream;
-  const PhiloxKey key{seed, offset};
-  const bool zf = z_dtype == CTL_F32, of = out_dtype == CTL_F32;
-  const int vw = zf ? 4 : 8;
-  const bool vec = (HW % vw == 0) && aligned16(z) && aligned16(z_out);
-  const int Ci = (int)C, HWi = (int)HW, ki = (int)k;
-#define CTL_TOPP(ZT, OT, V) \
-  return launch_topp_mode<ZT, OT, V>(mode, pdl, s, (const ZT*)z, (OT*)z_out, mask_out, thr_out, rand, key, N, Ci, HWi, \
-                                     ki, soft != 0, first_sample, st)
-  if (zf && of) { if (vec) CTL_TOPP(float, float, 4); else CTL_TOPP(float, float, 1); }
-  if (zf && !of) { if (vec) CTL_TOPP(float, __nv_bfloat16, 4); else CTL_TOPP(float, __nv_bfloat16, 1); }
-  if (!zf && of) { if (vec) CTL_TOPP(__nv_bfloat16, float, 8); else CTL_TOPP(__nv_bfloat16, float, 1); }
-  if (vec) CTL_TOPP(__nv_bfloat16, __nv_bfloat16, 8); else CTL_TOPP(__nv_bfloat16, __nv_bfloat16, 1);
-#undef CTL_TOPP
+  return launch_saliency(g, g_dtype, N, C, HW, mode, s_out, nullptr, (cudaStream_t)stream);
 }
 
 extern "C" int ctl_topp_mask_apply(const float* s, const void* z, int z_dtype, int64_t N, int64_t C, int64_t HW,
                                    int mode, int64_t k, int soft, const float* rand, uint64_t seed, uint64_t offset,
                                    int64_t first_sample, float* mask_out, float* thr_out, void* z_out, int out_dtype,
                                    void* stream) {
-  // stand-alone: z may have been written by the kernel just before us in the stream -> ordinary launch
-  return topp_impl(false, s, z, z_dtype, N, C, HW, mode, k, soft, rand, seed, offset, first_sample, mask_out, thr_out,
-                   z_out, out_dtype, stream);
+  CTL_REQUIRE(s && z && mask_out && z_out, CTL_ERR_INVALID, "ctl_topp_mask_apply: NULL pointer");
+  CTL_REQUIRE(valid_dtype(z_dtype) && valid_dtype(out_dtype), CTL_ERR_INVALID, "ctl_topp_mask_apply: unknown dtype");
+  CTL_REQUIRE(mode == CTL_MODE_CHANNEL || mode == CTL_MODE_SPATIAL, CTL_ERR_INVALID, "unknown mode %d", mode);
+  if (int rc = check_shape(N, C, HW)) return rc;
+  const int64_t n = mode == CTL_MODE_CHANNEL ? C : HW;
+  if (int rc = check_select(n, k, first_sample)) return rc;
+  if (sm_count() < 0) return CTL_ERR_CUDA;
+  cudaStream_t st = (cudaStream_t)stream;
+  SelectArgs sa = {nullptr, mask_out, thr_out, rand, PhiloxKey{seed, offset}, first_sample, (int)k, soft != 0};
+  select_mask_kernel<<<(unsigned)N, kThreads, 0, st>>>(s, (int)n, sa);
+  CTL_CUDA_OK(cudaGetLastError(), "select_mask launch");
+  return launch_apply_any(mode, z, z_dtype, z_out, out_dtype, mask_out, N, C, HW, st);
 }
 
 extern "C" int ctl_saliency_mask_apply(const void* g, int g_dtype, const void* z, int z_dtype, int64_t N, int64_t C,
                                        int64_t HW, int mode, int64_t k, int soft, const float* rand, uint64_t seed,
-                                       uint64_t offset, int64_t first_sample, float* s_scratch, float* mask_out,
-                                       float* thr_out, void* z_out, int out_dtype, void* stream) {
-  // validate k first so that an out-of-range k launches nothing (the reference raises before masking)
+                                       uint64_t offset, int64_t first_sample, float* s_scratch, void* workspace,
+                                       float* mask_out, float* thr_out, void* z_out, int out_dtype, void* stream) {
+  CTL_REQUIRE(g && z && s_scratch && workspace && mask_out && z_out, CTL_ERR_INVALID,
+              "ctl_saliency_mask_apply: NULL pointer");
+  CTL_REQUIRE(valid_dtype(g_dtype) && valid_dtype(z_dtype) && valid_dtype(out_dtype), CTL_ERR_INVALID,
+              "ctl_saliency_mask_apply: unknown dtype");
+  CTL_REQUIRE(mode == CTL_MODE_CHANNEL || mode == CTL_MODE_SPATIAL, CTL_ERR_INVALID, "unknown mode %d", mode);
+  if (int rc = check_shape(N, C, HW)) return rc;
   const int64_t n = mode == CTL_MODE_CHANNEL ? C : HW;
-  CTL_REQUIRE(k >= 0, CTL_ERR_INVALID, "k must be >= 0 (got %lld)", (long long)k);
-  CTL_REQUIRE(k < n, CTL_ERR_INDEX, "index %lld is out of bounds for dimension 1 with size %lld", (long long)k,
-              (long long)n);
-  CTL_REQUIRE(n <= 51200, CTL_ERR_UNSUPPORTED,
-              "one sample's saliency row is kept in shared memory: n=%lld > 51200", (long long)n);
-  CTL_REQUIRE(s_scratch && z && mask_out && z_out, CTL_ERR_INVALID, "ctl_saliency_mask_apply: NULL pointer");
-  if (int rc = ctl_saliency_reduce(g, g_dtype, N, C, HW, mode, s_scratch, stream)) return rc;
-  // K2 is launched with programmatic stream serialization: its CTAs become resident while K1 drains, request
-  // their first rows of z (K1 never writes z; everything older than K1 has completed because K1 itself was an
-  // ordinary launch) and only then wait for K1's s.
-  return topp_impl(true, s_scratch, z, z_dtype, N, C, HW, mode, k, soft, rand, seed, offset, first_sample, mask_out,
-                   thr_out, z_out, out_dtype, stream);
+  // validated before anything is launched: the reference raises IndexError before masking
+  if (int rc = check_select(n, k, first_sample)) return rc;
+  if (sm_count() < 0) return CTL_ERR_CUDA;
+  cudaStream_t st = (cudaStream_t)stream;
+  SelectArgs sa = {(int*)workspace, mask_out, thr_out, rand, PhiloxKey{seed, offset}, first_sample, (int)k, soft != 0};
+  if (int rc = launch_saliency(g, g_dtype, N, C, HW, mode, s_scratch, &sa, st)) return rc;
+  return launch_apply_any(mode, z, z_dtype, z_out, out_dtype, mask_out, N, C, HW, st);
 }
 
 extern "C" int ctl_channel_dropout(const void* z, int z_dtype, int64_t N, int64_t C, int64_t HW, float p, float scale,

@@ -63,19 +63,27 @@ int ctl_saliency_reduce(const void* g, int g_dtype, int64_t N, int64_t C, int64_
  * (first_sample+i)*n + j) (native, shard-invariant mode; first_sample = global index of row 0).
  * mask_out: fp32 [N,n] (viewed by the caller as [N,C,1,1] or [N,1,H,W]); thr_out: fp32 [N] or NULL.
  * z: [N,C,HW] (z_dtype) -> z_out same shape (out_dtype; the reference always produces fp32).
- * One sample's saliency row is staged in shared memory: n <= 51200, else CTL_ERR_UNSUPPORTED.
+ * Two launches: a one-CTA-per-sample select kernel, then the streaming apply kernel.
  */
 int ctl_topp_mask_apply(const float* s, const void* z, int z_dtype, int64_t N, int64_t C, int64_t HW,
                         int mode, int64_t k, int soft, const float* rand, uint64_t seed,
                         uint64_t offset, int64_t first_sample, float* mask_out, float* thr_out,
                         void* z_out, int out_dtype, void* stream);
 
-/* K1 + K2 back to back on `stream` (s_scratch: fp32 [N,n] caller scratch, holds s afterwards). */
+/* The whole tail of mask_latent_code_{channel,spatial}_wise in two launches: K1 whose last-arriving
+ * CTA per sample performs the selection and builds the mask row, then K2 (pure 128-bit streaming apply,
+ * launched with programmatic stream serialization so that its loads of z overlap K1's tail).
+ * s_scratch: fp32 [N,n] caller scratch, holds s afterwards.
+ * workspace: ctl_masking_workspace_bytes(N) bytes of per-sample arrival counters.  The caller zero-fills
+ * it ONCE after allocation; every call leaves it zero-filled again.  One workspace per concurrently
+ * used stream.
+ */
+size_t ctl_masking_workspace_bytes(int64_t N);
 int ctl_saliency_mask_apply(const void* g, int g_dtype, const void* z, int z_dtype, int64_t N,
                             int64_t C, int64_t HW, int mode, int64_t k, int soft, const float* rand,
                             uint64_t seed, uint64_t offset, int64_t first_sample, float* s_scratch,
-                            float* mask_out, float* thr_out, void* z_out, int out_dtype,
-                            void* stream);
+                            void* workspace, float* mask_out, float* thr_out, void* z_out,
+                            int out_dtype, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
  * Random channel dropout.  Replaces F.dropout2d(z, p) + the full-size `where(masked == z, 1, 0)`
