@@ -25,9 +25,8 @@ SIGNATURES = {
     "ctl_saliency_reduce": (_i, [_vp, _i, _i64, _i64, _i64, _i, _vp, _vp]),
     "ctl_topp_mask_apply": (_i, [_vp, _vp, _i, _i64, _i64, _i64, _i, _i64, _i, _vp, _u64, _u64, _i64,
                                  _vp, _vp, _vp, _i, _vp]),
-    "ctl_masking_workspace_bytes": (_c.c_size_t, [_i64]),
     "ctl_saliency_mask_apply": (_i, [_vp, _i, _vp, _i, _i64, _i64, _i64, _i, _i64, _i, _vp, _u64, _u64, _i64,
-                                     _vp, _vp, _vp, _vp, _vp, _i, _vp]),
+                                     _vp, _vp, _vp, _vp, _i, _vp]),
     "ctl_channel_dropout": (_i, [_vp, _i, _i64, _i64, _i64, _f, _f, _vp, _u64, _u64, _i64, _vp, _i, _vp, _vp, _vp]),
     "ctl_philox_uniform": (_i, [_u64, _u64, _u64, _i64, _vp, _vp]),
 }
@@ -35,7 +34,7 @@ SIGNATURES = {
 _lib = None
 # kernels launched through this binding since import (bench.py reports the count inside its timed
 # region as `gpu_launches`); name -> kernels per successful call
-KERNELS_PER_CALL = {"ctl_saliency_reduce": 1, "ctl_topp_mask_apply": 2, "ctl_saliency_mask_apply": 2,
+KERNELS_PER_CALL = {"ctl_saliency_reduce": 1, "ctl_topp_mask_apply": 2, "ctl_saliency_mask_apply": 3,
                     "ctl_channel_dropout": 1, "ctl_philox_uniform": 1}
 LAUNCHES = {"count": 0}
 

@@ -68,7 +68,6 @@ struct SelectSmem {
   uint32_t keys[kSelKeys];
   uint32_t hist[256];
   uint32_t sel[2];
-  int flag;
 };
 
 __device__ __forceinline__ float mask_value(float sv, float thr, int soft, const float* __restrict__ rand,
@@ -135,8 +134,7 @@ __device__ void select_and_build_mask(const float* srow, int n, int k, int soft,
   }
 }
 
-struct SelectArgs {          // everything the fused tail of K1 needs; counters == nullptr -> plain K1
-  int* counters;             // [N] arrival counters, zero on entry, zero again on exit
+struct SelectArgs {
   float* mask_out;           // [N,n]
   float* thr_out;            // [N] or nullptr
   const float* rand;         // [N,n] or nullptr
@@ -146,60 +144,33 @@ struct SelectArgs {          // everything the fused tail of K1 needs; counters 
   int soft;
 };
 
-// All threads of the CTA call this after their s values are written.  Exactly one CTA per sample
-// (the last to arrive) runs the selection.
-__device__ __forceinline__ void arrive_and_maybe_select(const SelectArgs& sa, const float* s, int64_t sample, int n,
-                                                        int ctas_per_sample, SelectSmem& sm) {
-  __syncthreads();                                   // writers fenced their s stores before this
-  if (threadIdx.x == 0) {
-    const int old = atomicAdd(&sa.counters[sample], 1);
-    const int last = (old == ctas_per_sample - 1);
-    if (last) sa.counters[sample] = 0;               // self-cleaning for the next call
-    sm.flag = last;
-  }
-  __syncthreads();
-  if (sm.flag) {
-    __threadfence();
-    select_and_build_mask(s + sample * n, n, sa.k, sa.soft, sa.rand, sa.key,
-                          (uint64_t)(sa.first_sample + sample) * (uint64_t)n, sample * (int64_t)n,
-                          sa.mask_out + sample * (int64_t)n, sa.thr_out ? sa.thr_out + sample : nullptr, sm);
-  }
-}
-
 // ------------------------------------------------------------------------------------------------
-// K1, channel mode: grid (row chunks, N); one L-lane group per (n,c) row, fp64 accumulation,
-// shuffle reduction; optional fused per-sample selection in the last CTA of each sample.
+// K1, channel mode: one L-lane group per (n,c) row, all of the row's 128-bit loads issued up front,
+// fp64 accumulation in four independent chains, shuffle reduction.  No barriers, no fences.
 // ------------------------------------------------------------------------------------------------
-template <typename T, int VEC, int L, bool SELECT>
+template <typename T, int VEC, int L>
 __global__ void __launch_bounds__(kThreads, 4)
-saliency_channel_kernel(const T* __restrict__ g, float* __restrict__ s, int C, int HW, int nv, SelectArgs sa) {
+saliency_channel_kernel(const T* __restrict__ g, float* __restrict__ s, int64_t rows, int HW, int nv) {
   pdl_launch_dependents();
-  __shared__ SelectSmem sm;
   const int lane = threadIdx.x & (L - 1);
   const unsigned gmask = group_mask<L>();
-  const int64_t sample = blockIdx.y;
-  const int c = blockIdx.x * (kThreads / L) + threadIdx.x / L;
-  if (c < C) {                                         // group-uniform
-    const T* __restrict__ p = g + (sample * C + c) * (int64_t)HW;
-    double acc0 = 0.0, acc1 = 0.0;
-    for (int base = 0; base < nv; base += kU * L) {
-      float a[kU][VEC];
-      load_batch<T, VEC, L>(p, base, lane, nv, a);
+  const int64_t row = (int64_t)blockIdx.x * (kThreads / L) + threadIdx.x / L;
+  if (row >= rows) return;                             // group-uniform
+  const T* __restrict__ p = g + row * HW;
+  double acc[4] = {0.0, 0.0, 0.0, 0.0};
+  for (int base = 0; base < nv; base += kU * L) {
+    float a[kU][VEC];
+    load_batch<T, VEC, L>(p, base, lane, nv, a);
 #pragma unroll
-      for (int j = 0; j < kU; j += 2) {
+    for (int j = 0; j < kU; ++j) {
 #pragma unroll
-        for (int i = 0; i < VEC; ++i) { acc0 += (double)a[j][i]; acc1 += (double)a[j + 1][i]; }
-      }
-    }
-    double acc = acc0 + acc1;
-#pragma unroll
-    for (int o = L / 2; o > 0; o >>= 1) acc += __shfl_xor_sync(gmask, acc, o);
-    if (lane == 0) {
-      s[sample * C + c] = (float)(acc / (double)HW);
-      if (SELECT) __threadfence();
+      for (int i = 0; i < VEC; ++i) acc[(j * VEC + i) & 3] += (double)a[j][i];
     }
   }
-  if (SELECT) arrive_and_maybe_select(sa, s, sample, C, gridDim.x, sm);
+  double t = (acc[0] + acc[1]) + (acc[2] + acc[3]);
+#pragma unroll
+  for (int o = L / 2; o > 0; o >>= 1) t += __shfl_xor_sync(gmask, t, o);
+  if (lane == 0) s[row] = (float)(t / (double)HW);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -207,12 +178,11 @@ saliency_channel_kernel(const T* __restrict__ g, float* __restrict__ s, int C, i
 // contiguous bytes of one channel row; each thread keeps kU channel rows in flight; the Y partial
 // sums meet in shared memory (fp64).
 // ------------------------------------------------------------------------------------------------
-template <typename T, int VEC, int X, int Y, bool SELECT>
+template <typename T, int VEC, int X, int Y>
 __global__ void __launch_bounds__(X * Y, 3)
-saliency_spatial_kernel(const T* __restrict__ g, float* __restrict__ s, int C, int HW, int nv, SelectArgs sa) {
+saliency_spatial_kernel(const T* __restrict__ g, float* __restrict__ s, int C, int HW, int nv) {
   pdl_launch_dependents();
   __shared__ double red[Y][X * VEC + 1];
-  __shared__ SelectSmem sm;
   const int x = threadIdx.x % X, y = threadIdx.x / X;
   const int64_t n = blockIdx.y;
   const int v = blockIdx.x * X + x;
@@ -250,16 +220,15 @@ saliency_spatial_kernel(const T* __restrict__ g, float* __restrict__ s, int C, i
 #pragma unroll
       for (int j = 0; j < Y; ++j) t += red[j][e];
       s[n * HW + hw] = (float)(t / (double)C);
-      if (SELECT) __threadfence();
     }
   }
-  if (SELECT) arrive_and_maybe_select(sa, s, n, HW, gridDim.x, sm);
 }
 
 // stand-alone selection for ctl_topp_mask_apply (s supplied by the caller): one CTA per sample
 __global__ void __launch_bounds__(kThreads)
-select_mask_kernel(const float* __restrict__ s, int n, SelectArgs sa) {
-  pdl_launch_dependents();
+select_mask_kernel(const float* s, int n, SelectArgs sa) {
+  pdl_launch_dependents();                 // lets K2 become resident and request its rows of z
+  pdl_wait();                              // s comes from the preceding launch (K1) when chained
   __shared__ SelectSmem sm;
   const int64_t sample = blockIdx.x;
   select_and_build_mask(s + sample * n, n, sa.k, sa.soft, sa.rand, sa.key,
@@ -372,61 +341,70 @@ __global__ void philox_uniform_kernel(PhiloxKey key, uint64_t first, int64_t cou
 inline int pick_lanes(int nv) { return nv >= 128 ? 32 : nv >= 64 ? 16 : nv >= 16 ? 8 : 4; }
 
 template <typename T, int VEC>
-int launch_saliency_channel(const T* g, float* s, int64_t N, int C, int HW, const SelectArgs* sa, cudaStream_t st) {
+int launch_saliency_channel(const T* g, float* s, int64_t N, int C, int HW, cudaStream_t st) {
   const int nv = HW / VEC;
   const int L = pick_lanes(nv);
-  dim3 grid((unsigned)ceil_div(C, kThreads / L), (unsigned)N);
-  const SelectArgs none = {};
-#define CTL_K1C(LL)                                                                                    \
-  do {                                                                                                 \
-    if (sa) saliency_channel_kernel<T, VEC, LL, true><<<grid, kThreads, 0, st>>>(g, s, C, HW, nv, *sa); \
-    else saliency_channel_kernel<T, VEC, LL, false><<<grid, kThreads, 0, st>>>(g, s, C, HW, nv, none);  \
-  } while (0)
+  const int64_t rows = N * C;
+  const int64_t grid64 = ceil_div(rows, kThreads / L);
+  CTL_REQUIRE(grid64 <= 0x7fffffff, CTL_ERR_UNSUPPORTED, "too many rows for one launch");
+  const unsigned grid = (unsigned)grid64;
   switch (L) {
-    case 32: CTL_K1C(32); break;
-    case 16: CTL_K1C(16); break;
-    case 8: CTL_K1C(8); break;
-    default: CTL_K1C(4); break;
+    case 32: saliency_channel_kernel<T, VEC, 32><<<grid, kThreads, 0, st>>>(g, s, rows, HW, nv); break;
+    case 16: saliency_channel_kernel<T, VEC, 16><<<grid, kThreads, 0, st>>>(g, s, rows, HW, nv); break;
+    case 8: saliency_channel_kernel<T, VEC, 8><<<grid, kThreads, 0, st>>>(g, s, rows, HW, nv); break;
+    default: saliency_channel_kernel<T, VEC, 4><<<grid, kThreads, 0, st>>>(g, s, rows, HW, nv); break;
   }
-#undef CTL_K1C
   CTL_CUDA_OK(cudaGetLastError(), "saliency_channel launch");
   return CTL_OK;
 }
 
 template <typename T, int VEC>
-int launch_saliency_spatial(const T* g, float* s, int64_t N, int C, int HW, const SelectArgs* sa, cudaStream_t st) {
+int launch_saliency_spatial(const T* g, float* s, int64_t N, int C, int HW, cudaStream_t st) {
   const int nv = HW / VEC;
   constexpr int X = 32, Y = 8;
   dim3 grid((unsigned)ceil_div(nv, X), (unsigned)N);
-  const SelectArgs none = {};
-  if (sa) saliency_spatial_kernel<T, VEC, X, Y, true><<<grid, X * Y, 0, st>>>(g, s, C, HW, nv, *sa);
-  else saliency_spatial_kernel<T, VEC, X, Y, false><<<grid, X * Y, 0, st>>>(g, s, C, HW, nv, none);
+  saliency_spatial_kernel<T, VEC, X, Y><<<grid, X * Y, 0, st>>>(g, s, C, HW, nv);
   CTL_CUDA_OK(cudaGetLastError(), "saliency_spatial launch");
   return CTL_OK;
 }
 
 int launch_saliency(const void* g, int g_dtype, int64_t N, int64_t C, int64_t HW, int mode, float* s,
-                    const SelectArgs* sa, cudaStream_t st) {
+                    cudaStream_t st) {
   const bool f32 = g_dtype == CTL_F32;
   const int vw = f32 ? 4 : 8;
   const bool vec = (HW % vw == 0) && aligned16(g);
   const int Ci = (int)C, HWi = (int)HW;
   if (mode == CTL_MODE_CHANNEL) {
-    if (f32) return vec ? launch_saliency_channel<float, 4>((const float*)g, s, N, Ci, HWi, sa, st)
-                        : launch_saliency_channel<float, 1>((const float*)g, s, N, Ci, HWi, sa, st);
-    return vec ? launch_saliency_channel<__nv_bfloat16, 8>((const __nv_bfloat16*)g, s, N, Ci, HWi, sa, st)
-               : launch_saliency_channel<__nv_bfloat16, 1>((const __nv_bfloat16*)g, s, N, Ci, HWi, sa, st);
+    if (f32) return vec ? launch_saliency_channel<float, 4>((const float*)g, s, N, Ci, HWi, st)
+                        : launch_saliency_channel<float, 1>((const float*)g, s, N, Ci, HWi, st);
+    return vec ? launch_saliency_channel<__nv_bfloat16, 8>((const __nv_bfloat16*)g, s, N, Ci, HWi, st)
+               : launch_saliency_channel<__nv_bfloat16, 1>((const __nv_bfloat16*)g, s, N, Ci, HWi, st);
   }
-  if (f32) return vec ? launch_saliency_spatial<float, 4>((const float*)g, s, N, Ci, HWi, sa, st)
-                      : launch_saliency_spatial<float, 1>((const float*)g, s, N, Ci, HWi, sa, st);
-  return vec ? launch_saliency_spatial<__nv_bfloat16, 8>((const __nv_bfloat16*)g, s, N, Ci, HWi, sa, st)
-             : launch_saliency_spatial<__nv_bfloat16, 1>((const __nv_bfloat16*)g, s, N, Ci, HWi, sa, st);
+  if (f32) return vec ? launch_saliency_spatial<float, 4>((const float*)g, s, N, Ci, HWi, st)
+                      : launch_saliency_spatial<float, 1>((const float*)g, s, N, Ci, HWi, st);
+  return vec ? launch_saliency_spatial<__nv_bfloat16, 8>((const __nv_bfloat16*)g, s, N, Ci, HWi, st)
+             : launch_saliency_spatial<__nv_bfloat16, 1>((const __nv_bfloat16*)g, s, N, Ci, HWi, st);
+}
+
+// one CTA per sample; chained == true: programmatic stream serialization after K1
+int launch_select(const float* s, int64_t N, int64_t n, const SelectArgs& sa, bool chained, cudaStream_t st) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((unsigned)N);
+  cfg.blockDim = dim3(kThreads);
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = chained ? 1 : 0;
+  CTL_CUDA_OK(cudaLaunchKernelEx(&cfg, select_mask_kernel, s, (int)n, sa), "select_mask launch");
+  return CTL_OK;
 }
 
 // K2 is always launched with programmatic stream serialization: its CTAs become resident while the
-// producer of the mask (K1 or the select kernel) drains, request their rows of z and only then wait.
-// Safe because that producer is an ordinary launch: everything older (including whatever wrote z) has
-// completed before it started, and it never writes z.
+// select kernel drains, request their rows of z and only then wait for the mask.  Safe because the head
+// of the chain (K1, or the select kernel when s is supplied) is an ORDINARY launch: everything older,
+// including whatever wrote z, completed before the chain started, and no kernel of the chain writes z.
 template <typename ZT, typename OT, int VEC, int L, int MODE>
 int launch_apply_kernel(const ZT* z, OT* z_out, const float* mask, int64_t rows, int C, int HW, int nv,
                         cudaStream_t st) {
@@ -521,8 +499,6 @@ int check_select(int64_t n, int64_t k, int64_t first_sample) {
 
 using namespace ctl;
 
-extern "C" size_t ctl_masking_workspace_bytes(int64_t N) { return N > 0 ? (size_t)N * sizeof(int) : 0; }
-
 extern "C" int ctl_saliency_reduce(const void* g, int g_dtype, int64_t N, int64_t C, int64_t HW, int mode,
                                    float* s_out, void* stream) {
   CTL_REQUIRE(g && s_out, CTL_ERR_INVALID, "ctl_saliency_reduce: NULL pointer");
@@ -530,7 +506,7 @@ extern "C" int ctl_saliency_reduce(const void* g, int g_dtype, int64_t N, int64_
   CTL_REQUIRE(mode == CTL_MODE_CHANNEL || mode == CTL_MODE_SPATIAL, CTL_ERR_INVALID, "unknown mode %d", mode);
   if (int rc = check_shape(N, C, HW)) return rc;
   if (sm_count() < 0) return CTL_ERR_CUDA;
-  return launch_saliency(g, g_dtype, N, C, HW, mode, s_out, nullptr, (cudaStream_t)stream);
+  return launch_saliency(g, g_dtype, N, C, HW, mode, s_out, (cudaStream_t)stream);
 }
 
 extern "C" int ctl_topp_mask_apply(const float* s, const void* z, int z_dtype, int64_t N, int64_t C, int64_t HW,
@@ -545,17 +521,16 @@ extern "C" int ctl_topp_mask_apply(const float* s, const void* z, int z_dtype, i
   if (int rc = check_select(n, k, first_sample)) return rc;
   if (sm_count() < 0) return CTL_ERR_CUDA;
   cudaStream_t st = (cudaStream_t)stream;
-  SelectArgs sa = {nullptr, mask_out, thr_out, rand, PhiloxKey{seed, offset}, first_sample, (int)k, soft != 0};
-  select_mask_kernel<<<(unsigned)N, kThreads, 0, st>>>(s, (int)n, sa);
-  CTL_CUDA_OK(cudaGetLastError(), "select_mask launch");
+  SelectArgs sa = {mask_out, thr_out, rand, PhiloxKey{seed, offset}, first_sample, (int)k, soft != 0};
+  if (int rc = launch_select(s, N, n, sa, /*chained=*/false, st)) return rc;
   return launch_apply_any(mode, z, z_dtype, z_out, out_dtype, mask_out, N, C, HW, st);
 }
 
 extern "C" int ctl_saliency_mask_apply(const void* g, int g_dtype, const void* z, int z_dtype, int64_t N, int64_t C,
                                        int64_t HW, int mode, int64_t k, int soft, const float* rand, uint64_t seed,
-                                       uint64_t offset, int64_t first_sample, float* s_scratch, void* workspace,
-                                       float* mask_out, float* thr_out, void* z_out, int out_dtype, void* stream) {
-  CTL_REQUIRE(g && z && s_scratch && workspace && mask_out && z_out, CTL_ERR_INVALID,
+                                       uint64_t offset, int64_t first_sample, float* s_scratch, float* mask_out,
+                                       float* thr_out, void* z_out, int out_dtype, void* stream) {
+  CTL_REQUIRE(g && z && s_scratch && mask_out && z_out, CTL_ERR_INVALID,
               "ctl_saliency_mask_apply: NULL pointer");
   CTL_REQUIRE(valid_dtype(g_dtype) && valid_dtype(z_dtype) && valid_dtype(out_dtype), CTL_ERR_INVALID,
               "ctl_saliency_mask_apply: unknown dtype");
@@ -566,8 +541,9 @@ extern "C" int ctl_saliency_mask_apply(const void* g, int g_dtype, const void* z
   if (int rc = check_select(n, k, first_sample)) return rc;
   if (sm_count() < 0) return CTL_ERR_CUDA;
   cudaStream_t st = (cudaStream_t)stream;
-  SelectArgs sa = {(int*)workspace, mask_out, thr_out, rand, PhiloxKey{seed, offset}, first_sample, (int)k, soft != 0};
-  if (int rc = launch_saliency(g, g_dtype, N, C, HW, mode, s_scratch, &sa, st)) return rc;
+  SelectArgs sa = {mask_out, thr_out, rand, PhiloxKey{seed, offset}, first_sample, (int)k, soft != 0};
+  if (int rc = launch_saliency(g, g_dtype, N, C, HW, mode, s_scratch, st)) return rc;      // ordinary launch
+  if (int rc = launch_select(s_scratch, N, n, sa, /*chained=*/true, st)) return rc;         // PDL after K1
   return launch_apply_any(mode, z, z_dtype, z_out, out_dtype, mask_out, N, C, HW, st);
 }
 

@@ -54,21 +54,6 @@ class NativeRNG:
         return o
 
 
-_WORKSPACES = {}
-
-
-def _masking_workspace(device, N):
-    """Per-(device, stream) arrival-counter workspace of ctl_saliency_mask_apply: zero-filled once here,
-    left zero-filled by every call (the kernels reset the counters they use)."""
-    key = (device.index, torch.cuda.current_stream(device).cuda_stream)
-    need = _lib.load().ctl_masking_workspace_bytes(N)
-    ws = _WORKSPACES.get(key)
-    if ws is None or ws.numel() < need:
-        ws = torch.zeros(max(need, 4096), device=device, dtype=torch.uint8)
-        _WORKSPACES[key] = ws
-    return ws
-
-
 def saliency_reduce(g, mode):
     """K1: fp32 [N,n] mean of g over space (channel mode) or channels (spatial mode)."""
     _need_cuda(g)
@@ -133,8 +118,8 @@ def saliency_mask_apply(g, z, mode, k, soft=False, rand=None, rng=None, out_dtyp
     with torch.cuda.device(z.device):
         _lib.check(_lib.load().ctl_saliency_mask_apply(
             g.data_ptr(), _dtype(g), z.data_ptr(), _dtype(z), N, C, HW, mode, int(k), int(bool(soft)), _ptr(rand),
-            seed, offset, first, s.data_ptr(), _masking_workspace(z.device, N).data_ptr(), mask.data_ptr(), _ptr(thr),
-            z_out.data_ptr(), _DTYPES[out_dtype], _stream()))
+            seed, offset, first, s.data_ptr(), mask.data_ptr(), _ptr(thr), z_out.data_ptr(), _DTYPES[out_dtype],
+            _stream()))
     return z_out, mask, s, thr
 
 

@@ -70,20 +70,16 @@ int ctl_topp_mask_apply(const float* s, const void* z, int z_dtype, int64_t N, i
                         uint64_t offset, int64_t first_sample, float* mask_out, float* thr_out,
                         void* z_out, int out_dtype, void* stream);
 
-/* The whole tail of mask_latent_code_{channel,spatial}_wise in two launches: K1 whose last-arriving
- * CTA per sample performs the selection and builds the mask row, then K2 (pure 128-bit streaming apply,
- * launched with programmatic stream serialization so that its loads of z overlap K1's tail).
- * s_scratch: fp32 [N,n] caller scratch, holds s afterwards.
- * workspace: ctl_masking_workspace_bytes(N) bytes of per-sample arrival counters.  The caller zero-fills
- * it ONCE after allocation; every call leaves it zero-filled again.  One workspace per concurrently
- * used stream.
+/* The whole tail of mask_latent_code_{channel,spatial}_wise as one chain of three launches on `stream`:
+ * K1 (saliency), a one-CTA-per-sample select/mask-build kernel and K2 (128-bit streaming apply).  The
+ * second and third are launched with programmatic stream serialization, so K2's loads of z are already
+ * in flight while K1 drains and the select runs.  s_scratch: fp32 [N,n] caller scratch, holds s afterwards.
  */
-size_t ctl_masking_workspace_bytes(int64_t N);
 int ctl_saliency_mask_apply(const void* g, int g_dtype, const void* z, int z_dtype, int64_t N,
                             int64_t C, int64_t HW, int mode, int64_t k, int soft, const float* rand,
                             uint64_t seed, uint64_t offset, int64_t first_sample, float* s_scratch,
-                            void* workspace, float* mask_out, float* thr_out, void* z_out,
-                            int out_dtype, void* stream);
+                            float* mask_out, float* thr_out, void* z_out, int out_dtype,
+                            void* stream);
 
 /* ---------------------------------------------------------------------------------------------
  * Random channel dropout.  Replaces F.dropout2d(z, p) + the full-size `where(masked == z, 1, 0)`
