@@ -13,6 +13,7 @@ LIB_PATH = os.path.join(_HERE, "libctl_b200.so")
 CTL_OK, CTL_ERR_INVALID, CTL_ERR_INDEX, CTL_ERR_UNSUPPORTED, CTL_ERR_CUDA = 0, 1, 2, 3, 4
 CTL_F32, CTL_BF16 = 0, 1
 MODE_CHANNEL, MODE_SPATIAL = 0, 1
+ACT_NONE, ACT_LRELU, ACT_RELU, ACT_SIGMOID = 0, 1, 2, 3
 
 _c = ctypes
 _vp, _i, _i64, _u64, _f = _c.c_void_p, _c.c_int, _c.c_int64, _c.c_uint64, _c.c_float
@@ -29,13 +30,16 @@ SIGNATURES = {
                                      _vp, _vp, _vp, _vp, _i, _vp]),
     "ctl_channel_dropout": (_i, [_vp, _i, _i64, _i64, _i64, _f, _f, _vp, _u64, _u64, _i64, _vp, _i, _vp, _vp, _vp]),
     "ctl_philox_uniform": (_i, [_u64, _u64, _u64, _i64, _vp, _vp]),
+    "ctl_conv2d_n_tile": (_i, [_i, _i, _i]),
+    "ctl_conv2d_nhwc_bf16": (_i, [_vp, _i64, _i64, _i64, _i64, _vp, _i64, _i, _i, _vp, _vp, _vp, _vp, _vp, _i, _vp,
+                                  _vp]),
 }
 
 _lib = None
 # kernels launched through this binding since import (bench.py reports the count inside its timed
 # region as `gpu_launches`); name -> kernels per successful call
 KERNELS_PER_CALL = {"ctl_saliency_reduce": 1, "ctl_topp_mask_apply": 2, "ctl_saliency_mask_apply": 3,
-                    "ctl_channel_dropout": 1, "ctl_philox_uniform": 1}
+                    "ctl_channel_dropout": 1, "ctl_philox_uniform": 1, "ctl_conv2d_nhwc_bf16": 1}
 LAUNCHES = {"count": 0}
 
 

@@ -1,0 +1,390 @@
+// K3: bf16 implicit-GEMM convolution on tcgen05 tensor cores, fed by TMA, accumulators in TMEM,
+// fused per-channel scale/shift (bias / folded BatchNorm) + residual + activation epilogue.
+//
+// Covers the conv layer classes of FCN_16_standard (reference modules
+// medseg/models/ebm/encoder_decoder.py:19-68, :285-348, :351-415, :418-453, :456-503):
+//   3x3 stride-1 pad-1 (TAPS = 9), 1x1 (TAPS = 1), and 3x3 stride-2 pad-1 as "compute at full
+//   resolution, keep even pixels" (the MMA is far from the bottleneck on these HBM-bound layers),
+//   Cin in {16,32,64,128}, Cout a multiple of 16.
+//
+// Data layout in HBM: activations NHWC bf16 (torch channels_last), weights pre-packed per N tile as
+//   [n_tile][tap][Cin/8][NT][8] bf16 (K-major core matrices, see pack_conv_weight in conv_blocks.py).
+//
+// One CTA = one SM, persistent over output tiles of 16 rows x (8*MT) columns of one image:
+//   warp 0  : TMA producer  -- per tile, Cin/8 box loads [halo_h][halo_w][8ch] (zero-filled halo) into a
+//             ring of STAGES shared-memory buffers laid out [Cin/8][halo_h][halo_w][8ch].  That is the
+//             UMMA no-swizzle K-major canonical layout with LBO = halo_h*halo_w*16, SBO = halo_w*16, so the
+//             nine filter taps are nine descriptor START ADDRESSES into the same tile: no im2col copy,
+//             every input byte crosses HBM once.
+//   warp 1  : MMA issuer    -- one elected thread issues TAPS*Cin/16 tcgen05.mma (M=128, N=NT, K=16) per
+//             8-column M tile into one of two TMEM accumulator stages, then tcgen05.commit frees the
+//             smem stage and publishes the accumulator.
+//   warp 2  : TMEM allocator; warp 3 idle.
+//   warps 4-7: epilogue     -- tcgen05.ld 16 columns at a time, y = act(acc*scale + shift + res*rs + rb),
+//             bf16 pack, 32-byte vector stores to NHWC.
+#include <algorithm>
+
+#include "ctl_common.cuh"
+#include "ctl_tcgen05.cuh"
+
+namespace ctl {
+namespace {
+
+using namespace sm100;
+
+constexpr int kTileH = 16;            // output rows per tile (= 8-row groups of the M=128 MMA: one group per row)
+constexpr int kConvThreads = 256;
+constexpr int kAccStages = 2;
+
+struct ConvParams {
+  int N, H, W;                        // input (= full-resolution output) size
+  int Cout;                           // total output channels
+  int tiles_x, tiles_y;               // tiles per image
+  int64_t num_tiles;                  // N * tiles_y * tiles_x
+  const __nv_bfloat16* w_packed;      // [Cout/NT][TAPS][Cin/8][NT][8]
+  const float* scale;                 // [Cout] or nullptr (=1)
+  const float* shift;                 // [Cout] or nullptr (=0)
+  const __nv_bfloat16* res;           // NHWC [N,Ho,Wo,Cout] or nullptr
+  const float* res_scale;             // [Cout] or nullptr (=1)
+  const float* res_shift;             // [Cout] or nullptr (=0)
+  __nv_bfloat16* out;                 // NHWC [N,Ho,Wo,Cout]
+  int act;                            // ctl_act
+  int subsample;                      // 1: Ho=H, Wo=W; 2: keep even (y,x) -> Ho=H/2, Wo=W/2 (3x3 stride-2 pad-1)
+};
+
+__device__ __forceinline__ float apply_act(float v, int act) {
+  switch (act) {
+    case CTL_ACT_LRELU: return v > 0.0f ? v : 0.2f * v;
+    case CTL_ACT_RELU: return fmaxf(v, 0.0f);
+    case CTL_ACT_SIGMOID: return 1.0f / (1.0f + __expf(-v));
+    default: return v;
+  }
+}
+
+template <int CIN, int NT, int TAPS, int MT, int STAGES>
+struct ConvCfg {
+  static constexpr int kPad = TAPS == 9 ? 1 : 0;
+  static constexpr int kHaloH = kTileH + 2 * kPad;
+  static constexpr int kHaloW = 8 * MT + 2 * kPad;
+  static constexpr int kChunkBytes = kHaloH * kHaloW * 16;        // one 8-channel chunk of the halo tile
+  static constexpr int kStageBytes = (CIN / 8) * kChunkBytes;
+  static constexpr int kWBytes = TAPS * CIN * NT * 2;
+  static constexpr int kTmemCols = kAccStages * MT * NT;
+  static constexpr int kTmemAlloc = kTmemCols <= 32 ? 32 : kTmemCols <= 64 ? 64 : kTmemCols <= 128 ? 128
+                                    : kTmemCols <= 256 ? 256 : 512;
+  // smem carve-up (all offsets multiples of 128)
+  static constexpr int kOffW = 0;
+  static constexpr int kOffA = (kWBytes + 127) / 128 * 128;
+  static constexpr int kOffVec = kOffA + STAGES * ((kStageBytes + 127) / 128 * 128);   // 4 x NT floats
+  static constexpr int kOffBar = kOffVec + 4 * NT * 4;
+  static constexpr int kSmemBytes = kOffBar + 128;
+  static_assert(kTmemCols <= 512, "accumulators exceed TMEM");
+  static_assert(CIN % 16 == 0 && NT % 16 == 0 && NT <= 256, "UMMA shape");
+  static_assert(kSmemBytes <= 227 * 1024, "shared memory budget");
+  static_assert(kChunkBytes % 16 == 0 && (kChunkBytes >> 4) < 16384 && kHaloW * 16 < 16384 * 16, "descriptor range");
+};
+
+template <int CIN, int NT, int TAPS, int MT, int STAGES>
+__global__ void __launch_bounds__(kConvThreads, 1)
+conv_tc_kernel(const __grid_constant__ CUtensorMap tmap, const ConvParams p) {
+  using Cfg = ConvCfg<CIN, NT, TAPS, MT, STAGES>;
+  extern __shared__ __align__(1024) uint8_t smem[];
+  uint8_t* sW = smem + Cfg::kOffW;
+  uint8_t* sA = smem + Cfg::kOffA;
+  float* sVec = reinterpret_cast<float*>(smem + Cfg::kOffVec);     // scale | shift | res_scale | res_shift
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Cfg::kOffBar);
+  uint64_t* full = bars;                        // [STAGES]  TMA -> MMA
+  uint64_t* empty = bars + STAGES;              // [STAGES]  MMA -> TMA
+  uint64_t* acc_full = bars + 2 * STAGES;       // [2]       MMA -> epilogue
+  uint64_t* acc_empty = bars + 2 * STAGES + 2;  // [2]       epilogue -> MMA
+  uint64_t* w_full = bars + 2 * STAGES + 4;     // [1]       weights landed
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 5);
+  constexpr int kStageStride = (Cfg::kStageBytes + 127) / 128 * 128;
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int n_tile = blockIdx.y;                // which NT-wide slice of the output channels
+  const int n0 = n_tile * NT;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmap);
+    for (int i = 0; i < STAGES; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
+    for (int i = 0; i < kAccStages; ++i) { mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], 4); }
+    mbar_init(w_full, 1);
+    mbar_fence_init();
+  }
+  if (warp == 2) tmem_alloc<Cfg::kTmemAlloc>(tmem_slot);
+  for (int i = threadIdx.x; i < NT; i += kConvThreads) {
+    sVec[i] = p.scale ? p.scale[n0 + i] : 1.0f;
+    sVec[NT + i] = p.shift ? p.shift[n0 + i] : 0.0f;
+    sVec[2 * NT + i] = p.res_scale ? p.res_scale[n0 + i] : 1.0f;
+    sVec[3 * NT + i] = p.res_shift ? p.res_shift[n0 + i] : 0.0f;
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  const int tiles_per_img = p.tiles_x * p.tiles_y;
+
+  if (warp == 0) {
+    // ================================================================= TMA producer
+    if (lane == 0) {
+      mbar_arrive_expect_tx(w_full, Cfg::kWBytes);
+      bulk_load_1d(sW, reinterpret_cast<const uint8_t*>(p.w_packed) + (size_t)n_tile * Cfg::kWBytes, Cfg::kWBytes,
+                   w_full);
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int64_t t = blockIdx.x; t < p.num_tiles; t += gridDim.x) {
+        const int img = (int)(t / tiles_per_img);
+        const int rem = (int)(t - (int64_t)img * tiles_per_img);
+        const int ty = rem / p.tiles_x, tx = rem - ty * p.tiles_x;
+        const int y0 = ty * kTileH - Cfg::kPad, x0 = tx * (8 * MT) - Cfg::kPad;
+        mbar_wait(&empty[stage], phase ^ 1);
+        mbar_arrive_expect_tx(&full[stage], Cfg::kStageBytes);
+        uint8_t* dst = sA + stage * kStageStride;
+#pragma unroll 1
+        for (int ch = 0; ch < CIN / 8; ++ch)
+          tma_load_4d(dst + ch * Cfg::kChunkBytes, &tmap, &full[stage], ch * 8, x0, y0, img);
+        if (++stage == STAGES) { stage = 0; phase ^= 1; }
+      }
+    }
+  } else if (warp == 1) {
+    // ================================================================= MMA issuer
+    if (lane == 0) {
+      constexpr uint32_t idesc = umma_idesc_bf16_f32(128, NT);
+      constexpr uint32_t kLboA = Cfg::kChunkBytes, kSboA = Cfg::kHaloW * 16;
+      constexpr uint32_t kLboB = NT * 16, kSboB = 128;
+      mbar_wait(w_full, 0);
+      int stage = 0, acc = 0;
+      uint32_t phase = 0, acc_phase = 0;
+      const uint32_t sW_addr = smem_u32(sW);
+      for (int64_t t = blockIdx.x; t < p.num_tiles; t += gridDim.x) {
+        mbar_wait(&acc_empty[acc], acc_phase ^ 1);
+        mbar_wait(&full[stage], phase);
+        tc_fence_after();
+        const uint32_t a_base = smem_u32(sA + stage * kStageStride);
+#pragma unroll
+        for (int mt = 0; mt < MT; ++mt) {
+          const uint32_t d_tmem = tmem_base + (uint32_t)((acc * MT + mt) * NT);
+#pragma unroll
+          for (int tap = 0; tap < TAPS; ++tap) {
+            const int r = TAPS == 9 ? tap / 3 : 0, s = TAPS == 9 ? tap % 3 : 0;
+            const uint32_t a_tap = a_base + (uint32_t)((r * Cfg::kHaloW + s + 8 * mt) * 16);
+#pragma unroll
+            for (int kk = 0; kk < CIN / 16; ++kk) {
+              const uint64_t adesc = umma_smem_desc(a_tap + (uint32_t)(2 * kk) * kLboA, kLboA, kSboA);
+              const uint64_t bdesc =
+                  umma_smem_desc(sW_addr + (uint32_t)((tap * (CIN / 8) + 2 * kk) * (NT * 16)), kLboB, kSboB);
+              umma_bf16(d_tmem, adesc, bdesc, idesc, (tap | kk) != 0 ? 1u : 0u);
+            }
+          }
+        }
+        umma_commit(&empty[stage]);       // smem stage reusable once these MMAs have read it
+        umma_commit(&acc_full[acc]);      // accumulator complete
+        if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        if (++acc == kAccStages) { acc = 0; acc_phase ^= 1; }
+      }
+    }
+  } else if (warp >= 4) {
+    // ================================================================= epilogue (TMEM lanes 32*(warp-4) ..)
+    const int q = warp - 4;                       // == warp % 4: the TMEM sub-partition this warp may read
+    const int m = q * 32 + lane;                  // accumulator row = pixel within the 16x8 M tile
+    const int py = m >> 3, px = m & 7;
+    const int Ho = p.H / p.subsample, Wo = p.W / p.subsample;
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int64_t t = blockIdx.x; t < p.num_tiles; t += gridDim.x) {
+      const int img = (int)(t / tiles_per_img);
+      const int rem = (int)(t - (int64_t)img * tiles_per_img);
+      const int ty = rem / p.tiles_x, tx = rem - ty * p.tiles_x;
+      mbar_wait(&acc_full[acc], acc_phase);
+      tc_fence_after();
+#pragma unroll
+      for (int mt = 0; mt < MT; ++mt) {
+        const int y = ty * kTileH + py, x = tx * (8 * MT) + mt * 8 + px;
+        bool valid = y < p.H && x < p.W;
+        int yo = y, xo = x;
+        if (p.subsample == 2) { valid = valid && !((y | x) & 1); yo = y >> 1; xo = x >> 1; }
+        const int64_t pix = ((int64_t)img * Ho + yo) * Wo + xo;
+        __nv_bfloat16* optr = p.out + pix * p.Cout + n0;
+        const __nv_bfloat16* rptr = p.res ? p.res + pix * p.Cout + n0 : nullptr;
+        const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)((acc * MT + mt) * NT);
+#pragma unroll 1
+        for (int c0 = 0; c0 < NT; c0 += 16) {
+          uint32_t v[16];
+          tmem_ld_32x32b_x16(t_row + (uint32_t)c0, v);      // warp-collective: executed by every lane
+          tmem_ld_wait();
+          if (valid) {
+            float f[16];
+#pragma unroll
+            for (int i = 0; i < 16; ++i) f[i] = __uint_as_float(v[i]) * sVec[c0 + i] + sVec[NT + c0 + i];
+            if (rptr) {
+              const uint4 r0 = *reinterpret_cast<const uint4*>(rptr + c0);
+              const uint4 r1 = *reinterpret_cast<const uint4*>(rptr + c0 + 8);
+              const uint32_t rw[8] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w};
+#pragma unroll
+              for (int i = 0; i < 8; ++i) {
+                f[2 * i] += __uint_as_float(rw[i] << 16) * sVec[2 * NT + c0 + 2 * i] + sVec[3 * NT + c0 + 2 * i];
+                f[2 * i + 1] += __uint_as_float(rw[i] & 0xffff0000u) * sVec[2 * NT + c0 + 2 * i + 1] +
+                                sVec[3 * NT + c0 + 2 * i + 1];
+              }
+            }
+            uint32_t o[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              const __nv_bfloat162 h = __floats2bfloat162_rn(apply_act(f[2 * i], p.act), apply_act(f[2 * i + 1], p.act));
+              o[i] = *reinterpret_cast<const uint32_t*>(&h);
+            }
+            *reinterpret_cast<uint4*>(optr + c0) = make_uint4(o[0], o[1], o[2], o[3]);
+            *reinterpret_cast<uint4*>(optr + c0 + 8) = make_uint4(o[4], o[5], o[6], o[7]);
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&acc_empty[acc]);
+      if (++acc == kAccStages) { acc = 0; acc_phase ^= 1; }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc<Cfg::kTmemAlloc>(tmem_base);
+  }
+}
+
+// ---- host side -------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn encode_tiled_fn() {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void* sym = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &sym, cudaEnableDefault, &qres) != cudaSuccess ||
+        qres != cudaDriverEntryPointSuccess)
+      return nullptr;
+    fn = reinterpret_cast<EncodeTiledFn>(sym);
+  }
+  return fn;
+}
+
+// NHWC bf16 activation [N,H,W,C] as a 4-D tensor map (C, W, H, N) with box (8, halo_w, halo_h, 1).
+int make_act_tmap(CUtensorMap* m, const void* x, int N, int H, int W, int C, int halo_w, int halo_h) {
+  EncodeTiledFn enc = encode_tiled_fn();
+  CTL_REQUIRE(enc != nullptr, CTL_ERR_CUDA, "cuTensorMapEncodeTiled is not available from the driver");
+  const cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)N};
+  const cuuint64_t strides[3] = {(cuuint64_t)C * 2, (cuuint64_t)W * C * 2, (cuuint64_t)H * W * C * 2};
+  const cuuint32_t box[4] = {8, (cuuint32_t)halo_w, (cuuint32_t)halo_h, 1};
+  const cuuint32_t estr[4] = {1, 1, 1, 1};
+  const CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(x), dims, strides, box, estr,
+                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  CTL_REQUIRE(r == CUDA_SUCCESS, CTL_ERR_CUDA, "cuTensorMapEncodeTiled failed with CUresult %d", (int)r);
+  return CTL_OK;
+}
+
+template <int CIN, int NT, int TAPS, int MT, int STAGES>
+int launch_conv(const void* x, const ConvParams& p0, cudaStream_t st) {
+  using Cfg = ConvCfg<CIN, NT, TAPS, MT, STAGES>;
+  ConvParams p = p0;
+  p.tiles_x = (int)ceil_div(p.W, 8 * MT);
+  p.tiles_y = (int)ceil_div(p.H, kTileH);
+  p.num_tiles = (int64_t)p.N * p.tiles_x * p.tiles_y;
+  CUtensorMap tmap;
+  if (int rc = make_act_tmap(&tmap, x, p.N, p.H, p.W, CIN, Cfg::kHaloW, Cfg::kHaloH)) return rc;
+  auto kern = conv_tc_kernel<CIN, NT, TAPS, MT, STAGES>;
+  CTL_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes),
+              "conv smem attribute");
+  const int n_tiles = p.Cout / NT;
+  const int ctas = (int)std::min<int64_t>(p.num_tiles, std::max(1, sm_count() / n_tiles));
+  dim3 grid((unsigned)ctas, (unsigned)n_tiles);
+  kern<<<grid, kConvThreads, Cfg::kSmemBytes, st>>>(tmap, p);
+  CTL_CUDA_OK(cudaGetLastError(), "conv_tc launch");
+  return CTL_OK;
+}
+
+template <int CIN, int TAPS>
+int dispatch_nt(const void* x, const ConvParams& p, int nt, cudaStream_t st) {
+  // MT = 2 (16x16 pixel tiles, halo overhead 1.27x) while the tile ring fits; STAGES from the smem left
+  if constexpr (CIN == 16) {
+    if (nt == 16) return launch_conv<16, 16, TAPS, 2, 4>(x, p, st);
+    if (nt == 32) return launch_conv<16, 32, TAPS, 2, 4>(x, p, st);
+    if (nt == 64) return launch_conv<16, 64, TAPS, 2, 4>(x, p, st);
+  } else if constexpr (CIN == 32) {
+    if (nt == 16) return launch_conv<32, 16, TAPS, 2, 4>(x, p, st);
+    if (nt == 32) return launch_conv<32, 32, TAPS, 2, 4>(x, p, st);
+    if (nt == 64) return launch_conv<32, 64, TAPS, 2, 3>(x, p, st);
+  } else if constexpr (CIN == 64) {
+    if (nt == 16) return launch_conv<64, 16, TAPS, 2, 3>(x, p, st);
+    if (nt == 32) return launch_conv<64, 32, TAPS, 2, 3>(x, p, st);
+    if (nt == 64) return launch_conv<64, 64, TAPS, 2, 2>(x, p, st);
+  } else if constexpr (CIN == 128) {
+    if (nt == 16) return launch_conv<128, 16, TAPS, 1, 3>(x, p, st);
+    if (nt == 32) return launch_conv<128, 32, TAPS, 1, 2>(x, p, st);
+    if (nt == 64) return launch_conv<128, 64, TAPS, 1, TAPS == 9 ? 1 : 2>(x, p, st);
+  }
+  set_error("ctl_conv2d_nhwc_bf16: no kernel for Cin=%d, n_tile=%d", CIN, nt);
+  return CTL_ERR_UNSUPPORTED;
+}
+
+}  // namespace
+}  // namespace ctl
+
+using namespace ctl;
+
+extern "C" int ctl_conv2d_n_tile(int Cin, int Cout, int taps) {
+  if (!(Cin == 16 || Cin == 32 || Cin == 64 || Cin == 128) || Cout <= 0 || Cout % 16 || !(taps == 1 || taps == 9))
+    return -1;
+  // widest N tile whose packed weights + a useful activation ring fit in 227 KB of shared memory
+  const int cap = (taps == 9 && Cin == 128) ? 32 : 64;
+  for (int nt = cap; nt >= 16; nt >>= 1)
+    if (Cout % nt == 0) return nt;
+  return -1;
+}
+
+extern "C" int ctl_conv2d_nhwc_bf16(const void* x, int64_t N, int64_t H, int64_t W, int64_t Cin, const void* w_packed,
+                                    int64_t Cout, int taps, int subsample, const float* scale, const float* shift,
+                                    const void* res, const float* res_scale, const float* res_shift, int act,
+                                    void* out, void* stream) {
+  CTL_REQUIRE(x && w_packed && out, CTL_ERR_INVALID, "ctl_conv2d_nhwc_bf16: NULL pointer");
+  CTL_REQUIRE(N > 0 && H > 0 && W > 0 && N <= 65535 && H <= 32768 && W <= 32768, CTL_ERR_INVALID,
+              "ctl_conv2d_nhwc_bf16: bad shape N=%lld H=%lld W=%lld", (long long)N, (long long)H, (long long)W);
+  CTL_REQUIRE(taps == 1 || taps == 9, CTL_ERR_INVALID, "taps must be 1 (1x1) or 9 (3x3 pad 1), got %d", taps);
+  CTL_REQUIRE(subsample == 1 || (subsample == 2 && H % 2 == 0 && W % 2 == 0), CTL_ERR_INVALID,
+              "subsample must be 1, or 2 with even H and W");
+  CTL_REQUIRE(act >= CTL_ACT_NONE && act <= CTL_ACT_SIGMOID, CTL_ERR_INVALID, "unknown activation %d", act);
+  const int nt = ctl_conv2d_n_tile((int)Cin, (int)Cout, taps);
+  CTL_REQUIRE(nt > 0, CTL_ERR_UNSUPPORTED,
+              "ctl_conv2d_nhwc_bf16 handles Cin in {16,32,64,128} and Cout %% 16 == 0 (got Cin=%lld Cout=%lld)",
+              (long long)Cin, (long long)Cout);
+  CTL_REQUIRE(aligned16(x) && aligned16(w_packed) && aligned16(out) && (!res || aligned16(res)), CTL_ERR_INVALID,
+              "ctl_conv2d_nhwc_bf16: pointers must be 16-byte aligned");
+  if (sm_count() < 0) return CTL_ERR_CUDA;
+  ConvParams p = {};
+  p.N = (int)N; p.H = (int)H; p.W = (int)W; p.Cout = (int)Cout;
+  p.w_packed = (const __nv_bfloat16*)w_packed;
+  p.scale = scale; p.shift = shift;
+  p.res = (const __nv_bfloat16*)res; p.res_scale = res_scale; p.res_shift = res_shift;
+  p.out = (__nv_bfloat16*)out; p.act = act; p.subsample = subsample;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (taps == 9) {
+    switch ((int)Cin) {
+      case 16: return dispatch_nt<16, 9>(x, p, nt, st);
+      case 32: return dispatch_nt<32, 9>(x, p, nt, st);
+      case 64: return dispatch_nt<64, 9>(x, p, nt, st);
+      default: return dispatch_nt<128, 9>(x, p, nt, st);
+    }
+  }
+  switch ((int)Cin) {
+    case 16: return dispatch_nt<16, 1>(x, p, nt, st);
+    case 32: return dispatch_nt<32, 1>(x, p, nt, st);
+    case 64: return dispatch_nt<64, 1>(x, p, nt, st);
+    default: return dispatch_nt<128, 1>(x, p, nt, st);
+  }
+}

@@ -162,3 +162,58 @@ def philox_uniform(seed, offset, first_index, count, device="cuda"):
         _lib.check(_lib.load().ctl_philox_uniform(int(seed), int(offset), int(first_index), count, out.data_ptr(),
                                                   _stream()))
     return out
+
+
+# ------------------------------------------------------------------------------------------------ K3: conv blocks
+ACT_NONE, ACT_LRELU, ACT_RELU, ACT_SIGMOID = _lib.ACT_NONE, _lib.ACT_LRELU, _lib.ACT_RELU, _lib.ACT_SIGMOID
+
+
+def conv_supported(cin, cout, kernel_size):
+    """True when ctl_conv2d_nhwc_bf16 has a tensor-core kernel for this layer class."""
+    taps = kernel_size * kernel_size
+    return taps in (1, 9) and _lib.load().ctl_conv2d_n_tile(int(cin), int(cout), taps) > 0
+
+
+def pack_conv_weight(weight):
+    """[Cout,Cin,k,k] (k = 1 or 3) -> bf16 [Cout/NT][taps][Cin/8][NT][8], the K-major core-matrix order the
+    UMMA descriptors of conv_tc.cu expect (include/ctl_b200.h).  Tiny tensors: plain torch ops."""
+    cout, cin, kh, kw = weight.shape
+    taps = kh * kw
+    nt = _lib.load().ctl_conv2d_n_tile(cin, cout, taps)
+    if kh != kw or nt <= 0:
+        raise NotImplementedError("no tcgen05 conv kernel for weight shape %s" % (tuple(weight.shape),))
+    w = weight.detach().to(torch.bfloat16).permute(2, 3, 1, 0).reshape(taps, cin // 8, 8, cout // nt, nt)
+    return w.permute(3, 0, 1, 4, 2).contiguous()
+
+
+def _channels_last_bf16(x):
+    if x.dtype != torch.bfloat16:
+        x = x.to(torch.bfloat16)
+    return x.contiguous(memory_format=torch.channels_last)
+
+
+def conv2d_bf16(x, w_packed, cout, taps, subsample=1, scale=None, shift=None, res=None, res_scale=None, res_shift=None,
+                act=ACT_NONE):
+    """out = act(conv(x) * scale + shift + res * res_scale + res_shift) on the tcgen05 kernel.
+    x / res / out: logical [N,C,H,W] bf16 tensors in channels_last memory format (NHWC in HBM)."""
+    _need_cuda(x, w_packed, scale, shift, res, res_scale, res_shift)
+    x = _channels_last_bf16(x)
+    N, cin, H, W = x.shape
+    Ho, Wo = H // subsample, W // subsample
+    out = torch.empty((N, cout, Ho, Wo), device=x.device, dtype=torch.bfloat16, memory_format=torch.channels_last)
+    if res is not None:
+        res = _channels_last_bf16(res)
+        if tuple(res.shape) != tuple(out.shape):
+            raise ValueError("res must have the output shape %s" % (tuple(out.shape),))
+    vecs = []
+    for v in (scale, shift, res_scale, res_shift):
+        if v is not None:
+            v = v.to(torch.float32).contiguous()
+            if v.numel() != cout:
+                raise ValueError("per-channel vectors must have Cout=%d elements" % cout)
+        vecs.append(v)
+    with torch.cuda.device(x.device):
+        _lib.check(_lib.load().ctl_conv2d_nhwc_bf16(
+            x.data_ptr(), N, H, W, cin, w_packed.data_ptr(), cout, taps, subsample, _ptr(vecs[0]), _ptr(vecs[1]),
+            _ptr(res), _ptr(vecs[2]), _ptr(vecs[3]), act, out.data_ptr(), _stream()))
+    return out

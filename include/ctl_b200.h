@@ -36,6 +36,7 @@ enum ctl_status {
 
 enum ctl_dtype { CTL_F32 = 0, CTL_BF16 = 1 };
 enum ctl_mode { CTL_MODE_CHANNEL = 0, CTL_MODE_SPATIAL = 1 };
+enum ctl_act { CTL_ACT_NONE = 0, CTL_ACT_LRELU = 1 /* slope 0.2 */, CTL_ACT_RELU = 2, CTL_ACT_SIGMOID = 3 };
 
 int ctl_version(void);
 const char* ctl_last_error(void);
@@ -98,6 +99,28 @@ int ctl_channel_dropout(const void* z, int z_dtype, int64_t N, int64_t C, int64_
 /* Philox4x32-10 uniform draw, exposed for parity tests of the native RNG: out[i] = u(first_index+i). */
 int ctl_philox_uniform(uint64_t seed, uint64_t offset, uint64_t first_index, int64_t count,
                        float* out, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * K3 -- conv blocks of the FTN/STN encoders/decoders as bf16 implicit GEMM on tcgen05 tensor cores
+ * (TMA-fed, TMEM accumulators).  Replaces the nn.Conv2d + BatchNorm2d(eval / folded) + LeakyReLU(0.2) |
+ * ReLU | Sigmoid + residual-add sequences of
+ *   res_convdown   medseg/models/ebm/encoder_decoder.py:19-68
+ *   res_up_family  medseg/models/ebm/encoder_decoder.py:285-348
+ *   MyEncoder / MyDecoder / Dual_Branch_Encoder  :351-415, :418-453, :456-503
+ * x: NHWC bf16 [N,H,W,Cin] (torch channels_last).  taps = 9: 3x3, padding 1; taps = 1: 1x1.
+ * subsample = 2 gives the 3x3 stride-2 padding-1 convolution of `down` (output [N,H/2,W/2,Cout]).
+ * w_packed: bf16 [Cout/NT][taps][Cin/8][NT][8] with NT = ctl_conv2d_n_tile(Cin, Cout, taps), element
+ *           (t, tap, q, n, j) = weight[t*NT + n][q*8 + j][tap/3][tap%3].
+ * out = act( conv(x) * scale[c] + shift[c] + (res * res_scale[c] + res_shift[c]) ), bf16 NHWC; scale/shift
+ * fold the conv bias and an eval-mode (or precomputed batch-statistics) BatchNorm; res (same shape as out)
+ * and every per-channel vector may be NULL (identity).  Cin in {16,32,64,128}, Cout %% 16 == 0.
+ */
+int ctl_conv2d_n_tile(int Cin, int Cout, int taps);
+int ctl_conv2d_nhwc_bf16(const void* x, int64_t N, int64_t H, int64_t W, int64_t Cin,
+                         const void* w_packed, int64_t Cout, int taps, int subsample,
+                         const float* scale, const float* shift, const void* res,
+                         const float* res_scale, const float* res_shift, int act, void* out,
+                         void* stream);
 
 #ifdef __cplusplus
 }
