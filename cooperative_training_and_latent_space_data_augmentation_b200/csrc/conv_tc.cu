@@ -12,8 +12,9 @@
 //
 // One CTA = one SM, persistent over output tiles of 16 rows x (8*MT) columns of one image:
 //   warp 0  : TMA producer  -- per tile, Cin/8 box loads [halo_h][halo_w][8ch] (zero-filled halo) into a
-//             ring of STAGES shared-memory buffers laid out [Cin/8][halo_h][halo_w][8ch].  That is the
-//             UMMA no-swizzle K-major canonical layout with LBO = halo_h*halo_w*16, SBO = halo_w*16, so the
+//             ring of STAGES shared-memory buffers laid out [Cin/8][halo_h][halo_w][8ch] (chunks padded to
+//             128 B).  That is the UMMA no-swizzle K-major canonical layout with LBO = chunk stride,
+//             SBO = halo_w*16, so the
 //             nine filter taps are nine descriptor START ADDRESSES into the same tile: no im2col copy,
 //             every input byte crosses HBM once.
 //   warp 1  : MMA issuer    -- one elected thread issues TAPS*Cin/16 tcgen05.mma (M=128, N=NT, K=16) per
@@ -66,8 +67,10 @@ struct ConvCfg {
   static constexpr int kPad = TAPS == 9 ? 1 : 0;
   static constexpr int kHaloH = kTileH + 2 * kPad;
   static constexpr int kHaloW = 8 * MT + 2 * kPad;
-  static constexpr int kChunkBytes = kHaloH * kHaloW * 16;        // one 8-channel chunk of the halo tile
-  static constexpr int kStageBytes = (CIN / 8) * kChunkBytes;
+  static constexpr int kChunkBytes = kHaloH * kHaloW * 16;        // one 8-channel chunk of the halo tile (TMA box)
+  static constexpr int kChunkStride = (kChunkBytes + 127) / 128 * 128;   // TMA smem destinations: 128-byte aligned
+  static constexpr int kStageBytes = (CIN / 8) * kChunkStride;
+  static constexpr int kStageTxBytes = (CIN / 8) * kChunkBytes;   // bytes the TMA loads of one stage deliver
   static constexpr int kWBytes = TAPS * CIN * NT * 2;
   static constexpr int kTmemCols = kAccStages * MT * NT;
   static constexpr int kTmemAlloc = kTmemCols <= 32 ? 32 : kTmemCols <= 64 ? 64 : kTmemCols <= 128 ? 128
@@ -81,7 +84,7 @@ struct ConvCfg {
   static_assert(kTmemCols <= 512, "accumulators exceed TMEM");
   static_assert(CIN % 16 == 0 && NT % 16 == 0 && NT <= 256, "UMMA shape");
   static_assert(kSmemBytes <= 227 * 1024, "shared memory budget");
-  static_assert(kChunkBytes % 16 == 0 && (kChunkBytes >> 4) < 16384 && kHaloW * 16 < 16384 * 16, "descriptor range");
+  static_assert((kChunkStride >> 4) < 16384 && kHaloW * 16 < 16384 * 16, "descriptor range");
 };
 
 template <int CIN, int NT, int TAPS, int MT, int STAGES>
@@ -141,11 +144,11 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap, const ConvParams p) {
         const int ty = rem / p.tiles_x, tx = rem - ty * p.tiles_x;
         const int y0 = ty * kTileH - Cfg::kPad, x0 = tx * (8 * MT) - Cfg::kPad;
         mbar_wait(&empty[stage], phase ^ 1);
-        mbar_arrive_expect_tx(&full[stage], Cfg::kStageBytes);
+        mbar_arrive_expect_tx(&full[stage], Cfg::kStageTxBytes);
         uint8_t* dst = sA + stage * kStageStride;
 #pragma unroll 1
         for (int ch = 0; ch < CIN / 8; ++ch)
-          tma_load_4d(dst + ch * Cfg::kChunkBytes, &tmap, &full[stage], ch * 8, x0, y0, img);
+          tma_load_4d(dst + ch * Cfg::kChunkStride, &tmap, &full[stage], ch * 8, x0, y0, img);
         if (++stage == STAGES) { stage = 0; phase ^= 1; }
       }
     }
@@ -153,7 +156,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap, const ConvParams p) {
     // ================================================================= MMA issuer
     if (lane == 0) {
       constexpr uint32_t idesc = umma_idesc_bf16_f32(128, NT);
-      constexpr uint32_t kLboA = Cfg::kChunkBytes, kSboA = Cfg::kHaloW * 16;
+      constexpr uint32_t kLboA = Cfg::kChunkStride, kSboA = Cfg::kHaloW * 16;
       constexpr uint32_t kLboB = NT * 16, kSboB = 128;
       mbar_wait(w_full, 0);
       int stage = 0, acc = 0;
