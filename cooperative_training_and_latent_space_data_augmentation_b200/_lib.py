@@ -31,15 +31,26 @@ SIGNATURES = {
     "ctl_channel_dropout": (_i, [_vp, _i, _i64, _i64, _i64, _f, _f, _vp, _u64, _u64, _i64, _vp, _i, _vp, _vp, _vp]),
     "ctl_philox_uniform": (_i, [_u64, _u64, _u64, _i64, _vp, _vp]),
     "ctl_conv2d_n_tile": (_i, [_i, _i, _i]),
-    "ctl_conv2d_nhwc_bf16": (_i, [_vp, _i64, _i64, _i64, _i64, _vp, _i64, _i, _i, _vp, _vp, _vp, _vp, _vp, _i, _vp,
-                                  _vp]),
+    "ctl_conv2d_c8_bf16": (_i, [_vp, _i64, _i64, _i64, _i64, _vp, _i64, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _i, _vp,
+                                _vp]),
+    "ctl_nchw_to_c8": (_i, [_vp, _i, _i64, _i64, _i64, _i64, _vp, _vp]),
+    "ctl_c8_to_nchw": (_i, [_vp, _i64, _i64, _i64, _i64, _vp, _i, _vp]),
+    "ctl_stem_conv3x3_c8": (_i, [_vp, _vp, _i, _f, _i64, _i64, _i64, _i64, _vp, _i64, _vp, _vp, _i, _vp, _vp]),
+    "ctl_head_conv1x1_c8": (_i, [_vp, _i64, _i64, _i64, _i64, _vp, _vp, _i64, _i, _vp, _vp]),
+    "ctl_upsample2x_c8": (_i, [_vp, _i64, _i64, _i64, _i64, _vp, _vp]),
+    "ctl_bn_workspace_bytes": (_c.c_size_t, [_i64, _i64]),
+    "ctl_bn_batch_affine_c8": (_i, [_vp, _i64, _i64, _i64, _i64, _vp, _vp, _f, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _f,
+                                    _vp]),
+    "ctl_scale_shift_act_c8": (_i, [_vp, _i64, _i64, _i64, _i64, _vp, _vp, _i, _vp, _vp]),
 }
 
 _lib = None
 # kernels launched through this binding since import (bench.py reports the count inside its timed
 # region as `gpu_launches`); name -> kernels per successful call
 KERNELS_PER_CALL = {"ctl_saliency_reduce": 1, "ctl_topp_mask_apply": 2, "ctl_saliency_mask_apply": 3,
-                    "ctl_channel_dropout": 1, "ctl_philox_uniform": 1, "ctl_conv2d_nhwc_bf16": 1}
+                    "ctl_channel_dropout": 1, "ctl_philox_uniform": 1, "ctl_conv2d_c8_bf16": 1,
+                    "ctl_nchw_to_c8": 1, "ctl_c8_to_nchw": 1, "ctl_stem_conv3x3_c8": 1, "ctl_head_conv1x1_c8": 1,
+                    "ctl_upsample2x_c8": 1, "ctl_bn_batch_affine_c8": 2, "ctl_scale_shift_act_c8": 1}
 LAUNCHES = {"count": 0}
 
 

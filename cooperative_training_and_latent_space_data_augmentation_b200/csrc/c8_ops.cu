@@ -1,0 +1,396 @@
+// CUDA-core kernels around K3 for the blocked activation layout C8 = bf16 [N][C/8][H][W][8]:
+// layout conversion, the stem convolution (Cin = 1 / 4: K = 9 / 36 is below what a UMMA tile can use, SURVEY.md
+// 7.3 #4) with the STN input construction fused into its prologue, the 1x1 head (Cout = 1 / 4), nearest x2
+// up-sampling, train-mode BatchNorm statistics and the per-channel scale/shift/activation pass.
+// All of them are HBM-bound streaming kernels: 16-byte accesses, consecutive threads on consecutive pixels.
+//
+// Reference code replaced:
+//   stem  : MyEncoder.inc[0] + norm + LeakyReLU           medseg/models/ebm/encoder_decoder.py:370-378
+//           construct_input (softmax(logit/T) | one-hot)   medseg/common_utils/basic_operations.py:110-158
+//   head  : MyDecoder.final_conv (+ Sigmoid)               medseg/models/ebm/encoder_decoder.py:439-452
+//   up2x  : nn.UpsamplingNearest2d(scale_factor=2)         medseg/models/ebm/encoder_decoder.py:294-296
+//   BN    : nn.BatchNorm2d training statistics             (norm(out_ch) in every block)
+#include <algorithm>
+
+#include "ctl_common.cuh"
+
+namespace ctl {
+namespace {
+
+constexpr int kT = 256;
+
+__device__ __forceinline__ float act_fn(float v, int act) {
+  switch (act) {
+    case CTL_ACT_LRELU: return v > 0.0f ? v : 0.2f * v;
+    case CTL_ACT_RELU: return fmaxf(v, 0.0f);
+    case CTL_ACT_SIGMOID: return 1.0f / (1.0f + __expf(-v));
+    default: return v;
+  }
+}
+__device__ __forceinline__ void unpack8(const uint4& r, float (&f)[8]) {
+  const uint32_t w[4] = {r.x, r.y, r.z, r.w};
+#pragma unroll
+  for (int i = 0; i < 4; ++i) { f[2 * i] = __uint_as_float(w[i] << 16); f[2 * i + 1] = __uint_as_float(w[i] & 0xffff0000u); }
+}
+__device__ __forceinline__ uint4 pack8(const float (&f)[8]) {
+  uint32_t o[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const __nv_bfloat162 h = __floats2bfloat162_rn(f[2 * i], f[2 * i + 1]);
+    o[i] = *reinterpret_cast<const uint32_t*>(&h);
+  }
+  return make_uint4(o[0], o[1], o[2], o[3]);
+}
+template <typename T> __device__ __forceinline__ float to_f(T v);
+template <> __device__ __forceinline__ float to_f<float>(float v) { return v; }
+template <> __device__ __forceinline__ float to_f<__nv_bfloat16>(__nv_bfloat16 v) { return __bfloat162float(v); }
+
+// ------------------------------------------------------------------------------------------------ layout
+template <typename T>
+__global__ void __launch_bounds__(kT) nchw_to_c8_kernel(const T* __restrict__ x, __nv_bfloat16* __restrict__ y,
+                                                         int64_t total /*N*C/8*HW*/, int C8, int64_t HW) {
+  for (int64_t i = (int64_t)blockIdx.x * kT + threadIdx.x; i < total; i += (int64_t)gridDim.x * kT) {
+    const int64_t pix = i % HW, nc = i / HW;             // nc = n*C8 + c8
+    const T* src = x + nc * 8 * HW + pix;
+    float f[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) f[j] = to_f<T>(src[j * HW]);
+    *reinterpret_cast<uint4*>(y + i * 8) = pack8(f);
+  }
+}
+template <typename T>
+__global__ void __launch_bounds__(kT) c8_to_nchw_kernel(const __nv_bfloat16* __restrict__ x, T* __restrict__ y,
+                                                         int64_t total, int C8, int64_t HW) {
+  for (int64_t i = (int64_t)blockIdx.x * kT + threadIdx.x; i < total; i += (int64_t)gridDim.x * kT) {
+    const int64_t pix = i % HW, nc = i / HW;
+    float f[8];
+    unpack8(*reinterpret_cast<const uint4*>(x + i * 8), f);
+    T* dst = y + nc * 8 * HW + pix;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) dst[j * HW] = (T)f[j];
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ stem
+// 3x3 pad-1 conv from a planar (NCHW) input with CIN <= 4 channels to COUT (16) blocked channels, then
+// y = act(acc*scale + shift).  in_mode: 0 = fp32 NCHW as is, 1 = softmax(x / temperature) over the CIN channels
+// (STN input built from logits), 2 = one-hot of an int64 label map [N,H,W] (STN input built from labels).
+template <int CIN, int COUT>
+__global__ void __launch_bounds__(kT)
+stem_conv_kernel(const float* __restrict__ x, const long long* __restrict__ labels, const float* __restrict__ w /*[COUT][CIN][3][3]*/,
+                 const float* __restrict__ scale, const float* __restrict__ shift, __nv_bfloat16* __restrict__ y, int N,
+                 int H, int W, int in_mode, float inv_temp, int act) {
+  __shared__ __align__(16) float sw[COUT * CIN * 9];
+  __shared__ float ssc[COUT], ssh[COUT];
+  // transposed to [ci][tap][COUT] so that one 16-byte broadcast read feeds four output channels
+  for (int i = threadIdx.x; i < COUT * CIN * 9; i += kT) {
+    const int c = i / (CIN * 9), rest = i - c * (CIN * 9);
+    sw[rest * COUT + c] = w[i];
+  }
+  for (int i = threadIdx.x; i < COUT; i += kT) { ssc[i] = scale ? scale[i] : 1.0f; ssh[i] = shift ? shift[i] : 0.0f; }
+  __syncthreads();
+  const int64_t HW = (int64_t)H * W, total = (int64_t)N * HW;
+  for (int64_t i = (int64_t)blockIdx.x * kT + threadIdx.x; i < total; i += (int64_t)gridDim.x * kT) {
+    const int n = (int)(i / HW);
+    const int pix = (int)(i - (int64_t)n * HW);
+    const int yy = pix / W, xx = pix - yy * W;
+    float acc[COUT];
+#pragma unroll
+    for (int c = 0; c < COUT; ++c) acc[c] = 0.0f;
+#pragma unroll
+    for (int r = 0; r < 3; ++r) {
+      const int iy = yy + r - 1;
+      if (iy < 0 || iy >= H) continue;
+#pragma unroll
+      for (int s = 0; s < 3; ++s) {
+        const int ix = xx + s - 1;
+        if (ix < 0 || ix >= W) continue;
+        float v[CIN];
+        const int64_t q = (int64_t)iy * W + ix;
+        if (in_mode == 2) {
+          const long long lab = labels[(int64_t)n * HW + q];
+#pragma unroll
+          for (int ci = 0; ci < CIN; ++ci) v[ci] = (lab == ci) ? 1.0f : 0.0f;
+        } else {
+#pragma unroll
+          for (int ci = 0; ci < CIN; ++ci) v[ci] = x[((int64_t)n * CIN + ci) * HW + q];
+          if (in_mode == 1) {
+            float mx = v[0];
+#pragma unroll
+            for (int ci = 1; ci < CIN; ++ci) mx = fmaxf(mx, v[ci]);
+            float sum = 0.0f;
+#pragma unroll
+            for (int ci = 0; ci < CIN; ++ci) { v[ci] = __expf((v[ci] - mx) * inv_temp); sum += v[ci]; }
+            const float inv = 1.0f / sum;
+#pragma unroll
+            for (int ci = 0; ci < CIN; ++ci) v[ci] *= inv;
+          }
+        }
+#pragma unroll
+        for (int ci = 0; ci < CIN; ++ci) {
+          const float4* wv = reinterpret_cast<const float4*>(sw + (ci * 9 + r * 3 + s) * COUT);
+#pragma unroll
+          for (int c4 = 0; c4 < COUT / 4; ++c4) {
+            const float4 ww = wv[c4];
+            acc[4 * c4] = fmaf(v[ci], ww.x, acc[4 * c4]);
+            acc[4 * c4 + 1] = fmaf(v[ci], ww.y, acc[4 * c4 + 1]);
+            acc[4 * c4 + 2] = fmaf(v[ci], ww.z, acc[4 * c4 + 2]);
+            acc[4 * c4 + 3] = fmaf(v[ci], ww.w, acc[4 * c4 + 3]);
+          }
+        }
+      }
+    }
+#pragma unroll
+    for (int c8 = 0; c8 < COUT / 8; ++c8) {
+      float f[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) f[j] = act_fn(acc[c8 * 8 + j] * ssc[c8 * 8 + j] + ssh[c8 * 8 + j], act);
+      *reinterpret_cast<uint4*>(y + (((int64_t)n * (COUT / 8) + c8) * HW + pix) * 8) = pack8(f);
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ head
+// 1x1 conv from CIN (16) blocked channels to COUT <= 4 planar fp32 channels (+ bias, optional sigmoid).
+template <int CIN>
+__global__ void __launch_bounds__(kT)
+head_conv_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict__ w /*[COUT][CIN]*/, const float* __restrict__ b,
+                 float* __restrict__ y, int N, int64_t HW, int COUT, int act) {
+  __shared__ float sw[4 * CIN];
+  __shared__ float sb[4];
+  for (int i = threadIdx.x; i < COUT * CIN; i += kT) sw[i] = w[i];
+  if (threadIdx.x < COUT) sb[threadIdx.x] = b ? b[threadIdx.x] : 0.0f;
+  __syncthreads();
+  const int64_t total = (int64_t)N * HW;
+  for (int64_t i = (int64_t)blockIdx.x * kT + threadIdx.x; i < total; i += (int64_t)gridDim.x * kT) {
+    const int64_t n = i / HW, pix = i - n * HW;
+    float v[CIN];
+#pragma unroll
+    for (int c8 = 0; c8 < CIN / 8; ++c8) {
+      float f[8];
+      unpack8(*reinterpret_cast<const uint4*>(x + ((n * (CIN / 8) + c8) * HW + pix) * 8), f);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) v[c8 * 8 + j] = f[j];
+    }
+    for (int co = 0; co < COUT; ++co) {
+      float a = sb[co];
+#pragma unroll
+      for (int ci = 0; ci < CIN; ++ci) a = fmaf(v[ci], sw[co * CIN + ci], a);
+      y[(n * COUT + co) * HW + pix] = act_fn(a, act);
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ up2x
+__global__ void __launch_bounds__(kT)
+upsample2x_c8_kernel(const uint4* __restrict__ x, uint4* __restrict__ y, int64_t planes, int H, int W) {
+  const int64_t total = planes * H * W;      // one thread per INPUT pixel: 16 B in, 4 x 16 B out
+  for (int64_t i = (int64_t)blockIdx.x * kT + threadIdx.x; i < total; i += (int64_t)gridDim.x * kT) {
+    const int64_t pl = i / ((int64_t)H * W);
+    const int pix = (int)(i - pl * H * W);
+    const int yy = pix / W, xx = pix - yy * W;
+    const uint4 v = x[i];
+    uint4* o = y + pl * 4 * H * W + (int64_t)(2 * yy) * (2 * W) + 2 * xx;
+    o[0] = v; o[1] = v; o[2 * W] = v; o[2 * W + 1] = v;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ BN
+// stage 1: per (n, c8) plane sums of x and x^2 (fp64 accumulation) -> partial[n][C][2]
+__global__ void __launch_bounds__(kT)
+bn_partial_stats_kernel(const __nv_bfloat16* __restrict__ x, double* __restrict__ partial, int C8, int64_t HW) {
+  const int64_t nc = blockIdx.x;              // n*C8 + c8
+  const uint4* p = reinterpret_cast<const uint4*>(x) + nc * HW;
+  double s[8], q[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) { s[j] = 0.0; q[j] = 0.0; }
+  for (int64_t i = threadIdx.x; i < HW; i += kT) {
+    float f[8];
+    unpack8(__ldcs(p + i), f);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { s[j] += (double)f[j]; q[j] += (double)f[j] * (double)f[j]; }
+  }
+  __shared__ double red[kT / 32][16];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      s[j] += __shfl_xor_sync(0xffffffffu, s[j], o);
+      q[j] += __shfl_xor_sync(0xffffffffu, q[j], o);
+    }
+  }
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (lane == 0) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { red[warp][j] = s[j]; red[warp][8 + j] = q[j]; }
+  }
+  __syncthreads();
+  if (threadIdx.x < 16) {
+    double t = 0.0;
+    for (int w = 0; w < kT / 32; ++w) t += red[w][threadIdx.x];
+    const int j = threadIdx.x & 7, is_sq = threadIdx.x >> 3;
+    partial[(nc * 8 + j) * 2 + is_sq] = t;    // [n][c][2] with c = c8*8 + j
+  }
+}
+// stage 2: batch mean / biased variance -> fused affine y = x*scale + shift (scale = gamma*rsqrt(var+eps),
+// shift = beta - mean*scale); optional running-stat update (momentum, unbiased variance) like nn.BatchNorm2d.
+__global__ void bn_finalize_kernel(const double* __restrict__ partial, int N, int C, double count,
+                                   const float* __restrict__ gamma, const float* __restrict__ beta, float eps,
+                                   float* __restrict__ scale, float* __restrict__ shift, float* __restrict__ mean_out,
+                                   float* __restrict__ var_out, float* running_mean, float* running_var,
+                                   float momentum) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  double s = 0.0, q = 0.0;
+  for (int n = 0; n < N; ++n) { s += partial[((int64_t)n * C + c) * 2]; q += partial[((int64_t)n * C + c) * 2 + 1]; }
+  const double mean = s / count;
+  double var = q / count - mean * mean;
+  if (var < 0.0) var = 0.0;
+  const float inv = (float)(1.0 / sqrt(var + (double)eps));
+  const float g = gamma ? gamma[c] : 1.0f, b = beta ? beta[c] : 0.0f;
+  scale[c] = g * inv;
+  shift[c] = b - (float)mean * g * inv;
+  if (mean_out) mean_out[c] = (float)mean;
+  if (var_out) var_out[c] = (float)var;
+  if (running_mean) {
+    const double unbiased = count > 1.0 ? var * count / (count - 1.0) : var;
+    running_mean[c] = (1.0f - momentum) * running_mean[c] + momentum * (float)mean;
+    running_var[c] = (1.0f - momentum) * running_var[c] + momentum * (float)unbiased;
+  }
+}
+
+// y = act(x*scale[c] + shift[c]), blocked -> blocked
+__global__ void __launch_bounds__(kT)
+scale_shift_act_c8_kernel(const uint4* __restrict__ x, uint4* __restrict__ y, const float* __restrict__ scale,
+                          const float* __restrict__ shift, int64_t total /*N*C8*HW*/, int C8, int64_t HW, int act) {
+  for (int64_t i = (int64_t)blockIdx.x * kT + threadIdx.x; i < total; i += (int64_t)gridDim.x * kT) {
+    const int c8 = (int)((i / HW) % C8);
+    float f[8];
+    unpack8(__ldcs(x + i), f);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) f[j] = act_fn(f[j] * __ldg(scale + c8 * 8 + j) + __ldg(shift + c8 * 8 + j), act);
+    y[i] = pack8(f);
+  }
+}
+
+inline unsigned grid_for(int64_t total) {
+  return (unsigned)std::min<int64_t>(ceil_div(total, kT), (int64_t)sm_count() * 16);
+}
+
+}  // namespace
+}  // namespace ctl
+
+using namespace ctl;
+
+extern "C" int ctl_nchw_to_c8(const void* x, int x_dtype, int64_t N, int64_t C, int64_t H, int64_t W, void* y,
+                              void* stream) {
+  CTL_REQUIRE(x && y && N > 0 && C > 0 && C % 8 == 0 && H > 0 && W > 0, CTL_ERR_INVALID,
+              "ctl_nchw_to_c8: bad arguments (C must be a multiple of 8)");
+  CTL_REQUIRE(x_dtype == CTL_F32 || x_dtype == CTL_BF16, CTL_ERR_INVALID, "unknown dtype %d", x_dtype);
+  if (sm_count() < 0) return CTL_ERR_CUDA;
+  const int64_t HW = H * W, total = N * (C / 8) * HW;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (x_dtype == CTL_F32)
+    nchw_to_c8_kernel<float><<<grid_for(total), kT, 0, st>>>((const float*)x, (__nv_bfloat16*)y, total, (int)(C / 8), HW);
+  else
+    nchw_to_c8_kernel<__nv_bfloat16><<<grid_for(total), kT, 0, st>>>((const __nv_bfloat16*)x, (__nv_bfloat16*)y, total,
+                                                                     (int)(C / 8), HW);
+  CTL_CUDA_OK(cudaGetLastError(), "nchw_to_c8 launch");
+  return CTL_OK;
+}
+
+extern "C" int ctl_c8_to_nchw(const void* x, int64_t N, int64_t C, int64_t H, int64_t W, void* y, int y_dtype,
+                              void* stream) {
+  CTL_REQUIRE(x && y && N > 0 && C > 0 && C % 8 == 0 && H > 0 && W > 0, CTL_ERR_INVALID,
+              "ctl_c8_to_nchw: bad arguments (C must be a multiple of 8)");
+  CTL_REQUIRE(y_dtype == CTL_F32 || y_dtype == CTL_BF16, CTL_ERR_INVALID, "unknown dtype %d", y_dtype);
+  if (sm_count() < 0) return CTL_ERR_CUDA;
+  const int64_t HW = H * W, total = N * (C / 8) * HW;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (y_dtype == CTL_F32)
+    c8_to_nchw_kernel<float><<<grid_for(total), kT, 0, st>>>((const __nv_bfloat16*)x, (float*)y, total, (int)(C / 8), HW);
+  else
+    c8_to_nchw_kernel<__nv_bfloat16><<<grid_for(total), kT, 0, st>>>((const __nv_bfloat16*)x, (__nv_bfloat16*)y, total,
+                                                                     (int)(C / 8), HW);
+  CTL_CUDA_OK(cudaGetLastError(), "c8_to_nchw launch");
+  return CTL_OK;
+}
+
+extern "C" int ctl_stem_conv3x3_c8(const float* x, const int64_t* labels, int in_mode, float temperature, int64_t N,
+                                   int64_t Cin, int64_t H, int64_t W, const float* weight, int64_t Cout,
+                                   const float* scale, const float* shift, int act, void* y, void* stream) {
+  CTL_REQUIRE(y && weight && N > 0 && H > 0 && W > 0, CTL_ERR_INVALID, "ctl_stem_conv3x3_c8: bad arguments");
+  CTL_REQUIRE(in_mode >= 0 && in_mode <= 2 && (in_mode == 2 ? labels != nullptr : x != nullptr), CTL_ERR_INVALID,
+              "ctl_stem_conv3x3_c8: in_mode %d needs %s", in_mode, in_mode == 2 ? "labels" : "x");
+  CTL_REQUIRE((Cin == 1 || Cin == 4) && Cout == 16, CTL_ERR_UNSUPPORTED,
+              "ctl_stem_conv3x3_c8 handles Cin in {1,4} -> Cout 16 (got %lld -> %lld)", (long long)Cin, (long long)Cout);
+  CTL_REQUIRE(temperature > 0.0f, CTL_ERR_INVALID, "temperature must be positive");
+  if (sm_count() < 0) return CTL_ERR_CUDA;
+  cudaStream_t st = (cudaStream_t)stream;
+  const unsigned grid = grid_for(N * H * W);
+  const long long* lab = reinterpret_cast<const long long*>(labels);
+  if (Cin == 1)
+    stem_conv_kernel<1, 16><<<grid, kT, 0, st>>>(x, lab, weight, scale, shift, (__nv_bfloat16*)y, (int)N, (int)H, (int)W,
+                                                  in_mode, 1.0f / temperature, act);
+  else
+    stem_conv_kernel<4, 16><<<grid, kT, 0, st>>>(x, lab, weight, scale, shift, (__nv_bfloat16*)y, (int)N, (int)H, (int)W,
+                                                  in_mode, 1.0f / temperature, act);
+  CTL_CUDA_OK(cudaGetLastError(), "stem_conv launch");
+  return CTL_OK;
+}
+
+extern "C" int ctl_head_conv1x1_c8(const void* x, int64_t N, int64_t Cin, int64_t H, int64_t W, const float* weight,
+                                   const float* bias, int64_t Cout, int act, float* y, void* stream) {
+  CTL_REQUIRE(x && weight && y && N > 0 && H > 0 && W > 0, CTL_ERR_INVALID, "ctl_head_conv1x1_c8: bad arguments");
+  CTL_REQUIRE(Cin == 16 && Cout >= 1 && Cout <= 4, CTL_ERR_UNSUPPORTED,
+              "ctl_head_conv1x1_c8 handles Cin 16 -> Cout in [1,4] (got %lld -> %lld)", (long long)Cin, (long long)Cout);
+  if (sm_count() < 0) return CTL_ERR_CUDA;
+  head_conv_kernel<16><<<grid_for(N * H * W), kT, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)x, weight, bias, y,
+                                                                           (int)N, H * W, (int)Cout, act);
+  CTL_CUDA_OK(cudaGetLastError(), "head_conv launch");
+  return CTL_OK;
+}
+
+extern "C" int ctl_upsample2x_c8(const void* x, int64_t N, int64_t C, int64_t H, int64_t W, void* y, void* stream) {
+  CTL_REQUIRE(x && y && N > 0 && C > 0 && C % 8 == 0 && H > 0 && W > 0, CTL_ERR_INVALID, "ctl_upsample2x_c8: bad arguments");
+  if (sm_count() < 0) return CTL_ERR_CUDA;
+  const int64_t planes = N * (C / 8);
+  upsample2x_c8_kernel<<<grid_for(planes * H * W), kT, 0, (cudaStream_t)stream>>>((const uint4*)x, (uint4*)y, planes,
+                                                                                (int)H, (int)W);
+  CTL_CUDA_OK(cudaGetLastError(), "upsample2x launch");
+  return CTL_OK;
+}
+
+extern "C" size_t ctl_bn_workspace_bytes(int64_t N, int64_t C) { return (N > 0 && C > 0) ? (size_t)(N * C * 2) * sizeof(double) : 0; }
+
+extern "C" int ctl_bn_batch_affine_c8(const void* x, int64_t N, int64_t C, int64_t H, int64_t W, const float* gamma,
+                                      const float* beta, float eps, void* workspace, float* scale, float* shift,
+                                      float* mean_out, float* var_out, float* running_mean, float* running_var,
+                                      float momentum, void* stream) {
+  CTL_REQUIRE(x && workspace && scale && shift && N > 0 && C > 0 && C % 8 == 0 && H > 0 && W > 0, CTL_ERR_INVALID,
+              "ctl_bn_batch_affine_c8: bad arguments");
+  CTL_REQUIRE((running_mean == nullptr) == (running_var == nullptr), CTL_ERR_INVALID,
+              "running_mean and running_var must be given together");
+  if (sm_count() < 0) return CTL_ERR_CUDA;
+  cudaStream_t st = (cudaStream_t)stream;
+  bn_partial_stats_kernel<<<(unsigned)(N * (C / 8)), kT, 0, st>>>((const __nv_bfloat16*)x, (double*)workspace, (int)(C / 8),
+                                                                 H * W);
+  CTL_CUDA_OK(cudaGetLastError(), "bn_partial_stats launch");
+  bn_finalize_kernel<<<(unsigned)ceil_div(C, 128), 128, 0, st>>>((const double*)workspace, (int)N, (int)C,
+                                                                 (double)(N * H * W), gamma, beta, eps, scale, shift,
+                                                                 mean_out, var_out, running_mean, running_var, momentum);
+  CTL_CUDA_OK(cudaGetLastError(), "bn_finalize launch");
+  return CTL_OK;
+}
+
+extern "C" int ctl_scale_shift_act_c8(const void* x, int64_t N, int64_t C, int64_t H, int64_t W, const float* scale,
+                                      const float* shift, int act, void* y, void* stream) {
+  CTL_REQUIRE(x && y && scale && shift && N > 0 && C > 0 && C % 8 == 0 && H > 0 && W > 0, CTL_ERR_INVALID,
+              "ctl_scale_shift_act_c8: bad arguments");
+  if (sm_count() < 0) return CTL_ERR_CUDA;
+  const int64_t total = N * (C / 8) * H * W;
+  scale_shift_act_c8_kernel<<<grid_for(total), kT, 0, (cudaStream_t)stream>>>((const uint4*)x, (uint4*)y, scale, shift,
+                                                                            total, (int)(C / 8), H * W, act);
+  CTL_CUDA_OK(cudaGetLastError(), "scale_shift_act launch");
+  return CTL_OK;
+}

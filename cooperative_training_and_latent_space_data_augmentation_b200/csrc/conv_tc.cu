@@ -7,22 +7,23 @@
 //   resolution, keep even pixels" (the MMA is far from the bottleneck on these HBM-bound layers),
 //   Cin in {16,32,64,128}, Cout a multiple of 16.
 //
-// Data layout in HBM: activations NHWC bf16 (torch channels_last), weights pre-packed per N tile as
-//   [n_tile][tap][Cin/8][NT][8] bf16 (K-major core matrices, see pack_conv_weight in conv_blocks.py).
+// Data layout in HBM ("blocked", C8): activations are bf16 [N][C/8][H][W][8] -- channels in groups of eight,
+// each group a dense H x W plane of 16-byte pixels.  This is the layout the tensor core consumes: ONE TMA box
+// {8*halo_w, halo_h, C/8, 1} per tile has (halo_w*16)-byte contiguous rows and lands in shared memory as
+// [C/8][halo_h][halo_w][8ch], which is exactly the UMMA no-swizzle K-major canonical layout
+// (LBO = halo_h*halo_w*16, SBO = halo_w*16).  The nine filter taps are nine descriptor START ADDRESSES into
+// the same tile: no im2col copy, every input byte crosses HBM once, and the epilogue's 16-byte stores of
+// consecutive pixels coalesce into 128-byte lines.  Weights are pre-packed per N tile as
+// [n_tile][tap][Cin/8][NT][8] bf16 (K-major core matrices, ops.pack_conv_weight).
 //
 // One CTA = one SM, persistent over output tiles of 16 rows x (8*MT) columns of one image:
-//   warp 0  : TMA producer  -- per tile, Cin/8 box loads [halo_h][halo_w][8ch] (zero-filled halo) into a
-//             ring of STAGES shared-memory buffers laid out [Cin/8][halo_h][halo_w][8ch] (chunks padded to
-//             128 B).  That is the UMMA no-swizzle K-major canonical layout with LBO = chunk stride,
-//             SBO = halo_w*16, so the
-//             nine filter taps are nine descriptor START ADDRESSES into the same tile: no im2col copy,
-//             every input byte crosses HBM once.
+//   warp 0  : TMA producer  -- one box load per tile (zero-filled halo) into a ring of STAGES buffers
 //   warp 1  : MMA issuer    -- one elected thread issues TAPS*Cin/16 tcgen05.mma (M=128, N=NT, K=16) per
 //             8-column M tile into one of two TMEM accumulator stages, then tcgen05.commit frees the
 //             smem stage and publishes the accumulator.
 //   warp 2  : TMEM allocator; warp 3 idle.
 //   warps 4-7: epilogue     -- tcgen05.ld 16 columns at a time, y = act(acc*scale + shift + res*rs + rb),
-//             bf16 pack, 32-byte vector stores to NHWC.
+//             bf16 pack, 16-byte stores (optionally scattered 2x2 for ConvTranspose2d k2 s2).
 #include <algorithm>
 
 #include "ctl_common.cuh"
@@ -45,12 +46,13 @@ struct ConvParams {
   const __nv_bfloat16* w_packed;      // [Cout/NT][TAPS][Cin/8][NT][8]
   const float* scale;                 // [Cout] or nullptr (=1)
   const float* shift;                 // [Cout] or nullptr (=0)
-  const __nv_bfloat16* res;           // NHWC [N,Ho,Wo,Cout] or nullptr
+  const __nv_bfloat16* res;           // blocked [N,Cout/8,Ho,Wo,8] or nullptr
   const float* res_scale;             // [Cout] or nullptr (=1)
   const float* res_shift;             // [Cout] or nullptr (=0)
-  __nv_bfloat16* out;                 // NHWC [N,Ho,Wo,Cout]
+  __nv_bfloat16* out;                 // blocked [N,Cout/8,Ho,Wo,8]  (up2x: [N,Cout/32,2H,2W,8])
   int act;                            // ctl_act
   int subsample;                      // 1: Ho=H, Wo=W; 2: keep even (y,x) -> Ho=H/2, Wo=W/2 (3x3 stride-2 pad-1)
+  int up2x;                           // 1: ConvTranspose2d(k=2,s=2) scatter: GEMM column n = (dy*2+dx)*Cout/4 + co
 };
 
 __device__ __forceinline__ float apply_act(float v, int act) {
@@ -67,10 +69,10 @@ struct ConvCfg {
   static constexpr int kPad = TAPS == 9 ? 1 : 0;
   static constexpr int kHaloH = kTileH + 2 * kPad;
   static constexpr int kHaloW = 8 * MT + 2 * kPad;
-  static constexpr int kChunkBytes = kHaloH * kHaloW * 16;        // one 8-channel chunk of the halo tile (TMA box)
-  static constexpr int kChunkStride = (kChunkBytes + 127) / 128 * 128;   // TMA smem destinations: 128-byte aligned
+  static constexpr int kChunkBytes = kHaloH * kHaloW * 16;        // one 8-channel plane of the halo tile
+  static constexpr int kChunkStride = kChunkBytes;                // the TMA box is written densely
   static constexpr int kStageBytes = (CIN / 8) * kChunkStride;
-  static constexpr int kStageTxBytes = (CIN / 8) * kChunkBytes;   // bytes the TMA loads of one stage deliver
+  static constexpr int kStageTxBytes = kStageBytes;               // bytes the TMA load of one stage delivers
   static constexpr int kWBytes = TAPS * CIN * NT * 2;
   static constexpr int kTmemCols = kAccStages * MT * NT;
   static constexpr int kTmemAlloc = kTmemCols <= 32 ? 32 : kTmemCols <= 64 ? 64 : kTmemCols <= 128 ? 128
@@ -85,6 +87,7 @@ struct ConvCfg {
   static_assert(CIN % 16 == 0 && NT % 16 == 0 && NT <= 256, "UMMA shape");
   static_assert(kSmemBytes <= 227 * 1024, "shared memory budget");
   static_assert((kChunkStride >> 4) < 16384 && kHaloW * 16 < 16384 * 16, "descriptor range");
+  static_assert(kHaloW * 8 <= 256 && kHaloH <= 256 && CIN / 8 <= 256, "TMA box dimensions");
 };
 
 template <int CIN, int NT, int TAPS, int MT, int STAGES>
@@ -145,10 +148,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap, const ConvParams p) {
         const int y0 = ty * kTileH - Cfg::kPad, x0 = tx * (8 * MT) - Cfg::kPad;
         mbar_wait(&empty[stage], phase ^ 1);
         mbar_arrive_expect_tx(&full[stage], Cfg::kStageTxBytes);
-        uint8_t* dst = sA + stage * kStageStride;
-#pragma unroll 1
-        for (int ch = 0; ch < CIN / 8; ++ch)
-          tma_load_4d(dst + ch * Cfg::kChunkStride, &tmap, &full[stage], ch * 8, x0, y0, img);
+        tma_load_4d(sA + stage * kStageStride, &tmap, &full[stage], x0 * 8, y0, 0, img);
         if (++stage == STAGES) { stage = 0; phase ^= 1; }
       }
     }
@@ -209,9 +209,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap, const ConvParams p) {
         bool valid = y < p.H && x < p.W;
         int yo = y, xo = x;
         if (p.subsample == 2) { valid = valid && !((y | x) & 1); yo = y >> 1; xo = x >> 1; }
-        const int64_t pix = ((int64_t)img * Ho + yo) * Wo + xo;
-        __nv_bfloat16* optr = p.out + pix * p.Cout + n0;
-        const __nv_bfloat16* rptr = p.res ? p.res + pix * p.Cout + n0 : nullptr;
+        const int64_t plane = (int64_t)Ho * Wo * 8;                          // elements per 8-channel plane
+        const int64_t pix8 = ((int64_t)yo * Wo + xo) * 8;
         const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)((acc * MT + mt) * NT);
 #pragma unroll 1
         for (int c0 = 0; c0 < NT; c0 += 16) {
@@ -222,25 +221,38 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap, const ConvParams p) {
             float f[16];
 #pragma unroll
             for (int i = 0; i < 16; ++i) f[i] = __uint_as_float(v[i]) * sVec[c0 + i] + sVec[NT + c0 + i];
-            if (rptr) {
-              const uint4 r0 = *reinterpret_cast<const uint4*>(rptr + c0);
-              const uint4 r1 = *reinterpret_cast<const uint4*>(rptr + c0 + 8);
-              const uint32_t rw[8] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w};
 #pragma unroll
-              for (int i = 0; i < 8; ++i) {
-                f[2 * i] += __uint_as_float(rw[i] << 16) * sVec[2 * NT + c0 + 2 * i] + sVec[3 * NT + c0 + 2 * i];
-                f[2 * i + 1] += __uint_as_float(rw[i] & 0xffff0000u) * sVec[2 * NT + c0 + 2 * i + 1] +
-                                sVec[3 * NT + c0 + 2 * i + 1];
+            for (int h8 = 0; h8 < 2; ++h8) {                 // two 8-channel planes per 16 accumulator columns
+              const int n = n0 + c0 + 8 * h8;                // GEMM column of this plane's first channel
+              int64_t off;
+              if (p.up2x) {
+                const int cq = p.Cout >> 2, qd = n / cq, co = n - qd * cq;   // n = (dy*2+dx)*Cout/4 + co
+                const int y2 = 2 * y + (qd >> 1), x2 = 2 * x + (qd & 1);
+                off = ((int64_t)img * (cq >> 3) + (co >> 3)) * (plane * 4) + ((int64_t)y2 * (2 * Wo) + x2) * 8;
+              } else {
+                off = ((int64_t)img * (p.Cout >> 3) + (n >> 3)) * plane + pix8;
               }
-            }
-            uint32_t o[8];
+              float* g = f + 8 * h8;
+              if (p.res) {
+                const uint4 r = *reinterpret_cast<const uint4*>(p.res + off);
+                const uint32_t rw[4] = {r.x, r.y, r.z, r.w};
+                const float* rsc = sVec + 2 * NT + c0 + 8 * h8;
+                const float* rsh = sVec + 3 * NT + c0 + 8 * h8;
 #pragma unroll
-            for (int i = 0; i < 8; ++i) {
-              const __nv_bfloat162 h = __floats2bfloat162_rn(apply_act(f[2 * i], p.act), apply_act(f[2 * i + 1], p.act));
-              o[i] = *reinterpret_cast<const uint32_t*>(&h);
+                for (int i = 0; i < 4; ++i) {
+                  g[2 * i] += __uint_as_float(rw[i] << 16) * rsc[2 * i] + rsh[2 * i];
+                  g[2 * i + 1] += __uint_as_float(rw[i] & 0xffff0000u) * rsc[2 * i + 1] + rsh[2 * i + 1];
+                }
+              }
+              uint32_t o[4];
+#pragma unroll
+              for (int i = 0; i < 4; ++i) {
+                const __nv_bfloat162 hh =
+                    __floats2bfloat162_rn(apply_act(g[2 * i], p.act), apply_act(g[2 * i + 1], p.act));
+                o[i] = *reinterpret_cast<const uint32_t*>(&hh);
+              }
+              *reinterpret_cast<uint4*>(p.out + off) = make_uint4(o[0], o[1], o[2], o[3]);
             }
-            *reinterpret_cast<uint4*>(optr + c0) = make_uint4(o[0], o[1], o[2], o[3]);
-            *reinterpret_cast<uint4*>(optr + c0 + 8) = make_uint4(o[4], o[5], o[6], o[7]);
           }
         }
       }
@@ -277,13 +289,14 @@ EncodeTiledFn encode_tiled_fn() {
   return fn;
 }
 
-// NHWC bf16 activation [N,H,W,C] as a 4-D tensor map (C, W, H, N) with box (8, halo_w, halo_h, 1).
+// Blocked bf16 activation [N][C/8][H][W][8] as a 4-D tensor map (W*8, H, C/8, N) with box
+// (halo_w*8, halo_h, C/8, 1): the whole halo tile of all channel planes in one bulk tensor copy.
 int make_act_tmap(CUtensorMap* m, const void* x, int N, int H, int W, int C, int halo_w, int halo_h) {
   EncodeTiledFn enc = encode_tiled_fn();
   CTL_REQUIRE(enc != nullptr, CTL_ERR_CUDA, "cuTensorMapEncodeTiled is not available from the driver");
-  const cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)N};
-  const cuuint64_t strides[3] = {(cuuint64_t)C * 2, (cuuint64_t)W * C * 2, (cuuint64_t)H * W * C * 2};
-  const cuuint32_t box[4] = {8, (cuuint32_t)halo_w, (cuuint32_t)halo_h, 1};
+  const cuuint64_t dims[4] = {(cuuint64_t)W * 8, (cuuint64_t)H, (cuuint64_t)(C / 8), (cuuint64_t)N};
+  const cuuint64_t strides[3] = {(cuuint64_t)W * 16, (cuuint64_t)H * W * 16, (cuuint64_t)(C / 8) * H * W * 16};
+  const cuuint32_t box[4] = {(cuuint32_t)halo_w * 8, (cuuint32_t)halo_h, (cuuint32_t)(C / 8), 1};
   const cuuint32_t estr[4] = {1, 1, 1, 1};
   const CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(x), dims, strides, box, estr,
                          CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
@@ -332,7 +345,7 @@ int dispatch_nt(const void* x, const ConvParams& p, int nt, cudaStream_t st) {
     if (nt == 32) return launch_conv<128, 32, TAPS, 1, 2>(x, p, st);
     if (nt == 64) return launch_conv<128, 64, TAPS, 1, TAPS == 9 ? 1 : 2>(x, p, st);
   }
-  set_error("ctl_conv2d_nhwc_bf16: no kernel for Cin=%d, n_tile=%d", CIN, nt);
+  set_error("ctl_conv2d_c8_bf16: no kernel for Cin=%d, n_tile=%d", CIN, nt);
   return CTL_ERR_UNSUPPORTED;
 }
 
@@ -351,30 +364,32 @@ extern "C" int ctl_conv2d_n_tile(int Cin, int Cout, int taps) {
   return -1;
 }
 
-extern "C" int ctl_conv2d_nhwc_bf16(const void* x, int64_t N, int64_t H, int64_t W, int64_t Cin, const void* w_packed,
-                                    int64_t Cout, int taps, int subsample, const float* scale, const float* shift,
-                                    const void* res, const float* res_scale, const float* res_shift, int act,
-                                    void* out, void* stream) {
-  CTL_REQUIRE(x && w_packed && out, CTL_ERR_INVALID, "ctl_conv2d_nhwc_bf16: NULL pointer");
+extern "C" int ctl_conv2d_c8_bf16(const void* x, int64_t N, int64_t H, int64_t W, int64_t Cin, const void* w_packed,
+                                  int64_t Cout, int taps, int subsample, int up2x, const float* scale,
+                                  const float* shift, const void* res, const float* res_scale, const float* res_shift,
+                                  int act, void* out, void* stream) {
+  CTL_REQUIRE(x && w_packed && out, CTL_ERR_INVALID, "ctl_conv2d_c8_bf16: NULL pointer");
+  CTL_REQUIRE(!up2x || (taps == 1 && subsample == 1 && Cout % 32 == 0), CTL_ERR_INVALID,
+              "up2x (ConvTranspose2d k2 s2) needs taps == 1, subsample == 1 and Cout = 4 * out_channels, out_channels %% 8 == 0");
   CTL_REQUIRE(N > 0 && H > 0 && W > 0 && N <= 65535 && H <= 32768 && W <= 32768, CTL_ERR_INVALID,
-              "ctl_conv2d_nhwc_bf16: bad shape N=%lld H=%lld W=%lld", (long long)N, (long long)H, (long long)W);
+              "ctl_conv2d_c8_bf16: bad shape N=%lld H=%lld W=%lld", (long long)N, (long long)H, (long long)W);
   CTL_REQUIRE(taps == 1 || taps == 9, CTL_ERR_INVALID, "taps must be 1 (1x1) or 9 (3x3 pad 1), got %d", taps);
   CTL_REQUIRE(subsample == 1 || (subsample == 2 && H % 2 == 0 && W % 2 == 0), CTL_ERR_INVALID,
               "subsample must be 1, or 2 with even H and W");
   CTL_REQUIRE(act >= CTL_ACT_NONE && act <= CTL_ACT_SIGMOID, CTL_ERR_INVALID, "unknown activation %d", act);
   const int nt = ctl_conv2d_n_tile((int)Cin, (int)Cout, taps);
   CTL_REQUIRE(nt > 0, CTL_ERR_UNSUPPORTED,
-              "ctl_conv2d_nhwc_bf16 handles Cin in {16,32,64,128} and Cout %% 16 == 0 (got Cin=%lld Cout=%lld)",
+              "ctl_conv2d_c8_bf16 handles Cin in {16,32,64,128} and Cout %% 16 == 0 (got Cin=%lld Cout=%lld)",
               (long long)Cin, (long long)Cout);
   CTL_REQUIRE(aligned16(x) && aligned16(w_packed) && aligned16(out) && (!res || aligned16(res)), CTL_ERR_INVALID,
-              "ctl_conv2d_nhwc_bf16: pointers must be 16-byte aligned");
+              "ctl_conv2d_c8_bf16: pointers must be 16-byte aligned");
   if (sm_count() < 0) return CTL_ERR_CUDA;
   ConvParams p = {};
   p.N = (int)N; p.H = (int)H; p.W = (int)W; p.Cout = (int)Cout;
   p.w_packed = (const __nv_bfloat16*)w_packed;
   p.scale = scale; p.shift = shift;
   p.res = (const __nv_bfloat16*)res; p.res_scale = res_scale; p.res_shift = res_shift;
-  p.out = (__nv_bfloat16*)out; p.act = act; p.subsample = subsample;
+  p.out = (__nv_bfloat16*)out; p.act = act; p.subsample = subsample; p.up2x = up2x;
   cudaStream_t st = (cudaStream_t)stream;
   if (taps == 9) {
     switch ((int)Cin) {

@@ -1,0 +1,163 @@
+"""No-grad forward of the reference-shaped FTN/STN modules (networks.py) entirely in this build's kernels:
+K3 (tcgen05 implicit-GEMM conv, conv_tc.cu) + the C8 streaming kernels (c8_ops.cu).  Activations stay in
+the blocked C8 layout between layers; only module inputs/outputs are planar NCHW (the image, the logits,
+and the latent codes that the masking API exposes).
+
+BatchNorm handling (`bn` argument):
+  'eval'   running statistics folded into the conv epilogue (inference; reference: module.eval())
+  'batch'  batch statistics, running stats untouched (reference: train mode inside _disable_tracking_bn_stats,
+           e.g. decoder_inference(..., disable_track_bn_stats=True), advanced...model.py:396-412)
+  'track'  batch statistics + momentum update of running_mean/var and num_batches_tracked (plain train mode)
+
+Kernel sequence of one residual block on the resampled input x' (encoder_decoder.py:54-57, :334-337):
+  eval : y1 = K3(x', W1, BN1-folded, LReLU); y2 = K3(y1, W2, BN2-folded); out = K3_1x1(x', Win, +y2, LReLU)
+  batch: y1 = K3(x', W1, +b1) -> stats -> scale/shift+LReLU (in place) ; y2 = K3(y1, W2, +b2) -> stats ->
+         out = K3_1x1(x', Win, + BN2(y2) as the epilogue's residual affine, LReLU)
+"""
+import torch
+import torch.nn as nn
+
+from . import ops
+
+_PACKED = {}
+
+
+def _packed(param, fn):
+    """Packed bf16 copy of a weight, rebuilt when the parameter is modified in place (optimizer step) or replaced."""
+    key = id(param)
+    ver = (param.data_ptr(), param._version)
+    hit = _PACKED.get(key)
+    if hit is None or hit[0] != ver:
+        hit = (ver, fn(param))
+        _PACKED[key] = hit
+    return hit[1]
+
+
+def _act_code(module):
+    if module is None:
+        return ops.ACT_NONE
+    if isinstance(module, nn.LeakyReLU):
+        return ops.ACT_LRELU
+    if isinstance(module, nn.ReLU):
+        return ops.ACT_RELU
+    if isinstance(module, nn.Sigmoid):
+        return ops.ACT_SIGMOID
+    raise NotImplementedError("activation %r has no fused epilogue" % (module,))
+
+
+def _fold_eval(conv, bn):
+    """conv bias + eval-mode BN -> per-channel (scale, shift)."""
+    scale = bn.weight.detach() * torch.rsqrt(bn.running_var + bn.eps)
+    shift = bn.bias.detach() + (conv.bias.detach() - bn.running_mean) * scale
+    return scale, shift
+
+
+def _bn_batch(bn, y_raw, mode):
+    track = mode == 'track' and bn.track_running_stats
+    scale, shift = ops.bn_batch_affine_c8(y_raw, bn.weight, bn.bias, bn.eps,
+                                          bn.running_mean if track else None, bn.running_var if track else None,
+                                          bn.momentum if bn.momentum is not None else 0.1)
+    if track:
+        bn.num_batches_tracked += 1
+    return scale, shift
+
+
+def _conv(conv, x, **kw):
+    k = conv.kernel_size[0]
+    sub = conv.stride[0]
+    wp = _packed(conv.weight, ops.pack_conv_weight)
+    return ops.conv2d_c8(x, wp, conv.out_channels, k * k, subsample=sub, **kw)
+
+
+def conv_bn_act(conv, bn, x, act, mode):
+    """K3 conv + BatchNorm + activation on a C8 tensor."""
+    if mode == 'eval':
+        scale, shift = _fold_eval(conv, bn)
+        return _conv(conv, x, scale=scale, shift=shift, act=act)
+    y = _conv(conv, x, shift=conv.bias)
+    scale, shift = _bn_batch(bn, y, mode)
+    return ops.scale_shift_act_c8(y, scale, shift, act, inplace=True)
+
+
+def double_conv(seq, x, mode, final_act=ops.ACT_NONE):
+    y = conv_bn_act(seq[0], seq[1], x, ops.ACT_LRELU, mode)
+    return conv_bn_act(seq[3], seq[4], y, final_act, mode)
+
+
+def residual_block(block, xr, mode):
+    """xr: resampled input (C8).  out = LReLU(conv_input(xr) + BN2(conv2(LReLU(BN1(conv1(xr))))))."""
+    seq = block.conv
+    y1 = conv_bn_act(seq[0], seq[1], xr, ops.ACT_LRELU, mode)
+    if mode == 'eval':
+        s2, t2 = _fold_eval(seq[3], seq[4])
+        y2 = _conv(seq[3], y1, scale=s2, shift=t2)
+        return _conv(block.conv_input, xr, shift=block.conv_input.bias, res=y2, act=ops.ACT_LRELU)
+    y2 = _conv(seq[3], y1, shift=seq[3].bias)
+    s2, t2 = _bn_batch(seq[4], y2, mode)
+    return _conv(block.conv_input, xr, shift=block.conv_input.bias, res=y2, res_scale=s2, res_shift=t2,
+                 act=ops.ACT_LRELU)
+
+
+def down_block(block, x, mode):
+    xd = _conv(block.down, x, shift=block.down.bias)            # 3x3 stride 2: subsample inferred from conv.stride
+    return residual_block(block, xd, mode)
+
+
+def up_block(block, x, mode):
+    if block.up_type == 'NN':
+        xu = ops.upsample2x_c8(x)
+    else:
+        up = block.up
+        wp = _packed(up.weight, ops.pack_convtranspose2x2_weight)
+        xu = ops.conv2d_c8(x, wp, 4 * up.out_channels, 1, up2x=True, shift=up.bias.detach().repeat(4))
+    return residual_block(block, xu, mode)
+
+
+def encoder_forward(enc, x, mode, in_mode=0, temperature=1.0):
+    """MyEncoder on planar input (fp32 image / logits, or an int64 label map with in_mode=2) -> C8 latent."""
+    inc = enc.inc
+    if mode == 'eval':
+        s0, t0 = _fold_eval(inc[0], inc[1])
+        y = ops.stem_conv_c8(x, inc[0].weight, s0, t0, ops.ACT_LRELU, in_mode, temperature)
+    else:
+        y = ops.stem_conv_c8(x, inc[0].weight, None, inc[0].bias, ops.ACT_NONE, in_mode, temperature)
+        s0, t0 = _bn_batch(inc[1], y, mode)
+        y = ops.scale_shift_act_c8(y, s0, t0, ops.ACT_LRELU, inplace=True)
+    y = conv_bn_act(inc[3], inc[4], y, ops.ACT_LRELU, mode)     # BN then F.leaky_relu (encoder_decoder.py:405)
+    for blk in (enc.down1, enc.down2, enc.down3, enc.down4):
+        y = down_block(blk, y, mode)
+    return conv_bn_act(enc.final_conv[0], enc.final_conv[1], y, _act_code(enc.act), mode)
+
+
+def filter_code(dual, z_c8, mode):
+    seq = dual.code_decoupler
+    return double_conv(seq, z_c8, mode, final_act=_act_code(seq[5]))
+
+
+def decoder_forward(dec, z_c8, mode):
+    """MyDecoder on a C8 latent -> planar fp32 [N,Cout,H,W] (logits, or the sigmoid image)."""
+    y = z_c8
+    for blk in (dec.up1, dec.up2, dec.up3, dec.up4):
+        y = up_block(blk, y, mode)
+    return ops.head_conv_c8(y, dec.final_conv.weight, dec.final_conv.bias, _act_code(dec.last_act))
+
+
+def decoder_from_nchw(dec, z, mode):
+    with torch.no_grad():
+        return decoder_forward(dec, ops.nchw_to_c8(z), mode)
+
+
+def ftn_forward(dual, seg_dec, image, mode):
+    """Dual_Branch_Encoder + segmentation decoder: image -> (z_i, z_s) as fp32 NCHW, logits."""
+    with torch.no_grad():
+        z_i = encoder_forward(dual.general_encoder, image, mode)
+        z_s = filter_code(dual, z_i, mode)
+        logits = decoder_forward(seg_dec, z_s, mode)
+        return ops.c8_to_nchw(z_i), ops.c8_to_nchw(z_s), logits
+
+
+def stn_forward(shape_enc, shape_dec, seg, mode, is_label_map=False, temperature=2.0):
+    """recon_shape: construct_input fused into the stem (softmax(logit/T) or one-hot) -> Es -> Dsh -> logits."""
+    with torch.no_grad():
+        z = encoder_forward(shape_enc, seg, mode, in_mode=2 if is_label_map else 1, temperature=temperature)
+        return decoder_forward(shape_dec, z, mode)

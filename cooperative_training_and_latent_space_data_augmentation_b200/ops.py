@@ -167,9 +167,27 @@ def philox_uniform(seed, offset, first_index, count, device="cuda"):
 # ------------------------------------------------------------------------------------------------ K3: conv blocks
 ACT_NONE, ACT_LRELU, ACT_RELU, ACT_SIGMOID = _lib.ACT_NONE, _lib.ACT_LRELU, _lib.ACT_RELU, _lib.ACT_SIGMOID
 
+# Blocked activation layout "C8": a bf16 tensor of shape [N, C/8, H, W, 8] (contiguous).  See DESIGN.md section 3.
+
+
+def _c8_dims(x):
+    if x.dim() != 5 or x.shape[-1] != 8 or x.dtype != torch.bfloat16 or not x.is_contiguous():
+        raise ValueError("expected a contiguous bf16 C8 tensor [N, C/8, H, W, 8], got %s %s" % (tuple(x.shape), x.dtype))
+    N, C8, H, W, _ = x.shape
+    return N, C8 * 8, H, W
+
+
+def _vec(v, n):
+    if v is None:
+        return None
+    v = v.detach().to(torch.float32).contiguous()
+    if v.numel() != n:
+        raise ValueError("per-channel vector must have %d elements, got %d" % (n, v.numel()))
+    return v
+
 
 def conv_supported(cin, cout, kernel_size):
-    """True when ctl_conv2d_nhwc_bf16 has a tensor-core kernel for this layer class."""
+    """True when ctl_conv2d_c8_bf16 has a tensor-core kernel for this layer class."""
     taps = kernel_size * kernel_size
     return taps in (1, 9) and _lib.load().ctl_conv2d_n_tile(int(cin), int(cout), taps) > 0
 
@@ -186,34 +204,125 @@ def pack_conv_weight(weight):
     return w.permute(3, 0, 1, 4, 2).contiguous()
 
 
-def _channels_last_bf16(x):
-    if x.dtype != torch.bfloat16:
-        x = x.to(torch.bfloat16)
-    return x.contiguous(memory_format=torch.channels_last)
+def pack_convtranspose2x2_weight(weight):
+    """ConvTranspose2d(k=2, s=2) weight [Cin, Cout, 2, 2] -> the 1x1 GEMM weight [4*Cout, Cin, 1, 1] with rows
+    ordered (dy*2+dx)*Cout + co, packed for ctl_conv2d_c8_bf16(up2x=1)."""
+    cin, cout, kh, kw = weight.shape
+    if (kh, kw) != (2, 2):
+        raise NotImplementedError("only kernel 2 / stride 2 transposed convolutions are on the hot path")
+    w = weight.detach().permute(2, 3, 1, 0).reshape(4 * cout, cin, 1, 1)
+    return pack_conv_weight(w)
 
 
-def conv2d_bf16(x, w_packed, cout, taps, subsample=1, scale=None, shift=None, res=None, res_scale=None, res_shift=None,
-                act=ACT_NONE):
-    """out = act(conv(x) * scale + shift + res * res_scale + res_shift) on the tcgen05 kernel.
-    x / res / out: logical [N,C,H,W] bf16 tensors in channels_last memory format (NHWC in HBM)."""
+def conv2d_c8(x, w_packed, cout, taps, subsample=1, up2x=False, scale=None, shift=None, res=None, res_scale=None,
+              res_shift=None, act=ACT_NONE):
+    """out = act(conv(x) * scale + shift + res * res_scale + res_shift) on the tcgen05 kernel; C8 in, C8 out.
+    `cout` is the number of GEMM columns (4 * out_channels when up2x)."""
     _need_cuda(x, w_packed, scale, shift, res, res_scale, res_shift)
-    x = _channels_last_bf16(x)
-    N, cin, H, W = x.shape
-    Ho, Wo = H // subsample, W // subsample
-    out = torch.empty((N, cout, Ho, Wo), device=x.device, dtype=torch.bfloat16, memory_format=torch.channels_last)
-    if res is not None:
-        res = _channels_last_bf16(res)
-        if tuple(res.shape) != tuple(out.shape):
-            raise ValueError("res must have the output shape %s" % (tuple(out.shape),))
-    vecs = []
-    for v in (scale, shift, res_scale, res_shift):
-        if v is not None:
-            v = v.to(torch.float32).contiguous()
-            if v.numel() != cout:
-                raise ValueError("per-channel vectors must have Cout=%d elements" % cout)
-        vecs.append(v)
+    N, cin, H, W = _c8_dims(x)
+    if up2x:
+        out = torch.empty((N, cout // 32, 2 * H, 2 * W, 8), device=x.device, dtype=torch.bfloat16)
+    else:
+        out = torch.empty((N, cout // 8, H // subsample, W // subsample, 8), device=x.device, dtype=torch.bfloat16)
+    if res is not None and (tuple(res.shape) != tuple(out.shape) or res.dtype != torch.bfloat16 or not res.is_contiguous()):
+        raise ValueError("res must be a contiguous bf16 C8 tensor of the output shape %s" % (tuple(out.shape),))
+    sc, sh, rs, rb = _vec(scale, cout), _vec(shift, cout), _vec(res_scale, cout), _vec(res_shift, cout)
     with torch.cuda.device(x.device):
-        _lib.check(_lib.load().ctl_conv2d_nhwc_bf16(
-            x.data_ptr(), N, H, W, cin, w_packed.data_ptr(), cout, taps, subsample, _ptr(vecs[0]), _ptr(vecs[1]),
-            _ptr(res), _ptr(vecs[2]), _ptr(vecs[3]), act, out.data_ptr(), _stream()))
+        _lib.check(_lib.load().ctl_conv2d_c8_bf16(
+            x.data_ptr(), N, H, W, cin, w_packed.data_ptr(), cout, taps, subsample, int(bool(up2x)), _ptr(sc), _ptr(sh),
+            _ptr(res), _ptr(rs), _ptr(rb), act, out.data_ptr(), _stream()))
     return out
+
+
+def nchw_to_c8(x):
+    _need_cuda(x)
+    x = x.contiguous()
+    N, C, H, W = x.shape
+    y = torch.empty((N, C // 8, H, W, 8), device=x.device, dtype=torch.bfloat16)
+    with torch.cuda.device(x.device):
+        _lib.check(_lib.load().ctl_nchw_to_c8(x.data_ptr(), _dtype(x), N, C, H, W, y.data_ptr(), _stream()))
+    return y
+
+
+def c8_to_nchw(x, dtype=torch.float32):
+    _need_cuda(x)
+    N, C, H, W = _c8_dims(x)
+    y = torch.empty((N, C, H, W), device=x.device, dtype=dtype)
+    with torch.cuda.device(x.device):
+        _lib.check(_lib.load().ctl_c8_to_nchw(x.data_ptr(), N, C, H, W, y.data_ptr(), _DTYPES[dtype], _stream()))
+    return y
+
+
+def stem_conv_c8(x, weight, scale=None, shift=None, act=ACT_NONE, in_mode=0, temperature=1.0):
+    """3x3 pad-1 stem from planar fp32 [N,Cin,H,W] (in_mode 0/1) or an int64 label map [N,H,W] (in_mode 2)."""
+    _need_cuda(x, weight)
+    cout, cin = weight.shape[0], weight.shape[1]
+    if in_mode == 2:
+        lab = x.contiguous()
+        if lab.dtype != torch.int64 or lab.dim() != 3:
+            raise ValueError("in_mode 2 expects an int64 label map [N,H,W]")
+        N, H, W = lab.shape
+        xp, lp = 0, lab.data_ptr()
+    else:
+        xf = x.to(torch.float32).contiguous()
+        N, c, H, W = xf.shape
+        if c != cin:
+            raise ValueError("input has %d channels, weight expects %d" % (c, cin))
+        xp, lp = xf.data_ptr(), 0
+    w = weight.detach().to(torch.float32).contiguous()
+    y = torch.empty((N, cout // 8, H, W, 8), device=weight.device, dtype=torch.bfloat16)
+    sc, sh = _vec(scale, cout), _vec(shift, cout)
+    with torch.cuda.device(weight.device):
+        _lib.check(_lib.load().ctl_stem_conv3x3_c8(xp, lp, in_mode, float(temperature), N, cin, H, W, w.data_ptr(), cout,
+                                                   _ptr(sc), _ptr(sh), act, y.data_ptr(), _stream()))
+    return y
+
+
+def head_conv_c8(x, weight, bias=None, act=ACT_NONE):
+    """1x1 head from a 16-channel C8 tensor to planar fp32 [N,Cout,H,W] (Cout <= 4)."""
+    _need_cuda(x, weight, bias)
+    N, cin, H, W = _c8_dims(x)
+    cout = weight.shape[0]
+    w = weight.detach().to(torch.float32).reshape(cout, cin).contiguous()
+    b = _vec(bias, cout)
+    y = torch.empty((N, cout, H, W), device=x.device, dtype=torch.float32)
+    with torch.cuda.device(x.device):
+        _lib.check(_lib.load().ctl_head_conv1x1_c8(x.data_ptr(), N, cin, H, W, w.data_ptr(), _ptr(b), cout, act,
+                                                   y.data_ptr(), _stream()))
+    return y
+
+
+def upsample2x_c8(x):
+    _need_cuda(x)
+    N, C, H, W = _c8_dims(x)
+    y = torch.empty((N, C // 8, 2 * H, 2 * W, 8), device=x.device, dtype=torch.bfloat16)
+    with torch.cuda.device(x.device):
+        _lib.check(_lib.load().ctl_upsample2x_c8(x.data_ptr(), N, C, H, W, y.data_ptr(), _stream()))
+    return y
+
+
+def bn_batch_affine_c8(x, gamma, beta, eps, running_mean=None, running_var=None, momentum=0.1):
+    """Batch statistics of a C8 tensor folded into (scale, shift); updates the running statistics in place when
+    they are given (pass None to reproduce _disable_tracking_bn_stats)."""
+    _need_cuda(x, gamma, beta, running_mean, running_var)
+    N, C, H, W = _c8_dims(x)
+    ws = torch.empty(_lib.load().ctl_bn_workspace_bytes(N, C), device=x.device, dtype=torch.uint8)
+    scale = torch.empty(C, device=x.device, dtype=torch.float32)
+    shift = torch.empty(C, device=x.device, dtype=torch.float32)
+    g, b = _vec(gamma, C), _vec(beta, C)
+    with torch.cuda.device(x.device):
+        _lib.check(_lib.load().ctl_bn_batch_affine_c8(
+            x.data_ptr(), N, C, H, W, _ptr(g), _ptr(b), float(eps), ws.data_ptr(), scale.data_ptr(), shift.data_ptr(), 0, 0,
+            _ptr(running_mean), _ptr(running_var), float(momentum), _stream()))
+    return scale, shift
+
+
+def scale_shift_act_c8(x, scale, shift, act=ACT_NONE, inplace=False):
+    _need_cuda(x, scale, shift)
+    N, C, H, W = _c8_dims(x)
+    y = x if inplace else torch.empty_like(x)
+    sc, sh = _vec(scale, C), _vec(shift, C)
+    with torch.cuda.device(x.device):
+        _lib.check(_lib.load().ctl_scale_shift_act_c8(x.data_ptr(), N, C, H, W, sc.data_ptr(), sh.data_ptr(), act,
+                                                      y.data_ptr(), _stream()))
+    return y

@@ -102,25 +102,61 @@ int ctl_philox_uniform(uint64_t seed, uint64_t offset, uint64_t first_index, int
 
 /* ---------------------------------------------------------------------------------------------
  * K3 -- conv blocks of the FTN/STN encoders/decoders as bf16 implicit GEMM on tcgen05 tensor cores
- * (TMA-fed, TMEM accumulators).  Replaces the nn.Conv2d + BatchNorm2d(eval / folded) + LeakyReLU(0.2) |
- * ReLU | Sigmoid + residual-add sequences of
+ * (TMA-fed, TMEM accumulators).  Replaces the nn.Conv2d / ConvTranspose2d(k2,s2) + BatchNorm2d (folded:
+ * eval running statistics, or batch statistics computed by ctl_bn_batch_affine_c8) + LeakyReLU(0.2) | ReLU |
+ * Sigmoid + residual-add sequences of
  *   res_convdown   medseg/models/ebm/encoder_decoder.py:19-68
  *   res_up_family  medseg/models/ebm/encoder_decoder.py:285-348
  *   MyEncoder / MyDecoder / Dual_Branch_Encoder  :351-415, :418-453, :456-503
- * x: NHWC bf16 [N,H,W,Cin] (torch channels_last).  taps = 9: 3x3, padding 1; taps = 1: 1x1.
- * subsample = 2 gives the 3x3 stride-2 padding-1 convolution of `down` (output [N,H/2,W/2,Cout]).
+ *
+ * Activation layout "C8": bf16 [N][C/8][H][W][8] (channels in groups of eight, each group a dense plane of
+ * 16-byte pixels) -- one TMA box per tile lands in shared memory in the UMMA canonical layout.
+ * taps = 9: 3x3, padding 1; taps = 1: 1x1.  subsample = 2: the 3x3 stride-2 padding-1 convolution of `down`
+ * (output H/2 x W/2).  up2x = 1 (taps 1): ConvTranspose2d(kernel 2, stride 2): Cout = 4*out_channels GEMM
+ * columns ordered (dy*2+dx)*out_channels + co, scattered to output pixel (2y+dy, 2x+dx) of [N][oc/8][2H][2W][8].
  * w_packed: bf16 [Cout/NT][taps][Cin/8][NT][8] with NT = ctl_conv2d_n_tile(Cin, Cout, taps), element
  *           (t, tap, q, n, j) = weight[t*NT + n][q*8 + j][tap/3][tap%3].
- * out = act( conv(x) * scale[c] + shift[c] + (res * res_scale[c] + res_shift[c]) ), bf16 NHWC; scale/shift
- * fold the conv bias and an eval-mode (or precomputed batch-statistics) BatchNorm; res (same shape as out)
- * and every per-channel vector may be NULL (identity).  Cin in {16,32,64,128}, Cout %% 16 == 0.
+ * out = act( conv(x) * scale[c] + shift[c] + (res * res_scale[c] + res_shift[c]) ); res has the output's shape
+ * and layout; res and every per-GEMM-column fp32 vector may be NULL (identity).
+ * Cin in {16,32,64,128}, Cout %% 16 == 0.
  */
 int ctl_conv2d_n_tile(int Cin, int Cout, int taps);
-int ctl_conv2d_nhwc_bf16(const void* x, int64_t N, int64_t H, int64_t W, int64_t Cin,
-                         const void* w_packed, int64_t Cout, int taps, int subsample,
-                         const float* scale, const float* shift, const void* res,
-                         const float* res_scale, const float* res_shift, int act, void* out,
-                         void* stream);
+int ctl_conv2d_c8_bf16(const void* x, int64_t N, int64_t H, int64_t W, int64_t Cin, const void* w_packed,
+                       int64_t Cout, int taps, int subsample, int up2x, const float* scale,
+                       const float* shift, const void* res, const float* res_scale,
+                       const float* res_shift, int act, void* out, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * CUDA-core kernels around K3 (all HBM-bound streaming passes over C8 tensors).
+ */
+/* NCHW (fp32 | bf16) <-> C8 bf16; C %% 8 == 0.  Used for the latent codes, which the masking API holds in NCHW. */
+int ctl_nchw_to_c8(const void* x, int x_dtype, int64_t N, int64_t C, int64_t H, int64_t W, void* y, void* stream);
+int ctl_c8_to_nchw(const void* x, int64_t N, int64_t C, int64_t H, int64_t W, void* y, int y_dtype, void* stream);
+/* Stem: 3x3 pad-1 conv from a planar fp32 NCHW input with Cin in {1,4} to 16 C8 channels, y = act(acc*scale+shift)
+ * (MyEncoder.inc[0] + norm + LeakyReLU, encoder_decoder.py:370-378).  in_mode 0: x as is; 1: softmax(x/temperature)
+ * over the Cin channels; 2: one-hot of the int64 label map `labels` [N,H,W] -- modes 1/2 fuse construct_input
+ * (basic_operations.py:110-158) into the first STN convolution.  weight: fp32 [16][Cin][3][3]. */
+int ctl_stem_conv3x3_c8(const float* x, const int64_t* labels, int in_mode, float temperature, int64_t N,
+                        int64_t Cin, int64_t H, int64_t W, const float* weight, int64_t Cout,
+                        const float* scale, const float* shift, int act, void* y, void* stream);
+/* Head: 1x1 conv from 16 C8 channels to Cout in [1,4] planar fp32 NCHW (+ bias, optional sigmoid)
+ * (MyDecoder.final_conv + last_act, encoder_decoder.py:439-452).  weight: fp32 [Cout][16]. */
+int ctl_head_conv1x1_c8(const void* x, int64_t N, int64_t Cin, int64_t H, int64_t W, const float* weight,
+                        const float* bias, int64_t Cout, int act, float* y, void* stream);
+/* nn.UpsamplingNearest2d(scale_factor=2) on a C8 tensor (encoder_decoder.py:294-296). */
+int ctl_upsample2x_c8(const void* x, int64_t N, int64_t C, int64_t H, int64_t W, void* y, void* stream);
+/* Train-mode BatchNorm2d statistics of a C8 tensor folded into y = x*scale + shift:
+ * scale = gamma*rsqrt(var_biased + eps), shift = beta - mean*scale (fp64 accumulation).  When running_mean/var are
+ * given they are updated like nn.BatchNorm2d (momentum, unbiased variance) -- pass NULL to reproduce
+ * _disable_tracking_bn_stats (model_util.py:414-451).  workspace: ctl_bn_workspace_bytes(N, C) bytes. */
+size_t ctl_bn_workspace_bytes(int64_t N, int64_t C);
+int ctl_bn_batch_affine_c8(const void* x, int64_t N, int64_t C, int64_t H, int64_t W, const float* gamma,
+                           const float* beta, float eps, void* workspace, float* scale, float* shift,
+                           float* mean_out, float* var_out, float* running_mean, float* running_var,
+                           float momentum, void* stream);
+/* y = act(x*scale[c] + shift[c]) on C8 tensors (BatchNorm apply + LeakyReLU in one pass). */
+int ctl_scale_shift_act_c8(const void* x, int64_t N, int64_t C, int64_t H, int64_t W, const float* scale,
+                           const float* shift, int act, void* y, void* stream);
 
 #ifdef __cplusplus
 }

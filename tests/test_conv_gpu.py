@@ -30,7 +30,9 @@ def _ref(x, w, k, stride, scale, shift, res, rs, rb, act):
 
 
 def _check(got, want):
-    assert got.dtype == torch.bfloat16 and got.is_contiguous(memory_format=torch.channels_last)
+    assert got.dtype == torch.bfloat16 and got.dim() == 5 and got.shape[-1] == 8      # C8 layout
+    import cooperative_training_and_latent_space_data_augmentation_b200 as pkg
+    got = pkg.ops.c8_to_nchw(got)
     err = (got.float() - want).abs()
     tol = 1e-2 * want.abs() + 2e-2
     assert bool((err <= tol).all()), "max err %.4f at ref %.4f (tol %.4f); mismatches %d / %d" % (
@@ -52,11 +54,11 @@ LAYERS = [  # (Cin, Cout, k, stride, N, H, W)   -- the layer classes of FCN_16_s
 @pytest.mark.parametrize("cin,cout,k,stride,N,H,W", LAYERS)
 def test_conv_matches_torch(ops, cin, cout, k, stride, N, H, W):
     g = torch.Generator(device="cuda").manual_seed(cin * 1000 + cout + k + H)
-    x = torch.randn(N, cin, H, W, device="cuda", generator=g).to(torch.bfloat16).contiguous(memory_format=torch.channels_last)
+    x = torch.randn(N, cin, H, W, device="cuda", generator=g).to(torch.bfloat16)
     w = torch.randn(cout, cin, k, k, device="cuda", generator=g) * (2.0 / (cin * k * k)) ** 0.5
     assert ops.conv_supported(cin, cout, k)
     wp = ops.pack_conv_weight(w)
-    got = ops.conv2d_bf16(x, wp, cout, k * k, subsample=stride)
+    got = ops.conv2d_c8(ops.nchw_to_c8(x), wp, cout, k * k, subsample=stride)
     _check(got, _ref(x, w, k, stride, None, None, None, None, None, 0))
 
 
@@ -65,18 +67,88 @@ def test_conv_matches_torch(ops, cin, cout, k, stride, N, H, W):
 def test_conv_fused_epilogue(ops, act, cin, cout, k):
     g = torch.Generator(device="cuda").manual_seed(act * 7 + cin + cout)
     N, H, W = 3, 40, 24
-    x = torch.randn(N, cin, H, W, device="cuda", generator=g).to(torch.bfloat16).contiguous(memory_format=torch.channels_last)
+    x = torch.randn(N, cin, H, W, device="cuda", generator=g).to(torch.bfloat16)
     w = torch.randn(cout, cin, k, k, device="cuda", generator=g) * (2.0 / (cin * k * k)) ** 0.5
     scale = 1 + 0.2 * torch.randn(cout, device="cuda", generator=g)
     shift = 0.3 * torch.randn(cout, device="cuda", generator=g)
-    res = torch.randn(N, cout, H, W, device="cuda", generator=g).to(torch.bfloat16).contiguous(memory_format=torch.channels_last)
+    res = torch.randn(N, cout, H, W, device="cuda", generator=g).to(torch.bfloat16)
     rs = 1 + 0.2 * torch.randn(cout, device="cuda", generator=g)
     rb = 0.3 * torch.randn(cout, device="cuda", generator=g)
     wp = ops.pack_conv_weight(w)
-    got = ops.conv2d_bf16(x, wp, cout, k * k, scale=scale, shift=shift, res=res, res_scale=rs, res_shift=rb, act=act)
+    xc = ops.nchw_to_c8(x)
+    got = ops.conv2d_c8(xc, wp, cout, k * k, scale=scale, shift=shift, res=ops.nchw_to_c8(res), res_scale=rs,
+                        res_shift=rb, act=act)
     _check(got, _ref(x, w, k, 1, scale, shift, res, rs, rb, act))
-    got = ops.conv2d_bf16(x, wp, cout, k * k, shift=shift, act=act)
+    got = ops.conv2d_c8(xc, wp, cout, k * k, shift=shift, act=act)
     _check(got, _ref(x, w, k, 1, None, shift, None, None, None, act))
+
+
+def test_layout_round_trip(ops):
+    x = torch.randn(3, 24, 7, 9, device="cuda")
+    c8 = ops.nchw_to_c8(x)
+    assert tuple(c8.shape) == (3, 3, 7, 9, 8)
+    assert torch.equal(ops.c8_to_nchw(c8), x.to(torch.bfloat16).float())
+    assert torch.equal(c8, x.to(torch.bfloat16).view(3, 3, 8, 7, 9).permute(0, 1, 3, 4, 2).contiguous())
+    assert torch.equal(ops.c8_to_nchw(ops.nchw_to_c8(x.to(torch.bfloat16)), torch.bfloat16), x.to(torch.bfloat16))
+
+
+@pytest.mark.parametrize("cin,cout,H,W", [(128, 128, 14, 14), (64, 64, 28, 28), (32, 32, 56, 40), (16, 16, 112, 112)])
+def test_convtranspose2x2_matches_torch(ops, cin, cout, H, W):
+    g = torch.Generator(device="cuda").manual_seed(cin + H)
+    x = torch.randn(2, cin, H, W, device="cuda", generator=g).to(torch.bfloat16)
+    w = torch.randn(cin, cout, 2, 2, device="cuda", generator=g) * (1.0 / cin) ** 0.5
+    b = 0.3 * torch.randn(cout, device="cuda", generator=g)
+    got = ops.conv2d_c8(ops.nchw_to_c8(x), ops.pack_convtranspose2x2_weight(w), 4 * cout, 1, up2x=True,
+                        shift=b.repeat(4))
+    assert tuple(got.shape) == (2, cout // 8, 2 * H, 2 * W, 8)
+    want = F.conv_transpose2d(x.float(), w.to(torch.bfloat16).float(), b, stride=2)
+    _check(got, want)
+
+
+@pytest.mark.parametrize("cin,in_mode", [(1, 0), (4, 0), (4, 1), (4, 2)])
+def test_stem_conv_matches_torch(ops, cin, in_mode):
+    g = torch.Generator(device="cuda").manual_seed(cin * 10 + in_mode)
+    N, H, W = 3, 37, 50
+    w = torch.randn(16, cin, 3, 3, device="cuda", generator=g) * 0.3
+    scale = 1 + 0.2 * torch.randn(16, device="cuda", generator=g)
+    shift = 0.3 * torch.randn(16, device="cuda", generator=g)
+    if in_mode == 2:
+        lab = torch.randint(0, 4, (N, H, W), device="cuda", generator=g)
+        xin = F.one_hot(lab, 4).permute(0, 3, 1, 2).float()
+        got = ops.stem_conv_c8(lab, w, scale, shift, ops.ACT_LRELU, in_mode=2)
+    else:
+        x = torch.randn(N, cin, H, W, device="cuda", generator=g) * 2
+        xin = torch.softmax(x / 2.0, dim=1) if in_mode == 1 else x
+        got = ops.stem_conv_c8(x, w, scale, shift, ops.ACT_LRELU, in_mode=in_mode, temperature=2.0)
+    want = F.leaky_relu(F.conv2d(xin, w, None, padding=1) * scale.view(1, -1, 1, 1) + shift.view(1, -1, 1, 1), 0.2)
+    _check(got, want)
+
+
+@pytest.mark.parametrize("cout,act", [(4, 0), (1, 3)])
+def test_head_upsample_bn_ops(ops, cout, act):
+    g = torch.Generator(device="cuda").manual_seed(cout)
+    N, H, W = 2, 30, 44
+    x = torch.randn(N, 16, H, W, device="cuda", generator=g).to(torch.bfloat16)
+    xc = ops.nchw_to_c8(x)
+    w = torch.randn(cout, 16, 1, 1, device="cuda", generator=g) * 0.3
+    b = torch.randn(cout, device="cuda", generator=g)
+    want = F.conv2d(x.float(), w, b)
+    want = torch.sigmoid(want) if act == 3 else want
+    got = ops.head_conv_c8(xc, w, b, act)
+    assert got.dtype == torch.float32 and tuple(got.shape) == (N, cout, H, W)
+    torch.testing.assert_close(got, want, rtol=1e-4, atol=1e-4)
+    up = ops.c8_to_nchw(ops.upsample2x_c8(xc))
+    assert torch.equal(up, F.interpolate(x.float(), scale_factor=2, mode="nearest"))
+    # batch-norm statistics folded into (scale, shift), with the running-stat update of nn.BatchNorm2d
+    bn = torch.nn.BatchNorm2d(16).cuda()
+    bn.weight.data.normal_(1, 0.2, generator=g); bn.bias.data.normal_(0, 0.3, generator=g)
+    rm, rv = bn.running_mean.clone(), bn.running_var.clone()
+    want_y = bn(x.float())
+    scale, shift = ops.bn_batch_affine_c8(xc, bn.weight, bn.bias, bn.eps, rm, rv, bn.momentum)
+    torch.testing.assert_close(rm, bn.running_mean, rtol=1e-4, atol=1e-5)
+    torch.testing.assert_close(rv, bn.running_var, rtol=1e-4, atol=1e-5)
+    y = ops.c8_to_nchw(ops.scale_shift_act_c8(xc, scale, shift, ops.ACT_LRELU))
+    torch.testing.assert_close(y, F.leaky_relu(want_y, 0.2), rtol=2e-2, atol=2e-2)
 
 
 def test_conv_rejects_unsupported(ops):
