@@ -318,7 +318,7 @@ def run_gpu_arm(args):
         "metric": "cooperative-training samples/sec", "value": value, "unit": "samples/s", "n_gpus": world,
         "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": 1e3 * t_dev / args.steps,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-        "dtype": "bf16" if args.precision == "bf16" else "f32", "data": "synthetic",
+        "dtype": "f32" if args.precision == "fp32" else "bf16", "data": "synthetic",
         "config": workload_config(args, args.batch),
         "e2e": {"value": e2e_value, "unit": "samples/s",
                 "h2d_bytes_per_step": int(img_h.numel() * 4 + lab_h.numel() * 8) * world,
@@ -346,7 +346,8 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--batch", type=int, default=64, help="batch per GPU (configs[1]: 64)")
     ap.add_argument("--size", type=int, default=224, help="slice height = width (configs[1]: 224)")
-    ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32"])
+    ap.add_argument("--precision", default="kernel", choices=["kernel", "bf16", "fp32"],
+                    help="kernel: the sm_100a kernels of this build (product path); bf16/fp32: library convolutions")
     ap.add_argument("--ref-batch", type=int, default=8, help="bounded CPU sample: batch per CPU step")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--profile", action="store_true", help="device loop only, honour --warmup < 3 (for ncu)")

@@ -32,7 +32,8 @@ SIGNATURES = {
     "ctl_philox_uniform": (_i, [_u64, _u64, _u64, _i64, _vp, _vp]),
     "ctl_conv2d_n_tile": (_i, [_i, _i, _i]),
     "ctl_conv2d_c8_bf16": (_i, [_vp, _i64, _i64, _i64, _i64, _vp, _i64, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _i, _vp,
-                                _vp]),
+                                _vp, _vp]),
+    "ctl_bn_affine_from_sums": (_i, [_vp, _i64, _i64, _vp, _vp, _f, _vp, _vp, _vp, _vp, _vp, _vp, _f, _vp]),
     "ctl_nchw_to_c8": (_i, [_vp, _i, _i64, _i64, _i64, _i64, _vp, _vp]),
     "ctl_c8_to_nchw": (_i, [_vp, _i64, _i64, _i64, _i64, _vp, _i, _vp]),
     "ctl_stem_conv3x3_c8": (_i, [_vp, _vp, _i, _f, _i64, _i64, _i64, _i64, _vp, _i64, _vp, _vp, _i, _vp, _vp]),
@@ -42,6 +43,19 @@ SIGNATURES = {
     "ctl_bn_batch_affine_c8": (_i, [_vp, _i64, _i64, _i64, _i64, _vp, _vp, _f, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _f,
                                     _vp]),
     "ctl_scale_shift_act_c8": (_i, [_vp, _i64, _i64, _i64, _i64, _vp, _vp, _i, _vp, _vp]),
+    "ctl_conv_wgrad_c8_bf16": (_i, [_vp, _vp, _i64, _i64, _i64, _i64, _i64, _i, _vp, _vp]),
+    "ctl_reduce_workspace_bytes": (_c.c_size_t, [_i64, _i64]),
+    "ctl_channel_sums_c8": (_i, [_vp, _i64, _i64, _i64, _i64, _vp, _vp, _vp, _vp]),
+    "ctl_bn_bwd_reduce_c8": (_i, [_vp, _vp, _vp, _i64, _i64, _i64, _i64, _i, _vp, _vp, _f, _vp, _vp, _vp, _vp, _vp, _vp,
+                                  _vp]),
+    "ctl_bn_bwd_apply_c8": (_i, [_vp, _vp, _vp, _i64, _i64, _i64, _i64, _i, _vp, _vp, _vp]),
+    "ctl_act_bwd_c8": (_i, [_vp, _vp, _i64, _i64, _i64, _i64, _i, _vp, _vp]),
+    "ctl_downsample2x_sum_c8": (_i, [_vp, _i64, _i64, _i64, _i64, _vp, _vp]),
+    "ctl_zero_stuff2x_c8": (_i, [_vp, _i64, _i64, _i64, _i64, _vp, _vp]),
+    "ctl_split_parity2x2_c8": (_i, [_vp, _i64, _i64, _i64, _i64, _vp, _vp]),
+    "ctl_head_bwd_c8": (_i, [_vp, _vp, _vp, _i64, _i64, _i64, _i64, _vp, _i64, _i, _vp, _vp, _vp, _vp]),
+    "ctl_stem_wgrad_c8": (_i, [_vp, _vp, _vp, _i, _f, _i64, _i64, _i64, _i64, _vp, _vp]),
+    "ctl_stem_dgrad_c8": (_i, [_vp, _vp, _i, _f, _i64, _i64, _i64, _i64, _vp, _vp, _vp]),
 }
 
 _lib = None
@@ -50,7 +64,11 @@ _lib = None
 KERNELS_PER_CALL = {"ctl_saliency_reduce": 1, "ctl_topp_mask_apply": 2, "ctl_saliency_mask_apply": 3,
                     "ctl_channel_dropout": 1, "ctl_philox_uniform": 1, "ctl_conv2d_c8_bf16": 1,
                     "ctl_nchw_to_c8": 1, "ctl_c8_to_nchw": 1, "ctl_stem_conv3x3_c8": 1, "ctl_head_conv1x1_c8": 1,
-                    "ctl_upsample2x_c8": 1, "ctl_bn_batch_affine_c8": 2, "ctl_scale_shift_act_c8": 1}
+                    "ctl_upsample2x_c8": 1, "ctl_bn_batch_affine_c8": 2, "ctl_scale_shift_act_c8": 1,
+                    "ctl_conv_wgrad_c8_bf16": 1, "ctl_channel_sums_c8": 2, "ctl_bn_affine_from_sums": 1, "ctl_bn_bwd_reduce_c8": 2,
+                    "ctl_bn_bwd_apply_c8": 1, "ctl_act_bwd_c8": 1, "ctl_downsample2x_sum_c8": 1,
+                    "ctl_zero_stuff2x_c8": 1, "ctl_split_parity2x2_c8": 1, "ctl_head_bwd_c8": 1,
+                    "ctl_stem_wgrad_c8": 1, "ctl_stem_dgrad_c8": 1}
 LAUNCHES = {"count": 0}
 
 

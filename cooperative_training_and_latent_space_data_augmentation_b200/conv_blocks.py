@@ -1,10 +1,13 @@
 """Arithmetic of the FTN/STN conv blocks.
 
-Two numerics modes, selected with `set_precision`:
-  'fp32'  parity mode: the exact op sequence of the reference in fp32 (what the reference itself
-          runs on a GPU); used by the parity tests that compare against the CPU oracle at 1e-4.
-  'bf16'  throughput mode: bf16 activations in NHWC (channels_last), fp32 master weights, fp32
-          BatchNorm statistics.
+Three numerics modes, selected with `set_precision`:
+  'fp32'    parity mode: the exact op sequence of the reference in fp32 (what the reference itself
+            runs on a GPU); used by the parity tests that compare against the CPU oracle at 1e-4.
+  'kernel'  product mode: whole sub-networks run forward AND backward on this build's sm_100a kernels
+            (trainpath.py / fastpath.py; bf16 C8 activations, fp32 master weights and statistics).  The
+            functions below are then only reached for the one case the kernels do not cover (eval-mode
+            BatchNorm with autograd enabled), where they behave like 'bf16'.
+  'bf16'    library comparison mode: bf16 activations in NHWC (channels_last) through cuDNN.
 
 Every function takes the reference-shaped nn.Module that owns the parameters, so BatchNorm
 bookkeeping (training flag, track_running_stats, momentum, num_batches_tracked) follows the
@@ -19,8 +22,8 @@ LRELU_SLOPE = 0.2
 
 def set_precision(mode):
     global _PRECISION
-    if mode not in ("fp32", "bf16"):
-        raise ValueError("precision must be 'fp32' or 'bf16'")
+    if mode not in ("fp32", "bf16", "kernel"):
+        raise ValueError("precision must be 'fp32', 'bf16' or 'kernel'")
     _PRECISION = mode
     _apply_tf32_policy()
 
@@ -40,7 +43,7 @@ _apply_tf32_policy()
 
 def _prep(x):
     """bf16 mode keeps activations NHWC bf16 end to end; fp32 mode leaves the tensor alone."""
-    if _PRECISION == "bf16":
+    if _PRECISION != "fp32":
         if x.dtype != torch.bfloat16:
             x = x.to(torch.bfloat16)
         return x.contiguous(memory_format=torch.channels_last)
@@ -48,7 +51,7 @@ def _prep(x):
 
 
 def _conv(conv, x):
-    if _PRECISION == "bf16":
+    if _PRECISION != "fp32":
         return F.conv2d(x, conv.weight.to(torch.bfloat16), conv.bias.to(torch.bfloat16) if conv.bias is not None
                         else None, conv.stride, conv.padding)
     return conv(x)
@@ -68,7 +71,7 @@ def resample_up(up, up_type, x):
     x = _prep(x)
     if up_type == 'NN':
         return F.interpolate(x, scale_factor=2, mode='nearest')
-    if _PRECISION == "bf16":
+    if _PRECISION != "fp32":
         return F.conv_transpose2d(x, up.weight.to(torch.bfloat16), up.bias.to(torch.bfloat16), stride=2)
     return up(x)
 

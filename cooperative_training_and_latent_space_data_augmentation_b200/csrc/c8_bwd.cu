@@ -1,0 +1,782 @@
+// Backward-pass CUDA-core kernels for the blocked activation layout C8 = bf16 [N][C/8][H][W][8] (HBM-bound streaming
+// passes around the tensor-core dgrad / wgrad kernels):
+//   train-mode BatchNorm + LeakyReLU/ReLU backward (two-stage reduce + apply), per-channel sums (bias gradients),
+//   nearest x2 up-sampling backward (2x2 sum), zero-stuffing / parity split (stride-2 conv and ConvTranspose2d k2 s2
+//   backward), the 1x1 head backward and the stem (Cin 1/4) weight / input gradients with the STN-input softmax fused.
+//
+// Reference code whose autograd these replace (the reference relies on torch autograd for all of them):
+//   nn.BatchNorm2d + LeakyReLU(0.2)/ReLU   medseg/models/ebm/encoder_decoder.py:34,43-49,322-328,370-378,394-397,468-476
+//   nn.UpsamplingNearest2d                  medseg/models/ebm/encoder_decoder.py:294-296
+//   ConvTranspose2d(k2,s2) / Conv2d s2      medseg/models/ebm/encoder_decoder.py:302, :40-41
+//   MyDecoder.final_conv (+Sigmoid)         medseg/models/ebm/encoder_decoder.py:439-452
+//   MyEncoder.inc[0] + construct_input      medseg/models/ebm/encoder_decoder.py:370-371, medseg/common_utils/basic_operations.py:110-158
+#include <algorithm>
+
+#include "ctl_common.cuh"
+
+namespace ctl {
+namespace {
+
+constexpr int kT = 256;
+
+__device__ __forceinline__ void unpack8(const uint4& r, float (&f)[8]) {
+  const uint32_t w[4] = {r.x, r.y, r.z, r.w};
+#pragma unroll
+  for (int i = 0; i < 4; ++i) { f[2 * i] = __uint_as_float(w[i] << 16); f[2 * i + 1] = __uint_as_float(w[i] & 0xffff0000u); }
+}
+__device__ __forceinline__ uint4 pack8(const float (&f)[8]) {
+  uint32_t o[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const __nv_bfloat162 h = __floats2bfloat162_rn(f[2 * i], f[2 * i + 1]);
+    o[i] = *reinterpret_cast<const uint32_t*>(&h);
+  }
+  return make_uint4(o[0], o[1], o[2], o[3]);
+}
+// derivative of the activation expressed through its OUTPUT h (sign(h) == sign(pre-activation) for LReLU/ReLU)
+__device__ __forceinline__ float act_slope(float h, int act) {
+  switch (act) {
+    case CTL_ACT_LRELU: return h > 0.0f ? 1.0f : 0.2f;
+    case CTL_ACT_RELU: return h > 0.0f ? 1.0f : 0.0f;
+    case CTL_ACT_SIGMOID: return h * (1.0f - h);
+    default: return 1.0f;
+  }
+}
+
+// plane split: enough CTAs to fill the GPU even when N*C/8 is small (16 channels at 224x224: 128 planes of 800 KB)
+inline int plane_splits(int64_t planes, int64_t HW) {
+  const int64_t want = (int64_t)sm_count() * 6;
+  int64_t s = ceil_div(want, planes);
+  const int64_t max_s = std::max<int64_t>(1, HW / (kT * 4));
+  s = std::min(s, max_s);
+  return (int)std::max<int64_t>(1, std::min<int64_t>(s, 64));
+}
+
+// ------------------------------------------------------------------------------------------------ reductions
+// Stage 1 of every per-channel reduction.  MODE 0: sum x, sum x^2 (forward statistics / bias gradients).
+// MODE 1: dv = dy * act'(h); sum dv, sum dv*a (BatchNorm backward); optionally materialises dv.
+// partial: double [(split*planes + plane)*8 + j][2]
+template <int MODE>
+__global__ void __launch_bounds__(kT)
+plane_reduce_kernel(const uint4* __restrict__ x, const uint4* __restrict__ h, const uint4* __restrict__ a,
+                    uint4* __restrict__ dv_out, double* __restrict__ partial, int64_t planes, int64_t HW, int splits,
+                    int act) {
+  const int64_t plane = blockIdx.x;
+  const int split = blockIdx.y;
+  const int64_t chunk = (HW + splits - 1) / splits;
+  const int64_t lo = split * chunk, hi = min(HW, lo + chunk);
+  float s[8], q[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) { s[j] = 0.0f; q[j] = 0.0f; }
+  for (int64_t i = lo + threadIdx.x; i < hi; i += kT) {
+    const int64_t idx = plane * HW + i;
+    float f[8];
+    unpack8(__ldcs(x + idx), f);
+    if (MODE == 0) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) { s[j] += f[j]; q[j] = fmaf(f[j], f[j], q[j]); }
+    } else {
+      float av[8];
+      unpack8(__ldg(a + idx), av);
+      if (h != nullptr) {
+        float hv[8];
+        unpack8(__ldg(h + idx), hv);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) f[j] *= act_slope(hv[j], act);
+        if (dv_out != nullptr) {
+          const uint4 packed = pack8(f);
+          dv_out[idx] = packed;
+          unpack8(packed, f);                     // reduce what the consumers will read (bf16-rounded)
+        }
+      }
+#pragma unroll
+      for (int j = 0; j < 8; ++j) { s[j] += f[j]; q[j] = fmaf(f[j], av[j], q[j]); }
+    }
+  }
+  __shared__ double red[kT / 32][16];
+  double ds[8], dq[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    ds[j] = (double)s[j]; dq[j] = (double)q[j];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      ds[j] += __shfl_xor_sync(0xffffffffu, ds[j], o);
+      dq[j] += __shfl_xor_sync(0xffffffffu, dq[j], o);
+    }
+  }
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (lane == 0) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { red[warp][j] = ds[j]; red[warp][8 + j] = dq[j]; }
+  }
+  __syncthreads();
+  if (threadIdx.x < 16) {
+    double t = 0.0;
+    for (int w = 0; w < kT / 32; ++w) t += red[w][threadIdx.x];
+    const int j = threadIdx.x & 7, second = threadIdx.x >> 3;
+    partial[(((int64_t)split * planes + plane) * 8 + j) * 2 + second] = t;
+  }
+}
+
+// one warp per channel: sums the partials over (split, n); lane 0 holds the totals
+__device__ __forceinline__ void channel_totals(const double* __restrict__ partial, int64_t planes, int splits, int N, int C,
+                                               int c, double& S1, double& S2) {
+  const int C8 = C >> 3, c8 = c >> 3, j = c & 7;
+  const int lane = threadIdx.x & 31;
+  double a = 0.0, b = 0.0;
+  const int entries = splits * N;
+  for (int e = lane; e < entries; e += 32) {
+    const int split = e / N, n = e - split * N;
+    const int64_t plane = (int64_t)n * C8 + c8;
+    const double* p = partial + (((int64_t)split * planes + plane) * 8 + j) * 2;
+    a += p[0]; b += p[1];
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) { a += __shfl_xor_sync(0xffffffffu, a, o); b += __shfl_xor_sync(0xffffffffu, b, o); }
+  S1 = a; S2 = b;
+}
+
+__global__ void channel_sum_finalize_kernel(const double* __restrict__ partial, int64_t planes, int splits, int N, int C,
+                                            float* __restrict__ sum_out, float* __restrict__ sumsq_out) {
+  const int c = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (c >= C) return;
+  double S1, S2;
+  channel_totals(partial, planes, splits, N, C, c, S1, S2);
+  if ((threadIdx.x & 31) == 0) {
+    if (sum_out) sum_out[c] = (float)S1;
+    if (sumsq_out) sumsq_out[c] = (float)S2;
+  }
+}
+
+
+// forward BatchNorm: batch mean / biased variance -> fused affine y = x*scale + shift (scale = gamma*rsqrt(var+eps),
+// shift = beta - mean*scale); optional running-stat update (momentum, unbiased variance) like nn.BatchNorm2d.
+__global__ void bn_fwd_finalize_kernel(const double* __restrict__ partial, int64_t planes, int splits, int N, int C,
+                                       double count, const float* __restrict__ gamma, const float* __restrict__ beta,
+                                       float eps, float* __restrict__ scale, float* __restrict__ shift,
+                                       float* __restrict__ mean_out, float* __restrict__ var_out, float* running_mean,
+                                       float* running_var, float momentum) {
+  const int c = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (c >= C) return;
+  double s, q;
+  channel_totals(partial, planes, splits, N, C, c, s, q);
+  if ((threadIdx.x & 31) != 0) return;
+  const double mean = s / count;
+  double var = q / count - mean * mean;
+  if (var < 0.0) var = 0.0;
+  const float inv = (float)(1.0 / sqrt(var + (double)eps));
+  const float g = gamma ? gamma[c] : 1.0f, b = beta ? beta[c] : 0.0f;
+  scale[c] = g * inv;
+  shift[c] = b - (float)mean * g * inv;
+  if (mean_out) mean_out[c] = (float)mean;
+  if (var_out) var_out[c] = (float)var;
+  if (running_mean) {
+    const double unbiased = count > 1.0 ? var * count / (count - 1.0) : var;
+    running_mean[c] = (1.0f - momentum) * running_mean[c] + momentum * (float)mean;
+    running_var[c] = (1.0f - momentum) * running_var[c] + momentum * (float)unbiased;
+  }
+}
+
+// same finalisation from per-channel sums accumulated by the conv epilogue: sums = double [2][C] (sum x | sum x^2)
+__global__ void bn_fwd_from_sums_kernel(const double* __restrict__ sums, int C, double count, const float* __restrict__ gamma,
+                                        const float* __restrict__ beta, float eps, float* __restrict__ scale,
+                                        float* __restrict__ shift, float* __restrict__ mean_out, float* __restrict__ var_out,
+                                        float* running_mean, float* running_var, float momentum) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  const double mean = sums[c] / count;
+  double var = sums[C + c] / count - mean * mean;
+  if (var < 0.0) var = 0.0;
+  const float inv = (float)(1.0 / sqrt(var + (double)eps));
+  const float g = gamma ? gamma[c] : 1.0f, b = beta ? beta[c] : 0.0f;
+  scale[c] = g * inv;
+  shift[c] = b - (float)mean * g * inv;
+  if (mean_out) mean_out[c] = (float)mean;
+  if (var_out) var_out[c] = (float)var;
+  if (running_mean) {
+    const double unbiased = count > 1.0 ? var * count / (count - 1.0) : var;
+    running_mean[c] = (1.0f - momentum) * running_mean[c] + momentum * (float)mean;
+    running_var[c] = (1.0f - momentum) * running_var[c] + momentum * (float)unbiased;
+  }
+}
+
+// BatchNorm backward coefficients: da = c1*dv + c2*a + c3 with
+//   c1 = scale, c2 = -scale*inv*dgamma/M, c3 = scale*(inv*mean*dgamma - dbeta)/M,  scale = gamma*inv, inv = rsqrt(var+eps)
+__global__ void bn_bwd_finalize_kernel(const double* __restrict__ partial, int64_t planes, int splits, int N, int C,
+                                       double count, const float* __restrict__ mean, const float* __restrict__ var,
+                                       float eps, const float* __restrict__ gamma, float* __restrict__ coef,
+                                       float* __restrict__ dgamma, float* __restrict__ dbeta) {
+  const int c = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (c >= C) return;
+  double S1, S2;
+  channel_totals(partial, planes, splits, N, C, c, S1, S2);
+  if ((threadIdx.x & 31) != 0) return;
+  const double mu = (double)mean[c];
+  const double inv = 1.0 / sqrt((double)var[c] + (double)eps);
+  const double g = gamma ? (double)gamma[c] : 1.0;
+  const double scale = g * inv;
+  const double dg = inv * (S2 - mu * S1);
+  coef[c] = (float)scale;
+  coef[C + c] = (float)(-scale * inv * dg / count);
+  coef[2 * C + c] = (float)(scale * (inv * mu * dg - S1) / count);
+  if (dgamma) dgamma[c] = (float)dg;
+  if (dbeta) dbeta[c] = (float)S1;
+}
+
+// da = c1*dv + c2*a + c3, dv = dy * act'(h) when h is given
+__global__ void __launch_bounds__(kT)
+bn_bwd_apply_kernel(const uint4* __restrict__ dy, const uint4* __restrict__ h, const uint4* __restrict__ a,
+                    const float* __restrict__ coef, uint4* __restrict__ da, int64_t total, int C8, int64_t HW, int act) {
+  const int C = C8 * 8;
+  for (int64_t i = (int64_t)blockIdx.x * kT + threadIdx.x; i < total; i += (int64_t)gridDim.x * kT) {
+    const int c0 = (int)((i / HW) % C8) * 8;
+    float f[8], av[8];
+    unpack8(__ldcs(dy + i), f);
+    unpack8(__ldcs(a + i), av);
+    if (h != nullptr) {
+      float hv[8];
+      unpack8(__ldcs(h + i), hv);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) f[j] *= act_slope(hv[j], act);
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j)
+      f[j] = fmaf(__ldg(coef + c0 + j), f[j], fmaf(__ldg(coef + C + c0 + j), av[j], __ldg(coef + 2 * C + c0 + j)));
+    da[i] = pack8(f);
+  }
+}
+
+// dv = dy * act'(h) only (activation backward without a BatchNorm in front)
+__global__ void __launch_bounds__(kT)
+act_bwd_kernel(const uint4* __restrict__ dy, const uint4* __restrict__ h, uint4* __restrict__ dv, int64_t total, int act) {
+  for (int64_t i = (int64_t)blockIdx.x * kT + threadIdx.x; i < total; i += (int64_t)gridDim.x * kT) {
+    float f[8], hv[8];
+    unpack8(__ldcs(dy + i), f);
+    unpack8(__ldcs(h + i), hv);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) f[j] *= act_slope(hv[j], act);
+    dv[i] = pack8(f);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ resampling
+// backward of nearest x2 up-sampling: dx[p] = sum of the 2x2 block of dy; one thread per OUTPUT (low-res) pixel
+__global__ void __launch_bounds__(kT)
+downsample2x_sum_kernel(const uint4* __restrict__ dy, uint4* __restrict__ dx, int64_t planes, int H, int W) {
+  const int64_t total = planes * H * W;
+  for (int64_t i = (int64_t)blockIdx.x * kT + threadIdx.x; i < total; i += (int64_t)gridDim.x * kT) {
+    const int64_t pl = i / ((int64_t)H * W);
+    const int pix = (int)(i - pl * H * W);
+    const int yy = pix / W, xx = pix - yy * W;
+    const uint4* p = dy + pl * 4 * H * W + (int64_t)(2 * yy) * (2 * W) + 2 * xx;
+    float acc[8], f[8];
+    unpack8(__ldcs(p), acc);
+    unpack8(__ldcs(p + 1), f);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[j] += f[j];
+    unpack8(__ldcs(p + 2 * W), f);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[j] += f[j];
+    unpack8(__ldcs(p + 2 * W + 1), f);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[j] += f[j];
+    dx[i] = pack8(acc);
+  }
+}
+// out[2y][2x] = x[y][x], the three other pixels of each 2x2 block = 0 (dy of a stride-2 conv seen at full resolution)
+__global__ void __launch_bounds__(kT)
+zero_stuff2x_kernel(const uint4* __restrict__ x, uint4* __restrict__ y, int64_t planes, int H, int W) {
+  const int64_t total = planes * H * W;
+  const uint4 z = make_uint4(0, 0, 0, 0);
+  for (int64_t i = (int64_t)blockIdx.x * kT + threadIdx.x; i < total; i += (int64_t)gridDim.x * kT) {
+    const int64_t pl = i / ((int64_t)H * W);
+    const int pix = (int)(i - pl * H * W);
+    const int yy = pix / W, xx = pix - yy * W;
+    uint4* o = y + pl * 4 * H * W + (int64_t)(2 * yy) * (2 * W) + 2 * xx;
+    o[0] = __ldcs(x + i); o[1] = z; o[2 * W] = z; o[2 * W + 1] = z;
+  }
+}
+// out[d][plane][y][x] = x[plane][2y + d/2][2x + d%2], d = 0..3 (dy of a ConvTranspose2d k2 s2 split by kernel tap)
+__global__ void __launch_bounds__(kT)
+split_parity2x2_kernel(const uint4* __restrict__ x, uint4* __restrict__ y, int64_t planes, int H, int W) {
+  const int64_t total = planes * H * W;                // H, W: LOW resolution
+  for (int64_t i = (int64_t)blockIdx.x * kT + threadIdx.x; i < total; i += (int64_t)gridDim.x * kT) {
+    const int64_t pl = i / ((int64_t)H * W);
+    const int pix = (int)(i - pl * H * W);
+    const int yy = pix / W, xx = pix - yy * W;
+    const uint4* p = x + pl * 4 * H * W + (int64_t)(2 * yy) * (2 * W) + 2 * xx;
+    y[i] = __ldcs(p);
+    y[total + i] = __ldcs(p + 1);
+    y[2 * total + i] = __ldcs(p + 2 * W);
+    y[3 * total + i] = __ldcs(p + 2 * W + 1);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ head backward
+// y = act(W x + b), x: 16 blocked channels, y: COUT planar fp32.  dz = dy * act'(y);
+// dx = W^T dz (C8 bf16); dW[co][ci] += sum_p dz[co] x[ci]; db[co] += sum_p dz[co]  (atomic accumulation into fp32).
+template <int COUT>
+__global__ void __launch_bounds__(kT)
+head_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ yout, const __nv_bfloat16* __restrict__ x,
+                const float* __restrict__ w, __nv_bfloat16* __restrict__ dx, float* __restrict__ dW,
+                float* __restrict__ db, int N, int64_t HW, int act) {
+  constexpr int CIN = 16;
+  __shared__ float sw[COUT * CIN];
+  __shared__ float red[kT / 32][COUT * CIN + COUT];
+  for (int i = threadIdx.x; i < COUT * CIN; i += kT) sw[i] = w[i];
+  __syncthreads();
+  float aw[COUT * CIN], ab[COUT];
+#pragma unroll
+  for (int i = 0; i < COUT * CIN; ++i) aw[i] = 0.0f;
+#pragma unroll
+  for (int i = 0; i < COUT; ++i) ab[i] = 0.0f;
+  const int64_t total = (int64_t)N * HW;
+  for (int64_t i = (int64_t)blockIdx.x * kT + threadIdx.x; i < total; i += (int64_t)gridDim.x * kT) {
+    const int64_t n = i / HW, pix = i - n * HW;
+    float xv[CIN];
+#pragma unroll
+    for (int c8 = 0; c8 < CIN / 8; ++c8) {
+      float f[8];
+      unpack8(*reinterpret_cast<const uint4*>(x + ((n * (CIN / 8) + c8) * HW + pix) * 8), f);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) xv[c8 * 8 + j] = f[j];
+    }
+    float dz[COUT];
+#pragma unroll
+    for (int co = 0; co < COUT; ++co) {
+      const int64_t o = (n * COUT + co) * HW + pix;
+      float g = dy[o];
+      if (act != CTL_ACT_NONE) g *= act_slope(yout[o], act);
+      dz[co] = g;
+      ab[co] += g;
+    }
+    float dxv[CIN];
+#pragma unroll
+    for (int ci = 0; ci < CIN; ++ci) {
+      float t = 0.0f;
+#pragma unroll
+      for (int co = 0; co < COUT; ++co) {
+        t = fmaf(sw[co * CIN + ci], dz[co], t);
+        aw[co * CIN + ci] = fmaf(dz[co], xv[ci], aw[co * CIN + ci]);
+      }
+      dxv[ci] = t;
+    }
+#pragma unroll
+    for (int c8 = 0; c8 < CIN / 8; ++c8) {
+      float f[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) f[j] = dxv[c8 * 8 + j];
+      *reinterpret_cast<uint4*>(dx + ((n * (CIN / 8) + c8) * HW + pix) * 8) = pack8(f);
+    }
+  }
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+#pragma unroll
+  for (int i = 0; i < COUT * CIN; ++i) {
+    float v = aw[i];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    if (lane == 0) red[warp][i] = v;
+  }
+#pragma unroll
+  for (int i = 0; i < COUT; ++i) {
+    float v = ab[i];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    if (lane == 0) red[warp][COUT * CIN + i] = v;
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < COUT * CIN + COUT; i += kT) {
+    float t = 0.0f;
+    for (int wq = 0; wq < kT / 32; ++wq) t += red[wq][i];
+    if (i < COUT * CIN) atomicAdd(dW + i, t);
+    else atomicAdd(db + (i - COUT * CIN), t);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ stem backward
+// value of the stem's input channel ci at (n, iy, ix) (zero outside the image), honouring in_mode
+template <int CIN>
+__device__ __forceinline__ void stem_input_at(const float* __restrict__ x, const long long* __restrict__ labels, int in_mode,
+                                              float inv_temp, int64_t n, int iy, int ix, int H, int W, float (&v)[CIN]) {
+  if (iy < 0 || iy >= H || ix < 0 || ix >= W) {
+#pragma unroll
+    for (int ci = 0; ci < CIN; ++ci) v[ci] = 0.0f;
+    return;
+  }
+  const int64_t HW = (int64_t)H * W, q = (int64_t)iy * W + ix;
+  if (in_mode == 2) {
+    const long long lab = labels[n * HW + q];
+#pragma unroll
+    for (int ci = 0; ci < CIN; ++ci) v[ci] = (lab == ci) ? 1.0f : 0.0f;
+    return;
+  }
+#pragma unroll
+  for (int ci = 0; ci < CIN; ++ci) v[ci] = x[(n * CIN + ci) * HW + q];
+  if (in_mode == 1) {
+    float mx = v[0];
+#pragma unroll
+    for (int ci = 1; ci < CIN; ++ci) mx = fmaxf(mx, v[ci]);
+    float sum = 0.0f;
+#pragma unroll
+    for (int ci = 0; ci < CIN; ++ci) { v[ci] = __expf((v[ci] - mx) * inv_temp); sum += v[ci]; }
+    const float inv = 1.0f / sum;
+#pragma unroll
+    for (int ci = 0; ci < CIN; ++ci) v[ci] *= inv;
+  }
+}
+
+// Weight gradient of the stem: dW[co][ci][r][s] += sum_p dy[p][co] * in[p + (r-1, s-1)][ci].
+// CTA = one 32x8 pixel tile per iteration (persistent), input tile with halo and dy tile staged in shared memory.
+// Thread (g = tid/16, t = tid%16): pixels g, g+16, ... of the tile; co quad t%4; k slice t/4 (CIN 4: channel t/4, nine
+// taps; CIN 1: filter row t/4 < 3, three taps) -> 4 x KT register accumulators, 1 + KT shared loads per 4*KT FMAs.
+template <int CIN>
+__global__ void __launch_bounds__(kT)
+stem_wgrad_kernel(const __nv_bfloat16* __restrict__ dy, const float* __restrict__ x, const long long* __restrict__ labels,
+                  int in_mode, float inv_temp, int N, int H, int W, float* __restrict__ dW) {
+  constexpr int COUT = 16, TW = 32, TH = 8, HW_T = TW + 2, HH_T = TH + 2;
+  constexpr int KT = CIN == 4 ? 9 : 3;
+  __shared__ float s_in[CIN][HH_T][HW_T + 1];
+  __shared__ __align__(16) float s_dy[TH * TW][COUT];
+  __shared__ float s_red[kT / 32][COUT * CIN * 9];
+  const int g = threadIdx.x >> 4, t = threadIdx.x & 15;
+  const int cq = t & 3, kq = t >> 2;
+  const bool k_active = CIN == 4 || kq < 3;
+  float acc[4][KT];
+#pragma unroll
+  for (int a = 0; a < 4; ++a)
+#pragma unroll
+    for (int b = 0; b < KT; ++b) acc[a][b] = 0.0f;
+  const int tiles_x = (W + TW - 1) / TW, tiles_y = (H + TH - 1) / TH;
+  const int64_t HW = (int64_t)H * W, num_tiles = (int64_t)N * tiles_x * tiles_y;
+  for (int64_t tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+    const int64_t n = tile / (tiles_x * tiles_y);
+    const int rem = (int)(tile - n * tiles_x * tiles_y);
+    const int y0 = (rem / tiles_x) * TH, x0 = (rem % tiles_x) * TW;
+    __syncthreads();                                      // previous iteration's readers are done
+    for (int i = threadIdx.x; i < HH_T * HW_T; i += kT) {
+      const int hy = i / HW_T, hx = i - hy * HW_T;
+      float v[CIN];
+      stem_input_at<CIN>(x, labels, in_mode, inv_temp, n, y0 + hy - 1, x0 + hx - 1, H, W, v);
+#pragma unroll
+      for (int ci = 0; ci < CIN; ++ci) s_in[ci][hy][hx] = v[ci];
+    }
+    for (int i = threadIdx.x; i < TH * TW * 2; i += kT) {  // one 16-byte half (8 channels) per thread
+      const int p = i >> 1, half = i & 1;
+      const int py = p / TW, px = p - py * TW;
+      float f[8];
+      if (y0 + py < H && x0 + px < W) {
+        unpack8(*reinterpret_cast<const uint4*>(dy + ((n * 2 + half) * HW + (int64_t)(y0 + py) * W + x0 + px) * 8), f);
+      } else {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) f[j] = 0.0f;
+      }
+#pragma unroll
+      for (int j = 0; j < 8; ++j) s_dy[p][half * 8 + j] = f[j];
+    }
+    __syncthreads();
+    if (k_active) {
+#pragma unroll 2
+      for (int p = g; p < TH * TW; p += 16) {
+        const int py = p / TW, px = p - py * TW;
+        const float4 d = *reinterpret_cast<const float4*>(&s_dy[p][cq * 4]);
+        float in[KT];
+        if (CIN == 4) {
+#pragma unroll
+          for (int k = 0; k < 9; ++k) in[k] = s_in[kq][py + k / 3][px + k % 3];
+        } else {
+#pragma unroll
+          for (int k = 0; k < 3; ++k) in[k] = s_in[0][py + kq][px + k];
+        }
+#pragma unroll
+        for (int k = 0; k < KT; ++k) {
+          acc[0][k] = fmaf(d.x, in[k], acc[0][k]);
+          acc[1][k] = fmaf(d.y, in[k], acc[1][k]);
+          acc[2][k] = fmaf(d.z, in[k], acc[2][k]);
+          acc[3][k] = fmaf(d.w, in[k], acc[3][k]);
+        }
+      }
+    }
+  }
+  // lanes l and l^16 share (cq, kq); then the 8 warps meet in shared memory
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+#pragma unroll
+  for (int a = 0; a < 4; ++a)
+#pragma unroll
+    for (int b = 0; b < KT; ++b) {
+      float v = acc[a][b] + __shfl_xor_sync(0xffffffffu, acc[a][b], 16);
+      if (lane < 16 && k_active) {
+        const int co = cq * 4 + a;
+        const int kidx = CIN == 4 ? kq * 9 + b : kq * 3 + b;          // ci*9 + tap
+        s_red[warp][co * (CIN * 9) + kidx] = v;
+      }
+    }
+  __syncthreads();
+  for (int i = threadIdx.x; i < COUT * CIN * 9; i += kT) {
+    float tsum = 0.0f;
+    for (int wq = 0; wq < kT / 32; ++wq) tsum += s_red[wq][i];
+    atomicAdd(dW + i, tsum);
+  }
+}
+
+// Input gradient of the stem (CIN = 4: the STN input): d_in[p][ci] = sum_{r,s,co} w[co][ci][r][s] * dy[p - (r-1,s-1)][co];
+// in_mode 1 chains through softmax(x / T): dx = (s * (d_in - sum_j s_j d_in_j)) / T.  Output planar fp32 [N,4,H,W].
+template <int CIN>
+__global__ void __launch_bounds__(kT)
+stem_dgrad_kernel(const __nv_bfloat16* __restrict__ dy, const float* __restrict__ x, const float* __restrict__ w,
+                  int in_mode, float inv_temp, int N, int H, int W, float* __restrict__ dx) {
+  constexpr int COUT = 16;
+  __shared__ __align__(16) float sw[9][COUT][CIN];          // [tap][co][ci]
+  for (int i = threadIdx.x; i < COUT * CIN * 9; i += kT) {
+    const int co = i / (CIN * 9), rest = i - co * (CIN * 9), ci = rest / 9, tap = rest - ci * 9;
+    sw[tap][co][ci] = w[i];
+  }
+  __syncthreads();
+  const int64_t HW = (int64_t)H * W, total = (int64_t)N * HW;
+  for (int64_t i = (int64_t)blockIdx.x * kT + threadIdx.x; i < total; i += (int64_t)gridDim.x * kT) {
+    const int64_t n = i / HW;
+    const int pix = (int)(i - n * HW);
+    const int yy = pix / W, xx = pix - yy * W;
+    float d[CIN];
+#pragma unroll
+    for (int ci = 0; ci < CIN; ++ci) d[ci] = 0.0f;
+#pragma unroll
+    for (int r = 0; r < 3; ++r) {
+      const int qy = yy - (r - 1);
+      if (qy < 0 || qy >= H) continue;
+#pragma unroll
+      for (int s = 0; s < 3; ++s) {
+        const int qx = xx - (s - 1);
+        if (qx < 0 || qx >= W) continue;
+#pragma unroll
+        for (int half = 0; half < 2; ++half) {
+          float f[8];
+          unpack8(__ldg(reinterpret_cast<const uint4*>(dy + ((n * 2 + half) * HW + (int64_t)qy * W + qx) * 8)), f);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const float* wv = sw[r * 3 + s][half * 8 + j];
+#pragma unroll
+            for (int ci = 0; ci < CIN; ++ci) d[ci] = fmaf(wv[ci], f[j], d[ci]);
+          }
+        }
+      }
+    }
+    if (in_mode == 1) {
+      float v[CIN];
+      stem_input_at<CIN>(x, nullptr, 1, inv_temp, n, yy, xx, H, W, v);
+      float dot = 0.0f;
+#pragma unroll
+      for (int ci = 0; ci < CIN; ++ci) dot = fmaf(v[ci], d[ci], dot);
+#pragma unroll
+      for (int ci = 0; ci < CIN; ++ci) d[ci] = v[ci] * (d[ci] - dot) * inv_temp;
+    }
+#pragma unroll
+    for (int ci = 0; ci < CIN; ++ci) dx[(n * CIN + ci) * HW + pix] = d[ci];
+  }
+}
+
+inline unsigned grid_for(int64_t total) {
+  return (unsigned)std::min<int64_t>(ceil_div(total, kT), (int64_t)sm_count() * 16);
+}
+
+int check_c8(const char* who, const void* a, const void* b, int64_t N, int64_t C, int64_t H, int64_t W) {
+  CTL_REQUIRE(a && b && N > 0 && C > 0 && C % 8 == 0 && H > 0 && W > 0, CTL_ERR_INVALID, "%s: bad arguments", who);
+  CTL_REQUIRE(N * (C / 8) <= 0x7fffffff, CTL_ERR_UNSUPPORTED, "%s: too many planes", who);
+  return CTL_OK;
+}
+
+}  // namespace
+}  // namespace ctl
+
+using namespace ctl;
+
+extern "C" size_t ctl_reduce_workspace_bytes(int64_t N, int64_t C) {
+  // 64 = upper bound of plane_splits()
+  return (N > 0 && C > 0) ? (size_t)64 * (size_t)(N * C) * 2 * sizeof(double) : 0;
+}
+
+extern "C" size_t ctl_bn_workspace_bytes(int64_t N, int64_t C) { return ctl_reduce_workspace_bytes(N, C); }
+
+extern "C" int ctl_bn_batch_affine_c8(const void* x, int64_t N, int64_t C, int64_t H, int64_t W, const float* gamma,
+                                      const float* beta, float eps, void* workspace, float* scale, float* shift,
+                                      float* mean_out, float* var_out, float* running_mean, float* running_var,
+                                      float momentum, void* stream) {
+  if (int rc = check_c8("ctl_bn_batch_affine_c8", x, workspace, N, C, H, W)) return rc;
+  CTL_REQUIRE(scale && shift, CTL_ERR_INVALID, "ctl_bn_batch_affine_c8: NULL pointer");
+  CTL_REQUIRE((running_mean == nullptr) == (running_var == nullptr), CTL_ERR_INVALID,
+              "running_mean and running_var must be given together");
+  if (sm_count() < 0) return CTL_ERR_CUDA;
+  cudaStream_t st = (cudaStream_t)stream;
+  const int64_t planes = N * (C / 8), HW = H * W;
+  const int splits = plane_splits(planes, HW);
+  plane_reduce_kernel<0><<<dim3((unsigned)planes, (unsigned)splits), kT, 0, st>>>(
+      (const uint4*)x, nullptr, nullptr, nullptr, (double*)workspace, planes, HW, splits, 0);
+  CTL_CUDA_OK(cudaGetLastError(), "bn_partial_stats launch");
+  bn_fwd_finalize_kernel<<<(unsigned)ceil_div(C, 4), 128, 0, st>>>((const double*)workspace, planes, splits, (int)N, (int)C,
+                                                                   (double)(N * HW), gamma, beta, eps, scale, shift,
+                                                                   mean_out, var_out, running_mean, running_var, momentum);
+  CTL_CUDA_OK(cudaGetLastError(), "bn_finalize launch");
+  return CTL_OK;
+}
+
+extern "C" int ctl_bn_affine_from_sums(const double* sums, int64_t C, int64_t count, const float* gamma, const float* beta,
+                                       float eps, float* scale, float* shift, float* mean_out, float* var_out,
+                                       float* running_mean, float* running_var, float momentum, void* stream) {
+  CTL_REQUIRE(sums && scale && shift && C > 0 && count > 0, CTL_ERR_INVALID, "ctl_bn_affine_from_sums: bad arguments");
+  CTL_REQUIRE((running_mean == nullptr) == (running_var == nullptr), CTL_ERR_INVALID,
+              "running_mean and running_var must be given together");
+  if (sm_count() < 0) return CTL_ERR_CUDA;
+  bn_fwd_from_sums_kernel<<<(unsigned)ceil_div(C, 128), 128, 0, (cudaStream_t)stream>>>(
+      sums, (int)C, (double)count, gamma, beta, eps, scale, shift, mean_out, var_out, running_mean, running_var, momentum);
+  CTL_CUDA_OK(cudaGetLastError(), "bn_fwd_from_sums launch");
+  return CTL_OK;
+}
+
+extern "C" int ctl_channel_sums_c8(const void* x, int64_t N, int64_t C, int64_t H, int64_t W, void* workspace,
+                                   float* sum_out, float* sumsq_out, void* stream) {
+  if (int rc = check_c8("ctl_channel_sums_c8", x, workspace, N, C, H, W)) return rc;
+  CTL_REQUIRE(sum_out || sumsq_out, CTL_ERR_INVALID, "ctl_channel_sums_c8: no output requested");
+  if (sm_count() < 0) return CTL_ERR_CUDA;
+  cudaStream_t st = (cudaStream_t)stream;
+  const int64_t planes = N * (C / 8), HW = H * W;
+  const int splits = plane_splits(planes, HW);
+  plane_reduce_kernel<0><<<dim3((unsigned)planes, (unsigned)splits), kT, 0, st>>>(
+      (const uint4*)x, nullptr, nullptr, nullptr, (double*)workspace, planes, HW, splits, 0);
+  CTL_CUDA_OK(cudaGetLastError(), "plane_reduce launch");
+  channel_sum_finalize_kernel<<<(unsigned)ceil_div(C, 4), 128, 0, st>>>((const double*)workspace, planes, splits, (int)N,
+                                                                        (int)C, sum_out, sumsq_out);
+  CTL_CUDA_OK(cudaGetLastError(), "channel_sum_finalize launch");
+  return CTL_OK;
+}
+
+extern "C" int ctl_bn_bwd_reduce_c8(const void* dy, const void* h, const void* a, int64_t N, int64_t C, int64_t H,
+                                    int64_t W, int act, const float* mean, const float* var, float eps,
+                                    const float* gamma, void* workspace, void* dv_out, float* coef, float* dgamma,
+                                    float* dbeta, void* stream) {
+  if (int rc = check_c8("ctl_bn_bwd_reduce_c8", dy, a, N, C, H, W)) return rc;
+  CTL_REQUIRE(mean && var && workspace && coef, CTL_ERR_INVALID, "ctl_bn_bwd_reduce_c8: NULL pointer");
+  CTL_REQUIRE(act >= CTL_ACT_NONE && act <= CTL_ACT_RELU, CTL_ERR_INVALID, "activation %d has no BN backward", act);
+  CTL_REQUIRE(h != nullptr || dv_out == nullptr, CTL_ERR_INVALID, "dv_out needs h");
+  if (sm_count() < 0) return CTL_ERR_CUDA;
+  cudaStream_t st = (cudaStream_t)stream;
+  const int64_t planes = N * (C / 8), HW = H * W;
+  const int splits = plane_splits(planes, HW);
+  plane_reduce_kernel<1><<<dim3((unsigned)planes, (unsigned)splits), kT, 0, st>>>(
+      (const uint4*)dy, (const uint4*)h, (const uint4*)a, (uint4*)dv_out, (double*)workspace, planes, HW, splits, act);
+  CTL_CUDA_OK(cudaGetLastError(), "bn_bwd_reduce launch");
+  bn_bwd_finalize_kernel<<<(unsigned)ceil_div(C, 4), 128, 0, st>>>((const double*)workspace, planes, splits, (int)N, (int)C,
+                                                                   (double)(N * HW), mean, var, eps, gamma, coef, dgamma,
+                                                                   dbeta);
+  CTL_CUDA_OK(cudaGetLastError(), "bn_bwd_finalize launch");
+  return CTL_OK;
+}
+
+extern "C" int ctl_bn_bwd_apply_c8(const void* dy, const void* h, const void* a, int64_t N, int64_t C, int64_t H,
+                                   int64_t W, int act, const float* coef, void* da, void* stream) {
+  if (int rc = check_c8("ctl_bn_bwd_apply_c8", dy, a, N, C, H, W)) return rc;
+  CTL_REQUIRE(coef && da, CTL_ERR_INVALID, "ctl_bn_bwd_apply_c8: NULL pointer");
+  if (sm_count() < 0) return CTL_ERR_CUDA;
+  const int64_t total = N * (C / 8) * H * W;
+  bn_bwd_apply_kernel<<<grid_for(total), kT, 0, (cudaStream_t)stream>>>((const uint4*)dy, (const uint4*)h, (const uint4*)a,
+                                                                      coef, (uint4*)da, total, (int)(C / 8), H * W, act);
+  CTL_CUDA_OK(cudaGetLastError(), "bn_bwd_apply launch");
+  return CTL_OK;
+}
+
+extern "C" int ctl_act_bwd_c8(const void* dy, const void* h, int64_t N, int64_t C, int64_t H, int64_t W, int act,
+                              void* dv, void* stream) {
+  if (int rc = check_c8("ctl_act_bwd_c8", dy, h, N, C, H, W)) return rc;
+  CTL_REQUIRE(dv, CTL_ERR_INVALID, "ctl_act_bwd_c8: NULL pointer");
+  if (sm_count() < 0) return CTL_ERR_CUDA;
+  const int64_t total = N * (C / 8) * H * W;
+  act_bwd_kernel<<<grid_for(total), kT, 0, (cudaStream_t)stream>>>((const uint4*)dy, (const uint4*)h, (uint4*)dv, total, act);
+  CTL_CUDA_OK(cudaGetLastError(), "act_bwd launch");
+  return CTL_OK;
+}
+
+extern "C" int ctl_downsample2x_sum_c8(const void* dy, int64_t N, int64_t C, int64_t H, int64_t W, void* dx, void* stream) {
+  if (int rc = check_c8("ctl_downsample2x_sum_c8", dy, dx, N, C, H, W)) return rc;
+  if (sm_count() < 0) return CTL_ERR_CUDA;
+  const int64_t planes = N * (C / 8);
+  downsample2x_sum_kernel<<<grid_for(planes * H * W), kT, 0, (cudaStream_t)stream>>>((const uint4*)dy, (uint4*)dx, planes,
+                                                                                   (int)H, (int)W);
+  CTL_CUDA_OK(cudaGetLastError(), "downsample2x_sum launch");
+  return CTL_OK;
+}
+
+extern "C" int ctl_zero_stuff2x_c8(const void* x, int64_t N, int64_t C, int64_t H, int64_t W, void* y, void* stream) {
+  if (int rc = check_c8("ctl_zero_stuff2x_c8", x, y, N, C, H, W)) return rc;
+  if (sm_count() < 0) return CTL_ERR_CUDA;
+  const int64_t planes = N * (C / 8);
+  zero_stuff2x_kernel<<<grid_for(planes * H * W), kT, 0, (cudaStream_t)stream>>>((const uint4*)x, (uint4*)y, planes, (int)H,
+                                                                               (int)W);
+  CTL_CUDA_OK(cudaGetLastError(), "zero_stuff2x launch");
+  return CTL_OK;
+}
+
+extern "C" int ctl_split_parity2x2_c8(const void* x, int64_t N, int64_t C, int64_t H, int64_t W, void* y, void* stream) {
+  if (int rc = check_c8("ctl_split_parity2x2_c8", x, y, N, C, H, W)) return rc;
+  if (sm_count() < 0) return CTL_ERR_CUDA;
+  const int64_t planes = N * (C / 8);
+  split_parity2x2_kernel<<<grid_for(planes * H * W), kT, 0, (cudaStream_t)stream>>>((const uint4*)x, (uint4*)y, planes,
+                                                                                  (int)H, (int)W);
+  CTL_CUDA_OK(cudaGetLastError(), "split_parity2x2 launch");
+  return CTL_OK;
+}
+
+extern "C" int ctl_head_bwd_c8(const float* dy, const float* y, const void* x, int64_t N, int64_t Cin, int64_t H,
+                               int64_t W, const float* weight, int64_t Cout, int act, void* dx, float* dW, float* db,
+                               void* stream) {
+  CTL_REQUIRE(dy && x && weight && dx && dW && db && N > 0 && H > 0 && W > 0, CTL_ERR_INVALID,
+              "ctl_head_bwd_c8: bad arguments");
+  CTL_REQUIRE(Cin == 16 && (Cout == 1 || Cout == 4), CTL_ERR_UNSUPPORTED,
+              "ctl_head_bwd_c8 handles Cin 16 -> Cout in {1,4} (got %lld -> %lld)", (long long)Cin, (long long)Cout);
+  CTL_REQUIRE(act == CTL_ACT_NONE || (act == CTL_ACT_SIGMOID && y), CTL_ERR_INVALID,
+              "ctl_head_bwd_c8: act must be none, or sigmoid with the forward output y");
+  if (sm_count() < 0) return CTL_ERR_CUDA;
+  cudaStream_t st = (cudaStream_t)stream;
+  const unsigned grid = (unsigned)std::min<int64_t>(ceil_div(N * H * W, kT), (int64_t)sm_count() * 4);
+  if (Cout == 1)
+    head_bwd_kernel<1><<<grid, kT, 0, st>>>(dy, y, (const __nv_bfloat16*)x, weight, (__nv_bfloat16*)dx, dW, db, (int)N, H * W, act);
+  else
+    head_bwd_kernel<4><<<grid, kT, 0, st>>>(dy, y, (const __nv_bfloat16*)x, weight, (__nv_bfloat16*)dx, dW, db, (int)N, H * W, act);
+  CTL_CUDA_OK(cudaGetLastError(), "head_bwd launch");
+  return CTL_OK;
+}
+
+extern "C" int ctl_stem_wgrad_c8(const void* dy, const float* x, const int64_t* labels, int in_mode, float temperature,
+                                 int64_t N, int64_t Cin, int64_t H, int64_t W, float* dW, void* stream) {
+  CTL_REQUIRE(dy && dW && N > 0 && H > 0 && W > 0, CTL_ERR_INVALID, "ctl_stem_wgrad_c8: bad arguments");
+  CTL_REQUIRE(in_mode >= 0 && in_mode <= 2 && (in_mode == 2 ? labels != nullptr : x != nullptr), CTL_ERR_INVALID,
+              "ctl_stem_wgrad_c8: in_mode %d needs %s", in_mode, in_mode == 2 ? "labels" : "x");
+  CTL_REQUIRE(Cin == 1 || Cin == 4, CTL_ERR_UNSUPPORTED, "ctl_stem_wgrad_c8 handles Cin in {1,4} (got %lld)", (long long)Cin);
+  CTL_REQUIRE(temperature > 0.0f, CTL_ERR_INVALID, "temperature must be positive");
+  if (sm_count() < 0) return CTL_ERR_CUDA;
+  cudaStream_t st = (cudaStream_t)stream;
+  const int64_t tiles = N * ceil_div(W, 32) * ceil_div(H, 8);
+  const unsigned grid = (unsigned)std::min<int64_t>(tiles, (int64_t)sm_count() * 2);
+  const long long* lab = reinterpret_cast<const long long*>(labels);
+  if (Cin == 1)
+    stem_wgrad_kernel<1><<<grid, kT, 0, st>>>((const __nv_bfloat16*)dy, x, lab, in_mode, 1.0f / temperature, (int)N, (int)H, (int)W, dW);
+  else
+    stem_wgrad_kernel<4><<<grid, kT, 0, st>>>((const __nv_bfloat16*)dy, x, lab, in_mode, 1.0f / temperature, (int)N, (int)H, (int)W, dW);
+  CTL_CUDA_OK(cudaGetLastError(), "stem_wgrad launch");
+  return CTL_OK;
+}
+
+extern "C" int ctl_stem_dgrad_c8(const void* dy, const float* x, int in_mode, float temperature, int64_t N, int64_t Cin,
+                                 int64_t H, int64_t W, const float* weight, float* dx, void* stream) {
+  CTL_REQUIRE(dy && weight && dx && N > 0 && H > 0 && W > 0, CTL_ERR_INVALID, "ctl_stem_dgrad_c8: bad arguments");
+  CTL_REQUIRE(in_mode == 0 || (in_mode == 1 && x != nullptr), CTL_ERR_INVALID,
+              "ctl_stem_dgrad_c8: in_mode must be 0, or 1 with the forward input x (a label map has no gradient)");
+  CTL_REQUIRE(Cin == 1 || Cin == 4, CTL_ERR_UNSUPPORTED, "ctl_stem_dgrad_c8 handles Cin in {1,4} (got %lld)", (long long)Cin);
+  CTL_REQUIRE(temperature > 0.0f, CTL_ERR_INVALID, "temperature must be positive");
+  if (sm_count() < 0) return CTL_ERR_CUDA;
+  cudaStream_t st = (cudaStream_t)stream;
+  const unsigned grid = grid_for(N * H * W);
+  if (Cin == 1)
+    stem_dgrad_kernel<1><<<grid, kT, 0, st>>>((const __nv_bfloat16*)dy, x, weight, in_mode, 1.0f / temperature, (int)N, (int)H, (int)W, dx);
+  else
+    stem_dgrad_kernel<4><<<grid, kT, 0, st>>>((const __nv_bfloat16*)dy, x, weight, in_mode, 1.0f / temperature, (int)N, (int)H, (int)W, dx);
+  CTL_CUDA_OK(cudaGetLastError(), "stem_dgrad launch");
+  return CTL_OK;
+}

@@ -1,7 +1,7 @@
 // CUDA-core kernels around K3 for the blocked activation layout C8 = bf16 [N][C/8][H][W][8]:
 // layout conversion, the stem convolution (Cin = 1 / 4: K = 9 / 36 is below what a UMMA tile can use, SURVEY.md
 // 7.3 #4) with the STN input construction fused into its prologue, the 1x1 head (Cout = 1 / 4), nearest x2
-// up-sampling, train-mode BatchNorm statistics and the per-channel scale/shift/activation pass.
+// up-sampling and the per-channel scale/shift/activation pass (train-mode BatchNorm statistics: c8_bwd.cu).
 // All of them are HBM-bound streaming kernels: 16-byte accesses, consecutive threads on consecutive pixels.
 //
 // Reference code replaced:
@@ -75,45 +75,46 @@ __global__ void __launch_bounds__(kT) c8_to_nchw_kernel(const __nv_bfloat16* __r
 // 3x3 pad-1 conv from a planar (NCHW) input with CIN <= 4 channels to COUT (16) blocked channels, then
 // y = act(acc*scale + shift).  in_mode: 0 = fp32 NCHW as is, 1 = softmax(x / temperature) over the CIN channels
 // (STN input built from logits), 2 = one-hot of an int64 label map [N,H,W] (STN input built from labels).
+// CTA = one 32x8 pixel tile per iteration (persistent): the input tile with its halo is built ONCE in shared memory
+// (softmax / one-hot evaluated once per pixel instead of nine times), then every thread owns one output pixel.
 template <int CIN, int COUT>
 __global__ void __launch_bounds__(kT)
 stem_conv_kernel(const float* __restrict__ x, const long long* __restrict__ labels, const float* __restrict__ w /*[COUT][CIN][3][3]*/,
                  const float* __restrict__ scale, const float* __restrict__ shift, __nv_bfloat16* __restrict__ y, int N,
                  int H, int W, int in_mode, float inv_temp, int act) {
+  constexpr int TW = 32, TH = 8, HW_T = TW + 2, HH_T = TH + 2;
   __shared__ __align__(16) float sw[COUT * CIN * 9];
   __shared__ float ssc[COUT], ssh[COUT];
+  __shared__ float s_in[CIN][HH_T][HW_T + 1];
   // transposed to [ci][tap][COUT] so that one 16-byte broadcast read feeds four output channels
   for (int i = threadIdx.x; i < COUT * CIN * 9; i += kT) {
     const int c = i / (CIN * 9), rest = i - c * (CIN * 9);
     sw[rest * COUT + c] = w[i];
   }
   for (int i = threadIdx.x; i < COUT; i += kT) { ssc[i] = scale ? scale[i] : 1.0f; ssh[i] = shift ? shift[i] : 0.0f; }
-  __syncthreads();
-  const int64_t HW = (int64_t)H * W, total = (int64_t)N * HW;
-  for (int64_t i = (int64_t)blockIdx.x * kT + threadIdx.x; i < total; i += (int64_t)gridDim.x * kT) {
-    const int n = (int)(i / HW);
-    const int pix = (int)(i - (int64_t)n * HW);
-    const int yy = pix / W, xx = pix - yy * W;
-    float acc[COUT];
+  const int tiles_x = (W + TW - 1) / TW, tiles_y = (H + TH - 1) / TH;
+  const int64_t HW = (int64_t)H * W, num_tiles = (int64_t)N * tiles_x * tiles_y;
+  const int py = threadIdx.x / TW, px = threadIdx.x % TW;
+  for (int64_t tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+    const int64_t n = tile / (tiles_x * tiles_y);
+    const int rem = (int)(tile - n * tiles_x * tiles_y);
+    const int y0 = (rem / tiles_x) * TH, x0 = (rem % tiles_x) * TW;
+    __syncthreads();                                      // previous tile's readers are done (and sw is visible)
+    for (int i = threadIdx.x; i < HH_T * HW_T; i += kT) {
+      const int hy = i / HW_T, hx = i - hy * HW_T;
+      const int iy = y0 + hy - 1, ix = x0 + hx - 1;
+      float v[CIN];
 #pragma unroll
-    for (int c = 0; c < COUT; ++c) acc[c] = 0.0f;
-#pragma unroll
-    for (int r = 0; r < 3; ++r) {
-      const int iy = yy + r - 1;
-      if (iy < 0 || iy >= H) continue;
-#pragma unroll
-      for (int s = 0; s < 3; ++s) {
-        const int ix = xx + s - 1;
-        if (ix < 0 || ix >= W) continue;
-        float v[CIN];
+      for (int ci = 0; ci < CIN; ++ci) v[ci] = 0.0f;
+      if (iy >= 0 && iy < H && ix >= 0 && ix < W) {
         const int64_t q = (int64_t)iy * W + ix;
         if (in_mode == 2) {
-          const long long lab = labels[(int64_t)n * HW + q];
+          const long long lab = labels[n * HW + q];
 #pragma unroll
           for (int ci = 0; ci < CIN; ++ci) v[ci] = (lab == ci) ? 1.0f : 0.0f;
         } else {
 #pragma unroll
-          for (int ci = 0; ci < CIN; ++ci) v[ci] = x[((int64_t)n * CIN + ci) * HW + q];
+          for (int ci = 0; ci < CIN; ++ci) v[ci] = x[(n * CIN + ci) * HW + q];
           if (in_mode == 1) {
             float mx = v[0];
 #pragma unroll
@@ -126,26 +127,43 @@ stem_conv_kernel(const float* __restrict__ x, const long long* __restrict__ labe
             for (int ci = 0; ci < CIN; ++ci) v[ci] *= inv;
           }
         }
+      }
 #pragma unroll
-        for (int ci = 0; ci < CIN; ++ci) {
-          const float4* wv = reinterpret_cast<const float4*>(sw + (ci * 9 + r * 3 + s) * COUT);
+      for (int ci = 0; ci < CIN; ++ci) s_in[ci][hy][hx] = v[ci];
+    }
+    __syncthreads();
+    const int yy = y0 + py, xx = x0 + px;
+    if (yy < H && xx < W) {
+      float acc[COUT];
 #pragma unroll
-          for (int c4 = 0; c4 < COUT / 4; ++c4) {
-            const float4 ww = wv[c4];
-            acc[4 * c4] = fmaf(v[ci], ww.x, acc[4 * c4]);
-            acc[4 * c4 + 1] = fmaf(v[ci], ww.y, acc[4 * c4 + 1]);
-            acc[4 * c4 + 2] = fmaf(v[ci], ww.z, acc[4 * c4 + 2]);
-            acc[4 * c4 + 3] = fmaf(v[ci], ww.w, acc[4 * c4 + 3]);
+      for (int c = 0; c < COUT; ++c) acc[c] = 0.0f;
+#pragma unroll
+      for (int ci = 0; ci < CIN; ++ci) {
+#pragma unroll
+        for (int r = 0; r < 3; ++r) {
+#pragma unroll
+          for (int s2 = 0; s2 < 3; ++s2) {
+            const float v = s_in[ci][py + r][px + s2];
+            const float4* wv = reinterpret_cast<const float4*>(sw + (ci * 9 + r * 3 + s2) * COUT);
+#pragma unroll
+            for (int c4 = 0; c4 < COUT / 4; ++c4) {
+              const float4 ww = wv[c4];
+              acc[4 * c4] = fmaf(v, ww.x, acc[4 * c4]);
+              acc[4 * c4 + 1] = fmaf(v, ww.y, acc[4 * c4 + 1]);
+              acc[4 * c4 + 2] = fmaf(v, ww.z, acc[4 * c4 + 2]);
+              acc[4 * c4 + 3] = fmaf(v, ww.w, acc[4 * c4 + 3]);
+            }
           }
         }
       }
-    }
+      const int64_t pix = (int64_t)yy * W + xx;
 #pragma unroll
-    for (int c8 = 0; c8 < COUT / 8; ++c8) {
-      float f[8];
+      for (int c8 = 0; c8 < COUT / 8; ++c8) {
+        float f[8];
 #pragma unroll
-      for (int j = 0; j < 8; ++j) f[j] = act_fn(acc[c8 * 8 + j] * ssc[c8 * 8 + j] + ssh[c8 * 8 + j], act);
-      *reinterpret_cast<uint4*>(y + (((int64_t)n * (COUT / 8) + c8) * HW + pix) * 8) = pack8(f);
+        for (int j = 0; j < 8; ++j) f[j] = act_fn(acc[c8 * 8 + j] * ssc[c8 * 8 + j] + ssh[c8 * 8 + j], act);
+        *reinterpret_cast<uint4*>(y + ((n * (COUT / 8) + c8) * HW + pix) * 8) = pack8(f);
+      }
     }
   }
 }
@@ -192,70 +210,6 @@ upsample2x_c8_kernel(const uint4* __restrict__ x, uint4* __restrict__ y, int64_t
     const uint4 v = x[i];
     uint4* o = y + pl * 4 * H * W + (int64_t)(2 * yy) * (2 * W) + 2 * xx;
     o[0] = v; o[1] = v; o[2 * W] = v; o[2 * W + 1] = v;
-  }
-}
-
-// ------------------------------------------------------------------------------------------------ BN
-// stage 1: per (n, c8) plane sums of x and x^2 (fp64 accumulation) -> partial[n][C][2]
-__global__ void __launch_bounds__(kT)
-bn_partial_stats_kernel(const __nv_bfloat16* __restrict__ x, double* __restrict__ partial, int C8, int64_t HW) {
-  const int64_t nc = blockIdx.x;              // n*C8 + c8
-  const uint4* p = reinterpret_cast<const uint4*>(x) + nc * HW;
-  double s[8], q[8];
-#pragma unroll
-  for (int j = 0; j < 8; ++j) { s[j] = 0.0; q[j] = 0.0; }
-  for (int64_t i = threadIdx.x; i < HW; i += kT) {
-    float f[8];
-    unpack8(__ldcs(p + i), f);
-#pragma unroll
-    for (int j = 0; j < 8; ++j) { s[j] += (double)f[j]; q[j] += (double)f[j] * (double)f[j]; }
-  }
-  __shared__ double red[kT / 32][16];
-#pragma unroll
-  for (int j = 0; j < 8; ++j) {
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-      s[j] += __shfl_xor_sync(0xffffffffu, s[j], o);
-      q[j] += __shfl_xor_sync(0xffffffffu, q[j], o);
-    }
-  }
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  if (lane == 0) {
-#pragma unroll
-    for (int j = 0; j < 8; ++j) { red[warp][j] = s[j]; red[warp][8 + j] = q[j]; }
-  }
-  __syncthreads();
-  if (threadIdx.x < 16) {
-    double t = 0.0;
-    for (int w = 0; w < kT / 32; ++w) t += red[w][threadIdx.x];
-    const int j = threadIdx.x & 7, is_sq = threadIdx.x >> 3;
-    partial[(nc * 8 + j) * 2 + is_sq] = t;    // [n][c][2] with c = c8*8 + j
-  }
-}
-// stage 2: batch mean / biased variance -> fused affine y = x*scale + shift (scale = gamma*rsqrt(var+eps),
-// shift = beta - mean*scale); optional running-stat update (momentum, unbiased variance) like nn.BatchNorm2d.
-__global__ void bn_finalize_kernel(const double* __restrict__ partial, int N, int C, double count,
-                                   const float* __restrict__ gamma, const float* __restrict__ beta, float eps,
-                                   float* __restrict__ scale, float* __restrict__ shift, float* __restrict__ mean_out,
-                                   float* __restrict__ var_out, float* running_mean, float* running_var,
-                                   float momentum) {
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c >= C) return;
-  double s = 0.0, q = 0.0;
-  for (int n = 0; n < N; ++n) { s += partial[((int64_t)n * C + c) * 2]; q += partial[((int64_t)n * C + c) * 2 + 1]; }
-  const double mean = s / count;
-  double var = q / count - mean * mean;
-  if (var < 0.0) var = 0.0;
-  const float inv = (float)(1.0 / sqrt(var + (double)eps));
-  const float g = gamma ? gamma[c] : 1.0f, b = beta ? beta[c] : 0.0f;
-  scale[c] = g * inv;
-  shift[c] = b - (float)mean * g * inv;
-  if (mean_out) mean_out[c] = (float)mean;
-  if (var_out) var_out[c] = (float)var;
-  if (running_mean) {
-    const double unbiased = count > 1.0 ? var * count / (count - 1.0) : var;
-    running_mean[c] = (1.0f - momentum) * running_mean[c] + momentum * (float)mean;
-    running_var[c] = (1.0f - momentum) * running_var[c] + momentum * (float)unbiased;
   }
 }
 
@@ -327,7 +281,8 @@ extern "C" int ctl_stem_conv3x3_c8(const float* x, const int64_t* labels, int in
   CTL_REQUIRE(temperature > 0.0f, CTL_ERR_INVALID, "temperature must be positive");
   if (sm_count() < 0) return CTL_ERR_CUDA;
   cudaStream_t st = (cudaStream_t)stream;
-  const unsigned grid = grid_for(N * H * W);
+  const int64_t tiles = N * ceil_div(W, 32) * ceil_div(H, 8);
+  const unsigned grid = (unsigned)std::min<int64_t>(tiles, (int64_t)sm_count() * 4);
   const long long* lab = reinterpret_cast<const long long*>(labels);
   if (Cin == 1)
     stem_conv_kernel<1, 16><<<grid, kT, 0, st>>>(x, lab, weight, scale, shift, (__nv_bfloat16*)y, (int)N, (int)H, (int)W,
@@ -358,28 +313,6 @@ extern "C" int ctl_upsample2x_c8(const void* x, int64_t N, int64_t C, int64_t H,
   upsample2x_c8_kernel<<<grid_for(planes * H * W), kT, 0, (cudaStream_t)stream>>>((const uint4*)x, (uint4*)y, planes,
                                                                                 (int)H, (int)W);
   CTL_CUDA_OK(cudaGetLastError(), "upsample2x launch");
-  return CTL_OK;
-}
-
-extern "C" size_t ctl_bn_workspace_bytes(int64_t N, int64_t C) { return (N > 0 && C > 0) ? (size_t)(N * C * 2) * sizeof(double) : 0; }
-
-extern "C" int ctl_bn_batch_affine_c8(const void* x, int64_t N, int64_t C, int64_t H, int64_t W, const float* gamma,
-                                      const float* beta, float eps, void* workspace, float* scale, float* shift,
-                                      float* mean_out, float* var_out, float* running_mean, float* running_var,
-                                      float momentum, void* stream) {
-  CTL_REQUIRE(x && workspace && scale && shift && N > 0 && C > 0 && C % 8 == 0 && H > 0 && W > 0, CTL_ERR_INVALID,
-              "ctl_bn_batch_affine_c8: bad arguments");
-  CTL_REQUIRE((running_mean == nullptr) == (running_var == nullptr), CTL_ERR_INVALID,
-              "running_mean and running_var must be given together");
-  if (sm_count() < 0) return CTL_ERR_CUDA;
-  cudaStream_t st = (cudaStream_t)stream;
-  bn_partial_stats_kernel<<<(unsigned)(N * (C / 8)), kT, 0, st>>>((const __nv_bfloat16*)x, (double*)workspace, (int)(C / 8),
-                                                                 H * W);
-  CTL_CUDA_OK(cudaGetLastError(), "bn_partial_stats launch");
-  bn_finalize_kernel<<<(unsigned)ceil_div(C, 128), 128, 0, st>>>((const double*)workspace, (int)N, (int)C,
-                                                                 (double)(N * H * W), gamma, beta, eps, scale, shift,
-                                                                 mean_out, var_out, running_mean, running_var, momentum);
-  CTL_CUDA_OK(cudaGetLastError(), "bn_finalize launch");
   return CTL_OK;
 }
 

@@ -22,8 +22,10 @@
 //             8-column M tile into one of two TMEM accumulator stages, then tcgen05.commit frees the
 //             smem stage and publishes the accumulator.
 //   warp 2  : TMEM allocator; warp 3 idle.
-//   warps 4-7: epilogue     -- tcgen05.ld 16 columns at a time, y = act(acc*scale + shift + res*rs + rb),
-//             bf16 pack, 16-byte stores (optionally scattered 2x2 for ConvTranspose2d k2 s2).
+//   warps 4-11: epilogue    -- two warps per TMEM sub-partition share a tile's (M tile, 16-column chunk) items:
+//             tcgen05.ld 16 columns, residual requested before the TMEM wait, y = act(acc*scale + shift + res*rs + rb),
+//             bf16 pack, 16-byte stores (optionally scattered 2x2 for ConvTranspose2d k2 s2), optional per-channel
+//             sum / sum-of-squares of the stored values (train-mode BatchNorm statistics without a second pass).
 #include <algorithm>
 
 #include "ctl_common.cuh"
@@ -35,8 +37,7 @@ namespace {
 using namespace sm100;
 
 constexpr int kTileH = 16;            // output rows per tile (= 8-row groups of the M=128 MMA: one group per row)
-constexpr int kConvThreads = 256;
-constexpr int kAccStages = 2;
+constexpr int kConvThreads = 384;      // warps 0-3: TMA, MMA, TMEM allocator, spare; warps 4-11: epilogue
 
 struct ConvParams {
   int N, H, W;                        // input (= full-resolution output) size
@@ -53,6 +54,7 @@ struct ConvParams {
   int act;                            // ctl_act
   int subsample;                      // 1: Ho=H, Wo=W; 2: keep even (y,x) -> Ho=H/2, Wo=W/2 (3x3 stride-2 pad-1)
   int up2x;                           // 1: ConvTranspose2d(k=2,s=2) scatter: GEMM column n = (dy*2+dx)*Cout/4 + co
+  double* stats;                      // [2][Cout] sum / sum of squares of the stored outputs, accumulated into (or nullptr)
 };
 
 __device__ __forceinline__ float apply_act(float v, int act) {
@@ -74,7 +76,9 @@ struct ConvCfg {
   static constexpr int kStageBytes = (CIN / 8) * kChunkStride;
   static constexpr int kStageTxBytes = kStageBytes;               // bytes the TMA load of one stage delivers
   static constexpr int kWBytes = TAPS * CIN * NT * 2;
-  static constexpr int kTmemCols = kAccStages * MT * NT;
+  // accumulator stages: the MMA issuer (and with it the TMA ring) runs up to kAcc tiles ahead of the epilogue
+  static constexpr int kAcc = (512 / (MT * NT)) >= 4 ? 4 : 2;
+  static constexpr int kTmemCols = kAcc * MT * NT;
   static constexpr int kTmemAlloc = kTmemCols <= 32 ? 32 : kTmemCols <= 64 ? 64 : kTmemCols <= 128 ? 128
                                     : kTmemCols <= 256 ? 256 : 512;
   // smem carve-up (all offsets multiples of 128)
@@ -82,12 +86,12 @@ struct ConvCfg {
   static constexpr int kOffA = (kWBytes + 127) / 128 * 128;
   static constexpr int kOffVec = kOffA + STAGES * ((kStageBytes + 127) / 128 * 128);   // 4 x NT floats
   static constexpr int kOffBar = kOffVec + 4 * NT * 4;
-  static constexpr int kSmemBytes = kOffBar + 128;
+  static constexpr int kSmemBytes = kOffBar + 256;
   static_assert(kTmemCols <= 512, "accumulators exceed TMEM");
   static_assert(CIN % 16 == 0 && NT % 16 == 0 && NT <= 256, "UMMA shape");
   static_assert(kSmemBytes <= 227 * 1024, "shared memory budget");
   static_assert((kChunkStride >> 4) < 16384 && kHaloW * 16 < 16384 * 16, "descriptor range");
-  static_assert(kHaloW * 8 <= 256 && kHaloH <= 256 && CIN / 8 <= 256, "TMA box dimensions");
+  static_assert(kHaloW * 2 <= 256 && kHaloH <= 256 && CIN / 8 <= 256, "TMA box dimensions (8-byte elements)");
 };
 
 template <int CIN, int NT, int TAPS, int MT, int STAGES>
@@ -101,10 +105,11 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap, const ConvParams p) {
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Cfg::kOffBar);
   uint64_t* full = bars;                        // [STAGES]  TMA -> MMA
   uint64_t* empty = bars + STAGES;              // [STAGES]  MMA -> TMA
-  uint64_t* acc_full = bars + 2 * STAGES;       // [2]       MMA -> epilogue
-  uint64_t* acc_empty = bars + 2 * STAGES + 2;  // [2]       epilogue -> MMA
-  uint64_t* w_full = bars + 2 * STAGES + 4;     // [1]       weights landed
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 5);
+  constexpr int kAccStages = Cfg::kAcc;
+  uint64_t* acc_full = bars + 2 * STAGES;                    // [kAcc]  MMA -> epilogue
+  uint64_t* acc_empty = bars + 2 * STAGES + kAccStages;      // [kAcc]  epilogue -> MMA
+  uint64_t* w_full = bars + 2 * STAGES + 2 * kAccStages;     // [1]     weights landed
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 2 * kAccStages + 1);
   constexpr int kStageStride = (Cfg::kStageBytes + 127) / 128 * 128;
 
   const int warp = threadIdx.x >> 5;
@@ -115,7 +120,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap, const ConvParams p) {
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmap);
     for (int i = 0; i < STAGES; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
-    for (int i = 0; i < kAccStages; ++i) { mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], 4); }
+    for (int i = 0; i < kAccStages; ++i) { mbar_init(&acc_full[i], 1); mbar_init(&acc_empty[i], 8); }
     mbar_init(w_full, 1);
     mbar_fence_init();
   }
@@ -148,7 +153,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap, const ConvParams p) {
         const int y0 = ty * kTileH - Cfg::kPad, x0 = tx * (8 * MT) - Cfg::kPad;
         mbar_wait(&empty[stage], phase ^ 1);
         mbar_arrive_expect_tx(&full[stage], Cfg::kStageTxBytes);
-        tma_load_4d(sA + stage * kStageStride, &tmap, &full[stage], x0 * 8, y0, 0, img);
+        tma_load_4d(sA + stage * kStageStride, &tmap, &full[stage], x0 * 2, y0, 0, img);
         if (++stage == STAGES) { stage = 0; phase ^= 1; }
       }
     }
@@ -190,11 +195,22 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap, const ConvParams p) {
       }
     }
   } else if (warp >= 4) {
-    // ================================================================= epilogue (TMEM lanes 32*(warp-4) ..)
-    const int q = warp - 4;                       // == warp % 4: the TMEM sub-partition this warp may read
+    // ================================================================= epilogue: 8 warps, two per TMEM sub-partition
+    const int q = warp & 3;                       // == warp % 4: the TMEM sub-partition this warp may read
+    const int half = (warp - 4) >> 2;             // the tile's (M tile, 16-column chunk) items alternate between the halves
     const int m = q * 32 + lane;                  // accumulator row = pixel within the 16x8 M tile
     const int py = m >> 3, px = m & 7;
     const int Ho = p.H / p.subsample, Wo = p.W / p.subsample;
+    const int64_t plane = (int64_t)Ho * Wo * 8;   // elements per 8-channel plane of the output
+    constexpr int kChunks = NT / 16;
+    constexpr int kItems = MT * kChunks;
+    const int act = p.act;
+    const bool has_res = p.res != nullptr;
+    // train-mode BatchNorm statistics of the stored (bf16-rounded) outputs: every thread owns one 16-column chunk
+    float st_s[16], st_q[16];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) { st_s[i] = 0.0f; st_q[i] = 0.0f; }
+    const bool do_stats = p.stats != nullptr;
     int acc = 0;
     uint32_t acc_phase = 0;
     for (int64_t t = blockIdx.x; t < p.num_tiles; t += gridDim.x) {
@@ -203,56 +219,81 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap, const ConvParams p) {
       const int ty = rem / p.tiles_x, tx = rem - ty * p.tiles_x;
       mbar_wait(&acc_full[acc], acc_phase);
       tc_fence_after();
-#pragma unroll
-      for (int mt = 0; mt < MT; ++mt) {
+#pragma unroll 1
+      for (int item = half; item < kItems; item += 2) {
+        const int mt = item / kChunks, c0 = (item - mt * kChunks) * 16;
         const int y = ty * kTileH + py, x = tx * (8 * MT) + mt * 8 + px;
         bool valid = y < p.H && x < p.W;
         int yo = y, xo = x;
         if (p.subsample == 2) { valid = valid && !((y | x) & 1); yo = y >> 1; xo = x >> 1; }
-        const int64_t plane = (int64_t)Ho * Wo * 8;                          // elements per 8-channel plane
-        const int64_t pix8 = ((int64_t)yo * Wo + xo) * 8;
-        const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)((acc * MT + mt) * NT);
-#pragma unroll 1
-        for (int c0 = 0; c0 < NT; c0 += 16) {
-          uint32_t v[16];
-          tmem_ld_32x32b_x16(t_row + (uint32_t)c0, v);      // warp-collective: executed by every lane
-          tmem_ld_wait();
-          if (valid) {
-            float f[16];
+        uint32_t v[16];
+        tmem_ld_32x32b_x16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)((acc * MT + mt) * NT + c0), v);
+        // output offsets of the two 8-channel planes of this chunk (and the residual, requested before the TMEM wait)
+        int64_t off[2];
 #pragma unroll
-            for (int i = 0; i < 16; ++i) f[i] = __uint_as_float(v[i]) * sVec[c0 + i] + sVec[NT + c0 + i];
+        for (int h8 = 0; h8 < 2; ++h8) {
+          const int n = n0 + c0 + 8 * h8;          // GEMM column of this plane's first channel
+          if (p.up2x) {
+            const int cq = p.Cout >> 2, qd = n / cq, co = n - qd * cq;       // n = (dy*2+dx)*Cout/4 + co
+            const int y2 = 2 * y + (qd >> 1), x2 = 2 * x + (qd & 1);
+            off[h8] = ((int64_t)img * (cq >> 3) + (co >> 3)) * (plane * 4) + ((int64_t)y2 * (2 * Wo) + x2) * 8;
+          } else {
+            off[h8] = ((int64_t)img * (p.Cout >> 3) + (n >> 3)) * plane + ((int64_t)yo * Wo + xo) * 8;
+          }
+        }
+        uint4 rr[2] = {make_uint4(0, 0, 0, 0), make_uint4(0, 0, 0, 0)};
+        if (has_res && valid) {
+          rr[0] = __ldg(reinterpret_cast<const uint4*>(p.res + off[0]));
+          rr[1] = __ldg(reinterpret_cast<const uint4*>(p.res + off[1]));
+        }
+        tmem_ld_wait();
+        if (valid) {
+          float f[16];
 #pragma unroll
-            for (int h8 = 0; h8 < 2; ++h8) {                 // two 8-channel planes per 16 accumulator columns
-              const int n = n0 + c0 + 8 * h8;                // GEMM column of this plane's first channel
-              int64_t off;
-              if (p.up2x) {
-                const int cq = p.Cout >> 2, qd = n / cq, co = n - qd * cq;   // n = (dy*2+dx)*Cout/4 + co
-                const int y2 = 2 * y + (qd >> 1), x2 = 2 * x + (qd & 1);
-                off = ((int64_t)img * (cq >> 3) + (co >> 3)) * (plane * 4) + ((int64_t)y2 * (2 * Wo) + x2) * 8;
-              } else {
-                off = ((int64_t)img * (p.Cout >> 3) + (n >> 3)) * plane + pix8;
-              }
-              float* g = f + 8 * h8;
-              if (p.res) {
-                const uint4 r = *reinterpret_cast<const uint4*>(p.res + off);
-                const uint32_t rw[4] = {r.x, r.y, r.z, r.w};
-                const float* rsc = sVec + 2 * NT + c0 + 8 * h8;
-                const float* rsh = sVec + 3 * NT + c0 + 8 * h8;
+          for (int i4 = 0; i4 < 4; ++i4) {
+            const float4 sc = *reinterpret_cast<const float4*>(sVec + c0 + 4 * i4);
+            const float4 sh = *reinterpret_cast<const float4*>(sVec + NT + c0 + 4 * i4);
+            f[4 * i4] = fmaf(__uint_as_float(v[4 * i4]), sc.x, sh.x);
+            f[4 * i4 + 1] = fmaf(__uint_as_float(v[4 * i4 + 1]), sc.y, sh.y);
+            f[4 * i4 + 2] = fmaf(__uint_as_float(v[4 * i4 + 2]), sc.z, sh.z);
+            f[4 * i4 + 3] = fmaf(__uint_as_float(v[4 * i4 + 3]), sc.w, sh.w);
+          }
+          if (has_res) {
 #pragma unroll
-                for (int i = 0; i < 4; ++i) {
-                  g[2 * i] += __uint_as_float(rw[i] << 16) * rsc[2 * i] + rsh[2 * i];
-                  g[2 * i + 1] += __uint_as_float(rw[i] & 0xffff0000u) * rsc[2 * i + 1] + rsh[2 * i + 1];
-                }
-              }
-              uint32_t o[4];
+            for (int h8 = 0; h8 < 2; ++h8) {
+              const uint32_t rw[4] = {rr[h8].x, rr[h8].y, rr[h8].z, rr[h8].w};
 #pragma unroll
               for (int i = 0; i < 4; ++i) {
-                const __nv_bfloat162 hh =
-                    __floats2bfloat162_rn(apply_act(g[2 * i], p.act), apply_act(g[2 * i + 1], p.act));
-                o[i] = *reinterpret_cast<const uint32_t*>(&hh);
+                const int c = 8 * h8 + 2 * i;
+                f[c] += fmaf(__uint_as_float(rw[i] << 16), sVec[2 * NT + c0 + c], sVec[3 * NT + c0 + c]);
+                f[c + 1] += fmaf(__uint_as_float(rw[i] & 0xffff0000u), sVec[2 * NT + c0 + c + 1], sVec[3 * NT + c0 + c + 1]);
               }
-              *reinterpret_cast<uint4*>(p.out + off) = make_uint4(o[0], o[1], o[2], o[3]);
             }
+          }
+          if (act == CTL_ACT_LRELU) {
+#pragma unroll
+            for (int i = 0; i < 16; ++i) f[i] = fmaxf(f[i], 0.2f * f[i]);
+          } else if (act == CTL_ACT_RELU) {
+#pragma unroll
+            for (int i = 0; i < 16; ++i) f[i] = fmaxf(f[i], 0.0f);
+          } else if (act == CTL_ACT_SIGMOID) {
+#pragma unroll
+            for (int i = 0; i < 16; ++i) f[i] = 1.0f / (1.0f + __expf(-f[i]));
+          }
+#pragma unroll
+          for (int h8 = 0; h8 < 2; ++h8) {
+            uint32_t o[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              const __nv_bfloat162 hh = __floats2bfloat162_rn(f[8 * h8 + 2 * i], f[8 * h8 + 2 * i + 1]);
+              o[i] = *reinterpret_cast<const uint32_t*>(&hh);
+              if (do_stats) {
+                const float lo = __uint_as_float(o[i] << 16), hi = __uint_as_float(o[i] & 0xffff0000u);
+                st_s[8 * h8 + 2 * i] += lo;      st_q[8 * h8 + 2 * i] = fmaf(lo, lo, st_q[8 * h8 + 2 * i]);
+                st_s[8 * h8 + 2 * i + 1] += hi;  st_q[8 * h8 + 2 * i + 1] = fmaf(hi, hi, st_q[8 * h8 + 2 * i + 1]);
+              }
+            }
+            *reinterpret_cast<uint4*>(p.out + off[h8]) = make_uint4(o[0], o[1], o[2], o[3]);
           }
         }
       }
@@ -260,6 +301,24 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap, const ConvParams p) {
       __syncwarp();
       if (lane == 0) mbar_arrive(&acc_empty[acc]);
       if (++acc == kAccStages) { acc = 0; acc_phase ^= 1; }
+    }
+    if (do_stats) {
+      // kChunks <= 2 (checked on the host): this thread's chunk is fixed -- chunk `half` when there are two, else 0
+      const int c0 = (kChunks == 2 ? half : 0) * 16;
+      const bool owner = kItems > half;          // MT == 1 && kChunks == 1: the second half never had an item
+#pragma unroll
+      for (int i = 0; i < 16; ++i) {
+        float s1 = st_s[i], s2 = st_q[i];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+          s1 += __shfl_xor_sync(0xffffffffu, s1, o);
+          s2 += __shfl_xor_sync(0xffffffffu, s2, o);
+        }
+        if (lane == 0 && owner) {
+          atomicAdd(p.stats + n0 + c0 + i, (double)s1);
+          atomicAdd(p.stats + p.Cout + n0 + c0 + i, (double)s2);
+        }
+      }
     }
   }
 
@@ -289,16 +348,17 @@ EncodeTiledFn encode_tiled_fn() {
   return fn;
 }
 
-// Blocked bf16 activation [N][C/8][H][W][8] as a 4-D tensor map (W*8, H, C/8, N) with box
-// (halo_w*8, halo_h, C/8, 1): the whole halo tile of all channel planes in one bulk tensor copy.
+// Blocked bf16 activation [N][C/8][H][W][8] as a 4-D tensor map of 8-BYTE elements (W*2, H, C/8, N) with box
+// (halo_w*2, halo_h, C/8, 1): the whole halo tile of all channel planes in one bulk tensor copy (bit-exact whatever
+// the element type; 8-byte elements keep wide halo rows inside the 256-elements-per-box-dimension limit).
 int make_act_tmap(CUtensorMap* m, const void* x, int N, int H, int W, int C, int halo_w, int halo_h) {
   EncodeTiledFn enc = encode_tiled_fn();
   CTL_REQUIRE(enc != nullptr, CTL_ERR_CUDA, "cuTensorMapEncodeTiled is not available from the driver");
-  const cuuint64_t dims[4] = {(cuuint64_t)W * 8, (cuuint64_t)H, (cuuint64_t)(C / 8), (cuuint64_t)N};
+  const cuuint64_t dims[4] = {(cuuint64_t)W * 2, (cuuint64_t)H, (cuuint64_t)(C / 8), (cuuint64_t)N};
   const cuuint64_t strides[3] = {(cuuint64_t)W * 16, (cuuint64_t)H * W * 16, (cuuint64_t)(C / 8) * H * W * 16};
-  const cuuint32_t box[4] = {(cuuint32_t)halo_w * 8, (cuuint32_t)halo_h, (cuuint32_t)(C / 8), 1};
+  const cuuint32_t box[4] = {(cuuint32_t)halo_w * 2, (cuuint32_t)halo_h, (cuuint32_t)(C / 8), 1};
   const cuuint32_t estr[4] = {1, 1, 1, 1};
-  const CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(x), dims, strides, box, estr,
+  const CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_UINT64, 4, const_cast<void*>(x), dims, strides, box, estr,
                          CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   CTL_REQUIRE(r == CUDA_SUCCESS, CTL_ERR_CUDA, "cuTensorMapEncodeTiled failed with CUresult %d", (int)r);
@@ -329,13 +389,13 @@ template <int CIN, int TAPS>
 int dispatch_nt(const void* x, const ConvParams& p, int nt, cudaStream_t st) {
   // MT = 2 (16x16 pixel tiles, halo overhead 1.27x) while the tile ring fits; STAGES from the smem left
   if constexpr (CIN == 16) {
-    if (nt == 16) return launch_conv<16, 16, TAPS, 2, 4>(x, p, st);
-    if (nt == 32) return launch_conv<16, 32, TAPS, 2, 4>(x, p, st);
-    if (nt == 64) return launch_conv<16, 64, TAPS, 2, 4>(x, p, st);
+    if (nt == 16) return launch_conv<16, 16, TAPS, 4, 6>(x, p, st);     // 16 x 32 pixel tiles: fewer, longer TMA rows
+    if (nt == 32) return launch_conv<16, 32, TAPS, 4, 6>(x, p, st);
+    if (nt == 64) return launch_conv<16, 64, TAPS, 2, 6>(x, p, st);
   } else if constexpr (CIN == 32) {
-    if (nt == 16) return launch_conv<32, 16, TAPS, 2, 4>(x, p, st);
-    if (nt == 32) return launch_conv<32, 32, TAPS, 2, 4>(x, p, st);
-    if (nt == 64) return launch_conv<32, 64, TAPS, 2, 3>(x, p, st);
+    if (nt == 16) return launch_conv<32, 16, TAPS, 2, 6>(x, p, st);
+    if (nt == 32) return launch_conv<32, 32, TAPS, 2, 6>(x, p, st);
+    if (nt == 64) return launch_conv<32, 64, TAPS, 2, 4>(x, p, st);
   } else if constexpr (CIN == 64) {
     if (nt == 16) return launch_conv<64, 16, TAPS, 2, 3>(x, p, st);
     if (nt == 32) return launch_conv<64, 32, TAPS, 2, 3>(x, p, st);
@@ -367,7 +427,7 @@ extern "C" int ctl_conv2d_n_tile(int Cin, int Cout, int taps) {
 extern "C" int ctl_conv2d_c8_bf16(const void* x, int64_t N, int64_t H, int64_t W, int64_t Cin, const void* w_packed,
                                   int64_t Cout, int taps, int subsample, int up2x, const float* scale,
                                   const float* shift, const void* res, const float* res_scale, const float* res_shift,
-                                  int act, void* out, void* stream) {
+                                  int act, void* out, double* stats, void* stream) {
   CTL_REQUIRE(x && w_packed && out, CTL_ERR_INVALID, "ctl_conv2d_c8_bf16: NULL pointer");
   CTL_REQUIRE(!up2x || (taps == 1 && subsample == 1 && Cout % 32 == 0), CTL_ERR_INVALID,
               "up2x (ConvTranspose2d k2 s2) needs taps == 1, subsample == 1 and Cout = 4 * out_channels, out_channels %% 8 == 0");
@@ -378,6 +438,8 @@ extern "C" int ctl_conv2d_c8_bf16(const void* x, int64_t N, int64_t H, int64_t W
               "subsample must be 1, or 2 with even H and W");
   CTL_REQUIRE(act >= CTL_ACT_NONE && act <= CTL_ACT_SIGMOID, CTL_ERR_INVALID, "unknown activation %d", act);
   const int nt = ctl_conv2d_n_tile((int)Cin, (int)Cout, taps);
+  CTL_REQUIRE(stats == nullptr || (nt > 0 && nt <= 32 && !up2x), CTL_ERR_UNSUPPORTED,
+              "fused output statistics need an N tile <= 32 (Cout %% 64 != 0 or 3x3 with Cin 128) and no up2x");
   CTL_REQUIRE(nt > 0, CTL_ERR_UNSUPPORTED,
               "ctl_conv2d_c8_bf16 handles Cin in {16,32,64,128} and Cout %% 16 == 0 (got Cin=%lld Cout=%lld)",
               (long long)Cin, (long long)Cout);
@@ -389,7 +451,7 @@ extern "C" int ctl_conv2d_c8_bf16(const void* x, int64_t N, int64_t H, int64_t W
   p.w_packed = (const __nv_bfloat16*)w_packed;
   p.scale = scale; p.shift = shift;
   p.res = (const __nv_bfloat16*)res; p.res_scale = res_scale; p.res_shift = res_shift;
-  p.out = (__nv_bfloat16*)out; p.act = act; p.subsample = subsample; p.up2x = up2x;
+  p.out = (__nv_bfloat16*)out; p.act = act; p.subsample = subsample; p.up2x = up2x; p.stats = stats;
   cudaStream_t st = (cudaStream_t)stream;
   if (taps == 9) {
     switch ((int)Cin) {

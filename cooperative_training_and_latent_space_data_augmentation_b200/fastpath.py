@@ -19,17 +19,19 @@ import torch.nn as nn
 
 from . import ops
 
-_PACKED = {}
-
-
-def _packed(param, fn):
-    """Packed bf16 copy of a weight, rebuilt when the parameter is modified in place (optimizer step) or replaced."""
-    key = id(param)
+def _packed(param, fn, tag='fwd'):
+    """Packed bf16 copy of a weight, rebuilt when the parameter is modified in place (optimizer step) or its storage is
+    replaced.  `tag` distinguishes the packings of one parameter (forward, input-gradient, per-tap transposed-conv
+    slices).  The cache lives ON the parameter object: a global table keyed by id() would hand a new parameter the
+    packed weights of a dead one whose id / address it inherited."""
+    cache = param.__dict__.get('_ctl_packed')
+    if cache is None:
+        cache = param.__dict__['_ctl_packed'] = {}
     ver = (param.data_ptr(), param._version)
-    hit = _PACKED.get(key)
+    hit = cache.get(tag)
     if hit is None or hit[0] != ver:
         hit = (ver, fn(param))
-        _PACKED[key] = hit
+        cache[tag] = hit
     return hit[1]
 
 

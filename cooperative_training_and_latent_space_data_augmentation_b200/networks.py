@@ -18,8 +18,19 @@ import torch
 import torch.nn as nn
 
 from . import conv_blocks as cb
+from . import fastpath, ops, trainpath
 
 LRELU_SLOPE = 0.2
+
+
+def _kernel_route(module, x):
+    """'train': forward+backward on the kernels (trainpath); 'eval': BN-folded no-grad forward (fastpath);
+    None: the torch path of conv_blocks (parity / library modes, CPU tensors, eval-mode BN under autograd)."""
+    if cb.get_precision() != 'kernel' or not x.is_cuda:
+        return None
+    if module.training:
+        return 'train'
+    return None if torch.is_grad_enabled() else 'eval'
 
 
 def _only_supported(if_SN, dropout, norm):
@@ -88,9 +99,26 @@ class MyEncoder(nn.Module):
         self.act = act
 
     def forward(self, x):
+        route = _kernel_route(self, x)
+        if route == 'train':
+            return trainpath.encoder_apply(self, x)
+        if route == 'eval':
+            return ops.c8_to_nchw(fastpath.encoder_forward(self, x, 'eval'))
         x = cb.stem(self.inc, x)
         x = self.down4(self.down3(self.down2(self.down1(x))))
         return cb.conv_bn_act(self.final_conv[0], self.final_conv[1], x, self.act)
+
+    def forward_from_segmentation(self, segmentation, is_label_map=False, temperature=2):
+        """STN entry (construct_input fused into the stem kernel): logits -> softmax(x / T), label map -> one-hot.
+        Only valid on the kernel routes; the caller falls back to construct_input + forward otherwise."""
+        route = _kernel_route(self, segmentation)
+        in_mode = 2 if is_label_map else 1
+        if route == 'train':
+            return trainpath.encoder_apply(self, segmentation, in_mode=in_mode, temperature=temperature)
+        if route == 'eval':
+            return ops.c8_to_nchw(fastpath.encoder_forward(self, segmentation, 'eval', in_mode=in_mode,
+                                                           temperature=temperature))
+        return None
 
 
 class MyDecoder(nn.Module):
@@ -107,6 +135,11 @@ class MyDecoder(nn.Module):
         self.last_act = last_act
 
     def forward(self, x):
+        route = _kernel_route(self, x)
+        if route == 'train':
+            return trainpath.decoder_apply(self, x)
+        if route == 'eval':
+            return fastpath.decoder_from_nchw(self, x, 'eval')
         x = self.up4(self.up3(self.up2(self.up1(x))))
         return cb.head(self.final_conv, x, self.last_act)
 
@@ -126,9 +159,20 @@ class Dual_Branch_Encoder(nn.Module):
             nn.Conv2d(c2, c2, 3, padding=1, bias=True), norm(c2), nn.ReLU())
 
     def filter_code(self, z):
+        route = _kernel_route(self, z)
+        if route == 'train':
+            return trainpath.decoupler_apply(self, z)
+        if route == 'eval':
+            return ops.c8_to_nchw(fastpath.filter_code(self, ops.nchw_to_c8(z), 'eval'))
         return cb.double_conv(self.code_decoupler, z, final_act=self.code_decoupler[5])
 
     def forward(self, x):
+        route = _kernel_route(self, x)
+        if route == 'train':
+            return trainpath.dual_encoder_apply(self, x)
+        if route == 'eval':
+            z_i = fastpath.encoder_forward(self.general_encoder, x, 'eval')
+            return ops.c8_to_nchw(z_i), ops.c8_to_nchw(fastpath.filter_code(self, z_i, 'eval'))
         z_i = self.general_encoder(x)
         return z_i, self.filter_code(z_i)
 

@@ -214,10 +214,16 @@ def pack_convtranspose2x2_weight(weight):
     return pack_conv_weight(w)
 
 
+def conv_stats_fusable(cin, cout, taps):
+    """True when the conv epilogue can accumulate the BatchNorm statistics of its own output (N tile <= 32)."""
+    return 0 < _lib.load().ctl_conv2d_n_tile(int(cin), int(cout), int(taps)) <= 32
+
+
 def conv2d_c8(x, w_packed, cout, taps, subsample=1, up2x=False, scale=None, shift=None, res=None, res_scale=None,
-              res_shift=None, act=ACT_NONE):
+              res_shift=None, act=ACT_NONE, stats=None):
     """out = act(conv(x) * scale + shift + res * res_scale + res_shift) on the tcgen05 kernel; C8 in, C8 out.
-    `cout` is the number of GEMM columns (4 * out_channels when up2x)."""
+    `cout` is the number of GEMM columns (4 * out_channels when up2x).  stats: zeroed float64 [2, cout] that receives
+    the per-channel sum / sum of squares of the stored outputs (see conv_stats_fusable)."""
     _need_cuda(x, w_packed, scale, shift, res, res_scale, res_shift)
     N, cin, H, W = _c8_dims(x)
     if up2x:
@@ -230,8 +236,21 @@ def conv2d_c8(x, w_packed, cout, taps, subsample=1, up2x=False, scale=None, shif
     with torch.cuda.device(x.device):
         _lib.check(_lib.load().ctl_conv2d_c8_bf16(
             x.data_ptr(), N, H, W, cin, w_packed.data_ptr(), cout, taps, subsample, int(bool(up2x)), _ptr(sc), _ptr(sh),
-            _ptr(res), _ptr(rs), _ptr(rb), act, out.data_ptr(), _stream()))
+            _ptr(res), _ptr(rs), _ptr(rb), act, out.data_ptr(), _ptr(stats), _stream()))
     return out
+
+
+def bn_affine_from_sums(sums, count, gamma, beta, eps, running_mean=None, running_var=None, momentum=0.1):
+    """(scale, shift, mean, var) from the [2, C] float64 sums a conv epilogue accumulated; running stats updated in place."""
+    _need_cuda(sums, gamma, beta, running_mean, running_var)
+    C = sums.shape[1]
+    out = torch.empty((4, C), device=sums.device, dtype=torch.float32)
+    g, b = _vec(gamma, C), _vec(beta, C)
+    with torch.cuda.device(sums.device):
+        _lib.check(_lib.load().ctl_bn_affine_from_sums(
+            sums.data_ptr(), C, int(count), _ptr(g), _ptr(b), float(eps), out[0].data_ptr(), out[1].data_ptr(),
+            out[2].data_ptr(), out[3].data_ptr(), _ptr(running_mean), _ptr(running_var), float(momentum), _stream()))
+    return out[0], out[1], out[2], out[3]
 
 
 def nchw_to_c8(x):
@@ -301,20 +320,23 @@ def upsample2x_c8(x):
     return y
 
 
-def bn_batch_affine_c8(x, gamma, beta, eps, running_mean=None, running_var=None, momentum=0.1):
+def bn_batch_affine_c8(x, gamma, beta, eps, running_mean=None, running_var=None, momentum=0.1, want_stats=False):
     """Batch statistics of a C8 tensor folded into (scale, shift); updates the running statistics in place when
-    they are given (pass None to reproduce _disable_tracking_bn_stats)."""
+    they are given (pass None to reproduce _disable_tracking_bn_stats).  want_stats: also return the batch mean and
+    biased variance (what the backward needs)."""
     _need_cuda(x, gamma, beta, running_mean, running_var)
     N, C, H, W = _c8_dims(x)
     ws = torch.empty(_lib.load().ctl_bn_workspace_bytes(N, C), device=x.device, dtype=torch.uint8)
-    scale = torch.empty(C, device=x.device, dtype=torch.float32)
-    shift = torch.empty(C, device=x.device, dtype=torch.float32)
+    out = torch.empty((4 if want_stats else 2, C), device=x.device, dtype=torch.float32)
     g, b = _vec(gamma, C), _vec(beta, C)
     with torch.cuda.device(x.device):
         _lib.check(_lib.load().ctl_bn_batch_affine_c8(
-            x.data_ptr(), N, C, H, W, _ptr(g), _ptr(b), float(eps), ws.data_ptr(), scale.data_ptr(), shift.data_ptr(), 0, 0,
+            x.data_ptr(), N, C, H, W, _ptr(g), _ptr(b), float(eps), ws.data_ptr(), out[0].data_ptr(), out[1].data_ptr(),
+            out[2].data_ptr() if want_stats else 0, out[3].data_ptr() if want_stats else 0,
             _ptr(running_mean), _ptr(running_var), float(momentum), _stream()))
-    return scale, shift
+    if want_stats:
+        return out[0], out[1], out[2], out[3]
+    return out[0], out[1]
 
 
 def scale_shift_act_c8(x, scale, shift, act=ACT_NONE, inplace=False):
@@ -326,3 +348,164 @@ def scale_shift_act_c8(x, scale, shift, act=ACT_NONE, inplace=False):
         _lib.check(_lib.load().ctl_scale_shift_act_c8(x.data_ptr(), N, C, H, W, sc.data_ptr(), sh.data_ptr(), act,
                                                       y.data_ptr(), _stream()))
     return y
+
+
+# ------------------------------------------------------------------------------------------------ backward kernels
+def pack_conv_weight_dgrad(weight):
+    """Packed weights of the INPUT-gradient convolution of a stride-1 (or zero-stuffed stride-2) Conv2d:
+    dx = conv(dy, w') with w'[ci][co][r][s] = w[co][ci][k-1-r][k-1-s]."""
+    return pack_conv_weight(weight.detach().flip(2, 3).transpose(0, 1))
+
+
+def conv_wgrad_c8(x, dy, taps):
+    """K3w: fp32 [taps][Cin][Cout] = sum_p x[p + tap - pad] (x) dy[p]  (tcgen05, both operands straight from C8)."""
+    _need_cuda(x, dy)
+    N, cin, H, W = _c8_dims(x)
+    N2, cout, H2, W2 = _c8_dims(dy)
+    if (N2, H2, W2) != (N, H, W):
+        raise ValueError("x %s and dy %s must share N, H, W" % (tuple(x.shape), tuple(dy.shape)))
+    dW = torch.zeros((taps, cin, cout), device=x.device, dtype=torch.float32)
+    with torch.cuda.device(x.device):
+        _lib.check(_lib.load().ctl_conv_wgrad_c8_bf16(x.data_ptr(), dy.data_ptr(), N, H, W, cin, cout, taps,
+                                                      dW.data_ptr(), _stream()))
+    return dW
+
+
+def wgrad_to_conv_weight(dW, k):
+    """[taps][Cin][Cout] -> nn.Conv2d weight layout [Cout][Cin][k][k]."""
+    taps, cin, cout = dW.shape
+    return dW.permute(2, 1, 0).reshape(cout, cin, k, k)
+
+
+def _reduce_ws(N, C, device):
+    return torch.empty(_lib.load().ctl_reduce_workspace_bytes(N, C), device=device, dtype=torch.uint8)
+
+
+def channel_sum_c8(x):
+    _need_cuda(x)
+    N, C, H, W = _c8_dims(x)
+    out = torch.empty(C, device=x.device, dtype=torch.float32)
+    ws = _reduce_ws(N, C, x.device)
+    with torch.cuda.device(x.device):
+        _lib.check(_lib.load().ctl_channel_sums_c8(x.data_ptr(), N, C, H, W, ws.data_ptr(), out.data_ptr(), 0, _stream()))
+    return out
+
+
+def bn_act_bwd_c8(dy, h, a, act, mean, var, eps, gamma, want_dv=False, want_param_grads=True):
+    """Backward of h = act(BatchNorm_train(a)).  Returns (da, dgamma, dbeta, dv): dv = dy*act'(h) is materialised only
+    when want_dv (h must then be given); dgamma/dbeta are None unless want_param_grads."""
+    _need_cuda(dy, h, a, mean, var, gamma)
+    N, C, H, W = _c8_dims(a)
+    if tuple(dy.shape) != tuple(a.shape) or (h is not None and tuple(h.shape) != tuple(a.shape)):
+        raise ValueError("dy, h and a must have the same C8 shape")
+    _c8_dims(dy)
+    lib = _lib.load()
+    ws = _reduce_ws(N, C, a.device)
+    coef = torch.empty((3, C), device=a.device, dtype=torch.float32)
+    pg = torch.empty((2, C), device=a.device, dtype=torch.float32) if want_param_grads else None
+    dv = torch.empty_like(a) if (want_dv and h is not None) else None
+    g = _vec(gamma, C)
+    da = torch.empty_like(a)
+    with torch.cuda.device(a.device):
+        _lib.check(lib.ctl_bn_bwd_reduce_c8(dy.data_ptr(), _ptr(h), a.data_ptr(), N, C, H, W, act, mean.data_ptr(),
+                                            var.data_ptr(), float(eps), _ptr(g), ws.data_ptr(), _ptr(dv), coef.data_ptr(),
+                                            pg[0].data_ptr() if pg is not None else 0,
+                                            pg[1].data_ptr() if pg is not None else 0, _stream()))
+        if dv is not None:
+            _lib.check(lib.ctl_bn_bwd_apply_c8(dv.data_ptr(), 0, a.data_ptr(), N, C, H, W, act, coef.data_ptr(),
+                                               da.data_ptr(), _stream()))
+        else:
+            _lib.check(lib.ctl_bn_bwd_apply_c8(dy.data_ptr(), _ptr(h), a.data_ptr(), N, C, H, W, act, coef.data_ptr(),
+                                               da.data_ptr(), _stream()))
+    if want_dv and dv is None:
+        dv = dy
+    return da, (pg[0] if pg is not None else None), (pg[1] if pg is not None else None), dv
+
+
+def act_bwd_c8(dy, h, act):
+    _need_cuda(dy, h)
+    N, C, H, W = _c8_dims(dy)
+    dv = torch.empty_like(dy)
+    with torch.cuda.device(dy.device):
+        _lib.check(_lib.load().ctl_act_bwd_c8(dy.data_ptr(), h.data_ptr(), N, C, H, W, act, dv.data_ptr(), _stream()))
+    return dv
+
+
+def downsample2x_sum_c8(dy):
+    _need_cuda(dy)
+    N, C, H2, W2 = _c8_dims(dy)
+    dx = torch.empty((N, C // 8, H2 // 2, W2 // 2, 8), device=dy.device, dtype=torch.bfloat16)
+    with torch.cuda.device(dy.device):
+        _lib.check(_lib.load().ctl_downsample2x_sum_c8(dy.data_ptr(), N, C, H2 // 2, W2 // 2, dx.data_ptr(), _stream()))
+    return dx
+
+
+def zero_stuff2x_c8(x):
+    _need_cuda(x)
+    N, C, H, W = _c8_dims(x)
+    y = torch.empty((N, C // 8, 2 * H, 2 * W, 8), device=x.device, dtype=torch.bfloat16)
+    with torch.cuda.device(x.device):
+        _lib.check(_lib.load().ctl_zero_stuff2x_c8(x.data_ptr(), N, C, H, W, y.data_ptr(), _stream()))
+    return y
+
+
+def split_parity2x2_c8(x):
+    """C8 [N,C/8,2H,2W,8] -> [4, N, C/8, H, W, 8]; slice d holds pixels (2i + d//2, 2j + d%2)."""
+    _need_cuda(x)
+    N, C, H2, W2 = _c8_dims(x)
+    y = torch.empty((4, N, C // 8, H2 // 2, W2 // 2, 8), device=x.device, dtype=torch.bfloat16)
+    with torch.cuda.device(x.device):
+        _lib.check(_lib.load().ctl_split_parity2x2_c8(x.data_ptr(), N, C, H2 // 2, W2 // 2, y.data_ptr(), _stream()))
+    return y
+
+
+def head_bwd_c8(dy, y, x, weight, act=ACT_NONE):
+    """Backward of head_conv_c8.  Returns (dx C8, dW [Cout,16,1,1] fp32, db [Cout] fp32)."""
+    _need_cuda(dy, y, x, weight)
+    N, cin, H, W = _c8_dims(x)
+    cout = weight.shape[0]
+    dy = dy.to(torch.float32).contiguous()
+    if tuple(dy.shape) != (N, cout, H, W):
+        raise ValueError("dy must be [%d,%d,%d,%d]" % (N, cout, H, W))
+    w = weight.detach().to(torch.float32).reshape(cout, cin).contiguous()
+    dx = torch.empty_like(x)
+    grads = torch.zeros(cout * cin + cout, device=x.device, dtype=torch.float32)
+    yp = 0
+    if act != ACT_NONE:
+        y = y.to(torch.float32).contiguous()
+        yp = y.data_ptr()
+    with torch.cuda.device(x.device):
+        _lib.check(_lib.load().ctl_head_bwd_c8(dy.data_ptr(), yp, x.data_ptr(), N, cin, H, W, w.data_ptr(), cout, act,
+                                               dx.data_ptr(), grads.data_ptr(), grads[cout * cin:].data_ptr(), _stream()))
+    return dx, grads[:cout * cin].view(cout, cin, 1, 1), grads[cout * cin:]
+
+
+def stem_wgrad_c8(dy, x, cin, in_mode=0, temperature=1.0):
+    """Weight gradient [16,cin,3,3] of stem_conv_c8 (dy: gradient of the raw stem output, C8 with 16 channels)."""
+    _need_cuda(dy, x)
+    N, cout, H, W = _c8_dims(dy)
+    if in_mode == 2:
+        lab = x.contiguous()
+        xp, lp = 0, lab.data_ptr()
+    else:
+        xf = x.detach().to(torch.float32).contiguous()
+        xp, lp = xf.data_ptr(), 0
+    dW = torch.zeros((cout, cin, 3, 3), device=dy.device, dtype=torch.float32)
+    with torch.cuda.device(dy.device):
+        _lib.check(_lib.load().ctl_stem_wgrad_c8(dy.data_ptr(), xp, lp, in_mode, float(temperature), N, cin, H, W,
+                                                 dW.data_ptr(), _stream()))
+    return dW
+
+
+def stem_dgrad_c8(dy, x, weight, in_mode=0, temperature=1.0):
+    """Input gradient (planar fp32 [N,cin,H,W]) of stem_conv_c8; in_mode 1 chains through softmax(x / temperature)."""
+    _need_cuda(dy, x, weight)
+    N, cout, H, W = _c8_dims(dy)
+    cin = weight.shape[1]
+    xf = x.detach().to(torch.float32).contiguous() if x is not None else None
+    w = weight.detach().to(torch.float32).contiguous()
+    dx = torch.empty((N, cin, H, W), device=dy.device, dtype=torch.float32)
+    with torch.cuda.device(dy.device):
+        _lib.check(_lib.load().ctl_stem_dgrad_c8(dy.data_ptr(), _ptr(xf), in_mode, float(temperature), N, cin, H, W,
+                                                 w.data_ptr(), dx.data_ptr(), _stream()))
+    return dx

@@ -165,11 +165,19 @@ class AdvancedTripletReconSegmentationModel(nn.Module):
         return self._maybe_untracked(dec, disable_track_bn_stats, lambda: dec(latent_code))
 
     def encode_shape(self, segmentation, is_label_map=False, disable_track_bn_stats=False, temperature=2):
-        prediction_map = construct_input(segmentation, image=None, num_classes=self.num_classes,
-                                         apply_softmax=not is_label_map, is_labelmap=is_label_map,
-                                         temperature=temperature, use_gpu=self.use_gpu, smooth_label=False)
         enc = self.model['shape_encoder']
-        shape_code = self._maybe_untracked(enc, disable_track_bn_stats, lambda: enc(prediction_map))
+
+        def run():
+            # kernel routes fuse construct_input (softmax(logit/T) | one-hot) into the first STN convolution
+            code = enc.forward_from_segmentation(segmentation, is_label_map=is_label_map, temperature=temperature)
+            if code is not None:
+                return code
+            prediction_map = construct_input(segmentation, image=None, num_classes=self.num_classes,
+                                             apply_softmax=not is_label_map, is_labelmap=is_label_map,
+                                             temperature=temperature, use_gpu=self.use_gpu, smooth_label=False)
+            return enc(prediction_map)
+
+        shape_code = self._maybe_untracked(enc, disable_track_bn_stats, run)
         self.latent_code['shape'] = shape_code
         return shape_code
 

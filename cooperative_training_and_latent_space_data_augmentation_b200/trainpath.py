@@ -1,0 +1,377 @@
+"""Forward AND backward of the reference-shaped FTN/STN modules (networks.py) on this build's kernels.
+
+One torch.autograd.Function per sub-network (MyEncoder / Dual_Branch_Encoder / MyDecoder).  Its forward is the kernel
+sequence of fastpath.py in train-mode BatchNorm ('track' = batch statistics + running-stat update, 'batch' = batch
+statistics only, as inside _disable_tracking_bn_stats) and keeps the blocked C8 activations; its backward is written
+out by hand on the backward kernels:
+
+  head / stem      ctl_head_bwd_c8, ctl_stem_wgrad_c8, ctl_stem_dgrad_c8 (softmax(x/T) of construct_input fused)
+  BN + LReLU/ReLU  ctl_bn_bwd_reduce_c8 + ctl_bn_bwd_apply_c8
+  conv dgrad       ctl_conv2d_c8_bf16 with transposed + flipped weights (K3 itself)
+  conv wgrad       ctl_conv_wgrad_c8_bf16 (K3w, tcgen05 with MN-major operands)
+  resampling       ctl_downsample2x_sum_c8 (nearest x2), ctl_zero_stuff2x_c8 (stride-2 conv),
+                   ctl_split_parity2x2_c8 (ConvTranspose2d k2 s2)
+
+torch autograd only connects the sub-networks (losses, detach points), exactly where the reference's graph has them
+(medseg/models/advanced_triplet_recon_segmentation_model.py:414-467, :525-559), so `loss.backward()` and the five Adam
+optimizers are unchanged.  Activations and activation gradients are bf16 (C8); parameters and their gradients fp32.
+
+Gradient of a convolution bias that feeds a train-mode BatchNorm is identically zero (the mean subtraction removes it):
+those entries are returned as exact zeros.
+"""
+import torch
+import torch.nn as nn
+
+from . import ops
+from .fastpath import _act_code, _packed
+
+LRELU = ops.ACT_LRELU
+
+
+# ------------------------------------------------------------------------------------------------ helpers
+def _bn_mode_stats(bn, a):
+    """Train-mode BatchNorm statistics of the raw conv output `a`; honours track_running_stats like nn.BatchNorm2d."""
+    track = bn.track_running_stats and bn.running_mean is not None
+    scale, shift, mean, var = ops.bn_batch_affine_c8(
+        a, bn.weight, bn.bias, bn.eps, bn.running_mean if track else None, bn.running_var if track else None,
+        bn.momentum if bn.momentum is not None else 0.1, want_stats=True)
+    if track:
+        bn.num_batches_tracked += 1
+    return scale, shift, mean, var
+
+
+def _conv_bn(conv, bn, x):
+    """Raw conv output (+bias) and the train-mode BatchNorm statistics of it.  When the conv's N tile allows it the
+    statistics are accumulated by the conv epilogue itself (no second pass over the tensor)."""
+    k = conv.kernel_size[0]
+    if conv.stride[0] != 1 or not ops.conv_stats_fusable(conv.in_channels, conv.out_channels, k * k):
+        a = _conv_raw(conv, x)
+        return (a,) + _bn_mode_stats(bn, a)
+    sums = torch.zeros((2, conv.out_channels), device=x.device, dtype=torch.float64)
+    wp = _packed(conv.weight, ops.pack_conv_weight)
+    a = ops.conv2d_c8(x, wp, conv.out_channels, k * k, shift=conv.bias, stats=sums)
+    track = bn.track_running_stats and bn.running_mean is not None
+    stats = ops.bn_affine_from_sums(sums, a.shape[0] * a.shape[2] * a.shape[3], bn.weight, bn.bias, bn.eps,
+                                    bn.running_mean if track else None, bn.running_var if track else None,
+                                    bn.momentum if bn.momentum is not None else 0.1)
+    if track:
+        bn.num_batches_tracked += 1
+    return (a,) + stats
+
+
+def _conv_raw(conv, x):
+    k = conv.kernel_size[0]
+    wp = _packed(conv.weight, ops.pack_conv_weight)
+    return ops.conv2d_c8(x, wp, conv.out_channels, k * k, subsample=conv.stride[0], shift=conv.bias)
+
+
+def _dgrad(conv, dy, res=None):
+    """Input gradient of a stride-1 conv (dy at the conv's output resolution)."""
+    k = conv.kernel_size[0]
+    wp = _packed(conv.weight, ops.pack_conv_weight_dgrad, tag='dgrad')
+    return ops.conv2d_c8(dy, wp, conv.in_channels, k * k, res=res)
+
+
+def _wgrad(conv, x, dy):
+    k = conv.kernel_size[0]
+    return ops.wgrad_to_conv_weight(ops.conv_wgrad_c8(x, dy, k * k), k)
+
+
+class _Grads(dict):
+    """parameter -> gradient for the parameters autograd asked for (requires_grad AT FORWARD TIME, which is what the
+    reference's graph records -- e.g. BatchNorm affine parameters are frozen inside _disable_tracking_bn_stats)."""
+
+    def __init__(self, params, needs):
+        super().__init__()
+        self.need = {id(p) for p, n in zip(params, needs) if n}
+
+    def wants(self, p):
+        return p is not None and id(p) in self.need
+
+    def add(self, p, g):
+        if g is None or not self.wants(p):
+            return
+        key = id(p)
+        self[key] = g if key not in self else self[key] + g
+
+
+# ------------------------------------------------------------------------------------------------ conv + BN + act
+def conv_bn_act_fwd(conv, bn, x, act):
+    a, scale, shift, mean, var = _conv_bn(conv, bn, x)
+    h = ops.scale_shift_act_c8(a, scale, shift, act)
+    return h, (x, a, h, mean, var)
+
+
+def conv_bn_act_bwd(conv, bn, act, saved, dh, grads, need_dx=True):
+    x, a, h, mean, var = saved
+    da, dg, db, _ = ops.bn_act_bwd_c8(dh, h, a, act, mean, var, bn.eps, bn.weight)
+    grads.add(bn.weight, dg)
+    grads.add(bn.bias, db)
+    if grads.wants(conv.weight):
+        grads.add(conv.weight, _wgrad(conv, x, da))
+    if grads.wants(conv.bias):
+        grads.add(conv.bias, torch.zeros_like(conv.bias))
+    return _dgrad(conv, da) if need_dx else None
+
+
+# ------------------------------------------------------------------------------------------------ residual body
+def residual_fwd(block, xr):
+    """out = LReLU(conv_input(xr) + BN2(conv2(LReLU(BN1(conv1(xr))))))   (encoder_decoder.py:54-57, :334-337)"""
+    seq = block.conv
+    h1, s1 = conv_bn_act_fwd(seq[0], seq[1], xr, LRELU)
+    a2, scale2, shift2, mean2, var2 = _conv_bn(seq[3], seq[4], h1)
+    ci = block.conv_input
+    wp = _packed(ci.weight, ops.pack_conv_weight)
+    out = ops.conv2d_c8(xr, wp, ci.out_channels, 1, shift=ci.bias, res=a2, res_scale=scale2, res_shift=shift2, act=LRELU)
+    return out, (s1, a2, mean2, var2, out)
+
+
+def residual_bwd(block, saved, dout, grads):
+    s1, a2, mean2, var2, out = saved
+    xr, h1 = s1[0], s1[2]
+    seq, ci = block.conv, block.conv_input
+    bn2 = seq[4]
+    # tail: d(pre) = dout * LReLU'(out) feeds both the 1x1 branch and BN2
+    da2, dg2, db2, dpre = ops.bn_act_bwd_c8(dout, out, a2, LRELU, mean2, var2, bn2.eps, bn2.weight, want_dv=True)
+    grads.add(bn2.weight, dg2)
+    grads.add(bn2.bias, db2)
+    if grads.wants(ci.weight):
+        grads.add(ci.weight, _wgrad(ci, xr, dpre))
+        grads.add(ci.bias, db2)                             # sum over pixels of dpre == dbeta of BN2
+    dxr = _dgrad(ci, dpre)
+    # conv2
+    if grads.wants(seq[3].weight):
+        grads.add(seq[3].weight, _wgrad(seq[3], h1, da2))
+        grads.add(seq[3].bias, torch.zeros_like(seq[3].bias))
+    dh1 = _dgrad(seq[3], da2)
+    # BN1 + LReLU + conv1
+    x, a1, h1_, mean1, var1 = s1
+    da1, dg1, db1, _ = ops.bn_act_bwd_c8(dh1, h1_, a1, LRELU, mean1, var1, seq[1].eps, seq[1].weight)
+    grads.add(seq[1].weight, dg1)
+    grads.add(seq[1].bias, db1)
+    if grads.wants(seq[0].weight):
+        grads.add(seq[0].weight, _wgrad(seq[0], xr, da1))
+        grads.add(seq[0].bias, torch.zeros_like(seq[0].bias))
+    return _dgrad(seq[0], da1, res=dxr)
+
+
+# ------------------------------------------------------------------------------------------------ down / up blocks
+def down_fwd(block, x):
+    xd = _conv_raw(block.down, x)                          # 3x3 stride 2 (no norm / activation)
+    out, s = residual_fwd(block, xd)
+    return out, (x, s)
+
+
+def down_bwd(block, saved, dout, grads, need_dx=True):
+    x, s = saved
+    dxd = residual_bwd(block, s, dout, grads)
+    down = block.down
+    want_w = grads.wants(down.weight)
+    if not (want_w or need_dx):
+        return None
+    dyz = ops.zero_stuff2x_c8(dxd)                          # the stride-2 output gradient seen at full resolution
+    if want_w:
+        grads.add(down.weight, _wgrad(down, x, dyz))
+        grads.add(down.bias, ops.channel_sum_c8(dxd))
+    return _dgrad(down, dyz) if need_dx else None
+
+
+def _convT_tap_weight(up, d):
+    return up.weight.detach()[:, :, d // 2, d % 2].reshape(up.in_channels, up.out_channels, 1, 1)
+
+
+def up_fwd(block, x):
+    if block.up_type == 'NN':
+        xu = ops.upsample2x_c8(x)
+    else:
+        up = block.up
+        wp = _packed(up.weight, ops.pack_convtranspose2x2_weight)
+        xu = ops.conv2d_c8(x, wp, 4 * up.out_channels, 1, up2x=True, shift=up.bias.detach().repeat(4))
+    out, s = residual_fwd(block, xu)
+    return out, (x, s)
+
+
+def up_bwd(block, saved, dout, grads, need_dx=True):
+    x, s = saved
+    dxu = residual_bwd(block, s, dout, grads)
+    if block.up_type == 'NN':
+        return ops.downsample2x_sum_c8(dxu) if need_dx else None
+    up = block.up
+    want_w = grads.wants(up.weight)
+    if not (want_w or need_dx):
+        return None
+    parts = ops.split_parity2x2_c8(dxu)                     # [4][N, C/8, H, W, 8]: dy per kernel tap
+    if want_w:
+        dW = torch.stack([ops.conv_wgrad_c8(x, parts[d], 1)[0] for d in range(4)], dim=2)     # [ci][co][4]
+        grads.add(up.weight, dW.reshape(up.in_channels, up.out_channels, 2, 2))
+        grads.add(up.bias, ops.channel_sum_c8(dxu))
+    dx = None
+    if need_dx:
+        for d in range(4):
+            wp = _packed(up.weight, lambda w, d=d: ops.pack_conv_weight(_convT_tap_weight(up, d)), tag='dgradT%d' % d)
+            dx = ops.conv2d_c8(parts[d], wp, up.in_channels, 1, res=dx)
+    return dx
+
+
+# ------------------------------------------------------------------------------------------------ encoder
+def encoder_fwd(enc, x, in_mode, temperature):
+    """MyEncoder: planar input (fp32 image / logits, or int64 label map with in_mode 2) -> C8 latent."""
+    inc = enc.inc
+    a0 = ops.stem_conv_c8(x, inc[0].weight, None, inc[0].bias, ops.ACT_NONE, in_mode, temperature)
+    scale0, shift0, mean0, var0 = _bn_mode_stats(inc[1], a0)
+    h0 = ops.scale_shift_act_c8(a0, scale0, shift0, LRELU)
+    h, s_inc = conv_bn_act_fwd(inc[3], inc[4], h0, LRELU)   # BN then F.leaky_relu (encoder_decoder.py:405)
+    tape = [(a0, h0, mean0, var0), s_inc]
+    for blk in (enc.down1, enc.down2, enc.down3, enc.down4):
+        h, s = down_fwd(blk, h)
+        tape.append(s)
+    z, s_fin = conv_bn_act_fwd(enc.final_conv[0], enc.final_conv[1], h, _act_code(enc.act))
+    tape.append(s_fin)
+    return z, tape
+
+
+def encoder_bwd(enc, tape, dz, grads, x, in_mode, temperature, need_dx):
+    inc = enc.inc
+    d = conv_bn_act_bwd(enc.final_conv[0], enc.final_conv[1], _act_code(enc.act), tape[6], dz, grads)
+    for i, blk in zip((5, 4, 3, 2), (enc.down4, enc.down3, enc.down2, enc.down1)):
+        d = down_bwd(blk, tape[i], d, grads)
+    dh0 = conv_bn_act_bwd(inc[3], inc[4], LRELU, tape[1], d, grads)
+    a0, h0, mean0, var0 = tape[0]
+    da0, dg0, db0, _ = ops.bn_act_bwd_c8(dh0, h0, a0, LRELU, mean0, var0, inc[1].eps, inc[1].weight)
+    grads.add(inc[1].weight, dg0)
+    grads.add(inc[1].bias, db0)
+    if grads.wants(inc[0].weight):
+        grads.add(inc[0].weight, ops.stem_wgrad_c8(da0, x, inc[0].in_channels, in_mode, temperature))
+        grads.add(inc[0].bias, torch.zeros_like(inc[0].bias))
+    if need_dx:
+        return ops.stem_dgrad_c8(da0, x, inc[0].weight, in_mode, temperature)
+    return None
+
+
+def decoupler_fwd(seq, z):
+    h, s1 = conv_bn_act_fwd(seq[0], seq[1], z, LRELU)
+    out, s2 = conv_bn_act_fwd(seq[3], seq[4], h, _act_code(seq[5]))
+    return out, (s1, s2)
+
+
+def decoupler_bwd(seq, saved, dout, grads):
+    s1, s2 = saved
+    dh = conv_bn_act_bwd(seq[3], seq[4], _act_code(seq[5]), s2, dout, grads)
+    return conv_bn_act_bwd(seq[0], seq[1], LRELU, s1, dh, grads)
+
+
+# ------------------------------------------------------------------------------------------------ decoder
+def decoder_fwd(dec, z_c8):
+    tape = []
+    y = z_c8
+    for blk in (dec.up1, dec.up2, dec.up3, dec.up4):
+        y, s = up_fwd(blk, y)
+        tape.append(s)
+    act = _act_code(dec.last_act)
+    out = ops.head_conv_c8(y, dec.final_conv.weight, dec.final_conv.bias, act)
+    tape.append((y, out if act != ops.ACT_NONE else None))
+    return out, tape
+
+
+def decoder_bwd(dec, tape, dout, grads, need_dz):
+    y, out = tape[4]
+    fc = dec.final_conv
+    dy, dW, db = ops.head_bwd_c8(dout, out, y, fc.weight, _act_code(dec.last_act))
+    grads.add(fc.weight, dW)
+    grads.add(fc.bias, db)
+    d = dy
+    blocks = (dec.up1, dec.up2, dec.up3, dec.up4)
+    for i in (3, 2, 1, 0):
+        d = up_bwd(blocks[i], tape[i], d, grads, need_dx=(i > 0 or need_dz))
+    return d
+
+
+# ------------------------------------------------------------------------------------------------ autograd glue
+def _param_grads(params, grads):
+    return tuple(grads.get(id(p)) for p in params)
+
+
+class _DecoderFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, dec, z, *params):
+        out, tape = decoder_fwd(dec, ops.nchw_to_c8(z))
+        ctx.dec, ctx.tape, ctx.params = dec, tape, params
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        grads = _Grads(ctx.params, ctx.needs_input_grad[2:])
+        dz = decoder_bwd(ctx.dec, ctx.tape, dout.contiguous(), grads, ctx.needs_input_grad[1])
+        ctx.tape = None
+        dz = ops.c8_to_nchw(dz) if dz is not None else None
+        return (None, dz) + _param_grads(ctx.params, grads)
+
+
+class _EncoderFn(torch.autograd.Function):
+    """MyEncoder, optionally followed by the code decoupler of Dual_Branch_Encoder (two outputs then)."""
+
+    @staticmethod
+    def forward(ctx, enc, decoupler, in_mode, temperature, x, *params):
+        z, tape = encoder_fwd(enc, x, in_mode, temperature)
+        ctx.enc, ctx.decoupler, ctx.tape, ctx.params = enc, decoupler, tape, params
+        ctx.in_mode, ctx.temperature, ctx.x = in_mode, temperature, x
+        z_i = ops.c8_to_nchw(z)
+        if decoupler is None:
+            ctx.tape2 = None
+            return z_i
+        zs, ctx.tape2 = decoupler_fwd(decoupler, z)
+        return z_i, ops.c8_to_nchw(zs)
+
+    @staticmethod
+    def backward(ctx, dz_i, dz_s=None):
+        grads = _Grads(ctx.params, ctx.needs_input_grad[5:])
+        dz = ops.nchw_to_c8(dz_i) if dz_i is not None else None
+        if ctx.decoupler is not None and dz_s is not None:
+            d2 = decoupler_bwd(ctx.decoupler, ctx.tape2, ops.nchw_to_c8(dz_s), grads)
+            dz = d2 if dz is None else ops.nchw_to_c8(dz_i + ops.c8_to_nchw(d2))
+        need_dx = ctx.needs_input_grad[4] and ctx.in_mode != 2
+        dx = encoder_bwd(ctx.enc, ctx.tape, dz, grads, ctx.x, ctx.in_mode, ctx.temperature, need_dx)
+        ctx.tape = ctx.tape2 = ctx.x = None
+        return (None, None, None, None, dx) + _param_grads(ctx.params, grads)
+
+
+class _DecouplerFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, seq, z, *params):
+        out, ctx.tape = decoupler_fwd(seq, ops.nchw_to_c8(z))
+        ctx.seq, ctx.params = seq, params
+        return ops.c8_to_nchw(out)
+
+    @staticmethod
+    def backward(ctx, dout):
+        grads = _Grads(ctx.params, ctx.needs_input_grad[2:])
+        dz = decoupler_bwd(ctx.seq, ctx.tape, ops.nchw_to_c8(dout), grads)
+        ctx.tape = None
+        return (None, ops.c8_to_nchw(dz)) + _param_grads(ctx.params, grads)
+
+
+def _trainable_kernel_path(module, x):
+    """The kernel path covers CUDA tensors in train mode (batch statistics).  Eval-mode forward with autograd enabled
+    is not on the reference's hot path (predict / decoder_inference(eval=True) run under no_grad)."""
+    return x.is_cuda and module.training
+
+
+def decoder_apply(dec, z):
+    params = tuple(dec.parameters())
+    return _DecoderFn.apply(dec, z.float(), *params)
+
+
+def encoder_apply(enc, x, in_mode=0, temperature=1.0):
+    params = tuple(enc.parameters())
+    if in_mode != 2:
+        x = x.float()
+    return _EncoderFn.apply(enc, None, in_mode, float(temperature), x, *params)
+
+
+def dual_encoder_apply(dual, x):
+    params = tuple(dual.general_encoder.parameters()) + tuple(dual.code_decoupler.parameters())
+    return _EncoderFn.apply(dual.general_encoder, dual.code_decoupler, 0, 1.0, x.float(), *params)
+
+
+def decoupler_apply(dual, z):
+    return _DecouplerFn.apply(dual.code_decoupler, z.float(), *tuple(dual.code_decoupler.parameters()))

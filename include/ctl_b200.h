@@ -119,12 +119,15 @@ int ctl_philox_uniform(uint64_t seed, uint64_t offset, uint64_t first_index, int
  * out = act( conv(x) * scale[c] + shift[c] + (res * res_scale[c] + res_shift[c]) ); res has the output's shape
  * and layout; res and every per-GEMM-column fp32 vector may be NULL (identity).
  * Cin in {16,32,64,128}, Cout %% 16 == 0.
+ * stats (may be NULL): double [2][Cout], the per-channel sum and sum of squares of the STORED (bf16-rounded) outputs are
+ * accumulated into it by the epilogue (zero it first) -- train-mode BatchNorm statistics without a second pass over the
+ * tensor; needs ctl_conv2d_n_tile(...) <= 32 and up2x == 0.  Finalise with ctl_bn_affine_from_sums.
  */
 int ctl_conv2d_n_tile(int Cin, int Cout, int taps);
 int ctl_conv2d_c8_bf16(const void* x, int64_t N, int64_t H, int64_t W, int64_t Cin, const void* w_packed,
                        int64_t Cout, int taps, int subsample, int up2x, const float* scale,
                        const float* shift, const void* res, const float* res_scale,
-                       const float* res_shift, int act, void* out, void* stream);
+                       const float* res_shift, int act, void* out, double* stats, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
  * CUDA-core kernels around K3 (all HBM-bound streaming passes over C8 tensors).
@@ -148,15 +151,68 @@ int ctl_upsample2x_c8(const void* x, int64_t N, int64_t C, int64_t H, int64_t W,
 /* Train-mode BatchNorm2d statistics of a C8 tensor folded into y = x*scale + shift:
  * scale = gamma*rsqrt(var_biased + eps), shift = beta - mean*scale (fp64 accumulation).  When running_mean/var are
  * given they are updated like nn.BatchNorm2d (momentum, unbiased variance) -- pass NULL to reproduce
- * _disable_tracking_bn_stats (model_util.py:414-451).  workspace: ctl_bn_workspace_bytes(N, C) bytes. */
+ * _disable_tracking_bn_stats (model_util.py:414-451).  mean_out / var_out (biased) are what the backward needs.
+ * workspace: ctl_bn_workspace_bytes(N, C) bytes. */
 size_t ctl_bn_workspace_bytes(int64_t N, int64_t C);
 int ctl_bn_batch_affine_c8(const void* x, int64_t N, int64_t C, int64_t H, int64_t W, const float* gamma,
                            const float* beta, float eps, void* workspace, float* scale, float* shift,
                            float* mean_out, float* var_out, float* running_mean, float* running_var,
                            float momentum, void* stream);
+/* ctl_bn_batch_affine_c8 from sums accumulated by the conv epilogue (sums: double [2][C], count = N*H*W of that tensor) */
+int ctl_bn_affine_from_sums(const double* sums, int64_t C, int64_t count, const float* gamma, const float* beta, float eps,
+                            float* scale, float* shift, float* mean_out, float* var_out, float* running_mean,
+                            float* running_var, float momentum, void* stream);
 /* y = act(x*scale[c] + shift[c]) on C8 tensors (BatchNorm apply + LeakyReLU in one pass). */
 int ctl_scale_shift_act_c8(const void* x, int64_t N, int64_t C, int64_t H, int64_t W, const float* scale,
                            const float* shift, int act, void* y, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Backward of the conv blocks (the reference leaves all of it to torch autograd over the modules of
+ * medseg/models/ebm/encoder_decoder.py:19-68, :285-348, :351-415, :418-453, :456-503).
+ * Input gradients of 3x3 / 1x1 convolutions run on ctl_conv2d_c8_bf16 itself with transposed + flipped weights.
+ */
+/* K3w: dW[tap][ci][co] += sum_p x[p + tap - pad][ci] * dy[p][co] on tcgen05 (both operands MN-major from C8 tiles).
+ * x: C8 [N,Cin/8,H,W,8], dy: C8 [N,Cout/8,H,W,8] (same H, W; 3x3 pad 1 or 1x1), dW: fp32 [taps][Cin][Cout], ACCUMULATED
+ * into (zero it first).  Cin in {16,32,64,128}, Cout %% 16 == 0. */
+int ctl_conv_wgrad_c8_bf16(const void* x, const void* dy, int64_t N, int64_t H, int64_t W, int64_t Cin, int64_t Cout,
+                           int taps, float* dW, void* stream);
+/* workspace bytes of the per-channel reductions below */
+size_t ctl_reduce_workspace_bytes(int64_t N, int64_t C);
+/* per-channel sum / sum of squares of a C8 tensor (bias gradients of convolutions without BatchNorm) */
+int ctl_channel_sums_c8(const void* x, int64_t N, int64_t C, int64_t H, int64_t W, void* workspace, float* sum_out,
+                        float* sumsq_out, void* stream);
+/* BatchNorm(train) + activation backward, stage 1.  dv = dy * act'(h) (h = the activation OUTPUT; NULL: dv = dy);
+ * reduces sum(dv), sum(dv*a) per channel (a = the BatchNorm input) and emits the coefficients of
+ *   da = coef[0][c]*dv + coef[1][c]*a + coef[2][c]      (coef: fp32 [3][C])
+ * plus dgamma / dbeta (either may be NULL).  dv_out (C8, may be NULL) materialises dv.  mean / var: the batch statistics
+ * of the forward (ctl_bn_batch_affine_c8 mean_out / var_out).  act in {NONE, LRELU, RELU}. */
+int ctl_bn_bwd_reduce_c8(const void* dy, const void* h, const void* a, int64_t N, int64_t C, int64_t H, int64_t W,
+                         int act, const float* mean, const float* var, float eps, const float* gamma, void* workspace,
+                         void* dv_out, float* coef, float* dgamma, float* dbeta, void* stream);
+/* stage 2: da = coef0*dv + coef1*a + coef2 with dv = dy * act'(h) (h NULL: dy is already dv) */
+int ctl_bn_bwd_apply_c8(const void* dy, const void* h, const void* a, int64_t N, int64_t C, int64_t H, int64_t W,
+                        int act, const float* coef, void* da, void* stream);
+/* dv = dy * act'(h) */
+int ctl_act_bwd_c8(const void* dy, const void* h, int64_t N, int64_t C, int64_t H, int64_t W, int act, void* dv,
+                   void* stream);
+/* backward of nearest x2 up-sampling: dy C8 [N,C/8,2H,2W,8] -> dx C8 [N,C/8,H,W,8] (2x2 sums); H, W = low resolution */
+int ctl_downsample2x_sum_c8(const void* dy, int64_t N, int64_t C, int64_t H, int64_t W, void* dx, void* stream);
+/* x C8 [N,C/8,H,W,8] -> y C8 [N,C/8,2H,2W,8] with y[2i][2j] = x[i][j], zeros elsewhere (dy of a stride-2 conv at full
+ * resolution, so that its input / weight gradients are ordinary stride-1 calls) */
+int ctl_zero_stuff2x_c8(const void* x, int64_t N, int64_t C, int64_t H, int64_t W, void* y, void* stream);
+/* x C8 [N,C/8,2H,2W,8] -> y C8 [4][N,C/8,H,W,8], y[d] = x[2i + d/2][2j + d%2] (dy of ConvTranspose2d k2 s2 per kernel tap) */
+int ctl_split_parity2x2_c8(const void* x, int64_t N, int64_t C, int64_t H, int64_t W, void* y, void* stream);
+/* backward of ctl_head_conv1x1_c8: dy planar fp32 [N,Cout,H,W], y = the forward output (sigmoid only, else NULL);
+ * dx C8 bf16 [N,2,H,W,8]; dW fp32 [Cout][16] and db fp32 [Cout] are ACCUMULATED into.  Cout in {1,4}. */
+int ctl_head_bwd_c8(const float* dy, const float* y, const void* x, int64_t N, int64_t Cin, int64_t H, int64_t W,
+                    const float* weight, int64_t Cout, int act, void* dx, float* dW, float* db, void* stream);
+/* backward of ctl_stem_conv3x3_c8 w.r.t. the weight: dy C8 (16 channels, gradient of the raw conv output);
+ * x / labels / in_mode / temperature as in the forward; dW fp32 [16][Cin][3][3] ACCUMULATED into. */
+int ctl_stem_wgrad_c8(const void* dy, const float* x, const int64_t* labels, int in_mode, float temperature, int64_t N,
+                      int64_t Cin, int64_t H, int64_t W, float* dW, void* stream);
+/* ... and w.r.t. the input (in_mode 0: plain, 1: through softmax(x / temperature)); dx planar fp32 [N,Cin,H,W] */
+int ctl_stem_dgrad_c8(const void* dy, const float* x, int in_mode, float temperature, int64_t N, int64_t Cin, int64_t H,
+                      int64_t W, const float* weight, float* dx, void* stream);
 
 #ifdef __cplusplus
 }

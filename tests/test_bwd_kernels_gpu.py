@@ -1,0 +1,185 @@
+"""GPU parity of the backward kernels (K3w weight gradient on tcgen05, dgrad through K3 with transposed weights,
+BatchNorm/activation backward, resampling backward, head and stem backward) against torch autograd in fp32 evaluated on
+the same bf16-rounded operands.  Tolerances are relative to the largest reference magnitude of each tensor:
+fp32-accumulated quantities (weight / bias / BN parameter gradients) 2e-3; bf16 activation gradients 1.5e-2
+(one bf16 rounding of the result plus accumulation-order noise)."""
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def ops():
+    import cooperative_training_and_latent_space_data_augmentation_b200 as pkg
+    return pkg.ops
+
+
+def _bf(*shape, gen, scale=1.0):
+    return (torch.randn(*shape, device="cuda", generator=gen) * scale).to(torch.bfloat16)
+
+
+def _cmp(got, want, rel, what=""):
+    got, want = got.float(), want.float()
+    assert got.shape == want.shape, (what, got.shape, want.shape)
+    ref = float(want.abs().max()) + 1e-30
+    err = float((got - want).abs().max())
+    assert err <= rel * ref, "%s: max err %.3e vs max |ref| %.3e (ratio %.2e > %.1e)" % (what, err, ref, err / ref, rel)
+
+
+WG_LAYERS = [  # (Cin, Cout, k, N, H, W)
+    (16, 16, 3, 2, 224, 224), (16, 32, 3, 2, 112, 112), (32, 32, 3, 2, 112, 112), (32, 64, 3, 2, 56, 56),
+    (64, 64, 3, 2, 56, 56), (64, 128, 3, 2, 28, 28), (128, 128, 3, 3, 28, 28), (128, 128, 3, 3, 14, 14),
+    (128, 64, 3, 2, 28, 28), (64, 32, 3, 2, 56, 56), (32, 16, 3, 2, 112, 112),
+    (16, 16, 1, 2, 224, 224), (16, 32, 1, 2, 112, 112), (64, 128, 1, 2, 28, 28), (128, 128, 1, 2, 14, 14),
+    (128, 64, 1, 2, 28, 28), (32, 16, 1, 2, 112, 112), (64, 32, 1, 2, 56, 56),
+    (16, 16, 3, 1, 20, 36), (32, 48, 3, 2, 17, 9), (64, 16, 1, 1, 5, 40), (16, 16, 3, 5, 16, 16), (128, 128, 3, 1, 7, 7),
+]
+
+
+@pytest.mark.parametrize("cin,cout,k,N,H,W", WG_LAYERS)
+def test_wgrad_matches_torch(ops, cin, cout, k, N, H, W):
+    g = torch.Generator(device="cuda").manual_seed(cin * 100 + cout + k + H)
+    x = _bf(N, cin, H, W, gen=g)
+    dy = _bf(N, cout, H, W, gen=g, scale=0.1)
+    got = ops.wgrad_to_conv_weight(ops.conv_wgrad_c8(ops.nchw_to_c8(x), ops.nchw_to_c8(dy), k * k), k)
+    want = torch.nn.grad.conv2d_weight(x.float(), (cout, cin, k, k), dy.float(), padding=k // 2)
+    _cmp(got, want, 2e-3, "wgrad %d->%d k%d" % (cin, cout, k))
+
+
+@pytest.mark.parametrize("cin,cout,k,N,H,W", [(16, 16, 3, 2, 64, 48), (16, 32, 3, 2, 40, 24), (128, 64, 3, 2, 28, 28),
+                                               (64, 128, 1, 2, 28, 28), (32, 16, 1, 2, 30, 20), (128, 128, 3, 2, 14, 14)])
+def test_dgrad_through_k3(ops, cin, cout, k, N, H, W):
+    g = torch.Generator(device="cuda").manual_seed(cin + cout * 7 + k)
+    w = torch.randn(cout, cin, k, k, device="cuda", generator=g) * (2.0 / (cin * k * k)) ** 0.5
+    dy = _bf(N, cout, H, W, gen=g)
+    res = _bf(N, cin, H, W, gen=g)
+    got = ops.conv2d_c8(ops.nchw_to_c8(dy), ops.pack_conv_weight_dgrad(w), cin, k * k, res=ops.nchw_to_c8(res))
+    want = torch.nn.grad.conv2d_input((N, cin, H, W), w.to(torch.bfloat16).float(), dy.float(), padding=k // 2) + res.float()
+    _cmp(ops.c8_to_nchw(got), want, 1.5e-2, "dgrad")
+
+
+@pytest.mark.parametrize("C,N,H,W", [(16, 2, 64, 48), (32, 2, 28, 36), (128, 2, 14, 14)])
+def test_stride2_conv_backward_via_zero_stuffing(ops, C, N, H, W):
+    g = torch.Generator(device="cuda").manual_seed(C + H)
+    w = torch.randn(C, C, 3, 3, device="cuda", generator=g) * (2.0 / (C * 9)) ** 0.5
+    x = _bf(N, C, H, W, gen=g)
+    dy = _bf(N, C, H // 2, W // 2, gen=g)
+    dyz = ops.zero_stuff2x_c8(ops.nchw_to_c8(dy))
+    assert tuple(dyz.shape) == (N, C // 8, H, W, 8)
+    z = ops.c8_to_nchw(dyz)
+    assert torch.equal(z[:, :, ::2, ::2], dy.float()) and int((z != 0).sum()) == int((dy != 0).sum())
+    xf = x.float().requires_grad_(True)
+    wf = w.to(torch.bfloat16).float().requires_grad_(True)
+    F.conv2d(xf, wf, None, stride=2, padding=1).backward(dy.float())
+    dx = ops.conv2d_c8(dyz, ops.pack_conv_weight_dgrad(w), C, 9)
+    _cmp(ops.c8_to_nchw(dx), xf.grad, 1.5e-2, "stride-2 dgrad")
+    dw = ops.wgrad_to_conv_weight(ops.conv_wgrad_c8(ops.nchw_to_c8(x), dyz, 9), 3)
+    _cmp(dw, wf.grad, 2e-3, "stride-2 wgrad")
+    _cmp(ops.channel_sum_c8(ops.nchw_to_c8(dy)), dy.float().sum(dim=(0, 2, 3)), 2e-3, "channel sum")
+
+
+@pytest.mark.parametrize("C,N,H,W", [(128, 2, 14, 14), (64, 2, 28, 20), (16, 2, 56, 56)])
+def test_convtranspose_backward_via_parity_split(ops, C, N, H, W):
+    g = torch.Generator(device="cuda").manual_seed(C * 3 + H)
+    w = torch.randn(C, C, 2, 2, device="cuda", generator=g) * (1.0 / C) ** 0.5
+    x = _bf(N, C, H, W, gen=g)
+    dy = _bf(N, C, 2 * H, 2 * W, gen=g)
+    xf = x.float().requires_grad_(True)
+    wf = w.to(torch.bfloat16).float().requires_grad_(True)
+    F.conv_transpose2d(xf, wf, None, stride=2).backward(dy.float())
+    parts = ops.split_parity2x2_c8(ops.nchw_to_c8(dy))
+    for d in range(4):
+        assert torch.equal(ops.c8_to_nchw(parts[d]), dy.float()[:, :, d // 2::2, d % 2::2])
+    xc = ops.nchw_to_c8(x)
+    dW = torch.stack([ops.conv_wgrad_c8(xc, parts[d], 1)[0] for d in range(4)], dim=2).reshape(C, C, 2, 2)
+    _cmp(dW, wf.grad, 2e-3, "convT wgrad")
+    dx = None
+    for d in range(4):
+        wp = ops.pack_conv_weight(w[:, :, d // 2, d % 2].reshape(C, C, 1, 1))
+        dx = ops.conv2d_c8(parts[d], wp, C, 1, res=dx)
+    _cmp(ops.c8_to_nchw(dx), xf.grad, 2e-2, "convT dgrad")
+
+
+@pytest.mark.parametrize("act", [0, 1, 2])
+@pytest.mark.parametrize("C,N,H,W", [(16, 3, 40, 24), (128, 4, 14, 14), (32, 2, 112, 112)])
+def test_bn_act_backward(ops, act, C, N, H, W):
+    g = torch.Generator(device="cuda").manual_seed(C + act)
+    a = _bf(N, C, H, W, gen=g) * 1.5 + 0.3
+    dy = _bf(N, C, H, W, gen=g, scale=0.1)
+    gamma = 1 + 0.2 * torch.randn(C, device="cuda", generator=g)
+    beta = 0.3 * torch.randn(C, device="cuda", generator=g)
+    ac = ops.nchw_to_c8(a)
+    scale, shift, mean, var = ops.bn_batch_affine_c8(ac, gamma, beta, 1e-5, want_stats=True)
+    h = ops.scale_shift_act_c8(ac, scale, shift, act)
+    af = a.float().requires_grad_(True)
+    gf, bf_ = gamma.clone().requires_grad_(True), beta.clone().requires_grad_(True)
+    v = F.batch_norm(af, None, None, gf, bf_, True, 0.1, 1e-5)
+    hf = F.leaky_relu(v, 0.2) if act == 1 else F.relu(v) if act == 2 else v
+    _cmp(ops.c8_to_nchw(h), hf.detach(), 1.5e-2, "forward")
+    # use the kernel's own (bf16) h for the activation mask, as the training path does
+    hk = ops.c8_to_nchw(h)
+    slope = torch.where(hk > 0, 1.0, 0.2) if act == 1 else (hk > 0).float() if act == 2 else torch.ones_like(hk)
+    v.backward(dy.float() * slope)
+    da, dg, db, dv = ops.bn_act_bwd_c8(ops.nchw_to_c8(dy), h if act else None, ac, act, mean, var, 1e-5, gamma,
+                                       want_dv=True)
+    _cmp(dg, gf.grad, 3e-3, "dgamma")
+    _cmp(db, bf_.grad, 3e-3, "dbeta")
+    _cmp(ops.c8_to_nchw(da), af.grad, 2e-2, "da")
+    _cmp(ops.c8_to_nchw(dv), dy.float() * slope, 1e-2, "dv")
+    da2, _, _, _ = ops.bn_act_bwd_c8(ops.nchw_to_c8(dy), h if act else None, ac, act, mean, var, 1e-5, gamma,
+                                     want_param_grads=False)
+    _cmp(ops.c8_to_nchw(da2), af.grad, 2e-2, "da (no dv)")
+    if act:
+        _cmp(ops.c8_to_nchw(ops.act_bwd_c8(ops.nchw_to_c8(dy), h, act)), dy.float() * slope, 1e-2, "act_bwd")
+
+
+def test_downsample_sum(ops):
+    g = torch.Generator(device="cuda").manual_seed(0)
+    dy = _bf(3, 24, 14, 22, gen=g)
+    got = ops.c8_to_nchw(ops.downsample2x_sum_c8(ops.nchw_to_c8(dy)))
+    want = F.avg_pool2d(dy.float(), 2) * 4
+    _cmp(got, want, 1e-2, "downsample2x_sum")
+
+
+@pytest.mark.parametrize("cout,act", [(4, 0), (1, 3)])
+def test_head_backward(ops, cout, act):
+    g = torch.Generator(device="cuda").manual_seed(cout)
+    N, H, W = 3, 30, 44
+    x = _bf(N, 16, H, W, gen=g)
+    w = torch.randn(cout, 16, 1, 1, device="cuda", generator=g) * 0.3
+    b = torch.randn(cout, device="cuda", generator=g)
+    dy = torch.randn(N, cout, H, W, device="cuda", generator=g) * 0.01
+    xf, wf, bf_ = x.float().requires_grad_(True), w.clone().requires_grad_(True), b.clone().requires_grad_(True)
+    y = F.conv2d(xf, wf, bf_)
+    y = torch.sigmoid(y) if act == 3 else y
+    y.backward(dy)
+    xc = ops.nchw_to_c8(x)
+    yk = ops.head_conv_c8(xc, w, b, act)
+    dx, dW, db = ops.head_bwd_c8(dy, yk if act else None, xc, w, act)
+    _cmp(dW, wf.grad, 2e-3, "head dW")
+    _cmp(db, bf_.grad, 2e-3, "head db")
+    _cmp(ops.c8_to_nchw(dx), xf.grad, 1e-2, "head dx")
+
+
+@pytest.mark.parametrize("cin,in_mode", [(1, 0), (4, 0), (4, 1), (4, 2)])
+def test_stem_backward(ops, cin, in_mode):
+    g = torch.Generator(device="cuda").manual_seed(cin * 10 + in_mode)
+    N, H, W = 3, 37, 50
+    w = torch.randn(16, cin, 3, 3, device="cuda", generator=g) * 0.3
+    dy = _bf(N, 16, H, W, gen=g, scale=0.1)
+    wf = w.clone().requires_grad_(True)
+    if in_mode == 2:
+        lab = torch.randint(0, 4, (N, H, W), device="cuda", generator=g)
+        F.conv2d(F.one_hot(lab, 4).permute(0, 3, 1, 2).float(), wf, None, padding=1).backward(dy.float())
+        got_w = ops.stem_wgrad_c8(ops.nchw_to_c8(dy), lab, cin, in_mode=2)
+        _cmp(got_w, wf.grad, 2e-3, "stem wgrad (labels)")
+        return
+    x = torch.randn(N, cin, H, W, device="cuda", generator=g) * 2
+    xf = x.clone().requires_grad_(True)
+    xin = torch.softmax(xf / 2.0, dim=1) if in_mode == 1 else xf
+    F.conv2d(xin, wf, None, padding=1).backward(dy.float())
+    dyc = ops.nchw_to_c8(dy)
+    _cmp(ops.stem_wgrad_c8(dyc, x, cin, in_mode=in_mode, temperature=2.0), wf.grad, 2e-3, "stem wgrad")
+    _cmp(ops.stem_dgrad_c8(dyc, x, w, in_mode=in_mode, temperature=2.0), xf.grad, 2e-3, "stem dgrad")
