@@ -227,6 +227,28 @@ scale_shift_act_c8_kernel(const uint4* __restrict__ x, uint4* __restrict__ y, co
   }
 }
 
+// ------------------------------------------------------------------------------------------------ weight packing
+// fp32 nn.Conv2d weight [Cout][Cin][k][k] -> bf16 [Cout'/NT][taps][Cin'/8][NT][8] (the K-major core-matrix order of
+// conv_tc.cu).  transposed == 0: the forward weight (Cout' = Cout, Cin' = Cin).  transposed == 1: the weight of the
+// INPUT-gradient convolution, w'[ci][co][r][s] = w[co][ci][k-1-r][k-1-s] (Cout' = Cin, Cin' = Cout).
+__global__ void __launch_bounds__(kT)
+pack_conv_weight_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ out, int Cout, int Cin, int taps, int nt,
+                        int transposed) {
+  const int co_p = transposed ? Cin : Cout, ci_p = transposed ? Cout : Cin;     // packed-view channel counts
+  const int total = co_p * ci_p * taps;
+  for (int i = blockIdx.x * kT + threadIdx.x; i < total; i += gridDim.x * kT) {
+    int r = i;
+    const int j = r & 7; r >>= 3;
+    const int n = r % nt; r /= nt;
+    const int q = r % (ci_p >> 3); r /= (ci_p >> 3);
+    const int tap = r % taps;
+    const int t = r / taps;
+    const int o = t * nt + n, c = q * 8 + j;                                    // packed-view (out, in) channel
+    const float v = transposed ? w[((int64_t)c * Cin + o) * taps + (taps - 1 - tap)] : w[((int64_t)o * Cin + c) * taps + tap];
+    out[i] = __float2bfloat16_rn(v);
+  }
+}
+
 inline unsigned grid_for(int64_t total) {
   return (unsigned)std::min<int64_t>(ceil_div(total, kT), (int64_t)sm_count() * 16);
 }
@@ -235,6 +257,20 @@ inline unsigned grid_for(int64_t total) {
 }  // namespace ctl
 
 using namespace ctl;
+
+extern "C" int ctl_pack_conv_weight(const float* weight, int64_t Cout, int64_t Cin, int taps, int transposed, void* out,
+                                    void* stream) {
+  CTL_REQUIRE(weight && out && (taps == 1 || taps == 9), CTL_ERR_INVALID, "ctl_pack_conv_weight: bad arguments");
+  const int co_p = (int)(transposed ? Cin : Cout), ci_p = (int)(transposed ? Cout : Cin);
+  const int nt = ctl_conv2d_n_tile(ci_p, co_p, taps);
+  CTL_REQUIRE(nt > 0, CTL_ERR_UNSUPPORTED, "ctl_pack_conv_weight: no tcgen05 conv kernel for %d -> %d channels", ci_p, co_p);
+  if (sm_count() < 0) return CTL_ERR_CUDA;
+  const int64_t total = Cout * Cin * taps;
+  pack_conv_weight_kernel<<<grid_for(total), kT, 0, (cudaStream_t)stream>>>(weight, (__nv_bfloat16*)out, (int)Cout, (int)Cin,
+                                                                          taps, nt, transposed);
+  CTL_CUDA_OK(cudaGetLastError(), "pack_conv_weight launch");
+  return CTL_OK;
+}
 
 extern "C" int ctl_nchw_to_c8(const void* x, int x_dtype, int64_t N, int64_t C, int64_t H, int64_t W, void* y,
                               void* stream) {

@@ -39,7 +39,8 @@ struct WgradParams {
   int N, H, W, Cout;
   int tiles_x, tiles_y;
   int64_t num_tiles;
-  float* dW;                 // fp32 [TAPS][CIN][Cout], accumulated into
+  float* dW;                 // fp32, accumulated into: element (tap, ci, co) at tap*s_tap + ci*s_ci + co*s_co
+  int64_t s_co, s_ci, s_tap;
 };
 
 template <int CIN, int NT, int TAPS, int STAGES>
@@ -194,11 +195,16 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constan
             tmem_ld_32x32b_x16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)((sx * Cfg::kG + j) * NT + c0), v);
             tmem_ld_wait();
             if (row_ok) {
-              float* dst = p.dW + ((int64_t)tap * CIN + ci) * p.Cout + n0 + c0;
+              float* dst = p.dW + tap * p.s_tap + ci * p.s_ci + (int64_t)(n0 + c0) * p.s_co;
+              if (p.s_co == 1 && ((reinterpret_cast<uintptr_t>(dst) & 15u) == 0)) {
 #pragma unroll
-              for (int i = 0; i < 16; i += 4)
-                red_add_v4(dst + i, __uint_as_float(v[i]), __uint_as_float(v[i + 1]), __uint_as_float(v[i + 2]),
-                           __uint_as_float(v[i + 3]));
+                for (int i = 0; i < 16; i += 4)
+                  red_add_v4(dst + i, __uint_as_float(v[i]), __uint_as_float(v[i + 1]), __uint_as_float(v[i + 2]),
+                             __uint_as_float(v[i + 3]));
+              } else {
+#pragma unroll
+                for (int i = 0; i < 16; ++i) atomicAdd(dst + i * p.s_co, __uint_as_float(v[i]));
+              }
             }
           }
         }
@@ -317,7 +323,8 @@ int dispatch_wgrad(const void* x, const void* dy, const WgradParams& p, int nt, 
 using namespace ctl;
 
 extern "C" int ctl_conv_wgrad_c8_bf16(const void* x, const void* dy, int64_t N, int64_t H, int64_t W, int64_t Cin,
-                                      int64_t Cout, int taps, float* dW, void* stream) {
+                                      int64_t Cout, int taps, float* dW, int64_t stride_co, int64_t stride_ci,
+                                      int64_t stride_tap, void* stream) {
   CTL_REQUIRE(x && dy && dW, CTL_ERR_INVALID, "ctl_conv_wgrad_c8_bf16: NULL pointer");
   CTL_REQUIRE(N > 0 && H > 0 && W > 0 && N <= 65535 && H <= 32768 && W <= 32768, CTL_ERR_INVALID,
               "ctl_conv_wgrad_c8_bf16: bad shape N=%lld H=%lld W=%lld", (long long)N, (long long)H, (long long)W);
@@ -325,13 +332,15 @@ extern "C" int ctl_conv_wgrad_c8_bf16(const void* x, const void* dy, int64_t N, 
   CTL_REQUIRE((Cin == 16 || Cin == 32 || Cin == 64 || Cin == 128) && Cout > 0 && Cout % 16 == 0, CTL_ERR_UNSUPPORTED,
               "ctl_conv_wgrad_c8_bf16 handles Cin in {16,32,64,128} and Cout %% 16 == 0 (got Cin=%lld Cout=%lld)",
               (long long)Cin, (long long)Cout);
-  CTL_REQUIRE(aligned16(x) && aligned16(dy) && aligned16(dW), CTL_ERR_INVALID,
-              "ctl_conv_wgrad_c8_bf16: pointers must be 16-byte aligned");
+  CTL_REQUIRE(aligned16(x) && aligned16(dy) && (reinterpret_cast<uintptr_t>(dW) & 3u) == 0, CTL_ERR_INVALID,
+              "ctl_conv_wgrad_c8_bf16: x / dy must be 16-byte aligned");
+  CTL_REQUIRE(stride_co > 0 && stride_ci > 0 && stride_tap > 0, CTL_ERR_INVALID, "ctl_conv_wgrad_c8_bf16: strides must be positive");
   const int nt = wgrad_n_tile((int)Cin, (int)Cout, taps);
   CTL_REQUIRE(nt > 0, CTL_ERR_UNSUPPORTED, "ctl_conv_wgrad_c8_bf16: no N tile for Cout=%lld", (long long)Cout);
   if (sm_count() < 0) return CTL_ERR_CUDA;
   WgradParams p = {};
   p.N = (int)N; p.H = (int)H; p.W = (int)W; p.Cout = (int)Cout; p.dW = dW;
+  p.s_co = stride_co; p.s_ci = stride_ci; p.s_tap = stride_tap;
   cudaStream_t st = (cudaStream_t)stream;
   if (taps == 9) {
     switch ((int)Cin) {

@@ -19,15 +19,35 @@ import torch.nn as nn
 
 from . import ops
 
+# Bumped after EVERY optimizer step (global post-step hook below).  Fused / foreach optimizers update parameters without
+# bumping Tensor._version, so the version counter alone would leave the packed bf16 copies stale -- and training on
+# stale forward weights silently stops learning.
+_WEIGHTS_EPOCH = [0]
+
+
+def weights_changed():
+    """Call after modifying parameters through a path autograd's version counter does not see."""
+    _WEIGHTS_EPOCH[0] += 1
+
+
+def _after_optimizer_step(optimizer, args, kwargs):
+    _WEIGHTS_EPOCH[0] += 1
+
+
+from torch.optim.optimizer import register_optimizer_step_post_hook as _register_post_hook  # noqa: E402
+
+_register_post_hook(_after_optimizer_step)
+
+
 def _packed(param, fn, tag='fwd'):
-    """Packed bf16 copy of a weight, rebuilt when the parameter is modified in place (optimizer step) or its storage is
-    replaced.  `tag` distinguishes the packings of one parameter (forward, input-gradient, per-tap transposed-conv
-    slices).  The cache lives ON the parameter object: a global table keyed by id() would hand a new parameter the
-    packed weights of a dead one whose id / address it inherited."""
+    """Packed bf16 copy of a weight, rebuilt when the parameter is modified in place, its storage is replaced, or any
+    optimizer has stepped since.  `tag` distinguishes the packings of one parameter (forward, input-gradient, per-tap
+    transposed-conv slices).  The cache lives ON the parameter object: a global table keyed by id() would hand a new
+    parameter the packed weights of a dead one whose id / address it inherited."""
     cache = param.__dict__.get('_ctl_packed')
     if cache is None:
         cache = param.__dict__['_ctl_packed'] = {}
-    ver = (param.data_ptr(), param._version)
+    ver = (param.data_ptr(), param._version, _WEIGHTS_EPOCH[0])
     hit = cache.get(tag)
     if hit is None or hit[0] != ver:
         hit = (ver, fn(param))

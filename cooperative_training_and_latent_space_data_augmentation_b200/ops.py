@@ -192,9 +192,10 @@ def conv_supported(cin, cout, kernel_size):
     return taps in (1, 9) and _lib.load().ctl_conv2d_n_tile(int(cin), int(cout), taps) > 0
 
 
-def pack_conv_weight(weight):
+def pack_conv_weight_torch(weight):
     """[Cout,Cin,k,k] (k = 1 or 3) -> bf16 [Cout/NT][taps][Cin/8][NT][8], the K-major core-matrix order the
-    UMMA descriptors of conv_tc.cu expect (include/ctl_b200.h).  Tiny tensors: plain torch ops."""
+    UMMA descriptors of conv_tc.cu expect (include/ctl_b200.h) -- the torch-ops statement of ctl_pack_conv_weight,
+    used for derived weights (transposed-conv slices) and by the tests."""
     cout, cin, kh, kw = weight.shape
     taps = kh * kw
     nt = _lib.load().ctl_conv2d_n_tile(cin, cout, taps)
@@ -204,6 +205,27 @@ def pack_conv_weight(weight):
     return w.permute(3, 0, 1, 4, 2).contiguous()
 
 
+def _pack_kernel(weight, transposed):
+    cout, cin, kh, kw = weight.shape
+    taps = kh * kw
+    co_p, ci_p = (cin, cout) if transposed else (cout, cin)
+    if kh != kw or taps not in (1, 9) or _lib.load().ctl_conv2d_n_tile(ci_p, co_p, taps) <= 0:
+        raise NotImplementedError("no tcgen05 conv kernel for weight shape %s" % (tuple(weight.shape),))
+    w = weight.detach()
+    if w.dtype != torch.float32 or not w.is_contiguous():
+        w = w.to(torch.float32).contiguous()
+    _need_cuda(w)
+    out = torch.empty(cout * cin * taps, device=w.device, dtype=torch.bfloat16)
+    with torch.cuda.device(w.device):
+        _lib.check(_lib.load().ctl_pack_conv_weight(w.data_ptr(), cout, cin, taps, int(transposed), out.data_ptr(), _stream()))
+    return out
+
+
+def pack_conv_weight(weight):
+    """Packed bf16 forward weight of a Conv2d (one kernel launch; see pack_conv_weight_torch for the layout)."""
+    return _pack_kernel(weight, False)
+
+
 def pack_convtranspose2x2_weight(weight):
     """ConvTranspose2d(k=2, s=2) weight [Cin, Cout, 2, 2] -> the 1x1 GEMM weight [4*Cout, Cin, 1, 1] with rows
     ordered (dy*2+dx)*Cout + co, packed for ctl_conv2d_c8_bf16(up2x=1)."""
@@ -211,7 +233,7 @@ def pack_convtranspose2x2_weight(weight):
     if (kh, kw) != (2, 2):
         raise NotImplementedError("only kernel 2 / stride 2 transposed convolutions are on the hot path")
     w = weight.detach().permute(2, 3, 1, 0).reshape(4 * cout, cin, 1, 1)
-    return pack_conv_weight(w)
+    return pack_conv_weight_torch(w)
 
 
 def conv_stats_fusable(cin, cout, taps):
@@ -354,21 +376,36 @@ def scale_shift_act_c8(x, scale, shift, act=ACT_NONE, inplace=False):
 def pack_conv_weight_dgrad(weight):
     """Packed weights of the INPUT-gradient convolution of a stride-1 (or zero-stuffed stride-2) Conv2d:
     dx = conv(dy, w') with w'[ci][co][r][s] = w[co][ci][k-1-r][k-1-s]."""
-    return pack_conv_weight(weight.detach().flip(2, 3).transpose(0, 1))
+    return _pack_kernel(weight, True)
 
 
-def conv_wgrad_c8(x, dy, taps):
-    """K3w: fp32 [taps][Cin][Cout] = sum_p x[p + tap - pad] (x) dy[p]  (tcgen05, both operands straight from C8)."""
-    _need_cuda(x, dy)
+def conv_wgrad_c8(x, dy, taps, out=None, layout='kernel'):
+    """K3w (tcgen05, both operands straight from C8): sum_p x[p + tap - pad] (x) dy[p], accumulated into `out` (zeroed
+    fp32; allocated when None).  layout 'kernel': [taps][Cin][Cout]; 'conv': nn.Conv2d's [Cout][Cin][k][k];
+    ('convT', d): tap d of a ConvTranspose2d weight [Cin][Cout][2][2] (taps must be 1)."""
+    _need_cuda(x, dy, out)
     N, cin, H, W = _c8_dims(x)
     N2, cout, H2, W2 = _c8_dims(dy)
     if (N2, H2, W2) != (N, H, W):
         raise ValueError("x %s and dy %s must share N, H, W" % (tuple(x.shape), tuple(dy.shape)))
-    dW = torch.zeros((taps, cin, cout), device=x.device, dtype=torch.float32)
+    offset = 0
+    if layout == 'kernel':
+        shape, strides = (taps, cin, cout), (1, cout, cin * cout)
+    elif layout == 'conv':
+        k = 3 if taps == 9 else 1
+        shape, strides = (cout, cin, k, k), (cin * taps, taps, 1)
+    else:
+        shape, strides, offset = (cin, cout, 2, 2), (4, 4 * cout, 1), int(layout[1])
+    numel = shape[0] * shape[1] * shape[2] * (shape[3] if len(shape) > 3 else 1)
+    if out is None:
+        out = torch.zeros(shape, device=x.device, dtype=torch.float32)
+    elif out.dtype != torch.float32 or not out.is_contiguous() or out.numel() != numel:
+        raise ValueError("out must be a contiguous float32 tensor of %d elements" % numel)
     with torch.cuda.device(x.device):
         _lib.check(_lib.load().ctl_conv_wgrad_c8_bf16(x.data_ptr(), dy.data_ptr(), N, H, W, cin, cout, taps,
-                                                      dW.data_ptr(), _stream()))
-    return dW
+                                                      out.data_ptr() + 4 * offset, strides[0], strides[1], strides[2],
+                                                      _stream()))
+    return out
 
 
 def wgrad_to_conv_weight(dW, k):
@@ -459,8 +496,9 @@ def split_parity2x2_c8(x):
     return y
 
 
-def head_bwd_c8(dy, y, x, weight, act=ACT_NONE):
-    """Backward of head_conv_c8.  Returns (dx C8, dW [Cout,16,1,1] fp32, db [Cout] fp32)."""
+def head_bwd_c8(dy, y, x, weight, act=ACT_NONE, out=None):
+    """Backward of head_conv_c8.  Returns (dx C8, dW [Cout,16,1,1] fp32, db [Cout] fp32); `out`: zeroed fp32 buffer of
+    Cout*16 + Cout elements to accumulate the parameter gradients into (allocated when None)."""
     _need_cuda(dy, y, x, weight)
     N, cin, H, W = _c8_dims(x)
     cout = weight.shape[0]
@@ -469,7 +507,7 @@ def head_bwd_c8(dy, y, x, weight, act=ACT_NONE):
         raise ValueError("dy must be [%d,%d,%d,%d]" % (N, cout, H, W))
     w = weight.detach().to(torch.float32).reshape(cout, cin).contiguous()
     dx = torch.empty_like(x)
-    grads = torch.zeros(cout * cin + cout, device=x.device, dtype=torch.float32)
+    grads = out if out is not None else torch.zeros(cout * cin + cout, device=x.device, dtype=torch.float32)
     yp = 0
     if act != ACT_NONE:
         y = y.to(torch.float32).contiguous()
@@ -480,8 +518,9 @@ def head_bwd_c8(dy, y, x, weight, act=ACT_NONE):
     return dx, grads[:cout * cin].view(cout, cin, 1, 1), grads[cout * cin:]
 
 
-def stem_wgrad_c8(dy, x, cin, in_mode=0, temperature=1.0):
-    """Weight gradient [16,cin,3,3] of stem_conv_c8 (dy: gradient of the raw stem output, C8 with 16 channels)."""
+def stem_wgrad_c8(dy, x, cin, in_mode=0, temperature=1.0, out=None):
+    """Weight gradient [16,cin,3,3] of stem_conv_c8 (dy: gradient of the raw stem output, C8 with 16 channels),
+    accumulated into `out` (zeroed fp32; allocated when None)."""
     _need_cuda(dy, x)
     N, cout, H, W = _c8_dims(dy)
     if in_mode == 2:
@@ -490,7 +529,7 @@ def stem_wgrad_c8(dy, x, cin, in_mode=0, temperature=1.0):
     else:
         xf = x.detach().to(torch.float32).contiguous()
         xp, lp = xf.data_ptr(), 0
-    dW = torch.zeros((cout, cin, 3, 3), device=dy.device, dtype=torch.float32)
+    dW = out if out is not None else torch.zeros((cout, cin, 3, 3), device=dy.device, dtype=torch.float32)
     with torch.cuda.device(dy.device):
         _lib.check(_lib.load().ctl_stem_wgrad_c8(dy.data_ptr(), xp, lp, in_mode, float(temperature), N, cin, H, W,
                                                  dW.data_ptr(), _stream()))

@@ -16,8 +16,9 @@ torch autograd only connects the sub-networks (losses, detach points), exactly w
 (medseg/models/advanced_triplet_recon_segmentation_model.py:414-467, :525-559), so `loss.backward()` and the five Adam
 optimizers are unchanged.  Activations and activation gradients are bf16 (C8); parameters and their gradients fp32.
 
-Gradient of a convolution bias that feeds a train-mode BatchNorm is identically zero (the mean subtraction removes it):
-those entries are returned as exact zeros.
+Gradient of a convolution bias that feeds a train-mode BatchNorm is identically zero (the mean subtraction removes it;
+the reference accumulates ~1e-9 rounding noise there): no gradient tensor is produced for those biases, so the
+optimizer leaves them alone -- the network function does not depend on them.
 """
 import torch
 import torch.nn as nn
@@ -29,25 +30,49 @@ LRELU = ops.ACT_LRELU
 
 
 # ------------------------------------------------------------------------------------------------ helpers
-def _bn_mode_stats(bn, a):
+class _Fwd:
+    """Per-forward scratch of one sub-network: ONE zeroed float64 arena for the BatchNorm sums the conv epilogues
+    accumulate, and the num_batches_tracked counters to bump (one foreach add at the end instead of one per layer)."""
+
+    def __init__(self, module, device):
+        n = getattr(module, '_ctl_bn_channels', None)
+        if n is None:
+            n = sum(m.num_features for m in module.modules() if isinstance(m, nn.BatchNorm2d))
+            module._ctl_bn_channels = n
+        self.arena = torch.zeros(2 * n, device=device, dtype=torch.float64)
+        self.used = 0
+        self.tracked = []
+
+    def sums(self, channels):
+        out = self.arena[self.used:self.used + 2 * channels].view(2, channels)
+        self.used += 2 * channels
+        return out
+
+    def finish(self):
+        if self.tracked:
+            torch._foreach_add_(self.tracked, 1)
+            self.tracked = []
+
+
+def _bn_mode_stats(fw, bn, a):
     """Train-mode BatchNorm statistics of the raw conv output `a`; honours track_running_stats like nn.BatchNorm2d."""
     track = bn.track_running_stats and bn.running_mean is not None
     scale, shift, mean, var = ops.bn_batch_affine_c8(
         a, bn.weight, bn.bias, bn.eps, bn.running_mean if track else None, bn.running_var if track else None,
         bn.momentum if bn.momentum is not None else 0.1, want_stats=True)
     if track:
-        bn.num_batches_tracked += 1
+        fw.tracked.append(bn.num_batches_tracked)
     return scale, shift, mean, var
 
 
-def _conv_bn(conv, bn, x):
+def _conv_bn(fw, conv, bn, x):
     """Raw conv output (+bias) and the train-mode BatchNorm statistics of it.  When the conv's N tile allows it the
     statistics are accumulated by the conv epilogue itself (no second pass over the tensor)."""
     k = conv.kernel_size[0]
     if conv.stride[0] != 1 or not ops.conv_stats_fusable(conv.in_channels, conv.out_channels, k * k):
         a = _conv_raw(conv, x)
-        return (a,) + _bn_mode_stats(bn, a)
-    sums = torch.zeros((2, conv.out_channels), device=x.device, dtype=torch.float64)
+        return (a,) + _bn_mode_stats(fw, bn, a)
+    sums = fw.sums(conv.out_channels)
     wp = _packed(conv.weight, ops.pack_conv_weight)
     a = ops.conv2d_c8(x, wp, conv.out_channels, k * k, shift=conv.bias, stats=sums)
     track = bn.track_running_stats and bn.running_mean is not None
@@ -55,7 +80,7 @@ def _conv_bn(conv, bn, x):
                                     bn.running_mean if track else None, bn.running_var if track else None,
                                     bn.momentum if bn.momentum is not None else 0.1)
     if track:
-        bn.num_batches_tracked += 1
+        fw.tracked.append(bn.num_batches_tracked)
     return (a,) + stats
 
 
@@ -72,9 +97,10 @@ def _dgrad(conv, dy, res=None):
     return ops.conv2d_c8(dy, wp, conv.in_channels, k * k, res=res)
 
 
-def _wgrad(conv, x, dy):
+def _wgrad(grads, conv, x, dy):
+    """K3w straight into nn.Conv2d's [Cout][Cin][k][k] layout, accumulated into a slice of the backward's zero arena."""
     k = conv.kernel_size[0]
-    return ops.wgrad_to_conv_weight(ops.conv_wgrad_c8(x, dy, k * k), k)
+    return ops.conv_wgrad_c8(x, dy, k * k, out=grads.zeros(conv.weight.shape), layout='conv')
 
 
 class _Grads(dict):
@@ -84,6 +110,18 @@ class _Grads(dict):
     def __init__(self, params, needs):
         super().__init__()
         self.need = {id(p) for p, n in zip(params, needs) if n}
+        # ONE zeroed fp32 arena for every accumulated (atomic) parameter gradient of this backward
+        total = sum(p.numel() for p, n in zip(params, needs) if n and p.dim() > 1)
+        self.arena = torch.zeros(total + 256, device=params[0].device, dtype=torch.float32) if total else None
+        self.used = 0
+
+    def zeros(self, shape):
+        n = 1
+        for d in shape:
+            n *= int(d)
+        out = self.arena[self.used:self.used + n].view(*shape)
+        self.used += (n + 3) // 4 * 4                      # keep slices 16-byte aligned
+        return out
 
     def wants(self, p):
         return p is not None and id(p) in self.need
@@ -96,8 +134,8 @@ class _Grads(dict):
 
 
 # ------------------------------------------------------------------------------------------------ conv + BN + act
-def conv_bn_act_fwd(conv, bn, x, act):
-    a, scale, shift, mean, var = _conv_bn(conv, bn, x)
+def conv_bn_act_fwd(fw, conv, bn, x, act):
+    a, scale, shift, mean, var = _conv_bn(fw, conv, bn, x)
     h = ops.scale_shift_act_c8(a, scale, shift, act)
     return h, (x, a, h, mean, var)
 
@@ -108,18 +146,16 @@ def conv_bn_act_bwd(conv, bn, act, saved, dh, grads, need_dx=True):
     grads.add(bn.weight, dg)
     grads.add(bn.bias, db)
     if grads.wants(conv.weight):
-        grads.add(conv.weight, _wgrad(conv, x, da))
-    if grads.wants(conv.bias):
-        grads.add(conv.bias, torch.zeros_like(conv.bias))
+        grads.add(conv.weight, _wgrad(grads, conv, x, da))
     return _dgrad(conv, da) if need_dx else None
 
 
 # ------------------------------------------------------------------------------------------------ residual body
-def residual_fwd(block, xr):
+def residual_fwd(fw, block, xr):
     """out = LReLU(conv_input(xr) + BN2(conv2(LReLU(BN1(conv1(xr))))))   (encoder_decoder.py:54-57, :334-337)"""
     seq = block.conv
-    h1, s1 = conv_bn_act_fwd(seq[0], seq[1], xr, LRELU)
-    a2, scale2, shift2, mean2, var2 = _conv_bn(seq[3], seq[4], h1)
+    h1, s1 = conv_bn_act_fwd(fw, seq[0], seq[1], xr, LRELU)
+    a2, scale2, shift2, mean2, var2 = _conv_bn(fw, seq[3], seq[4], h1)
     ci = block.conv_input
     wp = _packed(ci.weight, ops.pack_conv_weight)
     out = ops.conv2d_c8(xr, wp, ci.out_channels, 1, shift=ci.bias, res=a2, res_scale=scale2, res_shift=shift2, act=LRELU)
@@ -136,13 +172,12 @@ def residual_bwd(block, saved, dout, grads):
     grads.add(bn2.weight, dg2)
     grads.add(bn2.bias, db2)
     if grads.wants(ci.weight):
-        grads.add(ci.weight, _wgrad(ci, xr, dpre))
+        grads.add(ci.weight, _wgrad(grads, ci, xr, dpre))
         grads.add(ci.bias, db2)                             # sum over pixels of dpre == dbeta of BN2
     dxr = _dgrad(ci, dpre)
     # conv2
     if grads.wants(seq[3].weight):
-        grads.add(seq[3].weight, _wgrad(seq[3], h1, da2))
-        grads.add(seq[3].bias, torch.zeros_like(seq[3].bias))
+        grads.add(seq[3].weight, _wgrad(grads, seq[3], h1, da2))
     dh1 = _dgrad(seq[3], da2)
     # BN1 + LReLU + conv1
     x, a1, h1_, mean1, var1 = s1
@@ -150,15 +185,14 @@ def residual_bwd(block, saved, dout, grads):
     grads.add(seq[1].weight, dg1)
     grads.add(seq[1].bias, db1)
     if grads.wants(seq[0].weight):
-        grads.add(seq[0].weight, _wgrad(seq[0], xr, da1))
-        grads.add(seq[0].bias, torch.zeros_like(seq[0].bias))
+        grads.add(seq[0].weight, _wgrad(grads, seq[0], xr, da1))
     return _dgrad(seq[0], da1, res=dxr)
 
 
 # ------------------------------------------------------------------------------------------------ down / up blocks
-def down_fwd(block, x):
+def down_fwd(fw, block, x):
     xd = _conv_raw(block.down, x)                          # 3x3 stride 2 (no norm / activation)
-    out, s = residual_fwd(block, xd)
+    out, s = residual_fwd(fw, block, xd)
     return out, (x, s)
 
 
@@ -171,7 +205,7 @@ def down_bwd(block, saved, dout, grads, need_dx=True):
         return None
     dyz = ops.zero_stuff2x_c8(dxd)                          # the stride-2 output gradient seen at full resolution
     if want_w:
-        grads.add(down.weight, _wgrad(down, x, dyz))
+        grads.add(down.weight, _wgrad(grads, down, x, dyz))
         grads.add(down.bias, ops.channel_sum_c8(dxd))
     return _dgrad(down, dyz) if need_dx else None
 
@@ -180,14 +214,14 @@ def _convT_tap_weight(up, d):
     return up.weight.detach()[:, :, d // 2, d % 2].reshape(up.in_channels, up.out_channels, 1, 1)
 
 
-def up_fwd(block, x):
+def up_fwd(fw, block, x):
     if block.up_type == 'NN':
         xu = ops.upsample2x_c8(x)
     else:
         up = block.up
         wp = _packed(up.weight, ops.pack_convtranspose2x2_weight)
         xu = ops.conv2d_c8(x, wp, 4 * up.out_channels, 1, up2x=True, shift=up.bias.detach().repeat(4))
-    out, s = residual_fwd(block, xu)
+    out, s = residual_fwd(fw, block, xu)
     return out, (x, s)
 
 
@@ -202,8 +236,10 @@ def up_bwd(block, saved, dout, grads, need_dx=True):
         return None
     parts = ops.split_parity2x2_c8(dxu)                     # [4][N, C/8, H, W, 8]: dy per kernel tap
     if want_w:
-        dW = torch.stack([ops.conv_wgrad_c8(x, parts[d], 1)[0] for d in range(4)], dim=2)     # [ci][co][4]
-        grads.add(up.weight, dW.reshape(up.in_channels, up.out_channels, 2, 2))
+        dW = grads.zeros(up.weight.shape)                  # [ci][co][2][2], tap d written with stride 4
+        for d in range(4):
+            ops.conv_wgrad_c8(x, parts[d], 1, out=dW, layout=('convT', d))
+        grads.add(up.weight, dW)
         grads.add(up.bias, ops.channel_sum_c8(dxu))
     dx = None
     if need_dx:
@@ -217,16 +253,18 @@ def up_bwd(block, saved, dout, grads, need_dx=True):
 def encoder_fwd(enc, x, in_mode, temperature):
     """MyEncoder: planar input (fp32 image / logits, or int64 label map with in_mode 2) -> C8 latent."""
     inc = enc.inc
+    fw = _Fwd(enc, inc[0].weight.device)
     a0 = ops.stem_conv_c8(x, inc[0].weight, None, inc[0].bias, ops.ACT_NONE, in_mode, temperature)
-    scale0, shift0, mean0, var0 = _bn_mode_stats(inc[1], a0)
+    scale0, shift0, mean0, var0 = _bn_mode_stats(fw, inc[1], a0)
     h0 = ops.scale_shift_act_c8(a0, scale0, shift0, LRELU)
-    h, s_inc = conv_bn_act_fwd(inc[3], inc[4], h0, LRELU)   # BN then F.leaky_relu (encoder_decoder.py:405)
+    h, s_inc = conv_bn_act_fwd(fw, inc[3], inc[4], h0, LRELU)   # BN then F.leaky_relu (encoder_decoder.py:405)
     tape = [(a0, h0, mean0, var0), s_inc]
     for blk in (enc.down1, enc.down2, enc.down3, enc.down4):
-        h, s = down_fwd(blk, h)
+        h, s = down_fwd(fw, blk, h)
         tape.append(s)
-    z, s_fin = conv_bn_act_fwd(enc.final_conv[0], enc.final_conv[1], h, _act_code(enc.act))
+    z, s_fin = conv_bn_act_fwd(fw, enc.final_conv[0], enc.final_conv[1], h, _act_code(enc.act))
     tape.append(s_fin)
+    fw.finish()
     return z, tape
 
 
@@ -241,16 +279,18 @@ def encoder_bwd(enc, tape, dz, grads, x, in_mode, temperature, need_dx):
     grads.add(inc[1].weight, dg0)
     grads.add(inc[1].bias, db0)
     if grads.wants(inc[0].weight):
-        grads.add(inc[0].weight, ops.stem_wgrad_c8(da0, x, inc[0].in_channels, in_mode, temperature))
-        grads.add(inc[0].bias, torch.zeros_like(inc[0].bias))
+        grads.add(inc[0].weight, ops.stem_wgrad_c8(da0, x, inc[0].in_channels, in_mode, temperature,
+                                                   out=grads.zeros(inc[0].weight.shape)))
     if need_dx:
         return ops.stem_dgrad_c8(da0, x, inc[0].weight, in_mode, temperature)
     return None
 
 
 def decoupler_fwd(seq, z):
-    h, s1 = conv_bn_act_fwd(seq[0], seq[1], z, LRELU)
-    out, s2 = conv_bn_act_fwd(seq[3], seq[4], h, _act_code(seq[5]))
+    fw = _Fwd(seq, z.device)
+    h, s1 = conv_bn_act_fwd(fw, seq[0], seq[1], z, LRELU)
+    out, s2 = conv_bn_act_fwd(fw, seq[3], seq[4], h, _act_code(seq[5]))
+    fw.finish()
     return out, (s1, s2)
 
 
@@ -264,9 +304,11 @@ def decoupler_bwd(seq, saved, dout, grads):
 def decoder_fwd(dec, z_c8):
     tape = []
     y = z_c8
+    fw = _Fwd(dec, z_c8.device)
     for blk in (dec.up1, dec.up2, dec.up3, dec.up4):
-        y, s = up_fwd(blk, y)
+        y, s = up_fwd(fw, blk, y)
         tape.append(s)
+    fw.finish()
     act = _act_code(dec.last_act)
     out = ops.head_conv_c8(y, dec.final_conv.weight, dec.final_conv.bias, act)
     tape.append((y, out if act != ops.ACT_NONE else None))
@@ -276,7 +318,8 @@ def decoder_fwd(dec, z_c8):
 def decoder_bwd(dec, tape, dout, grads, need_dz):
     y, out = tape[4]
     fc = dec.final_conv
-    dy, dW, db = ops.head_bwd_c8(dout, out, y, fc.weight, _act_code(dec.last_act))
+    gbuf = grads.zeros((fc.weight.numel() + fc.out_channels,)) if grads.arena is not None else None
+    dy, dW, db = ops.head_bwd_c8(dout, out, y, fc.weight, _act_code(dec.last_act), out=gbuf)
     grads.add(fc.weight, dW)
     grads.add(fc.bias, db)
     d = dy

@@ -124,6 +124,9 @@ int ctl_philox_uniform(uint64_t seed, uint64_t offset, uint64_t first_index, int
  * tensor; needs ctl_conv2d_n_tile(...) <= 32 and up2x == 0.  Finalise with ctl_bn_affine_from_sums.
  */
 int ctl_conv2d_n_tile(int Cin, int Cout, int taps);
+/* fp32 nn.Conv2d weight [Cout][Cin][k][k] (taps = k*k) -> the packed bf16 w_packed above.  transposed = 1 packs the weight of
+ * the INPUT-gradient convolution instead, w'[ci][co][r][s] = w[co][ci][k-1-r][k-1-s] (its Cout' = Cin, Cin' = Cout). */
+int ctl_pack_conv_weight(const float* weight, int64_t Cout, int64_t Cin, int taps, int transposed, void* out, void* stream);
 int ctl_conv2d_c8_bf16(const void* x, int64_t N, int64_t H, int64_t W, int64_t Cin, const void* w_packed,
                        int64_t Cout, int taps, int subsample, int up2x, const float* scale,
                        const float* shift, const void* res, const float* res_scale,
@@ -171,11 +174,13 @@ int ctl_scale_shift_act_c8(const void* x, int64_t N, int64_t C, int64_t H, int64
  * medseg/models/ebm/encoder_decoder.py:19-68, :285-348, :351-415, :418-453, :456-503).
  * Input gradients of 3x3 / 1x1 convolutions run on ctl_conv2d_c8_bf16 itself with transposed + flipped weights.
  */
-/* K3w: dW[tap][ci][co] += sum_p x[p + tap - pad][ci] * dy[p][co] on tcgen05 (both operands MN-major from C8 tiles).
- * x: C8 [N,Cin/8,H,W,8], dy: C8 [N,Cout/8,H,W,8] (same H, W; 3x3 pad 1 or 1x1), dW: fp32 [taps][Cin][Cout], ACCUMULATED
- * into (zero it first).  Cin in {16,32,64,128}, Cout %% 16 == 0. */
+/* K3w: dW(tap, ci, co) += sum_p x[p + tap - pad][ci] * dy[p][co] on tcgen05 (both operands MN-major from C8 tiles).
+ * x: C8 [N,Cin/8,H,W,8], dy: C8 [N,Cout/8,H,W,8] (same H, W; 3x3 pad 1 or 1x1).  dW: fp32, ACCUMULATED into (zero it
+ * first); element (tap, ci, co) lives at dW[tap*stride_tap + ci*stride_ci + co*stride_co] -- (1, Cout, Cin*Cout) is the
+ * kernel's natural order, (Cin*taps, taps, 1) writes nn.Conv2d's [Cout][Cin][k][k] directly, (4, 4*Cout, -) with dW
+ * offset by d writes tap d of a ConvTranspose2d [Cin][Cout][2][2].  Cin in {16,32,64,128}, Cout %% 16 == 0. */
 int ctl_conv_wgrad_c8_bf16(const void* x, const void* dy, int64_t N, int64_t H, int64_t W, int64_t Cin, int64_t Cout,
-                           int taps, float* dW, void* stream);
+                           int taps, float* dW, int64_t stride_co, int64_t stride_ci, int64_t stride_tap, void* stream);
 /* workspace bytes of the per-channel reductions below */
 size_t ctl_reduce_workspace_bytes(int64_t N, int64_t C);
 /* per-channel sum / sum of squares of a C8 tensor (bias gradients of convolutions without BatchNorm) */

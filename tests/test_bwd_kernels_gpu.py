@@ -46,6 +46,12 @@ def test_wgrad_matches_torch(ops, cin, cout, k, N, H, W):
     got = ops.wgrad_to_conv_weight(ops.conv_wgrad_c8(ops.nchw_to_c8(x), ops.nchw_to_c8(dy), k * k), k)
     want = torch.nn.grad.conv2d_weight(x.float(), (cout, cin, k, k), dy.float(), padding=k // 2)
     _cmp(got, want, 2e-3, "wgrad %d->%d k%d" % (cin, cout, k))
+    # straight into nn.Conv2d's layout, accumulating into a caller-provided (arena) slice
+    arena = torch.zeros(cout * cin * k * k + 8, device="cuda")
+    direct = ops.conv_wgrad_c8(ops.nchw_to_c8(x), ops.nchw_to_c8(dy), k * k, out=arena[4:4 + cout * cin * k * k].view(cout, cin, k, k),
+                               layout='conv')
+    _cmp(direct, want, 2e-3, "wgrad (conv layout)")
+    assert float(arena[:4].abs().sum()) == 0 and float(arena[-4:].abs().sum()) == 0
 
 
 @pytest.mark.parametrize("cin,cout,k,N,H,W", [(16, 16, 3, 2, 64, 48), (16, 32, 3, 2, 40, 24), (128, 64, 3, 2, 28, 28),
@@ -95,6 +101,10 @@ def test_convtranspose_backward_via_parity_split(ops, C, N, H, W):
     xc = ops.nchw_to_c8(x)
     dW = torch.stack([ops.conv_wgrad_c8(xc, parts[d], 1)[0] for d in range(4)], dim=2).reshape(C, C, 2, 2)
     _cmp(dW, wf.grad, 2e-3, "convT wgrad")
+    dW2 = torch.zeros(C, C, 2, 2, device="cuda")
+    for d in range(4):
+        ops.conv_wgrad_c8(xc, parts[d], 1, out=dW2, layout=('convT', d))
+    _cmp(dW2, wf.grad, 2e-3, "convT wgrad (strided taps)")
     dx = None
     for d in range(4):
         wp = ops.pack_conv_weight(w[:, :, d // 2, d % 2].reshape(C, C, 1, 1))

@@ -156,3 +156,11 @@ def test_conv_rejects_unsupported(ops):
     assert not ops.conv_supported(8, 16, 3) and not ops.conv_supported(16, 4, 1) and not ops.conv_supported(16, 16, 5)
     with pytest.raises(NotImplementedError):
         ops.pack_conv_weight(torch.zeros(16, 8, 3, 3, device="cuda"))
+
+
+@pytest.mark.parametrize("cout,cin,k", [(16, 16, 3), (32, 16, 3), (128, 64, 3), (128, 128, 3), (64, 128, 1), (16, 32, 1)])
+def test_pack_kernel_matches_torch_statement(ops, cout, cin, k):
+    w = torch.randn(cout, cin, k, k, device="cuda")
+    assert torch.equal(ops.pack_conv_weight(w), ops.pack_conv_weight_torch(w).reshape(-1))
+    want = ops.pack_conv_weight_torch(w.flip(2, 3).transpose(0, 1)).reshape(-1)
+    assert torch.equal(ops.pack_conv_weight_dgrad(w), want)

@@ -248,3 +248,25 @@ def test_cooperative_step_kernel_mode_tracks_fp32(env, latent_DA):
     assert not bad, "%s\nall: %s" % (bad, info)
     if latent_DA:
         assert rb['perturbed_image'].requires_grad is False and rb['perturbed_seg'].requires_grad is False
+
+
+def test_kernel_mode_trains_like_the_library_path(env):
+    """Ten optimizer steps on a fixed batch: the loss must FALL as it does with cuDNN's bf16 path (a stale packed
+    weight or a wrong-signed gradient shows up here, not in single-step comparisons)."""
+    pkg, _ = env
+    curves = {}
+    for mode in ("bf16", "kernel"):
+        try:
+            pkg.conv_blocks.set_precision(mode)
+            solver, img, lab, noise = _solver_and_batch(pkg)
+            random.seed(3); np.random.seed(3); torch.manual_seed(3)
+            curves[mode] = [float(pkg.cooperative_step(solver, img, lab, CFG_I, CFG_S, noise=noise)['loss'])
+                            for _ in range(10)]
+        finally:
+            pkg.conv_blocks.set_precision("fp32")
+    print(curves)
+    drop_lib = curves["bf16"][0] - curves["bf16"][-1]
+    drop_ker = curves["kernel"][0] - curves["kernel"][-1]
+    assert drop_lib > 0.5, curves
+    assert drop_ker > 0.7 * drop_lib, curves
+    assert abs(curves["kernel"][-1] - curves["bf16"][-1]) < 0.08 * curves["bf16"][-1], curves
