@@ -219,6 +219,46 @@ def masking_microbench(pkg, peaks, iters=20):
     return roofline, out
 
 
+# ------------------------------------------------------------------------------------------------ conv microbench
+def conv_microbench(pkg, peaks, batch, iters=5):
+    """K3 (forward / dgrad kernel) and K3w (weight gradient) on the 3x3 layer classes of FCN_16_standard at the bench
+    batch: TFLOP/s against the measured bf16 peak (tensor-pipe utilisation) next to GB/s over the algorithmic bytes
+    (bf16 in + out) against the measured HBM peak -- the 16/32-channel layers sit below the ridge, so
+    their bound is HBM.  CUDA events, L2 flushed between iterations."""
+    ops = pkg.ops
+    flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device="cuda")
+    out = {}
+
+    def timed(fn):
+        for _ in range(2):
+            fn()
+        ts = []
+        for _ in range(iters):
+            flush.zero_()
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record(); fn(); b.record()
+            torch.cuda.synchronize()
+            ts.append(a.elapsed_time(b) * 1e-3)
+        return statistics.mean(ts)
+
+    for cin, cout, size in ((16, 16, 224), (32, 32, 112), (64, 64, 56), (128, 128, 28)):
+        x = ops.nchw_to_c8(torch.randn(batch, cin, size, size, device="cuda"))
+        dy = ops.nchw_to_c8(torch.randn(batch, cout, size, size, device="cuda") * 0.1)
+        wp = ops.pack_conv_weight(torch.randn(cout, cin, 3, 3, device="cuda") * 0.05)
+        shift = torch.randn(cout, device="cuda")
+        dw = torch.zeros(cout, cin, 3, 3, device="cuda")
+        flops = 2.0 * batch * size * size * cout * cin * 9
+        byts = 2.0 * batch * size * size * (cin + cout)
+        for name, fn in (("fwd", lambda: ops.conv2d_c8(x, wp, cout, 9, shift=shift, act=ops.ACT_LRELU)),
+                         ("wgrad", lambda: ops.conv_wgrad_c8(x, dy, 9, out=dw, layout='conv'))):
+            t = timed(fn)
+            out["%s_%dto%d_3x3_%d" % (name, cin, cout, size)] = {
+                "us": round(t * 1e6, 1), "TFLOPs": round(flops / t / 1e12, 1),
+                "tensor_frac": round(flops / t / 1e12 / peaks["bf16_tflops"], 3),
+                "GBps": round(byts / t / 1e9, 0), "hbm_frac": round(byts / t / 1e9 / peaks["hbm_gbs"], 3)}
+    return out
+
+
 # ------------------------------------------------------------------------------------------------ GPU arm
 def run_gpu_arm(args):
     import torch.distributed as dist
@@ -306,6 +346,7 @@ def run_gpu_arm(args):
     value = global_batch * args.steps / t_dev
     e2e_value = global_batch * args.steps / t_e2e
     roofline, sweep = masking_microbench(pkg, peaks)
+    conv_layers = conv_microbench(pkg, peaks, args.batch)
     gf = GF_PER_SAMPLE.get(args.size)
     cpu = None
     if world == 1 and not args.no_cpu_baseline:
@@ -328,6 +369,7 @@ def run_gpu_arm(args):
         "roofline": roofline,
         "masking_GBps": {k: round(v["GBps"], 1) for k, v in sweep.items()},
         "masking_us": {k: round(v["us"], 2) for k, v in sweep.items()},
+        "conv_blocks": conv_layers,
         "step_tensor_frac": (value * gf * 1e9 / (world * peaks["bf16_tflops_sustained"] * 1e12)) if gf else None,
         "cpu_baseline": cpu,
         "clocks": clocks,

@@ -80,6 +80,10 @@ def _compare(ref, got, what, in_tol=0.35, p_tol=0.4, cos_tol=0.95):
     flat_r, flat_k = [], []
     for n, r in gp_r.items():
         k = gp_k[n]
+        if r is not None and k is None:
+            # a conv bias in front of a train-mode BatchNorm: identically zero gradient, none is produced
+            assert float(r.norm()) < 1e-4 * big, (what, n, "no gradient produced but the reference has one")
+            continue
         assert (r is None) == (k is None), (what, n)
         if r is None:
             continue
@@ -176,8 +180,9 @@ def test_untracked_bn_pass_leaves_buffers_and_affine_grads_alone(env):
     for n, b in dec.named_buffers():
         assert torch.equal(b, before[n]), n
     for n, p in dec.named_parameters():
-        is_bn = p.dim() == 1 and (".conv.1." in n or ".conv.4." in n)
-        assert (p.grad is None) == is_bn, n
+        is_bn = p.dim() == 1 and (".conv.1." in n or ".conv.4." in n)                       # frozen inside the context
+        bias_before_bn = n.endswith((".conv.0.bias", ".conv.3.bias"))                       # identically zero: not produced
+        assert (p.grad is None) == (is_bn or bias_before_bn), n
         p.grad = None
     assert zz.grad is not None
 
@@ -228,8 +233,11 @@ def test_cooperative_step_kernel_mode_tracks_fp32(env, latent_DA):
         info.append((k, round(la[k], 5), round(lb[k], 5), round(lc[k], 5)))
         if abs(la[k] - lb[k]) > tol * abs(la[k]) + 1e-4:
             bad.append(info[-1])
-    if set(ga) != set(gb):
-        bad.append(("gradient sets differ", sorted(set(ga) ^ set(gb))[:8]))
+    bias_before_bn = (".conv.0.bias", ".conv.3.bias", ".inc.0.bias", ".inc.3.bias", ".final_conv.0.bias",
+                      ".code_decoupler.0.bias", ".code_decoupler.3.bias")
+    extra = [n for n in set(ga) ^ set(gb) if not (n in ga and n.endswith(bias_before_bn))]
+    if extra:
+        bad.append(("gradient sets differ", sorted(extra)[:8]))
 
     def cosine(x, y, names):
         a = torch.cat([x[n].reshape(-1) for n in names])
@@ -270,3 +278,27 @@ def test_kernel_mode_trains_like_the_library_path(env):
     assert drop_lib > 0.5, curves
     assert drop_ker > 0.7 * drop_lib, curves
     assert abs(curves["kernel"][-1] - curves["bf16"][-1]) < 0.08 * curves["bf16"][-1], curves
+
+
+def test_predict_on_a_10_slice_stack_matches_fp32(env):
+    """BASELINE.json configs[4]: inference-only FTN + STN refinement on a 10 x 256 x 256 stack (predict, n_iter=2) --
+    kernel mode runs the BN-folded all-kernel forward (fastpath 'eval'); the label map must agree with the fp32 modules."""
+    pkg, _ = env
+    solver, _, _, _ = _solver_and_batch(pkg)
+    img, _, _ = weights.synthetic_batch(10, 256, 256, seed=9)
+    img = img.cuda()
+    try:
+        pkg.conv_blocks.set_precision("fp32")
+        want = solver.predict(img, softmax=True, n_iter=2)
+        pkg.conv_blocks.set_precision("kernel")
+        n0 = pkg._lib.LAUNCHES["count"]
+        got = solver.predict(img, softmax=True, n_iter=2)
+        launched = pkg._lib.LAUNCHES["count"] - n0
+    finally:
+        pkg.conv_blocks.set_precision("fp32")
+    assert launched > 50, "predict did not run on the kernels"
+    assert got.shape == want.shape == (10, 4, 256, 256) and got.dtype == torch.float32
+    agree = float((got.argmax(1) == want.argmax(1)).float().mean())
+    assert agree > 0.9, agree            # synthetic random weights: many pixels sit on near-ties between classes
+    assert float((got - want).abs().mean()) < 2e-2
+    assert solver.training is False
