@@ -160,6 +160,8 @@ def workload_config(args, batch_per_gpu):
                         "thresholds (max 0.5)" % (args.size, args.size, batch_per_gpu),
             "batch_per_gpu": batch_per_gpu, "global_batch": batch_per_gpu * args.gpus, "image": [1, args.size, args.size],
             "num_classes": 4, "precision": args.precision, "parallelism": "dp%d" % args.gpus,
+            "step_mode": "eager launches" if getattr(args, "no_graph", False) else
+                         "CUDA-graph replay (fwd+bwd graph, NCCL all-reduce, optimizer graph)",
             "l2_policy": "inputs larger than L2: one step touches several GB of activations (126 MB L2); the masking "
                          "microbench reads/writes 308 MB per call and additionally flushes L2 between iterations"}
 
@@ -282,7 +284,11 @@ def run_gpu_arm(args):
     torch.manual_seed(0)
     solver = pkg.AdvancedTripletReconSegmentationModel('FCN_16_standard', num_classes=4, learning_rate=1e-4)
     global_batch = args.batch * world
-    trainer = pkg.CooperativeTrainer(solver, global_batch, seed=0, image_cfg=IMAGE_CFG, seg_cfg=SEG_CFG)
+    if args.no_graph:
+        trainer = pkg.CooperativeTrainer(solver, global_batch, seed=0, image_cfg=IMAGE_CFG, seg_cfg=SEG_CFG)
+    else:       # product path: the step replayed from CUDA graphs (training.GraphedCooperativeTrainer)
+        trainer = pkg.GraphedCooperativeTrainer(solver, global_batch, seed=0, image_cfg=IMAGE_CFG, seg_cfg=SEG_CFG,
+                                                eager_steps=1 if args.profile else 3)
 
     # every rank draws its own slice of the global synthetic batch
     img_h, lab_h = synthetic_batch(args.batch, args.size, seed=1000 + rank, pin=True)
@@ -297,9 +303,10 @@ def run_gpu_arm(args):
         return trainer.step(img_d, lab_d)
 
     def e2e_step():
-        a = img_h.cuda(non_blocking=True)
-        b = lab_h.cuda(non_blocking=True)
-        out = trainer.step(a, b)
+        if args.no_graph:
+            out = trainer.step(img_h.cuda(non_blocking=True), lab_h.cuda(non_blocking=True))
+        else:
+            out = trainer.step(img_h, lab_h)        # pinned host tensors -> the trainer's static device buffers (H2D)
         return float(out['loss'].item())            # D2H read of the step's result
 
     def timed_loop(fn, steps):
@@ -317,6 +324,8 @@ def run_gpu_arm(args):
         return float(t.item()) * 1e-3, last
 
     n_warm = args.warmup if args.profile else max(args.warmup, 3)
+    if not args.no_graph:
+        n_warm += trainer.eager_steps + 1           # eager library warm-up + the capture step, then n_warm replays
     for _ in range(n_warm):
         device_step()
     sampler = ClockSampler(local_rank)
@@ -357,14 +366,14 @@ def run_gpu_arm(args):
                          "(%.1f s)" % (args.ref_batch, args.size, args.size, dt)}
     line = {
         "metric": "cooperative-training samples/sec", "value": value, "unit": "samples/s", "n_gpus": world,
-        "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": 1e3 * t_dev / args.steps,
+        "steps": args.steps, "warmup": n_warm, "ms_per_step": 1e3 * t_dev / args.steps,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32" if args.precision == "fp32" else "bf16", "data": "synthetic",
         "config": workload_config(args, args.batch),
         "e2e": {"value": e2e_value, "unit": "samples/s",
                 "h2d_bytes_per_step": int(img_h.numel() * 4 + lab_h.numel() * 8) * world,
                 "d2h_bytes_per_step": 4 * world, "ms_per_step": 1e3 * t_e2e / args.steps,
-                "api": "CooperativeTrainer.step on pinned host tensors + loss.item()"},
+                "api": "%s.step on pinned host tensors + loss.item()" % type(trainer).__name__},
         "gpu_launches": launches,
         "roofline": roofline,
         "masking_GBps": {k: round(v["GBps"], 1) for k, v in sweep.items()},
@@ -392,6 +401,7 @@ def main():
                     help="kernel: the sm_100a kernels of this build (product path); bf16/fp32: library convolutions")
     ap.add_argument("--ref-batch", type=int, default=8, help="bounded CPU sample: batch per CPU step")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-graph", action="store_true", help="issue the step's launches one by one (no CUDA graphs)")
     ap.add_argument("--profile", action="store_true", help="device loop only, honour --warmup < 3 (for ncu)")
     args = ap.parse_args()
     if args.impl == "reference":

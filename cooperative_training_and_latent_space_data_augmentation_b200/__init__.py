@@ -5,6 +5,6 @@ from . import _lib, conv_blocks, losses, model_util, networks, ops  # noqa: F401
 from .model_util import (mask_latent_code_channel_wise, mask_latent_code_spatial_wise,  # noqa: F401
                          set_rng_mode)
 from .solver import AdvancedTripletReconSegmentationModel  # noqa: F401
-from .training import CooperativeTrainer, cooperative_step  # noqa: F401
+from .training import CooperativeTrainer, GraphedCooperativeTrainer, cooperative_step  # noqa: F401
 
 __version__ = "0.1.0"

@@ -29,6 +29,9 @@ SIGNATURES = {
     "ctl_saliency_mask_apply": (_i, [_vp, _i, _vp, _i, _i64, _i64, _i64, _i, _i64, _i, _vp, _u64, _u64, _i64,
                                      _vp, _vp, _vp, _vp, _i, _vp]),
     "ctl_channel_dropout": (_i, [_vp, _i, _i64, _i64, _i64, _f, _f, _vp, _u64, _u64, _i64, _vp, _i, _vp, _vp, _vp]),
+    "ctl_saliency_mask_apply_dyn": (_i, [_vp, _i, _vp, _i, _i64, _i64, _i64, _i, _i, _vp, _u64, _vp,
+                                         _vp, _vp, _vp, _vp, _i, _vp]),
+    "ctl_channel_dropout_dyn": (_i, [_vp, _i, _i64, _i64, _i64, _f, _f, _u64, _vp, _vp, _i, _vp, _vp, _vp]),
     "ctl_philox_uniform": (_i, [_u64, _u64, _u64, _i64, _vp, _vp]),
     "ctl_conv2d_n_tile": (_i, [_i, _i, _i]),
     "ctl_pack_conv_weight": (_i, [_vp, _i64, _i64, _i, _i, _vp, _vp]),
@@ -63,7 +66,8 @@ _lib = None
 # kernels launched through this binding since import (bench.py reports the count inside its timed
 # region as `gpu_launches`); name -> kernels per successful call
 KERNELS_PER_CALL = {"ctl_saliency_reduce": 1, "ctl_topp_mask_apply": 2, "ctl_saliency_mask_apply": 3,
-                    "ctl_channel_dropout": 1, "ctl_philox_uniform": 1, "ctl_conv2d_c8_bf16": 1,
+                    "ctl_channel_dropout": 1, "ctl_saliency_mask_apply_dyn": 3, "ctl_channel_dropout_dyn": 1,
+                    "ctl_philox_uniform": 1, "ctl_conv2d_c8_bf16": 1,
                     "ctl_nchw_to_c8": 1, "ctl_c8_to_nchw": 1, "ctl_stem_conv3x3_c8": 1, "ctl_head_conv1x1_c8": 1,
                     "ctl_upsample2x_c8": 1, "ctl_bn_batch_affine_c8": 2, "ctl_scale_shift_act_c8": 1,
                     "ctl_conv_wgrad_c8_bf16": 1, "ctl_channel_sums_c8": 2, "ctl_bn_affine_from_sums": 1, "ctl_pack_conv_weight": 1, "ctl_bn_bwd_reduce_c8": 2,

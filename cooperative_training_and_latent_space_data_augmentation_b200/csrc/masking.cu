@@ -13,6 +13,7 @@
 //   saliency reduce : sizeof(g) * N*C*HW                       (+ 4*N*n written)
 //   top-p apply     : (sizeof(z) + sizeof(z_out)) * N*C*HW     (+ 4*N*n read/written)
 //   dropout         : (sizeof(z) + sizeof(z_out)) * N*C*HW     (+ 4*N*C*HW with the quirk mask)
+#include <stdlib.h>
 #include <algorithm>
 
 #include "ctl_common.cuh"
@@ -142,6 +143,8 @@ struct SelectArgs {
   int64_t first_sample;
   int k;
   int soft;
+  const int64_t* dyn;        // device [3] = {k, offset, first_sample} overriding the by-value fields (CUDA-graph
+                             // replay: the launch is recorded once, the per-step draws change), or nullptr
 };
 
 // ------------------------------------------------------------------------------------------------
@@ -231,6 +234,12 @@ select_mask_kernel(const float* s, int n, SelectArgs sa) {
   pdl_wait();                              // s comes from the preceding launch (K1) when chained
   __shared__ SelectSmem sm;
   const int64_t sample = blockIdx.x;
+  if (sa.dyn) {                            // host-validated by the caller; clamped so a stale buffer cannot run wild
+    const int64_t kd = sa.dyn[0];
+    sa.k = (int)(kd < 0 ? 0 : kd >= n ? n - 1 : kd);
+    sa.key.offset = (uint64_t)sa.dyn[1];
+    sa.first_sample = sa.dyn[2];
+  }
   select_and_build_mask(s + sample * n, n, sa.k, sa.soft, sa.rand, sa.key,
                         (uint64_t)(sa.first_sample + sample) * (uint64_t)n, sample * (int64_t)n,
                         sa.mask_out + sample * (int64_t)n, sa.thr_out ? sa.thr_out + sample : nullptr, sm);
@@ -300,7 +309,12 @@ template <typename ZT, typename OT, int VEC, int L>
 __global__ void __launch_bounds__(kThreads)
 channel_dropout_kernel(const ZT* __restrict__ z, OT* __restrict__ z_out, float* __restrict__ mask_out,
                        const float* __restrict__ keep, float* __restrict__ keep_out, PhiloxKey key,
-                       int64_t rows, int HW, int nv, float p, float scale, uint64_t first_row) {
+                       int64_t rows, int HW, int nv, float p, float scale, uint64_t first_row, const int64_t* dyn,
+                       int C) {
+  if (dyn) {                                             // {-, offset, first_sample} from device memory (graph replay)
+    key.offset = (uint64_t)dyn[1];
+    first_row = (uint64_t)dyn[2] * (uint64_t)C;
+  }
   const int lane = threadIdx.x & (L - 1);
   const int64_t row = (int64_t)blockIdx.x * (kThreads / L) + threadIdx.x / L;
   if (row >= rows) return;
@@ -386,6 +400,12 @@ int launch_saliency(const void* g, int g_dtype, int64_t N, int64_t C, int64_t HW
              : launch_saliency_spatial<__nv_bfloat16, 1>((const __nv_bfloat16*)g, s, N, Ci, HWi, st);
 }
 
+// Programmatic dependent launch can be switched off (CTL_PDL=0) for debugging.
+bool pdl_enabled() {
+  static const bool on = [] { const char* e = getenv("CTL_PDL"); return !(e && e[0] == '0'); }();
+  return on;
+}
+
 // one CTA per sample; chained == true: programmatic stream serialization after K1
 int launch_select(const float* s, int64_t N, int64_t n, const SelectArgs& sa, bool chained, cudaStream_t st) {
   cudaLaunchConfig_t cfg = {};
@@ -396,7 +416,7 @@ int launch_select(const float* s, int64_t N, int64_t n, const SelectArgs& sa, bo
   attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
   attr[0].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
-  cfg.numAttrs = chained ? 1 : 0;
+  cfg.numAttrs = (chained && pdl_enabled()) ? 1 : 0;
   CTL_CUDA_OK(cudaLaunchKernelEx(&cfg, select_mask_kernel, s, (int)n, sa), "select_mask launch");
   return CTL_OK;
 }
@@ -419,7 +439,7 @@ int launch_apply_kernel(const ZT* z, OT* z_out, const float* mask, int64_t rows,
   attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
   attr[0].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
-  cfg.numAttrs = 1;
+  cfg.numAttrs = pdl_enabled() ? 1 : 0;
   CTL_CUDA_OK(cudaLaunchKernelEx(&cfg, mask_apply_kernel<ZT, OT, VEC, L, MODE>, z, z_out, mask, rows, C, HW, nv),
               "mask_apply launch");
   return CTL_OK;
@@ -459,17 +479,18 @@ int launch_apply_any(int mode, const void* z, int z_dtype, void* z_out, int out_
 
 template <typename ZT, typename OT, int VEC>
 int launch_dropout(const ZT* z, OT* z_out, float* mask_out, const float* keep, float* keep_out, PhiloxKey key,
-                   int64_t rows, int HW, float p, float scale, uint64_t first_row, cudaStream_t st) {
+                   int64_t rows, int HW, float p, float scale, uint64_t first_row, const int64_t* dyn, int C,
+                   cudaStream_t st) {
   const int nv = HW / VEC;
   const int L = pick_lanes(nv);
   const int64_t grid64 = ceil_div(rows, kThreads / L);
   CTL_REQUIRE(grid64 <= 0x7fffffff, CTL_ERR_UNSUPPORTED, "too many rows for one launch");
   const unsigned grid = (unsigned)grid64;
   switch (L) {
-    case 32: channel_dropout_kernel<ZT, OT, VEC, 32><<<grid, kThreads, 0, st>>>(z, z_out, mask_out, keep, keep_out, key, rows, HW, nv, p, scale, first_row); break;
-    case 16: channel_dropout_kernel<ZT, OT, VEC, 16><<<grid, kThreads, 0, st>>>(z, z_out, mask_out, keep, keep_out, key, rows, HW, nv, p, scale, first_row); break;
-    case 8: channel_dropout_kernel<ZT, OT, VEC, 8><<<grid, kThreads, 0, st>>>(z, z_out, mask_out, keep, keep_out, key, rows, HW, nv, p, scale, first_row); break;
-    default: channel_dropout_kernel<ZT, OT, VEC, 4><<<grid, kThreads, 0, st>>>(z, z_out, mask_out, keep, keep_out, key, rows, HW, nv, p, scale, first_row); break;
+    case 32: channel_dropout_kernel<ZT, OT, VEC, 32><<<grid, kThreads, 0, st>>>(z, z_out, mask_out, keep, keep_out, key, rows, HW, nv, p, scale, first_row, dyn, C); break;
+    case 16: channel_dropout_kernel<ZT, OT, VEC, 16><<<grid, kThreads, 0, st>>>(z, z_out, mask_out, keep, keep_out, key, rows, HW, nv, p, scale, first_row, dyn, C); break;
+    case 8: channel_dropout_kernel<ZT, OT, VEC, 8><<<grid, kThreads, 0, st>>>(z, z_out, mask_out, keep, keep_out, key, rows, HW, nv, p, scale, first_row, dyn, C); break;
+    default: channel_dropout_kernel<ZT, OT, VEC, 4><<<grid, kThreads, 0, st>>>(z, z_out, mask_out, keep, keep_out, key, rows, HW, nv, p, scale, first_row, dyn, C); break;
   }
   CTL_CUDA_OK(cudaGetLastError(), "channel_dropout launch");
   return CTL_OK;
@@ -521,15 +542,16 @@ extern "C" int ctl_topp_mask_apply(const float* s, const void* z, int z_dtype, i
   if (int rc = check_select(n, k, first_sample)) return rc;
   if (sm_count() < 0) return CTL_ERR_CUDA;
   cudaStream_t st = (cudaStream_t)stream;
-  SelectArgs sa = {mask_out, thr_out, rand, PhiloxKey{seed, offset}, first_sample, (int)k, soft != 0};
+  SelectArgs sa = {mask_out, thr_out, rand, PhiloxKey{seed, offset}, first_sample, (int)k, soft != 0, nullptr};
   if (int rc = launch_select(s, N, n, sa, /*chained=*/false, st)) return rc;
   return launch_apply_any(mode, z, z_dtype, z_out, out_dtype, mask_out, N, C, HW, st);
 }
 
-extern "C" int ctl_saliency_mask_apply(const void* g, int g_dtype, const void* z, int z_dtype, int64_t N, int64_t C,
+static int saliency_mask_apply_impl(const void* g, int g_dtype, const void* z, int z_dtype, int64_t N, int64_t C,
                                        int64_t HW, int mode, int64_t k, int soft, const float* rand, uint64_t seed,
                                        uint64_t offset, int64_t first_sample, float* s_scratch, float* mask_out,
-                                       float* thr_out, void* z_out, int out_dtype, void* stream) {
+                                       float* thr_out, void* z_out, int out_dtype, const int64_t* dyn,
+                                       void* stream) {
   CTL_REQUIRE(g && z && s_scratch && mask_out && z_out, CTL_ERR_INVALID,
               "ctl_saliency_mask_apply: NULL pointer");
   CTL_REQUIRE(valid_dtype(g_dtype) && valid_dtype(z_dtype) && valid_dtype(out_dtype), CTL_ERR_INVALID,
@@ -541,15 +563,33 @@ extern "C" int ctl_saliency_mask_apply(const void* g, int g_dtype, const void* z
   if (int rc = check_select(n, k, first_sample)) return rc;
   if (sm_count() < 0) return CTL_ERR_CUDA;
   cudaStream_t st = (cudaStream_t)stream;
-  SelectArgs sa = {mask_out, thr_out, rand, PhiloxKey{seed, offset}, first_sample, (int)k, soft != 0};
+  SelectArgs sa = {mask_out, thr_out, rand, PhiloxKey{seed, offset}, first_sample, (int)k, soft != 0, dyn};
   if (int rc = launch_saliency(g, g_dtype, N, C, HW, mode, s_scratch, st)) return rc;      // ordinary launch
   if (int rc = launch_select(s_scratch, N, n, sa, /*chained=*/true, st)) return rc;         // PDL after K1
   return launch_apply_any(mode, z, z_dtype, z_out, out_dtype, mask_out, N, C, HW, st);
 }
 
-extern "C" int ctl_channel_dropout(const void* z, int z_dtype, int64_t N, int64_t C, int64_t HW, float p, float scale,
+extern "C" int ctl_saliency_mask_apply(const void* g, int g_dtype, const void* z, int z_dtype, int64_t N, int64_t C,
+                                       int64_t HW, int mode, int64_t k, int soft, const float* rand, uint64_t seed,
+                                       uint64_t offset, int64_t first_sample, float* s_scratch, float* mask_out,
+                                       float* thr_out, void* z_out, int out_dtype, void* stream) {
+  return saliency_mask_apply_impl(g, g_dtype, z, z_dtype, N, C, HW, mode, k, soft, rand, seed, offset, first_sample,
+                                  s_scratch, mask_out, thr_out, z_out, out_dtype, nullptr, stream);
+}
+
+extern "C" int ctl_saliency_mask_apply_dyn(const void* g, int g_dtype, const void* z, int z_dtype, int64_t N,
+                                           int64_t C, int64_t HW, int mode, int soft, const float* rand,
+                                           uint64_t seed, const int64_t* step_params, float* s_scratch,
+                                           float* mask_out, float* thr_out, void* z_out, int out_dtype, void* stream) {
+  CTL_REQUIRE(step_params, CTL_ERR_INVALID, "ctl_saliency_mask_apply_dyn: NULL step_params");
+  return saliency_mask_apply_impl(g, g_dtype, z, z_dtype, N, C, HW, mode, /*k=*/0, soft, rand, seed, 0, 0, s_scratch,
+                                  mask_out, thr_out, z_out, out_dtype, step_params, stream);
+}
+
+static int channel_dropout_impl(const void* z, int z_dtype, int64_t N, int64_t C, int64_t HW, float p, float scale,
                                    const float* keep, uint64_t seed, uint64_t offset, int64_t first_sample,
-                                   void* z_out, int out_dtype, float* mask_out, float* keep_out, void* stream) {
+                                   void* z_out, int out_dtype, float* mask_out, float* keep_out, const int64_t* dyn,
+                                   void* stream) {
   CTL_REQUIRE(z && z_out, CTL_ERR_INVALID, "ctl_channel_dropout: NULL pointer");
   CTL_REQUIRE(valid_dtype(z_dtype) && valid_dtype(out_dtype), CTL_ERR_INVALID, "ctl_channel_dropout: unknown dtype");
   CTL_REQUIRE(p >= 0.0f && p <= 1.0f, CTL_ERR_INVALID,
@@ -566,12 +606,27 @@ extern "C" int ctl_channel_dropout(const void* z, int z_dtype, int64_t N, int64_
   const uint64_t first_row = (uint64_t)first_sample * (uint64_t)C;
 #define CTL_DROP(ZT, OT, V) \
   return launch_dropout<ZT, OT, V>((const ZT*)z, (OT*)z_out, mask_out, keep, keep_out, key, rows, (int)HW, p, scale, \
-                                   first_row, st)
+                                   first_row, dyn, (int)C, st)
   if (zf && of) { if (vec) CTL_DROP(float, float, 4); else CTL_DROP(float, float, 1); }
   if (zf && !of) { if (vec) CTL_DROP(float, __nv_bfloat16, 4); else CTL_DROP(float, __nv_bfloat16, 1); }
   if (!zf && of) { if (vec) CTL_DROP(__nv_bfloat16, float, 8); else CTL_DROP(__nv_bfloat16, float, 1); }
   if (vec) CTL_DROP(__nv_bfloat16, __nv_bfloat16, 8); else CTL_DROP(__nv_bfloat16, __nv_bfloat16, 1);
 #undef CTL_DROP
+}
+
+extern "C" int ctl_channel_dropout(const void* z, int z_dtype, int64_t N, int64_t C, int64_t HW, float p, float scale,
+                                   const float* keep, uint64_t seed, uint64_t offset, int64_t first_sample,
+                                   void* z_out, int out_dtype, float* mask_out, float* keep_out, void* stream) {
+  return channel_dropout_impl(z, z_dtype, N, C, HW, p, scale, keep, seed, offset, first_sample, z_out, out_dtype,
+                              mask_out, keep_out, nullptr, stream);
+}
+
+extern "C" int ctl_channel_dropout_dyn(const void* z, int z_dtype, int64_t N, int64_t C, int64_t HW, float p,
+                                       float scale, uint64_t seed, const int64_t* step_params, void* z_out,
+                                       int out_dtype, float* mask_out, float* keep_out, void* stream) {
+  CTL_REQUIRE(step_params, CTL_ERR_INVALID, "ctl_channel_dropout_dyn: NULL step_params");
+  return channel_dropout_impl(z, z_dtype, N, C, HW, p, scale, nullptr, seed, 0, 0, z_out, out_dtype, mask_out,
+                              keep_out, step_params, stream);
 }
 
 extern "C" int ctl_philox_uniform(uint64_t seed, uint64_t offset, uint64_t first_index, int64_t count, float* out,

@@ -49,6 +49,25 @@ def native_rng():
     return _NATIVE_RNG
 
 
+_STEP_PARAMS = None
+
+
+@contextlib.contextmanager
+def recording_step_params(step_params):
+    """Inside the context (the CUDA-graph capture pass of training.GraphedCooperativeTrainer) every masking /
+    dropout call launches the device-parameter form of its kernel on the next row of `step_params`."""
+    global _STEP_PARAMS
+    prev, _STEP_PARAMS = _STEP_PARAMS, step_params
+    try:
+        yield step_params
+    finally:
+        _STEP_PARAMS = prev
+
+
+def step_params():
+    return _STEP_PARAMS
+
+
 # ------------------------------------------------------------------------------------------------
 def makeVariable(tensor, use_gpu=True, type='long', requires_grad=True):
     """Detached leaf of the requested type.  The build is CUDA-only: `use_gpu=False` keeps the
@@ -189,7 +208,7 @@ def _mask_latent_code(mode, latent_code, decoder_function, label, num_classes, p
         else:
             rng = _NATIVE_RNG
     masked, mask, _, _ = ops.saliency_mask_apply(gradient, code.detach(), mode, k, soft=if_soft, rand=rand, rng=rng,
-                                                 out_dtype=torch.float32)
+                                                 out_dtype=torch.float32, step_params=_STEP_PARAMS)
     mask_all = mask.view(N, C, 1, 1) if mode == ops.MODE_CHANNEL else mask.view(N, 1, H, W)
     if not if_detach:
         # graph stays attached to the caller's latent (model_util.py:246-247)
@@ -202,8 +221,15 @@ def _mask_latent_code(mode, latent_code, decoder_function, label, num_classes, p
     else:
         # the reference returns `code * mask_all`: a non-leaf hanging off the fp32 leaf `code`
         masked_latent_code = _MaskedCode.apply(code, masked, mask_all)
+    # model_util.py:251-254.  The decoder's parameter gradients are cleared IN PLACE (nn.Module.zero_grad as of the
+    # reference's pinned torch 1.9, set_to_none=False): freeing them here would leave a captured CUDA graph of the
+    # step zeroing / accumulating into gradient buffers that no longer exist, and would detach them from the
+    # data-parallel gradient bucket.  Callables without that signature get the reference's bare call.
     try:
-        decoder_function.zero_grad()
+        try:
+            decoder_function.zero_grad(set_to_none=False)
+        except TypeError:
+            decoder_function.zero_grad()
     except Exception:  # noqa: BLE001  (the reference swallows everything here)
         pass
     return masked_latent_code, mask_all

@@ -54,6 +54,60 @@ class NativeRNG:
         return o
 
 
+class StepParams:
+    """Per-step scalar draws kept in DEVICE memory so that a CUDA graph of the cooperative step can be replayed with
+    new values (include/ctl_b200.h: ctl_saliency_mask_apply_dyn / ctl_channel_dropout_dyn).  One row of three int64
+    per masking call of the step: {k, philox offset, global index of the first local sample}.
+
+    While `recording` (the capture pass) every masking call takes the next row, notes what it will need at replay
+    time and launches the *_dyn kernel on that row.  At replay the owner refills the rows on the host (`fill`) and
+    `upload()` enqueues ONE small pinned H2D copy in front of the graph launch; a ring of pinned buffers guarded by
+    events keeps a copy that has not executed yet from being overwritten by the next step's draws."""
+
+    ROWS, RING = 8, 4
+
+    def __init__(self, device):
+        self.dev = torch.zeros((self.ROWS, 3), dtype=torch.int64, device=device)
+        self.host = [torch.zeros((self.ROWS, 3), dtype=torch.int64).pin_memory() for _ in range(self.RING)]
+        self.events = [None] * self.RING
+        self.turn = 0
+        self.rows = []              # per row: {"kind": "mask"|"dropout", "n": int, "draws": bool}
+        self.recording = False
+        self._stage = self.host[0]
+
+    def take(self, kind, n, k, rng):
+        """Capture pass: claims the next row for a call that runs now with (k, rng state) and returns its device
+        view.  `rng` is the NativeRNG the call draws from, or None when it consumes no Philox offset."""
+        if len(self.rows) >= self.ROWS:
+            raise RuntimeError("more than %d masking calls in one captured step" % self.ROWS)
+        i = len(self.rows)
+        self.rows.append({"kind": kind, "n": int(n), "draws": rng is not None})
+        self.fill(i, k, rng)
+        if not torch.cuda.is_current_stream_capturing():
+            self.dev[i].copy_(self._stage[i], non_blocking=True)     # eager use: the launch below really runs
+        return self.dev[i]
+
+    def begin(self):
+        """Replay pass: picks the pinned staging buffer of this step (waits if its last copy is still pending)."""
+        ev = self.events[self.turn]
+        if ev is not None:
+            ev.synchronize()
+        self._stage = self.host[self.turn]
+
+    def fill(self, i, k, rng):
+        row = self._stage[i]
+        row[0] = int(k)
+        row[1] = rng.next_offset() if rng is not None else 0
+        row[2] = rng.first_sample if rng is not None else 0
+
+    def upload(self):
+        self.dev.copy_(self._stage, non_blocking=True)
+        ev = self.events[self.turn] or torch.cuda.Event()
+        ev.record()
+        self.events[self.turn] = ev
+        self.turn = (self.turn + 1) % self.RING
+
+
 def saliency_reduce(g, mode):
     """K1: fp32 [N,n] mean of g over space (channel mode) or channels (spatial mode)."""
     _need_cuda(g)
@@ -93,8 +147,10 @@ def topp_mask_apply(s, z, mode, k, soft=False, rand=None, rng=None, out_dtype=to
     return z_out, mask, thr
 
 
-def saliency_mask_apply(g, z, mode, k, soft=False, rand=None, rng=None, out_dtype=torch.float32, want_thr=False):
-    """K1+K2 fused entry point.  Returns (z_masked, mask[N,n], s[N,n], thr or None)."""
+def saliency_mask_apply(g, z, mode, k, soft=False, rand=None, rng=None, out_dtype=torch.float32, want_thr=False,
+                        step_params=None):
+    """K1+K2 fused entry point.  Returns (z_masked, mask[N,n], s[N,n], thr or None).
+    step_params: a recording StepParams -> the launch reads (k, offset, first_sample) from device memory."""
     _need_cuda(g, z, rand)
     g = g.contiguous()
     z = z.contiguous()
@@ -107,14 +163,25 @@ def saliency_mask_apply(g, z, mode, k, soft=False, rand=None, rng=None, out_dtyp
         if tuple(rand.shape) != (N, n) or rand.dtype != torch.float32:
             raise ValueError("rand must be float32 [%d,%d]" % (N, n))
     seed = offset = first = 0
-    if soft and rand is None:
-        if rng is None:
-            raise ValueError("soft masking needs either `rand` (torch-compatible mode) or `rng` (native mode)")
-        seed, offset, first = rng.seed, rng.next_offset(), rng.first_sample
+    native = soft and rand is None
+    if native and rng is None:
+        raise ValueError("soft masking needs either `rand` (torch-compatible mode) or `rng` (native mode)")
     s = torch.empty((N, n), device=z.device, dtype=torch.float32)
     z_out = torch.empty(z.shape, device=z.device, dtype=out_dtype)
     mask = torch.empty((N, n), device=z.device, dtype=torch.float32)
     thr = torch.empty((N,), device=z.device, dtype=torch.float32) if want_thr else None
+    if step_params is not None:
+        if not 0 <= int(k) < n:
+            raise IndexError("index {} is out of bounds for dimension 1 with size {}".format(int(k), n))
+        row = step_params.take("mask", n, k, rng if native else None)
+        with torch.cuda.device(z.device):
+            _lib.check(_lib.load().ctl_saliency_mask_apply_dyn(
+                g.data_ptr(), _dtype(g), z.data_ptr(), _dtype(z), N, C, HW, mode, int(bool(soft)), _ptr(rand),
+                rng.seed if native else 0, row.data_ptr(), s.data_ptr(), mask.data_ptr(), _ptr(thr), z_out.data_ptr(),
+                _DTYPES[out_dtype], _stream()))
+        return z_out, mask, s, thr
+    if native:
+        seed, offset, first = rng.seed, rng.next_offset(), rng.first_sample
     with torch.cuda.device(z.device):
         _lib.check(_lib.load().ctl_saliency_mask_apply(
             g.data_ptr(), _dtype(g), z.data_ptr(), _dtype(z), N, C, HW, mode, int(k), int(bool(soft)), _ptr(rand),
@@ -130,7 +197,7 @@ def dropout_scale(p, dtype=torch.float32):
     return float(np.float32(1.0) / np.float32(1.0 - p))
 
 
-def channel_dropout(z, p, keep=None, rng=None, want_mask=True, want_keep=False, out_dtype=None):
+def channel_dropout(z, p, keep=None, rng=None, want_mask=True, want_keep=False, out_dtype=None, step_params=None):
     """Random channel dropout + the reference's full-size `masked == z` mask.
     keep: float32 [N,C] of 0/1 (torch-compatible mode) or None with rng (native Philox mode)."""
     _need_cuda(z, keep)
@@ -140,15 +207,22 @@ def channel_dropout(z, p, keep=None, rng=None, want_mask=True, want_keep=False, 
     N, C, HW = _nchw(z)
     out_dtype = out_dtype or z.dtype
     seed = offset = first = 0
-    if keep is None:
-        if rng is None:
-            raise ValueError("channel_dropout needs either `keep` (torch-compatible mode) or `rng` (native mode)")
-        seed, offset, first = rng.seed, rng.next_offset(), rng.first_sample
-    else:
+    if keep is None and rng is None:
+        raise ValueError("channel_dropout needs either `keep` (torch-compatible mode) or `rng` (native mode)")
+    if keep is not None:
         keep = keep.reshape(N, C).to(torch.float32).contiguous()
     z_out = torch.empty(z.shape, device=z.device, dtype=out_dtype)
     mask = torch.empty(z.shape, device=z.device, dtype=torch.float32) if want_mask else None
     keep_out = torch.empty((N, C), device=z.device, dtype=torch.float32) if want_keep else None
+    if keep is None and step_params is not None:
+        row = step_params.take("dropout", C, 0, rng)
+        with torch.cuda.device(z.device):
+            _lib.check(_lib.load().ctl_channel_dropout_dyn(
+                z.data_ptr(), _dtype(z), N, C, HW, float(p), dropout_scale(p), rng.seed, row.data_ptr(),
+                z_out.data_ptr(), _DTYPES[out_dtype], _ptr(mask), _ptr(keep_out), _stream()))
+        return z_out, mask, keep_out
+    if keep is None:
+        seed, offset, first = rng.seed, rng.next_offset(), rng.first_sample
     with torch.cuda.device(z.device):
         _lib.check(_lib.load().ctl_channel_dropout(
             z.data_ptr(), _dtype(z), N, C, HW, float(p), dropout_scale(p), _ptr(keep), seed, offset, first,

@@ -38,7 +38,7 @@ class _ChannelDropout(torch.autograd.Function):
     @staticmethod
     def forward(ctx, latent, p, keep, rng):
         out, mask, keep_used = ops.channel_dropout(latent.detach(), p, keep=keep, rng=rng, want_mask=True,
-                                                   want_keep=True)
+                                                   want_keep=True, step_params=model_util.step_params())
         N, C = latent.shape[:2]
         noise = (keep_used * ops.dropout_scale(p)).view(N, C, 1, 1).to(latent.dtype)
         ctx.save_for_backward(noise)
@@ -315,7 +315,7 @@ class AdvancedTripletReconSegmentationModel(nn.Module):
     # ------------------------------------------------------------------ training passes
     def standard_training(self, clean_image_l, label_l, perturbed_image, separate_training=False,
                           compute_gt_recon=True, update_latent=True, disable_track_bn_stats=False):
-        zero = torch.tensor(0., device=clean_image_l.device)
+        zero = torch.zeros((), device=clean_image_l.device)     # a fill kernel: legal under stream capture
         (z_i, z_s), y_0 = self.fast_predict(perturbed_image, disable_track_bn_stats=disable_track_bn_stats)
         if update_latent:
             self.z_i, self.z_s = z_i, z_s
@@ -334,7 +334,7 @@ class AdvancedTripletReconSegmentationModel(nn.Module):
 
     def hard_example_training(self, perturbed_image, clean_image_l, perturbed_seg, label_l, separate_training=False,
                               use_gpu=True):
-        zero = torch.tensor(0., device=clean_image_l.device)
+        zero = torch.zeros((), device=clean_image_l.device)     # a fill kernel: legal under stream capture
         seg_loss, recon_loss, shape_loss, perturbed_p_recon_loss = zero, zero, zero, zero
         if perturbed_image is not None:
             seg_loss, recon_loss, _, shape_loss = self.standard_training(
@@ -404,9 +404,14 @@ class AdvancedTripletReconSegmentationModel(nn.Module):
         assert self.optimizers, 'please set optimizers first before fetching'
         return self.optimizers if model_name is None else self.optimizers[model_name]
 
-    def set_optimizers(self):
+    def set_optimizers(self, capturable=None):
+        """Five Adam optimizers, one per sub-network (advanced...model.py:774-785).  capturable=True keeps the step
+        counters on the device so `optimize_all_params` can be recorded into a CUDA graph (same update rule)."""
         assert self.model
-        self.optimizers = {name: optim.Adam(m.parameters(), lr=self.learning_rate, fused=True)
+        if capturable is not None:
+            self._capturable = bool(capturable)
+        self.optimizers = {name: optim.Adam(m.parameters(), lr=self.learning_rate, fused=True,
+                                            capturable=getattr(self, '_capturable', False))
                            for name, m in self.model.items()}
 
     def optimize_all_params(self):

@@ -25,7 +25,7 @@ import numpy as np
 import torch
 import torch.distributed as dist
 
-from . import model_util
+from . import _lib, model_util, ops
 
 LOSS_KEYS = ('loss/standard/total', 'loss/standard/seg', 'loss/standard/image', 'loss/standard/shape',
              'loss/standard/gt_shape', 'loss/hard/total', 'loss/hard/seg', 'loss/hard/image', 'loss/hard/shape')
@@ -135,6 +135,15 @@ class FlatGradBucket:
                 p.grad = view
             off += n
 
+    def attached(self):
+        """True when every parameter's .grad is still its view of the flat buffer."""
+        off = 0
+        for p in self.params:
+            if p.grad is None or p.grad.data_ptr() != self.flat.data_ptr() + off * self.flat.element_size():
+                return False
+            off += p.numel()
+        return True
+
     def all_reduce_mean(self, group=None):
         if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
             self.reattach()
@@ -188,5 +197,143 @@ class CooperativeTrainer:
         model_util.native_rng().first_sample = self.step_index * self.global_batch + self.lo
         out = cooperative_step(self.solver, clean_local, label_local, self.image_cfg, self.seg_cfg,
                                noise=noise_local, grad_sync=lambda: self.bucket.all_reduce_mean(self.group))
+        self.step_index += 1
+        return out
+
+
+def draw_host_params(cfg):
+    """The host draws one `perturb_latent_code` call makes, in the reference's order: python `random.shuffle` for a
+    'random' mask type (advanced...model.py:325-328), then numpy's global generator for a random percentile
+    (model_util.py:224-225, :285-286; dropout uses the threshold as is).  Returns (perturb_type, percentile)."""
+    kind = cfg["mask_type"]
+    if kind == 'random':
+        candidates = ['dropout', 'spatial', 'channel']
+        _pyrandom.shuffle(candidates)
+        kind = candidates[0]
+    p = cfg["max_threshold"]
+    if kind != 'dropout' and cfg["random_threshold"]:
+        p = np.random.rand() * p
+    return kind, p
+
+
+class _CapturedStep:
+    """The two CUDA graphs of one (image mask type, shape mask type) combination and what their replay needs."""
+
+    def __init__(self, device):
+        self.forward_backward = torch.cuda.CUDAGraph()
+        self.optimizers = torch.cuda.CUDAGraph()
+        self.params = ops.StepParams(device)
+        self.out = None
+        self.kernels = 0            # kernels of libctl_b200.so recorded in the two graphs
+
+
+class GraphedCooperativeTrainer(CooperativeTrainer):
+    """CooperativeTrainer whose step is replayed from CUDA graphs (the step is ~2000 short launches: issued one by
+    one from Python it is host-bound on a B200).
+
+    * graph 1 = zero grads + clean pass + hard-example generation + corrupted passes + backward; the NCCL all-reduce
+      of the flat gradient bucket stays an ordinary call between the graphs; graph 2 = the five Adam steps
+    * inputs are copied into static buffers (so `step` takes host-pinned or device tensors alike); the returned losses
+      and perturbed examples are static tensors that the NEXT step overwrites
+    * the per-step host draws (mask type, percentile -> k) are made here exactly as the eager path makes them
+      (`draw_host_params`), uploaded as device-resident step parameters (ops.StepParams) and read by the *_dyn
+      kernels; one pair of graphs is captured lazily per (image mask type, shape mask type) combination, all in one
+      memory pool
+    * the first `eager_steps` calls run eagerly on the capture stream (library / allocator warm-up)
+    """
+
+    def __init__(self, solver, global_batch, seed=0, image_cfg=None, seg_cfg=None, group=None, eager_steps=3):
+        solver.set_optimizers(capturable=True)      # fresh optimizers: device-side step counters
+        super().__init__(solver, global_batch, seed, image_cfg, seg_cfg, group)
+        self.eager_steps = eager_steps
+        self.stream = torch.cuda.Stream()
+        self.pool = torch.cuda.graph_pool_handle()
+        self.captured = {}
+        self.static = None
+
+    # -------------------------------------------------------------------------------------------- helpers
+    def _stage_inputs(self, clean, label, noise):
+        if self.static is None:
+            dev = next(self.solver.parameters()).device
+            self.static = {"clean": torch.empty(clean.shape, device=dev, dtype=torch.float32),
+                           "label": torch.empty(label.shape, device=dev, dtype=torch.int64),
+                           "noise": None}
+        st = self.static
+        if tuple(clean.shape) != tuple(st["clean"].shape):
+            raise ValueError("a graphed trainer replays ONE batch shape: got %s, captured %s"
+                             % (tuple(clean.shape), tuple(st["clean"].shape)))
+        st["clean"].copy_(clean, non_blocking=True)
+        st["label"].copy_(label, non_blocking=True)
+        if noise is not None:
+            if st["noise"] is None:
+                st["noise"] = torch.empty_like(st["clean"])
+            st["noise"].copy_(noise, non_blocking=True)
+        return st["clean"], st["label"], (st["noise"] if noise is not None else None)
+
+    def _eager(self, clean, label, noise):
+        return cooperative_step(self.solver, clean, label, self.image_cfg, self.seg_cfg, noise=noise,
+                                grad_sync=lambda: self.bucket.all_reduce_mean(self.group))
+
+    def _capture(self, key, clean, label, noise):
+        from . import fastpath
+        cs = _CapturedStep(clean.device)
+        self.bucket.reattach()                      # every .grad is a view of the flat bucket before recording
+        fastpath.weights_changed()                  # every packed weight is rebuilt INSIDE the graph
+        n0 = _lib.LAUNCHES["count"]
+        with model_util.recording_step_params(cs.params):
+            with torch.cuda.graph(cs.forward_backward, pool=self.pool, stream=self.stream):
+                cs.out = cooperative_step(self.solver, clean, label, self.image_cfg, self.seg_cfg, noise=noise,
+                                          grad_sync=None, optimize=False)
+        with torch.cuda.graph(cs.optimizers, pool=self.pool, stream=self.stream):
+            self.solver.optimize_all_params()
+        if not self.bucket.attached():
+            raise RuntimeError("a parameter gradient left the flat bucket during capture: the recorded step would "
+                               "update buffers the optimizers do not read")
+        cs.kernels = _lib.LAUNCHES["count"] - n0
+        _lib.LAUNCHES["count"] = n0                 # nothing ran yet: replays add the count
+        self.captured[key] = cs
+        return cs
+
+    # -------------------------------------------------------------------------------------------- the step
+    def step(self, clean_local, label_local, noise_local=None):
+        from . import fastpath
+        rng = model_util.native_rng()
+        rng.first_sample = self.step_index * self.global_batch + self.lo
+        cur = torch.cuda.current_stream()
+        self.stream.wait_stream(cur)
+        with torch.cuda.stream(self.stream):
+            clean, label, noise = self._stage_inputs(clean_local, label_local, noise_local)
+            if self.step_index < self.eager_steps:
+                out = self._eager(clean, label, noise)
+            else:
+                host_state = (_pyrandom.getstate(), np.random.get_state())
+                draws = [draw_host_params(self.image_cfg), draw_host_params(self.seg_cfg)]
+                key = (draws[0][0], draws[1][0], noise is not None)
+                cs = self.captured.get(key)
+                if cs is None:
+                    # the capture pass runs the ordinary host code, which makes the same draws again
+                    _pyrandom.setstate(host_state[0])
+                    np.random.set_state(host_state[1])
+                    offset0 = rng.offset
+                    cs = self._capture(key, clean, label, noise)
+                    rng.offset = offset0
+                cs.params.begin()
+                rows = iter(enumerate(cs.params.rows))
+                for kind, p in draws:
+                    i, row = next(rows)
+                    if row["kind"] != ("dropout" if kind == "dropout" else "mask"):
+                        raise RuntimeError("captured step does not match this step's draws")
+                    k = int(row["n"] * p) if kind != "dropout" else 0
+                    if k >= row["n"] or k < -row["n"]:
+                        raise IndexError("index {} is out of bounds for dimension 1 with size {}".format(k, row["n"]))
+                    cs.params.fill(i, k % row["n"] if kind != "dropout" else 0, rng if row["draws"] else None)
+                cs.params.upload()
+                cs.forward_backward.replay()
+                self.bucket.all_reduce_mean(self.group)
+                cs.optimizers.replay()
+                _lib.LAUNCHES["count"] += cs.kernels
+                fastpath.weights_changed()          # the graph stepped the weights behind autograd's back
+                out = cs.out
+        cur.wait_stream(self.stream)
         self.step_index += 1
         return out

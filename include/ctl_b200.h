@@ -96,6 +96,24 @@ int ctl_channel_dropout(const void* z, int z_dtype, int64_t N, int64_t C, int64_
                         int64_t first_sample, void* z_out, int out_dtype, float* mask_out,
                         float* keep_out, void* stream);
 
+/* ---------------------------------------------------------------------------------------------
+ * CUDA-graph replay forms of the two entry points above.  A captured launch freezes its by-value
+ * arguments, but the reference draws a new percentile (hence k) and new random numbers every step
+ *   medseg/models/model_util.py:224-231 (np.random.rand() * percentile -> k), :238-241 (rand_like)
+ * so these variants read the per-step values from DEVICE memory at run time:
+ *   step_params: int64 [3] = {k, philox offset, global index of this rank's first sample}
+ * (k is ignored by the dropout form).  The host validates k < n before it uploads the values -- the
+ * reference's IndexError is raised there -- and the kernel clamps k into [0, n-1].
+ */
+int ctl_saliency_mask_apply_dyn(const void* g, int g_dtype, const void* z, int z_dtype, int64_t N,
+                                int64_t C, int64_t HW, int mode, int soft, const float* rand,
+                                uint64_t seed, const int64_t* step_params, float* s_scratch,
+                                float* mask_out, float* thr_out, void* z_out, int out_dtype,
+                                void* stream);
+int ctl_channel_dropout_dyn(const void* z, int z_dtype, int64_t N, int64_t C, int64_t HW, float p,
+                            float scale, uint64_t seed, const int64_t* step_params, void* z_out,
+                            int out_dtype, float* mask_out, float* keep_out, void* stream);
+
 /* Philox4x32-10 uniform draw, exposed for parity tests of the native RNG: out[i] = u(first_index+i). */
 int ctl_philox_uniform(uint64_t seed, uint64_t offset, uint64_t first_index, int64_t count,
                        float* out, void* stream);

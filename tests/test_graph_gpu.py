@@ -1,0 +1,124 @@
+"""GPU: the CUDA-graph replay of the cooperative step (training.GraphedCooperativeTrainer) against the same step issued
+launch by launch (training.CooperativeTrainer), same seeds, same weights, same inputs.
+
+What must hold:
+  * the host generators (python `random`, numpy) are consumed identically -- their final states are EQUAL, so the
+    mask types and percentiles of every step are the ones the eager path (hence the reference loop) draws
+  * k, the Philox offset and the first-sample index reach the kernels through device memory: the perturbed examples
+    of a replayed step equal the eager ones up to the arithmetic noise below
+  * losses agree step by step.  Not bit-exact: the weight-gradient kernels accumulate with fp32 atomics (order varies
+    run to run) and activations are bf16, so two EAGER runs already differ by ~1e-3 relative after a few steps;
+    bar: 2e-2 relative on every logged loss over 8 steps.
+"""
+import random
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import weights
+
+pytestmark = pytest.mark.gpu
+
+RANDOM_CFG = ({"loss_name": "mse", "mask_type": "random", "max_threshold": 0.5, "random_threshold": True,
+               "if_soft": True},
+              {"loss_name": "ce", "mask_type": "random", "max_threshold": 0.5, "random_threshold": True,
+               "if_soft": True})
+FIXED_CFG = ({"loss_name": "mse", "mask_type": "channel", "max_threshold": 0.5, "random_threshold": True,
+              "if_soft": True},
+             {"loss_name": "ce", "mask_type": "spatial", "max_threshold": 0.5, "random_threshold": True,
+              "if_soft": True})
+
+
+def _run(pkg, trainer_cls, cfgs, steps, **kw):
+    torch.manual_seed(0)
+    solver = pkg.AdvancedTripletReconSegmentationModel('FCN_16_standard', num_classes=4, learning_rate=1e-3)
+    for name, m in solver.model.items():
+        m.load_state_dict(weights.synthetic_state_dict(m, 5, prefix=name + "."))
+    solver.set_optimizers(capturable=True)
+    trainer = trainer_cls(solver, 4, seed=3, image_cfg=cfgs[0], seg_cfg=cfgs[1], **kw)
+    img, lab, noise = weights.synthetic_batch(4, 64, 64, seed=2)
+    img, lab, noise = img.cuda(), lab.cuda(), noise.cuda()
+    losses, pert = [], []
+    for _ in range(steps):
+        out = trainer.step(img, lab, noise)
+        losses.append({k: float(v) for k, v in out.items() if k.startswith('loss')})
+        pert.append((out['perturbed_image'].float().clone(), out['perturbed_seg'].float().clone()))
+    torch.cuda.synchronize()
+    host_state = (random.getstate(), np.random.get_state())
+    return trainer, losses, pert, host_state
+
+
+@pytest.fixture()
+def pkg():
+    import cooperative_training_and_latent_space_data_augmentation_b200 as pkg
+    pkg.conv_blocks.set_precision("kernel")
+    yield pkg
+    pkg.conv_blocks.set_precision("fp32")
+    pkg.set_rng_mode("torch")
+
+
+@pytest.mark.parametrize("cfgs", [FIXED_CFG, RANDOM_CFG], ids=["channel+spatial", "random"])
+def test_graph_replay_matches_eager_steps(pkg, cfgs):
+    steps = 8
+    _, want, want_p, want_state = _run(pkg, pkg.CooperativeTrainer, cfgs, steps)
+    n0 = pkg._lib.LAUNCHES["count"]
+    trainer, got, got_p, got_state = _run(pkg, pkg.GraphedCooperativeTrainer, cfgs, steps, eager_steps=2)
+    assert pkg._lib.LAUNCHES["count"] - n0 > 1000 * steps // 2, "replays did not account their kernels"
+    assert len(trainer.captured) >= 1
+    if cfgs is RANDOM_CFG:
+        assert len(trainer.captured) >= 2, "the random mask type should have met several type combinations"
+    # host generators consumed identically
+    assert got_state[0] == want_state[0]
+    assert all(np.array_equal(a, b) for a, b in zip(got_state[1], want_state[1]))
+    for step, (g, w) in enumerate(zip(got, want)):
+        for key in w:
+            assert np.isfinite(g[key])
+            assert abs(g[key] - w[key]) <= 2e-2 * max(1.0, abs(w[key])), (step, key, g[key], w[key])
+    # the perturbed examples of the replayed steps: same masks (k, draws) -> same images up to the run-to-run noise of
+    # the weights (measured 5e-2 after 3 steps at lr 1e-3; a wrong k or draw gives O(1)).  The bit-exact check of the
+    # device-resident parameters is test_step_params_reach_the_kernels.
+    for step in range(2, steps):
+        for a, b in zip(got_p[step], want_p[step]):
+            rel = float((a - b).norm() / b.norm().clamp_min(1e-6))
+            assert rel < 0.15, (step, rel)
+
+
+def test_step_params_reach_the_kernels(pkg):
+    """ctl_saliency_mask_apply_dyn / ctl_channel_dropout_dyn read (k, offset, first sample) from device memory:
+    bit-exact against the by-value entry points for several parameter sets on ONE recorded row."""
+    ops = pkg.ops
+    gen = torch.Generator(device="cuda").manual_seed(1)
+    z = torch.relu(torch.randn(6, 32, 7, 9, device="cuda", generator=gen))
+    g = 1e-5 * torch.randn(6, 32, 7, 9, device="cuda", generator=gen)
+    for mode, n in ((ops.MODE_CHANNEL, 32), (ops.MODE_SPATIAL, 63)):
+        sp = ops.StepParams("cuda")
+        rng = ops.NativeRNG(seed=9, first_sample=12)
+        ops.saliency_mask_apply(g, z, mode, 3, soft=True, rng=rng, step_params=sp)
+        for k, offset, first in ((3, 0, 12), (0, 5, 0), (n - 1, 2, 40)):
+            r2 = ops.NativeRNG(seed=9, first_sample=first)
+            r2.offset = offset
+            want = ops.saliency_mask_apply(g, z, mode, k, soft=True, rng=r2)
+            r3 = ops.NativeRNG(seed=9, first_sample=first)
+            r3.offset = offset
+            sp.begin()
+            sp.fill(0, k, r3)
+            sp.upload()
+            # same recorded launch, new device-resident values
+            row = sp.dev[0]
+            s = torch.empty_like(want[2]); zt = torch.empty_like(want[0]); mask = torch.empty_like(want[1])
+            N, C, H, W = z.shape
+            pkg._lib.check(pkg._lib.load().ctl_saliency_mask_apply_dyn(
+                g.data_ptr(), 0, z.data_ptr(), 0, N, C, H * W, mode, 1, 0, 9, row.data_ptr(), s.data_ptr(),
+                mask.data_ptr(), 0, zt.data_ptr(), 0, torch.cuda.current_stream().cuda_stream))
+            assert torch.equal(zt, want[0]) and torch.equal(mask, want[1]) and torch.equal(s, want[2])
+    sp = ops.StepParams("cuda")
+    rng = ops.NativeRNG(seed=4, first_sample=3)
+    rng.offset = 7
+    got = ops.channel_dropout(z, 0.5, rng=rng, want_keep=True, step_params=sp)
+    r2 = ops.NativeRNG(seed=4, first_sample=3)
+    r2.offset = 7
+    want = ops.channel_dropout(z, 0.5, rng=r2, want_keep=True)
+    assert all(torch.equal(a, b) for a, b in zip(got, want))
+    with pytest.raises(IndexError):
+        ops.saliency_mask_apply(g, z, ops.MODE_CHANNEL, 32, soft=False, step_params=ops.StepParams("cuda"))
