@@ -55,6 +55,7 @@ struct ConvParams {
   int subsample;                      // 1: Ho=H, Wo=W; 2: keep even (y,x) -> Ho=H/2, Wo=W/2 (3x3 stride-2 pad-1)
   int up2x;                           // 1: ConvTranspose2d(k=2,s=2) scatter: GEMM column n = (dy*2+dx)*Cout/4 + co
   double* stats;                      // [2][Cout] sum / sum of squares of the stored outputs, accumulated into (or nullptr)
+  int diag;                           // profiling only (env CTL_DIAG_SKIP): 1 no MMA, 2 no TMA loads, 4 no epilogue memory traffic, 8 no epilogue
 };
 
 __device__ __forceinline__ float apply_act(float v, int act) {
@@ -140,7 +141,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap, const ConvParams p) {
 
   if (warp == 0) {
     // ================================================================= TMA producer
-    if (lane == 0) {
+    // elect.sync (not `lane == 0`): ptxas then knows ONE thread runs the block, keeps descriptors / addresses in
+    // uniform registers and issues UTCHMMA / UTMALDG back to back instead of wrapping each in a divergence loop
+    if (elect_one()) {
       mbar_arrive_expect_tx(w_full, Cfg::kWBytes);
       bulk_load_1d(sW, reinterpret_cast<const uint8_t*>(p.w_packed) + (size_t)n_tile * Cfg::kWBytes, Cfg::kWBytes,
                    w_full);
@@ -152,14 +155,18 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap, const ConvParams p) {
         const int ty = rem / p.tiles_x, tx = rem - ty * p.tiles_x;
         const int y0 = ty * kTileH - Cfg::kPad, x0 = tx * (8 * MT) - Cfg::kPad;
         mbar_wait(&empty[stage], phase ^ 1);
-        mbar_arrive_expect_tx(&full[stage], Cfg::kStageTxBytes);
-        tma_load_4d(sA + stage * kStageStride, &tmap, &full[stage], x0 * 2, y0, 0, img);
+        if (p.diag & 2) {
+          mbar_arrive(&full[stage]);
+        } else {
+          mbar_arrive_expect_tx(&full[stage], Cfg::kStageTxBytes);
+          tma_load_4d(sA + stage * kStageStride, &tmap, &full[stage], x0 * 2, y0, 0, img);
+        }
         if (++stage == STAGES) { stage = 0; phase ^= 1; }
       }
     }
   } else if (warp == 1) {
     // ================================================================= MMA issuer
-    if (lane == 0) {
+    if (elect_one()) {
       constexpr uint32_t idesc = umma_idesc_bf16_f32(128, NT);
       constexpr uint32_t kLboA = Cfg::kChunkStride, kSboA = Cfg::kHaloW * 16;
       constexpr uint32_t kLboB = NT * 16, kSboB = 128;
@@ -172,6 +179,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap, const ConvParams p) {
         mbar_wait(&full[stage], phase);
         tc_fence_after();
         const uint32_t a_base = smem_u32(sA + stage * kStageStride);
+        if (!(p.diag & 1)) {
 #pragma unroll
         for (int mt = 0; mt < MT; ++mt) {
           const uint32_t d_tmem = tmem_base + (uint32_t)((acc * MT + mt) * NT);
@@ -187,6 +195,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap, const ConvParams p) {
               umma_bf16(d_tmem, adesc, bdesc, idesc, (tap | kk) != 0 ? 1u : 0u);
             }
           }
+        }
         }
         umma_commit(&empty[stage]);       // smem stage reusable once these MMAs have read it
         umma_commit(&acc_full[acc]);      // accumulator complete
@@ -220,12 +229,13 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap, const ConvParams p) {
       mbar_wait(&acc_full[acc], acc_phase);
       tc_fence_after();
 #pragma unroll 1
-      for (int item = half; item < kItems; item += 2) {
+      for (int item = (p.diag & 8) ? kItems : half; item < kItems; item += 2) {
         const int mt = item / kChunks, c0 = (item - mt * kChunks) * 16;
         const int y = ty * kTileH + py, x = tx * (8 * MT) + mt * 8 + px;
         bool valid = y < p.H && x < p.W;
         int yo = y, xo = x;
         if (p.subsample == 2) { valid = valid && !((y | x) & 1); yo = y >> 1; xo = x >> 1; }
+        if (p.diag & 4) valid = false;
         uint32_t v[16];
         tmem_ld_32x32b_x16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)((acc * MT + mt) * NT + c0), v);
         // output offsets of the two 8-channel planes of this chunk (and the residual, requested before the TMEM wait)
@@ -369,6 +379,7 @@ template <int CIN, int NT, int TAPS, int MT, int STAGES>
 int launch_conv(const void* x, const ConvParams& p0, cudaStream_t st) {
   using Cfg = ConvCfg<CIN, NT, TAPS, MT, STAGES>;
   ConvParams p = p0;
+  p.diag = diag_flags();
   p.tiles_x = (int)ceil_div(p.W, 8 * MT);
   p.tiles_y = (int)ceil_div(p.H, kTileH);
   p.num_tiles = (int64_t)p.N * p.tiles_x * p.tiles_y;

@@ -12,6 +12,7 @@ namespace ctl {
 void set_error(const char* fmt, ...);
 int cuda_fail(cudaError_t e, const char* what);   // records the message, returns CTL_ERR_CUDA
 int sm_count();                                   // cached per device; <0 on error
+int diag_flags();                                 // env CTL_DIAG_SKIP (profiling by elimination; 0 in normal use)
 
 #define CTL_CUDA_OK(expr, what)                         \
   do {                                                  \

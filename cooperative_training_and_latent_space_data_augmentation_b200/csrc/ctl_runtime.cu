@@ -1,6 +1,7 @@
 // Library-wide plumbing of the C ABI: version, thread-local error string, device properties.
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 
 #include "ctl_common.cuh"
 
@@ -33,6 +34,13 @@ int sm_count() {
   if (e != cudaSuccess) { cuda_fail(e, "cudaDeviceGetAttribute(MultiProcessorCount)"); return -1; }
   if (dev >= 0 && dev < 64) cache[dev] = sms;
   return sms;
+}
+
+// Profiling by elimination (tools/diag_conv.py): stages of the tcgen05 kernels can be switched off to see which one
+// bounds the pipeline.  Results are garbage with any bit set; never set outside the diagnostic tool.
+int diag_flags() {
+  const char* e = getenv("CTL_DIAG_SKIP");
+  return e ? atoi(e) : 0;
 }
 }  // namespace ctl
 

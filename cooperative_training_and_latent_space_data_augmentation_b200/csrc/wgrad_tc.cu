@@ -41,6 +41,7 @@ struct WgradParams {
   int64_t num_tiles;
   float* dW;                 // fp32, accumulated into: element (tap, ci, co) at tap*s_tap + ci*s_ci + co*s_co
   int64_t s_co, s_ci, s_tap;
+  int diag;                  // profiling only (env CTL_DIAG_SKIP): 1 no MMA, 2 no TMA loads
 };
 
 template <int CIN, int NT, int TAPS, int STAGES>
@@ -121,7 +122,8 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constan
 
   if (warp == 0) {
     // ================================================================= TMA producer
-    if (lane == 0) {
+    // elect.sync (not `lane == 0`): one provably-uniform thread, no per-instruction divergence loops around UTCHMMA
+    if (elect_one()) {
       int stage = 0;
       uint32_t phase = 0;
       for (int64_t t = blockIdx.x; t < p.num_tiles; t += gridDim.x) {
@@ -131,15 +133,19 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constan
         const int y0 = ty * kWgTH, x0 = tx * kWgTW;
         uint8_t* sx = smem + stage * Cfg::kStage;
         mbar_wait(&empty[stage], phase ^ 1);
-        mbar_arrive_expect_tx(&full[stage], Cfg::kXStage + Cfg::kDStage);
-        tma_load_4d(sx, &tmap_x, &full[stage], (x0 - Cfg::kPad) * 2, 0, y0 - Cfg::kPad, img);
-        tma_load_4d(sx + Cfg::kXStage, &tmap_dy, &full[stage], x0 * 2, y0, n_tile * (NT / 8), img);
+        if (p.diag & 2) {
+          mbar_arrive(&full[stage]);
+        } else {
+          mbar_arrive_expect_tx(&full[stage], Cfg::kXStage + Cfg::kDStage);
+          tma_load_4d(sx, &tmap_x, &full[stage], (x0 - Cfg::kPad) * 2, 0, y0 - Cfg::kPad, img);
+          tma_load_4d(sx + Cfg::kXStage, &tmap_dy, &full[stage], x0 * 2, y0, n_tile * (NT / 8), img);
+        }
         if (++stage == STAGES) { stage = 0; phase ^= 1; }
       }
     }
   } else if (warp == 1) {
     // ================================================================= MMA issuer
-    if (lane == 0 && has_work) {
+    if (has_work && elect_one()) {
       int stage = 0;
       uint32_t phase = 0;
       uint32_t accumulate = 0;
@@ -149,7 +155,7 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constan
         const uint32_t xs = smem_u32(smem + stage * Cfg::kStage);
         const uint32_t ds = xs + Cfg::kXStage;
 #pragma unroll 1
-        for (int y = 0; y < kWgTH; ++y) {
+        for (int y = (p.diag & 1) ? kWgTH : 0; y < kWgTH; ++y) {
 #pragma unroll
           for (int xc = 0; xc < kWgTW; xc += 16) {
             const uint64_t bdesc = umma_smem_desc(ds + (uint32_t)((y * kWgTW + xc) * 16), 128u, Cfg::kDPlane);
@@ -274,6 +280,7 @@ template <int CIN, int NT, int TAPS, int STAGES>
 int launch_wgrad(const void* x, const void* dy, const WgradParams& p0, cudaStream_t st) {
   using Cfg = WgCfg<CIN, NT, TAPS, STAGES>;
   WgradParams p = p0;
+  p.diag = diag_flags();
   p.tiles_x = (int)ceil_div(p.W, kWgTW);
   p.tiles_y = (int)ceil_div(p.H, kWgTH);
   p.num_tiles = (int64_t)p.N * p.tiles_x * p.tiles_y;
