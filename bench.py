@@ -212,10 +212,17 @@ def masking_microbench(pkg, peaks, iters=20):
     mean_t, _ = timed(lambda: pkg.ops.channel_dropout(z, 0.5, rng=rng, want_mask=True), iters)
     out["dropout_p50_with_quirk_mask"] = {"us": mean_t * 1e6, "GBps": 12.0 * numel / mean_t / 1e9}
     head = out["channel_p30"]
+    traffic = None          # dram bytes per call from the committed ncu --set full capture (profiles/, not a live value)
+    try:
+        with open(os.path.join(ROOT, "profiles", "r1_masking_dram_traffic.json")) as f:
+            traffic = float(json.load(f)["traffic_bytes_per_call"])
+    except (OSError, KeyError, ValueError):
+        pass
     roofline = {"kernel": "ctl_saliency_mask_apply (K1 saliency_channel + K2 topp_mask_apply), [512,64,28,28] fp32, "
                           "channel mode, p=0.3, soft, native Philox",
                 "bound": "hbm", "achieved": head["GBps"], "peak": peaks["hbm_gbs"], "unit": "GB/s",
-                "frac": head["GBps"] / peaks["hbm_gbs"], "traffic": None,
+                "frac": head["GBps"] / peaks["hbm_gbs"], "traffic": traffic,
+                "traffic_source": "profiles/r1_masking_dram_traffic.json (ncu dram__bytes_read.sum + dram__bytes_write.sum)",
                 "algorithmic_bytes_per_launch": head["algo_bytes"], "peak_source": peaks["source"] + " (burst copy)",
                 "avg_launch_us": head["us"]}
     return roofline, out

@@ -95,6 +95,178 @@ struct ConvCfg {
   static_assert(kHaloW * 2 <= 256 && kHaloH <= 256 && CIN / 8 <= 256, "TMA box dimensions (8-byte elements)");
 };
 
+// Epilogue of one warp (warps 4-11; q = warp % 4 is the TMEM sub-partition it may read, half = (warp - 4) / 4).  The
+// (M tile, 16-column chunk) items of a tile alternate between the two halves; a warp's items of one tile are handled
+// as a batch: every residual pixel of the tile is requested BEFORE the accumulator wait (the addresses do not depend on
+// it), the TMEM loads of two items are issued back to back behind one tcgen05.wait::ld, and the accumulator stage is
+// handed back to the MMA issuer as soon as the last load has landed in registers -- before the arithmetic and stores.
+template <int CIN, int NT, int TAPS, int MT, int STAGES, bool RES, bool STATS>
+__device__ __forceinline__ void conv_epilogue(const ConvParams& p, const uint32_t tmem_base, const float* sVec,
+                                              uint64_t* acc_full, uint64_t* acc_empty, const int n0) {
+  using Cfg = ConvCfg<CIN, NT, TAPS, MT, STAGES>;
+  constexpr int kAccStages = Cfg::kAcc;
+  constexpr int kChunks = NT / 16;
+  constexpr int kItems = MT * kChunks;
+  constexpr int kPer = (kItems + 1) / 2;          // items of one warp per tile: half, half + 2, ...
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int q = warp & 3;
+  const int half = (warp - 4) >> 2;
+  const int m = q * 32 + lane;                    // accumulator row = pixel within the 16x8 M tile
+  const int py = m >> 3, px = m & 7;
+  const int Ho = p.H / p.subsample, Wo = p.W / p.subsample;
+  const int64_t plane = (int64_t)Ho * Wo * 8;     // elements per 8-channel plane of the output
+  const int act = p.act;
+  const int tiles_per_img = p.tiles_x * p.tiles_y;
+  const int num_tiles = (int)p.num_tiles;         // < 2^31 (checked on the host)
+  const int first_item = (p.diag & 8) ? kItems : half;
+  // train-mode BatchNorm statistics of the stored (bf16-rounded) outputs: every thread owns one 16-column chunk
+  float st_s[STATS ? 16 : 1], st_q[STATS ? 16 : 1];
+#pragma unroll
+  for (int i = 0; i < (STATS ? 16 : 1); ++i) { st_s[i] = 0.0f; st_q[i] = 0.0f; }
+
+  int acc = 0;
+  uint32_t acc_phase = 0;
+  for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
+    const int img = t / tiles_per_img;
+    const int rem = t - img * tiles_per_img;
+    const int ty = rem / p.tiles_x, tx = rem - ty * p.tiles_x;
+    const int y = ty * kTileH + py;
+    // element offset of plane h8 of item u (the residual shares the output's geometry)
+    auto offset_of = [&](int u, int h8, bool& valid) -> int64_t {
+      const int item = first_item + 2 * u;
+      const int mt = item / kChunks, c0 = (item - mt * kChunks) * 16;
+      const int x = tx * (8 * MT) + mt * 8 + px;
+      valid = y < p.H && x < p.W && !(p.diag & 4);
+      const int n = n0 + c0 + 8 * h8;              // GEMM column of this plane's first channel
+      if (p.up2x) {
+        const int cq = p.Cout >> 2, qd = n / cq, co = n - qd * cq;       // n = (dy*2+dx)*Cout/4 + co
+        const int y2 = 2 * y + (qd >> 1), x2 = 2 * x + (qd & 1);
+        return ((int64_t)img * (cq >> 3) + (co >> 3)) * (plane * 4) + ((int64_t)y2 * (2 * Wo) + x2) * 8;
+      }
+      int yo = y, xo = x;
+      if (p.subsample == 2) { valid = valid && !((y | x) & 1); yo = y >> 1; xo = x >> 1; }
+      return ((int64_t)img * (p.Cout >> 3) + (n >> 3)) * plane + ((int64_t)yo * Wo + xo) * 8;
+    };
+
+    uint4 rr[RES ? kPer : 1][2];
+    if (RES) {
+#pragma unroll
+      for (int u = 0; u < kPer; ++u) {
+#pragma unroll
+        for (int h8 = 0; h8 < 2; ++h8) {
+          rr[u][h8] = make_uint4(0, 0, 0, 0);
+          bool valid;
+          const int64_t off = offset_of(u, h8, valid);
+          if (first_item + 2 * u < kItems && valid) rr[u][h8] = __ldg(reinterpret_cast<const uint4*>(p.res + off));
+        }
+      }
+    }
+
+    mbar_wait(&acc_full[acc], acc_phase);
+    tc_fence_after();
+#pragma unroll
+    for (int u0 = 0; u0 < kPer; u0 += 2) {
+      uint32_t v[2][16];
+#pragma unroll
+      for (int b = 0; b < 2; ++b) {
+        const int item = first_item + 2 * (u0 + b);                       // warp-uniform
+        if (u0 + b < kPer && item < kItems) {
+          const int mt = item / kChunks, c0 = (item - mt * kChunks) * 16;
+          tmem_ld_32x32b_x16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)((acc * MT + mt) * NT + c0), v[b]);
+        }
+      }
+      tmem_ld_wait();
+      if (u0 + 2 >= kPer) {            // the tile's accumulator is in registers: release the TMEM stage now
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&acc_empty[acc]);
+      }
+#pragma unroll
+      for (int b = 0; b < 2; ++b) {
+        const int u = u0 + b;
+        const int item = first_item + 2 * u;
+        if (u < kPer && item < kItems) {
+          const int c0 = (item % kChunks) * 16;
+          bool valid;
+          int64_t off[2];
+          off[0] = offset_of(u, 0, valid);
+          off[1] = offset_of(u, 1, valid);
+          if (valid) {
+            float f[16];
+#pragma unroll
+            for (int i4 = 0; i4 < 4; ++i4) {
+              const float4 sc = *reinterpret_cast<const float4*>(sVec + c0 + 4 * i4);
+              const float4 sh = *reinterpret_cast<const float4*>(sVec + NT + c0 + 4 * i4);
+              f[4 * i4] = fmaf(__uint_as_float(v[b][4 * i4]), sc.x, sh.x);
+              f[4 * i4 + 1] = fmaf(__uint_as_float(v[b][4 * i4 + 1]), sc.y, sh.y);
+              f[4 * i4 + 2] = fmaf(__uint_as_float(v[b][4 * i4 + 2]), sc.z, sh.z);
+              f[4 * i4 + 3] = fmaf(__uint_as_float(v[b][4 * i4 + 3]), sc.w, sh.w);
+            }
+            if (RES) {
+#pragma unroll
+              for (int h8 = 0; h8 < 2; ++h8) {
+                const uint4 r4 = rr[RES ? u : 0][h8];
+                const uint32_t rw[4] = {r4.x, r4.y, r4.z, r4.w};
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                  const int c = 8 * h8 + 2 * i;
+                  f[c] += fmaf(__uint_as_float(rw[i] << 16), sVec[2 * NT + c0 + c], sVec[3 * NT + c0 + c]);
+                  f[c + 1] += fmaf(__uint_as_float(rw[i] & 0xffff0000u), sVec[2 * NT + c0 + c + 1], sVec[3 * NT + c0 + c + 1]);
+                }
+              }
+            }
+            if (act == CTL_ACT_LRELU) {
+#pragma unroll
+              for (int i = 0; i < 16; ++i) f[i] = fmaxf(f[i], 0.2f * f[i]);
+            } else if (act == CTL_ACT_RELU) {
+#pragma unroll
+              for (int i = 0; i < 16; ++i) f[i] = fmaxf(f[i], 0.0f);
+            } else if (act == CTL_ACT_SIGMOID) {
+#pragma unroll
+              for (int i = 0; i < 16; ++i) f[i] = 1.0f / (1.0f + __expf(-f[i]));
+            }
+#pragma unroll
+            for (int h8 = 0; h8 < 2; ++h8) {
+              uint32_t o[4];
+#pragma unroll
+              for (int i = 0; i < 4; ++i) {
+                const __nv_bfloat162 hh = __floats2bfloat162_rn(f[8 * h8 + 2 * i], f[8 * h8 + 2 * i + 1]);
+                o[i] = *reinterpret_cast<const uint32_t*>(&hh);
+                if (STATS) {
+                  const float lo = __uint_as_float(o[i] << 16), hi = __uint_as_float(o[i] & 0xffff0000u);
+                  const int c = 8 * h8 + 2 * i;
+                  st_s[STATS ? c : 0] += lo;      st_q[STATS ? c : 0] = fmaf(lo, lo, st_q[STATS ? c : 0]);
+                  st_s[STATS ? c + 1 : 0] += hi;  st_q[STATS ? c + 1 : 0] = fmaf(hi, hi, st_q[STATS ? c + 1 : 0]);
+                }
+              }
+              *reinterpret_cast<uint4*>(p.out + off[h8]) = make_uint4(o[0], o[1], o[2], o[3]);
+            }
+          }
+        }
+      }
+    }
+    if (++acc == kAccStages) { acc = 0; acc_phase ^= 1; }
+  }
+  if (STATS) {
+    // kChunks <= 2 (checked on the host): this thread's chunk is fixed -- chunk `half` when there are two, else 0
+    const int c0 = (kChunks == 2 ? half : 0) * 16;
+    const bool owner = kItems > half;          // MT == 1 && kChunks == 1: the second half never had an item
+#pragma unroll
+    for (int i = 0; i < (STATS ? 16 : 1); ++i) {
+      float s1 = st_s[i], s2 = st_q[i];
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        s1 += __shfl_xor_sync(0xffffffffu, s1, o);
+        s2 += __shfl_xor_sync(0xffffffffu, s2, o);
+      }
+      if (lane == 0 && owner) {
+        atomicAdd(p.stats + n0 + c0 + i, (double)s1);
+        atomicAdd(p.stats + p.Cout + n0 + c0 + i, (double)s2);
+      }
+    }
+  }
+}
+
 template <int CIN, int NT, int TAPS, int MT, int STAGES>
 __global__ void __launch_bounds__(kConvThreads, 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap tmap, const ConvParams p) {
@@ -205,131 +377,11 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap, const ConvParams p) {
     }
   } else if (warp >= 4) {
     // ================================================================= epilogue: 8 warps, two per TMEM sub-partition
-    const int q = warp & 3;                       // == warp % 4: the TMEM sub-partition this warp may read
-    const int half = (warp - 4) >> 2;             // the tile's (M tile, 16-column chunk) items alternate between the halves
-    const int m = q * 32 + lane;                  // accumulator row = pixel within the 16x8 M tile
-    const int py = m >> 3, px = m & 7;
-    const int Ho = p.H / p.subsample, Wo = p.W / p.subsample;
-    const int64_t plane = (int64_t)Ho * Wo * 8;   // elements per 8-channel plane of the output
-    constexpr int kChunks = NT / 16;
-    constexpr int kItems = MT * kChunks;
-    const int act = p.act;
-    const bool has_res = p.res != nullptr;
-    // train-mode BatchNorm statistics of the stored (bf16-rounded) outputs: every thread owns one 16-column chunk
-    float st_s[16], st_q[16];
-#pragma unroll
-    for (int i = 0; i < 16; ++i) { st_s[i] = 0.0f; st_q[i] = 0.0f; }
-    const bool do_stats = p.stats != nullptr;
-    int acc = 0;
-    uint32_t acc_phase = 0;
-    for (int64_t t = blockIdx.x; t < p.num_tiles; t += gridDim.x) {
-      const int img = (int)(t / tiles_per_img);
-      const int rem = (int)(t - (int64_t)img * tiles_per_img);
-      const int ty = rem / p.tiles_x, tx = rem - ty * p.tiles_x;
-      mbar_wait(&acc_full[acc], acc_phase);
-      tc_fence_after();
-#pragma unroll 1
-      for (int item = (p.diag & 8) ? kItems : half; item < kItems; item += 2) {
-        const int mt = item / kChunks, c0 = (item - mt * kChunks) * 16;
-        const int y = ty * kTileH + py, x = tx * (8 * MT) + mt * 8 + px;
-        bool valid = y < p.H && x < p.W;
-        int yo = y, xo = x;
-        if (p.subsample == 2) { valid = valid && !((y | x) & 1); yo = y >> 1; xo = x >> 1; }
-        if (p.diag & 4) valid = false;
-        uint32_t v[16];
-        tmem_ld_32x32b_x16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)((acc * MT + mt) * NT + c0), v);
-        // output offsets of the two 8-channel planes of this chunk (and the residual, requested before the TMEM wait)
-        int64_t off[2];
-#pragma unroll
-        for (int h8 = 0; h8 < 2; ++h8) {
-          const int n = n0 + c0 + 8 * h8;          // GEMM column of this plane's first channel
-          if (p.up2x) {
-            const int cq = p.Cout >> 2, qd = n / cq, co = n - qd * cq;       // n = (dy*2+dx)*Cout/4 + co
-            const int y2 = 2 * y + (qd >> 1), x2 = 2 * x + (qd & 1);
-            off[h8] = ((int64_t)img * (cq >> 3) + (co >> 3)) * (plane * 4) + ((int64_t)y2 * (2 * Wo) + x2) * 8;
-          } else {
-            off[h8] = ((int64_t)img * (p.Cout >> 3) + (n >> 3)) * plane + ((int64_t)yo * Wo + xo) * 8;
-          }
-        }
-        uint4 rr[2] = {make_uint4(0, 0, 0, 0), make_uint4(0, 0, 0, 0)};
-        if (has_res && valid) {
-          rr[0] = __ldg(reinterpret_cast<const uint4*>(p.res + off[0]));
-          rr[1] = __ldg(reinterpret_cast<const uint4*>(p.res + off[1]));
-        }
-        tmem_ld_wait();
-        if (valid) {
-          float f[16];
-#pragma unroll
-          for (int i4 = 0; i4 < 4; ++i4) {
-            const float4 sc = *reinterpret_cast<const float4*>(sVec + c0 + 4 * i4);
-            const float4 sh = *reinterpret_cast<const float4*>(sVec + NT + c0 + 4 * i4);
-            f[4 * i4] = fmaf(__uint_as_float(v[4 * i4]), sc.x, sh.x);
-            f[4 * i4 + 1] = fmaf(__uint_as_float(v[4 * i4 + 1]), sc.y, sh.y);
-            f[4 * i4 + 2] = fmaf(__uint_as_float(v[4 * i4 + 2]), sc.z, sh.z);
-            f[4 * i4 + 3] = fmaf(__uint_as_float(v[4 * i4 + 3]), sc.w, sh.w);
-          }
-          if (has_res) {
-#pragma unroll
-            for (int h8 = 0; h8 < 2; ++h8) {
-              const uint32_t rw[4] = {rr[h8].x, rr[h8].y, rr[h8].z, rr[h8].w};
-#pragma unroll
-              for (int i = 0; i < 4; ++i) {
-                const int c = 8 * h8 + 2 * i;
-                f[c] += fmaf(__uint_as_float(rw[i] << 16), sVec[2 * NT + c0 + c], sVec[3 * NT + c0 + c]);
-                f[c + 1] += fmaf(__uint_as_float(rw[i] & 0xffff0000u), sVec[2 * NT + c0 + c + 1], sVec[3 * NT + c0 + c + 1]);
-              }
-            }
-          }
-          if (act == CTL_ACT_LRELU) {
-#pragma unroll
-            for (int i = 0; i < 16; ++i) f[i] = fmaxf(f[i], 0.2f * f[i]);
-          } else if (act == CTL_ACT_RELU) {
-#pragma unroll
-            for (int i = 0; i < 16; ++i) f[i] = fmaxf(f[i], 0.0f);
-          } else if (act == CTL_ACT_SIGMOID) {
-#pragma unroll
-            for (int i = 0; i < 16; ++i) f[i] = 1.0f / (1.0f + __expf(-f[i]));
-          }
-#pragma unroll
-          for (int h8 = 0; h8 < 2; ++h8) {
-            uint32_t o[4];
-#pragma unroll
-            for (int i = 0; i < 4; ++i) {
-              const __nv_bfloat162 hh = __floats2bfloat162_rn(f[8 * h8 + 2 * i], f[8 * h8 + 2 * i + 1]);
-              o[i] = *reinterpret_cast<const uint32_t*>(&hh);
-              if (do_stats) {
-                const float lo = __uint_as_float(o[i] << 16), hi = __uint_as_float(o[i] & 0xffff0000u);
-                st_s[8 * h8 + 2 * i] += lo;      st_q[8 * h8 + 2 * i] = fmaf(lo, lo, st_q[8 * h8 + 2 * i]);
-                st_s[8 * h8 + 2 * i + 1] += hi;  st_q[8 * h8 + 2 * i + 1] = fmaf(hi, hi, st_q[8 * h8 + 2 * i + 1]);
-              }
-            }
-            *reinterpret_cast<uint4*>(p.out + off[h8]) = make_uint4(o[0], o[1], o[2], o[3]);
-          }
-        }
-      }
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&acc_empty[acc]);
-      if (++acc == kAccStages) { acc = 0; acc_phase ^= 1; }
-    }
-    if (do_stats) {
-      // kChunks <= 2 (checked on the host): this thread's chunk is fixed -- chunk `half` when there are two, else 0
-      const int c0 = (kChunks == 2 ? half : 0) * 16;
-      const bool owner = kItems > half;          // MT == 1 && kChunks == 1: the second half never had an item
-#pragma unroll
-      for (int i = 0; i < 16; ++i) {
-        float s1 = st_s[i], s2 = st_q[i];
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) {
-          s1 += __shfl_xor_sync(0xffffffffu, s1, o);
-          s2 += __shfl_xor_sync(0xffffffffu, s2, o);
-        }
-        if (lane == 0 && owner) {
-          atomicAdd(p.stats + n0 + c0 + i, (double)s1);
-          atomicAdd(p.stats + p.Cout + n0 + c0 + i, (double)s2);
-        }
-      }
-    }
+    // three register budgets instead of one: the residual variant keeps a tile's residual pixels in flight while it
+    // waits for the accumulator, the statistics variant carries 32 running sums (the host rejects res + stats)
+    if (p.res != nullptr) conv_epilogue<CIN, NT, TAPS, MT, STAGES, true, false>(p, tmem_base, sVec, acc_full, acc_empty, n0);
+    else if (p.stats != nullptr) conv_epilogue<CIN, NT, TAPS, MT, STAGES, false, true>(p, tmem_base, sVec, acc_full, acc_empty, n0);
+    else conv_epilogue<CIN, NT, TAPS, MT, STAGES, false, false>(p, tmem_base, sVec, acc_full, acc_empty, n0);
   }
 
   tc_fence_before();
@@ -451,6 +503,9 @@ extern "C" int ctl_conv2d_c8_bf16(const void* x, int64_t N, int64_t H, int64_t W
   const int nt = ctl_conv2d_n_tile((int)Cin, (int)Cout, taps);
   CTL_REQUIRE(stats == nullptr || (nt > 0 && nt <= 32 && !up2x), CTL_ERR_UNSUPPORTED,
               "fused output statistics need an N tile <= 32 (Cout %% 64 != 0 or 3x3 with Cin 128) and no up2x");
+  CTL_REQUIRE(stats == nullptr || res == nullptr, CTL_ERR_UNSUPPORTED,
+              "ctl_conv2d_c8_bf16: fused output statistics and a residual input cannot be combined");
+  CTL_REQUIRE(N * ((H + 15) / 16) * ((W + 7) / 8) < (int64_t)1 << 31, CTL_ERR_INVALID, "ctl_conv2d_c8_bf16: too many tiles");
   CTL_REQUIRE(nt > 0, CTL_ERR_UNSUPPORTED,
               "ctl_conv2d_c8_bf16 handles Cin in {16,32,64,128} and Cout %% 16 == 0 (got Cin=%lld Cout=%lld)",
               (long long)Cin, (long long)Cout);

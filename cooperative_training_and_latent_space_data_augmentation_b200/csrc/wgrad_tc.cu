@@ -41,7 +41,7 @@ struct WgradParams {
   int64_t num_tiles;
   float* dW;                 // fp32, accumulated into: element (tap, ci, co) at tap*s_tap + ci*s_ci + co*s_co
   int64_t s_co, s_ci, s_tap;
-  int diag;                  // profiling only (env CTL_DIAG_SKIP): 1 no MMA, 2 no TMA loads
+  int diag;                  // profiling only (env CTL_DIAG_SKIP): 1 no MMA, 2 no TMA loads, 4 no epilogue
 };
 
 template <int CIN, int NT, int TAPS, int STAGES>
@@ -73,6 +73,8 @@ struct WgCfg {
   static constexpr int kLastReach = (STAGES - 1) * kStage + kReach;
   static constexpr int kOffBar = ((kRing > kLastReach ? kRing : kLastReach) + 127) / 128 * 128;
   static constexpr int kSmemBytes = (kOffBar + 128 + 127) / 128 * 128;
+  // the epilogue may stage the CTA's [NT][CIN][TAPS] fp32 result in the operand ring (idle by then)
+  static constexpr bool kStageFits = NT * CIN * TAPS * 4 <= kOffBar;
   static_assert(kTmemCols <= 512, "accumulators exceed TMEM");
   static_assert(NT % 16 == 0 && NT <= 256 && CIN % 16 == 0, "UMMA shape");
   static_assert(kSmemBytes <= 227 * 1024, "shared memory budget");
@@ -183,8 +185,15 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constan
       const int q = warp - 4;
       mbar_wait(acc_full, 0);
       tc_fence_after();
+      // nn.Conv2d layout [co][ci][tap]: this CTA's N tile is ONE contiguous block of NT*CIN*TAPS floats.  Transpose the
+      // accumulators through the (now idle) operand ring and add the block with coalesced 16-byte reductions -- the
+      // direct path below scatters 4-byte atomics with a stride of TAPS (lanes) x CIN*TAPS (registers).
+      float* block = p.dW + (int64_t)n0 * CIN * TAPS;
+      const bool staged = Cfg::kStageFits && p.s_tap == 1 && p.s_ci == TAPS && p.s_co == (int64_t)CIN * TAPS &&
+                          (reinterpret_cast<uintptr_t>(block) & 15u) == 0;
+      float* stage = reinterpret_cast<float*>(smem);
 #pragma unroll 1
-      for (int sx = 0; sx < Cfg::kS; ++sx) {
+      for (int sx = (p.diag & 4) ? Cfg::kS : 0; sx < Cfg::kS; ++sx) {
 #pragma unroll
         for (int j = 0; j < Cfg::kG; ++j) {
           // accumulator row m of this thread: M = 128 -> TMEM lane m; M = 64 -> lane (m % 16) + 32 * (m / 16)
@@ -201,6 +210,11 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constan
             tmem_ld_32x32b_x16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)((sx * Cfg::kG + j) * NT + c0), v);
             tmem_ld_wait();
             if (row_ok) {
+              if (staged) {
+#pragma unroll
+                for (int i = 0; i < 16; ++i) stage[((c0 + i) * CIN + ci) * TAPS + tap] = __uint_as_float(v[i]);
+                continue;
+              }
               float* dst = p.dW + tap * p.s_tap + ci * p.s_ci + (int64_t)(n0 + c0) * p.s_co;
               if (p.s_co == 1 && ((reinterpret_cast<uintptr_t>(dst) & 15u) == 0)) {
 #pragma unroll
@@ -213,6 +227,15 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constan
               }
             }
           }
+        }
+      }
+      if (staged && !(p.diag & 4)) {
+        asm volatile("bar.sync 1, 128;" ::: "memory");                 // the four epilogue warps only
+        const float4* s4 = reinterpret_cast<const float4*>(stage);
+        const int tid = threadIdx.x - 128;
+        for (int i = tid; i < NT * CIN * TAPS / 4; i += 128) {
+          const float4 f = s4[i];
+          red_add_v4(block + 4 * i, f.x, f.y, f.z, f.w);
         }
       }
     }
