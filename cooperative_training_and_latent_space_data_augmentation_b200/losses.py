@@ -11,10 +11,15 @@ so it is computed on the host from the shape and the loss never leaves the devic
 import torch
 import torch.nn.functional as F
 
+from . import ops
+
 
 def cross_entropy_2D(input, target, weight=None, size_average=True, mask=None, is_gt=False):
     """sum over pixels of NLL (or of -q*log p for 4-D soft targets) / number of (unmasked) pixels."""
     n, c, h, w = input.size()
+    if mask is None and weight is None and ops.ce2d_supported(input, target):
+        # one fused pass (csrc/loss.cu): no log-probability tensor, no NHWC transpose, divisor folded into the kernel
+        return ops.cross_entropy_2d(input, target, 1.0 / float(n * h * w) if size_average else 1.0)
     log_p = F.log_softmax(input.float(), dim=1)
     if mask is not None:
         mask = (mask != 0).to(log_p.dtype)

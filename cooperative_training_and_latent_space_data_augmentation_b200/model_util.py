@@ -104,6 +104,8 @@ def cross_entropy_2D(input, target, weight=None, size_average=True):
     """Saliency cross entropy: label-map targets -> sum NLL / (numel + 1e-10); 4-D targets are
     treated as logits (softmax) and give -mean(q * log p)."""
     n, c, h, w = input.size()
+    if weight is None and ops.ce2d_supported(input, target):
+        return ops.cross_entropy_2d(input, target, 1.0 / float(target.numel() + 1e-10) if size_average else 1.0)
     log_p = F.log_softmax(input, dim=1)
     if target.dim() == 3:
         if weight is not None:

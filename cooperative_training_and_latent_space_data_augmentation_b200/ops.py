@@ -581,15 +581,22 @@ def head_bwd_c8(dy, y, x, weight, act=ACT_NONE, out=None):
         raise ValueError("dy must be [%d,%d,%d,%d]" % (N, cout, H, W))
     w = weight.detach().to(torch.float32).reshape(cout, cin).contiguous()
     dx = torch.empty_like(x)
-    grads = out if out is not None else torch.zeros(cout * cin + cout, device=x.device, dtype=torch.float32)
+    if isinstance(out, tuple):            # (dW, db): two live accumulation targets (e.g. the parameters' .grad tensors)
+        gw, gb = out
+        if gw.dtype != torch.float32 or gb.dtype != torch.float32 or gw.numel() != cout * cin or gb.numel() != cout \
+                or not (gw.is_contiguous() and gb.is_contiguous()):
+            raise ValueError("out=(dW, db) must be contiguous float32 tensors of %d and %d elements" % (cout * cin, cout))
+    else:
+        grads = out if out is not None else torch.zeros(cout * cin + cout, device=x.device, dtype=torch.float32)
+        gw, gb = grads[:cout * cin].view(cout, cin, 1, 1), grads[cout * cin:]
     yp = 0
     if act != ACT_NONE:
         y = y.to(torch.float32).contiguous()
         yp = y.data_ptr()
     with torch.cuda.device(x.device):
         _lib.check(_lib.load().ctl_head_bwd_c8(dy.data_ptr(), yp, x.data_ptr(), N, cin, H, W, w.data_ptr(), cout, act,
-                                               dx.data_ptr(), grads.data_ptr(), grads[cout * cin:].data_ptr(), _stream()))
-    return dx, grads[:cout * cin].view(cout, cin, 1, 1), grads[cout * cin:]
+                                               dx.data_ptr(), gw.data_ptr(), gb.data_ptr(), _stream()))
+    return dx, gw, gb
 
 
 def stem_wgrad_c8(dy, x, cin, in_mode=0, temperature=1.0, out=None):
@@ -622,3 +629,59 @@ def stem_dgrad_c8(dy, x, weight, in_mode=0, temperature=1.0):
         _lib.check(_lib.load().ctl_stem_dgrad_c8(dy.data_ptr(), _ptr(xf), in_mode, float(temperature), N, cin, H, W,
                                                  w.data_ptr(), dx.data_ptr(), _stream()))
     return dx
+
+
+# ------------------------------------------------------------------------------------------------ fused cross entropy
+_CE_WS = {}
+
+
+def _ce_workspace(device):
+    """16 zeroed bytes per device (fp64 sum + CTA ticket); ctl_ce2d_fwd leaves them zeroed, so one buffer serves every
+    call of the stream -- also inside a captured CUDA graph (persistent address)."""
+    key = (device.type, device.index)
+    ws = _CE_WS.get(key)
+    if ws is None:
+        ws = _CE_WS[key] = torch.zeros(2, device=device, dtype=torch.float64)
+    return ws
+
+
+def ce2d_supported(logits, target):
+    """Shapes / dtypes the fused kernels take: CUDA fp32 contiguous [N,C,H,W] logits with C in {2,3,4,8}, int64
+    contiguous [N,H,W] label map."""
+    return (logits.is_cuda and logits.dtype == torch.float32 and logits.dim() == 4 and logits.shape[1] in (2, 3, 4, 8)
+            and target.is_cuda and target.dtype == torch.int64 and target.dim() == 3
+            and tuple(target.shape) == (logits.shape[0], logits.shape[2], logits.shape[3]))
+
+
+class _CrossEntropy2D(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, logits, target, scale):
+        x = logits.detach().contiguous()
+        t = target.contiguous()
+        N, C, H, W = x.shape
+        out = torch.empty(1, device=x.device, dtype=torch.float32)
+        with torch.cuda.device(x.device):
+            _lib.check(_lib.load().ctl_ce2d_fwd(x.data_ptr(), t.data_ptr(), N, C, H, W, float(scale),
+                                                _ce_workspace(x.device).data_ptr(), out.data_ptr(), _stream()))
+        ctx.save_for_backward(x, t)
+        ctx.scale = float(scale)
+        return out.view(())
+
+    @staticmethod
+    def backward(ctx, gout):
+        x, t = ctx.saved_tensors
+        N, C, H, W = x.shape
+        g = gout.detach().to(torch.float32).contiguous()
+        dx = torch.empty_like(x)
+        with torch.cuda.device(x.device):
+            _lib.check(_lib.load().ctl_ce2d_bwd(x.data_ptr(), t.data_ptr(), N, C, H, W, ctx.scale, g.data_ptr(),
+                                                dx.data_ptr(), _stream()))
+        return dx, None, None
+
+
+def cross_entropy_2d(logits, target, scale=1.0):
+    """scale * sum over pixels of -log softmax(logits)[target]  (0-d fp32 tensor, differentiable w.r.t. logits)."""
+    if not ce2d_supported(logits, target):
+        raise ValueError("cross_entropy_2d: unsupported logits %s %s / target %s %s"
+                         % (tuple(logits.shape), logits.dtype, tuple(target.shape), target.dtype))
+    return _CrossEntropy2D.apply(logits, target, scale)

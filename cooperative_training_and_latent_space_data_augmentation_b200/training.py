@@ -25,7 +25,7 @@ import numpy as np
 import torch
 import torch.distributed as dist
 
-from . import _lib, model_util, ops
+from . import _lib, model_util, ops, trainpath
 
 LOSS_KEYS = ('loss/standard/total', 'loss/standard/seg', 'loss/standard/image', 'loss/standard/shape',
              'loss/standard/gt_shape', 'loss/hard/total', 'loss/hard/seg', 'loss/hard/image', 'loss/hard/shape')
@@ -91,7 +91,10 @@ def cooperative_step(solver, clean_image_l, label_l, corrupted_image_DA_config=N
 
     loss = standard_loss + hard_loss
     solver.reset_all_optimizers()
-    loss.backward()
+    # parameters whose .grad already exists (the trainers' flat bucket, or zero_grad(set_to_none=False)) receive their
+    # gradients straight from the backward kernels instead of one autograd add per parameter and pass
+    with trainpath.accumulate_into_grads():
+        loss.backward()
     if grad_sync is not None:
         grad_sync()
     if optimize:
@@ -111,37 +114,37 @@ class FlatGradBucket:
             raise ValueError("no parameters")
         dev, dt = self.params[0].device, self.params[0].dtype
         self.numel = sum(p.numel() for p in self.params)
-        self.flat = torch.zeros(self.numel, device=dev, dtype=dt)
-        off = 0
+        # weight tensors start on 16-byte boundaries: the weight-gradient kernels accumulate straight into these views
+        # with 16-byte reductions (trainpath.accumulate_into_grads); the few padding elements stay zero
+        self.offsets, off = [], 0
         for p in self.params:
-            n = p.numel()
-            p.grad = self.flat[off:off + n].view_as(p)
-            off += n
+            if p.dim() > 1:
+                off = (off + 3) // 4 * 4
+            self.offsets.append(off)
+            off += p.numel()
+        self.flat = torch.zeros(off, device=dev, dtype=dt)
+        for p, o in zip(self.params, self.offsets):
+            p.grad = self.flat[o:o + p.numel()].view_as(p)
 
     def zero(self):
         self.flat.zero_()
 
     def reattach(self):
         """If something replaced a .grad (e.g. zero_grad(set_to_none=True)), fold it back into the bucket."""
-        off = 0
-        for p in self.params:
-            n = p.numel()
-            view = self.flat[off:off + n].view_as(p)
+        for p, o in zip(self.params, self.offsets):
+            view = self.flat[o:o + p.numel()].view_as(p)
             if p.grad is None:
                 view.zero_()
                 p.grad = view
             elif p.grad.data_ptr() != view.data_ptr():
                 view.copy_(p.grad)
                 p.grad = view
-            off += n
 
     def attached(self):
         """True when every parameter's .grad is still its view of the flat buffer."""
-        off = 0
-        for p in self.params:
-            if p.grad is None or p.grad.data_ptr() != self.flat.data_ptr() + off * self.flat.element_size():
+        for p, o in zip(self.params, self.offsets):
+            if p.grad is None or p.grad.data_ptr() != self.flat.data_ptr() + o * self.flat.element_size():
                 return False
-            off += p.numel()
         return True
 
     def all_reduce_mean(self, group=None):

@@ -20,6 +20,8 @@ Gradient of a convolution bias that feeds a train-mode BatchNorm is identically 
 the reference accumulates ~1e-9 rounding noise there): no gradient tensor is produced for those biases, so the
 optimizer leaves them alone -- the network function does not depend on them.
 """
+import contextlib
+
 import torch
 import torch.nn as nn
 
@@ -100,7 +102,25 @@ def _dgrad(conv, dy, res=None):
 def _wgrad(grads, conv, x, dy):
     """K3w straight into nn.Conv2d's [Cout][Cin][k][k] layout, accumulated into a slice of the backward's zero arena."""
     k = conv.kernel_size[0]
-    return ops.conv_wgrad_c8(x, dy, k * k, out=grads.zeros(conv.weight.shape), layout='conv')
+    return ops.conv_wgrad_c8(x, dy, k * k, out=grads.buffer(conv.weight), layout='conv')
+
+
+_DIRECT = {"on": False}      # process-global on purpose: backward nodes run on autograd's device thread
+
+
+@contextlib.contextmanager
+def accumulate_into_grads():
+    """While active, a backward of the Functions below ADDS the gradient of every parameter that already owns a
+    `.grad` tensor into that tensor itself -- the weight-gradient kernels accumulate atomically into it, the small
+    per-channel vectors go through one multi-tensor add per sub-network -- and returns None for it, instead of handing
+    ~280 tensors per pass to autograd's AccumulateGrad (one `add` launch each, per pass).  Same values, same place;
+    only valid around a plain `loss.backward()` (never around torch.autograd.grad w.r.t. parameters)."""
+    prev = _DIRECT["on"]
+    _DIRECT["on"] = True
+    try:
+        yield
+    finally:
+        _DIRECT["on"] = prev
 
 
 class _Grads(dict):
@@ -109,19 +129,26 @@ class _Grads(dict):
 
     def __init__(self, params, needs):
         super().__init__()
-        self.need = {id(p) for p, n in zip(params, needs) if n}
-        # ONE zeroed fp32 arena for every accumulated (atomic) parameter gradient of this backward
-        total = sum(p.numel() for p, n in zip(params, needs) if n and p.dim() > 1)
-        self.arena = torch.zeros(total + 256, device=params[0].device, dtype=torch.float32) if total else None
-        self.used = 0
+        wanted = [p for p, n in zip(params, needs) if n]
+        self.need = {id(p) for p in wanted}
+        self.direct = bool(wanted) and _DIRECT["on"] and all(
+            p.grad is not None and p.grad.is_contiguous() and p.grad.dtype == torch.float32 for p in wanted)
+        self.small_dst, self.small_src = [], []
+        self.arena, self.used = None, 0
+        if not self.direct:
+            # ONE zeroed fp32 arena for every accumulated (atomic) parameter gradient of this backward
+            total = sum((p.numel() + 3) // 4 * 4 for p in wanted if p.dim() > 1)
+            self.arena = torch.zeros(total + 256, device=params[0].device, dtype=torch.float32) if total else None
 
-    def zeros(self, shape):
-        n = 1
-        for d in shape:
-            n *= int(d)
-        out = self.arena[self.used:self.used + n].view(*shape)
+    def buffer(self, p, extra=0):
+        """Zero-initialised (or, in direct mode, the live `.grad`) fp32 buffer shaped like parameter `p` that a kernel
+        accumulates into; `extra` more elements follow it in the arena (head: weight | bias)."""
+        if self.direct:
+            return p.grad
+        n = p.numel() + extra
+        out = self.arena[self.used:self.used + n]
         self.used += (n + 3) // 4 * 4                      # keep slices 16-byte aligned
-        return out
+        return out.view(p.shape) if not extra else out
 
     def wants(self, p):
         return p is not None and id(p) in self.need
@@ -129,8 +156,24 @@ class _Grads(dict):
     def add(self, p, g):
         if g is None or not self.wants(p):
             return
+        if self.direct:
+            if g.data_ptr() == p.grad.data_ptr():          # a kernel accumulated into .grad itself: done
+                return
+            if any(d is p.grad for d in self.small_dst):   # second contribution in one backward: not in one foreach
+                p.grad.add_(g.view_as(p.grad))
+            else:
+                self.small_dst.append(p.grad)
+                self.small_src.append(g.view_as(p.grad))
+            return
         key = id(p)
         self[key] = g if key not in self else self[key] + g
+
+    def results(self, params):
+        if self.direct:
+            if self.small_dst:
+                torch._foreach_add_(self.small_dst, self.small_src)
+            return (None,) * len(params)
+        return tuple(self.get(id(p)) for p in params)
 
 
 # ------------------------------------------------------------------------------------------------ conv + BN + act
@@ -236,7 +279,7 @@ def up_bwd(block, saved, dout, grads, need_dx=True):
         return None
     parts = ops.split_parity2x2_c8(dxu)                     # [4][N, C/8, H, W, 8]: dy per kernel tap
     if want_w:
-        dW = grads.zeros(up.weight.shape)                  # [ci][co][2][2], tap d written with stride 4
+        dW = grads.buffer(up.weight)                       # [ci][co][2][2], tap d written with stride 4
         for d in range(4):
             ops.conv_wgrad_c8(x, parts[d], 1, out=dW, layout=('convT', d))
         grads.add(up.weight, dW)
@@ -280,7 +323,7 @@ def encoder_bwd(enc, tape, dz, grads, x, in_mode, temperature, need_dx):
     grads.add(inc[1].bias, db0)
     if grads.wants(inc[0].weight):
         grads.add(inc[0].weight, ops.stem_wgrad_c8(da0, x, inc[0].in_channels, in_mode, temperature,
-                                                   out=grads.zeros(inc[0].weight.shape)))
+                                                   out=grads.buffer(inc[0].weight)))
     if need_dx:
         return ops.stem_dgrad_c8(da0, x, inc[0].weight, in_mode, temperature)
     return None
@@ -318,7 +361,11 @@ def decoder_fwd(dec, z_c8):
 def decoder_bwd(dec, tape, dout, grads, need_dz):
     y, out = tape[4]
     fc = dec.final_conv
-    gbuf = grads.zeros((fc.weight.numel() + fc.out_channels,)) if grads.arena is not None else None
+    want_fc = grads.wants(fc.weight) and grads.wants(fc.bias)
+    if want_fc and grads.direct:
+        gbuf = (fc.weight.grad, fc.bias.grad)
+    else:
+        gbuf = grads.buffer(fc.weight, extra=fc.out_channels) if (want_fc and grads.arena is not None) else None
     dy, dW, db = ops.head_bwd_c8(dout, out, y, fc.weight, _act_code(dec.last_act), out=gbuf)
     grads.add(fc.weight, dW)
     grads.add(fc.bias, db)
@@ -331,7 +378,7 @@ def decoder_bwd(dec, tape, dout, grads, need_dz):
 
 # ------------------------------------------------------------------------------------------------ autograd glue
 def _param_grads(params, grads):
-    return tuple(grads.get(id(p)) for p in params)
+    return grads.results(params)
 
 
 class _DecoderFn(torch.autograd.Function):

@@ -229,6 +229,18 @@ int ctl_split_parity2x2_c8(const void* x, int64_t N, int64_t C, int64_t H, int64
  * dx C8 bf16 [N,2,H,W,8]; dW fp32 [Cout][16] and db fp32 [Cout] are ACCUMULATED into.  Cout in {1,4}. */
 int ctl_head_bwd_c8(const float* dy, const float* y, const void* x, int64_t N, int64_t Cin, int64_t H, int64_t W,
                     const float* weight, int64_t Cout, int act, void* dx, float* dW, float* db, void* stream);
+/* ---------------------------------------------------------------------------------------------
+ * Fused 2-D cross entropy with label-map targets (no mask, no class weights).  Replaces
+ *   log_softmax -> NHWC transpose -> nll_loss(sum) -> / region   medseg/models/custom_loss.py:706-741 (via :8-19)
+ *   log_softmax -> nll_loss(sum) / (numel + 1e-10)               medseg/models/model_util.py:104-135
+ * logits: planar fp32 [N,C,H,W], C in {2,3,4,8}; labels: int64 [N,H,W] (values outside [0,C) are ignored);
+ * loss_out[0] = scale * sum over pixels of (logsumexp(x) - x[label]).  workspace16: 16 bytes of device memory that
+ * are ZERO on entry and left zero on exit (fp64 sum + CTA ticket), so one buffer serves every call of a stream.
+ * ctl_ce2d_bwd: dlogits = grad_out[0] * scale * (softmax(x) - onehot(label)); grad_out is a DEVICE scalar (NULL = 1). */
+int ctl_ce2d_fwd(const float* logits, const int64_t* labels, int64_t N, int64_t C, int64_t H, int64_t W, double scale,
+                 void* workspace16, float* loss_out, void* stream);
+int ctl_ce2d_bwd(const float* logits, const int64_t* labels, int64_t N, int64_t C, int64_t H, int64_t W, double scale,
+                 const float* grad_out, float* dlogits, void* stream);
 /* backward of ctl_stem_conv3x3_c8 w.r.t. the weight: dy C8 (16 channels, gradient of the raw conv output);
  * x / labels / in_mode / temperature as in the forward; dW fp32 [16][Cin][3][3] ACCUMULATED into. */
 int ctl_stem_wgrad_c8(const void* dy, const float* x, const int64_t* labels, int in_mode, float temperature, int64_t N,

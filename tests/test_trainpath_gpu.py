@@ -302,3 +302,51 @@ def test_predict_on_a_10_slice_stack_matches_fp32(env):
     assert agree > 0.9, agree            # synthetic random weights: many pixels sit on near-ties between classes
     assert float((got - want).abs().mean()) < 3e-2   # bf16 through FTN + 2x STN on random weights (measured 2.1e-2)
     assert solver.training is False
+
+
+@pytest.mark.parametrize("name", ["segmentation_decoder", "image_decoder", "image_encoder"])
+def test_direct_grad_accumulation_equals_autograd_accumulation(env, name):
+    """trainpath.accumulate_into_grads(): two backward passes ADDED by the kernels into pre-existing .grad tensors give
+    what autograd's per-parameter accumulation gives (fp32 atomics in a different order: 1e-5 of the largest entry)."""
+    pkg, nets = env
+    from cooperative_training_and_latent_space_data_augmentation_b200 import trainpath
+    net = nets[name]
+    gen = torch.Generator(device="cuda").manual_seed(4)
+    if name == "image_encoder":
+        x = torch.rand(4, 1, 64, 48, device="cuda", generator=gen)
+    else:
+        x = torch.relu(torch.randn(4, 128, 4, 3, device="cuda", generator=gen))
+    pkg.conv_blocks.set_precision("kernel")
+    state0 = {n: b.clone() for n, b in net.named_buffers()}
+
+    def two_passes(direct):
+        for n, b in net.named_buffers():
+            b.copy_(state0[n])
+        for p in net.parameters():
+            p.grad = torch.zeros_like(p) if direct else None
+        for rep in range(2):
+            outs = net(x * (1.0 + 0.1 * rep))
+            outs = outs if isinstance(outs, tuple) else (outs,)
+            g = torch.Generator(device="cuda").manual_seed(11 + rep)
+            loss = sum((o.float() * torch.randn(o.shape, device="cuda", generator=g) * 1e-3).sum() for o in outs)
+            if direct:
+                with trainpath.accumulate_into_grads():
+                    loss.backward()
+            else:
+                loss.backward()
+        return {n: (p.grad.clone() if p.grad is not None else None) for n, p in net.named_parameters()}
+
+    try:
+        ref, got = two_passes(False), two_passes(True)
+    finally:
+        pkg.conv_blocks.set_precision("fp32")
+        for n, b in net.named_buffers():
+            b.copy_(state0[n])
+        for p in net.parameters():
+            p.grad = None
+    for n, r in ref.items():
+        k = got[n]
+        if r is None:                      # a conv bias in front of a train-mode BatchNorm: no gradient is produced
+            assert float(k.abs().max()) == 0.0, n
+            continue
+        assert float((k - r).abs().max()) <= 1e-5 * float(r.abs().max()) + 1e-12, (n, float((k - r).abs().max()))

@@ -9,7 +9,7 @@ run() {  # name, pytest args...
   rm -f gpurun_out/t_$name.full
   echo "== $name: $(tail -1 gpurun_out/t_$name.log)"
 }
-groups=${@:-"wgrad bwd train fast conv masking solver"}
+groups=${@:-"wgrad bwd train fast conv masking solver loss graph"}
 for g in $groups; do
   case $g in
     wgrad) run wgrad tests/test_bwd_kernels_gpu.py -k "wgrad or stride2 or convtranspose" ;;
@@ -19,5 +19,7 @@ for g in $groups; do
     conv) run conv tests/test_conv_gpu.py ;;
     masking) run masking tests/test_masking_gpu.py ;;
     solver) run solver tests/test_solver_gpu.py ;;
+    loss) run loss tests/test_loss_gpu.py ;;
+    graph) run graph tests/test_graph_gpu.py ;;
   esac
 done
