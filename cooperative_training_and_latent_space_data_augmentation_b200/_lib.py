@@ -51,8 +51,8 @@ SIGNATURES = {
     "ctl_reduce_workspace_bytes": (_c.c_size_t, [_i64, _i64]),
     "ctl_channel_sums_c8": (_i, [_vp, _i64, _i64, _i64, _i64, _vp, _vp, _vp, _vp]),
     "ctl_bn_bwd_reduce_c8": (_i, [_vp, _vp, _vp, _i64, _i64, _i64, _i64, _i, _vp, _vp, _f, _vp, _vp, _vp, _vp, _vp, _vp,
-                                  _vp]),
-    "ctl_bn_bwd_apply_c8": (_i, [_vp, _vp, _vp, _i64, _i64, _i64, _i64, _i, _vp, _vp, _vp]),
+                                  _vp, _vp, _vp]),
+    "ctl_bn_bwd_apply_c8": (_i, [_vp, _vp, _vp, _i64, _i64, _i64, _i64, _i, _vp, _vp, _vp, _vp, _vp]),
     "ctl_act_bwd_c8": (_i, [_vp, _vp, _i64, _i64, _i64, _i64, _i, _vp, _vp]),
     "ctl_downsample2x_sum_c8": (_i, [_vp, _i64, _i64, _i64, _i64, _vp, _vp]),
     "ctl_zero_stuff2x_c8": (_i, [_vp, _i64, _i64, _i64, _i64, _vp, _vp]),

@@ -60,8 +60,15 @@ template <int MODE>
 __global__ void __launch_bounds__(kT)
 plane_reduce_kernel(const uint4* __restrict__ x, const uint4* __restrict__ h, const uint4* __restrict__ a,
                     uint4* __restrict__ dv_out, double* __restrict__ partial, int64_t planes, int64_t HW, int splits,
-                    int act) {
+                    int act, const float* __restrict__ act_scale, const float* __restrict__ act_shift, int C8) {
   const int64_t plane = blockIdx.x;
+  // h == NULL with an affine: the activation input is recomputed, h = act(a*act_scale[c] + act_shift[c]) has its sign
+  float asc[8], ash[8];
+  if (MODE == 1 && h == nullptr && act_scale != nullptr) {
+    const int c0 = (int)(plane % C8) * 8;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { asc[j] = __ldg(act_scale + c0 + j); ash[j] = __ldg(act_shift + c0 + j); }
+  }
   const int split = blockIdx.y;
   const int64_t chunk = (HW + splits - 1) / splits;
   const int64_t lo = split * chunk, hi = min(HW, lo + chunk);
@@ -88,6 +95,9 @@ plane_reduce_kernel(const uint4* __restrict__ x, const uint4* __restrict__ h, co
           dv_out[idx] = packed;
           unpack8(packed, f);                     // reduce what the consumers will read (bf16-rounded)
         }
+      } else if (act_scale != nullptr) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) f[j] *= act_slope(av[j] * asc[j] + ash[j], act);
       }
 #pragma unroll
       for (int j = 0; j < 8; ++j) { s[j] += f[j]; q[j] = fmaf(f[j], av[j], q[j]); }
@@ -226,7 +236,8 @@ __global__ void bn_bwd_finalize_kernel(const double* __restrict__ partial, int64
 // da = c1*dv + c2*a + c3, dv = dy * act'(h) when h is given
 __global__ void __launch_bounds__(kT)
 bn_bwd_apply_kernel(const uint4* __restrict__ dy, const uint4* __restrict__ h, const uint4* __restrict__ a,
-                    const float* __restrict__ coef, uint4* __restrict__ da, int64_t total, int C8, int64_t HW, int act) {
+                    const float* __restrict__ coef, uint4* __restrict__ da, int64_t total, int C8, int64_t HW, int act,
+                    const float* __restrict__ act_scale, const float* __restrict__ act_shift) {
   const int C = C8 * 8;
   for (int64_t i = (int64_t)blockIdx.x * kT + threadIdx.x; i < total; i += (int64_t)gridDim.x * kT) {
     const int c0 = (int)((i / HW) % C8) * 8;
@@ -238,6 +249,9 @@ bn_bwd_apply_kernel(const uint4* __restrict__ dy, const uint4* __restrict__ h, c
       unpack8(__ldcs(h + i), hv);
 #pragma unroll
       for (int j = 0; j < 8; ++j) f[j] *= act_slope(hv[j], act);
+    } else if (act_scale != nullptr) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) f[j] *= act_slope(av[j] * __ldg(act_scale + c0 + j) + __ldg(act_shift + c0 + j), act);
     }
 #pragma unroll
     for (int j = 0; j < 8; ++j)
@@ -609,7 +623,7 @@ extern "C" int ctl_bn_batch_affine_c8(const void* x, int64_t N, int64_t C, int64
   const int64_t planes = N * (C / 8), HW = H * W;
   const int splits = plane_splits(planes, HW);
   plane_reduce_kernel<0><<<dim3((unsigned)planes, (unsigned)splits), kT, 0, st>>>(
-      (const uint4*)x, nullptr, nullptr, nullptr, (double*)workspace, planes, HW, splits, 0);
+      (const uint4*)x, nullptr, nullptr, nullptr, (double*)workspace, planes, HW, splits, 0, nullptr, nullptr, (int)(C / 8));
   CTL_CUDA_OK(cudaGetLastError(), "bn_partial_stats launch");
   bn_fwd_finalize_kernel<<<(unsigned)ceil_div(C, 4), 128, 0, st>>>((const double*)workspace, planes, splits, (int)N, (int)C,
                                                                    (double)(N * HW), gamma, beta, eps, scale, shift,
@@ -640,7 +654,7 @@ extern "C" int ctl_channel_sums_c8(const void* x, int64_t N, int64_t C, int64_t 
   const int64_t planes = N * (C / 8), HW = H * W;
   const int splits = plane_splits(planes, HW);
   plane_reduce_kernel<0><<<dim3((unsigned)planes, (unsigned)splits), kT, 0, st>>>(
-      (const uint4*)x, nullptr, nullptr, nullptr, (double*)workspace, planes, HW, splits, 0);
+      (const uint4*)x, nullptr, nullptr, nullptr, (double*)workspace, planes, HW, splits, 0, nullptr, nullptr, (int)(C / 8));
   CTL_CUDA_OK(cudaGetLastError(), "plane_reduce launch");
   channel_sum_finalize_kernel<<<(unsigned)ceil_div(C, 4), 128, 0, st>>>((const double*)workspace, planes, splits, (int)N,
                                                                         (int)C, sum_out, sumsq_out);
@@ -651,17 +665,20 @@ extern "C" int ctl_channel_sums_c8(const void* x, int64_t N, int64_t C, int64_t 
 extern "C" int ctl_bn_bwd_reduce_c8(const void* dy, const void* h, const void* a, int64_t N, int64_t C, int64_t H,
                                     int64_t W, int act, const float* mean, const float* var, float eps,
                                     const float* gamma, void* workspace, void* dv_out, float* coef, float* dgamma,
-                                    float* dbeta, void* stream) {
+                                    float* dbeta, const float* act_scale, const float* act_shift, void* stream) {
   if (int rc = check_c8("ctl_bn_bwd_reduce_c8", dy, a, N, C, H, W)) return rc;
   CTL_REQUIRE(mean && var && workspace && coef, CTL_ERR_INVALID, "ctl_bn_bwd_reduce_c8: NULL pointer");
   CTL_REQUIRE(act >= CTL_ACT_NONE && act <= CTL_ACT_RELU, CTL_ERR_INVALID, "activation %d has no BN backward", act);
   CTL_REQUIRE(h != nullptr || dv_out == nullptr, CTL_ERR_INVALID, "dv_out needs h");
+  CTL_REQUIRE((act_scale == nullptr) == (act_shift == nullptr) && (h == nullptr || act_scale == nullptr), CTL_ERR_INVALID,
+              "ctl_bn_bwd_reduce_c8: give either h or (act_scale, act_shift)");
   if (sm_count() < 0) return CTL_ERR_CUDA;
   cudaStream_t st = (cudaStream_t)stream;
   const int64_t planes = N * (C / 8), HW = H * W;
   const int splits = plane_splits(planes, HW);
   plane_reduce_kernel<1><<<dim3((unsigned)planes, (unsigned)splits), kT, 0, st>>>(
-      (const uint4*)dy, (const uint4*)h, (const uint4*)a, (uint4*)dv_out, (double*)workspace, planes, HW, splits, act);
+      (const uint4*)dy, (const uint4*)h, (const uint4*)a, (uint4*)dv_out, (double*)workspace, planes, HW, splits, act,
+      act_scale, act_shift, (int)(C / 8));
   CTL_CUDA_OK(cudaGetLastError(), "bn_bwd_reduce launch");
   bn_bwd_finalize_kernel<<<(unsigned)ceil_div(C, 4), 128, 0, st>>>((const double*)workspace, planes, splits, (int)N, (int)C,
                                                                    (double)(N * HW), mean, var, eps, gamma, coef, dgamma,
@@ -671,13 +688,17 @@ extern "C" int ctl_bn_bwd_reduce_c8(const void* dy, const void* h, const void* a
 }
 
 extern "C" int ctl_bn_bwd_apply_c8(const void* dy, const void* h, const void* a, int64_t N, int64_t C, int64_t H,
-                                   int64_t W, int act, const float* coef, void* da, void* stream) {
+                                   int64_t W, int act, const float* coef, void* da, const float* act_scale,
+                                   const float* act_shift, void* stream) {
   if (int rc = check_c8("ctl_bn_bwd_apply_c8", dy, a, N, C, H, W)) return rc;
   CTL_REQUIRE(coef && da, CTL_ERR_INVALID, "ctl_bn_bwd_apply_c8: NULL pointer");
+  CTL_REQUIRE((act_scale == nullptr) == (act_shift == nullptr) && (h == nullptr || act_scale == nullptr), CTL_ERR_INVALID,
+              "ctl_bn_bwd_apply_c8: give either h or (act_scale, act_shift)");
   if (sm_count() < 0) return CTL_ERR_CUDA;
   const int64_t total = N * (C / 8) * H * W;
   bn_bwd_apply_kernel<<<grid_for(total), kT, 0, (cudaStream_t)stream>>>((const uint4*)dy, (const uint4*)h, (const uint4*)a,
-                                                                      coef, (uint4*)da, total, (int)(C / 8), H * W, act);
+                                                                      coef, (uint4*)da, total, (int)(C / 8), H * W, act,
+                                                                      act_scale, act_shift);
   CTL_CUDA_OK(cudaGetLastError(), "bn_bwd_apply launch");
   return CTL_OK;
 }

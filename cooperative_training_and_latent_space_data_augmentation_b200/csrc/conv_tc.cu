@@ -100,9 +100,9 @@ struct ConvCfg {
 // as a batch: every residual pixel of the tile is requested BEFORE the accumulator wait (the addresses do not depend on
 // it), the TMEM loads of two items are issued back to back behind one tcgen05.wait::ld, and the accumulator stage is
 // handed back to the MMA issuer as soon as the last load has landed in registers -- before the arithmetic and stores.
-template <int CIN, int NT, int TAPS, int MT, int STAGES, bool RES, bool STATS>
+template <int CIN, int NT, int TAPS, int MT, int STAGES, bool RES, bool STATS, bool GEN>
 __device__ __forceinline__ void conv_epilogue(const ConvParams& p, const uint32_t tmem_base, const float* sVec,
-                                              uint64_t* acc_full, uint64_t* acc_empty, const int n0) {
+                                              uint64_t* acc_full, uint64_t* acc_empty, const int n0, float* stat_smem) {
   using Cfg = ConvCfg<CIN, NT, TAPS, MT, STAGES>;
   constexpr int kAccStages = Cfg::kAcc;
   constexpr int kChunks = NT / 16;
@@ -131,11 +131,19 @@ __device__ __forceinline__ void conv_epilogue(const ConvParams& p, const uint32_
     const int rem = t - img * tiles_per_img;
     const int ty = rem / p.tiles_x, tx = rem - ty * p.tiles_x;
     const int y = ty * kTileH + py;
+    const int xb = tx * (8 * MT) + px;
+    // plain geometry (stride 1, no ConvTranspose scatter): one 64-bit base per tile, items differ by constants
+    const bool y_ok = y < p.H && !(p.diag & 4);
+    const int64_t pix = ((int64_t)img * (p.Cout >> 3) + (n0 >> 3)) * plane + ((int64_t)y * p.W + xb) * 8;
     // element offset of plane h8 of item u (the residual shares the output's geometry)
     auto offset_of = [&](int u, int h8, bool& valid) -> int64_t {
       const int item = first_item + 2 * u;
       const int mt = item / kChunks, c0 = (item - mt * kChunks) * 16;
-      const int x = tx * (8 * MT) + mt * 8 + px;
+      if (!GEN) {
+        valid = y_ok && xb + mt * 8 < p.W;
+        return pix + mt * 64 + (int64_t)((c0 >> 3) + h8) * plane;
+      }
+      const int x = xb + mt * 8;
       valid = y < p.H && x < p.W && !(p.diag & 4);
       const int n = n0 + c0 + 8 * h8;              // GEMM column of this plane's first channel
       if (p.up2x) {
@@ -148,8 +156,9 @@ __device__ __forceinline__ void conv_epilogue(const ConvParams& p, const uint32_
       return ((int64_t)img * (p.Cout >> 3) + (n >> 3)) * plane + ((int64_t)yo * Wo + xo) * 8;
     };
 
+    const bool has_res = RES && (!GEN || p.res != nullptr);     // the GEN variant serves both
     uint4 rr[RES ? kPer : 1][2];
-    if (RES) {
+    if (has_res) {
 #pragma unroll
       for (int u = 0; u < kPer; ++u) {
 #pragma unroll
@@ -202,7 +211,7 @@ __device__ __forceinline__ void conv_epilogue(const ConvParams& p, const uint32_
               f[4 * i4 + 2] = fmaf(__uint_as_float(v[b][4 * i4 + 2]), sc.z, sh.z);
               f[4 * i4 + 3] = fmaf(__uint_as_float(v[b][4 * i4 + 3]), sc.w, sh.w);
             }
-            if (RES) {
+            if (has_res) {
 #pragma unroll
               for (int h8 = 0; h8 < 2; ++h8) {
                 const uint4 r4 = rr[RES ? u : 0][h8];
@@ -248,9 +257,13 @@ __device__ __forceinline__ void conv_epilogue(const ConvParams& p, const uint32_
     if (++acc == kAccStages) { acc = 0; acc_phase ^= 1; }
   }
   if (STATS) {
-    // kChunks <= 2 (checked on the host): this thread's chunk is fixed -- chunk `half` when there are two, else 0
+    // kChunks <= 2 (checked on the host): this thread's chunk is fixed -- chunk `half` when there are two, else 0.
+    // Warp shuffle reduce -> shared memory (the operand ring is idle: every MMA that read it has completed, or this
+    // warp could not have seen the last accumulator) -> ONE fp64 atomic per channel statistic and CTA: the per-warp
+    // form issued 8x as many onto the same 2*Cout addresses from all CTAs at once and cost ~30 us per launch.
     const int c0 = (kChunks == 2 ? half : 0) * 16;
     const bool owner = kItems > half;          // MT == 1 && kChunks == 1: the second half never had an item
+    float* red = stat_smem + (warp - 4) * 32;  // [8 warps][sum x16 | sumsq x16] of this warp's chunk
 #pragma unroll
     for (int i = 0; i < (STATS ? 16 : 1); ++i) {
       float s1 = st_s[i], s2 = st_q[i];
@@ -259,11 +272,24 @@ __device__ __forceinline__ void conv_epilogue(const ConvParams& p, const uint32_
         s1 += __shfl_xor_sync(0xffffffffu, s1, o);
         s2 += __shfl_xor_sync(0xffffffffu, s2, o);
       }
-      if (lane == 0 && owner) {
-        atomicAdd(p.stats + n0 + c0 + i, (double)s1);
-        atomicAdd(p.stats + p.Cout + n0 + c0 + i, (double)s2);
-      }
+      if (lane == 0) { red[i] = owner ? s1 : 0.0f; red[16 + i] = owner ? s2 : 0.0f; }
     }
+    asm volatile("bar.sync 2, 256;" ::: "memory");          // the eight epilogue warps
+    const int tid = threadIdx.x - 128;
+    if (tid < 2 * NT) {
+      // column j of statistic `which`: chunk j / 16 lives in the warps of half (kChunks == 2 ? j / 16 : both halves)
+      const int which = tid / NT, j = tid - which * NT;
+      const int chunk = j >> 4, i = j & 15;
+      double total = 0.0;
+#pragma unroll
+      for (int w = 0; w < 8; ++w) {
+        const int w_half = w >> 2;
+        const bool has = kChunks == 2 ? (w_half == chunk) : true;
+        if (has) total += (double)stat_smem[w * 32 + which * 16 + i];
+      }
+      atomicAdd(p.stats + which * p.Cout + n0 + j, total);
+    }
+    (void)c0;
   }
 }
 
@@ -377,11 +403,17 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap, const ConvParams p) {
     }
   } else if (warp >= 4) {
     // ================================================================= epilogue: 8 warps, two per TMEM sub-partition
-    // three register budgets instead of one: the residual variant keeps a tile's residual pixels in flight while it
-    // waits for the accumulator, the statistics variant carries 32 running sums (the host rejects res + stats)
-    if (p.res != nullptr) conv_epilogue<CIN, NT, TAPS, MT, STAGES, true, false>(p, tmem_base, sVec, acc_full, acc_empty, n0);
-    else if (p.stats != nullptr) conv_epilogue<CIN, NT, TAPS, MT, STAGES, false, true>(p, tmem_base, sVec, acc_full, acc_empty, n0);
-    else conv_epilogue<CIN, NT, TAPS, MT, STAGES, false, false>(p, tmem_base, sVec, acc_full, acc_empty, n0);
+    // separate register budgets: the residual variant keeps a tile's residual pixels in flight while it waits for the
+    // accumulator, the statistics variant carries 32 running sums (the host rejects res + stats), the generic-geometry
+    // variant (stride 2 / ConvTranspose scatter) pays the per-item 64-bit address arithmetic the others hoist
+    if (p.up2x || p.subsample != 1)
+      conv_epilogue<CIN, NT, TAPS, MT, STAGES, true, false, true>(p, tmem_base, sVec, acc_full, acc_empty, n0, reinterpret_cast<float*>(sA));
+    else if (p.res != nullptr)
+      conv_epilogue<CIN, NT, TAPS, MT, STAGES, true, false, false>(p, tmem_base, sVec, acc_full, acc_empty, n0, reinterpret_cast<float*>(sA));
+    else if (p.stats != nullptr)
+      conv_epilogue<CIN, NT, TAPS, MT, STAGES, false, true, false>(p, tmem_base, sVec, acc_full, acc_empty, n0, reinterpret_cast<float*>(sA));
+    else
+      conv_epilogue<CIN, NT, TAPS, MT, STAGES, false, false, false>(p, tmem_base, sVec, acc_full, acc_empty, n0, reinterpret_cast<float*>(sA));
   }
 
   tc_fence_before();

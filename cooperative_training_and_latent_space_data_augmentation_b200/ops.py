@@ -502,9 +502,11 @@ def channel_sum_c8(x):
     return out
 
 
-def bn_act_bwd_c8(dy, h, a, act, mean, var, eps, gamma, want_dv=False, want_param_grads=True):
+def bn_act_bwd_c8(dy, h, a, act, mean, var, eps, gamma, want_dv=False, want_param_grads=True, act_affine=None):
     """Backward of h = act(BatchNorm_train(a)).  Returns (da, dgamma, dbeta, dv): dv = dy*act'(h) is materialised only
-    when want_dv (h must then be given); dgamma/dbeta are None unless want_param_grads."""
+    when want_dv (h must then be given); dgamma/dbeta are None unless want_param_grads.
+    act_affine = (scale, shift) of the forward (h = act(a*scale + shift), LReLU / ReLU): h is then not read -- the sign
+    act' needs is recomputed from `a` -- unless dv is wanted."""
     _need_cuda(dy, h, a, mean, var, gamma)
     N, C, H, W = _c8_dims(a)
     if tuple(dy.shape) != tuple(a.shape) or (h is not None and tuple(h.shape) != tuple(a.shape)):
@@ -514,6 +516,10 @@ def bn_act_bwd_c8(dy, h, a, act, mean, var, eps, gamma, want_dv=False, want_para
     ws = _reduce_ws(N, C, a.device)
     coef = torch.empty((3, C), device=a.device, dtype=torch.float32)
     pg = torch.empty((2, C), device=a.device, dtype=torch.float32) if want_param_grads else None
+    sc = sh = None
+    if act_affine is not None and not want_dv and act in (ACT_LRELU, ACT_RELU):
+        sc, sh = _vec(act_affine[0], C), _vec(act_affine[1], C)
+        h = None
     dv = torch.empty_like(a) if (want_dv and h is not None) else None
     g = _vec(gamma, C)
     da = torch.empty_like(a)
@@ -521,13 +527,13 @@ def bn_act_bwd_c8(dy, h, a, act, mean, var, eps, gamma, want_dv=False, want_para
         _lib.check(lib.ctl_bn_bwd_reduce_c8(dy.data_ptr(), _ptr(h), a.data_ptr(), N, C, H, W, act, mean.data_ptr(),
                                             var.data_ptr(), float(eps), _ptr(g), ws.data_ptr(), _ptr(dv), coef.data_ptr(),
                                             pg[0].data_ptr() if pg is not None else 0,
-                                            pg[1].data_ptr() if pg is not None else 0, _stream()))
+                                            pg[1].data_ptr() if pg is not None else 0, _ptr(sc), _ptr(sh), _stream()))
         if dv is not None:
             _lib.check(lib.ctl_bn_bwd_apply_c8(dv.data_ptr(), 0, a.data_ptr(), N, C, H, W, act, coef.data_ptr(),
-                                               da.data_ptr(), _stream()))
+                                               da.data_ptr(), 0, 0, _stream()))
         else:
             _lib.check(lib.ctl_bn_bwd_apply_c8(dy.data_ptr(), _ptr(h), a.data_ptr(), N, C, H, W, act, coef.data_ptr(),
-                                               da.data_ptr(), _stream()))
+                                               da.data_ptr(), _ptr(sc), _ptr(sh), _stream()))
     if want_dv and dv is None:
         dv = dy
     return da, (pg[0] if pg is not None else None), (pg[1] if pg is not None else None), dv

@@ -180,12 +180,13 @@ class _Grads(dict):
 def conv_bn_act_fwd(fw, conv, bn, x, act):
     a, scale, shift, mean, var = _conv_bn(fw, conv, bn, x)
     h = ops.scale_shift_act_c8(a, scale, shift, act)
-    return h, (x, a, h, mean, var)
+    return h, (x, a, h, mean, var, scale, shift)
 
 
 def conv_bn_act_bwd(conv, bn, act, saved, dh, grads, need_dx=True):
-    x, a, h, mean, var = saved
-    da, dg, db, _ = ops.bn_act_bwd_c8(dh, h, a, act, mean, var, bn.eps, bn.weight)
+    x, a, h, mean, var, scale, shift = saved
+    # act'(h) from sign(a*scale + shift): the backward never reads h (it stays alive only as the next layer's input)
+    da, dg, db, _ = ops.bn_act_bwd_c8(dh, h, a, act, mean, var, bn.eps, bn.weight, act_affine=(scale, shift))
     grads.add(bn.weight, dg)
     grads.add(bn.bias, db)
     if grads.wants(conv.weight):
@@ -223,8 +224,9 @@ def residual_bwd(block, saved, dout, grads):
         grads.add(seq[3].weight, _wgrad(grads, seq[3], h1, da2))
     dh1 = _dgrad(seq[3], da2)
     # BN1 + LReLU + conv1
-    x, a1, h1_, mean1, var1 = s1
-    da1, dg1, db1, _ = ops.bn_act_bwd_c8(dh1, h1_, a1, LRELU, mean1, var1, seq[1].eps, seq[1].weight)
+    x, a1, h1_, mean1, var1, scale1, shift1 = s1
+    da1, dg1, db1, _ = ops.bn_act_bwd_c8(dh1, h1_, a1, LRELU, mean1, var1, seq[1].eps, seq[1].weight,
+                                         act_affine=(scale1, shift1))
     grads.add(seq[1].weight, dg1)
     grads.add(seq[1].bias, db1)
     if grads.wants(seq[0].weight):
@@ -301,7 +303,7 @@ def encoder_fwd(enc, x, in_mode, temperature):
     scale0, shift0, mean0, var0 = _bn_mode_stats(fw, inc[1], a0)
     h0 = ops.scale_shift_act_c8(a0, scale0, shift0, LRELU)
     h, s_inc = conv_bn_act_fwd(fw, inc[3], inc[4], h0, LRELU)   # BN then F.leaky_relu (encoder_decoder.py:405)
-    tape = [(a0, h0, mean0, var0), s_inc]
+    tape = [(a0, h0, mean0, var0, scale0, shift0), s_inc]
     for blk in (enc.down1, enc.down2, enc.down3, enc.down4):
         h, s = down_fwd(fw, blk, h)
         tape.append(s)
@@ -317,8 +319,9 @@ def encoder_bwd(enc, tape, dz, grads, x, in_mode, temperature, need_dx):
     for i, blk in zip((5, 4, 3, 2), (enc.down4, enc.down3, enc.down2, enc.down1)):
         d = down_bwd(blk, tape[i], d, grads)
     dh0 = conv_bn_act_bwd(inc[3], inc[4], LRELU, tape[1], d, grads)
-    a0, h0, mean0, var0 = tape[0]
-    da0, dg0, db0, _ = ops.bn_act_bwd_c8(dh0, h0, a0, LRELU, mean0, var0, inc[1].eps, inc[1].weight)
+    a0, h0, mean0, var0, scale0, shift0 = tape[0]
+    da0, dg0, db0, _ = ops.bn_act_bwd_c8(dh0, h0, a0, LRELU, mean0, var0, inc[1].eps, inc[1].weight,
+                                         act_affine=(scale0, shift0))
     grads.add(inc[1].weight, dg0)
     grads.add(inc[1].bias, db0)
     if grads.wants(inc[0].weight):

@@ -211,10 +211,15 @@ int ctl_channel_sums_c8(const void* x, int64_t N, int64_t C, int64_t H, int64_t 
  * of the forward (ctl_bn_batch_affine_c8 mean_out / var_out).  act in {NONE, LRELU, RELU}. */
 int ctl_bn_bwd_reduce_c8(const void* dy, const void* h, const void* a, int64_t N, int64_t C, int64_t H, int64_t W,
                          int act, const float* mean, const float* var, float eps, const float* gamma, void* workspace,
-                         void* dv_out, float* coef, float* dgamma, float* dbeta, void* stream);
-/* stage 2: da = coef0*dv + coef1*a + coef2 with dv = dy * act'(h) (h NULL: dy is already dv) */
+                         void* dv_out, float* coef, float* dgamma, float* dbeta, const float* act_scale,
+                         const float* act_shift, void* stream);
+/* stage 2: da = coef0*dv + coef1*a + coef2 with dv = dy * act'(h) (h NULL: dy is already dv).
+ * Both stages: when h is NULL and (act_scale, act_shift) -- the forward's folded BatchNorm affine, fp32 [C] each -- are
+ * given, h = act(a*act_scale + act_shift) is not read at all: act' only needs the sign of that expression (LReLU / ReLU),
+ * which is recomputed from `a` (one tensor read less per stage). */
 int ctl_bn_bwd_apply_c8(const void* dy, const void* h, const void* a, int64_t N, int64_t C, int64_t H, int64_t W,
-                        int act, const float* coef, void* da, void* stream);
+                        int act, const float* coef, void* da, const float* act_scale, const float* act_shift,
+                        void* stream);
 /* dv = dy * act'(h) */
 int ctl_act_bwd_c8(const void* dy, const void* h, int64_t N, int64_t C, int64_t H, int64_t W, int act, void* dv,
                    void* stream);

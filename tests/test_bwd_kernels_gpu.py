@@ -142,6 +142,12 @@ def test_bn_act_backward(ops, act, C, N, H, W):
                                      want_param_grads=False)
     _cmp(ops.c8_to_nchw(da2), af.grad, 2e-2, "da (no dv)")
     if act:
+        # act' from sign(a*scale + shift) instead of reading h: bit-identical to the h-reading form
+        da3, dg3, db3, _ = ops.bn_act_bwd_c8(ops.nchw_to_c8(dy), None, ac, act, mean, var, 1e-5, gamma,
+                                             act_affine=(scale, shift))
+        da4, dg4, db4, _ = ops.bn_act_bwd_c8(ops.nchw_to_c8(dy), h, ac, act, mean, var, 1e-5, gamma)
+        assert torch.equal(da3, da4) and torch.equal(dg3, dg4) and torch.equal(db3, db4)
+    if act:
         _cmp(ops.c8_to_nchw(ops.act_bwd_c8(ops.nchw_to_c8(dy), h, act)), dy.float() * slope, 1e-2, "act_bwd")
 
 

@@ -77,7 +77,10 @@ def test_graph_replay_matches_eager_steps(pkg, cfgs):
     for step, (g, w) in enumerate(zip(got, want)):
         for key in w:
             assert np.isfinite(g[key])
-            assert abs(g[key] - w[key]) <= 1e-2 * max(1.0, abs(w[key])), (step, key, g[key], w[key])
+            # the hard-example losses see the masks: bf16 noise in dL/dz can reorder a near-tie of the top-k selection in
+            # one of the 4 samples (observed: 1-2 % of such a loss, at any step) -- the wide bar is for those only
+            tol = 5e-2 if ('hard' in key or key == 'loss') else 1e-2
+            assert abs(g[key] - w[key]) <= tol * max(1.0, abs(w[key])), (step, key, g[key], w[key])
     # the perturbed examples of the replayed steps: same masks (k, draws) -> same images up to the run-to-run noise of
     # the weights (a wrong k or draw gives O(1)).  The bit-exact check of the
     # device-resident parameters is test_step_params_reach_the_kernels.
