@@ -126,49 +126,65 @@ __device__ __forceinline__ void conv_epilogue(const ConvParams& p, const uint32_
 
   int acc = 0;
   uint32_t acc_phase = 0;
-  for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
-    const int img = t / tiles_per_img;
-    const int rem = t - img * tiles_per_img;
+  // per-tile geometry of this thread's pixel
+  struct Geo { int img, y, xb; bool y_ok; int64_t pix; };
+  auto geometry = [&](int t) -> Geo {
+    Geo g;
+    g.img = t / tiles_per_img;
+    const int rem = t - g.img * tiles_per_img;
     const int ty = rem / p.tiles_x, tx = rem - ty * p.tiles_x;
-    const int y = ty * kTileH + py;
-    const int xb = tx * (8 * MT) + px;
+    g.y = ty * kTileH + py;
+    g.xb = tx * (8 * MT) + px;
     // plain geometry (stride 1, no ConvTranspose scatter): one 64-bit base per tile, items differ by constants
-    const bool y_ok = y < p.H && !(p.diag & 4);
-    const int64_t pix = ((int64_t)img * (p.Cout >> 3) + (n0 >> 3)) * plane + ((int64_t)y * p.W + xb) * 8;
-    // element offset of plane h8 of item u (the residual shares the output's geometry)
-    auto offset_of = [&](int u, int h8, bool& valid) -> int64_t {
-      const int item = first_item + 2 * u;
-      const int mt = item / kChunks, c0 = (item - mt * kChunks) * 16;
-      if (!GEN) {
-        valid = y_ok && xb + mt * 8 < p.W;
-        return pix + mt * 64 + (int64_t)((c0 >> 3) + h8) * plane;
+    g.y_ok = g.y < p.H && !(p.diag & 4);
+    g.pix = ((int64_t)g.img * (p.Cout >> 3) + (n0 >> 3)) * plane + ((int64_t)g.y * p.W + g.xb) * 8;
+    return g;
+  };
+  // element offset of plane h8 of item u (the residual shares the output's geometry)
+  auto offset_of = [&](const Geo& g, int u, int h8, bool& valid) -> int64_t {
+    const int item = first_item + 2 * u;
+    const int mt = item / kChunks, c0 = (item - mt * kChunks) * 16;
+    if (!GEN) {
+      valid = g.y_ok && g.xb + mt * 8 < p.W;
+      return g.pix + mt * 64 + (int64_t)((c0 >> 3) + h8) * plane;
+    }
+    const int y = g.y, x = g.xb + mt * 8;
+    valid = y < p.H && x < p.W && !(p.diag & 4);
+    const int n = n0 + c0 + 8 * h8;              // GEMM column of this plane's first channel
+    if (p.up2x) {
+      const int cq = p.Cout >> 2, qd = n / cq, co = n - qd * cq;       // n = (dy*2+dx)*Cout/4 + co
+      const int y2 = 2 * y + (qd >> 1), x2 = 2 * x + (qd & 1);
+      return ((int64_t)g.img * (cq >> 3) + (co >> 3)) * (plane * 4) + ((int64_t)y2 * (2 * Wo) + x2) * 8;
+    }
+    int yo = y, xo = x;
+    if (p.subsample == 2) { valid = valid && !((y | x) & 1); yo = y >> 1; xo = x >> 1; }
+    return ((int64_t)g.img * (p.Cout >> 3) + (n >> 3)) * plane + ((int64_t)yo * Wo + xo) * 8;
+  };
+  const bool has_res = RES && (!GEN || p.res != nullptr);     // the GEN variant serves both
+  // the residual pixels of a tile are requested ONE TILE AHEAD (the addresses do not depend on the accumulator): two
+  // tiles' worth of 16-byte loads per thread are in flight while the current tile is converted and stored
+  auto request_residual = [&](const Geo& g, uint4 (&dst)[RES ? kPer : 1][2]) {
+#pragma unroll
+    for (int u = 0; u < (RES ? kPer : 1); ++u) {
+#pragma unroll
+      for (int h8 = 0; h8 < 2; ++h8) {
+        dst[u][h8] = make_uint4(0, 0, 0, 0);
+        bool valid;
+        const int64_t off = offset_of(g, u, h8, valid);
+        if (first_item + 2 * u < kItems && valid) dst[u][h8] = __ldg(reinterpret_cast<const uint4*>(p.res + off));
       }
-      const int x = xb + mt * 8;
-      valid = y < p.H && x < p.W && !(p.diag & 4);
-      const int n = n0 + c0 + 8 * h8;              // GEMM column of this plane's first channel
-      if (p.up2x) {
-        const int cq = p.Cout >> 2, qd = n / cq, co = n - qd * cq;       // n = (dy*2+dx)*Cout/4 + co
-        const int y2 = 2 * y + (qd >> 1), x2 = 2 * x + (qd & 1);
-        return ((int64_t)img * (cq >> 3) + (co >> 3)) * (plane * 4) + ((int64_t)y2 * (2 * Wo) + x2) * 8;
-      }
-      int yo = y, xo = x;
-      if (p.subsample == 2) { valid = valid && !((y | x) & 1); yo = y >> 1; xo = x >> 1; }
-      return ((int64_t)img * (p.Cout >> 3) + (n >> 3)) * plane + ((int64_t)yo * Wo + xo) * 8;
-    };
+    }
+  };
 
-    const bool has_res = RES && (!GEN || p.res != nullptr);     // the GEN variant serves both
-    uint4 rr[RES ? kPer : 1][2];
-    if (has_res) {
-#pragma unroll
-      for (int u = 0; u < kPer; ++u) {
-#pragma unroll
-        for (int h8 = 0; h8 < 2; ++h8) {
-          rr[u][h8] = make_uint4(0, 0, 0, 0);
-          bool valid;
-          const int64_t off = offset_of(u, h8, valid);
-          if (first_item + 2 * u < kItems && valid) rr[u][h8] = __ldg(reinterpret_cast<const uint4*>(p.res + off));
-        }
-      }
+  uint4 rr[RES ? kPer : 1][2], rr_next[RES ? kPer : 1][2];
+  Geo geo = geometry(blockIdx.x);
+  if (has_res) request_residual(geo, rr);
+  for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
+    const int t_next = t + gridDim.x;
+    Geo geo_next = geo;
+    if (t_next < num_tiles) {
+      geo_next = geometry(t_next);
+      if (has_res) request_residual(geo_next, rr_next);
     }
 
     mbar_wait(&acc_full[acc], acc_phase);
@@ -198,8 +214,8 @@ __device__ __forceinline__ void conv_epilogue(const ConvParams& p, const uint32_
           const int c0 = (item % kChunks) * 16;
           bool valid;
           int64_t off[2];
-          off[0] = offset_of(u, 0, valid);
-          off[1] = offset_of(u, 1, valid);
+          off[0] = offset_of(geo, u, 0, valid);
+          off[1] = offset_of(geo, u, 1, valid);
           if (valid) {
             float f[16];
 #pragma unroll
@@ -255,6 +271,11 @@ __device__ __forceinline__ void conv_epilogue(const ConvParams& p, const uint32_
       }
     }
     if (++acc == kAccStages) { acc = 0; acc_phase ^= 1; }
+    geo = geo_next;
+    if (RES) {
+#pragma unroll
+      for (int u = 0; u < kPer; ++u) { rr[u][0] = rr_next[u][0]; rr[u][1] = rr_next[u][1]; }
+    }
   }
   if (STATS) {
     // kChunks <= 2 (checked on the host): this thread's chunk is fixed -- chunk `half` when there are two, else 0.

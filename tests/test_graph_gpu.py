@@ -74,23 +74,24 @@ def test_graph_replay_matches_eager_steps(pkg, cfgs):
     # host generators consumed identically
     assert got_state[0] == want_state[0]
     assert all(np.array_equal(a, b) for a, b in zip(got_state[1], want_state[1]))
+    # Strict window = the two eager steps and the first two REPLAYED steps: everything agrees to run-to-run noise.  Later
+    # steps are only sanity-checked: the scenario is bistable there -- on a 4x4 latent one near-tie of the top-k selection
+    # (decided by fp32-atomic ordering noise in the weight gradients) flips 1/16 of a shape mask, and from then on the two
+    # runs follow different trajectories.  tools/graph_divergence.py shows the same fork between two EAGER runs
+    # (profiles/r1_graph_divergence_session8.txt: differences are exactly 0 for 12 steps, then 0.17 / 0.42 -- identical
+    # values in an eager and three graphed runs).
+    strict = 4
     for step, (g, w) in enumerate(zip(got, want)):
         for key in w:
             assert np.isfinite(g[key])
-            # the hard-example losses see the masks: bf16 noise in dL/dz can reorder a near-tie of the top-k selection in
-            # one of the 4 samples (observed: 1-2 % of such a loss, at any step) -- the wide bar is for those only
-            tol = 5e-2 if ('hard' in key or key == 'loss') else 1e-2
+            tol = 2e-3 if step < strict else 0.25
             assert abs(g[key] - w[key]) <= tol * max(1.0, abs(w[key])), (step, key, g[key], w[key])
-    # the perturbed examples of the replayed steps: same masks (k, draws) -> same images up to the run-to-run noise of
-    # the weights (a wrong k or draw gives O(1)).  The bit-exact check of the
-    # device-resident parameters is test_step_params_reach_the_kernels.
-    # Robust form: a near-tie in one sample's top-k selection may flip one mask entry under the run-to-run noise, so the
-    # bar is on the MEDIAN over the samples of the per-sample relative error.
-    for step in range(2, steps):
+    # the perturbed examples of the replayed steps: same masks (k, draws) -> same images (a wrong k or draw gives O(1)
+    # on every sample).  The bit-exact check of the device-resident parameters is test_step_params_reach_the_kernels.
+    for step in range(2, strict):
         for a, b in zip(got_p[step], want_p[step]):
             d = (a - b).flatten(1).norm(dim=1) / b.flatten(1).norm(dim=1).clamp_min(1e-6)
-            rel = float(d.median())
-            assert rel < 0.05, (step, rel, d.tolist())
+            assert float(d.max()) < 0.02, (step, d.tolist())
 
 
 def test_step_params_reach_the_kernels(pkg):
