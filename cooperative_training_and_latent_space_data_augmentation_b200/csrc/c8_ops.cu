@@ -227,6 +227,42 @@ scale_shift_act_c8_kernel(const uint4* __restrict__ x, uint4* __restrict__ y, co
   }
 }
 
+// y = act(x*scale[c] + shift[c] + low[.., h/2, w/2]): the tail of a nearest-x2 residual up block whose 1x1 shortcut was
+// evaluated BEFORE the up-sampling (conv1x1(up(x)) == up(conv1x1(x))).  One thread per LOW-resolution pixel: 16 B of
+// `low`, a 2x2 block of x in, a 2x2 block of y out.  scale / shift may be NULL (1 / 0).
+__global__ void __launch_bounds__(kT)
+scale_shift_upadd_act_c8_kernel(const uint4* __restrict__ x, const uint4* __restrict__ low, uint4* __restrict__ y,
+                                const float* __restrict__ scale, const float* __restrict__ shift, int64_t planes, int C8,
+                                int Hl, int Wl, int act) {
+  const int64_t total = planes * Hl * Wl;
+  for (int64_t i = (int64_t)blockIdx.x * kT + threadIdx.x; i < total; i += (int64_t)gridDim.x * kT) {
+    const int64_t pl = i / ((int64_t)Hl * Wl);
+    const int pix = (int)(i - pl * Hl * Wl);
+    const int yy = pix / Wl, xx = pix - yy * Wl;
+    const int c0 = (int)(pl % C8) * 8;
+    float sc[8], sh[8], lo[8];
+    unpack8(__ldg(low + i), lo);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      sc[j] = scale ? __ldg(scale + c0 + j) : 1.0f;
+      sh[j] = (shift ? __ldg(shift + c0 + j) : 0.0f) + lo[j];
+    }
+    const int64_t base = pl * 4 * Hl * Wl + (int64_t)(2 * yy) * (2 * Wl) + 2 * xx;
+    const int64_t offs[4] = {base, base + 1, base + 2 * Wl, base + 2 * Wl + 1};
+    uint4 in[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) in[q] = __ldcs(x + offs[q]);
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      float f[8];
+      unpack8(in[q], f);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) f[j] = act_fn(f[j] * sc[j] + sh[j], act);
+      y[offs[q]] = pack8(f);
+    }
+  }
+}
+
 // ------------------------------------------------------------------------------------------------ weight packing
 // fp32 nn.Conv2d weight [Cout][Cin][k][k] -> bf16 [Cout'/NT][taps][Cin'/8][NT][8] (the K-major core-matrix order of
 // conv_tc.cu).  transposed == 0: the forward weight (Cout' = Cout, Cin' = Cin).  transposed == 1: the weight of the
@@ -349,6 +385,19 @@ extern "C" int ctl_upsample2x_c8(const void* x, int64_t N, int64_t C, int64_t H,
   upsample2x_c8_kernel<<<grid_for(planes * H * W), kT, 0, (cudaStream_t)stream>>>((const uint4*)x, (uint4*)y, planes,
                                                                                 (int)H, (int)W);
   CTL_CUDA_OK(cudaGetLastError(), "upsample2x launch");
+  return CTL_OK;
+}
+
+extern "C" int ctl_scale_shift_upadd_act_c8(const void* x, int64_t N, int64_t C, int64_t H, int64_t W, const float* scale,
+                                            const float* shift, const void* low, int act, void* y, void* stream) {
+  CTL_REQUIRE(x && y && low && N > 0 && C > 0 && C % 8 == 0 && H > 0 && W > 0 && H % 2 == 0 && W % 2 == 0, CTL_ERR_INVALID,
+              "ctl_scale_shift_upadd_act_c8: bad arguments (H and W must be even)");
+  CTL_REQUIRE(act >= CTL_ACT_NONE && act <= CTL_ACT_SIGMOID, CTL_ERR_INVALID, "unknown activation %d", act);
+  if (sm_count() < 0) return CTL_ERR_CUDA;
+  const int64_t planes = N * (C / 8);
+  scale_shift_upadd_act_c8_kernel<<<grid_for(planes * (H / 2) * (W / 2)), kT, 0, (cudaStream_t)stream>>>(
+      (const uint4*)x, (const uint4*)low, (uint4*)y, scale, shift, planes, (int)(C / 8), (int)(H / 2), (int)(W / 2), act);
+  CTL_CUDA_OK(cudaGetLastError(), "scale_shift_upadd_act launch");
   return CTL_OK;
 }
 

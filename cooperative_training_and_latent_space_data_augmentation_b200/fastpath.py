@@ -106,18 +106,24 @@ def double_conv(seq, x, mode, final_act=ops.ACT_NONE):
     return conv_bn_act(seq[3], seq[4], y, final_act, mode)
 
 
-def residual_block(block, xr, mode):
-    """xr: resampled input (C8).  out = LReLU(conv_input(xr) + BN2(conv2(LReLU(BN1(conv1(xr))))))."""
+def residual_block(block, xr, mode, x_low=None):
+    """xr: resampled input (C8).  out = LReLU(conv_input(xr) + BN2(conv2(LReLU(BN1(conv1(xr)))))).
+    x_low: the input before a nearest x2 up-sampling -- the 1x1 shortcut is then taken at the low resolution
+    (conv1x1(up(x)) == up(conv1x1(x))) and added, up-sampled on the fly, together with BN2 + LReLU."""
     seq = block.conv
+    ci = block.conv_input
     y1 = conv_bn_act(seq[0], seq[1], xr, ops.ACT_LRELU, mode)
     if mode == 'eval':
         s2, t2 = _fold_eval(seq[3], seq[4])
         y2 = _conv(seq[3], y1, scale=s2, shift=t2)
-        return _conv(block.conv_input, xr, shift=block.conv_input.bias, res=y2, act=ops.ACT_LRELU)
+        if x_low is not None:
+            return ops.scale_shift_upadd_act_c8(y2, None, None, _conv(ci, x_low, shift=ci.bias), ops.ACT_LRELU)
+        return _conv(ci, xr, shift=ci.bias, res=y2, act=ops.ACT_LRELU)
     y2 = _conv(seq[3], y1, shift=seq[3].bias)
     s2, t2 = _bn_batch(seq[4], y2, mode)
-    return _conv(block.conv_input, xr, shift=block.conv_input.bias, res=y2, res_scale=s2, res_shift=t2,
-                 act=ops.ACT_LRELU)
+    if x_low is not None:
+        return ops.scale_shift_upadd_act_c8(y2, s2, t2, _conv(ci, x_low, shift=ci.bias), ops.ACT_LRELU)
+    return _conv(ci, xr, shift=ci.bias, res=y2, res_scale=s2, res_shift=t2, act=ops.ACT_LRELU)
 
 
 def down_block(block, x, mode):
@@ -127,11 +133,10 @@ def down_block(block, x, mode):
 
 def up_block(block, x, mode):
     if block.up_type == 'NN':
-        xu = ops.upsample2x_c8(x)
-    else:
-        up = block.up
-        wp = _packed(up.weight, ops.pack_convtranspose2x2_weight)
-        xu = ops.conv2d_c8(x, wp, 4 * up.out_channels, 1, up2x=True, shift=up.bias.detach().repeat(4))
+        return residual_block(block, ops.upsample2x_c8(x), mode, x_low=x)
+    up = block.up
+    wp = _packed(up.weight, ops.pack_convtranspose2x2_weight)
+    xu = ops.conv2d_c8(x, wp, 4 * up.out_channels, 1, up2x=True, shift=up.bias.detach().repeat(4))
     return residual_block(block, xu, mode)
 
 

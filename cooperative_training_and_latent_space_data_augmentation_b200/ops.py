@@ -446,6 +446,22 @@ def scale_shift_act_c8(x, scale, shift, act=ACT_NONE, inplace=False):
     return y
 
 
+def scale_shift_upadd_act_c8(x, scale, shift, low, act=ACT_NONE):
+    """act(x*scale + shift + nearest_up2(low)): the tail of a nearest-x2 residual up block (shortcut taken at low
+    resolution).  x: C8 [N,C/8,H,W,8]; low: C8 [N,C/8,H/2,W/2,8]; scale / shift: [C] or None (1 / 0)."""
+    _need_cuda(x, low, scale, shift)
+    N, C, H, W = _c8_dims(x)
+    if tuple(low.shape) != (N, C // 8, H // 2, W // 2, 8) or H % 2 or W % 2:
+        raise ValueError("low must be C8 %s for x %s" % ((N, C // 8, H // 2, W // 2, 8), tuple(x.shape)))
+    y = torch.empty_like(x)
+    sc = _vec(scale, C) if scale is not None else None
+    sh = _vec(shift, C) if shift is not None else None
+    with torch.cuda.device(x.device):
+        _lib.check(_lib.load().ctl_scale_shift_upadd_act_c8(x.data_ptr(), N, C, H, W, _ptr(sc), _ptr(sh), low.data_ptr(),
+                                                            act, y.data_ptr(), _stream()))
+    return y
+
+
 # ------------------------------------------------------------------------------------------------ backward kernels
 def pack_conv_weight_dgrad(weight):
     """Packed weights of the INPUT-gradient convolution of a stride-1 (or zero-stuffed stride-2) Conv2d:

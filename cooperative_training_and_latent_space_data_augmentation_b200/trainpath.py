@@ -195,18 +195,28 @@ def conv_bn_act_bwd(conv, bn, act, saved, dh, grads, need_dx=True):
 
 
 # ------------------------------------------------------------------------------------------------ residual body
-def residual_fwd(fw, block, xr):
-    """out = LReLU(conv_input(xr) + BN2(conv2(LReLU(BN1(conv1(xr))))))   (encoder_decoder.py:54-57, :334-337)"""
+def residual_fwd(fw, block, xr, x_low=None):
+    """out = LReLU(conv_input(xr) + BN2(conv2(LReLU(BN1(conv1(xr))))))   (encoder_decoder.py:54-57, :334-337).
+    x_low: the block input BEFORE a nearest x2 up-sampling (xr = up(x_low)).  A 1x1 convolution commutes with nearest
+    up-sampling, so the shortcut is then taken at the low resolution (a quarter of the pixels) and added, up-sampled on
+    the fly, by the kernel that applies BN2 + LReLU."""
     seq = block.conv
     h1, s1 = conv_bn_act_fwd(fw, seq[0], seq[1], xr, LRELU)
     a2, scale2, shift2, mean2, var2 = _conv_bn(fw, seq[3], seq[4], h1)
     ci = block.conv_input
     wp = _packed(ci.weight, ops.pack_conv_weight)
-    out = ops.conv2d_c8(xr, wp, ci.out_channels, 1, shift=ci.bias, res=a2, res_scale=scale2, res_shift=shift2, act=LRELU)
+    if x_low is not None:
+        c = ops.conv2d_c8(x_low, wp, ci.out_channels, 1, shift=ci.bias)
+        out = ops.scale_shift_upadd_act_c8(a2, scale2, shift2, c, LRELU)
+    else:
+        out = ops.conv2d_c8(xr, wp, ci.out_channels, 1, shift=ci.bias, res=a2, res_scale=scale2, res_shift=shift2,
+                            act=LRELU)
     return out, (s1, a2, mean2, var2, out)
 
 
-def residual_bwd(block, saved, dout, grads):
+def residual_bwd(block, saved, dout, grads, x_low=None):
+    """Returns (gradient w.r.t. xr, dc): dc is None unless x_low was given -- then the shortcut's share of the input
+    gradient still has to be added at the LOW resolution by the caller: dgrad(conv_input, dc)."""
     s1, a2, mean2, var2, out = saved
     xr, h1 = s1[0], s1[2]
     seq, ci = block.conv, block.conv_input
@@ -215,10 +225,17 @@ def residual_bwd(block, saved, dout, grads):
     da2, dg2, db2, dpre = ops.bn_act_bwd_c8(dout, out, a2, LRELU, mean2, var2, bn2.eps, bn2.weight, want_dv=True)
     grads.add(bn2.weight, dg2)
     grads.add(bn2.bias, db2)
-    if grads.wants(ci.weight):
-        grads.add(ci.weight, _wgrad(grads, ci, xr, dpre))
-        grads.add(ci.bias, db2)                             # sum over pixels of dpre == dbeta of BN2
-    dxr = _dgrad(ci, dpre)
+    dc = dxr = None
+    if x_low is not None:
+        dc = ops.downsample2x_sum_c8(dpre)                  # backward of the on-the-fly nearest up-sampling
+        if grads.wants(ci.weight):
+            grads.add(ci.weight, _wgrad(grads, ci, x_low, dc))
+            grads.add(ci.bias, db2)
+    else:
+        if grads.wants(ci.weight):
+            grads.add(ci.weight, _wgrad(grads, ci, xr, dpre))
+            grads.add(ci.bias, db2)                             # sum over pixels of dpre == dbeta of BN2
+        dxr = _dgrad(ci, dpre)
     # conv2
     if grads.wants(seq[3].weight):
         grads.add(seq[3].weight, _wgrad(grads, seq[3], h1, da2))
@@ -231,7 +248,7 @@ def residual_bwd(block, saved, dout, grads):
     grads.add(seq[1].bias, db1)
     if grads.wants(seq[0].weight):
         grads.add(seq[0].weight, _wgrad(grads, seq[0], xr, da1))
-    return _dgrad(seq[0], da1, res=dxr)
+    return _dgrad(seq[0], da1, res=dxr), dc
 
 
 # ------------------------------------------------------------------------------------------------ down / up blocks
@@ -243,7 +260,7 @@ def down_fwd(fw, block, x):
 
 def down_bwd(block, saved, dout, grads, need_dx=True):
     x, s = saved
-    dxd = residual_bwd(block, s, dout, grads)
+    dxd, _ = residual_bwd(block, s, dout, grads)
     down = block.down
     want_w = grads.wants(down.weight)
     if not (want_w or need_dx):
@@ -262,19 +279,24 @@ def _convT_tap_weight(up, d):
 def up_fwd(fw, block, x):
     if block.up_type == 'NN':
         xu = ops.upsample2x_c8(x)
+        out, s = residual_fwd(fw, block, xu, x_low=x)
     else:
         up = block.up
         wp = _packed(up.weight, ops.pack_convtranspose2x2_weight)
         xu = ops.conv2d_c8(x, wp, 4 * up.out_channels, 1, up2x=True, shift=up.bias.detach().repeat(4))
-    out, s = residual_fwd(fw, block, xu)
+        out, s = residual_fwd(fw, block, xu)
     return out, (x, s)
 
 
 def up_bwd(block, saved, dout, grads, need_dx=True):
     x, s = saved
-    dxu = residual_bwd(block, s, dout, grads)
     if block.up_type == 'NN':
-        return ops.downsample2x_sum_c8(dxu) if need_dx else None
+        dxu, dc = residual_bwd(block, s, dout, grads, x_low=x)
+        if not need_dx:
+            return None
+        # main branch back through the up-sampling (2x2 sums) + the shortcut's input gradient, both at low resolution
+        return _dgrad(block.conv_input, dc, res=ops.downsample2x_sum_c8(dxu))
+    dxu, _ = residual_bwd(block, s, dout, grads)
     up = block.up
     want_w = grads.wants(up.weight)
     if not (want_w or need_dx):

@@ -186,6 +186,11 @@ int ctl_bn_affine_from_sums(const double* sums, int64_t C, int64_t count, const 
 /* y = act(x*scale[c] + shift[c]) on C8 tensors (BatchNorm apply + LeakyReLU in one pass). */
 int ctl_scale_shift_act_c8(const void* x, int64_t N, int64_t C, int64_t H, int64_t W, const float* scale,
                            const float* shift, int act, void* y, void* stream);
+/* y = act(x*scale[c] + shift[c] + up2(low)): x, y C8 [N,C/8,H,W,8], low C8 [N,C/8,H/2,W/2,8] (nearest x2 on the fly).
+ * Tail of res_up_family with nn.UpsamplingNearest2d (encoder_decoder.py:294-296, :334-337) once the 1x1 shortcut is taken
+ * at the low resolution: conv1x1(up(x)) == up(conv1x1(x)).  scale / shift may be NULL (1 / 0); H, W even. */
+int ctl_scale_shift_upadd_act_c8(const void* x, int64_t N, int64_t C, int64_t H, int64_t W, const float* scale,
+                                 const float* shift, const void* low, int act, void* y, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
  * Backward of the conv blocks (the reference leaves all of it to torch autograd over the modules of

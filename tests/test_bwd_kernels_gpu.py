@@ -199,3 +199,21 @@ def test_stem_backward(ops, cin, in_mode):
     dyc = ops.nchw_to_c8(dy)
     _cmp(ops.stem_wgrad_c8(dyc, x, cin, in_mode=in_mode, temperature=2.0), wf.grad, 2e-3, "stem wgrad")
     _cmp(ops.stem_dgrad_c8(dyc, x, w, in_mode=in_mode, temperature=2.0), xf.grad, 2e-3, "stem dgrad")
+
+
+@pytest.mark.parametrize("act", [0, 1])
+def test_scale_shift_upadd_act(ops, act):
+    """act(x*scale + shift + nearest_up2(low)) against torch on the same bf16 operands (one bf16 rounding of the result)."""
+    g = torch.Generator(device="cuda").manual_seed(21 + act)
+    x = _bf(3, 24, 10, 12, gen=g)
+    low = _bf(3, 24, 5, 6, gen=g)
+    scale = 1 + 0.2 * torch.randn(24, device="cuda", generator=g)
+    shift = 0.3 * torch.randn(24, device="cuda", generator=g)
+    want = x.float() * scale.view(1, -1, 1, 1) + shift.view(1, -1, 1, 1) + F.interpolate(low.float(), scale_factor=2, mode='nearest')
+    if act:
+        want = F.leaky_relu(want, 0.2)
+    got = ops.scale_shift_upadd_act_c8(ops.nchw_to_c8(x), scale, shift, ops.nchw_to_c8(low), act)
+    _cmp(ops.c8_to_nchw(got), want, 1e-2, "upadd")
+    got1 = ops.scale_shift_upadd_act_c8(ops.nchw_to_c8(x), None, None, ops.nchw_to_c8(low), act)
+    want1 = x.float() + F.interpolate(low.float(), scale_factor=2, mode='nearest')
+    _cmp(ops.c8_to_nchw(got1), F.leaky_relu(want1, 0.2) if act else want1, 1e-2, "upadd (no affine)")
