@@ -11,6 +11,7 @@
 //   MyDecoder.final_conv (+Sigmoid)         medseg/models/ebm/encoder_decoder.py:439-452
 //   MyEncoder.inc[0] + construct_input      medseg/models/ebm/encoder_decoder.py:370-371, medseg/common_utils/basic_operations.py:110-158
 #include <algorithm>
+#include <cmath>
 
 #include "ctl_common.cuh"
 
@@ -43,13 +44,22 @@ __device__ __forceinline__ float act_slope(float h, int act) {
   }
 }
 
-// plane split: enough CTAs to fill the GPU even when N*C/8 is small (16 channels at 224x224: 128 planes of 800 KB)
-inline int plane_splits(int64_t planes, int64_t HW) {
-  const int64_t want = (int64_t)sm_count() * 6;
-  int64_t s = ceil_div(want, planes);
-  const int64_t max_s = std::max<int64_t>(1, HW / (kT * 4));
-  s = std::min(s, max_s);
-  return (int)std::max<int64_t>(1, std::min<int64_t>(s, 64));
+// plane split: enough CTAs to fill the GPU even when N*C/8 is small (16 channels at 224x224: 128 planes of 800 KB), and
+// a CTA count that fills WHOLE waves: with `resident` CTA slots on the device, planes*splits = 2.02 waves runs as three
+// (measured: 896 CTAs on 444 slots cost +50 %).  Smallest split count in [1, 64] that gives at least one full wave and
+// wastes < 6 % of the last one; else the most efficient candidate.
+inline int plane_splits(int64_t planes, int64_t HW, int ctas_per_sm) {
+  const int64_t resident = (int64_t)sm_count() * std::max(1, ctas_per_sm);
+  const int64_t max_s = std::max<int64_t>(1, std::min<int64_t>(64, HW / (kT * 4)));
+  int best = 1;
+  double best_eff = 0.0;
+  for (int64_t s = 1; s <= max_s; ++s) {
+    const double waves = (double)(planes * s) / (double)resident;
+    const double eff = waves / std::ceil(waves);
+    if (eff > best_eff + 1e-9) { best_eff = eff; best = (int)s; }
+    if (waves >= 1.0 && eff >= 0.94) return (int)s;
+  }
+  return best;
 }
 
 // ------------------------------------------------------------------------------------------------ reductions
@@ -57,7 +67,7 @@ inline int plane_splits(int64_t planes, int64_t HW) {
 // MODE 1: dv = dy * act'(h); sum dv, sum dv*a (BatchNorm backward); optionally materialises dv.
 // partial: double [(split*planes + plane)*8 + j][2]
 template <int MODE>
-__global__ void __launch_bounds__(kT)
+__global__ void __launch_bounds__(kT, 3)
 plane_reduce_kernel(const uint4* __restrict__ x, const uint4* __restrict__ h, const uint4* __restrict__ a,
                     uint4* __restrict__ dv_out, double* __restrict__ partial, int64_t planes, int64_t HW, int splits,
                     int act, const float* __restrict__ act_scale, const float* __restrict__ act_shift, int C8) {
@@ -75,19 +85,19 @@ plane_reduce_kernel(const uint4* __restrict__ x, const uint4* __restrict__ h, co
   float s[8], q[8];
 #pragma unroll
   for (int j = 0; j < 8; ++j) { s[j] = 0.0f; q[j] = 0.0f; }
-  for (int64_t i = lo + threadIdx.x; i < hi; i += kT) {
-    const int64_t idx = plane * HW + i;
+  const bool from_a = MODE == 1 && h == nullptr && act_scale != nullptr;
+  auto accumulate = [&](const int64_t idx, const uint4 xr, const uint4 ar, const uint4 hr) {
     float f[8];
-    unpack8(__ldcs(x + idx), f);
+    unpack8(xr, f);
     if (MODE == 0) {
 #pragma unroll
       for (int j = 0; j < 8; ++j) { s[j] += f[j]; q[j] = fmaf(f[j], f[j], q[j]); }
     } else {
       float av[8];
-      unpack8(__ldg(a + idx), av);
+      unpack8(ar, av);
       if (h != nullptr) {
         float hv[8];
-        unpack8(__ldg(h + idx), hv);
+        unpack8(hr, hv);
 #pragma unroll
         for (int j = 0; j < 8; ++j) f[j] *= act_slope(hv[j], act);
         if (dv_out != nullptr) {
@@ -95,13 +105,31 @@ plane_reduce_kernel(const uint4* __restrict__ x, const uint4* __restrict__ h, co
           dv_out[idx] = packed;
           unpack8(packed, f);                     // reduce what the consumers will read (bf16-rounded)
         }
-      } else if (act_scale != nullptr) {
+      } else if (from_a) {
 #pragma unroll
         for (int j = 0; j < 8; ++j) f[j] *= act_slope(av[j] * asc[j] + ash[j], act);
       }
 #pragma unroll
       for (int j = 0; j < 8; ++j) { s[j] += f[j]; q[j] = fmaf(f[j], av[j], q[j]); }
     }
+  };
+  // two positions per iteration, every load issued before the first use: with ~80 registers only three CTAs fit an SM,
+  // and one position's 2-3 16-byte loads per thread left the HBM pipe half empty (2.3 TB/s)
+  const uint4 zero = make_uint4(0, 0, 0, 0);
+  for (int64_t i = lo + threadIdx.x; i < hi; i += 2 * kT) {
+    const int64_t idx0 = plane * HW + i, idx1 = idx0 + kT;
+    const bool two = i + kT < hi;
+    const uint4 x0 = __ldcs(x + idx0);
+    const uint4 a0 = MODE == 1 ? __ldg(a + idx0) : zero;
+    const uint4 h0 = (MODE == 1 && h != nullptr) ? __ldg(h + idx0) : zero;
+    uint4 x1 = zero, a1 = zero, h1 = zero;
+    if (two) {
+      x1 = __ldcs(x + idx1);
+      if (MODE == 1) a1 = __ldg(a + idx1);
+      if (MODE == 1 && h != nullptr) h1 = __ldg(h + idx1);
+    }
+    accumulate(idx0, x0, a0, h0);
+    if (two) accumulate(idx1, x1, a1, h1);
   }
   __shared__ double red[kT / 32][16];
   double ds[8], dq[8];
@@ -126,6 +154,18 @@ plane_reduce_kernel(const uint4* __restrict__ x, const uint4* __restrict__ h, co
     const int j = threadIdx.x & 7, second = threadIdx.x >> 3;
     partial[(((int64_t)split * planes + plane) * 8 + j) * 2 + second] = t;
   }
+}
+
+// resident CTAs of the reduction per SM (register-limited; queried once per variant)
+template <int MODE>
+int reduce_ctas_per_sm() {
+  static int cached = 0;
+  if (cached <= 0) {
+    int n = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, plane_reduce_kernel<MODE>, kT, 0) != cudaSuccess || n <= 0) n = 3;
+    cached = n;
+  }
+  return cached;
 }
 
 // one warp per channel: sums the partials over (split, n); lane 0 holds the totals
@@ -621,7 +661,7 @@ extern "C" int ctl_bn_batch_affine_c8(const void* x, int64_t N, int64_t C, int64
   if (sm_count() < 0) return CTL_ERR_CUDA;
   cudaStream_t st = (cudaStream_t)stream;
   const int64_t planes = N * (C / 8), HW = H * W;
-  const int splits = plane_splits(planes, HW);
+  const int splits = plane_splits(planes, HW, reduce_ctas_per_sm<0>());
   plane_reduce_kernel<0><<<dim3((unsigned)planes, (unsigned)splits), kT, 0, st>>>(
       (const uint4*)x, nullptr, nullptr, nullptr, (double*)workspace, planes, HW, splits, 0, nullptr, nullptr, (int)(C / 8));
   CTL_CUDA_OK(cudaGetLastError(), "bn_partial_stats launch");
@@ -652,7 +692,7 @@ extern "C" int ctl_channel_sums_c8(const void* x, int64_t N, int64_t C, int64_t 
   if (sm_count() < 0) return CTL_ERR_CUDA;
   cudaStream_t st = (cudaStream_t)stream;
   const int64_t planes = N * (C / 8), HW = H * W;
-  const int splits = plane_splits(planes, HW);
+  const int splits = plane_splits(planes, HW, reduce_ctas_per_sm<0>());
   plane_reduce_kernel<0><<<dim3((unsigned)planes, (unsigned)splits), kT, 0, st>>>(
       (const uint4*)x, nullptr, nullptr, nullptr, (double*)workspace, planes, HW, splits, 0, nullptr, nullptr, (int)(C / 8));
   CTL_CUDA_OK(cudaGetLastError(), "plane_reduce launch");
@@ -675,7 +715,7 @@ extern "C" int ctl_bn_bwd_reduce_c8(const void* dy, const void* h, const void* a
   if (sm_count() < 0) return CTL_ERR_CUDA;
   cudaStream_t st = (cudaStream_t)stream;
   const int64_t planes = N * (C / 8), HW = H * W;
-  const int splits = plane_splits(planes, HW);
+  const int splits = plane_splits(planes, HW, reduce_ctas_per_sm<1>());
   plane_reduce_kernel<1><<<dim3((unsigned)planes, (unsigned)splits), kT, 0, st>>>(
       (const uint4*)dy, (const uint4*)h, (const uint4*)a, (uint4*)dv_out, (double*)workspace, planes, HW, splits, act,
       act_scale, act_shift, (int)(C / 8));
