@@ -35,6 +35,7 @@ SIGNATURES = {
     "ctl_philox_uniform": (_i, [_u64, _u64, _u64, _i64, _vp, _vp]),
     "ctl_conv2d_n_tile": (_i, [_i, _i, _i]),
     "ctl_pack_conv_weight": (_i, [_vp, _i64, _i64, _i, _i, _vp, _vp]),
+    "ctl_pack_conv_weights_batched": (_i, [_vp, _i64, _i64, _vp]),
     "ctl_conv2d_c8_bf16": (_i, [_vp, _i64, _i64, _i64, _i64, _vp, _i64, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _i, _vp,
                                 _vp, _vp]),
     "ctl_bn_affine_from_sums": (_i, [_vp, _i64, _i64, _vp, _vp, _f, _vp, _vp, _vp, _vp, _vp, _vp, _f, _vp]),
@@ -76,7 +77,7 @@ KERNELS_PER_CALL = {"ctl_saliency_reduce": 1, "ctl_topp_mask_apply": 2, "ctl_sal
                     "ctl_conv_wgrad_c8_bf16": 1, "ctl_channel_sums_c8": 2, "ctl_bn_affine_from_sums": 1, "ctl_pack_conv_weight": 1, "ctl_bn_bwd_reduce_c8": 2,
                     "ctl_bn_bwd_apply_c8": 1, "ctl_act_bwd_c8": 1, "ctl_downsample2x_sum_c8": 1,
                     "ctl_zero_stuff2x_c8": 1, "ctl_split_parity2x2_c8": 1, "ctl_head_bwd_c8": 1,
-                    "ctl_stem_wgrad_c8": 1, "ctl_stem_dgrad_c8": 1, "ctl_ce2d_fwd": 1, "ctl_ce2d_bwd": 1, "ctl_scale_shift_upadd_act_c8": 1}
+                    "ctl_stem_wgrad_c8": 1, "ctl_stem_dgrad_c8": 1, "ctl_ce2d_fwd": 1, "ctl_ce2d_bwd": 1, "ctl_scale_shift_upadd_act_c8": 1, "ctl_pack_conv_weights_batched": 1}
 LAUNCHES = {"count": 0}
 
 

@@ -285,6 +285,29 @@ pack_conv_weight_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__
   }
 }
 
+// every packing job of a step in ONE launch: blockIdx.y = job (table in device memory, int64 [n][8] =
+// {weight ptr, out ptr, Cout, Cin, taps, nt, transposed, 0}), blockIdx.x strides over the job's elements
+__global__ void __launch_bounds__(kT)
+pack_conv_weights_batched_kernel(const int64_t* __restrict__ jobs) {
+  const int64_t* job = jobs + (int64_t)blockIdx.y * 8;
+  const float* __restrict__ w = reinterpret_cast<const float*>(job[0]);
+  __nv_bfloat16* __restrict__ out = reinterpret_cast<__nv_bfloat16*>(job[1]);
+  const int Cout = (int)job[2], Cin = (int)job[3], taps = (int)job[4], nt = (int)job[5], transposed = (int)job[6];
+  const int co_p = transposed ? Cin : Cout, ci_p = transposed ? Cout : Cin;
+  const int total = co_p * ci_p * taps;
+  for (int i = blockIdx.x * kT + threadIdx.x; i < total; i += gridDim.x * kT) {
+    int r = i;
+    const int j = r & 7; r >>= 3;
+    const int n = r % nt; r /= nt;
+    const int q = r % (ci_p >> 3); r /= (ci_p >> 3);
+    const int tap = r % taps;
+    const int t = r / taps;
+    const int o = t * nt + n, c = q * 8 + j;
+    const float v = transposed ? w[((int64_t)c * Cin + o) * taps + (taps - 1 - tap)] : w[((int64_t)o * Cin + c) * taps + tap];
+    out[i] = __float2bfloat16_rn(v);
+  }
+}
+
 inline unsigned grid_for(int64_t total) {
   return (unsigned)std::min<int64_t>(ceil_div(total, kT), (int64_t)sm_count() * 16);
 }
@@ -305,6 +328,16 @@ extern "C" int ctl_pack_conv_weight(const float* weight, int64_t Cout, int64_t C
   pack_conv_weight_kernel<<<grid_for(total), kT, 0, (cudaStream_t)stream>>>(weight, (__nv_bfloat16*)out, (int)Cout, (int)Cin,
                                                                           taps, nt, transposed);
   CTL_CUDA_OK(cudaGetLastError(), "pack_conv_weight launch");
+  return CTL_OK;
+}
+
+extern "C" int ctl_pack_conv_weights_batched(const int64_t* jobs, int64_t n_jobs, int64_t max_elements, void* stream) {
+  CTL_REQUIRE(jobs && n_jobs > 0 && n_jobs <= 65535 && max_elements > 0, CTL_ERR_INVALID,
+              "ctl_pack_conv_weights_batched: bad arguments");
+  if (sm_count() < 0) return CTL_ERR_CUDA;
+  const unsigned gx = (unsigned)std::min<int64_t>(ceil_div(max_elements, kT * 4), 64);
+  pack_conv_weights_batched_kernel<<<dim3(gx, (unsigned)n_jobs), kT, 0, (cudaStream_t)stream>>>(jobs);
+  CTL_CUDA_OK(cudaGetLastError(), "pack_conv_weights_batched launch");
   return CTL_OK;
 }
 

@@ -39,11 +39,88 @@ from torch.optim.optimizer import register_optimizer_step_post_hook as _register
 _register_post_hook(_after_optimizer_step)
 
 
+class _PackRegistry:
+    """Every (conv weight, forward | input-gradient) packing the networks have asked for, with a PERSISTENT bf16 output
+    buffer each, so that after an optimizer step ONE launch (ctl_pack_conv_weights_batched, job table in device memory)
+    refreshes all of them instead of ~160 three-microsecond launches.  The first request for a weight packs it alone and
+    adds it to the table; a weight whose storage moved is re-registered."""
+
+    def __init__(self):
+        self.entries = {}           # (id(param), tag) -> dict(param=weakref, ptr, out, transposed, epoch)
+        self.table = None           # device int64 [n, 8]
+        self.table_keys = []
+        self.max_elements = 0
+        self.retired = []
+        self.dirty = False          # entries were added since the table was built
+
+    def _rebuild_table(self):
+        rows, keys, biggest = [], [], 0
+        for key, e in self.entries.items():
+            p = e["param"]()
+            if p is None:
+                continue
+            rows.append(ops.pack_job(p.detach(), e["transposed"], e["out"]))
+            keys.append(key)
+            biggest = max(biggest, p.numel())
+        dev = next(iter(self.entries.values()))["out"].device
+        if self.table is not None:
+            self.retired.append(self.table)                 # a captured CUDA graph may still read the old table
+        self.table = torch.tensor(rows, dtype=torch.int64).to(dev)
+        self.table_keys, self.max_elements = keys, biggest
+        self.dirty = False
+
+    def get(self, param, transposed, tag):
+        import weakref
+        epoch = _WEIGHTS_EPOCH[0]
+        key = (id(param), tag)
+        e = self.entries.get(key)
+        if e is not None and (e["param"]() is not param or e["ptr"] != param.data_ptr()):
+            e = None                                        # a dead parameter's id, or the storage moved
+        if e is None:
+            if torch.cuda.is_current_stream_capturing():
+                raise RuntimeError("a conv weight was packed for the first time inside a CUDA-graph capture: run the "
+                                   "step eagerly once before capturing")
+            out = ops._pack_kernel(param, transposed)
+            self.entries[key] = {"param": weakref.ref(param), "ptr": param.data_ptr(), "out": out,
+                                 "transposed": transposed, "epoch": epoch, "version": param._version}
+            self.dirty = True
+            return out
+        if e["epoch"] != epoch or e["version"] != param._version:
+            if self.table is None or self.dirty:
+                if torch.cuda.is_current_stream_capturing():
+                    raise RuntimeError("the weight-packing table must be built before a CUDA-graph capture "
+                                       "(fastpath.prepare_packing())")
+                self._rebuild_table()
+            # refresh EVERY registered packing at once (the optimizers stepped all networks)
+            ops.pack_conv_weights_batched(self.table, len(self.table_keys), self.max_elements)
+            for k in self.table_keys:
+                ent = self.entries[k]
+                p = ent["param"]()
+                ent["epoch"] = epoch
+                if p is not None:
+                    ent["version"] = p._version
+        return e["out"]
+
+
+_REGISTRY = _PackRegistry()
+
+
+def prepare_packing():
+    """Builds the device job table of the batched weight packing now (host -> device copy): call before capturing a
+    CUDA graph of a step, after at least one eager step has registered the networks' weights."""
+    if _REGISTRY.entries and (_REGISTRY.table is None or _REGISTRY.dirty):
+        _REGISTRY._rebuild_table()
+
+
 def _packed(param, fn, tag='fwd'):
     """Packed bf16 copy of a weight, rebuilt when the parameter is modified in place, its storage is replaced, or any
     optimizer has stepped since.  `tag` distinguishes the packings of one parameter (forward, input-gradient, per-tap
-    transposed-conv slices).  The cache lives ON the parameter object: a global table keyed by id() would hand a new
-    parameter the packed weights of a dead one whose id / address it inherited."""
+    transposed-conv slices).  Plain Conv2d packings (forward / input-gradient) of fp32 contiguous weights go through the
+    batched registry above; derived ones (transposed-conv slices) keep a per-parameter cache: it lives ON the parameter
+    object -- a global table keyed by id() alone would hand a new parameter the packed weights of a dead one."""
+    if (fn is ops.pack_conv_weight or fn is ops.pack_conv_weight_dgrad) and param.is_cuda \
+            and param.dtype == torch.float32 and param.is_contiguous():
+        return _REGISTRY.get(param, fn is ops.pack_conv_weight_dgrad, tag)
     cache = param.__dict__.get('_ctl_packed')
     if cache is None:
         cache = param.__dict__['_ctl_packed'] = {}

@@ -295,6 +295,24 @@ def _pack_kernel(weight, transposed):
     return out
 
 
+def pack_job(weight, transposed, out):
+    """One row of the ctl_pack_conv_weights_batched job table for a contiguous fp32 [Cout,Cin,k,k] weight."""
+    cout, cin, kh, kw = weight.shape
+    taps = kh * kw
+    co_p, ci_p = (cin, cout) if transposed else (cout, cin)
+    nt = _lib.load().ctl_conv2d_n_tile(ci_p, co_p, taps)
+    if kh != kw or taps not in (1, 9) or nt <= 0 or weight.dtype != torch.float32 or not weight.is_contiguous():
+        raise NotImplementedError("no batched packing for weight %s %s" % (tuple(weight.shape), weight.dtype))
+    return [weight.data_ptr(), out.data_ptr(), cout, cin, taps, nt, int(transposed), 0]
+
+
+def pack_conv_weights_batched(table, n_jobs, max_elements):
+    """table: DEVICE int64 [n_jobs, 8] built from pack_job rows; packs every listed weight in one launch."""
+    _need_cuda(table)
+    with torch.cuda.device(table.device):
+        _lib.check(_lib.load().ctl_pack_conv_weights_batched(table.data_ptr(), int(n_jobs), int(max_elements), _stream()))
+
+
 def pack_conv_weight(weight):
     """Packed bf16 forward weight of a Conv2d (one kernel launch; see pack_conv_weight_torch for the layout)."""
     return _pack_kernel(weight, False)

@@ -281,6 +281,7 @@ class GraphedCooperativeTrainer(CooperativeTrainer):
         from . import fastpath
         cs = _CapturedStep(clean.device)
         self.bucket.reattach()                      # every .grad is a view of the flat bucket before recording
+        fastpath.prepare_packing()                  # job table of the batched weight packing (host -> device copy)
         fastpath.weights_changed()                  # every packed weight is rebuilt INSIDE the graph
         n0 = _lib.LAUNCHES["count"]
         with model_util.recording_step_params(cs.params):

@@ -145,6 +145,10 @@ int ctl_conv2d_n_tile(int Cin, int Cout, int taps);
 /* fp32 nn.Conv2d weight [Cout][Cin][k][k] (taps = k*k) -> the packed bf16 w_packed above.  transposed = 1 packs the weight of
  * the INPUT-gradient convolution instead, w'[ci][co][r][s] = w[co][ci][k-1-r][k-1-s] (its Cout' = Cin, Cin' = Cout). */
 int ctl_pack_conv_weight(const float* weight, int64_t Cout, int64_t Cin, int taps, int transposed, void* out, void* stream);
+/* The same for many weights in ONE launch (a training step repacks every conv weight after the optimizers ran).
+ * jobs: DEVICE int64 [n_jobs][8] = {weight ptr, out ptr, Cout, Cin, taps, ctl_conv2d_n_tile of the packed view,
+ * transposed, 0}; max_elements = the largest Cout*Cin*taps among them (grid sizing). */
+int ctl_pack_conv_weights_batched(const int64_t* jobs, int64_t n_jobs, int64_t max_elements, void* stream);
 int ctl_conv2d_c8_bf16(const void* x, int64_t N, int64_t H, int64_t W, int64_t Cin, const void* w_packed,
                        int64_t Cout, int taps, int subsample, int up2x, const float* scale,
                        const float* shift, const void* res, const float* res_scale,
