@@ -64,7 +64,12 @@ struct WgCfg {
     const int rows = (kR - j * kRowsPer) < kRowsPer ? (kR - j * kRowsPer) : kRowsPer;
     return rows * CIN > 64 ? 128 : 64;
   }
-  static constexpr int kTmemCols = kS * kG * NT;
+  // Cin <= 32, 3x3: the MMA's M already spans FOUR image rows of x (3 used), so two dy rows ride in one instruction:
+  // N = (dy row y | dy row y+1) x NT.  Rows (r', ci) x columns (d, co) hold tap r = r' - d; both useful blocks of the
+  // 4 x 2 grid are kept -- twice the useful work per operand fetch of the (fetch-bound) small-N MMAs.
+  static constexpr bool kPair = TAPS == 9 && CIN <= 32;
+  static constexpr int kNmma = kPair ? 2 * NT : NT;
+  static constexpr int kTmemCols = kS * kG * kNmma;
   static constexpr int kTmemAlloc = kTmemCols <= 32 ? 32 : kTmemCols <= 64 ? 64 : kTmemCols <= 128 ? 128
                                     : kTmemCols <= 256 ? 256 : 512;
   // the discarded M rows of the last image rows reach up to 16 lines past the tile
@@ -76,7 +81,7 @@ struct WgCfg {
   // the epilogue may stage the CTA's [NT][CIN][TAPS] fp32 result in the operand ring (idle by then)
   static constexpr bool kStageFits = NT * CIN * TAPS * 4 <= kOffBar;
   static_assert(kTmemCols <= 512, "accumulators exceed TMEM");
-  static_assert(NT % 16 == 0 && NT <= 256 && CIN % 16 == 0, "UMMA shape");
+  static_assert(NT % 16 == 0 && kNmma <= 256 && CIN % 16 == 0, "UMMA shape");
   static_assert(kSmemBytes <= 227 * 1024, "shared memory budget");
   static_assert((kLine >> 4) < 16384 && (kDPlane >> 4) < 16384, "descriptor range");
 };
@@ -140,7 +145,10 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constan
         } else {
           mbar_arrive_expect_tx(&full[stage], Cfg::kXStage + Cfg::kDStage);
           tma_load_4d(sx, &tmap_x, &full[stage], (x0 - Cfg::kPad) * 2, 0, y0 - Cfg::kPad, img);
-          tma_load_4d(sx + Cfg::kXStage, &tmap_dy, &full[stage], x0 * 2, y0, n_tile * (NT / 8), img);
+          if (Cfg::kPair)   // row-interleaved dy tile [row][plane][pixel][8ch]
+            tma_load_4d(sx + Cfg::kXStage, &tmap_dy, &full[stage], x0 * 2, n_tile * (NT / 8), y0, img);
+          else
+            tma_load_4d(sx + Cfg::kXStage, &tmap_dy, &full[stage], x0 * 2, y0, n_tile * (NT / 8), img);
         }
         if (++stage == STAGES) { stage = 0; phase ^= 1; }
       }
@@ -157,18 +165,21 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constan
         const uint32_t xs = smem_u32(smem + stage * Cfg::kStage);
         const uint32_t ds = xs + Cfg::kXStage;
 #pragma unroll 1
-        for (int y = (p.diag & 1) ? kWgTH : 0; y < kWgTH; ++y) {
+        for (int y = (p.diag & 1) ? kWgTH : 0; y < kWgTH; y += (Cfg::kPair ? 2 : 1)) {
 #pragma unroll
           for (int xc = 0; xc < kWgTW; xc += 16) {
-            const uint64_t bdesc = umma_smem_desc(ds + (uint32_t)((y * kWgTW + xc) * 16), 128u, Cfg::kDPlane);
+            // pair: N groups of 8 columns walk (dy row y, planes 0..P-1), (dy row y+1, planes 0..P-1): stride one line
+            const uint64_t bdesc =
+                Cfg::kPair ? umma_smem_desc(ds + (uint32_t)(y * (NT / 8) * (kWgTW * 16) + xc * 16), 128u, kWgTW * 16)
+                           : umma_smem_desc(ds + (uint32_t)((y * kWgTW + xc) * 16), 128u, Cfg::kDPlane);
 #pragma unroll
             for (int sx = 0; sx < Cfg::kS; ++sx) {
 #pragma unroll
               for (int j = 0; j < Cfg::kG; ++j) {
                 const uint32_t a_addr = xs + (uint32_t)((y + j * Cfg::kRowsPer) * Cfg::kPlanes * Cfg::kLine + (xc + sx) * 16);
                 const uint64_t adesc = umma_smem_desc(a_addr, 128u, Cfg::kLine);
-                umma_bf16(tmem_base + (uint32_t)((sx * Cfg::kG + j) * NT), adesc, bdesc, idesc_bf16_mn(Cfg::m_of(j), NT),
-                          accumulate);
+                umma_bf16(tmem_base + (uint32_t)((sx * Cfg::kG + j) * Cfg::kNmma), adesc, bdesc,
+                          idesc_bf16_mn(Cfg::m_of(j), Cfg::kNmma), accumulate);
               }
             }
             accumulate = 1;
@@ -192,38 +203,52 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constan
       const bool staged = Cfg::kStageFits && p.s_tap == 1 && p.s_ci == TAPS && p.s_co == (int64_t)CIN * TAPS &&
                           (reinterpret_cast<uintptr_t>(block) & 15u) == 0;
       float* stage = reinterpret_cast<float*>(smem);
+      // pair mode: pass d = 0 reads columns [0, NT) (tap r = r'), pass d = 1 columns [NT, 2NT) (tap r = r' - 1); every
+      // (tap, ci, co) has exactly one writer per pass, the staged block is stored in pass 0 and added to in pass 1
 #pragma unroll 1
-      for (int sx = (p.diag & 4) ? Cfg::kS : 0; sx < Cfg::kS; ++sx) {
-#pragma unroll
-        for (int j = 0; j < Cfg::kG; ++j) {
-          // accumulator row m of this thread: M = 128 -> TMEM lane m; M = 64 -> lane (m % 16) + 32 * (m / 16)
-          const bool m128 = Cfg::m_of(j) == 128;
-          const int m = m128 ? q * 32 + lane : q * 16 + lane;
-          const int line = m >> 3;                                       // 8-row group = (image row, plane)
-          const int r = j * Cfg::kRowsPer + line / Cfg::kPlanes;
-          const int ci = (line % Cfg::kPlanes) * 8 + (m & 7);
-          const bool row_ok = (m128 || lane < 16) && r < Cfg::kR && line / Cfg::kPlanes < Cfg::kRowsPer;
-          const int tap = TAPS == 9 ? r * 3 + sx : 0;
+      for (int d = 0; d < (Cfg::kPair ? 2 : 1); ++d) {
+        if (d == 1 && staged && !(p.diag & 4)) asm volatile("bar.sync 1, 128;" ::: "memory");
 #pragma unroll 1
-          for (int c0 = 0; c0 < NT; c0 += 16) {
-            uint32_t v[16];
-            tmem_ld_32x32b_x16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)((sx * Cfg::kG + j) * NT + c0), v);
-            tmem_ld_wait();
-            if (row_ok) {
-              if (staged) {
+        for (int sx = (p.diag & 4) ? Cfg::kS : 0; sx < Cfg::kS; ++sx) {
 #pragma unroll
-                for (int i = 0; i < 16; ++i) stage[((c0 + i) * CIN + ci) * TAPS + tap] = __uint_as_float(v[i]);
-                continue;
-              }
-              float* dst = p.dW + tap * p.s_tap + ci * p.s_ci + (int64_t)(n0 + c0) * p.s_co;
-              if (p.s_co == 1 && ((reinterpret_cast<uintptr_t>(dst) & 15u) == 0)) {
+          for (int j = 0; j < Cfg::kG; ++j) {
+            // accumulator row m of this thread: M = 128 -> TMEM lane m; M = 64 -> lane (m % 16) + 32 * (m / 16)
+            const bool m128 = Cfg::m_of(j) == 128;
+            const int m = m128 ? q * 32 + lane : q * 16 + lane;
+            const int line = m >> 3;                                       // 8-row group = (image row, plane)
+            const int rp = line / Cfg::kPlanes;                            // image row of x within the MMA's M rows
+            const int r = j * Cfg::kRowsPer + rp - d;                      // vertical tap this block contributes to
+            const int ci = (line % Cfg::kPlanes) * 8 + (m & 7);
+            const bool row_ok = (m128 || lane < 16) && r >= 0 && r < Cfg::kR &&
+                                rp < (Cfg::kPair ? Cfg::kRowsPer + 1 : Cfg::kRowsPer);
+            const int tap = TAPS == 9 ? r * 3 + sx : 0;
+#pragma unroll 1
+            for (int c0 = 0; c0 < NT; c0 += 16) {
+              uint32_t v[16];
+              tmem_ld_32x32b_x16(tmem_base + ((uint32_t)(q * 32) << 16) +
+                                     (uint32_t)((sx * Cfg::kG + j) * Cfg::kNmma + d * NT + c0), v);
+              tmem_ld_wait();
+              if (row_ok) {
+                if (staged) {
+                  if (d == 0) {
 #pragma unroll
-                for (int i = 0; i < 16; i += 4)
-                  red_add_v4(dst + i, __uint_as_float(v[i]), __uint_as_float(v[i + 1]), __uint_as_float(v[i + 2]),
-                             __uint_as_float(v[i + 3]));
-              } else {
+                    for (int i = 0; i < 16; ++i) stage[((c0 + i) * CIN + ci) * TAPS + tap] = __uint_as_float(v[i]);
+                  } else {
 #pragma unroll
-                for (int i = 0; i < 16; ++i) atomicAdd(dst + i * p.s_co, __uint_as_float(v[i]));
+                    for (int i = 0; i < 16; ++i) stage[((c0 + i) * CIN + ci) * TAPS + tap] += __uint_as_float(v[i]);
+                  }
+                  continue;
+                }
+                float* dst = p.dW + tap * p.s_tap + ci * p.s_ci + (int64_t)(n0 + c0) * p.s_co;
+                if (p.s_co == 1 && ((reinterpret_cast<uintptr_t>(dst) & 15u) == 0)) {
+#pragma unroll
+                  for (int i = 0; i < 16; i += 4)
+                    red_add_v4(dst + i, __uint_as_float(v[i]), __uint_as_float(v[i + 1]), __uint_as_float(v[i + 2]),
+                               __uint_as_float(v[i + 3]));
+                } else {
+#pragma unroll
+                  for (int i = 0; i < 16; ++i) atomicAdd(dst + i * p.s_co, __uint_as_float(v[i]));
+                }
               }
             }
           }
@@ -285,12 +310,12 @@ int make_c8_tmap(CUtensorMap* m, const void* x, int N, int H, int W, int C, int 
 }
 
 // x as (W*2, C/8, H, N) -- planes before rows -- so that the box lands row-interleaved: [row][plane][pixel][8ch]
-int make_c8_tmap_rows(CUtensorMap* m, const void* x, int N, int H, int W, int C, int box_w, int box_h) {
+int make_c8_tmap_rows(CUtensorMap* m, const void* x, int N, int H, int W, int C, int box_w, int box_h, int box_c8 = 0) {
   EncodeTiledFn enc = encode_tiled_fn();
   CTL_REQUIRE(enc != nullptr, CTL_ERR_CUDA, "cuTensorMapEncodeTiled is not available from the driver");
   const cuuint64_t dims[4] = {(cuuint64_t)W * 2, (cuuint64_t)(C / 8), (cuuint64_t)H, (cuuint64_t)N};
   const cuuint64_t strides[3] = {(cuuint64_t)H * W * 16, (cuuint64_t)W * 16, (cuuint64_t)(C / 8) * H * W * 16};
-  const cuuint32_t box[4] = {(cuuint32_t)box_w * 2, (cuuint32_t)(C / 8), (cuuint32_t)box_h, 1};
+  const cuuint32_t box[4] = {(cuuint32_t)box_w * 2, (cuuint32_t)(box_c8 > 0 ? box_c8 : C / 8), (cuuint32_t)box_h, 1};
   const cuuint32_t estr[4] = {1, 1, 1, 1};
   const CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_UINT64, 4, const_cast<void*>(x), dims, strides, box, estr,
                          CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
@@ -309,7 +334,11 @@ int launch_wgrad(const void* x, const void* dy, const WgradParams& p0, cudaStrea
   p.num_tiles = (int64_t)p.N * p.tiles_x * p.tiles_y;
   CUtensorMap tx, td;
   if (int rc = make_c8_tmap_rows(&tx, x, p.N, p.H, p.W, CIN, Cfg::kHaloW, Cfg::kHaloH)) return rc;
-  if (int rc = make_c8_tmap(&td, dy, p.N, p.H, p.W, p.Cout, kWgTW, kWgTH, NT / 8)) return rc;
+  if (Cfg::kPair) {
+    if (int rc = make_c8_tmap_rows(&td, dy, p.N, p.H, p.W, p.Cout, kWgTW, kWgTH, NT / 8)) return rc;
+  } else {
+    if (int rc = make_c8_tmap(&td, dy, p.N, p.H, p.W, p.Cout, kWgTW, kWgTH, NT / 8)) return rc;
+  }
   auto kern = wgrad_tc_kernel<CIN, NT, TAPS, STAGES>;
   CTL_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes),
               "wgrad smem attribute");
@@ -325,8 +354,9 @@ int launch_wgrad(const void* x, const void* dy, const WgradParams& p0, cudaStrea
 }
 
 int wgrad_n_tile(int Cin, int Cout, int taps) {
-  // TMEM: kS*kG*NT <= 512 columns -> 3x3: NT <= 32 (Cin 128), 64 (Cin 64), 128 (Cin <= 32); 1x1: 128
-  const int cap = taps == 9 ? (Cin == 128 ? 32 : Cin == 64 ? 64 : 128) : 128;
+  // TMEM: kS*kG*NT <= 512 columns -> 3x3: NT <= 32 (Cin 128), 64 (Cin 64); 1x1: 128
+  // (pair mode, Cin <= 32 3x3: 3 * 2*NT <= 512 -> NT <= 64)
+  const int cap = taps == 9 ? (Cin == 128 ? 32 : 64) : 128;
   for (int nt = cap; nt >= 16; nt >>= 1)
     if (Cout % nt == 0) return nt;
   return -1;
@@ -340,7 +370,7 @@ int dispatch_wgrad(const void* x, const void* dy, const WgradParams& p, int nt, 
   if constexpr (TAPS == 1 || CIN <= 64) {
     if (nt == 64) return launch_wgrad<CIN, 64, TAPS, (CIN >= 64 ? 2 : S)>(x, dy, p, st);
   }
-  if constexpr (TAPS == 1 || CIN <= 32) {
+  if constexpr (TAPS == 1) {
     if (nt == 128) return launch_wgrad<CIN, 128, TAPS, (CIN == 128 ? 1 : 2)>(x, dy, p, st);
   }
   set_error("ctl_conv_wgrad_c8_bf16: no kernel for Cin=%d, n_tile=%d, taps=%d", CIN, nt, TAPS);
