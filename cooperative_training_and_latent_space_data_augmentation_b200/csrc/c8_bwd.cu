@@ -495,6 +495,37 @@ __device__ __forceinline__ void stem_input_at(const float* __restrict__ x, const
   }
 }
 
+// The stem's input as a 16-channel C8 tensor so that the stem convolution and its weight gradient run on the tensor-core
+// kernels (K3 / K3w with Cin = 16) instead of the CUDA-core stem kernels: in_mode 0 the image, 1 softmax(x / T), 2 the
+// one-hot of the label map (construct_input, basic_operations.py:110-158).  The fp32 value v of input channel c is kept
+// to ~16 mantissa bits as a bf16 pair: channel c = hi = bf16(v), channel CIN + c = lo = bf16(v - hi), channel 2*CIN + c
+// = hi again (it meets the low half of the split WEIGHT, ops.pad_stem_weight); the rest is zero.  One thread per
+// pixel: CIN planar reads, 2 x 16 bytes out.
+template <int CIN>
+__global__ void __launch_bounds__(kT)
+stem_input_c8_kernel(const float* __restrict__ x, const long long* __restrict__ labels, int in_mode, float inv_temp, int N,
+                     int H, int W, uint4* __restrict__ out) {
+  const int64_t HW = (int64_t)H * W, total = (int64_t)N * HW;
+  for (int64_t i = (int64_t)blockIdx.x * kT + threadIdx.x; i < total; i += (int64_t)gridDim.x * kT) {
+    const int64_t n = i / HW, q = i - n * HW;
+    const int iy = (int)(q / W), ix = (int)(q - (int64_t)iy * W);
+    float v[CIN];
+    stem_input_at<CIN>(x, labels, in_mode, inv_temp, n, iy, ix, H, W, v);
+    float f[16];
+#pragma unroll
+    for (int j = 0; j < 16; ++j) f[j] = 0.0f;
+#pragma unroll
+    for (int c = 0; c < CIN; ++c) {
+      const float hi = __bfloat162float(__float2bfloat16_rn(v[c]));
+      f[c] = hi;
+      f[CIN + c] = v[c] - hi;
+      f[2 * CIN + c] = hi;
+    }
+    out[(n * 2 + 0) * HW + q] = pack8(*reinterpret_cast<const float(*)[8]>(&f[0]));
+    out[(n * 2 + 1) * HW + q] = pack8(*reinterpret_cast<const float(*)[8]>(&f[8]));
+  }
+}
+
 // Weight gradient of the stem: dW[co][ci][r][s] += sum_p dy[p][co] * in[p + (r-1, s-1)][ci].
 // CTA = one 32x8 pixel tile per iteration (persistent), input tile with halo and dy tile staged in shared memory.
 // Thread (g = tid/16, t = tid%16): pixels g, g+16, ... of the tile; co quad t%4; k slice t/4 (CIN 4: channel t/4, nine
@@ -817,6 +848,25 @@ extern "C" int ctl_head_bwd_c8(const float* dy, const float* y, const void* x, i
   else
     head_bwd_kernel<4><<<grid, kT, 0, st>>>(dy, y, (const __nv_bfloat16*)x, weight, (__nv_bfloat16*)dx, dW, db, (int)N, H * W, act);
   CTL_CUDA_OK(cudaGetLastError(), "head_bwd launch");
+  return CTL_OK;
+}
+
+extern "C" int ctl_stem_input_c8(const float* x, const int64_t* labels, int in_mode, float temperature, int64_t N,
+                                 int64_t Cin, int64_t H, int64_t W, void* out, void* stream) {
+  CTL_REQUIRE(out && N > 0 && H > 0 && W > 0, CTL_ERR_INVALID, "ctl_stem_input_c8: bad arguments");
+  CTL_REQUIRE(in_mode >= 0 && in_mode <= 2 && (in_mode == 2 ? labels != nullptr : x != nullptr), CTL_ERR_INVALID,
+              "ctl_stem_input_c8: in_mode %d needs %s", in_mode, in_mode == 2 ? "labels" : "x");
+  CTL_REQUIRE(Cin == 1 || Cin == 4, CTL_ERR_UNSUPPORTED, "ctl_stem_input_c8 handles Cin in {1,4} (got %lld)", (long long)Cin);
+  CTL_REQUIRE(temperature > 0.0f && aligned16(out), CTL_ERR_INVALID, "temperature must be positive, out 16-byte aligned");
+  if (sm_count() < 0) return CTL_ERR_CUDA;
+  cudaStream_t st = (cudaStream_t)stream;
+  const unsigned grid = grid_for(N * H * W);
+  const long long* lab = reinterpret_cast<const long long*>(labels);
+  if (Cin == 1)
+    stem_input_c8_kernel<1><<<grid, kT, 0, st>>>(x, lab, in_mode, 1.0f / temperature, (int)N, (int)H, (int)W, (uint4*)out);
+  else
+    stem_input_c8_kernel<4><<<grid, kT, 0, st>>>(x, lab, in_mode, 1.0f / temperature, (int)N, (int)H, (int)W, (uint4*)out);
+  CTL_CUDA_OK(cudaGetLastError(), "stem_input launch");
   return CTL_OK;
 }
 

@@ -132,6 +132,10 @@ def _packed(param, fn, tag='fwd'):
     return hit[1]
 
 
+def _pack_stem_weight(weight):
+    return ops.pack_conv_weight(ops.pad_stem_weight(weight))
+
+
 def _act_code(module):
     if module is None:
         return ops.ACT_NONE
@@ -220,11 +224,14 @@ def up_block(block, x, mode):
 def encoder_forward(enc, x, mode, in_mode=0, temperature=1.0):
     """MyEncoder on planar input (fp32 image / logits, or an int64 label map with in_mode=2) -> C8 latent."""
     inc = enc.inc
+    # stem on the tensor core: 16-channel C8 input of bf16 (hi | lo | hi) groups, weight (w_hi | w_hi | w_lo | 0)
+    xin = ops.stem_input_c8(x, inc[0].in_channels, in_mode, temperature)
+    wp = _packed(inc[0].weight, _pack_stem_weight, tag='stem')
     if mode == 'eval':
         s0, t0 = _fold_eval(inc[0], inc[1])
-        y = ops.stem_conv_c8(x, inc[0].weight, s0, t0, ops.ACT_LRELU, in_mode, temperature)
+        y = ops.conv2d_c8(xin, wp, inc[0].out_channels, 9, scale=s0, shift=t0, act=ops.ACT_LRELU)
     else:
-        y = ops.stem_conv_c8(x, inc[0].weight, None, inc[0].bias, ops.ACT_NONE, in_mode, temperature)
+        y = ops.conv2d_c8(xin, wp, inc[0].out_channels, 9, shift=inc[0].bias)
         s0, t0 = _bn_batch(inc[1], y, mode)
         y = ops.scale_shift_act_c8(y, s0, t0, ops.ACT_LRELU, inplace=True)
     y = conv_bn_act(inc[3], inc[4], y, ops.ACT_LRELU, mode)     # BN then F.leaky_relu (encoder_decoder.py:405)

@@ -411,6 +411,48 @@ def stem_conv_c8(x, weight, scale=None, shift=None, act=ACT_NONE, in_mode=0, tem
     return y
 
 
+def stem_input_c8(x, cin, in_mode=0, temperature=1.0):
+    """The stem's input as a 16-channel C8 tensor: image (in_mode 0), softmax(x / T) (1) or the one-hot of an int64
+    label map (2), each channel as a bf16 (hi | lo | hi) triple in channel groups of `cin` (see pad_stem_weight) -- the
+    operand of the tensor-core stem (conv2d_c8 / conv_wgrad_c8 with Cin 16)."""
+    _need_cuda(x)
+    if in_mode == 2:
+        lab = x.contiguous()
+        if lab.dtype != torch.int64 or lab.dim() != 3:
+            raise ValueError("in_mode 2 expects an int64 label map [N,H,W]")
+        N, H, W = lab.shape
+        xp, lp = 0, lab.data_ptr()
+    else:
+        xf = x.to(torch.float32).contiguous()
+        N, c, H, W = xf.shape
+        if c != cin:
+            raise ValueError("input has %d channels, expected %d" % (c, cin))
+        xp, lp = xf.data_ptr(), 0
+    out = torch.empty((N, 2, H, W, 8), device=x.device, dtype=torch.bfloat16)
+    with torch.cuda.device(x.device):
+        _lib.check(_lib.load().ctl_stem_input_c8(xp, lp, in_mode, float(temperature), N, cin, H, W, out.data_ptr(), _stream()))
+    return out
+
+
+def pad_stem_weight(weight):
+    """[16, cin, 3, 3] -> [16, 16, 3, 3] fp32 for the tensor-core stem: input-channel groups (w_hi | w_hi | w_lo | 0) with
+    w_hi = bf16(w), w_lo = w - w_hi, matching stem_input_c8's (x_hi | x_lo | x_hi | 0): x*w ~ x_hi*w_hi + x_lo*w_hi +
+    x_hi*w_lo keeps ~16 mantissa bits of both operands (the CUDA-core stem it replaces was fp32)."""
+    cout, cin = weight.shape[0], weight.shape[1]
+    w = weight.detach().to(torch.float32)
+    hi = w.to(torch.bfloat16).to(torch.float32)
+    out = torch.zeros((cout, 16, 3, 3), device=weight.device, dtype=torch.float32)
+    out[:, :cin] = hi
+    out[:, cin:2 * cin] = hi
+    out[:, 2 * cin:3 * cin] = w - hi
+    return out
+
+
+def stem_weight_grad(dW16, cin):
+    """Weight gradient [16, cin, 3, 3] from K3w's 16-channel result: the (x_hi | x_lo) channel groups carry sum dy * x."""
+    return dW16[:, :cin] + dW16[:, cin:2 * cin]
+
+
 def head_conv_c8(x, weight, bias=None, act=ACT_NONE):
     """1x1 head from a 16-channel C8 tensor to planar fp32 [N,Cout,H,W] (Cout <= 4)."""
     _need_cuda(x, weight, bias)

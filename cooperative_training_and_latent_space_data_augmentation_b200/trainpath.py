@@ -86,6 +86,10 @@ def _conv_bn(fw, conv, bn, x):
     return (a,) + stats
 
 
+def _pack_stem_weight(weight):
+    return ops.pack_conv_weight(ops.pad_stem_weight(weight))
+
+
 def _conv_raw(conv, x):
     k = conv.kernel_size[0]
     wp = _packed(conv.weight, ops.pack_conv_weight)
@@ -321,11 +325,23 @@ def encoder_fwd(enc, x, in_mode, temperature):
     """MyEncoder: planar input (fp32 image / logits, or int64 label map with in_mode 2) -> C8 latent."""
     inc = enc.inc
     fw = _Fwd(enc, inc[0].weight.device)
-    a0 = ops.stem_conv_c8(x, inc[0].weight, None, inc[0].bias, ops.ACT_NONE, in_mode, temperature)
-    scale0, shift0, mean0, var0 = _bn_mode_stats(fw, inc[1], a0)
+    # stem on the tensor core: the input (image / softmax(logits/T) / one-hot labels) becomes a 16-channel C8 tensor of
+    # bf16 (hi | lo | hi) channel groups, the weight [16,16,3,3] = (w_hi | w_hi | w_lo | 0): fp32-like products on K3,
+    # which then also accumulates the BatchNorm statistics
+    xin = ops.stem_input_c8(x, inc[0].in_channels, in_mode, temperature)
+    wp = _packed(inc[0].weight, _pack_stem_weight, tag='stem')
+    sums = fw.sums(inc[0].out_channels)
+    a0 = ops.conv2d_c8(xin, wp, inc[0].out_channels, 9, shift=inc[0].bias, stats=sums)
+    bn0 = inc[1]
+    track = bn0.track_running_stats and bn0.running_mean is not None
+    scale0, shift0, mean0, var0 = ops.bn_affine_from_sums(
+        sums, a0.shape[0] * a0.shape[2] * a0.shape[3], bn0.weight, bn0.bias, bn0.eps, bn0.running_mean if track else None,
+        bn0.running_var if track else None, bn0.momentum if bn0.momentum is not None else 0.1)
+    if track:
+        fw.tracked.append(bn0.num_batches_tracked)
     h0 = ops.scale_shift_act_c8(a0, scale0, shift0, LRELU)
     h, s_inc = conv_bn_act_fwd(fw, inc[3], inc[4], h0, LRELU)   # BN then F.leaky_relu (encoder_decoder.py:405)
-    tape = [(a0, h0, mean0, var0, scale0, shift0), s_inc]
+    tape = [(a0, h0, mean0, var0, scale0, shift0, xin), s_inc]
     for blk in (enc.down1, enc.down2, enc.down3, enc.down4):
         h, s = down_fwd(fw, blk, h)
         tape.append(s)
@@ -341,14 +357,15 @@ def encoder_bwd(enc, tape, dz, grads, x, in_mode, temperature, need_dx):
     for i, blk in zip((5, 4, 3, 2), (enc.down4, enc.down3, enc.down2, enc.down1)):
         d = down_bwd(blk, tape[i], d, grads)
     dh0 = conv_bn_act_bwd(inc[3], inc[4], LRELU, tape[1], d, grads)
-    a0, h0, mean0, var0, scale0, shift0 = tape[0]
+    a0, h0, mean0, var0, scale0, shift0, xin = tape[0]
     da0, dg0, db0, _ = ops.bn_act_bwd_c8(dh0, h0, a0, LRELU, mean0, var0, inc[1].eps, inc[1].weight,
                                          act_affine=(scale0, shift0))
     grads.add(inc[1].weight, dg0)
     grads.add(inc[1].bias, db0)
     if grads.wants(inc[0].weight):
-        grads.add(inc[0].weight, ops.stem_wgrad_c8(da0, x, inc[0].in_channels, in_mode, temperature,
-                                                   out=grads.buffer(inc[0].weight)))
+        # K3w on the 16-channel stem input; the gradient of the real input channels is the leading slice
+        dW16 = ops.conv_wgrad_c8(xin, da0, 9, layout='conv')
+        grads.add(inc[0].weight, ops.stem_weight_grad(dW16, inc[0].in_channels))
     if need_dx:
         return ops.stem_dgrad_c8(da0, x, inc[0].weight, in_mode, temperature)
     return None

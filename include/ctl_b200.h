@@ -255,6 +255,14 @@ int ctl_ce2d_fwd(const float* logits, const int64_t* labels, int64_t N, int64_t 
                  void* workspace16, float* loss_out, void* stream);
 int ctl_ce2d_bwd(const float* logits, const int64_t* labels, int64_t N, int64_t C, int64_t H, int64_t W, double scale,
                  const float* grad_out, float* dlogits, void* stream);
+/* The stem's input as a 16-channel C8 bf16 tensor [N,2,H,W,8] (in_mode as above), so that MyEncoder.inc[0] and its
+ * weight gradient run on ctl_conv2d_c8_bf16 / ctl_conv_wgrad_c8_bf16 with Cin = 16 -- the tensor-core route of the
+ * training path; Cin in {1,4}.  Input channel c is stored as a bf16 pair (fp32 value v): channel c = hi = bf16(v),
+ * channel Cin+c = lo = bf16(v - hi), channel 2*Cin+c = hi again; the other channels are zero.  With the weight laid out
+ * as [16][16][3][3] = (w_hi | w_hi | w_lo | 0) over those channel groups the convolution keeps ~16 mantissa bits of
+ * both operands; the weight gradient is the sum of the first two channel groups of the 16-channel result. */
+int ctl_stem_input_c8(const float* x, const int64_t* labels, int in_mode, float temperature, int64_t N, int64_t Cin,
+                      int64_t H, int64_t W, void* out, void* stream);
 /* backward of ctl_stem_conv3x3_c8 w.r.t. the weight: dy C8 (16 channels, gradient of the raw conv output);
  * x / labels / in_mode / temperature as in the forward; dW fp32 [16][Cin][3][3] ACCUMULATED into. */
 int ctl_stem_wgrad_c8(const void* dy, const float* x, const int64_t* labels, int in_mode, float temperature, int64_t N,

@@ -217,3 +217,31 @@ def test_scale_shift_upadd_act(ops, act):
     got1 = ops.scale_shift_upadd_act_c8(ops.nchw_to_c8(x), None, None, ops.nchw_to_c8(low), act)
     want1 = x.float() + F.interpolate(low.float(), scale_factor=2, mode='nearest')
     _cmp(ops.c8_to_nchw(got1), F.leaky_relu(want1, 0.2) if act else want1, 1e-2, "upadd (no affine)")
+
+
+@pytest.mark.parametrize("cin,in_mode", [(1, 0), (4, 0), (4, 1), (4, 2)])
+def test_stem_input_c8_and_tensor_core_stem(ops, cin, in_mode):
+    """ctl_stem_input_c8: the stem input as 16 C8 channels (image / softmax(x/T) / one-hot, zero padding), and the stem
+    convolution + its weight gradient through K3 / K3w on it against torch fp32 on the same bf16-rounded operands."""
+    g = torch.Generator(device="cuda").manual_seed(31 + cin + in_mode)
+    N, H, W = 3, 24, 40
+    if in_mode == 2:
+        x = torch.randint(0, cin, (N, H, W), device="cuda", generator=g)
+        want_in = F.one_hot(x, cin).permute(0, 3, 1, 2).float()
+    else:
+        x = torch.randn(N, cin, H, W, device="cuda", generator=g)
+        want_in = torch.softmax(x / 2.0, dim=1) if in_mode == 1 else x
+    xin = ops.stem_input_c8(x, cin, in_mode, 2.0)
+    got_in = ops.c8_to_nchw(xin)
+    assert float(got_in[:, 3 * cin:].abs().max()) == 0.0
+    assert torch.equal(got_in[:, :cin], got_in[:, 2 * cin:3 * cin])
+    _cmp(got_in[:, :cin] + got_in[:, cin:2 * cin], want_in, 2e-5, "stem input (hi + lo)")
+    w = 0.2 * torch.randn(16, cin, 3, 3, device="cuda", generator=g)
+    wf = w.clone().requires_grad_(True)
+    y = F.conv2d(want_in, wf, padding=1)                       # fp32 reference on the UNROUNDED operands
+    got = ops.conv2d_c8(xin, ops.pack_conv_weight(ops.pad_stem_weight(w)), 16, 9)
+    _cmp(ops.c8_to_nchw(got), y.detach(), 5e-3, "tensor-core stem forward")      # one bf16 rounding of the output
+    dy = _bf(N, 16, H, W, gen=g, scale=0.1)
+    y.backward(dy.float())
+    dW16 = ops.conv_wgrad_c8(xin, ops.nchw_to_c8(dy), 9, layout='conv')
+    _cmp(ops.stem_weight_grad(dW16, cin), wf.grad, 1e-4, "tensor-core stem wgrad")
