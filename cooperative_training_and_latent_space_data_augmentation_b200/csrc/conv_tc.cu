@@ -58,15 +58,6 @@ struct ConvParams {
   int diag;                           // profiling only (env CTL_DIAG_SKIP): 1 no MMA, 2 no TMA loads, 4 no epilogue memory traffic, 8 no epilogue
 };
 
-__device__ __forceinline__ float apply_act(float v, int act) {
-  switch (act) {
-    case CTL_ACT_LRELU: return v > 0.0f ? v : 0.2f * v;
-    case CTL_ACT_RELU: return fmaxf(v, 0.0f);
-    case CTL_ACT_SIGMOID: return 1.0f / (1.0f + __expf(-v));
-    default: return v;
-  }
-}
-
 template <int CIN, int NT, int TAPS, int MT, int STAGES>
 struct ConvCfg {
   static constexpr int kPad = TAPS == 9 ? 1 : 0;

@@ -97,3 +97,26 @@ def test_latent_da_config_block_is_read_verbatim():
     gi, ic, gs, sc = training.latent_da_configs(opt)
     assert gi and gs and ic["loss_name"] == "mse" and sc["loss_name"] == "ce"
     assert training.latent_da_configs({"learning": {"latent_DA": False}}) == (False, None, False, None)
+
+
+def test_flat_bucket_aligns_weight_views_to_16_bytes():
+    """The weight-gradient kernels accumulate straight into these views with 16-byte reductions
+    (trainpath.accumulate_into_grads): every multi-dimensional parameter starts on a 16-byte boundary, the views tile
+    the buffer without overlap, and the padding elements are (and stay) zero."""
+    from cooperative_training_and_latent_space_data_augmentation_b200 import training
+    torch.manual_seed(0)
+    net = nn.Sequential(nn.Conv2d(2, 3, 3), nn.BatchNorm2d(3), nn.Conv2d(3, 1, 1), nn.Conv2d(1, 5, 3))
+    bucket = training.FlatGradBucket(list(net.parameters()))
+    assert bucket.numel == sum(p.numel() for p in net.parameters()) and bucket.flat.numel() >= bucket.numel
+    covered = torch.zeros(bucket.flat.numel(), dtype=torch.bool)
+    for p, off in zip(bucket.params, bucket.offsets):
+        if p.dim() > 1:
+            assert off % 4 == 0 and p.grad.data_ptr() % 16 == 0
+        assert p.grad.data_ptr() == bucket.flat.data_ptr() + 4 * off and p.grad.shape == p.shape
+        assert not covered[off:off + p.numel()].any()
+        covered[off:off + p.numel()] = True
+    net(torch.ones(2, 2, 9, 9)).sum().backward()
+    assert bucket.attached()
+    assert float(bucket.flat[~covered].abs().sum()) == 0.0
+    bucket.zero()
+    assert float(bucket.flat.abs().sum()) == 0.0 and bucket.attached()

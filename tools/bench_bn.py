@@ -37,7 +37,6 @@ def main():
         gamma = torch.ones(C, device="cuda"); beta = torch.zeros(C, device="cuda")
         scale, shift, mean, var = ops.bn_batch_affine_c8(a, gamma, beta, 1e-5, want_stats=True)
         h = ops.scale_shift_act_c8(a, scale, shift, ops.ACT_LRELU)
-        T = a.numel() * 2 / 1e3          # KB -> us*GB/s bookkeeping below uses bytes/us = MB/s... keep bytes
         nbytes = a.numel() * 2
         ws = torch.empty(lib.ctl_reduce_workspace_bytes(B, C), device="cuda", dtype=torch.uint8)
         coef = torch.empty((3, C), device="cuda"); pg = torch.empty((2, C), device="cuda"); da = torch.empty_like(a)
