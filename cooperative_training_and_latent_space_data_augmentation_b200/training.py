@@ -250,6 +250,10 @@ class GraphedCooperativeTrainer(CooperativeTrainer):
         super().__init__(solver, global_batch, seed, image_cfg, seg_cfg, group)
         self.eager_steps = eager_steps
         self.stream = torch.cuda.Stream()
+        self.copy_stream = torch.cuda.Stream()      # input prefetch (prefetch()): H2D under the previous step's compute
+        self._stage, self._prefetched = None, None
+        self._stage_consumed = torch.cuda.Event()
+        self._stage_consumed.record()
         self.pool = torch.cuda.graph_pool_handle()
         self.captured = {}
         self.static = None
@@ -265,13 +269,42 @@ class GraphedCooperativeTrainer(CooperativeTrainer):
         if tuple(clean.shape) != tuple(st["clean"].shape):
             raise ValueError("a graphed trainer replays ONE batch shape: got %s, captured %s"
                              % (tuple(clean.shape), tuple(st["clean"].shape)))
-        st["clean"].copy_(clean, non_blocking=True)
-        st["label"].copy_(label, non_blocking=True)
+        pf = self._prefetched
+        if pf is not None and pf["clean"] is clean and pf["label"] is label:
+            # the host -> device copy of this batch already ran on the copy stream, under the previous step's compute
+            torch.cuda.current_stream().wait_event(pf["ready"])
+            st["clean"].copy_(pf["dev_clean"], non_blocking=True)
+            st["label"].copy_(pf["dev_label"], non_blocking=True)
+            self._stage_consumed.record()
+            self._prefetched = None
+        else:
+            st["clean"].copy_(clean, non_blocking=True)
+            st["label"].copy_(label, non_blocking=True)
         if noise is not None:
             if st["noise"] is None:
                 st["noise"] = torch.empty_like(st["clean"])
             st["noise"].copy_(noise, non_blocking=True)
         return st["clean"], st["label"], (st["noise"] if noise is not None else None)
+
+    def prefetch(self, clean, label):
+        """Starts the host -> device copy of the NEXT step's batch (pinned host tensors) on a side stream, so that it
+        overlaps the step that is currently running; `step(clean, label)` with the SAME tensor objects then only does a
+        device-to-device copy into the graph's static inputs.  Input pipelining: call it right after `step` returns and
+        before reading that step's results.  The host tensors must not be modified until the next `step` has returned."""
+        if self.static is None or not (clean.device.type == "cpu" and clean.is_pinned() and label.is_pinned()):
+            return                                      # first step not staged yet / nothing to overlap
+        if self._stage is None:
+            self._stage = {"clean": torch.empty_like(self.static["clean"]), "label": torch.empty_like(self.static["label"])}
+        if tuple(clean.shape) != tuple(self._stage["clean"].shape) or tuple(label.shape) != tuple(self._stage["label"].shape):
+            return
+        self.copy_stream.wait_event(self._stage_consumed)   # the previous batch has left the staging buffers
+        with torch.cuda.stream(self.copy_stream):
+            self._stage["clean"].copy_(clean, non_blocking=True)
+            self._stage["label"].copy_(label, non_blocking=True)
+            ready = torch.cuda.Event()
+            ready.record()
+        self._prefetched = {"clean": clean, "label": label, "ready": ready, "dev_clean": self._stage["clean"],
+                            "dev_label": self._stage["label"]}
 
     def _eager(self, clean, label, noise):
         return cooperative_step(self.solver, clean, label, self.image_cfg, self.seg_cfg, noise=noise,

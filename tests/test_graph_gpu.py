@@ -33,7 +33,7 @@ FIXED_CFG = ({"loss_name": "mse", "mask_type": "channel", "max_threshold": 0.5, 
               "if_soft": True})
 
 
-def _run(pkg, trainer_cls, cfgs, steps, **kw):
+def _run(pkg, trainer_cls, cfgs, steps, prefetch=False, **kw):
     torch.manual_seed(0)
     solver = pkg.AdvancedTripletReconSegmentationModel('FCN_16_standard', num_classes=4, learning_rate=1e-5)
     for name, m in solver.model.items():
@@ -41,10 +41,13 @@ def _run(pkg, trainer_cls, cfgs, steps, **kw):
     solver.set_optimizers(capturable=True)
     trainer = trainer_cls(solver, 4, seed=3, image_cfg=cfgs[0], seg_cfg=cfgs[1], **kw)
     img, lab, noise = weights.synthetic_batch(4, 64, 64, seed=2)
-    img, lab, noise = img.cuda(), lab.cuda(), noise.cuda()
+    noise = noise.cuda()
+    img, lab = (img.pin_memory(), lab.pin_memory()) if prefetch else (img.cuda(), lab.cuda())
     losses, pert = [], []
     for _ in range(steps):
         out = trainer.step(img, lab, noise)
+        if prefetch:
+            trainer.prefetch(img, lab)          # next step's H2D copy on the side stream, consumed by the next step()
         losses.append({k: float(v) for k, v in out.items() if k.startswith('loss')})
         pert.append((out['perturbed_image'].float().clone(), out['perturbed_seg'].float().clone()))
     torch.cuda.synchronize()
@@ -89,6 +92,22 @@ def test_graph_replay_matches_eager_steps(pkg, cfgs):
     # the perturbed examples of the replayed steps: same masks (k, draws) -> same images (a wrong k or draw gives O(1)
     # on every sample).  The bit-exact check of the device-resident parameters is test_step_params_reach_the_kernels.
     for step in range(2, strict):
+        for a, b in zip(got_p[step], want_p[step]):
+            d = (a - b).flatten(1).norm(dim=1) / b.flatten(1).norm(dim=1).clamp_min(1e-6)
+            assert float(d.max()) < 0.02, (step, d.tolist())
+
+
+def test_prefetched_inputs_give_the_same_steps(pkg):
+    """GraphedCooperativeTrainer.prefetch: the batch copied host -> device on the side stream under the previous step is
+    the batch the next step trains on (strict window: the two eager and the first two replayed steps)."""
+    steps = 4
+    _, want, want_p, _ = _run(pkg, pkg.GraphedCooperativeTrainer, FIXED_CFG, steps, eager_steps=2)
+    trainer, got, got_p, _ = _run(pkg, pkg.GraphedCooperativeTrainer, FIXED_CFG, steps, prefetch=True, eager_steps=2)
+    assert trainer._prefetched is not None and trainer._stage is not None      # the last prefetch is pending
+    for step, (g, w) in enumerate(zip(got, want)):
+        for key in w:
+            assert abs(g[key] - w[key]) <= 2e-3 * max(1.0, abs(w[key])), (step, key, g[key], w[key])
+    for step in range(steps):
         for a, b in zip(got_p[step], want_p[step]):
             d = (a - b).flatten(1).norm(dim=1) / b.flatten(1).norm(dim=1).clamp_min(1e-6)
             assert float(d.max()) < 0.02, (step, d.tolist())
