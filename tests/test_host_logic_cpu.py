@@ -31,3 +31,110 @@ def test_packed_weight_cache_follows_every_kind_of_update():
     fastpath.weights_changed()
     fastpath._packed(q, pack)
     assert len(calls) == 7
+
+
+def test_batched_pack_registry_refreshes_every_weight_in_one_launch(monkeypatch):
+    """fastpath._PackRegistry (the conv weights' forward / input-gradient packings): first request packs alone and
+    registers a persistent buffer; after an optimizer step ONE batched launch refreshes every registered packing (job
+    table with one row per entry); a moved storage re-registers; the table must exist before a CUDA-graph capture."""
+    from cooperative_training_and_latent_space_data_augmentation_b200 import fastpath, ops
+    single, batched, capturing = [], [], [False]
+
+    def fake_pack_kernel(param, transposed):
+        single.append((id(param), transposed))
+        return param.detach().clone().reshape(-1)            # persistent "packed" buffer
+
+    def fake_pack_job(weight, transposed, out):
+        return [weight.data_ptr(), out.data_ptr(), weight.shape[0], weight.shape[1], 9, 16, int(transposed), 0]
+
+    def fake_batched(table, n_jobs, max_elements):
+        assert table.dtype == torch.int64 and tuple(table.shape) == (n_jobs, 8)
+        batched.append((n_jobs, max_elements, table.clone()))
+
+    monkeypatch.setattr(ops, "_pack_kernel", fake_pack_kernel)
+    monkeypatch.setattr(ops, "pack_job", fake_pack_job)
+    monkeypatch.setattr(ops, "pack_conv_weights_batched", fake_batched)
+    monkeypatch.setattr(torch.cuda, "is_current_stream_capturing", lambda: capturing[0])
+    reg = fastpath._PackRegistry()
+    w1 = torch.nn.Parameter(torch.randn(16, 16, 3, 3))
+    w2 = torch.nn.Parameter(torch.randn(32, 16, 3, 3))
+    a1 = reg.get(w1, False, 'fwd')
+    a1d = reg.get(w1, True, 'dgrad')
+    a2 = reg.get(w2, False, 'fwd')
+    assert len(single) == 3 and not batched and reg.dirty
+    assert reg.get(w1, False, 'fwd') is a1 and len(single) == 3                 # cached within the same weights epoch
+    fastpath.weights_changed()                                                   # = an optimizer stepped
+    assert reg.get(w2, False, 'fwd') is a2                                      # same persistent buffer ...
+    assert len(batched) == 1 and batched[0][0] == 3 and batched[0][1] == w2.numel()   # ... refreshed with ALL others
+    rows = batched[0][2]
+    assert sorted(rows[:, 0].tolist()) == sorted([w1.data_ptr(), w1.data_ptr(), w2.data_ptr()])
+    assert sorted(rows[:, 1].tolist()) == sorted([a1.data_ptr(), a1d.data_ptr(), a2.data_ptr()])
+    assert reg.get(w1, False, 'fwd') is a1 and reg.get(w1, True, 'dgrad') is a1d and len(batched) == 1
+    assert len(single) == 3 and not reg.dirty
+    with torch.no_grad():
+        w1.mul_(2.0)                                                             # in-place edit (version bump) -> refresh
+    reg.get(w1, False, 'fwd')
+    assert len(batched) == 2
+    w2.data = torch.zeros(32, 16, 3, 3)                                          # storage moved -> packed alone, re-registered
+    b2 = reg.get(w2, False, 'fwd')
+    assert len(single) == 4 and b2 is not a2 and reg.dirty
+    # a capture must find the table built: a stale table raises instead of copying host -> device inside the capture
+    fastpath.weights_changed()
+    capturing[0] = True
+    try:
+        reg.get(w1, False, 'fwd')
+        raised = False
+    except RuntimeError:
+        raised = True
+    assert raised
+    capturing[0] = False
+    reg._rebuild_table()
+    capturing[0] = True
+    reg.get(w1, False, 'fwd')                                                    # table ready: the launch is capturable
+    assert len(batched) == 3 and batched[2][0] == 3
+    w3 = torch.nn.Parameter(torch.randn(16, 16, 1, 1))
+    try:
+        reg.get(w3, False, 'fwd')                                                # first sight of a weight inside a capture
+        raised = False
+    except RuntimeError:
+        raised = True
+    assert raised
+
+
+def test_grads_direct_mode_accumulates_in_place_and_returns_none():
+    """trainpath._Grads: inside accumulate_into_grads() parameters that own a .grad receive their gradients in place
+    (kernel-accumulated buffers are the .grad itself, small vectors go through one foreach add, a second contribution
+    to the same parameter is added immediately) and autograd gets None; outside, or when a .grad is missing, gradients
+    are returned and summed per parameter."""
+    from cooperative_training_and_latent_space_data_augmentation_b200 import trainpath
+    w = torch.nn.Parameter(torch.zeros(2, 3, 1, 1))
+    b = torch.nn.Parameter(torch.zeros(2))
+    frozen = torch.nn.Parameter(torch.zeros(2), requires_grad=False)
+    params, needs = (w, b, frozen), (True, True, False)
+    # ordinary mode: returned, summed, frozen parameter ignored
+    g = trainpath._Grads(params, needs)
+    assert not g.direct
+    buf = g.buffer(w)
+    assert buf.shape == w.shape and float(buf.abs().sum()) == 0.0
+    buf += 1.0
+    g.add(w, buf)
+    g.add(b, torch.ones(2)); g.add(b, 2 * torch.ones(2)); g.add(frozen, torch.ones(2)); g.add(b, None)
+    out = g.results(params)
+    assert torch.equal(out[0], torch.ones_like(w)) and torch.equal(out[1], 3 * torch.ones(2)) and out[2] is None
+    # direct mode needs the context AND existing .grad tensors
+    with trainpath.accumulate_into_grads():
+        assert not trainpath._Grads(params, needs).direct            # no .grad yet
+    w.grad, b.grad = torch.full_like(w, 10.0), torch.full_like(b, 10.0)
+    assert not trainpath._Grads(params, needs).direct                # .grad exists but the context is off
+    with trainpath.accumulate_into_grads():
+        g = trainpath._Grads(params, needs)
+        assert g.direct and g.arena is None
+        buf = g.buffer(w)
+        assert buf.data_ptr() == w.grad.data_ptr()                   # kernels accumulate into .grad itself
+        buf += 1.0
+        g.add(w, buf)                                                # ... and that is not added a second time
+        g.add(b, torch.ones(2)); g.add(b, 2 * torch.ones(2)); g.add(frozen, torch.ones(2))
+        out = g.results(params)
+    assert out == (None, None, None)
+    assert torch.equal(w.grad, torch.full_like(w, 11.0)) and torch.equal(b.grad, torch.full_like(b, 13.0))
+    assert not trainpath._DIRECT["on"]
