@@ -718,9 +718,10 @@ _CE_WS = {}
 
 
 def _ce_workspace(device):
-    """16 zeroed bytes per device (fp64 sum + CTA ticket); ctl_ce2d_fwd leaves them zeroed, so one buffer serves every
-    call of the stream -- also inside a captured CUDA graph (persistent address)."""
-    key = (device.type, device.index)
+    """16 zeroed bytes per (device, stream) (fp64 sum + CTA ticket); ctl_ce2d_fwd leaves them zeroed, so one buffer
+    serves every call of that stream -- also inside a captured CUDA graph (persistent address).  Per stream because two
+    streams running the kernel concurrently must not share the accumulator."""
+    key = (device.type, device.index, _stream())
     ws = _CE_WS.get(key)
     if ws is None:
         ws = _CE_WS[key] = torch.zeros(2, device=device, dtype=torch.float64)
