@@ -138,3 +138,42 @@ def test_grads_direct_mode_accumulates_in_place_and_returns_none():
     assert out == (None, None, None)
     assert torch.equal(w.grad, torch.full_like(w, 11.0)) and torch.equal(b.grad, torch.full_like(b, 13.0))
     assert not trainpath._DIRECT["on"]
+
+
+def test_identities_the_kernel_path_relies_on():
+    """(1) a 1x1 convolution commutes with nearest-neighbour up-sampling (trainpath.residual_fwd takes the shortcut of
+    res_up_family, encoder_decoder.py:294-296 / :334-337, at the low resolution); (2) the (hi | lo | hi) x (w_hi | w_hi |
+    w_lo) channel-group layout of the tensor-core stem reproduces the fp32 product to ~2^-16 although every operand the
+    tensor core sees is bf16 (ops.pad_stem_weight / ctl_stem_input_c8)."""
+    import torch.nn.functional as F
+    from cooperative_training_and_latent_space_data_augmentation_b200 import ops
+    g = torch.Generator().manual_seed(0)
+    x = torch.randn(2, 8, 5, 7, generator=g)
+    w = torch.randn(4, 8, 1, 1, generator=g)
+    b = torch.randn(4, generator=g)
+    up = lambda t: F.interpolate(t, scale_factor=2, mode='nearest')
+    assert torch.equal(F.conv2d(up(x), w, b), up(F.conv2d(x, w, b)))
+
+    cin = 4
+    xs = torch.rand(2, cin, 9, 11, generator=g)
+    ws = 0.3 * torch.randn(16, cin, 3, 3, generator=g)
+    bf = lambda t: t.to(torch.bfloat16).to(torch.float32)
+    hi = bf(xs)
+    x16 = torch.zeros(2, 16, 9, 11)
+    x16[:, :cin], x16[:, cin:2 * cin], x16[:, 2 * cin:3 * cin] = hi, bf(xs - hi), hi       # what ctl_stem_input_c8 writes
+    w16 = bf(ops.pad_stem_weight(ws))                                                     # the packing rounds to bf16
+    want = F.conv2d(xs.double(), ws.double(), padding=1)
+    got = F.conv2d(x16.double(), w16.double(), padding=1)
+    plain = F.conv2d(hi.double(), bf(ws).double(), padding=1)                             # single bf16 operands
+    scale = float(want.abs().max())
+    assert float((got - want).abs().max()) < 3e-5 * scale
+    assert float((plain - want).abs().max()) > 20 * float((got - want).abs().max())       # what the split buys
+    # the weight gradient's two channel groups add up to sum dy * x
+    dy = torch.randn(2, 16, 9, 11, generator=g)
+    xi = x16.clone().requires_grad_(False)
+    w_var = torch.zeros(16, 16, 3, 3, requires_grad=True)
+    F.conv2d(xi, w_var, padding=1).backward(dy)
+    w_ref = ws.clone().requires_grad_(True)
+    F.conv2d(xs, w_ref, padding=1).backward(dy)
+    err = (ops.stem_weight_grad(w_var.grad, cin) - w_ref.grad).abs().max()
+    assert float(err) < 3e-5 * float(w_ref.grad.abs().max())
