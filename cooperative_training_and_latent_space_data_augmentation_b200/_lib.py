@@ -65,6 +65,11 @@ SIGNATURES = {
     "ctl_stem_dgrad_c8": (_i, [_vp, _vp, _i, _f, _i64, _i64, _i64, _i64, _vp, _vp, _vp]),
     "ctl_ce2d_fwd": (_i, [_vp, _vp, _i64, _i64, _i64, _i64, _c.c_double, _vp, _vp, _vp]),
     "ctl_ce2d_bwd": (_i, [_vp, _vp, _i64, _i64, _i64, _i64, _c.c_double, _vp, _vp, _vp]),
+    "ctl_adam_flat": (_i, [_vp, _vp, _vp, _vp, _c.POINTER(_i64), _i, _c.c_uint, _vp, _f, _f, _f, _f, _f, _f, _i, _vp]),
+    "ctl_sse_fwd": (_i, [_vp, _vp, _i64, _c.c_double, _vp, _vp, _vp]),
+    "ctl_sse_bwd": (_i, [_vp, _vp, _i64, _c.c_double, _vp, _vp, _vp]),
+    "ctl_confusion_update": (_i, [_vp, _vp, _vp, _i64, _i64, _i64, _vp, _vp, _vp]),
+    "ctl_confusion_scores": (_i, [_vp, _i64, _vp, _vp]),
 }
 
 _lib = None
@@ -78,7 +83,9 @@ KERNELS_PER_CALL = {"ctl_saliency_reduce": 1, "ctl_topp_mask_apply": 2, "ctl_sal
                     "ctl_conv_wgrad_c8_bf16": 1, "ctl_channel_sums_c8": 2, "ctl_bn_affine_from_sums": 1, "ctl_pack_conv_weight": 1, "ctl_bn_bwd_reduce_c8": 2,
                     "ctl_bn_bwd_apply_c8": 1, "ctl_act_bwd_c8": 1, "ctl_downsample2x_sum_c8": 1,
                     "ctl_zero_stuff2x_c8": 1, "ctl_split_parity2x2_c8": 1, "ctl_head_bwd_c8": 1,
-                    "ctl_stem_wgrad_c8": 1, "ctl_stem_dgrad_c8": 1, "ctl_ce2d_fwd": 1, "ctl_ce2d_bwd": 1, "ctl_scale_shift_upadd_act_c8": 1, "ctl_pack_conv_weights_batched": 1, "ctl_stem_input_c8": 1}
+                    "ctl_stem_wgrad_c8": 1, "ctl_stem_dgrad_c8": 1, "ctl_ce2d_fwd": 1, "ctl_ce2d_bwd": 1, "ctl_scale_shift_upadd_act_c8": 1, "ctl_pack_conv_weights_batched": 1, "ctl_stem_input_c8": 1,
+                    "ctl_adam_flat": 2, "ctl_sse_fwd": 1, "ctl_sse_bwd": 1, "ctl_confusion_update": 1,
+                    "ctl_confusion_scores": 1}
 LAUNCHES = {"count": 0}
 
 

@@ -1,103 +1,78 @@
-"""Arithmetic of the FTN/STN conv blocks.
+"""Numerics-mode switch of the FTN/STN conv blocks.
 
-Three numerics modes, selected with `set_precision`:
-  'fp32'    parity mode: the exact op sequence of the reference in fp32 (what the reference itself
-            runs on a GPU); used by the parity tests that compare against the CPU oracle at 1e-4.
-  'kernel'  product mode: whole sub-networks run forward AND backward on this build's sm_100a kernels
-            (trainpath.py / fastpath.py; bf16 C8 activations, fp32 master weights and statistics).  The
-            functions below are then only reached for the one case the kernels do not cover (eval-mode
-            BatchNorm with autograd enabled), where they behave like 'bf16'.
-  'bf16'    library comparison mode: bf16 activations in NHWC (channels_last) through cuDNN.
+The product computes the conv blocks on this build's sm_100a kernels only -- `'kernel'`, the default: whole
+sub-networks run forward AND backward through trainpath.py / fastpath.py (bf16 C8 activations, fp32 master weights and
+statistics).  There is no library (cuDNN) path in this package and no dispatch between back ends.
 
-Every function takes the reference-shaped nn.Module that owns the parameters, so BatchNorm
-bookkeeping (training flag, track_running_stats, momentum, num_batches_tracked) follows the
-module state exactly as in the reference -- including inside `_disable_tracking_bn_stats`.
+For parity testing and for the eager-GPU baseline of bench.py a *yardstick* -- torch / cuDNN restatements of the same
+blocks, `yardstick/torch_modes.py` at the repository root, beside the oracle -- can be installed with
+`install_yardstick(module)`; only then are `set_precision('fp32')` (the reference's own fp32 op sequence) and
+`set_precision('bf16')` (cuDNN bf16) accepted, and only then do inputs the kernels do not cover (eval-mode BatchNorm
+with autograd enabled) have somewhere to go.  Without a yardstick those cases raise.
 """
-import torch
-import torch.nn.functional as F
-
-_PRECISION = "fp32"
+_PRECISION = "kernel"
+_YARDSTICK = None
 LRELU_SLOPE = 0.2
+
+
+def install_yardstick(module):
+    """Registers the torch-ops restatement of the blocks (test / baseline infrastructure, never imported by the package)."""
+    global _YARDSTICK
+    _YARDSTICK = module
+
+
+def yardstick_installed():
+    return _YARDSTICK is not None
 
 
 def set_precision(mode):
     global _PRECISION
     if mode not in ("fp32", "bf16", "kernel"):
-        raise ValueError("precision must be 'fp32', 'bf16' or 'kernel'")
+        raise ValueError("precision must be 'kernel' (product) or, with a yardstick installed, 'fp32' / 'bf16'")
+    if mode != "kernel" and _YARDSTICK is None:
+        raise RuntimeError("precision %r is a library-convolution yardstick mode; the product package has no such path. "
+                           "Tests and baselines install one first: `import yardstick; yardstick.install()`" % (mode,))
     _PRECISION = mode
-    _apply_tf32_policy()
-
-
-def _apply_tf32_policy():
-    # parity mode must be true fp32: torch lets cuDNN use TF32 for fp32 convolutions by default
-    torch.backends.cudnn.allow_tf32 = _PRECISION != "fp32"
-    torch.backends.cuda.matmul.allow_tf32 = _PRECISION != "fp32"
+    if _YARDSTICK is not None:
+        _YARDSTICK.set_mode(mode)
 
 
 def get_precision():
     return _PRECISION
 
 
-_apply_tf32_policy()
-
-
-def _prep(x):
-    """bf16 mode keeps activations NHWC bf16 end to end; fp32 mode leaves the tensor alone."""
-    if _PRECISION != "fp32":
-        if x.dtype != torch.bfloat16:
-            x = x.to(torch.bfloat16)
-        return x.contiguous(memory_format=torch.channels_last)
-    return x
-
-
-def _conv(conv, x):
-    if _PRECISION != "fp32":
-        return F.conv2d(x, conv.weight.to(torch.bfloat16), conv.bias.to(torch.bfloat16) if conv.bias is not None
-                        else None, conv.stride, conv.padding)
-    return conv(x)
-
-
-def _bn(bn, x):
-    # nn.BatchNorm2d.forward handles training / eval / track_running_stats=False (batch stats, no update);
-    # cuDNN computes the statistics in fp32 for bf16 inputs.
-    return bn(x)
+def _yardstick(what):
+    if _YARDSTICK is None:
+        raise NotImplementedError(
+            "%s is not covered by the sm_100a kernels of this build (they take CUDA tensors, train-mode BatchNorm, or "
+            "eval-mode BatchNorm under torch.no_grad(), H and W multiples of 16) and the product has no library "
+            "fallback" % what)
+    return _YARDSTICK
 
 
 def resample_down(down, x):
-    return _conv(down, _prep(x))
+    return _yardstick("this stride-2 convolution").resample_down(down, x)
 
 
 def resample_up(up, up_type, x):
-    x = _prep(x)
-    if up_type == 'NN':
-        return F.interpolate(x, scale_factor=2, mode='nearest')
-    if _PRECISION != "fp32":
-        return F.conv_transpose2d(x, up.weight.to(torch.bfloat16), up.bias.to(torch.bfloat16), stride=2)
-    return up(x)
+    return _yardstick("this up-sampling block").resample_up(up, up_type, x)
 
 
 def double_conv(seq, x, final_act=None):
-    """conv3x3 - BN - LReLU(0.2) - conv3x3 - BN [- act]   (nn.Sequential indices 0,1,2,3,4[,5])."""
-    x = _prep(x)
-    y = F.leaky_relu(_bn(seq[1], _conv(seq[0], x)), LRELU_SLOPE)
-    y = _bn(seq[4], _conv(seq[3], y))
-    return final_act(y) if final_act is not None else y
+    return _yardstick("this double convolution").double_conv(seq, x, final_act)
 
 
 def residual_block(block, x):
-    """LReLU(conv1x1(x) + double_conv(x)); x is already resampled."""
-    return F.leaky_relu(_conv(block.conv_input, x) + double_conv(block.conv, x), LRELU_SLOPE)
+    return _yardstick("this residual block").residual_block(block, x)
 
 
 def stem(inc, x):
-    return F.leaky_relu(double_conv(inc, x), LRELU_SLOPE)
+    return _yardstick("this encoder stem").stem(inc, x)
 
 
 def conv_bn_act(conv, bn, x, act):
-    y = _bn(bn, _conv(conv, _prep(x)))
-    return act(y) if act is not None else y
+    return _yardstick("this convolution").conv_bn_act(conv, bn, x, act)
 
 
 def head(conv, x, last_act):
-    y = _conv(conv, _prep(x))
-    return last_act(y) if last_act is not None else y
+    return _yardstick("this output head").head(conv, x, last_act)

@@ -109,7 +109,7 @@ __device__ __forceinline__ void conv_epilogue(const ConvParams& p, const uint32_
   const int act = p.act;
   const int tiles_per_img = p.tiles_x * p.tiles_y;
   const int num_tiles = (int)p.num_tiles;         // < 2^31 (checked on the host)
-  const int first_item = (p.diag & 8) ? kItems : half;
+  const int first_item = CTL_DIAGF(p, 8) ? kItems : half;
   // train-mode BatchNorm statistics of the stored (bf16-rounded) outputs: every thread owns one 16-column chunk
   float st_s[STATS ? 16 : 1], st_q[STATS ? 16 : 1];
 #pragma unroll
@@ -127,7 +127,7 @@ __device__ __forceinline__ void conv_epilogue(const ConvParams& p, const uint32_
     g.y = ty * kTileH + py;
     g.xb = tx * (8 * MT) + px;
     // plain geometry (stride 1, no ConvTranspose scatter): one 64-bit base per tile, items differ by constants
-    g.y_ok = g.y < p.H && !(p.diag & 4);
+    g.y_ok = g.y < p.H && !CTL_DIAGF(p, 4);
     g.pix = ((int64_t)g.img * (p.Cout >> 3) + (n0 >> 3)) * plane + ((int64_t)g.y * p.W + g.xb) * 8;
     return g;
   };
@@ -140,7 +140,7 @@ __device__ __forceinline__ void conv_epilogue(const ConvParams& p, const uint32_
       return g.pix + mt * 64 + (int64_t)((c0 >> 3) + h8) * plane;
     }
     const int y = g.y, x = g.xb + mt * 8;
-    valid = y < p.H && x < p.W && !(p.diag & 4);
+    valid = y < p.H && x < p.W && !CTL_DIAGF(p, 4);
     const int n = n0 + c0 + 8 * h8;              // GEMM column of this plane's first channel
     if (p.up2x) {
       const int cq = p.Cout >> 2, qd = n / cq, co = n - qd * cq;       // n = (dy*2+dx)*Cout/4 + co
@@ -365,7 +365,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap, const ConvParams p) {
         const int ty = rem / p.tiles_x, tx = rem - ty * p.tiles_x;
         const int y0 = ty * kTileH - Cfg::kPad, x0 = tx * (8 * MT) - Cfg::kPad;
         mbar_wait(&empty[stage], phase ^ 1);
-        if (p.diag & 2) {
+        if (CTL_DIAGF(p, 2)) {
           mbar_arrive(&full[stage]);
         } else {
           mbar_arrive_expect_tx(&full[stage], Cfg::kStageTxBytes);
@@ -389,7 +389,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap, const ConvParams p) {
         mbar_wait(&full[stage], phase);
         tc_fence_after();
         const uint32_t a_base = smem_u32(sA + stage * kStageStride);
-        if (!(p.diag & 1)) {
+        if (!CTL_DIAGF(p, 1)) {
 #pragma unroll
         for (int mt = 0; mt < MT; ++mt) {
           const uint32_t d_tmem = tmem_base + (uint32_t)((acc * MT + mt) * NT);

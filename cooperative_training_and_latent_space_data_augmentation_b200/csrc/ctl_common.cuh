@@ -12,7 +12,15 @@ namespace ctl {
 void set_error(const char* fmt, ...);
 int cuda_fail(cudaError_t e, const char* what);   // records the message, returns CTL_ERR_CUDA
 int sm_count();                                   // cached per device; <0 on error
-int diag_flags();                                 // env CTL_DIAG_SKIP (profiling by elimination; 0 in normal use)
+int diag_flags();                                 // env CTL_DIAG_SKIP; always 0 unless the library is built with -DCTL_DIAG
+
+// Profiling by elimination (tools/diag_conv.py) exists only in a -DCTL_DIAG build (make DIAG=1): the shipped kernels
+// contain no work-skipping switch.
+#ifdef CTL_DIAG
+#define CTL_DIAGF(p, bit) (((p).diag & (bit)) != 0)
+#else
+#define CTL_DIAGF(p, bit) (false)
+#endif
 
 #define CTL_CUDA_OK(expr, what)                         \
   do {                                                  \

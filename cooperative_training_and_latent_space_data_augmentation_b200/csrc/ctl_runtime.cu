@@ -37,10 +37,15 @@ int sm_count() {
 }
 
 // Profiling by elimination (tools/diag_conv.py): stages of the tcgen05 kernels can be switched off to see which one
-// bounds the pipeline.  Results are garbage with any bit set; never set outside the diagnostic tool.
+// bounds the pipeline.  Results are garbage with any bit set; never set outside the diagnostic tool.  Compiled in only with -DCTL_DIAG
+// (make DIAG=1); the default build ignores the variable and the kernels carry no skip branches.
 int diag_flags() {
+#ifdef CTL_DIAG
   const char* e = getenv("CTL_DIAG_SKIP");
   return e ? atoi(e) : 0;
+#else
+  return 0;
+#endif
 }
 }  // namespace ctl
 

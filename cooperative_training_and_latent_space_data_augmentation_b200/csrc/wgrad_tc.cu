@@ -140,7 +140,7 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constan
         const int y0 = ty * kWgTH, x0 = tx * kWgTW;
         uint8_t* sx = smem + stage * Cfg::kStage;
         mbar_wait(&empty[stage], phase ^ 1);
-        if (p.diag & 2) {
+        if (CTL_DIAGF(p, 2)) {
           mbar_arrive(&full[stage]);
         } else {
           mbar_arrive_expect_tx(&full[stage], Cfg::kXStage + Cfg::kDStage);
@@ -165,7 +165,7 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constan
         const uint32_t xs = smem_u32(smem + stage * Cfg::kStage);
         const uint32_t ds = xs + Cfg::kXStage;
 #pragma unroll 1
-        for (int y = (p.diag & 1) ? kWgTH : 0; y < kWgTH; y += (Cfg::kPair ? 2 : 1)) {
+        for (int y = CTL_DIAGF(p, 1) ? kWgTH : 0; y < kWgTH; y += (Cfg::kPair ? 2 : 1)) {
 #pragma unroll
           for (int xc = 0; xc < kWgTW; xc += 16) {
             // pair: N groups of 8 columns walk (dy row y, planes 0..P-1), (dy row y+1, planes 0..P-1): stride one line
@@ -207,9 +207,9 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constan
       // (tap, ci, co) has exactly one writer per pass, the staged block is stored in pass 0 and added to in pass 1
 #pragma unroll 1
       for (int d = 0; d < (Cfg::kPair ? 2 : 1); ++d) {
-        if (d == 1 && staged && !(p.diag & 4)) asm volatile("bar.sync 1, 128;" ::: "memory");
+        if (d == 1 && staged && !CTL_DIAGF(p, 4)) asm volatile("bar.sync 1, 128;" ::: "memory");
 #pragma unroll 1
-        for (int sx = (p.diag & 4) ? Cfg::kS : 0; sx < Cfg::kS; ++sx) {
+        for (int sx = CTL_DIAGF(p, 4) ? Cfg::kS : 0; sx < Cfg::kS; ++sx) {
 #pragma unroll
           for (int j = 0; j < Cfg::kG; ++j) {
             // accumulator row m of this thread: M = 128 -> TMEM lane m; M = 64 -> lane (m % 16) + 32 * (m / 16)
@@ -254,7 +254,7 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constan
           }
         }
       }
-      if (staged && !(p.diag & 4)) {
+      if (staged && !CTL_DIAGF(p, 4)) {
         asm volatile("bar.sync 1, 128;" ::: "memory");                 // the four epilogue warps only
         const float4* s4 = reinterpret_cast<const float4*>(stage);
         const int tid = threadIdx.x - 128;

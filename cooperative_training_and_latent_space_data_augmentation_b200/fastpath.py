@@ -148,10 +148,36 @@ def _act_code(module):
     raise NotImplementedError("activation %r has no fused epilogue" % (module,))
 
 
+_FROZEN_AFFINES = [None]       # dict (id(conv), id(bn)) -> (scale, shift) while a frozen_eval_affines() context is active
+
+
+class frozen_eval_affines:
+    """Inference on FIXED weights (inference.GraphedPredictor): inside the context the folded eval-mode BatchNorm affine
+    of every (conv, BatchNorm) pair is computed once and reused, instead of ~5 tiny launches per pair and forward.  The
+    dict is returned by __enter__ so the caller can keep it alive / reuse it (`frozen_eval_affines(cache)`)."""
+
+    def __init__(self, cache=None):
+        self.cache = {} if cache is None else cache
+
+    def __enter__(self):
+        self.prev, _FROZEN_AFFINES[0] = _FROZEN_AFFINES[0], self.cache
+        return self.cache
+
+    def __exit__(self, *exc):
+        _FROZEN_AFFINES[0] = self.prev
+        return False
+
+
 def _fold_eval(conv, bn):
     """conv bias + eval-mode BN -> per-channel (scale, shift)."""
+    cache = _FROZEN_AFFINES[0]
+    key = (id(conv), id(bn))
+    if cache is not None and key in cache:
+        return cache[key]
     scale = bn.weight.detach() * torch.rsqrt(bn.running_var + bn.eps)
     shift = bn.bias.detach() + (conv.bias.detach() - bn.running_mean) * scale
+    if cache is not None:
+        cache[key] = (scale, shift)
     return scale, shift
 
 

@@ -50,6 +50,14 @@ def cross_entropy_2D(input, target, weight=None, size_average=True, mask=None, i
     raise NotImplementedError
 
 
+def half_mse_loss(pred, target):
+    """0.5 * nn.MSELoss()(pred, target) (advanced...model.py:443-447) -- one fused kernel each way on CUDA fp32."""
+    pred = pred.float()
+    if ops.sse_supported(pred, target):
+        return ops.squared_error(pred, target, 0.5 / pred.numel())
+    return 0.5 * F.mse_loss(pred, target, reduction='mean')
+
+
 def basic_loss_fn(pred, target, loss_type='cross_entropy', class_weights=None, use_gpu=True):
     """Only the losses the ACDC configs select are built ('cross entropy', 'weighted cross entropy')."""
     num_classes = pred.size(1)

@@ -179,7 +179,11 @@ def _latent_gradient(latent_code, decoder_function, label, num_classes, loss_typ
     if loss_type == 'corr':
         loss = torch.mean(decoder_function(code) * gt_y)
     elif loss_type == 'mse':
-        loss = torch.mean((decoder_function(code) - gt_y) ** 2)
+        pred = decoder_function(code)
+        if ops.sse_supported(pred, gt_y):
+            loss = ops.squared_error(pred, gt_y, 1.0 / pred.numel())       # torch.mean((pred - gt)**2), one kernel each way
+        else:
+            loss = torch.mean((pred - gt_y) ** 2)
     elif loss_type == 'ce':
         loss = torch.mean(cross_entropy_2D(input=decoder_function(code), target=label, weight=None,
                                            size_average=True))
@@ -227,13 +231,17 @@ def _mask_latent_code(mode, latent_code, decoder_function, label, num_classes, p
     # reference's pinned torch 1.9, set_to_none=False): freeing them here would leave a captured CUDA graph of the
     # step zeroing / accumulating into gradient buffers that no longer exist, and would detach them from the
     # data-parallel gradient bucket.  Callables without that signature get the reference's bare call.
-    try:
+    flat = getattr(decoder_function, '_ctl_flat_segment', None)
+    if flat is not None and flat[0].attached():
+        flat[0].zero_grad(flat[1])                          # one memset of the decoder's slice of the flat gradients
+    else:
         try:
-            decoder_function.zero_grad(set_to_none=False)
-        except TypeError:
-            decoder_function.zero_grad()
-    except Exception:  # noqa: BLE001  (the reference swallows everything here)
-        pass
+            try:
+                decoder_function.zero_grad(set_to_none=False)
+            except TypeError:
+                decoder_function.zero_grad()
+        except Exception:  # noqa: BLE001  (the reference swallows everything here)
+            pass
     return masked_latent_code, mask_all
 
 

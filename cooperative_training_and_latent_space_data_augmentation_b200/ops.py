@@ -768,3 +768,105 @@ def cross_entropy_2d(logits, target, scale=1.0):
         raise ValueError("cross_entropy_2d: unsupported logits %s %s / target %s %s"
                          % (tuple(logits.shape), logits.dtype, tuple(target.shape), target.dtype))
     return _CrossEntropy2D.apply(logits, target, scale)
+
+
+# ------------------------------------------------------------------------------------------------ fused squared error
+class _SquaredError(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, pred, target, scale):
+        x = pred.detach().contiguous()
+        t = target.detach().contiguous()
+        out = torch.empty(1, device=x.device, dtype=torch.float32)
+        with torch.cuda.device(x.device):
+            _lib.check(_lib.load().ctl_sse_fwd(x.data_ptr(), t.data_ptr(), x.numel(), float(scale),
+                                               _ce_workspace(x.device).data_ptr(), out.data_ptr(), _stream()))
+        ctx.save_for_backward(x, t)
+        ctx.scale = float(scale)
+        return out.view(())
+
+    @staticmethod
+    def backward(ctx, gout):
+        x, t = ctx.saved_tensors
+        g = gout.detach().to(torch.float32).contiguous()
+        dx = torch.empty_like(x)
+        with torch.cuda.device(x.device):
+            _lib.check(_lib.load().ctl_sse_bwd(x.data_ptr(), t.data_ptr(), x.numel(), ctx.scale, g.data_ptr(),
+                                               dx.data_ptr(), _stream()))
+        return dx, None, None
+
+
+def sse_supported(pred, target):
+    return (pred.is_cuda and target.is_cuda and pred.dtype == torch.float32 and target.dtype == torch.float32
+            and tuple(pred.shape) == tuple(target.shape) and pred.numel() > 0 and not target.requires_grad)
+
+
+def squared_error(pred, target, scale):
+    """scale * sum((pred - target)**2) as a 0-d fp32 tensor, differentiable w.r.t. pred (one kernel each way):
+    mean squared error with scale = 1/numel, the reference's 0.5 * MSELoss with scale = 0.5/numel."""
+    if not sse_supported(pred, target):
+        raise ValueError("squared_error: CUDA fp32 tensors of one shape expected, got %s %s / %s %s"
+                         % (tuple(pred.shape), pred.dtype, tuple(target.shape), target.dtype))
+    return _SquaredError.apply(pred, target, scale)
+
+
+# ------------------------------------------------------------------------------------------------ multi-tensor Adam
+def adam_flat(params, grads, exp_avg, exp_avg_sq, bounds, steps, lr, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.0,
+              grad_scale=1.0, zero_grad=False, seg_mask=None):
+    """One Adam step over flat fp32 buffers (ctl_adam_flat).  bounds: [(begin, end), ...] one element range per
+    optimizer segment; steps: device fp32 [len(bounds)] step counters (incremented by the call)."""
+    _need_cuda(params, grads, exp_avg, exp_avg_sq, steps)
+    import ctypes
+    n = len(bounds)
+    arr = (ctypes.c_int64 * (2 * n))(*[int(v) for b in bounds for v in b])
+    mask = (1 << n) - 1 if seg_mask is None else int(seg_mask)
+    with torch.cuda.device(params.device):
+        _lib.check(_lib.load().ctl_adam_flat(params.data_ptr(), grads.data_ptr(), exp_avg.data_ptr(), exp_avg_sq.data_ptr(),
+                                             arr, n, mask, steps.data_ptr(), float(lr), float(betas[0]), float(betas[1]),
+                                             float(eps), float(weight_decay), float(grad_scale), int(bool(zero_grad)),
+                                             _stream()))
+
+
+# ------------------------------------------------------------------------------------------------ evaluation metric
+def confusion_update(hist, gt, logits=None, pred_labels=None, want_labels=False):
+    """hist (uint64-as-int64 [C,C], row = gt, column = prediction) += confusion matrix of argmax(logits) (or of
+    pred_labels) against gt; returns the uint8 label map [N,H,W] when want_labels."""
+    src = logits if logits is not None else pred_labels
+    _need_cuda(src, gt, hist)
+    if logits is not None:
+        logits = logits.detach()
+        if logits.dtype != torch.float32 or not logits.is_contiguous():
+            logits = logits.to(torch.float32).contiguous()
+        N, C = logits.shape[0], logits.shape[1]
+        HW = logits[0, 0].numel()
+        shape = (N,) + tuple(logits.shape[2:])
+    else:
+        pred_labels = pred_labels.to(torch.int64).contiguous()
+        N, HW = pred_labels.shape[0], pred_labels[0].numel()
+        C = hist.shape[0]
+        shape = tuple(pred_labels.shape)
+    if gt is not None:
+        gt = gt.to(torch.int64).contiguous()
+        if gt.numel() != N * HW:
+            raise ValueError("gt has %d elements, predictions have %d" % (gt.numel(), N * HW))
+        if hist.dtype != torch.int64 or tuple(hist.shape) != (C, C) or not hist.is_contiguous():
+            raise ValueError("hist must be a contiguous int64 [%d,%d] tensor" % (C, C))
+    labels = torch.empty(shape, device=src.device, dtype=torch.uint8) if want_labels else None
+    with torch.cuda.device(src.device):
+        _lib.check(_lib.load().ctl_confusion_update(_ptr(logits), _ptr(pred_labels), _ptr(gt), N, C, HW,
+                                                    _ptr(hist) if gt is not None else 0, _ptr(labels), _stream()))
+    return labels
+
+
+def argmax_labels(logits):
+    """uint8 label map [N,H,W] = argmax over the class dimension of planar fp32 logits (first maximum)."""
+    return confusion_update(None, None, logits=logits, want_labels=True)
+
+
+def confusion_scores(hist):
+    """Device fp64 [4 + C]: overall acc, mean acc, frequency-weighted acc, mean IoU, IoU per class."""
+    _need_cuda(hist)
+    C = hist.shape[0]
+    out = torch.empty(4 + C, device=hist.device, dtype=torch.float64)
+    with torch.cuda.device(hist.device):
+        _lib.check(_lib.load().ctl_confusion_scores(hist.data_ptr(), C, out.data_ptr(), _stream()))
+    return out

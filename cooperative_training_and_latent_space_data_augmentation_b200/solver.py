@@ -22,13 +22,12 @@ from os.path import join
 
 import torch
 import torch.nn as nn
-import torch.nn.functional as F
-import torch.optim as optim
 
 from . import conv_blocks, model_util, ops
-from .losses import basic_loss_fn, construct_input
+from .losses import basic_loss_fn, construct_input, half_mse_loss
 from .model_util import (_disable_tracking_bn_stats, makeVariable, mask_latent_code_channel_wise,
                          mask_latent_code_spatial_wise, set_grad)
+from .optim import FlatAdam
 from .networks import Dual_Branch_Encoder, MyDecoder, MyEncoder, init_weights_kaiming
 
 
@@ -321,7 +320,7 @@ class AdvancedTripletReconSegmentationModel(nn.Module):
             self.z_i, self.z_s = z_i, z_s
         standard_supervised_loss = basic_loss_fn(pred=y_0, target=label_l.detach(), loss_type='cross entropy')
         image_recon = self.decode_image(z_i)
-        image_recon_loss = 0.5 * F.mse_loss(image_recon.float(), clean_image_l, reduction='mean')
+        image_recon_loss = half_mse_loss(image_recon, clean_image_l)      # 0.5 * MSELoss (advanced...model.py:443-447)
         if compute_gt_recon:
             gt_recon = self.recon_shape(label_l.detach(), is_label_map=True)
             gt_shape_recon_loss = basic_loss_fn(pred=gt_recon, target=label_l, loss_type='cross entropy')
@@ -372,11 +371,13 @@ class AdvancedTripletReconSegmentationModel(nn.Module):
             refined = self.recon_shape(pred_logit.detach())
             for i in range(n_steps):
                 prev, s_t = s_t, refined
-                if auto_stop and torch.sqrt(torch.mean((prev - s_t) ** 2)) < 1e-4:
+                stop = bool(auto_stop and torch.sqrt(torch.mean((prev - s_t) ** 2)) < 1e-4)
+                if stop:
                     s_t = prev
-                    break
                 if save_internal_predicts:
-                    internal_predicts[i] = [s_t]
+                    internal_predicts[i] = [s_t]        # recorded before the break, as the reference does (:636-640)
+                if stop:
+                    break
         return s_t, internal_predicts
 
     # ------------------------------------------------------------------ state
@@ -390,33 +391,60 @@ class AdvancedTripletReconSegmentationModel(nn.Module):
                 v.eval()
 
     def eval(self):
+        """Modules to eval mode, no-grad inference.  Documented deviation: the reference's eval() calls
+        train(if_testing=True), which sets `self.training` back to True (advanced...model.py:740-753), so a
+        fast_predict() issued after eval() but OUTSIDE predict() keeps autograd enabled on eval-mode modules there.
+        Here `self.training` stays False and fast_predict runs under torch.no_grad(): eval-mode BatchNorm with
+        autograd enabled is not on the hot path and has no kernel route (predict / evaluate, which wrap everything
+        in no_grad in the reference too, are unaffected)."""
         self.training = False
         self.train(if_testing=True)
         self.training = False
 
+    # ------------------------------------------------------------------ evaluation metric (on the device)
+    def set_running_metric(self):
+        from .metrics import runningScore
+        return runningScore(n_classes=self.num_classes)
+
+    def evaluate(self, input, targets_npy, n_iter=None):
+        """advanced...model.py:643-664: predict, arg-max, running-metric update -- the arg-max and the confusion
+        matrix stay on the device (metrics.runningScore); `targets_npy` may be a numpy array or a tensor [N,H,W].
+        Returns the logits; `self.cur_eval_predicts` holds the uint8 label map (device)."""
+        if getattr(self, 'running_metric', None) is None:
+            self.running_metric = self.set_running_metric()
+        n_iter = self.n_iter if n_iter is None else n_iter
+        self.train(if_testing=True)
+        pred = self.predict(input, n_iter=n_iter)
+        self.cur_eval_predicts = self.running_metric.update_from_logits(targets_npy, pred, want_labels=True)
+        self.cur_eval_images, self.cur_eval_gts = input, targets_npy
+        return pred
+
     def reset_all_optimizers(self):
         if self.optimizers is None:
             self.set_optimizers()
-        for v in self.optimizers.values():
-            v.zero_grad(set_to_none=getattr(self, '_grads_set_to_none', True))
+        self.flat_adam.zero_grad()                  # one memset of the flat gradient buffer (all five networks)
 
     def get_optimizer(self, model_name=None):
         assert self.optimizers, 'please set optimizers first before fetching'
         return self.optimizers if model_name is None else self.optimizers[model_name]
 
     def set_optimizers(self, capturable=None):
-        """Five Adam optimizers, one per sub-network (advanced...model.py:774-785).  capturable=True keeps the step
-        counters on the device so `optimize_all_params` can be recorded into a CUDA graph (same update rule)."""
+        """One Adam optimizer per sub-network (advanced...model.py:774-785), all five backed by ONE multi-tensor kernel
+        over flat parameter / gradient / moment buffers (optim.FlatAdam).  `solver.optimizers[name]` keeps the
+        torch.optim surface the reference uses (step / zero_grad / state_dict / load_state_dict / param_groups).
+        Step counters live on the device, so `optimize_all_params` can always be recorded into a CUDA graph
+        (`capturable` is accepted for compatibility and ignored).  Calling it again keeps the existing optimizer
+        state (moments, step counts): a trainer built after load_snapshots resumes where the checkpoint stopped."""
         assert self.model
-        if capturable is not None:
-            self._capturable = bool(capturable)
-        self.optimizers = {name: optim.Adam(m.parameters(), lr=self.learning_rate, fused=True,
-                                            capturable=getattr(self, '_capturable', False))
-                           for name, m in self.model.items()}
+        flat = getattr(self, 'flat_adam', None)
+        if flat is None:
+            flat = self.flat_adam = FlatAdam(self.model, lr=self.learning_rate)
+        elif not flat.attached():
+            flat.reattach()
+        self.optimizers = {name: flat.view(name) for name in self.model}
 
     def optimize_all_params(self):
-        for v in self.optimizers.values():
-            v.step()
+        self.flat_adam.step()                       # one launch for the five networks
 
     def optimize_params(self, model_name):
         self.optimizers[model_name].step()

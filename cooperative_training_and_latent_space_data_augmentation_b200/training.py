@@ -4,7 +4,8 @@ form over NCCL (the reference has no distributed code).
 
 Step = clean pass (standard_training) -> hard-example generation (latent masking, K1/K2) ->
 corrupted-image and corrupted-shape passes (hard_example_training) -> backward -> gradient
-all-reduce (one flat fp32 bucket, 2,528,953 elements) -> Adam.
+all-reduce (the flat fp32 gradient buffer of optim.FlatAdam, 2.53 M elements) -> ONE multi-tensor Adam launch that also
+takes the 1/world average.
 
 Differences from the reference loop that do not change results: losses stay on the device (the
 reference calls .item() nine times per step), no gc.collect()/empty_cache().
@@ -169,10 +170,38 @@ def broadcast_module_state(modules, src=0, group=None):
     for m in modules:
         for t in list(m.parameters()) + list(m.buffers()):
             dist.broadcast(t.data, src=src, group=group)
+    # the write went through .data: neither Tensor._version nor the optimizer hook saw it, and ranks != src may hold
+    # packed bf16 copies of their pre-broadcast weights (a forward that ran before the trainer was built)
+    from . import fastpath
+    fastpath.weights_changed()
+
+
+class _GradExchange:
+    """The data-parallel exchange of one step: ONE all-reduce (sum) of the solver's flat gradient buffer; the 1/world
+    average is applied inside the Adam kernel (FlatAdam.grad_scale), so no separate division pass runs."""
+
+    def __init__(self, flat_adam, group, world):
+        self.flat_adam, self.group, self.world = flat_adam, group, world
+        self.flat = flat_adam.flat_grads
+        flat_adam.grad_scale = 1.0 / world
+
+    def attached(self):
+        return self.flat_adam.attached()
+
+    def reattach(self):
+        self.flat_adam.reattach()
+
+    def all_reduce_sum(self):
+        if self.world > 1:
+            dist.all_reduce(self.flat, op=dist.ReduceOp.SUM, group=self.group)
+
+    def mean_gradients(self):
+        """The averaged gradient as the optimizer sees it (a copy; the buffer itself holds the sum)."""
+        return self.flat * (1.0 / self.world)
 
 
 class CooperativeTrainer:
-    """Batch-sharded cooperative training: one process per GPU, NCCL all-reduce of one flat bucket."""
+    """Batch-sharded cooperative training: one process per GPU, one NCCL all-reduce of the flat gradient buffer."""
 
     def __init__(self, solver, global_batch, seed=0, image_cfg=None, seg_cfg=None, group=None):
         self.solver = solver
@@ -185,21 +214,36 @@ class CooperativeTrainer:
         self.seg_cfg = seg_cfg or DEFAULT_SEG_CFG
         self.seed = seed
         self.step_index = 0
+        if solver.optimizers is None:
+            solver.set_optimizers()
+        if not solver.flat_adam.attached():
+            solver.flat_adam.reattach()
         broadcast_module_state(solver.model.values(), 0, group)
-        self.bucket = FlatGradBucket(list(solver.parameters()))
-        solver._grads_set_to_none = False          # keep .grad views of the flat bucket alive
+        self.bucket = _GradExchange(solver.flat_adam, group, self.world)
         seed_host_rng(seed)                         # identical host draws on every rank
         model_util.set_rng_mode("philox", seed=seed, first_sample=self.lo)
 
     def local_slice(self, global_tensor):
         return global_tensor[self.lo:self.hi]
 
+    def params_in_sync(self):
+        """True when every rank holds bit-identical parameters (checksum MIN == MAX over ranks of the flat parameter
+        buffer's sum and absolute sum, in fp64)."""
+        flat = self.solver.flat_adam.flat_params.double()
+        probe = torch.stack([flat.sum(), flat.abs().sum(), (flat * flat).sum()])
+        if self.world == 1:
+            return True
+        lo, hi = probe.clone(), probe.clone()
+        dist.all_reduce(lo, op=dist.ReduceOp.MIN, group=self.group)
+        dist.all_reduce(hi, op=dist.ReduceOp.MAX, group=self.group)
+        return bool(torch.equal(lo, hi))
+
     def step(self, clean_local, label_local, noise_local=None):
         """`clean_local` / `label_local` are this rank's slice of the global batch."""
         # Philox stream: advance first_sample by the global batch per step so no (sample, step) pair repeats
         model_util.native_rng().first_sample = self.step_index * self.global_batch + self.lo
         out = cooperative_step(self.solver, clean_local, label_local, self.image_cfg, self.seg_cfg,
-                               noise=noise_local, grad_sync=lambda: self.bucket.all_reduce_mean(self.group))
+                               noise=noise_local, grad_sync=self.bucket.all_reduce_sum)
         self.step_index += 1
         return out
 
@@ -220,34 +264,44 @@ def draw_host_params(cfg):
 
 
 class _CapturedStep:
-    """The two CUDA graphs of one (image mask type, shape mask type) combination and what their replay needs."""
+    """The CUDA graph of one (image mask type, shape mask type) combination and what its replay needs."""
 
     def __init__(self, device):
-        self.forward_backward = torch.cuda.CUDAGraph()
-        self.optimizers = torch.cuda.CUDAGraph()
+        self.graph = torch.cuda.CUDAGraph()
+        self.optimizers = None      # second graph, only when the all-reduce is NOT captured
         self.params = ops.StepParams(device)
         self.out = None
-        self.kernels = 0            # kernels of libctl_b200.so recorded in the two graphs
+        self.kernels = 0            # kernels of libctl_b200.so recorded in the graph(s)
 
 
 class GraphedCooperativeTrainer(CooperativeTrainer):
-    """CooperativeTrainer whose step is replayed from CUDA graphs (the step is ~2000 short launches: issued one by
+    """CooperativeTrainer whose step is replayed from ONE CUDA graph (the step is >1000 short launches: issued one by
     one from Python it is host-bound on a B200).
 
-    * graph 1 = zero grads + clean pass + hard-example generation + corrupted passes + backward; the NCCL all-reduce
-      of the flat gradient bucket stays an ordinary call between the graphs; graph 2 = the five Adam steps
+    * the graph = zero grads + clean pass + hard-example generation + corrupted passes + backward + the NCCL all-reduce
+      of the flat gradient buffer + the multi-tensor Adam launch (1/world folded in): nothing of a step is issued from
+      the host but the inputs' copy, one 192-byte parameter upload and the graph launch.
+      `capture_collective=False` (or env CTL_NO_CAPTURED_COLLECTIVE=1) keeps the all-reduce an ordinary call between a
+      forward/backward graph and an optimizer graph
     * inputs are copied into static buffers (so `step` takes host-pinned or device tensors alike); the returned losses
       and perturbed examples are static tensors that the NEXT step overwrites
     * the per-step host draws (mask type, percentile -> k) are made here exactly as the eager path makes them
       (`draw_host_params`), uploaded as device-resident step parameters (ops.StepParams) and read by the *_dyn
-      kernels; one pair of graphs is captured lazily per (image mask type, shape mask type) combination, all in one
-      memory pool
-    * the first `eager_steps` calls run eagerly on the capture stream (library / allocator warm-up)
+      kernels; one graph is captured lazily per (image mask type, shape mask type) combination, all in one memory pool
+    * the first `eager_steps` calls run eagerly on the capture stream (library / allocator / communicator warm-up)
+    * ONE batch shape per trainer; BatchNorm running statistics are per rank (rank 0's are the ones checkpointed)
+    * optimizer state (moments, step counts) lives in solver.flat_adam and is never recreated here: build the trainer
+      after `solver.load_snapshots(...)` to resume, or call load_snapshots later -- it copies in place, so captured
+      graphs stay valid
     """
 
-    def __init__(self, solver, global_batch, seed=0, image_cfg=None, seg_cfg=None, group=None, eager_steps=3):
-        solver.set_optimizers(capturable=True)      # fresh optimizers: device-side step counters
+    def __init__(self, solver, global_batch, seed=0, image_cfg=None, seg_cfg=None, group=None, eager_steps=3,
+                 capture_collective=True):
         super().__init__(solver, global_batch, seed, image_cfg, seg_cfg, group)
+        import os
+        if os.environ.get("CTL_NO_CAPTURED_COLLECTIVE", "0") == "1":
+            capture_collective = False
+        self.capture_collective = bool(capture_collective) or self.world == 1
         self.eager_steps = eager_steps
         self.stream = torch.cuda.Stream()
         self.copy_stream = torch.cuda.Stream()      # input prefetch (prefetch()): H2D under the previous step's compute
@@ -308,24 +362,28 @@ class GraphedCooperativeTrainer(CooperativeTrainer):
 
     def _eager(self, clean, label, noise):
         return cooperative_step(self.solver, clean, label, self.image_cfg, self.seg_cfg, noise=noise,
-                                grad_sync=lambda: self.bucket.all_reduce_mean(self.group))
+                                grad_sync=self.bucket.all_reduce_sum)
 
     def _capture(self, key, clean, label, noise):
         from . import fastpath
         cs = _CapturedStep(clean.device)
-        self.bucket.reattach()                      # every .grad is a view of the flat bucket before recording
+        if not self.bucket.attached():
+            self.bucket.reattach()                  # every parameter / .grad is a view of the flat buffers before recording
         fastpath.prepare_packing()                  # job table of the batched weight packing (host -> device copy)
         fastpath.weights_changed()                  # every packed weight is rebuilt INSIDE the graph
         n0 = _lib.LAUNCHES["count"]
         with model_util.recording_step_params(cs.params):
-            with torch.cuda.graph(cs.forward_backward, pool=self.pool, stream=self.stream):
+            with torch.cuda.graph(cs.graph, pool=self.pool, stream=self.stream):
                 cs.out = cooperative_step(self.solver, clean, label, self.image_cfg, self.seg_cfg, noise=noise,
-                                          grad_sync=None, optimize=False)
-        with torch.cuda.graph(cs.optimizers, pool=self.pool, stream=self.stream):
-            self.solver.optimize_all_params()
+                                          grad_sync=self.bucket.all_reduce_sum if self.capture_collective else None,
+                                          optimize=self.capture_collective)
+        if not self.capture_collective:
+            cs.optimizers = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(cs.optimizers, pool=self.pool, stream=self.stream):
+                self.solver.optimize_all_params()
         if not self.bucket.attached():
-            raise RuntimeError("a parameter gradient left the flat bucket during capture: the recorded step would "
-                               "update buffers the optimizers do not read")
+            raise RuntimeError("a parameter or gradient left the flat buffers during capture: the recorded step would "
+                               "update memory the optimizer does not read")
         cs.kernels = _lib.LAUNCHES["count"] - n0
         _lib.LAUNCHES["count"] = n0                 # nothing ran yet: replays add the count
         self.captured[key] = cs
@@ -365,9 +423,10 @@ class GraphedCooperativeTrainer(CooperativeTrainer):
                         raise IndexError("index {} is out of bounds for dimension 1 with size {}".format(k, row["n"]))
                     cs.params.fill(i, k % row["n"] if kind != "dropout" else 0, rng if row["draws"] else None)
                 cs.params.upload()
-                cs.forward_backward.replay()
-                self.bucket.all_reduce_mean(self.group)
-                cs.optimizers.replay()
+                cs.graph.replay()
+                if cs.optimizers is not None:
+                    self.bucket.all_reduce_sum()
+                    cs.optimizers.replay()
                 _lib.LAUNCHES["count"] += cs.kernels
                 fastpath.weights_changed()          # the graph stepped the weights behind autograd's back
                 out = cs.out

@@ -24,7 +24,7 @@
 extern "C" {
 #endif
 
-#define CTL_B200_VERSION 100 /* 0.1.0 */
+#define CTL_B200_VERSION 200 /* 0.2.0 */
 
 enum ctl_status {
   CTL_OK = 0,
@@ -270,6 +270,43 @@ int ctl_stem_wgrad_c8(const void* dy, const float* x, const int64_t* labels, int
 /* ... and w.r.t. the input (in_mode 0: plain, 1: through softmax(x / temperature)); dx planar fp32 [N,Cin,H,W] */
 int ctl_stem_dgrad_c8(const void* dy, const float* x, int in_mode, float temperature, int64_t N, int64_t Cin, int64_t H,
                       int64_t W, const float* weight, float* dx, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Multi-tensor Adam over flat buffers.  Replaces the five optim.Adam(...).step() calls of
+ *   medseg/models/advanced_triplet_recon_segmentation_model.py:774-785 (set_optimizers / optimize_all_params),
+ *   medseg/train_adv_supervised_segmentation_triplet.py:230-231
+ * params / grads / exp_avg / exp_avg_sq: flat fp32 DEVICE buffers of equal length (16-byte aligned, length padded to a
+ * multiple of 4); seg_bounds_host: HOST array of n_segments (<= 8) [begin, end) element pairs, begin %% 4 == 0, ascending
+ * -- one segment per optimizer of the reference; seg_mask bit s: segment s takes a step; steps: DEVICE fp32
+ * [n_segments] step counters, incremented for the stepped segments before use (CUDA-graph replayable).
+ * g' = grads*grad_scale (+ weight_decay*p); m += (g'-m)(1-beta1); v = beta2*v + (1-beta2) g'^2;
+ * p -= lr/(1-beta1^t) * m / (sqrt(v)/sqrt(1-beta2^t) + eps)      (torch.optim.Adam, amsgrad=False).
+ * zero_grad != 0: the gradients of the stepped segments are cleared in the same pass (the next step accumulates into
+ * zeros: optimizer.zero_grad() of advanced...model.py:755-758 without another sweep). */
+int ctl_adam_flat(float* params, float* grads, float* exp_avg, float* exp_avg_sq, const int64_t* seg_bounds_host,
+                  int n_segments, unsigned seg_mask, float* steps, float lr, float beta1, float beta2, float eps,
+                  float weight_decay, float grad_scale, int zero_grad, void* stream);
+/* ---------------------------------------------------------------------------------------------
+ * Sum of squared errors and its gradient (row f2): loss_out[0] = scale * sum (pred - target)^2 over n fp32 elements;
+ * dpred = grad_out[0] * 2 * scale * (pred - target).  Replaces 0.5 * nn.MSELoss()(recon, image)
+ * (advanced...model.py:443-447, scale = 0.5/n) and torch.mean((decoder(code) - gt)**2) (model_util.py:207-208).
+ * workspace16 / grad_out as in ctl_ce2d_fwd / ctl_ce2d_bwd. */
+int ctl_sse_fwd(const float* pred, const float* target, int64_t n, double scale, void* workspace16, float* loss_out,
+                void* stream);
+int ctl_sse_bwd(const float* pred, const float* target, int64_t n, double scale, const float* grad_out, float* dpred,
+                void* stream);
+/* ---------------------------------------------------------------------------------------------
+ * On-device evaluation metric (row f4).  Replaces pred.max(1)[1].cpu().numpy() + runningScore._fast_hist / update /
+ * get_scores (medseg/common_utils/metrics.py:18-53, advanced...model.py:656-659).
+ * Prediction per pixel = argmax over classes of planar fp32 logits [N,C,HW] (first maximum), or pred_labels int64 [N,HW]
+ * when logits is NULL.  gt: int64 [N,HW] (pixels with gt outside [0,C) are skipped, as _fast_hist's mask does);
+ * hist: uint64 [C][C] (row = gt, column = prediction) ACCUMULATED into; labels_out: optional uint8 [N,HW] label map.
+ * gt == hist == NULL: only the label map is produced.  C in {2,3,4,8}.
+ * ctl_confusion_scores: scores_out fp64 [4 + C] = overall acc, mean acc (nanmean), frequency-weighted acc, mean IoU
+ * (nanmean), IoU per class (NaN for an absent class). */
+int ctl_confusion_update(const float* logits, const int64_t* pred_labels, const int64_t* gt, int64_t N, int64_t C,
+                         int64_t HW, void* hist, void* labels_out, void* stream);
+int ctl_confusion_scores(const void* hist, int64_t C, double* scores_out, void* stream);
 
 #ifdef __cplusplus
 }

@@ -1,7 +1,7 @@
 """Profiling by elimination for the tcgen05 conv kernels (K3 forward / K3w weight gradient).
 
 Each layer class is timed with stages of the kernel pipeline switched off through the CTL_DIAG_SKIP environment
-variable (csrc/ctl_runtime.cu: 1 = no MMA issue, 2 = no TMA loads, 4 = no epilogue memory traffic (K3w: no epilogue),
+variable (a `make DIAG=1` build only; csrc/ctl_runtime.cu: 1 = no MMA issue, 2 = no TMA loads, 4 = no epilogue memory traffic (K3w: no epilogue),
 8 = no epilogue at all): whichever removal makes the time collapse names the bounding stage.  Outputs with any bit set are garbage;
 the tool never checks them.  CUDA-event timing, L2 flushed between launches.  usage: python tools/diag_conv.py [B]"""
 import json
