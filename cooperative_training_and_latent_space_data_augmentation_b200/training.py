@@ -56,9 +56,11 @@ def latent_da_configs(experiment_opt):
 
 def cooperative_step(solver, clean_image_l, label_l, corrupted_image_DA_config=None, corrupted_seg_DA_config=None,
                      gen_corrupted_image=True, gen_corrupted_seg=True, latent_DA=True, separate_training=False,
-                     noise=None, grad_sync=None, optimize=True):
+                     noise=None, grad_sync=None, optimize=True, hard_examples=None):
     """Runs the loop body once.  Returns a dict of 0-d DEVICE tensors keyed like the reference's loss_dict
-    plus 'loss' (nothing is synchronised; call .item() on what you want to log)."""
+    plus 'loss' (nothing is synchronised; call .item() on what you want to log).
+    hard_examples: optional (perturbed_image, perturbed_seg) to train on instead of generating them (replaying a
+    recorded step; the parity tests use it to compare two numerics modes on IDENTICAL hard examples)."""
     icfg = corrupted_image_DA_config or DEFAULT_IMAGE_CFG
     scfg = corrupted_seg_DA_config or DEFAULT_SEG_CFG
     solver.train()
@@ -75,9 +77,12 @@ def cooperative_step(solver, clean_image_l, label_l, corrupted_image_DA_config=N
            'loss/standard/gt_shape': gt_recon_loss.detach()}
 
     if latent_DA:
-        p_img, p_seg = solver.hard_example_generation(
-            clean_image_l.detach(), label_l.detach(), gen_corrupted_seg=gen_corrupted_seg,
-            gen_corrupted_image=gen_corrupted_image, corrupted_image_DA_config=icfg, corrupted_seg_DA_config=scfg)
+        if hard_examples is not None:
+            p_img, p_seg = hard_examples
+        else:
+            p_img, p_seg = solver.hard_example_generation(
+                clean_image_l.detach(), label_l.detach(), gen_corrupted_seg=gen_corrupted_seg,
+                gen_corrupted_image=gen_corrupted_image, corrupted_image_DA_config=icfg, corrupted_seg_DA_config=scfg)
         h_seg, h_img, h_shape2, h_cshape = solver.hard_example_training(
             perturbed_image=p_img, perturbed_seg=p_seg, clean_image_l=clean_image_l, label_l=label_l,
             separate_training=separate_training)
@@ -102,57 +107,6 @@ def cooperative_step(solver, clean_image_l, label_l, corrupted_image_DA_config=N
         solver.optimize_all_params()
     out['loss'] = loss.detach()
     return out
-
-
-class FlatGradBucket:
-    """All gradients of a parameter list as views of ONE flat fp32 buffer, so the data-parallel
-    exchange is a single all-reduce (10.1 MB for FCN_16_standard; latency-bound on NVLink 5 /
-    NVSwitch, hence one bucket rather than many).  Device-agnostic: the CPU tests drive it over gloo."""
-
-    def __init__(self, params):
-        self.params = [p for p in params]
-        if not self.params:
-            raise ValueError("no parameters")
-        dev, dt = self.params[0].device, self.params[0].dtype
-        self.numel = sum(p.numel() for p in self.params)
-        # weight tensors start on 16-byte boundaries: the weight-gradient kernels accumulate straight into these views
-        # with 16-byte reductions (trainpath.accumulate_into_grads); the few padding elements stay zero
-        self.offsets, off = [], 0
-        for p in self.params:
-            if p.dim() > 1:
-                off = (off + 3) // 4 * 4
-            self.offsets.append(off)
-            off += p.numel()
-        self.flat = torch.zeros(off, device=dev, dtype=dt)
-        for p, o in zip(self.params, self.offsets):
-            p.grad = self.flat[o:o + p.numel()].view_as(p)
-
-    def zero(self):
-        self.flat.zero_()
-
-    def reattach(self):
-        """If something replaced a .grad (e.g. zero_grad(set_to_none=True)), fold it back into the bucket."""
-        for p, o in zip(self.params, self.offsets):
-            view = self.flat[o:o + p.numel()].view_as(p)
-            if p.grad is None:
-                view.zero_()
-                p.grad = view
-            elif p.grad.data_ptr() != view.data_ptr():
-                view.copy_(p.grad)
-                p.grad = view
-
-    def attached(self):
-        """True when every parameter's .grad is still its view of the flat buffer."""
-        for p, o in zip(self.params, self.offsets):
-            if p.grad is None or p.grad.data_ptr() != self.flat.data_ptr() + o * self.flat.element_size():
-                return False
-        return True
-
-    def all_reduce_mean(self, group=None):
-        if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
-            self.reattach()
-            dist.all_reduce(self.flat, op=dist.ReduceOp.SUM, group=group)
-            self.flat.div_(dist.get_world_size(group))
 
 
 def shard_bounds(global_batch, world_size, rank):

@@ -7,6 +7,7 @@ The fixtures are small (inputs are regenerated from seeds; only outputs are stor
 import contextlib
 import io
 import os
+import sys
 import random
 
 import numpy as np
@@ -116,10 +117,11 @@ def _probe(t, n=512):
     return a[:: max(1, a.size // n)][:n].astype(np.float32)
 
 
-def gen_model(RefSolver):
+def gen_model(RefSolver, N=2, H=64, W=64, name="model_step.npz", full_latents=True, steps=2):
     """Forward/backward of every sub-network, hard_example_generation with fixed mask types and
-    two full cooperative steps, all on weights regenerated from oracle/weights.py."""
-    N, H, W, wseed = 2, 64, 64, 7
+    full cooperative steps, all on weights regenerated from oracle/weights.py.  The default is the small
+    fixture; `model_step_224.npz` is BASELINE.json configs[0] (batch 8 of 1x224x224), probes / checksums only."""
+    wseed = 7
     with contextlib.redirect_stdout(io.StringIO()):
         solver = RefSolver("FCN_16_standard", num_classes=4, use_gpu=False, learning_rate=1e-4)
     for k, m in solver.model.items():
@@ -134,7 +136,11 @@ def gen_model(RefSolver):
         seg = solver.model["segmentation_decoder"](z_s)
         rec = solver.model["image_decoder"](z_i)
         pred2 = solver.predict(img, n_iter=2)
-    out.update(eval_z_i=z_i.numpy(), eval_z_s=z_s.numpy(), eval_seg=_probe(seg, 4096), eval_rec=_probe(rec, 4096),
+    out.update(eval_z_i=z_i.numpy() if full_latents else _probe(z_i, 4096),
+               eval_z_s=z_s.numpy() if full_latents else _probe(z_s, 4096),
+               eval_z_i_sum=np.float64(z_i.double().sum()), eval_z_s_sum=np.float64(z_s.double().sum()),
+               eval_pred2_labels_hist=np.bincount(pred2.max(1)[1].numpy().reshape(-1), minlength=4),
+               eval_seg=_probe(seg, 4096), eval_rec=_probe(rec, 4096),
                eval_pred2=_probe(pred2, 4096), eval_seg_sum=np.float64(seg.double().sum()),
                eval_pred2_sum=np.float64(pred2.double().sum()))
 
@@ -143,7 +149,7 @@ def gen_model(RefSolver):
 
     # ---- two cooperative steps (train...triplet.py:171-237), fixed channel(image)+spatial(shape)
     seed_all(5)
-    for step in range(2):
+    for step in range(steps):
         solver.train()
         solver.reset_all_optimizers()
         noisy = torch.clamp(img + noise, 0, 1)
@@ -181,17 +187,52 @@ def gen_model(RefSolver):
         out["final_param_sum_" + k] = np.float64(sum(float(p.double().sum()) for p in m.parameters()))
         out["final_bn_tracked_" + k] = np.array([int(b) for n_, b in m.named_buffers() if n_.endswith("num_batches_tracked")])
         out["final_running_mean_sum_" + k] = np.float64(sum(float(b.double().sum()) for n_, b in m.named_buffers() if n_.endswith("running_mean")))
-    np.savez_compressed(os.path.join(OUT, "model_step.npz"), **out)
-    print("model: losses", out["step0_loss"], out["step1_loss"])
+    np.savez_compressed(os.path.join(OUT, name), **out)
+    print("model:", name, "losses", [float(out["step%d_loss" % i]) for i in range(steps)])
+
+
+def gen_metrics():
+    """runningScore (medseg/common_utils/metrics.py:12-57) of the unmodified reference on seeded label maps, including
+    out-of-range true labels (ignored by _fast_hist's mask) and a class that never occurs (NaN IoU -> nanmean)."""
+    from medseg.common_utils.metrics import runningScore
+    rs = np.random.RandomState(11)
+    cases = {}
+    for name, n_cls, absent in (("a", 4, None), ("b", 4, 3), ("c", 2, None)):
+        m = runningScore(n_cls)
+        gts, preds = [], []
+        for _ in range(3):
+            gt = rs.randint(0, n_cls, size=(5, 32, 48)).astype(np.int64)
+            pr = np.where(rs.rand(5, 32, 48) < 0.7, gt, rs.randint(0, n_cls, size=(5, 32, 48))).astype(np.int64)
+            if absent is not None:
+                gt[gt == absent] = 0
+                pr[pr == absent] = 1
+            gt[0, :2, :3] = 255 if name == "a" else gt[0, :2, :3]     # out-of-range labels are skipped
+            m.update(gt, pr)
+            gts.append(gt); preds.append(pr)
+        scores, cls_iu = m.get_scores()
+        cases.update({name + "_n": n_cls, name + "_gt": np.stack(gts).astype(np.uint8), name + "_pred": np.stack(preds).astype(np.uint8),
+                      name + "_hist": m.confusion_matrix, name + "_scores": np.array(list(scores.values()), np.float64),
+                      name + "_score_keys": np.array(list(scores.keys())),
+                      name + "_cls_iu": np.array([cls_iu[i] for i in range(n_cls)], np.float64)})
+    np.savez_compressed(os.path.join(OUT, "metrics_scores.npz"), **cases)
+    print("metrics: mean IoU", cases["a_scores"][3], cases["b_scores"][3], cases["c_scores"][3])
 
 
 def main():
     os.makedirs(OUT, exist_ok=True)
     torch.set_num_threads(1)          # fixtures must not depend on the thread count of the box
     ref_mu, RefSolver = import_reference()
-    gen_masking(ref_mu)
-    gen_dropout(RefSolver)
-    gen_model(RefSolver)
+    only = sys.argv[1:]
+    if not only or "masking" in only:
+        gen_masking(ref_mu)
+        gen_dropout(RefSolver)
+    if not only or "model" in only:
+        gen_model(RefSolver)
+    if not only or "model224" in only:
+        # BASELINE.json configs[0]: batch 8 of 1x224x224 -- one cooperative step (CPU, single thread: minutes)
+        gen_model(RefSolver, N=8, H=224, W=224, name="model_step_224.npz", full_latents=False, steps=1)
+    if not only or "metrics" in only:
+        gen_metrics()
 
 
 if __name__ == "__main__":

@@ -1,0 +1,164 @@
+"""GPU: the kernel-path cooperative step and predict AT THE BENCHMARKED SHAPES (BASELINE.json configs[0..2, 4]):
+8 x 224^2 (configs[0], also pinned by the reference-generated fixture tests/golden/model_step_224.npz), 64 x 224^2
+(configs[1], the bench.py workload), 8 x 256^2 (configs[2]'s slice shape) -- against (i) the torch-fp32 yardstick
+(the reference's own op sequence on this GPU) and (ii) the unmodified reference's CPU outputs.
+
+The hard examples of a step come out of per-sample top-k selections that a 1-ulp change of dL/dz can flip, so two
+numerics modes are compared on IDENTICAL hard examples: the fp32 run's perturbed image / segmentation are fed to the
+kernel run (`cooperative_step(hard_examples=...)`).  With the fork removed the bars can fail for real reasons:
+losses within 3e-2 relative, per-sub-network gradient cosine >= 0.9 and norm ratio in [0.8, 1.25]
+(bf16 activations through ~60 layers; measured values are printed).  The generation itself is compared separately:
+the kernel run's own hard examples must be close to the fp32 run's (relative L1 < 0.1)."""
+import os
+import random
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import weights
+
+pytestmark = pytest.mark.gpu
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+MODULES = ('image_encoder', 'segmentation_decoder', 'shape_encoder', 'shape_decoder', 'image_decoder')
+CFG_I = {"loss_name": "mse", "mask_type": "channel", "max_threshold": 0.5, "random_threshold": True, "if_soft": True}
+CFG_S = {"loss_name": "ce", "mask_type": "spatial", "max_threshold": 0.5, "random_threshold": True, "if_soft": True}
+
+
+def _probe(a, n):
+    a = np.asarray(a).reshape(-1)
+    return a[:: max(1, a.size // n)][:n]
+
+
+def _seed_all(seed):
+    random.seed(seed)
+    np.random.seed(seed)
+    torch.manual_seed(seed)
+
+
+def _solver(pkg):
+    pkg.set_rng_mode("torch")
+    s = pkg.AdvancedTripletReconSegmentationModel('FCN_16_standard', num_classes=4, learning_rate=1e-4)
+    for k, m in s.model.items():
+        m.load_state_dict(weights.synthetic_state_dict(m, 7, prefix=k + "."))
+    return s
+
+
+def _step(pkg, solver, state0, mode, img, lab, noise, hard_examples=None):
+    pkg.conv_blocks.set_precision(mode)
+    for k, m in solver.model.items():
+        for n, b in m.named_buffers():
+            b.copy_(state0[k][n])
+    _seed_all(5)
+    r = pkg.cooperative_step(solver, img, lab, CFG_I, CFG_S, noise=noise, optimize=False, hard_examples=hard_examples)
+    grads = {n: p.grad.clone() for n, p in solver.named_parameters()}
+    return {k: float(v) for k, v in r.items() if k.startswith('loss')}, grads, r
+
+
+@pytest.mark.parametrize("batch,size", [(8, 224), (64, 224), (8, 256)])
+def test_kernel_step_tracks_fp32_at_bench_shapes(batch, size):
+    import cooperative_training_and_latent_space_data_augmentation_b200 as pkg
+    solver = _solver(pkg)
+    img, lab, noise = weights.synthetic_batch(batch, size, size, seed=21)
+    img, lab, noise = img.cuda(), lab.cuda(), noise.cuda()
+    state0 = {k: {n: b.clone() for n, b in m.named_buffers()} for k, m in solver.model.items()}
+    try:
+        la, ga, ra = _step(pkg, solver, state0, "fp32", img, lab, noise)
+        hard = (ra['perturbed_image'].detach().clone(), ra['perturbed_seg'].detach().clone())
+        n0 = pkg._lib.LAUNCHES["count"]
+        lb, gb, _ = _step(pkg, solver, state0, "kernel", img, lab, noise, hard_examples=hard)
+        launched = pkg._lib.LAUNCHES["count"] - n0
+        lc, _, rc = _step(pkg, solver, state0, "kernel", img, lab, noise)      # the kernel path's own hard examples
+    finally:
+        pkg.conv_blocks.set_precision("fp32")
+    assert launched > 500, "the kernel-mode step launched only %d kernels of libctl_b200.so" % launched
+    info, bad = [], []
+    for k in sorted(la):
+        info.append((k, round(la[k], 5), round(lb[k], 5)))
+        if abs(la[k] - lb[k]) > 3e-2 * abs(la[k]) + 1e-4:
+            bad.append(info[-1])
+
+    def cosine(x, y, names):
+        a = torch.cat([x[n].reshape(-1) for n in names]).double()
+        b = torch.cat([y[n].reshape(-1) for n in names]).double()
+        return float(torch.nn.functional.cosine_similarity(a, b, dim=0)), float(b.norm() / a.norm())
+
+    for mod in MODULES:
+        names = [n for n in ga if n.startswith(mod + '.')]
+        ck, rk = cosine(ga, gb, names)
+        info.append((mod, "cos", round(ck, 4), "norm ratio", round(rk, 3)))
+        if not ck >= 0.9 or not 0.8 <= rk <= 1.25:
+            bad.append(info[-1])
+    # generation at this shape: the kernel path's own hard examples vs the fp32 run's
+    for key in ('perturbed_image', 'perturbed_seg'):
+        a, c = ra[key].float(), rc[key].float()
+        rel = float((a - c).abs().mean() / a.abs().mean())
+        info.append((key, "relative L1 kernel-vs-fp32", round(rel, 4)))
+        if not rel < 0.1:
+            bad.append(info[-1])
+    for k in ('loss/hard/total',):
+        if abs(la[k] - lc[k]) > 8e-2 * abs(la[k]):
+            bad.append((k, "own hard examples", la[k], lc[k]))
+    print(info)
+    assert not bad, "%s\nall: %s" % (bad, info)
+
+
+def test_step_at_224_matches_the_reference_fixture():
+    """BASELINE.json configs[0] (batch 8, 1x224x224): one cooperative step against what the UNMODIFIED reference
+    computed on CPU (model_step_224.npz): the fp32 yardstick at 1e-3 (clean pass) / 5e-2 (hard passes: top-k forks),
+    the kernel path at 3e-2 / 8e-2."""
+    import cooperative_training_and_latent_space_data_augmentation_b200 as pkg
+    f = np.load(os.path.join(GOLDEN, "model_step_224.npz"))
+    img, lab, noise = weights.synthetic_batch(int(f["N"]), int(f["H"]), int(f["W"]), seed=int(f["data_seed"]))
+    img, lab, noise = img.cuda(), lab.cuda(), noise.cuda()
+    try:
+        for mode, tol_std, tol_hard in (("fp32", 1e-3, 5e-2), ("kernel", 3e-2, 8e-2)):
+            pkg.conv_blocks.set_precision(mode)
+            solver = _solver(pkg)
+            _seed_all(5)
+            r = pkg.cooperative_step(solver, img, lab, CFG_I, CFG_S, noise=noise)
+            std = [r['loss/standard/seg'], r['loss/standard/image'], r['loss/standard/gt_shape'], r['loss/standard/shape']]
+            np.testing.assert_allclose([float(x) for x in std], f["step0_standard"], rtol=tol_std, err_msg=mode)
+            np.testing.assert_allclose([float(r['loss/hard/seg']), float(r['loss/hard/image'])], f["step0_hard"][:2],
+                                       rtol=tol_hard, err_msg=mode)
+            np.testing.assert_allclose(float(r['loss/hard/shape']), float(f["step0_hard"][2] + f["step0_hard"][3]),
+                                       rtol=tol_hard, err_msg=mode)
+            np.testing.assert_allclose(float(r['loss']), float(f["step0_loss"]), rtol=tol_hard, err_msg=mode)
+            # the soft-mask values are 0.5 * U(0,1) draws of the DEVICE generator here and of the CPU generator in the
+            # fixture: the hard examples agree in distribution, not element by element
+            for key, name in (('perturbed_image', 'step0_p_img'), ('perturbed_seg', 'step0_p_seg')):
+                got = _probe(r[key].float().cpu().numpy(), 4096)[:4096]
+                assert abs(np.abs(got).mean() - np.abs(f[name]).mean()) < 0.1 * np.abs(f[name]).mean(), (mode, key)
+            tracked = {k: sorted({int(b) for n_, b in m.named_buffers() if n_.endswith("num_batches_tracked")})
+                       for k, m in solver.model.items()}
+            assert tracked == {k: sorted(set(int(x) for x in f["final_bn_tracked_" + k])) for k in solver.model}, mode
+            # Adam moved every module like the reference's five optimizers did (checksum of the parameters)
+            for k, m in solver.model.items():
+                psum = sum(float(p.detach().double().sum()) for p in m.parameters())
+                np.testing.assert_allclose(psum, float(f["final_param_sum_" + k]), rtol=2e-4, atol=5e-2, err_msg=mode + k)
+    finally:
+        pkg.conv_blocks.set_precision("fp32")
+
+
+def test_predict_at_224_matches_the_reference_fixture():
+    import cooperative_training_and_latent_space_data_augmentation_b200 as pkg
+    f = np.load(os.path.join(GOLDEN, "model_step_224.npz"))
+    img, _, _ = weights.synthetic_batch(int(f["N"]), int(f["H"]), int(f["W"]), seed=int(f["data_seed"]))
+    img = img.cuda()
+    try:
+        for mode, tol in (("fp32", 2e-3), ("kernel", 4e-2)):
+            pkg.conv_blocks.set_precision(mode)
+            solver = _solver(pkg)
+            solver.eval()
+            with torch.no_grad():
+                z_i, z_s = solver.model['image_encoder'](img)
+            pred2 = solver.predict(img, n_iter=2)
+            for got, name in ((z_i, "eval_z_i"), (z_s, "eval_z_s"), (pred2, "eval_pred2")):
+                g = _probe(got.float().cpu().numpy(), 4096)[:4096]
+                err = float(np.abs(g - f[name]).mean() / (np.abs(f[name]).mean() + 1e-12))
+                assert err < tol, (mode, name, err)
+            hist = np.bincount(pred2.argmax(1).cpu().numpy().reshape(-1), minlength=4)
+            assert np.abs(hist - f["eval_pred2_labels_hist"]).sum() <= (1e-3 if mode == "fp32" else 0.1) * hist.sum(), \
+                (mode, hist, f["eval_pred2_labels_hist"])
+    finally:
+        pkg.conv_blocks.set_precision("fp32")

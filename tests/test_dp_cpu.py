@@ -1,5 +1,5 @@
-"""CPU, world size 2 over gloo: the host side of the batch-sharded step -- shard bounds, the single flat
-gradient bucket and its all-reduce-mean, parameter broadcast, identical host RNG draws on every rank, and the
+"""CPU, world size 2 over gloo: the host side of the batch-sharded step -- shard bounds, the flat gradient
+buffer of optim.FlatAdam and its all-reduce (the 1/world average is folded into the Adam kernel), parameter broadcast, identical host RNG draws on every rank, and the
 shard-invariance of the native Philox stream (restated by the oracle)."""
 import os
 import random
@@ -24,26 +24,30 @@ def _worker(rank, world, port, out):
     os.environ["MASTER_PORT"] = str(port)
     dist.init_process_group("gloo", rank=rank, world_size=world)
     try:
-        from cooperative_training_and_latent_space_data_augmentation_b200 import training
+        from cooperative_training_and_latent_space_data_augmentation_b200 import optim, training
         torch.manual_seed(100 + rank)                       # different initial weights per rank on purpose
         net = nn.Sequential(nn.Conv2d(2, 3, 3), nn.BatchNorm2d(3), nn.Conv2d(3, 1, 1))
+        net(torch.ones(1, 2, 5, 5))                         # a forward BEFORE the trainer exists (stale packed weights case)
+        flat = optim.FlatAdam({"net": net}, lr=1e-3)        # parameters / gradients become views of flat buffers
         training.broadcast_module_state([net], src=0)
         w_after_bcast = torch.cat([p.detach().reshape(-1) for p in net.parameters()]).clone()
-        bucket = training.FlatGradBucket(list(net.parameters()))
-        assert bucket.numel == sum(p.numel() for p in net.parameters())
-        for p in net.parameters():                          # every gradient is a view of the flat buffer
-            assert p.grad.data_ptr() >= bucket.flat.data_ptr()
+        assert flat.attached()                              # the broadcast wrote THROUGH the views
+        exchange = training._GradExchange(flat, None, world)
+        assert flat.grad_scale == 1.0 / world               # the average is taken inside the Adam kernel
         # a rank-dependent "backward": loss = (rank+1) * sum(net(x))
         x = torch.ones(2, 2, 5, 5)
         ((rank + 1.0) * net(x).sum()).backward()
-        local = bucket.flat.clone()
+        local = exchange.flat.clone()
         net[0].weight.grad = None                           # something dropped a grad: reattach must restore the view
-        bucket.all_reduce_mean()
-        assert net[0].weight.grad is not None and net[0].weight.grad.data_ptr() == bucket.flat.data_ptr()
+        assert not exchange.attached()
+        exchange.reattach()
+        exchange.all_reduce_sum()
+        assert net[0].weight.grad is not None and net[0].weight.grad.data_ptr() == exchange.flat.data_ptr()
+        reduced = exchange.mean_gradients()
         lo, hi = training.shard_bounds(8, world, rank)
         training.seed_host_rng(7)
         draws = (random.random(), float(np.random.rand()))
-        out[rank] = {"w": w_after_bcast, "local": local, "reduced": bucket.flat.clone(), "bounds": (lo, hi),
+        out[rank] = {"w": w_after_bcast, "local": local, "reduced": reduced.clone(), "bounds": (lo, hi),
                      "draws": draws}
     finally:
         dist.destroy_process_group()
@@ -97,26 +101,3 @@ def test_latent_da_config_block_is_read_verbatim():
     gi, ic, gs, sc = training.latent_da_configs(opt)
     assert gi and gs and ic["loss_name"] == "mse" and sc["loss_name"] == "ce"
     assert training.latent_da_configs({"learning": {"latent_DA": False}}) == (False, None, False, None)
-
-
-def test_flat_bucket_aligns_weight_views_to_16_bytes():
-    """The weight-gradient kernels accumulate straight into these views with 16-byte reductions
-    (trainpath.accumulate_into_grads): every multi-dimensional parameter starts on a 16-byte boundary, the views tile
-    the buffer without overlap, and the padding elements are (and stay) zero."""
-    from cooperative_training_and_latent_space_data_augmentation_b200 import training
-    torch.manual_seed(0)
-    net = nn.Sequential(nn.Conv2d(2, 3, 3), nn.BatchNorm2d(3), nn.Conv2d(3, 1, 1), nn.Conv2d(1, 5, 3))
-    bucket = training.FlatGradBucket(list(net.parameters()))
-    assert bucket.numel == sum(p.numel() for p in net.parameters()) and bucket.flat.numel() >= bucket.numel
-    covered = torch.zeros(bucket.flat.numel(), dtype=torch.bool)
-    for p, off in zip(bucket.params, bucket.offsets):
-        if p.dim() > 1:
-            assert off % 4 == 0 and p.grad.data_ptr() % 16 == 0
-        assert p.grad.data_ptr() == bucket.flat.data_ptr() + 4 * off and p.grad.shape == p.shape
-        assert not covered[off:off + p.numel()].any()
-        covered[off:off + p.numel()] = True
-    net(torch.ones(2, 2, 9, 9)).sum().backward()
-    assert bucket.attached()
-    assert float(bucket.flat[~covered].abs().sum()) == 0.0
-    bucket.zero()
-    assert float(bucket.flat.abs().sum()) == 0.0 and bucket.attached()
