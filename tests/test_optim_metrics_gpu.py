@@ -52,8 +52,9 @@ def test_adam_flat_matches_torch_adam(pkg):
     for s, (b, e) in enumerate(bounds):
         np.testing.assert_allclose(p[b:e].cpu().numpy(), ref_p[s].detach().cpu().numpy(), rtol=2e-6, atol=1e-7)
         st = opts[s].state[ref_p[s]]
-        np.testing.assert_allclose(m[b:e].cpu().numpy(), st["exp_avg"].cpu().numpy(), rtol=1e-5, atol=1e-10)
-        np.testing.assert_allclose(v[b:e].cpu().numpy(), st["exp_avg_sq"].cpu().numpy(), rtol=1e-5, atol=1e-12)
+        want_m, want_v = st["exp_avg"].cpu().numpy(), st["exp_avg_sq"].cpu().numpy()
+        np.testing.assert_allclose(m[b:e].cpu().numpy(), want_m, rtol=1e-5, atol=1e-6 * np.abs(want_m).max())
+        np.testing.assert_allclose(v[b:e].cpu().numpy(), want_v, rtol=1e-5, atol=1e-6 * np.abs(want_v).max())
     # untouched padding between the segments
     assert torch.equal(p[1001:1024], p_init[1001:1024]) and float(m[1001:1024].abs().sum()) == 0.0
     # fp64 oracle on one segment, one step from scratch
