@@ -303,6 +303,24 @@ def conv_microbench(pkg, peaks, batch, iters=5, sizes=((16, 16, 224), (32, 32, 1
 
 
 # ------------------------------------------------------------------------------------------------ GPU arm
+def shutdown_distributed(dist, world, trainer=None):
+    """Tears the process group down at a point ALL ranks reach together (right after the timed loops): graphs that
+    recorded NCCL kernels go first -- a communicator still referenced by live CUDA graphs cannot be destroyed -- then
+    the group.  A watchdog ends the process if the teardown blocks anyway."""
+    if world <= 1:
+        return
+    import threading
+    sys.stdout.flush()
+    dog = threading.Timer(60.0, lambda: os._exit(3))
+    dog.daemon = True
+    dog.start()
+    if trainer is not None and hasattr(trainer, "close"):
+        trainer.close()
+    dist.barrier()
+    dist.destroy_process_group()
+    dog.cancel()
+
+
 def eager_gpu_baseline(args, img_d, lab_d):
     """The bar SURVEY.md section 2 / BASELINE.md name: the reference's own op sequence as eager PyTorch fp32 on THIS
     GPU (the reference runs `.to('cuda')` fp32 eager, advanced...model.py:133-138) -- the torch-ops yardstick
@@ -409,9 +427,8 @@ def run_predict_arm(args, world, rank, local_rank, dist):
         predictor._forward(dev_stacks[0][0], dev_stacks[0][1])
     kernels_per_step = _lib.LAUNCHES["count"] - n0
     scores, cls_iu = predictor.scores()
+    shutdown_distributed(dist, world)
     if rank != 0:
-        if world > 1:
-            dist.destroy_process_group()
         return
     peaks = measured_peaks()
     conv_layers = conv_microbench(pkg, peaks, S, sizes=((16, 16, size),))
@@ -446,8 +463,6 @@ def run_predict_arm(args, world, rank, local_rank, dist):
         "cpu_baseline": cpu, "clocks": clocks,
     }
     print(json.dumps(line), flush=True)
-    if world > 1:
-        dist.destroy_process_group()
 
 
 def run_gpu_arm(args):
@@ -534,19 +549,32 @@ def run_gpu_arm(args):
             sampler.stop()
             print(json.dumps({"profile_only": True, "ms_per_step": 1e3 * t_dev / args.steps,
                               "kernels_per_step": launches // max(1, args.steps)}), flush=True)
-        if world > 1:
-            dist.destroy_process_group()
+        shutdown_distributed(dist, world, trainer)
         return
     for _ in range(2):
         e2e_step()
     t_e2e, last_loss = timed_loop(e2e_step, args.steps)
     clocks = sampler.stop() if rank == 0 else None
-    # data-parallel result check (every rank takes part): bit-identical parameters on all ranks after the timed steps
+    # data-parallel result checks (every rank takes part): bit-identical parameters on all ranks after the timed steps,
+    # and one extra eager step without the optimizer whose all-reduced gradient must equal the mean of the ranks' local
+    # gradients (gathered)
     in_sync = trainer.params_in_sync()
+    grad_check = None
+    if world > 1:
+        from cooperative_training_and_latent_space_data_augmentation_b200.training import cooperative_step
+        cooperative_step(solver, img_d, lab_d, IMAGE_CFG, SEG_CFG, optimize=False)
+        local = solver.flat_adam.flat_grads.clone()
+        gathered = [torch.empty_like(local) for _ in range(world)]
+        dist.all_gather(gathered, local)
+        want = torch.stack(gathered).double().mean(0)
+        trainer.bucket.all_reduce_sum()
+        got = trainer.bucket.mean_gradients().double()
+        grad_check = {"max_err_over_max_abs": float((got - want).abs().max() / want.abs().max()),
+                      "what": "all-reduced flat gradient x 1/world vs the mean of the %d ranks' gathered local gradients "
+                              "(one eager step, optimizer off)" % world}
 
+    shutdown_distributed(dist, world, trainer)          # every rank; rank 0 carries on alone with the microbenchmarks
     if rank != 0:
-        if world > 1:
-            dist.destroy_process_group()
         return
 
     peaks = measured_peaks()
@@ -601,14 +629,13 @@ def run_gpu_arm(args):
         "conv_blocks": conv_layers,
         "step_tensor_frac": (value * gf * 1e9 / (world * peaks["bf16_tflops_sustained"] * 1e12)) if gf else None,
         "params_in_sync": in_sync,
+        "dp_gradient_check": grad_check,
         "cpu_baseline": cpu,
         "eager_gpu_baseline": eager,
         "clocks": clocks,
         "last_loss": last_loss,
     }
     print(json.dumps(line), flush=True)
-    if world > 1:
-        dist.destroy_process_group()
 
 
 def main():

@@ -343,6 +343,17 @@ class GraphedCooperativeTrainer(CooperativeTrainer):
         self.captured[key] = cs
         return cs
 
+    def close(self):
+        """Destroys the captured graphs.  Call before torch.distributed.destroy_process_group(): a communicator whose
+        collectives are still referenced by live CUDA graphs cannot be torn down (the destroy blocks)."""
+        torch.cuda.synchronize()
+        for cs in self.captured.values():
+            cs.graph.reset()
+            if cs.optimizers is not None:
+                cs.optimizers.reset()
+        self.captured.clear()
+        torch.cuda.synchronize()
+
     # -------------------------------------------------------------------------------------------- the step
     def step(self, clean_local, label_local, noise_local=None):
         from . import fastpath
