@@ -65,11 +65,15 @@ SIGNATURES = {
     "ctl_stem_dgrad_c8": (_i, [_vp, _vp, _i, _f, _i64, _i64, _i64, _i64, _vp, _vp, _vp]),
     "ctl_ce2d_fwd": (_i, [_vp, _vp, _i64, _i64, _i64, _i64, _c.c_double, _vp, _vp, _vp]),
     "ctl_ce2d_bwd": (_i, [_vp, _vp, _i64, _i64, _i64, _i64, _c.c_double, _vp, _vp, _vp]),
-    "ctl_adam_flat": (_i, [_vp, _vp, _vp, _vp, _c.POINTER(_i64), _i, _c.c_uint, _vp, _f, _f, _f, _f, _f, _f, _i, _vp]),
+    "ctl_adam_flat": (_i, [_vp, _vp, _vp, _vp, _c.POINTER(_i64), _i, _c.c_uint, _vp, _c.c_double, _c.c_double, _c.c_double,
+                           _c.c_double, _c.c_double, _c.c_double, _i, _vp]),
     "ctl_sse_fwd": (_i, [_vp, _vp, _i64, _c.c_double, _vp, _vp, _vp]),
     "ctl_sse_bwd": (_i, [_vp, _vp, _i64, _c.c_double, _vp, _vp, _vp]),
     "ctl_confusion_update": (_i, [_vp, _vp, _vp, _i64, _i64, _i64, _vp, _vp, _vp]),
     "ctl_confusion_scores": (_i, [_vp, _i64, _vp, _vp]),
+    "ctl_conv2d_c8_bf16_saliency": (_i, [_vp, _i64, _i64, _i64, _i64, _vp, _i64, _vp, _vp, _vp, _i, _i, _vp]),
+    "ctl_saliency_sums_mask_apply": (_i, [_vp, _vp, _i64, _i64, _i64, _i, _i64, _i, _vp, _u64, _u64, _i64, _vp, _vp, _vp,
+                                          _vp, _vp, _vp, _vp]),
 }
 
 _lib = None
@@ -85,7 +89,7 @@ KERNELS_PER_CALL = {"ctl_saliency_reduce": 1, "ctl_topp_mask_apply": 2, "ctl_sal
                     "ctl_zero_stuff2x_c8": 1, "ctl_split_parity2x2_c8": 1, "ctl_head_bwd_c8": 1,
                     "ctl_stem_wgrad_c8": 1, "ctl_stem_dgrad_c8": 1, "ctl_ce2d_fwd": 1, "ctl_ce2d_bwd": 1, "ctl_scale_shift_upadd_act_c8": 1, "ctl_pack_conv_weights_batched": 1, "ctl_stem_input_c8": 1,
                     "ctl_adam_flat": 2, "ctl_sse_fwd": 1, "ctl_sse_bwd": 1, "ctl_confusion_update": 1,
-                    "ctl_confusion_scores": 1}
+                    "ctl_confusion_scores": 1, "ctl_conv2d_c8_bf16_saliency": 1, "ctl_saliency_sums_mask_apply": 1}
 LAUNCHES = {"count": 0}
 
 

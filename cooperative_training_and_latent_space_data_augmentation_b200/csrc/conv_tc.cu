@@ -55,6 +55,10 @@ struct ConvParams {
   int subsample;                      // 1: Ho=H, Wo=W; 2: keep even (y,x) -> Ho=H/2, Wo=W/2 (3x3 stride-2 pad-1)
   int up2x;                           // 1: ConvTranspose2d(k=2,s=2) scatter: GEMM column n = (dy*2+dx)*Cout/4 + co
   double* stats;                      // [2][Cout] sum / sum of squares of the stored outputs, accumulated into (or nullptr)
+  double* sal;                        // latent saliency sums: [N][Cout] (channel mode: sum over pixels) or
+                                      // [N][H*W] (spatial mode: sum over channels) of the bf16-rounded outputs, accumulated into
+  int sal_mode;                       // ctl_mode
+  int no_store;                       // 1: the output tensor is not written (only the saliency sums are wanted)
   int diag;                           // profiling only (env CTL_DIAG_SKIP): 1 no MMA, 2 no TMA loads, 4 no epilogue memory traffic, 8 no epilogue
 };
 
@@ -91,7 +95,7 @@ struct ConvCfg {
 // as a batch: every residual pixel of the tile is requested BEFORE the accumulator wait (the addresses do not depend on
 // it), the TMEM loads of two items are issued back to back behind one tcgen05.wait::ld, and the accumulator stage is
 // handed back to the MMA issuer as soon as the last load has landed in registers -- before the arithmetic and stores.
-template <int CIN, int NT, int TAPS, int MT, int STAGES, bool RES, bool STATS, bool GEN>
+template <int CIN, int NT, int TAPS, int MT, int STAGES, bool RES, bool STATS, bool GEN, bool SAL = false>
 __device__ __forceinline__ void conv_epilogue(const ConvParams& p, const uint32_t tmem_base, const float* sVec,
                                               uint64_t* acc_full, uint64_t* acc_empty, const int n0, float* stat_smem) {
   using Cfg = ConvCfg<CIN, NT, TAPS, MT, STAGES>;
@@ -207,6 +211,9 @@ __device__ __forceinline__ void conv_epilogue(const ConvParams& p, const uint32_
           int64_t off[2];
           off[0] = offset_of(geo, u, 0, valid);
           off[1] = offset_of(geo, u, 1, valid);
+          float sv[SAL ? 16 : 1];               // this pixel's 16 bf16-rounded outputs (zero for pixels outside the image)
+#pragma unroll
+          for (int i = 0; i < (SAL ? 16 : 1); ++i) sv[i] = 0.0f;
           if (valid) {
             float f[16];
 #pragma unroll
@@ -255,7 +262,34 @@ __device__ __forceinline__ void conv_epilogue(const ConvParams& p, const uint32_
                   st_s[STATS ? c + 1 : 0] += hi;  st_q[STATS ? c + 1 : 0] = fmaf(hi, hi, st_q[STATS ? c + 1 : 0]);
                 }
               }
-              *reinterpret_cast<uint4*>(p.out + off[h8]) = make_uint4(o[0], o[1], o[2], o[3]);
+              if (SAL) {
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                  sv[SAL ? 8 * h8 + 2 * i : 0] = __uint_as_float(o[i] << 16);
+                  sv[SAL ? 8 * h8 + 2 * i + 1 : 0] = __uint_as_float(o[i] & 0xffff0000u);
+                }
+              }
+              if (!SAL || !p.no_store) *reinterpret_cast<uint4*>(p.out + off[h8]) = make_uint4(o[0], o[1], o[2], o[3]);
+            }
+          }
+          if (SAL) {
+            // fp64 sums of bf16 values: exact (hence order-independent) while the dynamic range of one sample's
+            // gradient stays below 2^37 -- the same numbers K1 would sum from the materialised tensor
+            const int mt = item / kChunks;
+            if (p.sal_mode == CTL_MODE_CHANNEL) {
+              // the warp's 32 pixels belong to one image: reduce over them, one atomic per channel
+#pragma unroll
+              for (int i = 0; i < 16; ++i) {
+                double t = (double)sv[SAL ? i : 0];
+#pragma unroll
+                for (int o2 = 16; o2 > 0; o2 >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o2);
+                if (lane == i) atomicAdd(p.sal + (int64_t)geo.img * p.Cout + n0 + c0 + i, t);
+              }
+            } else if (valid) {
+              double t = 0.0;
+#pragma unroll
+              for (int i = 0; i < 16; ++i) t += (double)sv[SAL ? i : 0];
+              atomicAdd(p.sal + (int64_t)geo.img * ((int64_t)p.H * p.W) + (int64_t)geo.y * p.W + geo.xb + mt * 8, t);
             }
           }
         }
@@ -420,7 +454,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap, const ConvParams p) {
     // variant (stride 2 / ConvTranspose scatter) pays the per-item 64-bit address arithmetic the others hoist
     if (p.up2x || p.subsample != 1)
       conv_epilogue<CIN, NT, TAPS, MT, STAGES, true, false, true>(p, tmem_base, sVec, acc_full, acc_empty, n0, reinterpret_cast<float*>(sA));
-    else if (p.res != nullptr)
+    else if (p.res != nullptr && p.sal != nullptr) {
+      if constexpr ((CIN == 64 || CIN == 128) && TAPS == 1)   // the last input-gradient convolution of a decoder (up1: 1x1)
+        conv_epilogue<CIN, NT, TAPS, MT, STAGES, true, false, false, true>(p, tmem_base, sVec, acc_full, acc_empty, n0, reinterpret_cast<float*>(sA));
+    } else if (p.res != nullptr)
       conv_epilogue<CIN, NT, TAPS, MT, STAGES, true, false, false>(p, tmem_base, sVec, acc_full, acc_empty, n0, reinterpret_cast<float*>(sA));
     else if (p.stats != nullptr)
       conv_epilogue<CIN, NT, TAPS, MT, STAGES, false, true, false>(p, tmem_base, sVec, acc_full, acc_empty, n0, reinterpret_cast<float*>(sA));
@@ -531,11 +568,11 @@ extern "C" int ctl_conv2d_n_tile(int Cin, int Cout, int taps) {
   return -1;
 }
 
-extern "C" int ctl_conv2d_c8_bf16(const void* x, int64_t N, int64_t H, int64_t W, int64_t Cin, const void* w_packed,
-                                  int64_t Cout, int taps, int subsample, int up2x, const float* scale,
-                                  const float* shift, const void* res, const float* res_scale, const float* res_shift,
-                                  int act, void* out, double* stats, void* stream) {
-  CTL_REQUIRE(x && w_packed && out, CTL_ERR_INVALID, "ctl_conv2d_c8_bf16: NULL pointer");
+static int conv2d_c8_impl(const void* x, int64_t N, int64_t H, int64_t W, int64_t Cin, const void* w_packed,
+                          int64_t Cout, int taps, int subsample, int up2x, const float* scale,
+                          const float* shift, const void* res, const float* res_scale, const float* res_shift,
+                          int act, void* out, double* stats, double* sal, int sal_mode, int store_out, void* stream) {
+  CTL_REQUIRE(x && w_packed && (out || (sal && !store_out)), CTL_ERR_INVALID, "ctl_conv2d_c8_bf16: NULL pointer");
   CTL_REQUIRE(!up2x || (taps == 1 && subsample == 1 && Cout % 32 == 0), CTL_ERR_INVALID,
               "up2x (ConvTranspose2d k2 s2) needs taps == 1, subsample == 1 and Cout = 4 * out_channels, out_channels %% 8 == 0");
   CTL_REQUIRE(N > 0 && H > 0 && W > 0 && N <= 65535 && H <= 32768 && W <= 32768, CTL_ERR_INVALID,
@@ -562,6 +599,13 @@ extern "C" int ctl_conv2d_c8_bf16(const void* x, int64_t N, int64_t H, int64_t W
   p.scale = scale; p.shift = shift;
   p.res = (const __nv_bfloat16*)res; p.res_scale = res_scale; p.res_shift = res_shift;
   p.out = (__nv_bfloat16*)out; p.act = act; p.subsample = subsample; p.up2x = up2x; p.stats = stats;
+  if (sal != nullptr) {
+    CTL_REQUIRE((Cin == 64 || Cin == 128) && taps == 1 && res != nullptr && stats == nullptr && subsample == 1 && !up2x,
+                CTL_ERR_UNSUPPORTED,
+                "fused latent saliency: only a 1x1 input-gradient convolution with 64 / 128 input channels and a residual carries it");
+    CTL_REQUIRE(sal_mode == CTL_MODE_CHANNEL || sal_mode == CTL_MODE_SPATIAL, CTL_ERR_INVALID, "unknown saliency mode %d", sal_mode);
+    p.sal = sal; p.sal_mode = sal_mode; p.no_store = store_out ? 0 : 1;
+  }
   cudaStream_t st = (cudaStream_t)stream;
   if (taps == 9) {
     switch ((int)Cin) {
@@ -577,4 +621,20 @@ extern "C" int ctl_conv2d_c8_bf16(const void* x, int64_t N, int64_t H, int64_t W
     case 64: return dispatch_nt<64, 1>(x, p, nt, st);
     default: return dispatch_nt<128, 1>(x, p, nt, st);
   }
+}
+
+extern "C" int ctl_conv2d_c8_bf16(const void* x, int64_t N, int64_t H, int64_t W, int64_t Cin, const void* w_packed,
+                                  int64_t Cout, int taps, int subsample, int up2x, const float* scale,
+                                  const float* shift, const void* res, const float* res_scale, const float* res_shift,
+                                  int act, void* out, double* stats, void* stream) {
+  return conv2d_c8_impl(x, N, H, W, Cin, w_packed, Cout, taps, subsample, up2x, scale, shift, res, res_scale, res_shift, act,
+                        out, stats, nullptr, 0, 1, stream);
+}
+
+extern "C" int ctl_conv2d_c8_bf16_saliency(const void* x, int64_t N, int64_t H, int64_t W, int64_t Cin,
+                                           const void* w_packed, int64_t Cout, const void* res, void* out,
+                                           double* sal_sums, int sal_mode, int store_out, void* stream) {
+  CTL_REQUIRE(sal_sums != nullptr, CTL_ERR_INVALID, "ctl_conv2d_c8_bf16_saliency: NULL saliency buffer");
+  return conv2d_c8_impl(x, N, H, W, Cin, w_packed, Cout, 1, 1, 0, nullptr, nullptr, res, nullptr, nullptr, CTL_ACT_NONE, out,
+                        nullptr, sal_sums, sal_mode, store_out, stream);
 }

@@ -350,6 +350,53 @@ __global__ void philox_uniform_kernel(PhiloxKey key, uint64_t first, int64_t cou
     out[i] = philox_uniform(key, first + (uint64_t)i);
 }
 
+// ------------------------------------------------------------------------------------------------
+// Fused tail of the latent masking for the training path: ONE CTA per sample takes the
+// per-sample saliency SUMS that the decoder's last input-gradient convolution accumulated in its epilogue
+// (conv_tc.cu, fp64, dL/dz itself never reaches HBM), turns them into s exactly as K1 does (fp64 sum / count, rounded
+// to fp32 once), selects the k-th largest, builds the mask row and applies it to the sample's code -- written BOTH as
+// the NCHW fp32 tensor the reference API returns and as the blocked bf16 C8 tensor the decoder's first convolution
+// consumes (no separate layout conversion in front of decoder_inference).
+// ------------------------------------------------------------------------------------------------
+template <int MODE>
+__global__ void __launch_bounds__(kThreads)
+sums_select_apply_kernel(const double* __restrict__ sums, const float* __restrict__ z, int C, int HW, SelectArgs sa,
+                         float* __restrict__ s_out, float* __restrict__ z_out, __nv_bfloat16* __restrict__ z_c8) {
+  __shared__ SelectSmem sm;
+  const int64_t sample = blockIdx.x;
+  const int n = MODE == CTL_MODE_CHANNEL ? C : HW;
+  const double count = (double)(MODE == CTL_MODE_CHANNEL ? HW : C);
+  if (sa.dyn) {
+    const int64_t kd = sa.dyn[0];
+    sa.k = (int)(kd < 0 ? 0 : kd >= n ? n - 1 : kd);
+    sa.key.offset = (uint64_t)sa.dyn[1];
+    sa.first_sample = sa.dyn[2];
+  }
+  float* srow = s_out + sample * n;
+  for (int j = threadIdx.x; j < n; j += blockDim.x) srow[j] = (float)(sums[sample * n + j] / count);
+  __syncthreads();
+  float* mrow = sa.mask_out + sample * (int64_t)n;
+  select_and_build_mask(srow, n, sa.k, sa.soft, sa.rand, sa.key, (uint64_t)(sa.first_sample + sample) * (uint64_t)n,
+                        sample * (int64_t)n, mrow, sa.thr_out ? sa.thr_out + sample : nullptr, sm);
+  __syncthreads();
+  const float* __restrict__ zs = z + sample * (int64_t)C * HW;
+  float* __restrict__ zo = z_out + sample * (int64_t)C * HW;
+  const int groups = C >> 3;                                  // C % 8 == 0 (checked on the host)
+  for (int idx = threadIdx.x; idx < groups * HW; idx += blockDim.x) {
+    const int gq = idx / HW, pix = idx - gq * HW;
+    float v[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) v[j] = __ldcs(zs + (int64_t)(gq * 8 + j) * HW + pix);
+    const float mp = MODE == CTL_MODE_SPATIAL ? __ldcg(mrow + pix) : 1.0f;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      v[j] *= MODE == CTL_MODE_CHANNEL ? __ldcg(mrow + gq * 8 + j) : mp;
+      zo[(int64_t)(gq * 8 + j) * HW + pix] = v[j];
+    }
+    if (z_c8) store_from_float<__nv_bfloat16, 8>(z_c8 + ((sample * groups + gq) * (int64_t)HW + pix) * 8, v);
+  }
+}
+
 // ---- launch helpers ------------------------------------------------------------------------------
 // lanes per row: enough rows in flight per CTA, yet most of a row covered by one kU-deep batch
 inline int pick_lanes(int nv) { return nv >= 128 ? 32 : nv >= 64 ? 16 : nv >= 16 ? 8 : 4; }
@@ -584,6 +631,31 @@ extern "C" int ctl_saliency_mask_apply_dyn(const void* g, int g_dtype, const voi
   CTL_REQUIRE(step_params, CTL_ERR_INVALID, "ctl_saliency_mask_apply_dyn: NULL step_params");
   return saliency_mask_apply_impl(g, g_dtype, z, z_dtype, N, C, HW, mode, /*k=*/0, soft, rand, seed, 0, 0, s_scratch,
                                   mask_out, thr_out, z_out, out_dtype, step_params, stream);
+}
+
+extern "C" int ctl_saliency_sums_mask_apply(const double* sums, const float* z, int64_t N, int64_t C, int64_t HW, int mode,
+                                            int64_t k, int soft, const float* rand, uint64_t seed, uint64_t offset,
+                                            int64_t first_sample, const int64_t* step_params, float* s_out,
+                                            float* mask_out, float* thr_out, float* z_out, void* z_c8_out, void* stream) {
+  CTL_REQUIRE(sums && z && s_out && mask_out && z_out, CTL_ERR_INVALID, "ctl_saliency_sums_mask_apply: NULL pointer");
+  CTL_REQUIRE(mode == CTL_MODE_CHANNEL || mode == CTL_MODE_SPATIAL, CTL_ERR_INVALID, "unknown mode %d", mode);
+  if (int rc = check_shape(N, C, HW)) return rc;
+  CTL_REQUIRE(C % 8 == 0, CTL_ERR_UNSUPPORTED, "ctl_saliency_sums_mask_apply: C must be a multiple of 8 (got %lld)", (long long)C);
+  CTL_REQUIRE(!z_c8_out || aligned16(z_c8_out), CTL_ERR_INVALID, "ctl_saliency_sums_mask_apply: z_c8_out must be 16-byte aligned");
+  const int64_t n = mode == CTL_MODE_CHANNEL ? C : HW;
+  if (!step_params)
+    if (int rc = check_select(n, k, first_sample)) return rc;
+  if (sm_count() < 0) return CTL_ERR_CUDA;
+  cudaStream_t st = (cudaStream_t)stream;
+  SelectArgs sa = {mask_out, thr_out, rand, PhiloxKey{seed, offset}, first_sample, (int)k, soft != 0, step_params};
+  if (mode == CTL_MODE_CHANNEL)
+    sums_select_apply_kernel<CTL_MODE_CHANNEL><<<(unsigned)N, kThreads, 0, st>>>(sums, z, (int)C, (int)HW, sa, s_out, z_out,
+                                                                                 (__nv_bfloat16*)z_c8_out);
+  else
+    sums_select_apply_kernel<CTL_MODE_SPATIAL><<<(unsigned)N, kThreads, 0, st>>>(sums, z, (int)C, (int)HW, sa, s_out, z_out,
+                                                                                 (__nv_bfloat16*)z_c8_out);
+  CTL_CUDA_OK(cudaGetLastError(), "sums_select_apply launch");
+  return CTL_OK;
 }
 
 static int channel_dropout_impl(const void* z, int z_dtype, int64_t N, int64_t C, int64_t HW, float p, float scale,

@@ -41,18 +41,19 @@ __global__ void adam_bump_kernel(float* __restrict__ steps, int count, unsigned 
 // v = b2*v + (1-b2) g'^2;  p -= lr/(1-b1^t) * m / (sqrt(v)/sqrt(1-b2^t) + eps)
 __global__ void __launch_bounds__(kT)
 adam_flat_kernel(float* __restrict__ p, float* __restrict__ g, float* __restrict__ m, float* __restrict__ v,
-                 const AdamSegs segs, const float* __restrict__ steps, float lr, float b1, float b2, float eps, float wd,
+                 const AdamSegs segs, const float* __restrict__ steps, double lr, double b1d, double b2d, float eps, float wd,
                  float grad_scale, int zero_grad) {
   __shared__ float s_step_size[kMaxSeg], s_bc2_rsqrt[kMaxSeg];
   if ((int)threadIdx.x < segs.count) {
     const double t = (double)steps[threadIdx.x];
-    const double bc1 = 1.0 - pow((double)b1, t), bc2 = 1.0 - pow((double)b2, t);
-    s_step_size[threadIdx.x] = (float)((double)lr / bc1);
+    const double bc1 = 1.0 - pow(b1d, t), bc2 = 1.0 - pow(b2d, t);
+    s_step_size[threadIdx.x] = (float)(lr / bc1);
     s_bc2_rsqrt[threadIdx.x] = (float)(1.0 / sqrt(bc2));
   }
   __syncthreads();
   const long long n4 = segs.end[segs.count - 1] >> 2;          // the buffers are padded to a multiple of 4
-  const float omb1 = 1.0f - b1, omb2 = 1.0f - b2;
+  // the constants as torch.optim.Adam forms them: 1 - beta in DOUBLE, then rounded to fp32 (1.0f - 0.999f is 4.7e-5 off)
+  const float b2 = (float)b2d, omb1 = (float)(1.0 - b1d), omb2 = (float)(1.0 - b2d);
   for (long long i = (long long)blockIdx.x * kT + threadIdx.x; i < n4; i += (long long)gridDim.x * kT) {
     const long long e = i << 2;
     int s = 0;
@@ -220,15 +221,15 @@ int stream_grid(long long work_items) {
 using namespace ctl;
 
 extern "C" int ctl_adam_flat(float* params, float* grads, float* exp_avg, float* exp_avg_sq, const int64_t* seg_bounds_host,
-                             int n_segments, unsigned seg_mask, float* steps, float lr, float beta1, float beta2, float eps,
-                             float weight_decay, float grad_scale, int zero_grad, void* stream) {
+                             int n_segments, unsigned seg_mask, float* steps, double lr, double beta1, double beta2, double eps,
+                             double weight_decay, double grad_scale, int zero_grad, void* stream) {
   CTL_REQUIRE(params && grads && exp_avg && exp_avg_sq && seg_bounds_host && steps, CTL_ERR_INVALID,
               "ctl_adam_flat: NULL pointer");
   CTL_REQUIRE(n_segments >= 1 && n_segments <= kMaxSeg, CTL_ERR_INVALID, "ctl_adam_flat: 1..%d segments (got %d)", kMaxSeg,
               n_segments);
   CTL_REQUIRE(aligned16(params) && aligned16(grads) && aligned16(exp_avg) && aligned16(exp_avg_sq), CTL_ERR_INVALID,
               "ctl_adam_flat: buffers must be 16-byte aligned");
-  CTL_REQUIRE(lr >= 0.f && beta1 >= 0.f && beta1 < 1.f && beta2 >= 0.f && beta2 < 1.f && eps >= 0.f, CTL_ERR_INVALID,
+  CTL_REQUIRE(lr >= 0. && beta1 >= 0. && beta1 < 1. && beta2 >= 0. && beta2 < 1. && eps >= 0., CTL_ERR_INVALID,
               "ctl_adam_flat: bad hyper-parameters lr=%g betas=(%g,%g) eps=%g", lr, beta1, beta2, eps);
   AdamSegs segs = {};
   segs.count = n_segments;
@@ -251,8 +252,8 @@ extern "C" int ctl_adam_flat(float* params, float* grads, float* exp_avg, float*
   if (grid < 0) return CTL_ERR_CUDA;
   cudaStream_t st = (cudaStream_t)stream;
   adam_bump_kernel<<<1, 32, 0, st>>>(steps, n_segments, seg_mask);
-  adam_flat_kernel<<<grid, kT, 0, st>>>(params, grads, exp_avg, exp_avg_sq, segs, steps, lr, beta1, beta2, eps,
-                                        weight_decay, grad_scale, zero_grad);
+  adam_flat_kernel<<<grid, kT, 0, st>>>(params, grads, exp_avg, exp_avg_sq, segs, steps, lr, beta1, beta2, (float)eps,
+                                        (float)weight_decay, (float)grad_scale, zero_grad);
   CTL_CUDA_OK(cudaGetLastError(), "adam_flat launch");
   return CTL_OK;
 }

@@ -50,6 +50,15 @@ def native_rng():
 
 
 _STEP_PARAMS = None
+_FUSED_SALIENCY = True      # tests switch it off to compare with the materialised-gradient chain (K1 -> select -> K2)
+
+
+def set_fused_saliency(flag):
+    """True (default): on the kernel training route the latent saliency is reduced in the epilogue of the decoder's last
+    input-gradient convolution and dL/dz is never materialised; False: autograd.grad + K1 + select + K2."""
+    global _FUSED_SALIENCY
+    _FUSED_SALIENCY = bool(flag)
+
 
 
 @contextlib.contextmanager
@@ -170,33 +179,43 @@ class _MaskedCode(torch.autograd.Function):
         return grad_out * mask_all, None, None
 
 
-def _latent_gradient(latent_code, decoder_function, label, num_classes, loss_type):
+def _latent_gradient(latent_code, decoder_function, label, num_classes, loss_type, fused_mode=None):
+    """Returns (code leaf, dL/dcode, saliency request or None).  fused_mode (ops.MODE_*) asks for the on-chip saliency
+    reduction: when this build's own decoder serves it, the request comes back `served` with the per-sample sums and the
+    returned gradient tensor is an uninitialised placeholder (dL/dz was never stored)."""
     if not latent_code.is_cuda:
         raise RuntimeError("this build runs the latent masking on CUDA only (sm_100a kernels, no CPU fallback); "
                            "got a latent code on %s" % latent_code.device)
+    from . import trainpath
     code = makeVariable(latent_code, use_gpu=True, type='float', requires_grad=True)
+    request = None
+    if fused_mode is not None and loss_type in ('mse', 'ce') and trainpath.saliency_fusable(decoder_function, code):
+        N, C, H, W = code.shape
+        request = trainpath.SaliencyRequest(fused_mode, N, C if fused_mode == ops.MODE_CHANNEL else H * W, code.device)
     gt_y = make_one_hot(label, num_classes) if label.dim() < code.dim() else label
-    if loss_type == 'corr':
-        loss = torch.mean(decoder_function(code) * gt_y)
-    elif loss_type == 'mse':
-        pred = decoder_function(code)
-        if ops.sse_supported(pred, gt_y):
-            loss = ops.squared_error(pred, gt_y, 1.0 / pred.numel())       # torch.mean((pred - gt)**2), one kernel each way
+    with (request if request is not None else contextlib.nullcontext()):
+        if loss_type == 'corr':
+            loss = torch.mean(decoder_function(code) * gt_y)
+        elif loss_type == 'mse':
+            pred = decoder_function(code)
+            if ops.sse_supported(pred, gt_y):
+                loss = ops.squared_error(pred, gt_y, 1.0 / pred.numel())   # torch.mean((pred - gt)**2), one kernel each way
+            else:
+                loss = torch.mean((pred - gt_y) ** 2)
+        elif loss_type == 'ce':
+            loss = torch.mean(cross_entropy_2D(input=decoder_function(code), target=label, weight=None,
+                                               size_average=True))
         else:
-            loss = torch.mean((pred - gt_y) ** 2)
-    elif loss_type == 'ce':
-        loss = torch.mean(cross_entropy_2D(input=decoder_function(code), target=label, weight=None,
-                                           size_average=True))
-    else:
-        # the reference falls through to an unbound `loss` here -> UnboundLocalError
-        raise UnboundLocalError("loss_type %r is not one of 'corr', 'mse', 'ce'" % (loss_type,))
-    gradient = torch.autograd.grad(loss, [code])[0]
-    return code, gradient
+            # the reference falls through to an unbound `loss` here -> UnboundLocalError
+            raise UnboundLocalError("loss_type %r is not one of 'corr', 'mse', 'ce'" % (loss_type,))
+        gradient = torch.autograd.grad(loss, [code])[0]
+    return code, gradient, request
 
 
 def _mask_latent_code(mode, latent_code, decoder_function, label, num_classes, percentile, random, loss_type,
                       if_detach, if_soft):
-    code, gradient = _latent_gradient(latent_code, decoder_function, label, num_classes, loss_type)
+    code, gradient, request = _latent_gradient(latent_code, decoder_function, label, num_classes, loss_type,
+                                               fused_mode=mode if _FUSED_SALIENCY else None)
     N, C, H, W = code.shape
     n = C if mode == ops.MODE_CHANNEL else H * W
     if random:
@@ -213,8 +232,15 @@ def _mask_latent_code(mode, latent_code, decoder_function, label, num_classes, p
             rand = torch.rand((N, n), device=code.device, dtype=torch.float32)   # == torch.rand_like(s)
         else:
             rng = _NATIVE_RNG
-    masked, mask, _, _ = ops.saliency_mask_apply(gradient, code.detach(), mode, k, soft=if_soft, rand=rand, rng=rng,
-                                                 out_dtype=torch.float32, step_params=_STEP_PARAMS)
+    if request is not None and request.served:
+        # dL/dz was reduced inside the decoder's last input-gradient convolution; one kernel per call finishes the job
+        # and also writes the masked code in the decoder's own blocked layout
+        masked, mask, _, _, c8 = ops.saliency_sums_mask_apply(request.sums, code.detach(), mode, k, soft=if_soft,
+                                                              rand=rand, rng=rng, step_params=_STEP_PARAMS)
+        ops.register_c8_twin(masked, c8)
+    else:
+        masked, mask, _, _ = ops.saliency_mask_apply(gradient, code.detach(), mode, k, soft=if_soft, rand=rand, rng=rng,
+                                                     out_dtype=torch.float32, step_params=_STEP_PARAMS)
     mask_all = mask.view(N, C, 1, 1) if mode == ops.MODE_CHANNEL else mask.view(N, 1, H, W)
     if not if_detach:
         # graph stays attached to the caller's latent (model_util.py:246-247)

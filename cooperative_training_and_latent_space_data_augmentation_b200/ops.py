@@ -870,3 +870,80 @@ def confusion_scores(hist):
     with torch.cuda.device(hist.device):
         _lib.check(_lib.load().ctl_confusion_scores(hist.data_ptr(), C, out.data_ptr(), _stream()))
     return out
+
+
+# ------------------------------------------------------------------------------------------------ fused latent saliency
+def conv2d_c8_saliency(x, w_packed, cout, res, sal_sums, mode, store_out=False):
+    """1x1 convolution out = conv(x) + res (the decoder's last input-gradient convolution) whose epilogue accumulates the
+    per-sample saliency sums of its bf16-rounded output into `sal_sums` (fp64 [N, cout] channel mode / [N, H*W] spatial
+    mode, zeroed by the caller).  store_out=False: the output -- dL/dz -- is not written at all; returns None then."""
+    _need_cuda(x, w_packed, res, sal_sums)
+    N, cin, H, W = _c8_dims(x)
+    n = cout if mode == MODE_CHANNEL else H * W
+    if sal_sums.dtype != torch.float64 or tuple(sal_sums.shape) != (N, n) or not sal_sums.is_contiguous():
+        raise ValueError("sal_sums must be a contiguous float64 [%d,%d] tensor" % (N, n))
+    if res is None or tuple(res.shape) != (N, cout // 8, H, W, 8):
+        raise ValueError("res must be the C8 tensor the convolution output is added to")
+    out = torch.empty((N, cout // 8, H, W, 8), device=x.device, dtype=torch.bfloat16) if store_out else None
+    with torch.cuda.device(x.device):
+        _lib.check(_lib.load().ctl_conv2d_c8_bf16_saliency(x.data_ptr(), N, H, W, cin, w_packed.data_ptr(), cout,
+                                                           res.data_ptr(), _ptr(out), sal_sums.data_ptr(), mode,
+                                                           int(bool(store_out)), _stream()))
+    return out
+
+
+def saliency_sums_mask_apply(sums, z, mode, k, soft=False, rand=None, rng=None, want_thr=False, step_params=None,
+                             want_c8=True):
+    """The masking tail on saliency SUMS (see conv2d_c8_saliency).  Returns (z_masked NCHW fp32, mask [N,n], s [N,n],
+    thr or None, z_masked as C8 bf16 or None)."""
+    _need_cuda(sums, z, rand)
+    z = z.contiguous()
+    N, C, HW = _nchw(z)
+    n = C if mode == MODE_CHANNEL else HW
+    if z.dtype != torch.float32 or sums.dtype != torch.float64 or tuple(sums.shape) != (N, n):
+        raise ValueError("expected fp32 z and float64 sums [%d,%d]" % (N, n))
+    if rand is not None:
+        rand = rand.contiguous()
+        if tuple(rand.shape) != (N, n) or rand.dtype != torch.float32:
+            raise ValueError("rand must be float32 [%d,%d]" % (N, n))
+    native = soft and rand is None
+    if native and rng is None:
+        raise ValueError("soft masking needs either `rand` (torch-compatible mode) or `rng` (native mode)")
+    s = torch.empty((N, n), device=z.device, dtype=torch.float32)
+    z_out = torch.empty_like(z)
+    mask = torch.empty((N, n), device=z.device, dtype=torch.float32)
+    thr = torch.empty((N,), device=z.device, dtype=torch.float32) if want_thr else None
+    c8 = torch.empty((N, C // 8, z.shape[2], z.shape[3], 8), device=z.device, dtype=torch.bfloat16) if want_c8 else None
+    seed = offset = first = 0
+    row = None
+    if step_params is not None:
+        if not 0 <= int(k) < n:
+            raise IndexError("index {} is out of bounds for dimension 1 with size {}".format(int(k), n))
+        row = step_params.take("mask", n, k, rng if native else None)
+        seed = rng.seed if native else 0
+    elif native:
+        seed, offset, first = rng.seed, rng.next_offset(), rng.first_sample
+    with torch.cuda.device(z.device):
+        _lib.check(_lib.load().ctl_saliency_sums_mask_apply(
+            sums.data_ptr(), z.data_ptr(), N, C, HW, mode, int(k), int(bool(soft)), _ptr(rand), seed, offset, first,
+            _ptr(row), s.data_ptr(), mask.data_ptr(), _ptr(thr), z_out.data_ptr(), _ptr(c8), _stream()))
+    return z_out, mask, s, thr, c8
+
+
+# NCHW fp32 latent code -> its blocked bf16 twin written by the same kernel (saliency_sums_mask_apply): the decoder's
+# forward picks the twin up instead of converting the layout again.  The entry keeps the NCHW tensor alive, so its
+# address cannot be reused by another tensor while the entry exists; two entries (image code, shape code) are kept.
+_C8_TWINS = []
+
+
+def register_c8_twin(nchw, c8):
+    _C8_TWINS.append((nchw, nchw._version, c8))
+    del _C8_TWINS[:-2]
+
+
+def c8_twin(nchw):
+    for t, version, c8 in _C8_TWINS:
+        if t.data_ptr() == nchw.data_ptr() and tuple(t.shape) == tuple(nchw.shape) and t._version == version \
+                and nchw._version == version and nchw.dtype == t.dtype and nchw.is_contiguous():
+            return c8
+    return None

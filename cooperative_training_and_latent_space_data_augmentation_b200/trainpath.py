@@ -109,6 +109,34 @@ def _wgrad(grads, conv, x, dy):
     return ops.conv_wgrad_c8(x, dy, k * k, out=grads.buffer(conv.weight), layout='conv')
 
 
+class SaliencyRequest:
+    """While active (a `with` block around the saliency pass of model_util._mask_latent_code), the backward of the next
+    decoder Function does not materialise dL/dz: its last input-gradient convolution accumulates the per-sample saliency
+    sums in its epilogue (ops.conv2d_c8_saliency) into `sums` and `served` turns True."""
+    active = None             # process-global on purpose: backward nodes run on autograd's device thread
+
+    def __init__(self, mode, N, n, device):
+        self.mode, self.N, self.n = mode, N, n
+        self.sums = torch.zeros((N, n), device=device, dtype=torch.float64)
+        self.served = False
+
+    def __enter__(self):
+        self.prev, SaliencyRequest.active = SaliencyRequest.active, self
+        return self
+
+    def __exit__(self, *exc):
+        SaliencyRequest.active = self.prev
+        return False
+
+
+def saliency_fusable(decoder, code):
+    """The fused form covers this build's own decoders on the kernel training route with a 128-channel CUDA fp32 code."""
+    from . import networks
+    return (isinstance(decoder, networks.MyDecoder) and networks._kernel_route(decoder, code) == 'train'
+            and code.dim() == 4 and code.dtype == torch.float32 and code.shape[1] % 8 == 0
+            and decoder.up1.conv_input.in_channels == code.shape[1])
+
+
 _DIRECT = {"on": False}      # process-global on purpose: backward nodes run on autograd's device thread
 
 
@@ -292,13 +320,28 @@ def up_fwd(fw, block, x):
     return out, (x, s)
 
 
-def up_bwd(block, saved, dout, grads, need_dx=True):
+def _dgrad_saliency(sal, weight, fn, tag, dy, cout, res):
+    """Last input-gradient convolution of a decoder with the saliency sums fused into its epilogue; dL/dz is not stored."""
+    wp = _packed(weight, fn, tag=tag)
+    ops.conv2d_c8_saliency(dy, wp, cout, res, sal.sums, sal.mode, store_out=False)
+    sal.served = True
+    return None
+
+
+def up_bwd(block, saved, dout, grads, need_dx=True, sal=None):
     x, s = saved
+    if sal is not None and (sal.sums.shape[0] != x.shape[0] or
+                            sal.n != (x.shape[1] * 8 if sal.mode == ops.MODE_CHANNEL else x.shape[2] * x.shape[3])):
+        sal = None                                              # a request for another tensor shape: ignore it
     if block.up_type == 'NN':
         dxu, dc = residual_bwd(block, s, dout, grads, x_low=x)
         if not need_dx:
             return None
         # main branch back through the up-sampling (2x2 sums) + the shortcut's input gradient, both at low resolution
+        ci = block.conv_input
+        if sal is not None and ci.out_channels in (64, 128):
+            return _dgrad_saliency(sal, ci.weight, ops.pack_conv_weight_dgrad, 'dgrad', dc, ci.in_channels,
+                                   ops.downsample2x_sum_c8(dxu))
         return _dgrad(block.conv_input, dc, res=ops.downsample2x_sum_c8(dxu))
     dxu, _ = residual_bwd(block, s, dout, grads)
     up = block.up
@@ -315,7 +358,10 @@ def up_bwd(block, saved, dout, grads, need_dx=True):
     dx = None
     if need_dx:
         for d in range(4):
-            wp = _packed(up.weight, lambda w, d=d: ops.pack_conv_weight(_convT_tap_weight(up, d)), tag='dgradT%d' % d)
+            fn = lambda w, d=d: ops.pack_conv_weight(_convT_tap_weight(up, d))      # noqa: E731
+            if d == 3 and sal is not None and up.out_channels in (64, 128):
+                return _dgrad_saliency(sal, up.weight, fn, 'dgradT3', parts[3], up.in_channels, dx)
+            wp = _packed(up.weight, fn, tag='dgradT%d' % d)
             dx = ops.conv2d_c8(parts[d], wp, up.in_channels, 1, res=dx)
     return dx
 
@@ -413,8 +459,9 @@ def decoder_bwd(dec, tape, dout, grads, need_dz):
     grads.add(fc.bias, db)
     d = dy
     blocks = (dec.up1, dec.up2, dec.up3, dec.up4)
+    sal = SaliencyRequest.active if need_dz else None
     for i in (3, 2, 1, 0):
-        d = up_bwd(blocks[i], tape[i], d, grads, need_dx=(i > 0 or need_dz))
+        d = up_bwd(blocks[i], tape[i], d, grads, need_dx=(i > 0 or need_dz), sal=sal if i == 0 else None)
     return d
 
 
@@ -426,15 +473,26 @@ def _param_grads(params, grads):
 class _DecoderFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, dec, z, *params):
-        out, tape = decoder_fwd(dec, ops.nchw_to_c8(z))
+        z_c8 = ops.c8_twin(z)               # written by the masking kernel itself when z is a freshly masked code
+        out, tape = decoder_fwd(dec, z_c8 if z_c8 is not None else ops.nchw_to_c8(z))
         ctx.dec, ctx.tape, ctx.params = dec, tape, params
+        ctx.z_shape = tuple(z.shape)
         return out
 
     @staticmethod
     def backward(ctx, dout):
+        if ctx.tape is None:
+            raise RuntimeError("this sub-network's activations were released by its first backward pass "
+                               "(retain_graph / a second backward through the kernel path is not supported)")
         grads = _Grads(ctx.params, ctx.needs_input_grad[2:])
+        sal = SaliencyRequest.active
+        served0 = sal.served if sal is not None else False
         dz = decoder_bwd(ctx.dec, ctx.tape, dout.contiguous(), grads, ctx.needs_input_grad[1])
         ctx.tape = None
+        if dz is None and ctx.needs_input_grad[1] and sal is not None and sal.served and not served0:
+            # the saliency pass: dL/dz was reduced on-chip and never stored; autograd still wants a tensor of the
+            # right shape for the (ignored) input gradient -- an allocation, no kernel
+            return (None, torch.empty(ctx.z_shape, device=dout.device, dtype=torch.float32)) + _param_grads(ctx.params, grads)
         dz = ops.c8_to_nchw(dz) if dz is not None else None
         return (None, dz) + _param_grads(ctx.params, grads)
 
@@ -456,6 +514,9 @@ class _EncoderFn(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, dz_i, dz_s=None):
+        if ctx.tape is None:
+            raise RuntimeError("this sub-network's activations were released by its first backward pass "
+                               "(retain_graph / a second backward through the kernel path is not supported)")
         grads = _Grads(ctx.params, ctx.needs_input_grad[5:])
         dz = ops.nchw_to_c8(dz_i) if dz_i is not None else None
         if ctx.decoupler is not None and dz_s is not None:
@@ -476,6 +537,9 @@ class _DecouplerFn(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, dout):
+        if ctx.tape is None:
+            raise RuntimeError("this sub-network's activations were released by its first backward pass "
+                               "(retain_graph / a second backward through the kernel path is not supported)")
         grads = _Grads(ctx.params, ctx.needs_input_grad[2:])
         dz = decoupler_bwd(ctx.seq, ctx.tape, ops.nchw_to_c8(dout), grads)
         ctx.tape = None

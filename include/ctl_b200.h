@@ -284,8 +284,8 @@ int ctl_stem_dgrad_c8(const void* dy, const float* x, int in_mode, float tempera
  * zero_grad != 0: the gradients of the stepped segments are cleared in the same pass (the next step accumulates into
  * zeros: optimizer.zero_grad() of advanced...model.py:755-758 without another sweep). */
 int ctl_adam_flat(float* params, float* grads, float* exp_avg, float* exp_avg_sq, const int64_t* seg_bounds_host,
-                  int n_segments, unsigned seg_mask, float* steps, float lr, float beta1, float beta2, float eps,
-                  float weight_decay, float grad_scale, int zero_grad, void* stream);
+                  int n_segments, unsigned seg_mask, float* steps, double lr, double beta1, double beta2, double eps,
+                  double weight_decay, double grad_scale, int zero_grad, void* stream);
 /* ---------------------------------------------------------------------------------------------
  * Sum of squared errors and its gradient (row f2): loss_out[0] = scale * sum (pred - target)^2 over n fp32 elements;
  * dpred = grad_out[0] * 2 * scale * (pred - target).  Replaces 0.5 * nn.MSELoss()(recon, image)
@@ -307,6 +307,27 @@ int ctl_sse_bwd(const float* pred, const float* target, int64_t n, double scale,
 int ctl_confusion_update(const float* logits, const int64_t* pred_labels, const int64_t* gt, int64_t N, int64_t C,
                          int64_t HW, void* hist, void* labels_out, void* stream);
 int ctl_confusion_scores(const void* hist, int64_t C, double* scores_out, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Latent saliency reduced ON-CHIP in the epilogue of the decoder's last input-gradient convolution, and the masking tail
+ * that consumes it.  Replaces, on the training path, the materialised gradient of
+ *   gradient = torch.autograd.grad(loss, [code])  +  torch.mean(gradient...)    medseg/models/model_util.py:217-225, :285-286
+ * and the layout conversion in front of decoder_inference (advanced...model.py:396-412).
+ * ctl_conv2d_c8_bf16_saliency: the 1x1 convolution (Cin 64 or 128) out = conv(x) + res of ctl_conv2d_c8_bf16 whose
+ * epilogue also accumulates (fp64 atomics, buffer zeroed by the caller) per-sample sums of the bf16-rounded outputs:
+ * sal_sums[N][Cout] summed over pixels (CTL_MODE_CHANNEL) or sal_sums[N][H*W] summed over channels (CTL_MODE_SPATIAL);
+ * store_out == 0: `out` is not written (may be NULL) -- dL/dz never reaches HBM.
+ * ctl_saliency_sums_mask_apply: s = fp32(sums / count) (count = HW or C: the value K1 computes from the materialised
+ * tensor), per-sample top-k threshold and mask as ctl_topp_mask_apply, z~ = z * mask written as NCHW fp32 (z_out) and,
+ * when z_c8_out != NULL, as the blocked bf16 tensor [N][C/8][HW][8] the decoder's first convolution reads.
+ * step_params: NULL, or DEVICE int64[3] = {k, offset, first_sample} as in ctl_saliency_mask_apply_dyn.  z: fp32, C %% 8 == 0. */
+int ctl_conv2d_c8_bf16_saliency(const void* x, int64_t N, int64_t H, int64_t W, int64_t Cin, const void* w_packed,
+                                int64_t Cout, const void* res, void* out, double* sal_sums, int sal_mode, int store_out,
+                                void* stream);
+int ctl_saliency_sums_mask_apply(const double* sums, const float* z, int64_t N, int64_t C, int64_t HW, int mode, int64_t k,
+                                 int soft, const float* rand, uint64_t seed, uint64_t offset, int64_t first_sample,
+                                 const int64_t* step_params, float* s_out, float* mask_out, float* thr_out, float* z_out,
+                                 void* z_c8_out, void* stream);
 
 #ifdef __cplusplus
 }
