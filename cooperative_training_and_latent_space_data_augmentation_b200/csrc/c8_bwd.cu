@@ -71,6 +71,7 @@ __global__ void __launch_bounds__(kT, 3)
 plane_reduce_kernel(const uint4* __restrict__ x, const uint4* __restrict__ h, const uint4* __restrict__ a,
                     uint4* __restrict__ dv_out, double* __restrict__ partial, int64_t planes, int64_t HW, int splits,
                     int act, const float* __restrict__ act_scale, const float* __restrict__ act_shift, int C8) {
+  pdl_entry();
   const int64_t plane = blockIdx.x;
   // h == NULL with an affine: the activation input is recomputed, h = act(a*act_scale[c] + act_shift[c]) has its sign
   float asc[8], ash[8];
@@ -188,6 +189,7 @@ __device__ __forceinline__ void channel_totals(const double* __restrict__ partia
 
 __global__ void channel_sum_finalize_kernel(const double* __restrict__ partial, int64_t planes, int splits, int N, int C,
                                             float* __restrict__ sum_out, float* __restrict__ sumsq_out) {
+  pdl_entry();
   const int c = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (c >= C) return;
   double S1, S2;
@@ -206,6 +208,7 @@ __global__ void bn_fwd_finalize_kernel(const double* __restrict__ partial, int64
                                        float eps, float* __restrict__ scale, float* __restrict__ shift,
                                        float* __restrict__ mean_out, float* __restrict__ var_out, float* running_mean,
                                        float* running_var, float momentum) {
+  pdl_entry();
   const int c = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (c >= C) return;
   double s, q;
@@ -232,6 +235,7 @@ __global__ void bn_fwd_from_sums_kernel(const double* __restrict__ sums, int C, 
                                         const float* __restrict__ beta, float eps, float* __restrict__ scale,
                                         float* __restrict__ shift, float* __restrict__ mean_out, float* __restrict__ var_out,
                                         float* running_mean, float* running_var, float momentum) {
+  pdl_entry();
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= C) return;
   const double mean = sums[c] / count;
@@ -256,6 +260,7 @@ __global__ void bn_bwd_finalize_kernel(const double* __restrict__ partial, int64
                                        double count, const float* __restrict__ mean, const float* __restrict__ var,
                                        float eps, const float* __restrict__ gamma, float* __restrict__ coef,
                                        float* __restrict__ dgamma, float* __restrict__ dbeta) {
+  pdl_entry();
   const int c = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (c >= C) return;
   double S1, S2;
@@ -278,6 +283,7 @@ __global__ void __launch_bounds__(kT)
 bn_bwd_apply_kernel(const uint4* __restrict__ dy, const uint4* __restrict__ h, const uint4* __restrict__ a,
                     const float* __restrict__ coef, uint4* __restrict__ da, int64_t total, int C8, int64_t HW, int act,
                     const float* __restrict__ act_scale, const float* __restrict__ act_shift) {
+  pdl_entry();
   const int C = C8 * 8;
   for (int64_t i = (int64_t)blockIdx.x * kT + threadIdx.x; i < total; i += (int64_t)gridDim.x * kT) {
     const int c0 = (int)((i / HW) % C8) * 8;
@@ -303,6 +309,7 @@ bn_bwd_apply_kernel(const uint4* __restrict__ dy, const uint4* __restrict__ h, c
 // dv = dy * act'(h) only (activation backward without a BatchNorm in front)
 __global__ void __launch_bounds__(kT)
 act_bwd_kernel(const uint4* __restrict__ dy, const uint4* __restrict__ h, uint4* __restrict__ dv, int64_t total, int act) {
+  pdl_entry();
   for (int64_t i = (int64_t)blockIdx.x * kT + threadIdx.x; i < total; i += (int64_t)gridDim.x * kT) {
     float f[8], hv[8];
     unpack8(__ldcs(dy + i), f);
@@ -317,6 +324,7 @@ act_bwd_kernel(const uint4* __restrict__ dy, const uint4* __restrict__ h, uint4*
 // backward of nearest x2 up-sampling: dx[p] = sum of the 2x2 block of dy; one thread per OUTPUT (low-res) pixel
 __global__ void __launch_bounds__(kT)
 downsample2x_sum_kernel(const uint4* __restrict__ dy, uint4* __restrict__ dx, int64_t planes, int H, int W) {
+  pdl_entry();
   const int64_t total = planes * H * W;
   for (int64_t i = (int64_t)blockIdx.x * kT + threadIdx.x; i < total; i += (int64_t)gridDim.x * kT) {
     const int64_t pl = i / ((int64_t)H * W);
@@ -340,6 +348,7 @@ downsample2x_sum_kernel(const uint4* __restrict__ dy, uint4* __restrict__ dx, in
 // out[2y][2x] = x[y][x], the three other pixels of each 2x2 block = 0 (dy of a stride-2 conv seen at full resolution)
 __global__ void __launch_bounds__(kT)
 zero_stuff2x_kernel(const uint4* __restrict__ x, uint4* __restrict__ y, int64_t planes, int H, int W) {
+  pdl_entry();
   const int64_t total = planes * H * W;
   const uint4 z = make_uint4(0, 0, 0, 0);
   for (int64_t i = (int64_t)blockIdx.x * kT + threadIdx.x; i < total; i += (int64_t)gridDim.x * kT) {
@@ -353,6 +362,7 @@ zero_stuff2x_kernel(const uint4* __restrict__ x, uint4* __restrict__ y, int64_t 
 // out[d][plane][y][x] = x[plane][2y + d/2][2x + d%2], d = 0..3 (dy of a ConvTranspose2d k2 s2 split by kernel tap)
 __global__ void __launch_bounds__(kT)
 split_parity2x2_kernel(const uint4* __restrict__ x, uint4* __restrict__ y, int64_t planes, int H, int W) {
+  pdl_entry();
   const int64_t total = planes * H * W;                // H, W: LOW resolution
   for (int64_t i = (int64_t)blockIdx.x * kT + threadIdx.x; i < total; i += (int64_t)gridDim.x * kT) {
     const int64_t pl = i / ((int64_t)H * W);
@@ -374,6 +384,7 @@ __global__ void __launch_bounds__(kT, 2)
 head_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ yout, const __nv_bfloat16* __restrict__ x,
                 const float* __restrict__ w, __nv_bfloat16* __restrict__ dx, float* __restrict__ dW,
                 float* __restrict__ db, int N, int64_t HW, int act) {
+  pdl_entry();
   constexpr int CIN = 16;
   __shared__ float sw[COUT * CIN];
   __shared__ float red[kT / 32][COUT * CIN + COUT];
@@ -505,6 +516,7 @@ template <int CIN>
 __global__ void __launch_bounds__(kT)
 stem_input_c8_kernel(const float* __restrict__ x, const long long* __restrict__ labels, int in_mode, float inv_temp, int N,
                      int H, int W, uint4* __restrict__ out) {
+  pdl_entry();
   const int64_t HW = (int64_t)H * W, total = (int64_t)N * HW;
   for (int64_t i = (int64_t)blockIdx.x * kT + threadIdx.x; i < total; i += (int64_t)gridDim.x * kT) {
     const int64_t n = i / HW, q = i - n * HW;
@@ -534,6 +546,7 @@ template <int CIN>
 __global__ void __launch_bounds__(kT)
 stem_wgrad_kernel(const __nv_bfloat16* __restrict__ dy, const float* __restrict__ x, const long long* __restrict__ labels,
                   int in_mode, float inv_temp, int N, int H, int W, float* __restrict__ dW) {
+  pdl_entry();
   constexpr int COUT = 16, TW = 32, TH = 8, HW_T = TW + 2, HH_T = TH + 2;
   constexpr int KT = CIN == 4 ? 9 : 3;
   __shared__ float s_in[CIN][HH_T][HW_T + 1];
@@ -625,6 +638,7 @@ template <int CIN>
 __global__ void __launch_bounds__(kT)
 stem_dgrad_kernel(const __nv_bfloat16* __restrict__ dy, const float* __restrict__ x, const float* __restrict__ w,
                   int in_mode, float inv_temp, int N, int H, int W, float* __restrict__ dx) {
+  pdl_entry();
   constexpr int COUT = 16;
   __shared__ __align__(16) float sw[9][COUT][CIN];          // [tap][co][ci]
   for (int i = threadIdx.x; i < COUT * CIN * 9; i += kT) {
@@ -709,10 +723,10 @@ extern "C" int ctl_bn_batch_affine_c8(const void* x, int64_t N, int64_t C, int64
   cudaStream_t st = (cudaStream_t)stream;
   const int64_t planes = N * (C / 8), HW = H * W;
   const int splits = plane_splits(planes, HW, reduce_ctas_per_sm<0>());
-  plane_reduce_kernel<0><<<dim3((unsigned)planes, (unsigned)splits), kT, 0, st>>>(
+  launch_chained(plane_reduce_kernel<0>, dim3((unsigned)planes, (unsigned)splits), kT, 0, st)(
       (const uint4*)x, nullptr, nullptr, nullptr, (double*)workspace, planes, HW, splits, 0, nullptr, nullptr, (int)(C / 8));
   CTL_CUDA_OK(cudaGetLastError(), "bn_partial_stats launch");
-  bn_fwd_finalize_kernel<<<(unsigned)ceil_div(C, 4), 128, 0, st>>>((const double*)workspace, planes, splits, (int)N, (int)C,
+  launch_chained(bn_fwd_finalize_kernel, (unsigned)ceil_div(C, 4), 128, 0, st)((const double*)workspace, planes, splits, (int)N, (int)C,
                                                                    (double)(N * HW), gamma, beta, eps, scale, shift,
                                                                    mean_out, var_out, running_mean, running_var, momentum);
   CTL_CUDA_OK(cudaGetLastError(), "bn_finalize launch");
@@ -726,7 +740,7 @@ extern "C" int ctl_bn_affine_from_sums(const double* sums, int64_t C, int64_t co
   CTL_REQUIRE((running_mean == nullptr) == (running_var == nullptr), CTL_ERR_INVALID,
               "running_mean and running_var must be given together");
   if (sm_count() < 0) return CTL_ERR_CUDA;
-  bn_fwd_from_sums_kernel<<<(unsigned)ceil_div(C, 128), 128, 0, (cudaStream_t)stream>>>(
+  launch_chained(bn_fwd_from_sums_kernel, (unsigned)ceil_div(C, 128), 128, 0, (cudaStream_t)stream)(
       sums, (int)C, (double)count, gamma, beta, eps, scale, shift, mean_out, var_out, running_mean, running_var, momentum);
   CTL_CUDA_OK(cudaGetLastError(), "bn_fwd_from_sums launch");
   return CTL_OK;
@@ -740,10 +754,10 @@ extern "C" int ctl_channel_sums_c8(const void* x, int64_t N, int64_t C, int64_t 
   cudaStream_t st = (cudaStream_t)stream;
   const int64_t planes = N * (C / 8), HW = H * W;
   const int splits = plane_splits(planes, HW, reduce_ctas_per_sm<0>());
-  plane_reduce_kernel<0><<<dim3((unsigned)planes, (unsigned)splits), kT, 0, st>>>(
+  launch_chained(plane_reduce_kernel<0>, dim3((unsigned)planes, (unsigned)splits), kT, 0, st)(
       (const uint4*)x, nullptr, nullptr, nullptr, (double*)workspace, planes, HW, splits, 0, nullptr, nullptr, (int)(C / 8));
   CTL_CUDA_OK(cudaGetLastError(), "plane_reduce launch");
-  channel_sum_finalize_kernel<<<(unsigned)ceil_div(C, 4), 128, 0, st>>>((const double*)workspace, planes, splits, (int)N,
+  launch_chained(channel_sum_finalize_kernel, (unsigned)ceil_div(C, 4), 128, 0, st)((const double*)workspace, planes, splits, (int)N,
                                                                         (int)C, sum_out, sumsq_out);
   CTL_CUDA_OK(cudaGetLastError(), "channel_sum_finalize launch");
   return CTL_OK;
@@ -763,11 +777,11 @@ extern "C" int ctl_bn_bwd_reduce_c8(const void* dy, const void* h, const void* a
   cudaStream_t st = (cudaStream_t)stream;
   const int64_t planes = N * (C / 8), HW = H * W;
   const int splits = plane_splits(planes, HW, reduce_ctas_per_sm<1>());
-  plane_reduce_kernel<1><<<dim3((unsigned)planes, (unsigned)splits), kT, 0, st>>>(
+  launch_chained(plane_reduce_kernel<1>, dim3((unsigned)planes, (unsigned)splits), kT, 0, st)(
       (const uint4*)dy, (const uint4*)h, (const uint4*)a, (uint4*)dv_out, (double*)workspace, planes, HW, splits, act,
       act_scale, act_shift, (int)(C / 8));
   CTL_CUDA_OK(cudaGetLastError(), "bn_bwd_reduce launch");
-  bn_bwd_finalize_kernel<<<(unsigned)ceil_div(C, 4), 128, 0, st>>>((const double*)workspace, planes, splits, (int)N, (int)C,
+  launch_chained(bn_bwd_finalize_kernel, (unsigned)ceil_div(C, 4), 128, 0, st)((const double*)workspace, planes, splits, (int)N, (int)C,
                                                                    (double)(N * HW), mean, var, eps, gamma, coef, dgamma,
                                                                    dbeta);
   CTL_CUDA_OK(cudaGetLastError(), "bn_bwd_finalize launch");
@@ -783,7 +797,7 @@ extern "C" int ctl_bn_bwd_apply_c8(const void* dy, const void* h, const void* a,
               "ctl_bn_bwd_apply_c8: give either h or (act_scale, act_shift)");
   if (sm_count() < 0) return CTL_ERR_CUDA;
   const int64_t total = N * (C / 8) * H * W;
-  bn_bwd_apply_kernel<<<grid_for(total), kT, 0, (cudaStream_t)stream>>>((const uint4*)dy, (const uint4*)h, (const uint4*)a,
+  launch_chained(bn_bwd_apply_kernel, grid_for(total), kT, 0, (cudaStream_t)stream)((const uint4*)dy, (const uint4*)h, (const uint4*)a,
                                                                       coef, (uint4*)da, total, (int)(C / 8), H * W, act,
                                                                       act_scale, act_shift);
   CTL_CUDA_OK(cudaGetLastError(), "bn_bwd_apply launch");
@@ -796,7 +810,7 @@ extern "C" int ctl_act_bwd_c8(const void* dy, const void* h, int64_t N, int64_t 
   CTL_REQUIRE(dv, CTL_ERR_INVALID, "ctl_act_bwd_c8: NULL pointer");
   if (sm_count() < 0) return CTL_ERR_CUDA;
   const int64_t total = N * (C / 8) * H * W;
-  act_bwd_kernel<<<grid_for(total), kT, 0, (cudaStream_t)stream>>>((const uint4*)dy, (const uint4*)h, (uint4*)dv, total, act);
+  launch_chained(act_bwd_kernel, grid_for(total), kT, 0, (cudaStream_t)stream)((const uint4*)dy, (const uint4*)h, (uint4*)dv, total, act);
   CTL_CUDA_OK(cudaGetLastError(), "act_bwd launch");
   return CTL_OK;
 }
@@ -805,7 +819,7 @@ extern "C" int ctl_downsample2x_sum_c8(const void* dy, int64_t N, int64_t C, int
   if (int rc = check_c8("ctl_downsample2x_sum_c8", dy, dx, N, C, H, W)) return rc;
   if (sm_count() < 0) return CTL_ERR_CUDA;
   const int64_t planes = N * (C / 8);
-  downsample2x_sum_kernel<<<grid_for(planes * H * W), kT, 0, (cudaStream_t)stream>>>((const uint4*)dy, (uint4*)dx, planes,
+  launch_chained(downsample2x_sum_kernel, grid_for(planes * H * W), kT, 0, (cudaStream_t)stream)((const uint4*)dy, (uint4*)dx, planes,
                                                                                    (int)H, (int)W);
   CTL_CUDA_OK(cudaGetLastError(), "downsample2x_sum launch");
   return CTL_OK;
@@ -815,7 +829,7 @@ extern "C" int ctl_zero_stuff2x_c8(const void* x, int64_t N, int64_t C, int64_t 
   if (int rc = check_c8("ctl_zero_stuff2x_c8", x, y, N, C, H, W)) return rc;
   if (sm_count() < 0) return CTL_ERR_CUDA;
   const int64_t planes = N * (C / 8);
-  zero_stuff2x_kernel<<<grid_for(planes * H * W), kT, 0, (cudaStream_t)stream>>>((const uint4*)x, (uint4*)y, planes, (int)H,
+  launch_chained(zero_stuff2x_kernel, grid_for(planes * H * W), kT, 0, (cudaStream_t)stream)((const uint4*)x, (uint4*)y, planes, (int)H,
                                                                                (int)W);
   CTL_CUDA_OK(cudaGetLastError(), "zero_stuff2x launch");
   return CTL_OK;
@@ -825,7 +839,7 @@ extern "C" int ctl_split_parity2x2_c8(const void* x, int64_t N, int64_t C, int64
   if (int rc = check_c8("ctl_split_parity2x2_c8", x, y, N, C, H, W)) return rc;
   if (sm_count() < 0) return CTL_ERR_CUDA;
   const int64_t planes = N * (C / 8);
-  split_parity2x2_kernel<<<grid_for(planes * H * W), kT, 0, (cudaStream_t)stream>>>((const uint4*)x, (uint4*)y, planes,
+  launch_chained(split_parity2x2_kernel, grid_for(planes * H * W), kT, 0, (cudaStream_t)stream)((const uint4*)x, (uint4*)y, planes,
                                                                                   (int)H, (int)W);
   CTL_CUDA_OK(cudaGetLastError(), "split_parity2x2 launch");
   return CTL_OK;
@@ -844,9 +858,9 @@ extern "C" int ctl_head_bwd_c8(const float* dy, const float* y, const void* x, i
   cudaStream_t st = (cudaStream_t)stream;
   const unsigned grid = (unsigned)std::min<int64_t>(ceil_div(N * H * W, kT), (int64_t)sm_count() * 4);
   if (Cout == 1)
-    head_bwd_kernel<1><<<grid, kT, 0, st>>>(dy, y, (const __nv_bfloat16*)x, weight, (__nv_bfloat16*)dx, dW, db, (int)N, H * W, act);
+    launch_chained(head_bwd_kernel<1>, grid, kT, 0, st)(dy, y, (const __nv_bfloat16*)x, weight, (__nv_bfloat16*)dx, dW, db, (int)N, H * W, act);
   else
-    head_bwd_kernel<4><<<grid, kT, 0, st>>>(dy, y, (const __nv_bfloat16*)x, weight, (__nv_bfloat16*)dx, dW, db, (int)N, H * W, act);
+    launch_chained(head_bwd_kernel<4>, grid, kT, 0, st)(dy, y, (const __nv_bfloat16*)x, weight, (__nv_bfloat16*)dx, dW, db, (int)N, H * W, act);
   CTL_CUDA_OK(cudaGetLastError(), "head_bwd launch");
   return CTL_OK;
 }
@@ -863,9 +877,9 @@ extern "C" int ctl_stem_input_c8(const float* x, const int64_t* labels, int in_m
   const unsigned grid = grid_for(N * H * W);
   const long long* lab = reinterpret_cast<const long long*>(labels);
   if (Cin == 1)
-    stem_input_c8_kernel<1><<<grid, kT, 0, st>>>(x, lab, in_mode, 1.0f / temperature, (int)N, (int)H, (int)W, (uint4*)out);
+    launch_chained(stem_input_c8_kernel<1>, grid, kT, 0, st)(x, lab, in_mode, 1.0f / temperature, (int)N, (int)H, (int)W, (uint4*)out);
   else
-    stem_input_c8_kernel<4><<<grid, kT, 0, st>>>(x, lab, in_mode, 1.0f / temperature, (int)N, (int)H, (int)W, (uint4*)out);
+    launch_chained(stem_input_c8_kernel<4>, grid, kT, 0, st)(x, lab, in_mode, 1.0f / temperature, (int)N, (int)H, (int)W, (uint4*)out);
   CTL_CUDA_OK(cudaGetLastError(), "stem_input launch");
   return CTL_OK;
 }
@@ -883,9 +897,9 @@ extern "C" int ctl_stem_wgrad_c8(const void* dy, const float* x, const int64_t* 
   const unsigned grid = (unsigned)std::min<int64_t>(tiles, (int64_t)sm_count() * 2);
   const long long* lab = reinterpret_cast<const long long*>(labels);
   if (Cin == 1)
-    stem_wgrad_kernel<1><<<grid, kT, 0, st>>>((const __nv_bfloat16*)dy, x, lab, in_mode, 1.0f / temperature, (int)N, (int)H, (int)W, dW);
+    launch_chained(stem_wgrad_kernel<1>, grid, kT, 0, st)((const __nv_bfloat16*)dy, x, lab, in_mode, 1.0f / temperature, (int)N, (int)H, (int)W, dW);
   else
-    stem_wgrad_kernel<4><<<grid, kT, 0, st>>>((const __nv_bfloat16*)dy, x, lab, in_mode, 1.0f / temperature, (int)N, (int)H, (int)W, dW);
+    launch_chained(stem_wgrad_kernel<4>, grid, kT, 0, st)((const __nv_bfloat16*)dy, x, lab, in_mode, 1.0f / temperature, (int)N, (int)H, (int)W, dW);
   CTL_CUDA_OK(cudaGetLastError(), "stem_wgrad launch");
   return CTL_OK;
 }
@@ -901,9 +915,9 @@ extern "C" int ctl_stem_dgrad_c8(const void* dy, const float* x, int in_mode, fl
   cudaStream_t st = (cudaStream_t)stream;
   const unsigned grid = grid_for(N * H * W);
   if (Cin == 1)
-    stem_dgrad_kernel<1><<<grid, kT, 0, st>>>((const __nv_bfloat16*)dy, x, weight, in_mode, 1.0f / temperature, (int)N, (int)H, (int)W, dx);
+    launch_chained(stem_dgrad_kernel<1>, grid, kT, 0, st)((const __nv_bfloat16*)dy, x, weight, in_mode, 1.0f / temperature, (int)N, (int)H, (int)W, dx);
   else
-    stem_dgrad_kernel<4><<<grid, kT, 0, st>>>((const __nv_bfloat16*)dy, x, weight, in_mode, 1.0f / temperature, (int)N, (int)H, (int)W, dx);
+    launch_chained(stem_dgrad_kernel<4>, grid, kT, 0, st)((const __nv_bfloat16*)dy, x, weight, in_mode, 1.0f / temperature, (int)N, (int)H, (int)W, dx);
   CTL_CUDA_OK(cudaGetLastError(), "stem_dgrad launch");
   return CTL_OK;
 }

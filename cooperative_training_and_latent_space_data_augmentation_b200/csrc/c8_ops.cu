@@ -49,6 +49,7 @@ template <> __device__ __forceinline__ float to_f<__nv_bfloat16>(__nv_bfloat16 v
 template <typename T>
 __global__ void __launch_bounds__(kT) nchw_to_c8_kernel(const T* __restrict__ x, __nv_bfloat16* __restrict__ y,
                                                          int64_t total /*N*C/8*HW*/, int C8, int64_t HW) {
+  pdl_entry();
   for (int64_t i = (int64_t)blockIdx.x * kT + threadIdx.x; i < total; i += (int64_t)gridDim.x * kT) {
     const int64_t pix = i % HW, nc = i / HW;             // nc = n*C8 + c8
     const T* src = x + nc * 8 * HW + pix;
@@ -61,6 +62,7 @@ __global__ void __launch_bounds__(kT) nchw_to_c8_kernel(const T* __restrict__ x,
 template <typename T>
 __global__ void __launch_bounds__(kT) c8_to_nchw_kernel(const __nv_bfloat16* __restrict__ x, T* __restrict__ y,
                                                          int64_t total, int C8, int64_t HW) {
+  pdl_entry();
   for (int64_t i = (int64_t)blockIdx.x * kT + threadIdx.x; i < total; i += (int64_t)gridDim.x * kT) {
     const int64_t pix = i % HW, nc = i / HW;
     float f[8];
@@ -82,6 +84,7 @@ __global__ void __launch_bounds__(kT)
 stem_conv_kernel(const float* __restrict__ x, const long long* __restrict__ labels, const float* __restrict__ w /*[COUT][CIN][3][3]*/,
                  const float* __restrict__ scale, const float* __restrict__ shift, __nv_bfloat16* __restrict__ y, int N,
                  int H, int W, int in_mode, float inv_temp, int act) {
+  pdl_entry();
   constexpr int TW = 32, TH = 8, HW_T = TW + 2, HH_T = TH + 2;
   __shared__ __align__(16) float sw[COUT * CIN * 9];
   __shared__ float ssc[COUT], ssh[COUT];
@@ -174,6 +177,7 @@ template <int CIN>
 __global__ void __launch_bounds__(kT)
 head_conv_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict__ w /*[COUT][CIN]*/, const float* __restrict__ b,
                  float* __restrict__ y, int N, int64_t HW, int COUT, int act) {
+  pdl_entry();
   __shared__ float sw[4 * CIN];
   __shared__ float sb[4];
   for (int i = threadIdx.x; i < COUT * CIN; i += kT) sw[i] = w[i];
@@ -202,6 +206,7 @@ head_conv_kernel(const __nv_bfloat16* __restrict__ x, const float* __restrict__ 
 // ------------------------------------------------------------------------------------------------ up2x
 __global__ void __launch_bounds__(kT)
 upsample2x_c8_kernel(const uint4* __restrict__ x, uint4* __restrict__ y, int64_t planes, int H, int W) {
+  pdl_entry();
   const int64_t total = planes * H * W;      // one thread per INPUT pixel: 16 B in, 4 x 16 B out
   for (int64_t i = (int64_t)blockIdx.x * kT + threadIdx.x; i < total; i += (int64_t)gridDim.x * kT) {
     const int64_t pl = i / ((int64_t)H * W);
@@ -217,6 +222,7 @@ upsample2x_c8_kernel(const uint4* __restrict__ x, uint4* __restrict__ y, int64_t
 __global__ void __launch_bounds__(kT)
 scale_shift_act_c8_kernel(const uint4* __restrict__ x, uint4* __restrict__ y, const float* __restrict__ scale,
                           const float* __restrict__ shift, int64_t total /*N*C8*HW*/, int C8, int64_t HW, int act) {
+  pdl_entry();
   for (int64_t i = (int64_t)blockIdx.x * kT + threadIdx.x; i < total; i += (int64_t)gridDim.x * kT) {
     const int c8 = (int)((i / HW) % C8);
     float f[8];
@@ -234,6 +240,7 @@ __global__ void __launch_bounds__(kT)
 scale_shift_upadd_act_c8_kernel(const uint4* __restrict__ x, const uint4* __restrict__ low, uint4* __restrict__ y,
                                 const float* __restrict__ scale, const float* __restrict__ shift, int64_t planes, int C8,
                                 int Hl, int Wl, int act) {
+  pdl_entry();
   const int64_t total = planes * Hl * Wl;
   for (int64_t i = (int64_t)blockIdx.x * kT + threadIdx.x; i < total; i += (int64_t)gridDim.x * kT) {
     const int64_t pl = i / ((int64_t)Hl * Wl);
@@ -270,6 +277,7 @@ scale_shift_upadd_act_c8_kernel(const uint4* __restrict__ x, const uint4* __rest
 __global__ void __launch_bounds__(kT)
 pack_conv_weight_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ out, int Cout, int Cin, int taps, int nt,
                         int transposed) {
+  pdl_entry();
   const int co_p = transposed ? Cin : Cout, ci_p = transposed ? Cout : Cin;     // packed-view channel counts
   const int total = co_p * ci_p * taps;
   for (int i = blockIdx.x * kT + threadIdx.x; i < total; i += gridDim.x * kT) {
@@ -289,6 +297,7 @@ pack_conv_weight_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__
 // {weight ptr, out ptr, Cout, Cin, taps, nt, transposed, 0}), blockIdx.x strides over the job's elements
 __global__ void __launch_bounds__(kT)
 pack_conv_weights_batched_kernel(const int64_t* __restrict__ jobs) {
+  pdl_entry();
   const int64_t* job = jobs + (int64_t)blockIdx.y * 8;
   const float* __restrict__ w = reinterpret_cast<const float*>(job[0]);
   __nv_bfloat16* __restrict__ out = reinterpret_cast<__nv_bfloat16*>(job[1]);
@@ -325,7 +334,7 @@ extern "C" int ctl_pack_conv_weight(const float* weight, int64_t Cout, int64_t C
   CTL_REQUIRE(nt > 0, CTL_ERR_UNSUPPORTED, "ctl_pack_conv_weight: no tcgen05 conv kernel for %d -> %d channels", ci_p, co_p);
   if (sm_count() < 0) return CTL_ERR_CUDA;
   const int64_t total = Cout * Cin * taps;
-  pack_conv_weight_kernel<<<grid_for(total), kT, 0, (cudaStream_t)stream>>>(weight, (__nv_bfloat16*)out, (int)Cout, (int)Cin,
+  launch_chained(pack_conv_weight_kernel, grid_for(total), kT, 0, (cudaStream_t)stream)(weight, (__nv_bfloat16*)out, (int)Cout, (int)Cin,
                                                                           taps, nt, transposed);
   CTL_CUDA_OK(cudaGetLastError(), "pack_conv_weight launch");
   return CTL_OK;
@@ -336,7 +345,7 @@ extern "C" int ctl_pack_conv_weights_batched(const int64_t* jobs, int64_t n_jobs
               "ctl_pack_conv_weights_batched: bad arguments");
   if (sm_count() < 0) return CTL_ERR_CUDA;
   const unsigned gx = (unsigned)std::min<int64_t>(ceil_div(max_elements, kT * 4), 64);
-  pack_conv_weights_batched_kernel<<<dim3(gx, (unsigned)n_jobs), kT, 0, (cudaStream_t)stream>>>(jobs);
+  launch_chained(pack_conv_weights_batched_kernel, dim3(gx, (unsigned)n_jobs), kT, 0, (cudaStream_t)stream)(jobs);
   CTL_CUDA_OK(cudaGetLastError(), "pack_conv_weights_batched launch");
   return CTL_OK;
 }
@@ -350,9 +359,9 @@ extern "C" int ctl_nchw_to_c8(const void* x, int x_dtype, int64_t N, int64_t C, 
   const int64_t HW = H * W, total = N * (C / 8) * HW;
   cudaStream_t st = (cudaStream_t)stream;
   if (x_dtype == CTL_F32)
-    nchw_to_c8_kernel<float><<<grid_for(total), kT, 0, st>>>((const float*)x, (__nv_bfloat16*)y, total, (int)(C / 8), HW);
+    launch_chained(nchw_to_c8_kernel<float>, grid_for(total), kT, 0, st)((const float*)x, (__nv_bfloat16*)y, total, (int)(C / 8), HW);
   else
-    nchw_to_c8_kernel<__nv_bfloat16><<<grid_for(total), kT, 0, st>>>((const __nv_bfloat16*)x, (__nv_bfloat16*)y, total,
+    launch_chained(nchw_to_c8_kernel<__nv_bfloat16>, grid_for(total), kT, 0, st)((const __nv_bfloat16*)x, (__nv_bfloat16*)y, total,
                                                                      (int)(C / 8), HW);
   CTL_CUDA_OK(cudaGetLastError(), "nchw_to_c8 launch");
   return CTL_OK;
@@ -367,9 +376,9 @@ extern "C" int ctl_c8_to_nchw(const void* x, int64_t N, int64_t C, int64_t H, in
   const int64_t HW = H * W, total = N * (C / 8) * HW;
   cudaStream_t st = (cudaStream_t)stream;
   if (y_dtype == CTL_F32)
-    c8_to_nchw_kernel<float><<<grid_for(total), kT, 0, st>>>((const __nv_bfloat16*)x, (float*)y, total, (int)(C / 8), HW);
+    launch_chained(c8_to_nchw_kernel<float>, grid_for(total), kT, 0, st)((const __nv_bfloat16*)x, (float*)y, total, (int)(C / 8), HW);
   else
-    c8_to_nchw_kernel<__nv_bfloat16><<<grid_for(total), kT, 0, st>>>((const __nv_bfloat16*)x, (__nv_bfloat16*)y, total,
+    launch_chained(c8_to_nchw_kernel<__nv_bfloat16>, grid_for(total), kT, 0, st)((const __nv_bfloat16*)x, (__nv_bfloat16*)y, total,
                                                                      (int)(C / 8), HW);
   CTL_CUDA_OK(cudaGetLastError(), "c8_to_nchw launch");
   return CTL_OK;
@@ -390,10 +399,10 @@ extern "C" int ctl_stem_conv3x3_c8(const float* x, const int64_t* labels, int in
   const unsigned grid = (unsigned)std::min<int64_t>(tiles, (int64_t)sm_count() * 4);
   const long long* lab = reinterpret_cast<const long long*>(labels);
   if (Cin == 1)
-    stem_conv_kernel<1, 16><<<grid, kT, 0, st>>>(x, lab, weight, scale, shift, (__nv_bfloat16*)y, (int)N, (int)H, (int)W,
+    launch_chained(stem_conv_kernel<1, 16>, grid, kT, 0, st)(x, lab, weight, scale, shift, (__nv_bfloat16*)y, (int)N, (int)H, (int)W,
                                                   in_mode, 1.0f / temperature, act);
   else
-    stem_conv_kernel<4, 16><<<grid, kT, 0, st>>>(x, lab, weight, scale, shift, (__nv_bfloat16*)y, (int)N, (int)H, (int)W,
+    launch_chained(stem_conv_kernel<4, 16>, grid, kT, 0, st)(x, lab, weight, scale, shift, (__nv_bfloat16*)y, (int)N, (int)H, (int)W,
                                                   in_mode, 1.0f / temperature, act);
   CTL_CUDA_OK(cudaGetLastError(), "stem_conv launch");
   return CTL_OK;
@@ -405,7 +414,7 @@ extern "C" int ctl_head_conv1x1_c8(const void* x, int64_t N, int64_t Cin, int64_
   CTL_REQUIRE(Cin == 16 && Cout >= 1 && Cout <= 4, CTL_ERR_UNSUPPORTED,
               "ctl_head_conv1x1_c8 handles Cin 16 -> Cout in [1,4] (got %lld -> %lld)", (long long)Cin, (long long)Cout);
   if (sm_count() < 0) return CTL_ERR_CUDA;
-  head_conv_kernel<16><<<grid_for(N * H * W), kT, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)x, weight, bias, y,
+  launch_chained(head_conv_kernel<16>, grid_for(N * H * W), kT, 0, (cudaStream_t)stream)((const __nv_bfloat16*)x, weight, bias, y,
                                                                            (int)N, H * W, (int)Cout, act);
   CTL_CUDA_OK(cudaGetLastError(), "head_conv launch");
   return CTL_OK;
@@ -415,7 +424,7 @@ extern "C" int ctl_upsample2x_c8(const void* x, int64_t N, int64_t C, int64_t H,
   CTL_REQUIRE(x && y && N > 0 && C > 0 && C % 8 == 0 && H > 0 && W > 0, CTL_ERR_INVALID, "ctl_upsample2x_c8: bad arguments");
   if (sm_count() < 0) return CTL_ERR_CUDA;
   const int64_t planes = N * (C / 8);
-  upsample2x_c8_kernel<<<grid_for(planes * H * W), kT, 0, (cudaStream_t)stream>>>((const uint4*)x, (uint4*)y, planes,
+  launch_chained(upsample2x_c8_kernel, grid_for(planes * H * W), kT, 0, (cudaStream_t)stream)((const uint4*)x, (uint4*)y, planes,
                                                                                 (int)H, (int)W);
   CTL_CUDA_OK(cudaGetLastError(), "upsample2x launch");
   return CTL_OK;
@@ -428,7 +437,7 @@ extern "C" int ctl_scale_shift_upadd_act_c8(const void* x, int64_t N, int64_t C,
   CTL_REQUIRE(act >= CTL_ACT_NONE && act <= CTL_ACT_SIGMOID, CTL_ERR_INVALID, "unknown activation %d", act);
   if (sm_count() < 0) return CTL_ERR_CUDA;
   const int64_t planes = N * (C / 8);
-  scale_shift_upadd_act_c8_kernel<<<grid_for(planes * (H / 2) * (W / 2)), kT, 0, (cudaStream_t)stream>>>(
+  launch_chained(scale_shift_upadd_act_c8_kernel, grid_for(planes * (H / 2) * (W / 2)), kT, 0, (cudaStream_t)stream)(
       (const uint4*)x, (const uint4*)low, (uint4*)y, scale, shift, planes, (int)(C / 8), (int)(H / 2), (int)(W / 2), act);
   CTL_CUDA_OK(cudaGetLastError(), "scale_shift_upadd_act launch");
   return CTL_OK;
@@ -440,7 +449,7 @@ extern "C" int ctl_scale_shift_act_c8(const void* x, int64_t N, int64_t C, int64
               "ctl_scale_shift_act_c8: bad arguments");
   if (sm_count() < 0) return CTL_ERR_CUDA;
   const int64_t total = N * (C / 8) * H * W;
-  scale_shift_act_c8_kernel<<<grid_for(total), kT, 0, (cudaStream_t)stream>>>((const uint4*)x, (uint4*)y, scale, shift,
+  launch_chained(scale_shift_act_c8_kernel, grid_for(total), kT, 0, (cudaStream_t)stream)((const uint4*)x, (uint4*)y, scale, shift,
                                                                             total, (int)(C / 8), H * W, act);
   CTL_CUDA_OK(cudaGetLastError(), "scale_shift_act launch");
   return CTL_OK;

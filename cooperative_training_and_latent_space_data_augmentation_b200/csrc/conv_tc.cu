@@ -342,6 +342,7 @@ __device__ __forceinline__ void conv_epilogue(const ConvParams& p, const uint32_
 template <int CIN, int NT, int TAPS, int MT, int STAGES>
 __global__ void __launch_bounds__(kConvThreads, 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap tmap, const ConvParams p) {
+  pdl_entry();
   using Cfg = ConvCfg<CIN, NT, TAPS, MT, STAGES>;
   extern __shared__ __align__(1024) uint8_t smem[];
   uint8_t* sW = smem + Cfg::kOffW;
@@ -524,7 +525,7 @@ int launch_conv(const void* x, const ConvParams& p0, cudaStream_t st) {
   const int n_tiles = p.Cout / NT;
   const int ctas = (int)std::min<int64_t>(p.num_tiles, std::max(1, sm_count() / n_tiles));
   dim3 grid((unsigned)ctas, (unsigned)n_tiles);
-  kern<<<grid, kConvThreads, Cfg::kSmemBytes, st>>>(tmap, p);
+  launch_chained(kern, grid, kConvThreads, Cfg::kSmemBytes, st)(tmap, p);
   CTL_CUDA_OK(cudaGetLastError(), "conv_tc launch");
   return CTL_OK;
 }

@@ -36,8 +36,50 @@ int diag_flags();                                 // env CTL_DIAG_SKIP; always 0
     }                                 \
   } while (0)
 
+// ---- chained launches (programmatic dependent launch) -----------------------------------------------------------------
+// The cooperative step is ~1900 short, strictly ordered kernels.  Every kernel of this library except the masking
+// chain (masking.cu has its own, finer-grained use of the mechanism) is launched with programmatic stream
+// serialization and begins with pdl_entry(): it lets the NEXT launch be set up while it runs, then waits until the
+// PREVIOUS grid has completed and its memory is visible.  No kernel touches global memory before that wait, so the
+// results are those of ordinary in-order launches; what disappears is the launch latency between dependent kernels
+// (also inside a captured CUDA graph, where the attribute becomes a programmatic dependency edge).  CTL_PDL_ALL=0
+// switches back to ordinary launches.
+bool pdl_chain_enabled();
+
+template <typename... KArgs>
+struct ChainedLaunch {
+  void (*kernel)(KArgs...);
+  dim3 grid, block;
+  size_t smem;
+  cudaStream_t stream;
+  template <typename... Args>
+  void operator()(Args&&... args) const {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = pdl_chain_enabled() ? 1 : 0;
+    (void)cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);   // the call sites check cudaGetLastError()
+  }
+};
+template <typename... KArgs>
+inline ChainedLaunch<KArgs...> launch_chained(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st) {
+  return ChainedLaunch<KArgs...>{kernel, grid, block, smem, st};
+}
+
 static inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
 static inline int64_t ceil_div(int64_t a, int64_t b) { return (a + b - 1) / b; }
+
+// first statement of every chained kernel (see launch_chained)
+__device__ __forceinline__ void pdl_entry() {
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+}
 
 // ---- device side: 16-byte streaming access -----------------------------------------------------
 template <typename T>

@@ -36,6 +36,11 @@ int sm_count() {
   return sms;
 }
 
+bool pdl_chain_enabled() {
+  static const bool on = [] { const char* e = getenv("CTL_PDL_ALL"); return !(e && e[0] == '0'); }();
+  return on;
+}
+
 // Profiling by elimination (tools/diag_conv.py): stages of the tcgen05 kernels can be switched off to see which one
 // bounds the pipeline.  Results are garbage with any bit set; never set outside the diagnostic tool.  Compiled in only with -DCTL_DIAG
 // (make DIAG=1); the default build ignores the variable and the kernels carry no skip branches.

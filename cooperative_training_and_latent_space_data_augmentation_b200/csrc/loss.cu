@@ -35,6 +35,7 @@ template <int C, int VEC>
 __global__ void __launch_bounds__(kT)
 ce2d_fwd_kernel(const float* __restrict__ logits, const int64_t* __restrict__ labels, int64_t groups_per_img, int64_t HW,
                 int64_t total_groups, double scale, unsigned long long* __restrict__ ws, float* __restrict__ out) {
+  pdl_entry();
   float acc = 0.0f;
   for (int64_t g = (int64_t)blockIdx.x * kT + threadIdx.x; g < total_groups; g += (int64_t)gridDim.x * kT) {
     const int64_t n = g / groups_per_img;
@@ -92,6 +93,7 @@ template <int C, int VEC>
 __global__ void __launch_bounds__(kT)
 ce2d_bwd_kernel(const float* __restrict__ logits, const int64_t* __restrict__ labels, const float* __restrict__ gout,
                 float scale, int64_t groups_per_img, int64_t HW, int64_t total_groups, float* __restrict__ dlogits) {
+  pdl_entry();
   const float gs = (gout ? __ldg(gout) : 1.0f) * scale;
   for (int64_t g = (int64_t)blockIdx.x * kT + threadIdx.x; g < total_groups; g += (int64_t)gridDim.x * kT) {
     const int64_t n = g / groups_per_img;
@@ -131,9 +133,9 @@ int launch_ce(bool backward, const float* logits, const int64_t* labels, int64_t
   if (sms < 0) return CTL_ERR_CUDA;
   const int grid = (int)std::max<int64_t>(1, std::min<int64_t>(ceil_div(total, kT), (int64_t)sms * 8));
   if (!backward) {
-    ce2d_fwd_kernel<C, VEC><<<grid, kT, 0, st>>>(logits, labels, groups_per_img, HW, total, scale, ws, out);
+    launch_chained(ce2d_fwd_kernel<C, VEC>, grid, kT, 0, st)(logits, labels, groups_per_img, HW, total, scale, ws, out);
   } else {
-    ce2d_bwd_kernel<C, VEC><<<grid, kT, 0, st>>>(logits, labels, gout, (float)scale, groups_per_img, HW, total, dlogits);
+    launch_chained(ce2d_bwd_kernel<C, VEC>, grid, kT, 0, st)(logits, labels, gout, (float)scale, groups_per_img, HW, total, dlogits);
   }
   CTL_CUDA_OK(cudaGetLastError(), "ce2d launch");
   return CTL_OK;

@@ -32,6 +32,7 @@ struct AdamSegs {
 };
 
 __global__ void adam_bump_kernel(float* __restrict__ steps, int count, unsigned mask) {
+  pdl_entry();
   const int s = threadIdx.x;
   if (s < count && ((mask >> s) & 1u)) steps[s] += 1.0f;
 }
@@ -43,6 +44,7 @@ __global__ void __launch_bounds__(kT)
 adam_flat_kernel(float* __restrict__ p, float* __restrict__ g, float* __restrict__ m, float* __restrict__ v,
                  const AdamSegs segs, const float* __restrict__ steps, double lr, double b1d, double b2d, float eps, float wd,
                  float grad_scale, int zero_grad) {
+  pdl_entry();
   __shared__ float s_step_size[kMaxSeg], s_bc2_rsqrt[kMaxSeg];
   if ((int)threadIdx.x < segs.count) {
     const double t = (double)steps[threadIdx.x];
@@ -90,6 +92,7 @@ template <int VEC>
 __global__ void __launch_bounds__(kT)
 sse_fwd_kernel(const float* __restrict__ pred, const float* __restrict__ target, long long n, double scale,
                unsigned long long* __restrict__ ws, float* __restrict__ out) {
+  pdl_entry();
   float acc = 0.0f;
   const long long groups = n / VEC;
   for (long long i = (long long)blockIdx.x * kT + threadIdx.x; i < groups; i += (long long)gridDim.x * kT) {
@@ -127,6 +130,7 @@ template <int VEC>
 __global__ void __launch_bounds__(kT)
 sse_bwd_kernel(const float* __restrict__ pred, const float* __restrict__ target, const float* __restrict__ gout,
                float scale2, long long n, float* __restrict__ dpred) {
+  pdl_entry();
   const float gs = (gout ? __ldg(gout) : 1.0f) * scale2;
   const long long groups = n / VEC;
   for (long long i = (long long)blockIdx.x * kT + threadIdx.x; i < groups; i += (long long)gridDim.x * kT) {
@@ -147,6 +151,7 @@ __global__ void __launch_bounds__(kT)
 confusion_kernel(const float* __restrict__ logits, const int64_t* __restrict__ pred_labels,
                  const int64_t* __restrict__ gt, long long N, long long HW, unsigned long long* __restrict__ hist,
                  uint8_t* __restrict__ labels_out) {
+  pdl_entry();
   __shared__ unsigned int cell[C * C];
   for (int i = threadIdx.x; i < C * C; i += kT) cell[i] = 0u;
   __syncthreads();
@@ -180,6 +185,7 @@ confusion_kernel(const float* __restrict__ logits, const int64_t* __restrict__ p
 
 // out: [0] overall acc, [1] mean acc (nanmean), [2] freq-weighted acc, [3] mean IoU (nanmean), [4 + c] IoU of class c
 __global__ void confusion_scores_kernel(const unsigned long long* __restrict__ hist, int C, double* __restrict__ out) {
+  pdl_entry();
   if (threadIdx.x != 0 || blockIdx.x != 0) return;
   const double nan = __longlong_as_double(0x7ff8000000000000LL);
   double total = 0.0, diag = 0.0;
@@ -251,8 +257,8 @@ extern "C" int ctl_adam_flat(float* params, float* grads, float* exp_avg, float*
   const int grid = stream_grid(segs.end[n_segments - 1] / 4);
   if (grid < 0) return CTL_ERR_CUDA;
   cudaStream_t st = (cudaStream_t)stream;
-  adam_bump_kernel<<<1, 32, 0, st>>>(steps, n_segments, seg_mask);
-  adam_flat_kernel<<<grid, kT, 0, st>>>(params, grads, exp_avg, exp_avg_sq, segs, steps, lr, beta1, beta2, (float)eps,
+  launch_chained(adam_bump_kernel, 1, 32, 0, st)(steps, n_segments, seg_mask);
+  launch_chained(adam_flat_kernel, grid, kT, 0, st)(params, grads, exp_avg, exp_avg_sq, segs, steps, lr, beta1, beta2, (float)eps,
                                         (float)weight_decay, (float)grad_scale, zero_grad);
   CTL_CUDA_OK(cudaGetLastError(), "adam_flat launch");
   return CTL_OK;
@@ -265,9 +271,9 @@ extern "C" int ctl_sse_fwd(const float* pred, const float* target, int64_t n, do
   if (grid < 0) return CTL_ERR_CUDA;
   cudaStream_t st = (cudaStream_t)stream;
   if (n % 4 == 0 && aligned16(pred) && aligned16(target))
-    sse_fwd_kernel<4><<<grid, kT, 0, st>>>(pred, target, n, scale, (unsigned long long*)workspace16, loss_out);
+    launch_chained(sse_fwd_kernel<4>, grid, kT, 0, st)(pred, target, n, scale, (unsigned long long*)workspace16, loss_out);
   else
-    sse_fwd_kernel<1><<<grid, kT, 0, st>>>(pred, target, n, scale, (unsigned long long*)workspace16, loss_out);
+    launch_chained(sse_fwd_kernel<1>, grid, kT, 0, st)(pred, target, n, scale, (unsigned long long*)workspace16, loss_out);
   CTL_CUDA_OK(cudaGetLastError(), "sse_fwd launch");
   return CTL_OK;
 }
@@ -280,9 +286,9 @@ extern "C" int ctl_sse_bwd(const float* pred, const float* target, int64_t n, do
   cudaStream_t st = (cudaStream_t)stream;
   const float s2 = (float)(2.0 * scale);
   if (n % 4 == 0 && aligned16(pred) && aligned16(target) && aligned16(dpred))
-    sse_bwd_kernel<4><<<grid, kT, 0, st>>>(pred, target, grad_out, s2, n, dpred);
+    launch_chained(sse_bwd_kernel<4>, grid, kT, 0, st)(pred, target, grad_out, s2, n, dpred);
   else
-    sse_bwd_kernel<1><<<grid, kT, 0, st>>>(pred, target, grad_out, s2, n, dpred);
+    launch_chained(sse_bwd_kernel<1>, grid, kT, 0, st)(pred, target, grad_out, s2, n, dpred);
   CTL_CUDA_OK(cudaGetLastError(), "sse_bwd launch");
   return CTL_OK;
 }
@@ -300,10 +306,10 @@ extern "C" int ctl_confusion_update(const float* logits, const int64_t* pred_lab
   unsigned long long* h = (unsigned long long*)hist;
   uint8_t* lo = (uint8_t*)labels_out;
   switch ((int)C) {
-    case 2: confusion_kernel<2><<<grid, kT, 0, st>>>(logits, pred_labels, gt, N, HW, h, lo); break;
-    case 3: confusion_kernel<3><<<grid, kT, 0, st>>>(logits, pred_labels, gt, N, HW, h, lo); break;
-    case 4: confusion_kernel<4><<<grid, kT, 0, st>>>(logits, pred_labels, gt, N, HW, h, lo); break;
-    case 8: confusion_kernel<8><<<grid, kT, 0, st>>>(logits, pred_labels, gt, N, HW, h, lo); break;
+    case 2: launch_chained(confusion_kernel<2>, grid, kT, 0, st)(logits, pred_labels, gt, N, HW, h, lo); break;
+    case 3: launch_chained(confusion_kernel<3>, grid, kT, 0, st)(logits, pred_labels, gt, N, HW, h, lo); break;
+    case 4: launch_chained(confusion_kernel<4>, grid, kT, 0, st)(logits, pred_labels, gt, N, HW, h, lo); break;
+    case 8: launch_chained(confusion_kernel<8>, grid, kT, 0, st)(logits, pred_labels, gt, N, HW, h, lo); break;
     default:
       set_error("ctl_confusion_update: number of classes must be 2, 3, 4 or 8 (got %lld)", (long long)C);
       return CTL_ERR_UNSUPPORTED;
@@ -315,7 +321,7 @@ extern "C" int ctl_confusion_update(const float* logits, const int64_t* pred_lab
 extern "C" int ctl_confusion_scores(const void* hist, int64_t C, double* scores_out, void* stream) {
   CTL_REQUIRE(hist && scores_out && C >= 1 && C <= 64, CTL_ERR_INVALID, "ctl_confusion_scores: NULL pointer or bad C");
   if (sm_count() < 0) return CTL_ERR_CUDA;
-  confusion_scores_kernel<<<1, 32, 0, (cudaStream_t)stream>>>((const unsigned long long*)hist, (int)C, scores_out);
+  launch_chained(confusion_scores_kernel, 1, 32, 0, (cudaStream_t)stream)((const unsigned long long*)hist, (int)C, scores_out);
   CTL_CUDA_OK(cudaGetLastError(), "confusion_scores launch");
   return CTL_OK;
 }

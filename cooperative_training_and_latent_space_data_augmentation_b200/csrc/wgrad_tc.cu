@@ -99,6 +99,7 @@ template <int CIN, int NT, int TAPS, int STAGES>
 __global__ void __launch_bounds__(kWgThreads, 1)
 wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ CUtensorMap tmap_dy,
                 const WgradParams p) {
+  pdl_entry();
   using Cfg = WgCfg<CIN, NT, TAPS, STAGES>;
   extern __shared__ __align__(1024) uint8_t smem[];
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Cfg::kOffBar);
@@ -348,7 +349,7 @@ int launch_wgrad(const void* x, const void* dy, const WgradParams& p0, cudaStrea
   int64_t ctas = std::min<int64_t>(ceil_div(p.num_tiles, min_tiles), std::max(1, sm_count() / n_tiles));
   ctas = std::max<int64_t>(1, std::min<int64_t>(ctas, p.num_tiles));
   dim3 grid((unsigned)ctas, (unsigned)n_tiles);
-  kern<<<grid, kWgThreads, Cfg::kSmemBytes, st>>>(tx, td, p);
+  launch_chained(kern, grid, kWgThreads, Cfg::kSmemBytes, st)(tx, td, p);
   CTL_CUDA_OK(cudaGetLastError(), "wgrad_tc launch");
   return CTL_OK;
 }
