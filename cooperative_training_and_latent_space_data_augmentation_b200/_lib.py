@@ -34,7 +34,8 @@ SIGNATURES = {
     "ctl_channel_dropout_dyn": (_i, [_vp, _i, _i64, _i64, _i64, _f, _f, _u64, _vp, _vp, _i, _vp, _vp, _vp]),
     "ctl_philox_uniform": (_i, [_u64, _u64, _u64, _i64, _vp, _vp]),
     "ctl_conv2d_n_tile": (_i, [_i, _i, _i]),
-    "ctl_pack_conv_weight": (_i, [_vp, _i64, _i64, _i, _i, _vp, _vp]),
+    "ctl_conv2d_vpacked": (_i, [_i, _i, _i, _i]),
+    "ctl_pack_conv_weight": (_i, [_vp, _i64, _i64, _i, _i, _i, _vp, _vp]),
     "ctl_pack_conv_weights_batched": (_i, [_vp, _i64, _i64, _vp]),
     "ctl_conv2d_c8_bf16": (_i, [_vp, _i64, _i64, _i64, _i64, _vp, _i64, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _i, _vp,
                                 _vp, _vp]),

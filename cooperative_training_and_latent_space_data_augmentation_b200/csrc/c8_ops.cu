@@ -274,27 +274,44 @@ scale_shift_upadd_act_c8_kernel(const uint4* __restrict__ x, const uint4* __rest
 // fp32 nn.Conv2d weight [Cout][Cin][k][k] -> bf16 [Cout'/NT][taps][Cin'/8][NT][8] (the K-major core-matrix order of
 // conv_tc.cu).  transposed == 0: the forward weight (Cout' = Cout, Cin' = Cin).  transposed == 1: the weight of the
 // INPUT-gradient convolution, w'[ci][co][r][s] = w[co][ci][k-1-r][k-1-s] (Cout' = Cin, Cin' = Cout).
+// Element i of the packed weight -> (packed-view out channel o, in channel c, tap).  tap_major (1x1 filters and the
+// 3x3 stride-2 kernel): [n_tile][tap][Cin'/8][NT][8].  Otherwise the vertically packed 3x3 layout of conv_tc.cu:
+// [n_tile][s][Cin'/8][3*NT][8] with row n' = r*NT + n of the N dimension (tap = 3*r + s).
+__device__ __forceinline__ void packed_index(int i, int ci_p, int taps, int nt, bool tap_major, int& o, int& c, int& tap) {
+  int r = i;
+  const int j = r & 7; r >>= 3;
+  if (tap_major || taps != 9) {
+    const int n = r % nt; r /= nt;
+    const int q = r % (ci_p >> 3); r /= (ci_p >> 3);
+    tap = r % taps;
+    o = (r / taps) * nt + n;
+    c = q * 8 + j;
+  } else {
+    const int np = r % (3 * nt); r /= (3 * nt);
+    const int q = r % (ci_p >> 3); r /= (ci_p >> 3);
+    const int sx = r % 3;
+    tap = (np / nt) * 3 + sx;
+    o = (r / 3) * nt + np % nt;
+    c = q * 8 + j;
+  }
+}
+
 __global__ void __launch_bounds__(kT)
 pack_conv_weight_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ out, int Cout, int Cin, int taps, int nt,
-                        int transposed) {
+                        int transposed, int tap_major) {
   pdl_entry();
   const int co_p = transposed ? Cin : Cout, ci_p = transposed ? Cout : Cin;     // packed-view channel counts
   const int total = co_p * ci_p * taps;
   for (int i = blockIdx.x * kT + threadIdx.x; i < total; i += gridDim.x * kT) {
-    int r = i;
-    const int j = r & 7; r >>= 3;
-    const int n = r % nt; r /= nt;
-    const int q = r % (ci_p >> 3); r /= (ci_p >> 3);
-    const int tap = r % taps;
-    const int t = r / taps;
-    const int o = t * nt + n, c = q * 8 + j;                                    // packed-view (out, in) channel
+    int o, c, tap;
+    packed_index(i, ci_p, taps, nt, tap_major != 0, o, c, tap);
     const float v = transposed ? w[((int64_t)c * Cin + o) * taps + (taps - 1 - tap)] : w[((int64_t)o * Cin + c) * taps + tap];
     out[i] = __float2bfloat16_rn(v);
   }
 }
 
 // every packing job of a step in ONE launch: blockIdx.y = job (table in device memory, int64 [n][8] =
-// {weight ptr, out ptr, Cout, Cin, taps, nt, transposed, 0}), blockIdx.x strides over the job's elements
+// {weight ptr, out ptr, Cout, Cin, taps, nt, transposed, tap_major}), blockIdx.x strides over the job's elements
 __global__ void __launch_bounds__(kT)
 pack_conv_weights_batched_kernel(const int64_t* __restrict__ jobs) {
   pdl_entry();
@@ -302,16 +319,12 @@ pack_conv_weights_batched_kernel(const int64_t* __restrict__ jobs) {
   const float* __restrict__ w = reinterpret_cast<const float*>(job[0]);
   __nv_bfloat16* __restrict__ out = reinterpret_cast<__nv_bfloat16*>(job[1]);
   const int Cout = (int)job[2], Cin = (int)job[3], taps = (int)job[4], nt = (int)job[5], transposed = (int)job[6];
+  const bool tap_major = job[7] != 0;
   const int co_p = transposed ? Cin : Cout, ci_p = transposed ? Cout : Cin;
   const int total = co_p * ci_p * taps;
   for (int i = blockIdx.x * kT + threadIdx.x; i < total; i += gridDim.x * kT) {
-    int r = i;
-    const int j = r & 7; r >>= 3;
-    const int n = r % nt; r /= nt;
-    const int q = r % (ci_p >> 3); r /= (ci_p >> 3);
-    const int tap = r % taps;
-    const int t = r / taps;
-    const int o = t * nt + n, c = q * 8 + j;
+    int o, c, tap;
+    packed_index(i, ci_p, taps, nt, tap_major, o, c, tap);
     const float v = transposed ? w[((int64_t)c * Cin + o) * taps + (taps - 1 - tap)] : w[((int64_t)o * Cin + c) * taps + tap];
     out[i] = __float2bfloat16_rn(v);
   }
@@ -326,8 +339,8 @@ inline unsigned grid_for(int64_t total) {
 
 using namespace ctl;
 
-extern "C" int ctl_pack_conv_weight(const float* weight, int64_t Cout, int64_t Cin, int taps, int transposed, void* out,
-                                    void* stream) {
+extern "C" int ctl_pack_conv_weight(const float* weight, int64_t Cout, int64_t Cin, int taps, int transposed, int tap_major,
+                                    void* out, void* stream) {
   CTL_REQUIRE(weight && out && (taps == 1 || taps == 9), CTL_ERR_INVALID, "ctl_pack_conv_weight: bad arguments");
   const int co_p = (int)(transposed ? Cin : Cout), ci_p = (int)(transposed ? Cout : Cin);
   const int nt = ctl_conv2d_n_tile(ci_p, co_p, taps);
@@ -335,7 +348,7 @@ extern "C" int ctl_pack_conv_weight(const float* weight, int64_t Cout, int64_t C
   if (sm_count() < 0) return CTL_ERR_CUDA;
   const int64_t total = Cout * Cin * taps;
   launch_chained(pack_conv_weight_kernel, grid_for(total), kT, 0, (cudaStream_t)stream)(weight, (__nv_bfloat16*)out, (int)Cout, (int)Cin,
-                                                                          taps, nt, transposed);
+                                                                          taps, nt, transposed, tap_major);
   CTL_CUDA_OK(cudaGetLastError(), "pack_conv_weight launch");
   return CTL_OK;
 }

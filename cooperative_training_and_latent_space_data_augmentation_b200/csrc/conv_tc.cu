@@ -26,6 +26,16 @@
 //             tcgen05.ld 16 columns, residual requested before the TMEM wait, y = act(acc*scale + shift + res*rs + rb),
 //             bf16 pack, 16-byte stores (optionally scattered 2x2 for ConvTranspose2d k2 s2), optional per-channel
 //             sum / sum-of-squares of the stored values (train-mode BatchNorm statistics without a second pass).
+//
+// VP (vertically packed 3x3, stride 1): with N = Cout <= 64 every tcgen05.mma re-reads a 4 KB pixel tile from shared
+// memory for little math, so the tensor pipe idles behind operand fetch (measured ~52 issue cycles per N = 16 MMA for
+// 8 cycles of math).  The three VERTICAL taps of a filter column s are therefore packed into the N dimension:
+//   B_s = (W[0][s] | W[1][s] | W[2][s])  ->  N = 3*NT, three MMAs per 16-channel K slice instead of nine,
+//   D[(row, px), (r, co)] = sum_ci X[y0-1+row][x0+px+s-1][ci] * W[r][s][co][ci]   (accumulated over s and ci)
+// and the epilogue finishes the sum across rows: out[j][px][co] = D[j][0,co] + D[j+1][1,co] + D[j+2][2,co].  A tile is
+// 16 INPUT rows (= the M rows of the MMA, no vertical halo) and produces 14 output rows; every feature-map height of
+// the 224^2 configuration (224, 112, 56, 28, 14) is a multiple of 14.  Rows meet through a small shared-memory exchange
+// between the four epilogue warps that share an item.
 #include <algorithm>
 
 #include "ctl_common.cuh"
@@ -62,29 +72,35 @@ struct ConvParams {
   int diag;                           // profiling only (env CTL_DIAG_SKIP): 1 no MMA, 2 no TMA loads, 4 no epilogue memory traffic, 8 no epilogue
 };
 
-template <int CIN, int NT, int TAPS, int MT, int STAGES>
+template <int CIN, int NT, int TAPS, int MT, int STAGES, bool VP = false>
 struct ConvCfg {
+  static_assert(!VP || TAPS == 9, "vertical tap packing is for 3x3 filters");
   static constexpr int kPad = TAPS == 9 ? 1 : 0;
-  static constexpr int kHaloH = kTileH + 2 * kPad;
+  static constexpr int kOutH = VP ? 14 : kTileH;                  // output rows per tile
+  static constexpr int kHaloH = VP ? kTileH : kTileH + 2 * kPad;  // VP: the 16 M rows ARE the input rows y0-1 .. y0+14
   static constexpr int kHaloW = 8 * MT + 2 * kPad;
   static constexpr int kChunkBytes = kHaloH * kHaloW * 16;        // one 8-channel plane of the halo tile
   static constexpr int kChunkStride = kChunkBytes;                // the TMA box is written densely
   static constexpr int kStageBytes = (CIN / 8) * kChunkStride;
   static constexpr int kStageTxBytes = kStageBytes;               // bytes the TMA load of one stage delivers
   static constexpr int kWBytes = TAPS * CIN * NT * 2;
+  static constexpr int kAccCols = VP ? 3 * NT : NT;               // TMEM columns of one M tile's accumulator
   // accumulator stages: the MMA issuer (and with it the TMA ring) runs up to kAcc tiles ahead of the epilogue
-  static constexpr int kAcc = (512 / (MT * NT)) >= 4 ? 4 : 2;
-  static constexpr int kTmemCols = kAcc * MT * NT;
+  static constexpr int kAcc = (512 / (MT * kAccCols)) >= 4 ? 4 : 2;
+  static constexpr int kTmemCols = kAcc * MT * kAccCols;
   static constexpr int kTmemAlloc = kTmemCols <= 32 ? 32 : kTmemCols <= 64 ? 64 : kTmemCols <= 128 ? 128
                                     : kTmemCols <= 256 ? 256 : 512;
+  // VP: per epilogue half, the (r = 1 | r = 2) partial sums of one item: [2][4 float4][128 pixels] fp32 = 16 KB
+  static constexpr int kXBytes = VP ? 2 * 2 * 4 * 128 * 16 : 0;
   // smem carve-up (all offsets multiples of 128)
   static constexpr int kOffW = 0;
   static constexpr int kOffA = (kWBytes + 127) / 128 * 128;
-  static constexpr int kOffVec = kOffA + STAGES * ((kStageBytes + 127) / 128 * 128);   // 4 x NT floats
+  static constexpr int kOffX = kOffA + STAGES * ((kStageBytes + 127) / 128 * 128);
+  static constexpr int kOffVec = kOffX + kXBytes;                                       // 4 x NT floats
   static constexpr int kOffBar = kOffVec + 4 * NT * 4;
   static constexpr int kSmemBytes = kOffBar + 256;
   static_assert(kTmemCols <= 512, "accumulators exceed TMEM");
-  static_assert(CIN % 16 == 0 && NT % 16 == 0 && NT <= 256, "UMMA shape");
+  static_assert(CIN % 16 == 0 && NT % 16 == 0 && kAccCols <= 256, "UMMA shape");
   static_assert(kSmemBytes <= 227 * 1024, "shared memory budget");
   static_assert((kChunkStride >> 4) < 16384 && kHaloW * 16 < 16384 * 16, "descriptor range");
   static_assert(kHaloW * 2 <= 256 && kHaloH <= 256 && CIN / 8 <= 256, "TMA box dimensions (8-byte elements)");
@@ -95,10 +111,12 @@ struct ConvCfg {
 // as a batch: every residual pixel of the tile is requested BEFORE the accumulator wait (the addresses do not depend on
 // it), the TMEM loads of two items are issued back to back behind one tcgen05.wait::ld, and the accumulator stage is
 // handed back to the MMA issuer as soon as the last load has landed in registers -- before the arithmetic and stores.
-template <int CIN, int NT, int TAPS, int MT, int STAGES, bool RES, bool STATS, bool GEN, bool SAL = false>
+template <int CIN, int NT, int TAPS, int MT, int STAGES, bool VP, bool RES, bool STATS, bool GEN, bool SAL = false>
 __device__ __forceinline__ void conv_epilogue(const ConvParams& p, const uint32_t tmem_base, const float* sVec,
-                                              uint64_t* acc_full, uint64_t* acc_empty, const int n0, float* stat_smem) {
-  using Cfg = ConvCfg<CIN, NT, TAPS, MT, STAGES>;
+                                              uint64_t* acc_full, uint64_t* acc_empty, const int n0, float* stat_smem,
+                                              float4* xbuf) {
+  using Cfg = ConvCfg<CIN, NT, TAPS, MT, STAGES, VP>;
+  static_assert(!(VP && GEN), "the generic-geometry epilogue (stride 2 / ConvTranspose) runs on unpacked taps");
   constexpr int kAccStages = Cfg::kAcc;
   constexpr int kChunks = NT / 16;
   constexpr int kItems = MT * kChunks;
@@ -128,10 +146,10 @@ __device__ __forceinline__ void conv_epilogue(const ConvParams& p, const uint32_
     g.img = t / tiles_per_img;
     const int rem = t - g.img * tiles_per_img;
     const int ty = rem / p.tiles_x, tx = rem - ty * p.tiles_x;
-    g.y = ty * kTileH + py;
+    g.y = ty * Cfg::kOutH + py;
     g.xb = tx * (8 * MT) + px;
     // plain geometry (stride 1, no ConvTranspose scatter): one 64-bit base per tile, items differ by constants
-    g.y_ok = g.y < p.H && !CTL_DIAGF(p, 4);
+    g.y_ok = py < Cfg::kOutH && g.y < p.H && !CTL_DIAGF(p, 4);
     g.pix = ((int64_t)g.img * (p.Cout >> 3) + (n0 >> 3)) * plane + ((int64_t)g.y * p.W + g.xb) * 8;
     return g;
   };
@@ -187,19 +205,66 @@ __device__ __forceinline__ void conv_epilogue(const ConvParams& p, const uint32_
 #pragma unroll
     for (int u0 = 0; u0 < kPer; u0 += 2) {
       uint32_t v[2][16];
+      if constexpr (!VP) {
 #pragma unroll
-      for (int b = 0; b < 2; ++b) {
-        const int item = first_item + 2 * (u0 + b);                       // warp-uniform
-        if (u0 + b < kPer && item < kItems) {
-          const int mt = item / kChunks, c0 = (item - mt * kChunks) * 16;
-          tmem_ld_32x32b_x16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)((acc * MT + mt) * NT + c0), v[b]);
+        for (int b = 0; b < 2; ++b) {
+          const int item = first_item + 2 * (u0 + b);                       // warp-uniform
+          if (u0 + b < kPer && item < kItems) {
+            const int mt = item / kChunks, c0 = (item - mt * kChunks) * 16;
+            tmem_ld_32x32b_x16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)((acc * MT + mt) * NT + c0), v[b]);
+          }
         }
-      }
-      tmem_ld_wait();
-      if (u0 + 2 >= kPer) {            // the tile's accumulator is in registers: release the TMEM stage now
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&acc_empty[acc]);
+        tmem_ld_wait();
+        if (u0 + 2 >= kPer) {            // the tile's accumulator is in registers: release the TMEM stage now
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&acc_empty[acc]);
+        }
+      } else {
+        // vertically packed taps: three column groups per item; this thread's D row (py) holds the r = 0 term of
+        // output row py, the r = 1 term of output row py - 1 and the r = 2 term of output row py - 2.  The r = 1 / 2
+        // groups go through a shared-memory exchange between the four warps (TMEM sub-partitions) of this half.
+        float4* xh = xbuf + half * (2 * 4 * 128);
+#pragma unroll
+        for (int b = 0; b < 2; ++b) {
+          const int item = first_item + 2 * (u0 + b);                       // warp-uniform
+          if (u0 + b < kPer && item < kItems) {
+            const int mt = item / kChunks, c0 = (item - mt * kChunks) * 16;
+            const uint32_t col = (uint32_t)((acc * MT + mt) * Cfg::kAccCols + c0);
+            const uint32_t tl = tmem_base + ((uint32_t)(q * 32) << 16) + col;
+            uint32_t v1[16], v2[16];
+            tmem_ld_32x32b_x16(tl, v[b]);
+            tmem_ld_32x32b_x16(tl + NT, v1);
+            tmem_ld_32x32b_x16(tl + 2 * NT, v2);
+            tmem_ld_wait();
+            const bool last_item = (u0 + b + 1 >= kPer) || (first_item + 2 * (u0 + b + 1) >= kItems);
+            if (last_item) {             // everything of this tile's accumulator this warp needs is in registers
+              tc_fence_before();
+              __syncwarp();
+              if (lane == 0) mbar_arrive(&acc_empty[acc]);
+            }
+#pragma unroll
+            for (int f = 0; f < 4; ++f) {
+              xh[(0 * 4 + f) * 128 + m] = make_float4(__uint_as_float(v1[4 * f]), __uint_as_float(v1[4 * f + 1]),
+                                                      __uint_as_float(v1[4 * f + 2]), __uint_as_float(v1[4 * f + 3]));
+              xh[(1 * 4 + f) * 128 + m] = make_float4(__uint_as_float(v2[4 * f]), __uint_as_float(v2[4 * f + 1]),
+                                                      __uint_as_float(v2[4 * f + 2]), __uint_as_float(v2[4 * f + 3]));
+            }
+            asm volatile("bar.sync %0, 128;" ::"r"(3 + half) : "memory");
+            if (py < Cfg::kOutH) {
+#pragma unroll
+              for (int f = 0; f < 4; ++f) {
+                const float4 a1 = xh[(0 * 4 + f) * 128 + m + 8];       // D row py + 1, r = 1
+                const float4 a2 = xh[(1 * 4 + f) * 128 + m + 16];      // D row py + 2, r = 2
+                v[b][4 * f] = __float_as_uint(__uint_as_float(v[b][4 * f]) + a1.x + a2.x);
+                v[b][4 * f + 1] = __float_as_uint(__uint_as_float(v[b][4 * f + 1]) + a1.y + a2.y);
+                v[b][4 * f + 2] = __float_as_uint(__uint_as_float(v[b][4 * f + 2]) + a1.z + a2.z);
+                v[b][4 * f + 3] = __float_as_uint(__uint_as_float(v[b][4 * f + 3]) + a1.w + a2.w);
+              }
+            }
+            asm volatile("bar.sync %0, 128;" ::"r"(3 + half) : "memory");   // the buffer is rewritten by the next item
+          }
+        }
       }
 #pragma unroll
       for (int b = 0; b < 2; ++b) {
@@ -339,11 +404,11 @@ __device__ __forceinline__ void conv_epilogue(const ConvParams& p, const uint32_
   }
 }
 
-template <int CIN, int NT, int TAPS, int MT, int STAGES>
+template <int CIN, int NT, int TAPS, int MT, int STAGES, bool VP>
 __global__ void __launch_bounds__(kConvThreads, 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap tmap, const ConvParams p) {
   pdl_entry();
-  using Cfg = ConvCfg<CIN, NT, TAPS, MT, STAGES>;
+  using Cfg = ConvCfg<CIN, NT, TAPS, MT, STAGES, VP>;
   extern __shared__ __align__(1024) uint8_t smem[];
   uint8_t* sW = smem + Cfg::kOffW;
   uint8_t* sA = smem + Cfg::kOffA;
@@ -398,7 +463,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap, const ConvParams p) {
         const int img = (int)(t / tiles_per_img);
         const int rem = (int)(t - (int64_t)img * tiles_per_img);
         const int ty = rem / p.tiles_x, tx = rem - ty * p.tiles_x;
-        const int y0 = ty * kTileH - Cfg::kPad, x0 = tx * (8 * MT) - Cfg::kPad;
+        const int y0 = ty * Cfg::kOutH - Cfg::kPad, x0 = tx * (8 * MT) - Cfg::kPad;
         mbar_wait(&empty[stage], phase ^ 1);
         if (CTL_DIAGF(p, 2)) {
           mbar_arrive(&full[stage]);
@@ -412,9 +477,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap, const ConvParams p) {
   } else if (warp == 1) {
     // ================================================================= MMA issuer
     if (elect_one()) {
-      constexpr uint32_t idesc = umma_idesc_bf16_f32(128, NT);
+      constexpr uint32_t idesc = umma_idesc_bf16_f32(128, Cfg::kAccCols);
       constexpr uint32_t kLboA = Cfg::kChunkStride, kSboA = Cfg::kHaloW * 16;
-      constexpr uint32_t kLboB = NT * 16, kSboB = 128;
+      constexpr uint32_t kLboB = Cfg::kAccCols * 16, kSboB = 128;
       mbar_wait(w_full, 0);
       int stage = 0, acc = 0;
       uint32_t phase = 0, acc_phase = 0;
@@ -427,16 +492,19 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap, const ConvParams p) {
         if (!CTL_DIAGF(p, 1)) {
 #pragma unroll
         for (int mt = 0; mt < MT; ++mt) {
-          const uint32_t d_tmem = tmem_base + (uint32_t)((acc * MT + mt) * NT);
+          const uint32_t d_tmem = tmem_base + (uint32_t)((acc * MT + mt) * Cfg::kAccCols);
+          // VP: one MMA per filter COLUMN s and K slice, its N dimension spans the three vertical taps; the A tile
+          // starts at row 0 (the M rows are the input rows) and is only shifted horizontally
+          constexpr int kGroups = VP ? 3 : TAPS;
 #pragma unroll
-          for (int tap = 0; tap < TAPS; ++tap) {
-            const int r = TAPS == 9 ? tap / 3 : 0, s = TAPS == 9 ? tap % 3 : 0;
+          for (int tap = 0; tap < kGroups; ++tap) {
+            const int r = (TAPS == 9 && !VP) ? tap / 3 : 0, s = TAPS == 9 ? (VP ? tap : tap % 3) : 0;
             const uint32_t a_tap = a_base + (uint32_t)((r * Cfg::kHaloW + s + 8 * mt) * 16);
 #pragma unroll
             for (int kk = 0; kk < CIN / 16; ++kk) {
               const uint64_t adesc = umma_smem_desc(a_tap + (uint32_t)(2 * kk) * kLboA, kLboA, kSboA);
               const uint64_t bdesc =
-                  umma_smem_desc(sW_addr + (uint32_t)((tap * (CIN / 8) + 2 * kk) * (NT * 16)), kLboB, kSboB);
+                  umma_smem_desc(sW_addr + (uint32_t)((tap * (CIN / 8) + 2 * kk) * (Cfg::kAccCols * 16)), kLboB, kSboB);
               umma_bf16(d_tmem, adesc, bdesc, idesc, (tap | kk) != 0 ? 1u : 0u);
             }
           }
@@ -453,17 +521,27 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap, const ConvParams p) {
     // separate register budgets: the residual variant keeps a tile's residual pixels in flight while it waits for the
     // accumulator, the statistics variant carries 32 running sums (the host rejects res + stats), the generic-geometry
     // variant (stride 2 / ConvTranspose scatter) pays the per-item 64-bit address arithmetic the others hoist
-    if (p.up2x || p.subsample != 1)
-      conv_epilogue<CIN, NT, TAPS, MT, STAGES, true, false, true>(p, tmem_base, sVec, acc_full, acc_empty, n0, reinterpret_cast<float*>(sA));
-    else if (p.res != nullptr && p.sal != nullptr) {
-      if constexpr ((CIN == 64 || CIN == 128) && TAPS == 1)   // the last input-gradient convolution of a decoder (up1: 1x1)
-        conv_epilogue<CIN, NT, TAPS, MT, STAGES, true, false, false, true>(p, tmem_base, sVec, acc_full, acc_empty, n0, reinterpret_cast<float*>(sA));
-    } else if (p.res != nullptr)
-      conv_epilogue<CIN, NT, TAPS, MT, STAGES, true, false, false>(p, tmem_base, sVec, acc_full, acc_empty, n0, reinterpret_cast<float*>(sA));
-    else if (p.stats != nullptr)
-      conv_epilogue<CIN, NT, TAPS, MT, STAGES, false, true, false>(p, tmem_base, sVec, acc_full, acc_empty, n0, reinterpret_cast<float*>(sA));
-    else
-      conv_epilogue<CIN, NT, TAPS, MT, STAGES, false, false, false>(p, tmem_base, sVec, acc_full, acc_empty, n0, reinterpret_cast<float*>(sA));
+    float* stat_smem = reinterpret_cast<float*>(sA);
+    float4* xbuf = reinterpret_cast<float4*>(smem + Cfg::kOffX);
+#define CTL_EPI(RES_, STATS_, GEN_, SAL_) \
+    conv_epilogue<CIN, NT, TAPS, MT, STAGES, VP, RES_, STATS_, GEN_, SAL_>(p, tmem_base, sVec, acc_full, acc_empty, n0, stat_smem, xbuf)
+    if constexpr (TAPS == 9 && !VP && CIN == 128) {
+      CTL_EPI(true, false, true, false);           // unpacked 3x3 with 128 input channels: only the stride-2 form runs here
+    } else {
+      if (p.up2x || p.subsample != 1) {
+        if constexpr (!VP) CTL_EPI(true, false, true, false);
+      } else if (p.res != nullptr && p.sal != nullptr) {
+        if constexpr ((CIN == 64 || CIN == 128) && TAPS == 1)   // the last input-gradient convolution of a decoder (up1: 1x1)
+          CTL_EPI(true, false, false, true);
+      } else if (p.res != nullptr) {
+        CTL_EPI(true, false, false, false);
+      } else if (p.stats != nullptr) {
+        CTL_EPI(false, true, false, false);
+      } else {
+        CTL_EPI(false, false, false, false);
+      }
+    }
+#undef CTL_EPI
   }
 
   tc_fence_before();
@@ -509,17 +587,17 @@ int make_act_tmap(CUtensorMap* m, const void* x, int N, int H, int W, int C, int
   return CTL_OK;
 }
 
-template <int CIN, int NT, int TAPS, int MT, int STAGES>
+template <int CIN, int NT, int TAPS, int MT, int STAGES, bool VP = false>
 int launch_conv(const void* x, const ConvParams& p0, cudaStream_t st) {
-  using Cfg = ConvCfg<CIN, NT, TAPS, MT, STAGES>;
+  using Cfg = ConvCfg<CIN, NT, TAPS, MT, STAGES, VP>;
   ConvParams p = p0;
   p.diag = diag_flags();
   p.tiles_x = (int)ceil_div(p.W, 8 * MT);
-  p.tiles_y = (int)ceil_div(p.H, kTileH);
+  p.tiles_y = (int)ceil_div(p.H, Cfg::kOutH);
   p.num_tiles = (int64_t)p.N * p.tiles_x * p.tiles_y;
   CUtensorMap tmap;
   if (int rc = make_act_tmap(&tmap, x, p.N, p.H, p.W, CIN, Cfg::kHaloW, Cfg::kHaloH)) return rc;
-  auto kern = conv_tc_kernel<CIN, NT, TAPS, MT, STAGES>;
+  auto kern = conv_tc_kernel<CIN, NT, TAPS, MT, STAGES, VP>;
   CTL_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes),
               "conv smem attribute");
   const int n_tiles = p.Cout / NT;
@@ -530,6 +608,7 @@ int launch_conv(const void* x, const ConvParams& p0, cudaStream_t st) {
   return CTL_OK;
 }
 
+// 1x1 filters, and 3x3 stride 2 on unpacked taps (full-resolution compute, keep even pixels)
 template <int CIN, int TAPS>
 int dispatch_nt(const void* x, const ConvParams& p, int nt, cudaStream_t st) {
   // MT = 2 (16x16 pixel tiles, halo overhead 1.27x) while the tile ring fits; STAGES from the smem left
@@ -554,10 +633,31 @@ int dispatch_nt(const void* x, const ConvParams& p, int nt, cudaStream_t st) {
   return CTL_ERR_UNSUPPORTED;
 }
 
+// 3x3 stride 1 with the vertical taps packed into N (N = 3 * nt <= 192): M tiles per tile bounded by the 512 TMEM
+// columns (two accumulator stages of MT * 3 * nt columns), ring depth by the shared memory left beside the weights and
+// the 32 KB row-exchange buffer
+template <int CIN>
+int dispatch_vp(const void* x, const ConvParams& p, int nt, cudaStream_t st) {
+  if constexpr (CIN == 128) {
+    if (nt == 16) return launch_conv<128, 16, 9, 1, 3, true>(x, p, st);
+    if (nt == 32) return launch_conv<128, 32, 9, 1, 2, true>(x, p, st);
+  }
+  set_error("ctl_conv2d_c8_bf16: no packed 3x3 kernel for Cin=%d, n_tile=%d", CIN, nt);
+  return CTL_ERR_UNSUPPORTED;
+}
+
 }  // namespace
 }  // namespace ctl
 
 using namespace ctl;
+
+// 1: the kernel of this layer class expects the vertically packed 3x3 weight layout.  Measured on a B200 (batch 64):
+// with 128 input channels the packed form cuts the MMA issue time enough to win (128->128 @28^2: 36.3 -> 26.0 us);
+// with <= 64 input channels the layers are bound by the epilogue, which the row exchange makes heavier (16->16 @224^2:
+// 58.8 -> 92.6 us), so they stay on unpacked taps.
+extern "C" int ctl_conv2d_vpacked(int Cin, int Cout, int taps, int subsample) {
+  return (taps == 9 && subsample == 1 && Cin == 128 && Cout % 16 == 0) ? 1 : 0;
+}
 
 extern "C" int ctl_conv2d_n_tile(int Cin, int Cout, int taps) {
   if (!(Cin == 16 || Cin == 32 || Cin == 64 || Cin == 128) || Cout <= 0 || Cout % 16 || !(taps == 1 || taps == 9))
@@ -587,7 +687,7 @@ static int conv2d_c8_impl(const void* x, int64_t N, int64_t H, int64_t W, int64_
               "fused output statistics need an N tile <= 32 (Cout %% 64 != 0 or 3x3 with Cin 128) and no up2x");
   CTL_REQUIRE(stats == nullptr || res == nullptr, CTL_ERR_UNSUPPORTED,
               "ctl_conv2d_c8_bf16: fused output statistics and a residual input cannot be combined");
-  CTL_REQUIRE(N * ((H + 15) / 16) * ((W + 7) / 8) < (int64_t)1 << 31, CTL_ERR_INVALID, "ctl_conv2d_c8_bf16: too many tiles");
+  CTL_REQUIRE(N * ((H + 13) / 14) * ((W + 7) / 8) < (int64_t)1 << 31, CTL_ERR_INVALID, "ctl_conv2d_c8_bf16: too many tiles");
   CTL_REQUIRE(nt > 0, CTL_ERR_UNSUPPORTED,
               "ctl_conv2d_c8_bf16 handles Cin in {16,32,64,128} and Cout %% 16 == 0 (got Cin=%lld Cout=%lld)",
               (long long)Cin, (long long)Cout);
@@ -608,7 +708,9 @@ static int conv2d_c8_impl(const void* x, int64_t N, int64_t H, int64_t W, int64_
     p.sal = sal; p.sal_mode = sal_mode; p.no_store = store_out ? 0 : 1;
   }
   cudaStream_t st = (cudaStream_t)stream;
-  if (taps == 9) {
+  if (ctl_conv2d_vpacked((int)Cin, (int)Cout, taps, subsample))   // w_packed in the vertically packed layout
+    return dispatch_vp<128>(x, p, nt, st);
+  if (taps == 9) {                             // tap-major weights
     switch ((int)Cin) {
       case 16: return dispatch_nt<16, 9>(x, p, nt, st);
       case 32: return dispatch_nt<32, 9>(x, p, nt, st);

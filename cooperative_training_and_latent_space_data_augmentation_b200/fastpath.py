@@ -59,7 +59,7 @@ class _PackRegistry:
             p = e["param"]()
             if p is None:
                 continue
-            rows.append(ops.pack_job(p.detach(), e["transposed"], e["out"]))
+            rows.append(ops.pack_job(p.detach(), e["transposed"], e["out"], e["tap_major"]))
             keys.append(key)
             biggest = max(biggest, p.numel())
         dev = next(iter(self.entries.values()))["out"].device
@@ -69,7 +69,7 @@ class _PackRegistry:
         self.table_keys, self.max_elements = keys, biggest
         self.dirty = False
 
-    def get(self, param, transposed, tag):
+    def get(self, param, transposed, tag, tap_major=None):
         import weakref
         epoch = _WEIGHTS_EPOCH[0]
         key = (id(param), tag)
@@ -80,9 +80,10 @@ class _PackRegistry:
             if torch.cuda.is_current_stream_capturing():
                 raise RuntimeError("a conv weight was packed for the first time inside a CUDA-graph capture: run the "
                                    "step eagerly once before capturing")
-            out = ops._pack_kernel(param, transposed)
+            out = ops._pack_kernel(param, transposed, tap_major)
             self.entries[key] = {"param": weakref.ref(param), "ptr": param.data_ptr(), "out": out,
-                                 "transposed": transposed, "epoch": epoch, "version": param._version}
+                                 "transposed": transposed, "tap_major": tap_major, "epoch": epoch,
+                                 "version": param._version}
             self.dirty = True
             return out
         if e["epoch"] != epoch or e["version"] != param._version:
@@ -118,9 +119,12 @@ def _packed(param, fn, tag='fwd'):
     transposed-conv slices).  Plain Conv2d packings (forward / input-gradient) of fp32 contiguous weights go through the
     batched registry above; derived ones (transposed-conv slices) keep a per-parameter cache: it lives ON the parameter
     object -- a global table keyed by id() alone would hand a new parameter the packed weights of a dead one."""
-    if (fn is ops.pack_conv_weight or fn is ops.pack_conv_weight_dgrad) and param.is_cuda \
+    if (fn is ops.pack_conv_weight or fn is ops.pack_conv_weight_dgrad or fn is ops.pack_conv_weight_s2) and param.is_cuda \
             and param.dtype == torch.float32 and param.is_contiguous():
-        return _REGISTRY.get(param, fn is ops.pack_conv_weight_dgrad, tag)
+        if fn is ops.pack_conv_weight_s2 and tag == 'fwd':
+            tag = 'fwd_s2'
+        return _REGISTRY.get(param, fn is ops.pack_conv_weight_dgrad, tag,
+                             tap_major=True if fn is ops.pack_conv_weight_s2 else None)
     cache = param.__dict__.get('_ctl_packed')
     if cache is None:
         cache = param.__dict__['_ctl_packed'] = {}
@@ -194,7 +198,7 @@ def _bn_batch(bn, y_raw, mode):
 def _conv(conv, x, **kw):
     k = conv.kernel_size[0]
     sub = conv.stride[0]
-    wp = _packed(conv.weight, ops.pack_conv_weight)
+    wp = _packed(conv.weight, ops.pack_conv_weight_s2 if (sub == 2 and k == 3) else ops.pack_conv_weight)
     return ops.conv2d_c8(x, wp, conv.out_channels, k * k, subsample=sub, **kw)
 
 

@@ -266,23 +266,36 @@ def conv_supported(cin, cout, kernel_size):
     return taps in (1, 9) and _lib.load().ctl_conv2d_n_tile(int(cin), int(cout), taps) > 0
 
 
-def pack_conv_weight_torch(weight):
-    """[Cout,Cin,k,k] (k = 1 or 3) -> bf16 [Cout/NT][taps][Cin/8][NT][8], the K-major core-matrix order the
-    UMMA descriptors of conv_tc.cu expect (include/ctl_b200.h) -- the torch-ops statement of ctl_pack_conv_weight,
-    used for derived weights (transposed-conv slices) and by the tests."""
+def _tap_major(cout_p, cin_p, taps, stride=1):
+    """Weight layout the kernel of this layer class reads (packed-view channel counts)."""
+    return not _lib.load().ctl_conv2d_vpacked(int(cin_p), int(cout_p), int(taps), int(stride))
+
+
+def pack_conv_weight_torch(weight, tap_major=None):
+    """[Cout,Cin,k,k] (k = 1 or 3) -> the packed bf16 weight of conv_tc.cu (include/ctl_b200.h), stated in torch ops
+    (used for derived weights -- transposed-conv slices -- and by the tests).  1x1 and tap_major 3x3 (the stride-2
+    kernel): [Cout/NT][taps][Cin/8][NT][8]; 3x3 stride 1: [Cout/NT][3 (s)][Cin/8][3*NT (r, n)][8]."""
     cout, cin, kh, kw = weight.shape
     taps = kh * kw
     nt = _lib.load().ctl_conv2d_n_tile(cin, cout, taps)
     if kh != kw or nt <= 0:
         raise NotImplementedError("no tcgen05 conv kernel for weight shape %s" % (tuple(weight.shape),))
-    w = weight.detach().to(torch.bfloat16).permute(2, 3, 1, 0).reshape(taps, cin // 8, 8, cout // nt, nt)
-    return w.permute(3, 0, 1, 4, 2).contiguous()
+    wb = weight.detach().to(torch.bfloat16)
+    if tap_major is None:
+        tap_major = _tap_major(cout, cin, taps)
+    if taps == 1 or tap_major:
+        w = wb.permute(2, 3, 1, 0).reshape(taps, cin // 8, 8, cout // nt, nt)
+        return w.permute(3, 0, 1, 4, 2).contiguous()
+    w = wb.reshape(cout // nt, nt, cin // 8, 8, 3, 3)            # [t][n][q][j][r][s]
+    return w.permute(0, 5, 2, 4, 1, 3).contiguous()              # [t][s][q][r][n][j]
 
 
-def _pack_kernel(weight, transposed):
+def _pack_kernel(weight, transposed, tap_major=None):
     cout, cin, kh, kw = weight.shape
     taps = kh * kw
     co_p, ci_p = (cin, cout) if transposed else (cout, cin)
+    if tap_major is None:
+        tap_major = _tap_major(co_p, ci_p, taps)
     if kh != kw or taps not in (1, 9) or _lib.load().ctl_conv2d_n_tile(ci_p, co_p, taps) <= 0:
         raise NotImplementedError("no tcgen05 conv kernel for weight shape %s" % (tuple(weight.shape),))
     w = weight.detach()
@@ -291,19 +304,22 @@ def _pack_kernel(weight, transposed):
     _need_cuda(w)
     out = torch.empty(cout * cin * taps, device=w.device, dtype=torch.bfloat16)
     with torch.cuda.device(w.device):
-        _lib.check(_lib.load().ctl_pack_conv_weight(w.data_ptr(), cout, cin, taps, int(transposed), out.data_ptr(), _stream()))
+        _lib.check(_lib.load().ctl_pack_conv_weight(w.data_ptr(), cout, cin, taps, int(transposed), int(bool(tap_major)),
+                                                    out.data_ptr(), _stream()))
     return out
 
 
-def pack_job(weight, transposed, out):
+def pack_job(weight, transposed, out, tap_major=None):
     """One row of the ctl_pack_conv_weights_batched job table for a contiguous fp32 [Cout,Cin,k,k] weight."""
     cout, cin, kh, kw = weight.shape
     taps = kh * kw
     co_p, ci_p = (cin, cout) if transposed else (cout, cin)
+    if tap_major is None:
+        tap_major = _tap_major(co_p, ci_p, taps)
     nt = _lib.load().ctl_conv2d_n_tile(ci_p, co_p, taps)
     if kh != kw or taps not in (1, 9) or nt <= 0 or weight.dtype != torch.float32 or not weight.is_contiguous():
         raise NotImplementedError("no batched packing for weight %s %s" % (tuple(weight.shape), weight.dtype))
-    return [weight.data_ptr(), out.data_ptr(), cout, cin, taps, nt, int(transposed), 0]
+    return [weight.data_ptr(), out.data_ptr(), cout, cin, taps, nt, int(transposed), int(bool(tap_major))]
 
 
 def pack_conv_weights_batched(table, n_jobs, max_elements):
@@ -314,8 +330,13 @@ def pack_conv_weights_batched(table, n_jobs, max_elements):
 
 
 def pack_conv_weight(weight):
-    """Packed bf16 forward weight of a Conv2d (one kernel launch; see pack_conv_weight_torch for the layout)."""
+    """Packed bf16 forward weight of a stride-1 Conv2d (one kernel launch; see pack_conv_weight_torch for the layout)."""
     return _pack_kernel(weight, False)
+
+
+def pack_conv_weight_s2(weight):
+    """Packed bf16 forward weight of the 3x3 STRIDE-2 Conv2d (`down`): tap-major layout of the unpacked-tap kernel."""
+    return _pack_kernel(weight, False, tap_major=True)
 
 
 def pack_convtranspose2x2_weight(weight):

@@ -92,7 +92,7 @@ def _pack_stem_weight(weight):
 
 def _conv_raw(conv, x):
     k = conv.kernel_size[0]
-    wp = _packed(conv.weight, ops.pack_conv_weight)
+    wp = _packed(conv.weight, ops.pack_conv_weight_s2 if (conv.stride[0] == 2 and k == 3) else ops.pack_conv_weight)
     return ops.conv2d_c8(x, wp, conv.out_channels, k * k, subsample=conv.stride[0], shift=conv.bias)
 
 

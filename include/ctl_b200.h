@@ -132,8 +132,11 @@ int ctl_philox_uniform(uint64_t seed, uint64_t offset, uint64_t first_index, int
  * taps = 9: 3x3, padding 1; taps = 1: 1x1.  subsample = 2: the 3x3 stride-2 padding-1 convolution of `down`
  * (output H/2 x W/2).  up2x = 1 (taps 1): ConvTranspose2d(kernel 2, stride 2): Cout = 4*out_channels GEMM
  * columns ordered (dy*2+dx)*out_channels + co, scattered to output pixel (2y+dy, 2x+dx) of [N][oc/8][2H][2W][8].
- * w_packed: bf16 [Cout/NT][taps][Cin/8][NT][8] with NT = ctl_conv2d_n_tile(Cin, Cout, taps), element
- *           (t, tap, q, n, j) = weight[t*NT + n][q*8 + j][tap/3][tap%3].
+ * w_packed, NT = ctl_conv2d_n_tile(Cin, Cout, taps):
+ *   ctl_conv2d_vpacked(...) == 0 ("tap-major": 1x1, 3x3 stride 2, 3x3 with Cin <= 64): bf16 [Cout/NT][taps][Cin/8][NT][8], element
+ *           (t, tap, q, n, j) = weight[t*NT + n][q*8 + j][tap/3][tap%3];
+ *   ctl_conv2d_vpacked(...) == 1 ("vertically packed": the three vertical taps of a filter column share one MMA, N = 3*NT):
+ *           bf16 [Cout/NT][3][Cin/8][3*NT][8], element (t, s, q, r*NT + n, j) = weight[t*NT + n][q*8 + j][r][s].
  * out = act( conv(x) * scale[c] + shift[c] + (res * res_scale[c] + res_shift[c]) ); res has the output's shape
  * and layout; res and every per-GEMM-column fp32 vector may be NULL (identity).
  * Cin in {16,32,64,128}, Cout %% 16 == 0.
@@ -142,12 +145,17 @@ int ctl_philox_uniform(uint64_t seed, uint64_t offset, uint64_t first_index, int
  * tensor; needs ctl_conv2d_n_tile(...) <= 32 and up2x == 0.  Finalise with ctl_bn_affine_from_sums.
  */
 int ctl_conv2d_n_tile(int Cin, int Cout, int taps);
+/* 1 when ctl_conv2d_c8_bf16 expects the vertically packed 3x3 layout for this layer class (today: 3x3, stride 1, 128 input
+ * channels), 0 for the tap-major layout. */
+int ctl_conv2d_vpacked(int Cin, int Cout, int taps, int subsample);
 /* fp32 nn.Conv2d weight [Cout][Cin][k][k] (taps = k*k) -> the packed bf16 w_packed above.  transposed = 1 packs the weight of
- * the INPUT-gradient convolution instead, w'[ci][co][r][s] = w[co][ci][k-1-r][k-1-s] (its Cout' = Cin, Cin' = Cout). */
-int ctl_pack_conv_weight(const float* weight, int64_t Cout, int64_t Cin, int taps, int transposed, void* out, void* stream);
+ * the INPUT-gradient convolution instead, w'[ci][co][r][s] = w[co][ci][k-1-r][k-1-s] (its Cout' = Cin, Cin' = Cout).
+ * tap_major = 1: tap-major layout; 0: vertically packed 3x3 layout -- pass !ctl_conv2d_vpacked(Cin', Cout', taps, subsample). */
+int ctl_pack_conv_weight(const float* weight, int64_t Cout, int64_t Cin, int taps, int transposed, int tap_major, void* out,
+                         void* stream);
 /* The same for many weights in ONE launch (a training step repacks every conv weight after the optimizers ran).
  * jobs: DEVICE int64 [n_jobs][8] = {weight ptr, out ptr, Cout, Cin, taps, ctl_conv2d_n_tile of the packed view,
- * transposed, 0}; max_elements = the largest Cout*Cin*taps among them (grid sizing). */
+ * transposed, tap_major}; max_elements = the largest Cout*Cin*taps among them (grid sizing). */
 int ctl_pack_conv_weights_batched(const int64_t* jobs, int64_t n_jobs, int64_t max_elements, void* stream);
 int ctl_conv2d_c8_bf16(const void* x, int64_t N, int64_t H, int64_t W, int64_t Cin, const void* w_packed,
                        int64_t Cout, int taps, int subsample, int up2x, const float* scale,

@@ -48,6 +48,10 @@ LAYERS = [  # (Cin, Cout, k, stride, N, H, W)   -- the layer classes of FCN_16_s
     (128, 64, 1, 1, 2, 28, 28), (32, 16, 1, 1, 2, 112, 112),
     (16, 16, 3, 2, 2, 224, 224), (32, 32, 3, 2, 2, 112, 112), (64, 64, 3, 2, 2, 56, 56), (128, 128, 3, 2, 2, 28, 28),
     (16, 16, 3, 1, 1, 20, 36), (32, 48, 3, 1, 2, 17, 9), (64, 16, 1, 1, 1, 5, 40), (16, 16, 3, 1, 5, 16, 16),
+    # vertically packed 3x3: heights around the 14-row tile (13, 14, 15, 29), 256^2-configuration sizes, every N tile
+    (16, 16, 3, 1, 2, 13, 24), (16, 16, 3, 1, 2, 15, 8), (32, 32, 3, 1, 1, 29, 33), (16, 16, 3, 1, 1, 256, 256),
+    (64, 64, 3, 1, 2, 64, 64), (128, 128, 3, 1, 2, 32, 32), (128, 128, 3, 1, 2, 16, 16), (16, 64, 3, 1, 1, 30, 30),
+    (32, 64, 3, 1, 1, 28, 28), (64, 16, 3, 1, 1, 28, 28), (128, 16, 3, 1, 1, 14, 14), (128, 64, 3, 1, 1, 14, 14),
 ]
 
 
@@ -57,7 +61,7 @@ def test_conv_matches_torch(ops, cin, cout, k, stride, N, H, W):
     x = torch.randn(N, cin, H, W, device="cuda", generator=g).to(torch.bfloat16)
     w = torch.randn(cout, cin, k, k, device="cuda", generator=g) * (2.0 / (cin * k * k)) ** 0.5
     assert ops.conv_supported(cin, cout, k)
-    wp = ops.pack_conv_weight(w)
+    wp = ops.pack_conv_weight_s2(w) if (stride == 2 and k == 3) else ops.pack_conv_weight(w)
     got = ops.conv2d_c8(ops.nchw_to_c8(x), wp, cout, k * k, subsample=stride)
     _check(got, _ref(x, w, k, stride, None, None, None, None, None, 0))
 
@@ -162,5 +166,8 @@ def test_conv_rejects_unsupported(ops):
 def test_pack_kernel_matches_torch_statement(ops, cout, cin, k):
     w = torch.randn(cout, cin, k, k, device="cuda")
     assert torch.equal(ops.pack_conv_weight(w), ops.pack_conv_weight_torch(w).reshape(-1))
+    if k == 3:
+        assert torch.equal(ops.pack_conv_weight_s2(w), ops.pack_conv_weight_torch(w, tap_major=True).reshape(-1))
+        assert torch.equal(ops._pack_kernel(w, False, tap_major=False), ops.pack_conv_weight_torch(w, tap_major=False).reshape(-1))
     want = ops.pack_conv_weight_torch(w.flip(2, 3).transpose(0, 1)).reshape(-1)
     assert torch.equal(ops.pack_conv_weight_dgrad(w), want)
