@@ -67,7 +67,7 @@ inline int plane_splits(int64_t planes, int64_t HW, int ctas_per_sm) {
 // MODE 1: dv = dy * act'(h); sum dv, sum dv*a (BatchNorm backward); optionally materialises dv.
 // partial: double [(split*planes + plane)*8 + j][2]
 template <int MODE>
-__global__ void __launch_bounds__(kT, 3)
+__global__ void __launch_bounds__(kT, 2)
 plane_reduce_kernel(const uint4* __restrict__ x, const uint4* __restrict__ h, const uint4* __restrict__ a,
                     uint4* __restrict__ dv_out, double* __restrict__ partial, int64_t planes, int64_t HW, int splits,
                     int act, const float* __restrict__ act_scale, const float* __restrict__ act_shift, int C8) {
@@ -114,39 +114,38 @@ plane_reduce_kernel(const uint4* __restrict__ x, const uint4* __restrict__ h, co
       for (int j = 0; j < 8; ++j) { s[j] += f[j]; q[j] = fmaf(f[j], av[j], q[j]); }
     }
   };
-  // two positions per iteration, every load issued before the first use: with ~80 registers only three CTAs fit an SM,
-  // and one position's 2-3 16-byte loads per thread left the HBM pipe half empty (2.3 TB/s)
+  // four positions per iteration, every load issued before the first use: 8-12 independent 16-byte loads per thread
+  // (~100 KB in flight per SM with three resident CTAs) -- two positions left the HBM pipe at 3.0 TB/s
   const uint4 zero = make_uint4(0, 0, 0, 0);
-  for (int64_t i = lo + threadIdx.x; i < hi; i += 2 * kT) {
-    const int64_t idx0 = plane * HW + i, idx1 = idx0 + kT;
-    const bool two = i + kT < hi;
-    const uint4 x0 = __ldcs(x + idx0);
-    const uint4 a0 = MODE == 1 ? __ldg(a + idx0) : zero;
-    const uint4 h0 = (MODE == 1 && h != nullptr) ? __ldg(h + idx0) : zero;
-    uint4 x1 = zero, a1 = zero, h1 = zero;
-    if (two) {
-      x1 = __ldcs(x + idx1);
-      if (MODE == 1) a1 = __ldg(a + idx1);
-      if (MODE == 1 && h != nullptr) h1 = __ldg(h + idx1);
+  constexpr int kP = 4;
+  for (int64_t i = lo + threadIdx.x; i < hi; i += kP * kT) {
+    uint4 xv[kP], av[kP], hv[kP];
+#pragma unroll
+    for (int u = 0; u < kP; ++u) {
+      const int64_t idx = plane * HW + i + u * kT;
+      const bool ok = i + u * kT < hi;
+      xv[u] = ok ? __ldcs(x + idx) : zero;
+      av[u] = (MODE == 1 && ok) ? __ldg(a + idx) : zero;
+      hv[u] = (MODE == 1 && h != nullptr && ok) ? __ldg(h + idx) : zero;
     }
-    accumulate(idx0, x0, a0, h0);
-    if (two) accumulate(idx1, x1, a1, h1);
+#pragma unroll
+    for (int u = 0; u < kP; ++u)
+      if (i + u * kT < hi) accumulate(plane * HW + i + u * kT, xv[u], av[u], hv[u]);
   }
+  // warp level in fp32 (a thread holds ~20 values, a warp ~640: a few ulp), fp64 from there on
   __shared__ double red[kT / 32][16];
-  double ds[8], dq[8];
 #pragma unroll
   for (int j = 0; j < 8; ++j) {
-    ds[j] = (double)s[j]; dq[j] = (double)q[j];
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
-      ds[j] += __shfl_xor_sync(0xffffffffu, ds[j], o);
-      dq[j] += __shfl_xor_sync(0xffffffffu, dq[j], o);
+      s[j] += __shfl_xor_sync(0xffffffffu, s[j], o);
+      q[j] += __shfl_xor_sync(0xffffffffu, q[j], o);
     }
   }
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (lane == 0) {
 #pragma unroll
-    for (int j = 0; j < 8; ++j) { red[warp][j] = ds[j]; red[warp][8 + j] = dq[j]; }
+    for (int j = 0; j < 8; ++j) { red[warp][j] = (double)s[j]; red[warp][8 + j] = (double)q[j]; }
   }
   __syncthreads();
   if (threadIdx.x < 16) {
