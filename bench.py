@@ -542,7 +542,12 @@ def run_gpu_arm(args):
     if rank == 0:
         sampler.start()
     launches0 = _lib.LAUNCHES["count"]
+    if args.profile:                        # `ncu --profile-from-start off`: only the timed (graph-replayed) steps
+        torch.cuda.synchronize()
+        torch.cuda.profiler.start()
     t_dev, _ = timed_loop(device_step, args.steps)
+    if args.profile:
+        torch.cuda.profiler.stop()
     launches = _lib.LAUNCHES["count"] - launches0
     if args.profile:                        # ncu launch-list pass: the device loop only
         if rank == 0:

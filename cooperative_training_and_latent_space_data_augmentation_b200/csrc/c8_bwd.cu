@@ -70,7 +70,8 @@ template <int MODE>
 __global__ void __launch_bounds__(kT, 2)
 plane_reduce_kernel(const uint4* __restrict__ x, const uint4* __restrict__ h, const uint4* __restrict__ a,
                     uint4* __restrict__ dv_out, double* __restrict__ partial, int64_t planes, int64_t HW, int splits,
-                    int act, const float* __restrict__ act_scale, const float* __restrict__ act_shift, int C8) {
+                    int act, const float* __restrict__ act_scale, const float* __restrict__ act_shift, int C8,
+                    double* __restrict__ totals) {
   pdl_entry();
   const int64_t plane = blockIdx.x;
   // h == NULL with an affine: the activation input is recomputed, h = act(a*act_scale[c] + act_shift[c]) has its sign
@@ -152,7 +153,10 @@ plane_reduce_kernel(const uint4* __restrict__ x, const uint4* __restrict__ h, co
     double t = 0.0;
     for (int w = 0; w < kT / 32; ++w) t += red[w][threadIdx.x];
     const int j = threadIdx.x & 7, second = threadIdx.x >> 3;
-    partial[(((int64_t)split * planes + plane) * 8 + j) * 2 + second] = t;
+    if (totals != nullptr)      // per-channel totals [2][C] (zeroed by the caller): ONE fp64 atomic per value and CTA, no
+      atomicAdd(totals + second * (C8 * 8) + (int)(plane % C8) * 8 + j, t);      // finalisation launch afterwards
+    else
+      partial[(((int64_t)split * planes + plane) * 8 + j) * 2 + second] = t;
   }
 }
 
@@ -278,12 +282,49 @@ __global__ void bn_bwd_finalize_kernel(const double* __restrict__ partial, int64
 }
 
 // da = c1*dv + c2*a + c3, dv = dy * act'(h) when h is given
+struct BnBwdTotals {          // coefficients computed in the kernel's prologue from the reduction's per-channel totals
+  const double* totals;       // [2][C]: sum dv | sum dv*a; nullptr -> `coef` is read from global memory
+  const float* mean;
+  const float* var;
+  const float* gamma;
+  float* dgamma;              // written by CTA 0 (may be nullptr)
+  float* dbeta;
+  double count;
+  float eps;
+};
+constexpr int kMaxBnC = 256;
+
 __global__ void __launch_bounds__(kT)
 bn_bwd_apply_kernel(const uint4* __restrict__ dy, const uint4* __restrict__ h, const uint4* __restrict__ a,
-                    const float* __restrict__ coef, uint4* __restrict__ da, int64_t total, int C8, int64_t HW, int act,
-                    const float* __restrict__ act_scale, const float* __restrict__ act_shift) {
+                    const float* __restrict__ coef_in, uint4* __restrict__ da, int64_t total, int C8, int64_t HW, int act,
+                    const float* __restrict__ act_scale, const float* __restrict__ act_shift, const BnBwdTotals bt) {
   pdl_entry();
   const int C = C8 * 8;
+  __shared__ float s_coef[3 * kMaxBnC];
+  const float* coef = coef_in;
+  if (bt.totals != nullptr) {
+    // same arithmetic as bn_bwd_finalize_kernel, once per CTA (C <= 256 values): no finalisation launch
+    for (int c = threadIdx.x; c < C; c += kT) {
+      // fp64 only where it matters (the cancellation in S2 - mean*S1); 1/sqrt and the divisions in fp32 -- this
+      // runs in every CTA's prologue, and fp64 division / square root are ~100-instruction sequences
+      const double S1 = bt.totals[c], S2 = bt.totals[C + c];
+      const float mu = bt.mean[c];
+      const float inv = 1.0f / sqrtf(bt.var[c] + bt.eps);
+      const float g = bt.gamma ? bt.gamma[c] : 1.0f;
+      const float scale = g * inv;
+      const float dg = inv * (float)(S2 - (double)mu * S1);
+      const float rc = (float)(1.0 / bt.count), s1 = (float)S1;
+      s_coef[c] = scale;
+      s_coef[C + c] = -scale * inv * dg * rc;
+      s_coef[2 * C + c] = scale * (inv * mu * dg - s1) * rc;
+      if (blockIdx.x == 0) {
+        if (bt.dgamma) bt.dgamma[c] = dg;
+        if (bt.dbeta) bt.dbeta[c] = s1;
+      }
+    }
+    __syncthreads();
+    coef = s_coef;
+  }
   for (int64_t i = (int64_t)blockIdx.x * kT + threadIdx.x; i < total; i += (int64_t)gridDim.x * kT) {
     const int c0 = (int)((i / HW) % C8) * 8;
     float f[8], av[8];
@@ -300,7 +341,7 @@ bn_bwd_apply_kernel(const uint4* __restrict__ dy, const uint4* __restrict__ h, c
     }
 #pragma unroll
     for (int j = 0; j < 8; ++j)
-      f[j] = fmaf(__ldg(coef + c0 + j), f[j], fmaf(__ldg(coef + C + c0 + j), av[j], __ldg(coef + 2 * C + c0 + j)));
+      f[j] = fmaf(coef[c0 + j], f[j], fmaf(coef[C + c0 + j], av[j], coef[2 * C + c0 + j]));
     da[i] = pack8(f);
   }
 }
@@ -723,7 +764,8 @@ extern "C" int ctl_bn_batch_affine_c8(const void* x, int64_t N, int64_t C, int64
   const int64_t planes = N * (C / 8), HW = H * W;
   const int splits = plane_splits(planes, HW, reduce_ctas_per_sm<0>());
   launch_chained(plane_reduce_kernel<0>, dim3((unsigned)planes, (unsigned)splits), kT, 0, st)(
-      (const uint4*)x, nullptr, nullptr, nullptr, (double*)workspace, planes, HW, splits, 0, nullptr, nullptr, (int)(C / 8));
+      (const uint4*)x, nullptr, nullptr, nullptr, (double*)workspace, planes, HW, splits, 0, nullptr, nullptr, (int)(C / 8),
+      nullptr);
   CTL_CUDA_OK(cudaGetLastError(), "bn_partial_stats launch");
   launch_chained(bn_fwd_finalize_kernel, (unsigned)ceil_div(C, 4), 128, 0, st)((const double*)workspace, planes, splits, (int)N, (int)C,
                                                                    (double)(N * HW), gamma, beta, eps, scale, shift,
@@ -754,7 +796,8 @@ extern "C" int ctl_channel_sums_c8(const void* x, int64_t N, int64_t C, int64_t 
   const int64_t planes = N * (C / 8), HW = H * W;
   const int splits = plane_splits(planes, HW, reduce_ctas_per_sm<0>());
   launch_chained(plane_reduce_kernel<0>, dim3((unsigned)planes, (unsigned)splits), kT, 0, st)(
-      (const uint4*)x, nullptr, nullptr, nullptr, (double*)workspace, planes, HW, splits, 0, nullptr, nullptr, (int)(C / 8));
+      (const uint4*)x, nullptr, nullptr, nullptr, (double*)workspace, planes, HW, splits, 0, nullptr, nullptr, (int)(C / 8),
+      nullptr);
   CTL_CUDA_OK(cudaGetLastError(), "plane_reduce launch");
   launch_chained(channel_sum_finalize_kernel, (unsigned)ceil_div(C, 4), 128, 0, st)((const double*)workspace, planes, splits, (int)N,
                                                                         (int)C, sum_out, sumsq_out);
@@ -778,7 +821,7 @@ extern "C" int ctl_bn_bwd_reduce_c8(const void* dy, const void* h, const void* a
   const int splits = plane_splits(planes, HW, reduce_ctas_per_sm<1>());
   launch_chained(plane_reduce_kernel<1>, dim3((unsigned)planes, (unsigned)splits), kT, 0, st)(
       (const uint4*)dy, (const uint4*)h, (const uint4*)a, (uint4*)dv_out, (double*)workspace, planes, HW, splits, act,
-      act_scale, act_shift, (int)(C / 8));
+      act_scale, act_shift, (int)(C / 8), nullptr);
   CTL_CUDA_OK(cudaGetLastError(), "bn_bwd_reduce launch");
   launch_chained(bn_bwd_finalize_kernel, (unsigned)ceil_div(C, 4), 128, 0, st)((const double*)workspace, planes, splits, (int)N, (int)C,
                                                                    (double)(N * HW), mean, var, eps, gamma, coef, dgamma,
@@ -798,8 +841,43 @@ extern "C" int ctl_bn_bwd_apply_c8(const void* dy, const void* h, const void* a,
   const int64_t total = N * (C / 8) * H * W;
   launch_chained(bn_bwd_apply_kernel, grid_for(total), kT, 0, (cudaStream_t)stream)((const uint4*)dy, (const uint4*)h, (const uint4*)a,
                                                                       coef, (uint4*)da, total, (int)(C / 8), H * W, act,
-                                                                      act_scale, act_shift);
+                                                                      act_scale, act_shift, BnBwdTotals{});
   CTL_CUDA_OK(cudaGetLastError(), "bn_bwd_apply launch");
+  return CTL_OK;
+}
+
+extern "C" int ctl_bn_bwd_c8(const void* dy, const void* h, const void* a, int64_t N, int64_t C, int64_t H, int64_t W,
+                             int act, const float* mean, const float* var, float eps, const float* gamma, double* totals,
+                             void* dv_out, void* da, float* dgamma, float* dbeta, const float* act_scale,
+                             const float* act_shift, void* stream) {
+  if (int rc = check_c8("ctl_bn_bwd_c8", dy, a, N, C, H, W)) return rc;
+  CTL_REQUIRE(mean && var && totals && da, CTL_ERR_INVALID, "ctl_bn_bwd_c8: NULL pointer");
+  CTL_REQUIRE(C <= kMaxBnC, CTL_ERR_UNSUPPORTED, "ctl_bn_bwd_c8: at most %d channels (got %lld)", kMaxBnC, (long long)C);
+  CTL_REQUIRE(act >= CTL_ACT_NONE && act <= CTL_ACT_RELU, CTL_ERR_INVALID, "activation %d has no BN backward", act);
+  CTL_REQUIRE(h != nullptr || dv_out == nullptr, CTL_ERR_INVALID, "dv_out needs h");
+  CTL_REQUIRE((act_scale == nullptr) == (act_shift == nullptr) && (h == nullptr || act_scale == nullptr), CTL_ERR_INVALID,
+              "ctl_bn_bwd_c8: give either h or (act_scale, act_shift)");
+  if (sm_count() < 0) return CTL_ERR_CUDA;
+  cudaStream_t st = (cudaStream_t)stream;
+  const int64_t planes = N * (C / 8), HW = H * W, total = planes * HW;
+  const int splits = plane_splits(planes, HW, reduce_ctas_per_sm<1>());
+  launch_chained(plane_reduce_kernel<1>, dim3((unsigned)planes, (unsigned)splits), kT, 0, st)(
+      (const uint4*)dy, (const uint4*)h, (const uint4*)a, (uint4*)dv_out, nullptr, planes, HW, splits, act, act_scale,
+      act_shift, (int)(C / 8), totals);
+  CTL_CUDA_OK(cudaGetLastError(), "bn_bwd reduce launch");
+  const BnBwdTotals bt = {totals, mean, var, gamma, dgamma, dbeta, (double)(N * HW), eps};
+  // every CTA pays the coefficient prologue: a grid of a few CTAs per SM striding over the tensor amortises it
+  const unsigned apply_grid = (unsigned)std::min<int64_t>(ceil_div(total, kT), (int64_t)sm_count() * 6);
+  // dv materialised (the residual tail feeds it to the shortcut branch too): the apply pass reads it, activation done
+  if (dv_out != nullptr)
+    launch_chained(bn_bwd_apply_kernel, apply_grid, kT, 0, st)((const uint4*)dv_out, nullptr, (const uint4*)a, nullptr,
+                                                                    (uint4*)da, total, (int)(C / 8), HW, act, nullptr,
+                                                                    nullptr, bt);
+  else
+    launch_chained(bn_bwd_apply_kernel, apply_grid, kT, 0, st)((const uint4*)dy, (const uint4*)h, (const uint4*)a, nullptr,
+                                                               (uint4*)da, total, (int)(C / 8), HW, act, act_scale,
+                                                               act_shift, bt);
+  CTL_CUDA_OK(cudaGetLastError(), "bn_bwd apply launch");
   return CTL_OK;
 }
 

@@ -599,7 +599,8 @@ def channel_sum_c8(x):
     return out
 
 
-def bn_act_bwd_c8(dy, h, a, act, mean, var, eps, gamma, want_dv=False, want_param_grads=True, act_affine=None):
+def bn_act_bwd_c8(dy, h, a, act, mean, var, eps, gamma, want_dv=False, want_param_grads=True, act_affine=None,
+                  totals=None):
     """Backward of h = act(BatchNorm_train(a)).  Returns (da, dgamma, dbeta, dv): dv = dy*act'(h) is materialised only
     when want_dv (h must then be given); dgamma/dbeta are None unless want_param_grads.
     act_affine = (scale, shift) of the forward (h = act(a*scale + shift), LReLU / ReLU): h is then not read -- the sign
@@ -620,6 +621,16 @@ def bn_act_bwd_c8(dy, h, a, act, mean, var, eps, gamma, want_dv=False, want_para
     dv = torch.empty_like(a) if (want_dv and h is not None) else None
     g = _vec(gamma, C)
     da = torch.empty_like(a)
+    if totals is not None and C <= 256:
+        # zeroed float64 [2, C] scratch from the caller's arena: reduction -> totals -> apply, no finalisation launch
+        with torch.cuda.device(a.device):
+            _lib.check(lib.ctl_bn_bwd_c8(dy.data_ptr(), _ptr(h), a.data_ptr(), N, C, H, W, act, mean.data_ptr(),
+                                         var.data_ptr(), float(eps), _ptr(g), totals.data_ptr(), _ptr(dv), da.data_ptr(),
+                                         pg[0].data_ptr() if pg is not None else 0,
+                                         pg[1].data_ptr() if pg is not None else 0, _ptr(sc), _ptr(sh), _stream()))
+        if want_dv and dv is None:
+            dv = dy
+        return da, (pg[0] if pg is not None else None), (pg[1] if pg is not None else None), dv
     with torch.cuda.device(a.device):
         _lib.check(lib.ctl_bn_bwd_reduce_c8(dy.data_ptr(), _ptr(h), a.data_ptr(), N, C, H, W, act, mean.data_ptr(),
                                             var.data_ptr(), float(eps), _ptr(g), ws.data_ptr(), _ptr(dv), coef.data_ptr(),

@@ -167,6 +167,10 @@ class _Grads(dict):
             p.grad is not None and p.grad.is_contiguous() and p.grad.dtype == torch.float32 for p in wanted)
         self.small_dst, self.small_src = [], []
         self.arena, self.used = None, 0
+        # ONE zeroed float64 arena for the BatchNorm-backward totals of this backward pass (2 * C values per layer;
+        # the deepest sub-network has 13 BatchNorm layers of <= 128 channels)
+        self.bn_arena = torch.zeros(8192, device=params[0].device, dtype=torch.float64)
+        self.bn_used = 0
         if not self.direct:
             # ONE zeroed fp32 arena for every accumulated (atomic) parameter gradient of this backward
             total = sum((p.numel() + 3) // 4 * 4 for p in wanted if p.dim() > 1)
@@ -181,6 +185,14 @@ class _Grads(dict):
         out = self.arena[self.used:self.used + n]
         self.used += (n + 3) // 4 * 4                      # keep slices 16-byte aligned
         return out.view(p.shape) if not extra else out
+
+    def bn_totals(self, channels):
+        n = 2 * channels
+        if self.bn_used + n > self.bn_arena.numel():
+            return None                                     # falls back to the three-launch form
+        out = self.bn_arena[self.bn_used:self.bn_used + n]
+        self.bn_used += n
+        return out
 
     def wants(self, p):
         return p is not None and id(p) in self.need
@@ -218,7 +230,8 @@ def conv_bn_act_fwd(fw, conv, bn, x, act):
 def conv_bn_act_bwd(conv, bn, act, saved, dh, grads, need_dx=True):
     x, a, h, mean, var, scale, shift = saved
     # act'(h) from sign(a*scale + shift): the backward never reads h (it stays alive only as the next layer's input)
-    da, dg, db, _ = ops.bn_act_bwd_c8(dh, h, a, act, mean, var, bn.eps, bn.weight, act_affine=(scale, shift))
+    da, dg, db, _ = ops.bn_act_bwd_c8(dh, h, a, act, mean, var, bn.eps, bn.weight, act_affine=(scale, shift),
+                                      totals=grads.bn_totals(a.shape[1] * 8))
     grads.add(bn.weight, dg)
     grads.add(bn.bias, db)
     if grads.wants(conv.weight):
@@ -254,7 +267,8 @@ def residual_bwd(block, saved, dout, grads, x_low=None):
     seq, ci = block.conv, block.conv_input
     bn2 = seq[4]
     # tail: d(pre) = dout * LReLU'(out) feeds both the 1x1 branch and BN2
-    da2, dg2, db2, dpre = ops.bn_act_bwd_c8(dout, out, a2, LRELU, mean2, var2, bn2.eps, bn2.weight, want_dv=True)
+    da2, dg2, db2, dpre = ops.bn_act_bwd_c8(dout, out, a2, LRELU, mean2, var2, bn2.eps, bn2.weight, want_dv=True,
+                                            totals=grads.bn_totals(a2.shape[1] * 8))
     grads.add(bn2.weight, dg2)
     grads.add(bn2.bias, db2)
     dc = dxr = None
@@ -275,7 +289,7 @@ def residual_bwd(block, saved, dout, grads, x_low=None):
     # BN1 + LReLU + conv1
     x, a1, h1_, mean1, var1, scale1, shift1 = s1
     da1, dg1, db1, _ = ops.bn_act_bwd_c8(dh1, h1_, a1, LRELU, mean1, var1, seq[1].eps, seq[1].weight,
-                                         act_affine=(scale1, shift1))
+                                         act_affine=(scale1, shift1), totals=grads.bn_totals(a1.shape[1] * 8))
     grads.add(seq[1].weight, dg1)
     grads.add(seq[1].bias, db1)
     if grads.wants(seq[0].weight):
@@ -405,7 +419,7 @@ def encoder_bwd(enc, tape, dz, grads, x, in_mode, temperature, need_dx):
     dh0 = conv_bn_act_bwd(inc[3], inc[4], LRELU, tape[1], d, grads)
     a0, h0, mean0, var0, scale0, shift0, xin = tape[0]
     da0, dg0, db0, _ = ops.bn_act_bwd_c8(dh0, h0, a0, LRELU, mean0, var0, inc[1].eps, inc[1].weight,
-                                         act_affine=(scale0, shift0))
+                                         act_affine=(scale0, shift0), totals=grads.bn_totals(a0.shape[1] * 8))
     grads.add(inc[1].weight, dg0)
     grads.add(inc[1].bias, db0)
     if grads.wants(inc[0].weight):

@@ -237,6 +237,13 @@ int ctl_bn_bwd_reduce_c8(const void* dy, const void* h, const void* a, int64_t N
 int ctl_bn_bwd_apply_c8(const void* dy, const void* h, const void* a, int64_t N, int64_t C, int64_t H, int64_t W,
                         int act, const float* coef, void* da, const float* act_scale, const float* act_shift,
                         void* stream);
+/* The two BatchNorm-backward stages in ONE call without a finalisation launch: the reduction leaves sum dv / sum dv*a in
+ * `totals` (double [2][C], ZEROED by the caller; one fp64 atomic per value and CTA) and the apply pass forms its
+ * coefficients from them in its prologue; dgamma / dbeta (may be NULL) are written by its first CTA.  Arguments as
+ * ctl_bn_bwd_reduce_c8 / ctl_bn_bwd_apply_c8; C <= 256. */
+int ctl_bn_bwd_c8(const void* dy, const void* h, const void* a, int64_t N, int64_t C, int64_t H, int64_t W, int act,
+                  const float* mean, const float* var, float eps, const float* gamma, double* totals, void* dv_out, void* da,
+                  float* dgamma, float* dbeta, const float* act_scale, const float* act_shift, void* stream);
 /* dv = dy * act'(h) */
 int ctl_act_bwd_c8(const void* dy, const void* h, int64_t N, int64_t C, int64_t H, int64_t W, int act, void* dv,
                    void* stream);

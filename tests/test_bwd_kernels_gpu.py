@@ -245,3 +245,26 @@ def test_stem_input_c8_and_tensor_core_stem(ops, cin, in_mode):
     y.backward(dy.float())
     dW16 = ops.conv_wgrad_c8(xin, ops.nchw_to_c8(dy), 9, layout='conv')
     _cmp(ops.stem_weight_grad(dW16, cin), wf.grad, 1e-4, "tensor-core stem wgrad")
+
+
+@pytest.mark.parametrize("C,H,W,want_dv", [(16, 40, 24, False), (32, 28, 28, True), (128, 14, 14, False), (64, 9, 7, True)])
+def test_bn_backward_totals_form_equals_the_three_launch_form(ops, C, H, W, want_dv):
+    """ctl_bn_bwd_c8 (reduction -> per-channel fp64 totals -> coefficients formed in the apply pass's prologue) against
+    ctl_bn_bwd_reduce_c8 + finalise + ctl_bn_bwd_apply_c8: same sums in a different order (1e-6)."""
+    g = torch.Generator(device="cuda").manual_seed(C + H)
+    N = 5
+    a = ops.nchw_to_c8(torch.randn(N, C, H, W, device="cuda", generator=g))
+    dy = ops.nchw_to_c8(torch.randn(N, C, H, W, device="cuda", generator=g) * 0.1)
+    gamma = 1 + 0.2 * torch.randn(C, device="cuda", generator=g)
+    beta = 0.3 * torch.randn(C, device="cuda", generator=g)
+    scale, shift, mean, var = ops.bn_batch_affine_c8(a, gamma, beta, 1e-5, want_stats=True)
+    h = ops.scale_shift_act_c8(a, scale, shift, ops.ACT_LRELU)
+    kw = dict(want_dv=True) if want_dv else dict(act_affine=(scale, shift))
+    want = ops.bn_act_bwd_c8(dy, h, a, ops.ACT_LRELU, mean, var, 1e-5, gamma, **kw)
+    totals = torch.zeros(2 * C, device="cuda", dtype=torch.float64)
+    got = ops.bn_act_bwd_c8(dy, h, a, ops.ACT_LRELU, mean, var, 1e-5, gamma, totals=totals, **kw)
+    assert float(totals.abs().sum()) > 0
+    for w_, g_ in zip(want[:3], got[:3]):
+        torch.testing.assert_close(g_.float(), w_.float(), rtol=1e-5, atol=1e-6 * float(w_.float().abs().max()) + 1e-9)
+    if want_dv:
+        assert torch.equal(got[3], want[3])
