@@ -132,6 +132,9 @@ class MyDecoder(nn.Module):
         self.up3 = res_up_family(w[1], w[2], norm=norm, up_type=up_type)
         self.up4 = res_up_family(w[2], w[2], norm=norm, up_type=up_type)
         self.final_conv = nn.Conv2d(w[2], output_channel, kernel_size=1, stride=1, padding=0)
+        # the reference runs normal_init over the decoder's DIRECT children (encoder_decoder.py:441-442, :13-16): of those
+        # only final_conv is a convolution -- its bias starts at zero (the weight is re-initialised by kaiming later)
+        nn.init.zeros_(self.final_conv.bias)
         self.last_act = last_act
 
     def forward(self, x):
