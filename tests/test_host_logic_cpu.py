@@ -40,11 +40,11 @@ def test_batched_pack_registry_refreshes_every_weight_in_one_launch(monkeypatch)
     from cooperative_training_and_latent_space_data_augmentation_b200 import fastpath, ops
     single, batched, capturing = [], [], [False]
 
-    def fake_pack_kernel(param, transposed):
+    def fake_pack_kernel(param, transposed, tap_major=None):
         single.append((id(param), transposed))
         return param.detach().clone().reshape(-1)            # persistent "packed" buffer
 
-    def fake_pack_job(weight, transposed, out):
+    def fake_pack_job(weight, transposed, out, tap_major=None):
         return [weight.data_ptr(), out.data_ptr(), weight.shape[0], weight.shape[1], 9, 16, int(transposed), 0]
 
     def fake_batched(table, n_jobs, max_elements):
