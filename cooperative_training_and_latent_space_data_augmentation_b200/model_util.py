@@ -50,7 +50,16 @@ def native_rng():
 
 
 _STEP_PARAMS = None
+_REUSE_FORWARD = True       # the saliency pass reuses the clean pass's decoder forward when it is the same computation
 _FUSED_SALIENCY = True      # tests switch it off to compare with the materialised-gradient chain (K1 -> select -> K2)
+
+
+def set_reuse_forward(flag):
+    """True (default): when mask_latent_code_* is asked to differentiate decoder(code) and that exact forward (same
+    storage, weights and BatchNorm mode) is the decoder's most recent one -- the case inside hard_example_generation --
+    only the backward runs; False: the forward is recomputed as the reference does."""
+    global _REUSE_FORWARD
+    _REUSE_FORWARD = bool(flag)
 
 
 def set_fused_saliency(flag):
@@ -192,6 +201,23 @@ def _latent_gradient(latent_code, decoder_function, label, num_classes, loss_typ
     if fused_mode is not None and loss_type in ('mse', 'ce') and trainpath.saliency_fusable(decoder_function, code):
         N, C, H, W = code.shape
         request = trainpath.SaliencyRequest(fused_mode, N, C if fused_mode == ops.MODE_CHANNEL else H * W, code.device)
+    if request is not None and _REUSE_FORWARD:
+        # `code` is the latent the clean pass has just decoded (same storage, same weights, same BatchNorm mode): the
+        # forward the reference recomputes here is already on tape -- only its backward w.r.t. the code runs, and the
+        # skipped forward's running-statistics update is replayed
+        hit = trainpath.cached_forward(decoder_function, code)
+        if hit is not None:
+            out = hit["out"]
+            if loss_type == 'mse' and label.dim() == code.dim() and ops.sse_supported(out, label):
+                dout = ops.sse_grad(out, label, 1.0 / out.numel())
+            elif loss_type == 'ce' and ops.ce2d_supported(out, label):
+                dout = ops.ce2d_grad(out, label, 1.0 / float(label.numel() + 1e-10))
+            else:
+                dout = None
+            if dout is not None and trainpath.saliency_from_tape(decoder_function, hit, dout, request):
+                if hit["tracked"]:
+                    trainpath.replay_bn_tracking(decoder_function, hit["tape"])
+                return code, None, request
     gt_y = make_one_hot(label, num_classes) if label.dim() < code.dim() else label
     with (request if request is not None else contextlib.nullcontext()):
         if loss_type == 'corr':

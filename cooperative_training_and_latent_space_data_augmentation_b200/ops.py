@@ -979,3 +979,23 @@ def c8_twin(nchw):
                 and nchw._version == version and nchw.dtype == t.dtype and nchw.is_contiguous():
             return c8
     return None
+
+
+# ------------------------------------------------------------------------------------------------ loss gradients alone
+def ce2d_grad(logits, target, scale):
+    """d/dlogits of scale * sum_p -log softmax(logits)[target] (what autograd.grad of the scalar loss returns)."""
+    x, t = logits.detach().contiguous(), target.contiguous()
+    N, C, H, W = x.shape
+    dx = torch.empty_like(x)
+    with torch.cuda.device(x.device):
+        _lib.check(_lib.load().ctl_ce2d_bwd(x.data_ptr(), t.data_ptr(), N, C, H, W, float(scale), 0, dx.data_ptr(), _stream()))
+    return dx
+
+
+def sse_grad(pred, target, scale):
+    """d/dpred of scale * sum (pred - target)**2."""
+    x, t = pred.detach().contiguous(), target.detach().contiguous()
+    dx = torch.empty_like(x)
+    with torch.cuda.device(x.device):
+        _lib.check(_lib.load().ctl_sse_bwd(x.data_ptr(), t.data_ptr(), x.numel(), float(scale), 0, dx.data_ptr(), _stream()))
+    return dx

@@ -137,6 +137,67 @@ def saliency_fusable(decoder, code):
             and decoder.up1.conv_input.in_channels == code.shape[1])
 
 
+# decoder -> its most recent training-route forward: {"z": input tensor, "version", "epoch", "out", "tape", "tracked"}.
+# hard_example_generation differentiates decoder(code) w.r.t. code where `code` IS the latent the clean pass has just
+# decoded with the same weights in the same BatchNorm mode (advanced...model.py:440-447 then :497-523): the forward the
+# reference computes a second time is bit-for-bit the one already on tape.  model_util reuses it for the saliency pass
+# (only the backward runs; the BatchNorm running-stat side effect of the skipped forward is replayed).
+_FORWARD_CACHE = {}
+
+
+def forget_forwards():
+    _FORWARD_CACHE.clear()
+
+
+def cached_forward(dec, code):
+    """The tape of decoder(code) when that exact forward is the decoder's most recent one, else None."""
+    from . import fastpath
+    hit = _FORWARD_CACHE.get(id(dec))
+    if hit is None or hit["dec"] is not dec:
+        return None
+    z = hit["z"]
+    tracked = bool(dec.training and all(m.track_running_stats for m in dec.modules() if isinstance(m, nn.BatchNorm2d)))
+    if (z.data_ptr() != code.data_ptr() or tuple(z.shape) != tuple(code.shape) or z._version != hit["version"]
+            or code._version != hit["version"] or hit["epoch"] != fastpath._WEIGHTS_EPOCH[0] or hit["tracked"] != tracked
+            or not dec.training):
+        return None
+    return hit
+
+
+def replay_bn_tracking(dec, tape):
+    """The running-statistics update a train-mode forward performs, from the batch statistics on `tape` (the forward
+    itself is not recomputed): running = (1 - m) * running + m * batch (unbiased variance), num_batches_tracked += 1."""
+    rm, rv, means, variances, tracked, keep, m_mean, m_var = [], [], [], [], [], [], [], []
+    blocks = (dec.up1, dec.up2, dec.up3, dec.up4)
+    for blk, (x, s) in zip(blocks, tape[:4]):
+        s1, a2, mean2, var2, out = s
+        for bn, a, mean, var in ((blk.conv[1], s1[1], s1[3], s1[4]), (blk.conv[4], a2, mean2, var2)):
+            if not (bn.track_running_stats and bn.running_mean is not None):
+                continue
+            count = a.shape[0] * a.shape[2] * a.shape[3]
+            m = bn.momentum if bn.momentum is not None else 0.1
+            rm.append(bn.running_mean); rv.append(bn.running_var)
+            means.append(mean); variances.append(var)
+            tracked.append(bn.num_batches_tracked)
+            keep.append(1.0 - m); m_mean.append(m); m_var.append(m * count / max(1, count - 1))
+    if rm:                                   # seven multi-tensor launches for the decoder's eight BatchNorm layers
+        torch._foreach_mul_(rm, keep)
+        torch._foreach_add_(rm, torch._foreach_mul(means, m_mean))
+        torch._foreach_mul_(rv, keep)
+        torch._foreach_add_(rv, torch._foreach_mul(variances, m_var))
+        torch._foreach_add_(tracked, 1)
+
+
+def saliency_from_tape(dec, hit, dout, request):
+    """Backward of the cached decoder forward w.r.t. its latent input only, with the saliency sums fused into its last
+    convolution (`request`); the tape is left intact for the training backward that follows."""
+    params = tuple(dec.parameters())
+    grads = _Grads(params, [False] * len(params))
+    with request:
+        decoder_bwd(dec, hit["tape"], dout.contiguous(), grads, True)
+    return request.served
+
+
 _DIRECT = {"on": False}      # process-global on purpose: backward nodes run on autograd's device thread
 
 
@@ -491,6 +552,10 @@ class _DecoderFn(torch.autograd.Function):
         out, tape = decoder_fwd(dec, z_c8 if z_c8 is not None else ops.nchw_to_c8(z))
         ctx.dec, ctx.tape, ctx.params = dec, tape, params
         ctx.z_shape = tuple(z.shape)
+        from . import fastpath
+        _FORWARD_CACHE[id(dec)] = {
+            "dec": dec, "z": z, "version": z._version, "epoch": fastpath._WEIGHTS_EPOCH[0], "out": out, "tape": tape,
+            "tracked": all(m.track_running_stats for m in dec.modules() if isinstance(m, nn.BatchNorm2d))}
         return out
 
     @staticmethod

@@ -250,7 +250,7 @@ def test_stem_input_c8_and_tensor_core_stem(ops, cin, in_mode):
 @pytest.mark.parametrize("C,H,W,want_dv", [(16, 40, 24, False), (32, 28, 28, True), (128, 14, 14, False), (64, 9, 7, True)])
 def test_bn_backward_totals_form_equals_the_three_launch_form(ops, C, H, W, want_dv):
     """ctl_bn_bwd_c8 (reduction -> per-channel fp64 totals -> coefficients formed in the apply pass's prologue) against
-    ctl_bn_bwd_reduce_c8 + finalise + ctl_bn_bwd_apply_c8: same sums in a different order (1e-6)."""
+    ctl_bn_bwd_reduce_c8 + finalise + ctl_bn_bwd_apply_c8: same sums in a different order; dgamma / dbeta 1e-4, da equal up to isolated bf16 roundings."""
     g = torch.Generator(device="cuda").manual_seed(C + H)
     N = 5
     a = ops.nchw_to_c8(torch.randn(N, C, H, W, device="cuda", generator=g))
@@ -264,7 +264,10 @@ def test_bn_backward_totals_form_equals_the_three_launch_form(ops, C, H, W, want
     totals = torch.zeros(2 * C, device="cuda", dtype=torch.float64)
     got = ops.bn_act_bwd_c8(dy, h, a, ops.ACT_LRELU, mean, var, 1e-5, gamma, totals=totals, **kw)
     assert float(totals.abs().sum()) > 0
-    for w_, g_ in zip(want[:3], got[:3]):
-        torch.testing.assert_close(g_.float(), w_.float(), rtol=1e-5, atol=1e-6 * float(w_.float().abs().max()) + 1e-9)
+    # da is bf16: the two forms may round an element to neighbouring bf16 values (coefficients formed in fp32 vs fp64)
+    torch.testing.assert_close(got[0].float(), want[0].float(), rtol=8e-3, atol=1e-5 * float(want[0].float().abs().max()))
+    assert float((got[0].float() != want[0].float()).float().mean()) < 1e-3
+    for w_, g_ in zip(want[1:3], got[1:3]):
+        torch.testing.assert_close(g_.float(), w_.float(), rtol=1e-4, atol=1e-5 * float(w_.float().abs().max()) + 1e-9)
     if want_dv:
         assert torch.equal(got[3], want[3])

@@ -119,3 +119,61 @@ def test_fused_masking_equals_the_materialised_chain_through_the_public_api(pkg,
     assert ca["c8_to_nchw"] == 1 and ca["nchw_to_c8"] == 2, ca
     assert cb["c8_to_nchw"] == 0 and cb["nchw_to_c8"] == 1, cb
     assert zb.requires_grad is False and tuple(mb.shape) == ((8, 128, 1, 1) if which == "image" else (8, 1, 14, 14))
+
+
+def test_saliency_pass_reuses_the_clean_pass_forward(pkg):
+    """hard_example_generation differentiates decoder(code) where `code` is the latent the clean pass has just decoded:
+    with set_reuse_forward(True) (default) that forward is taken from the tape -- two decoder forwards fewer per step --
+    and hard examples, BatchNorm buffers (the skipped forward's running-stat update is replayed) and the training
+    backward that follows are what recomputing gives."""
+    from cooperative_training_and_latent_space_data_augmentation_b200 import trainpath
+    torch.manual_seed(0)
+    solver = pkg.AdvancedTripletReconSegmentationModel('FCN_16_standard', num_classes=4)
+    for k, m in solver.model.items():
+        m.load_state_dict(weights.synthetic_state_dict(m, 7, prefix=k + "."))
+    img, lab, noise = weights.synthetic_batch(8, 224, 224, seed=4)
+    img, lab, noise = img.cuda(), lab.cuda(), noise.cuda()
+    cfg_i = {"loss_name": "mse", "mask_type": "channel", "max_threshold": 0.5, "random_threshold": True, "if_soft": True}
+    cfg_s = {"loss_name": "ce", "mask_type": "spatial", "max_threshold": 0.5, "random_threshold": True, "if_soft": True}
+    state0 = {k: {n: b.clone() for n, b in m.named_buffers()} for k, m in solver.model.items()}
+    calls = {"n": 0}
+    orig = trainpath.decoder_fwd
+
+    def counted(*a, **kw):
+        calls["n"] += 1
+        return orig(*a, **kw)
+
+    out = {}
+    try:
+        trainpath.decoder_fwd = counted
+        for reuse in (False, True):
+            pkg.model_util.set_reuse_forward(reuse)
+            for k, m in solver.model.items():
+                for n, b in m.named_buffers():
+                    b.copy_(state0[k][n])
+            random.seed(3); np.random.seed(3); torch.manual_seed(3)
+            calls["n"] = 0
+            r = pkg.cooperative_step(solver, img, lab, cfg_i, cfg_s, noise=noise, optimize=False)
+            torch.cuda.synchronize()
+            out[reuse] = dict(
+                n=calls["n"], p_img=r['perturbed_image'].float().clone(), p_seg=r['perturbed_seg'].float().clone(),
+                loss=float(r['loss']), grads=solver.flat_adam.flat_grads.clone(),
+                buffers={k: {n: b.clone() for n, b in m.named_buffers()} for k, m in solver.model.items()})
+    finally:
+        trainpath.decoder_fwd = orig
+        pkg.model_util.set_reuse_forward(True)
+    a, b = out[False], out[True]
+    assert a["n"] - b["n"] == 2, (a["n"], b["n"])                    # image decoder + segmentation decoder
+    for key in ("p_img", "p_seg"):
+        d = (a[key] - b[key]).flatten(1).norm(dim=1) / a[key].flatten(1).norm(dim=1)
+        assert float(d.max()) < 1e-3, (key, d.tolist())
+    assert abs(a["loss"] - b["loss"]) <= 1e-4 * abs(a["loss"])
+    cos = torch.nn.functional.cosine_similarity(a["grads"].double(), b["grads"].double(), dim=0)
+    assert float(cos) > 0.9999, float(cos)
+    for k in a["buffers"]:
+        for n, v in a["buffers"][k].items():
+            w = b["buffers"][k][n]
+            if n.endswith("num_batches_tracked"):
+                assert int(v) == int(w), (k, n, int(v), int(w))
+            else:
+                torch.testing.assert_close(w, v, rtol=1e-4, atol=1e-6, msg=lambda m_, k=k, n=n: "%s.%s: %s" % (k, n, m_))
