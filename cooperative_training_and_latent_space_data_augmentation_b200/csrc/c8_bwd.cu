@@ -998,3 +998,21 @@ extern "C" int ctl_stem_dgrad_c8(const void* dy, const float* x, int in_mode, fl
   CTL_CUDA_OK(cudaGetLastError(), "stem_dgrad launch");
   return CTL_OK;
 }
+
+extern "C" int ctl_bn_bwd_apply_totals_c8(const void* dy, const void* a, int64_t N, int64_t C, int64_t H, int64_t W, int act,
+                                          const float* mean, const float* var, float eps, const float* gamma,
+                                          const double* totals, void* da, float* dgamma, float* dbeta,
+                                          const float* act_scale, const float* act_shift, void* stream) {
+  if (int rc = check_c8("ctl_bn_bwd_apply_totals_c8", dy, a, N, C, H, W)) return rc;
+  CTL_REQUIRE(mean && var && totals && da && act_scale && act_shift, CTL_ERR_INVALID, "ctl_bn_bwd_apply_totals_c8: NULL pointer");
+  CTL_REQUIRE(C <= kMaxBnC, CTL_ERR_UNSUPPORTED, "ctl_bn_bwd_apply_totals_c8: at most %d channels", kMaxBnC);
+  if (sm_count() < 0) return CTL_ERR_CUDA;
+  const int64_t HW = H * W, total = N * (C / 8) * HW;
+  const BnBwdTotals bt = {totals, mean, var, gamma, dgamma, dbeta, (double)(N * HW), eps};
+  const unsigned apply_grid = (unsigned)std::min<int64_t>(ceil_div(total, kT), (int64_t)sm_count() * 6);
+  launch_chained(bn_bwd_apply_kernel, apply_grid, kT, 0, (cudaStream_t)stream)((const uint4*)dy, nullptr, (const uint4*)a, nullptr,
+                                                                              (uint4*)da, total, (int)(C / 8), HW, act,
+                                                                              act_scale, act_shift, bt);
+  CTL_CUDA_OK(cudaGetLastError(), "bn_bwd apply launch");
+  return CTL_OK;
+}

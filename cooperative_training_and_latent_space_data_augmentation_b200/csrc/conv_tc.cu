@@ -69,6 +69,9 @@ struct ConvParams {
                                       // [N][H*W] (spatial mode: sum over channels) of the bf16-rounded outputs, accumulated into
   int sal_mode;                       // ctl_mode
   int no_store;                       // 1: the output tensor is not written (only the saliency sums are wanted)
+  int bnb_act;                        // != 0: BatchNorm-backward statistics mode (see conv_epilogue<.., BNB>): `res` is the
+                                      // BatchNorm INPUT a of the layer this output gradient flows into, res_scale / res_shift
+                                      // its forward affine, bnb_act its activation; stats receives sum dv | sum dv*a
   int diag;                           // profiling only (env CTL_DIAG_SKIP): 1 no MMA, 2 no TMA loads, 4 no epilogue memory traffic, 8 no epilogue
 };
 
@@ -111,7 +114,11 @@ struct ConvCfg {
 // as a batch: every residual pixel of the tile is requested BEFORE the accumulator wait (the addresses do not depend on
 // it), the TMEM loads of two items are issued back to back behind one tcgen05.wait::ld, and the accumulator stage is
 // handed back to the MMA issuer as soon as the last load has landed in registers -- before the arithmetic and stores.
-template <int CIN, int NT, int TAPS, int MT, int STAGES, bool VP, bool RES, bool STATS, bool GEN, bool SAL = false>
+// BNB (with RES and STATS): the output is an activation gradient dy that feeds the backward of h = act(BN(a)); the
+// epilogue reads a at the output's own pixels (through the residual path, current tile only) and accumulates
+// sum dv and sum dv*a with dv = dy * act'(a*scale + shift) -- the BatchNorm-backward reduction without a pass of its own.
+template <int CIN, int NT, int TAPS, int MT, int STAGES, bool VP, bool RES, bool STATS, bool GEN, bool SAL = false,
+          bool BNB = false>
 __device__ __forceinline__ void conv_epilogue(const ConvParams& p, const uint32_t tmem_base, const float* sVec,
                                               uint64_t* acc_full, uint64_t* acc_empty, const int n0, float* stat_smem,
                                               float4* xbuf) {
@@ -189,16 +196,19 @@ __device__ __forceinline__ void conv_epilogue(const ConvParams& p, const uint32_
     }
   };
 
-  uint4 rr[RES ? kPer : 1][2], rr_next[RES ? kPer : 1][2];
+  uint4 rr[RES ? kPer : 1][2], rr_next[(RES && !BNB) ? kPer : 1][2];
   Geo geo = geometry(blockIdx.x);
-  if (has_res) request_residual(geo, rr);
+  if (has_res && !BNB) request_residual(geo, rr);
   for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
     const int t_next = t + gridDim.x;
     Geo geo_next = geo;
     if (t_next < num_tiles) {
       geo_next = geometry(t_next);
-      if (has_res) request_residual(geo_next, rr_next);
+      if constexpr (!BNB) {
+        if (has_res) request_residual(geo_next, rr_next);
+      }
     }
+    if constexpr (BNB) request_residual(geo, rr);       // the 32 running sums leave no room for a second tile in flight
 
     mbar_wait(&acc_full[acc], acc_phase);
     tc_fence_after();
@@ -290,7 +300,7 @@ __device__ __forceinline__ void conv_epilogue(const ConvParams& p, const uint32_
               f[4 * i4 + 2] = fmaf(__uint_as_float(v[b][4 * i4 + 2]), sc.z, sh.z);
               f[4 * i4 + 3] = fmaf(__uint_as_float(v[b][4 * i4 + 3]), sc.w, sh.w);
             }
-            if (has_res) {
+            if (has_res && !BNB) {
 #pragma unroll
               for (int h8 = 0; h8 < 2; ++h8) {
                 const uint4 r4 = rr[RES ? u : 0][h8];
@@ -320,11 +330,25 @@ __device__ __forceinline__ void conv_epilogue(const ConvParams& p, const uint32_
               for (int i = 0; i < 4; ++i) {
                 const __nv_bfloat162 hh = __floats2bfloat162_rn(f[8 * h8 + 2 * i], f[8 * h8 + 2 * i + 1]);
                 o[i] = *reinterpret_cast<const uint32_t*>(&hh);
-                if (STATS) {
+                if (STATS && !BNB) {
                   const float lo = __uint_as_float(o[i] << 16), hi = __uint_as_float(o[i] & 0xffff0000u);
                   const int c = 8 * h8 + 2 * i;
                   st_s[STATS ? c : 0] += lo;      st_q[STATS ? c : 0] = fmaf(lo, lo, st_q[STATS ? c : 0]);
                   st_s[STATS ? c + 1 : 0] += hi;  st_q[STATS ? c + 1 : 0] = fmaf(hi, hi, st_q[STATS ? c + 1 : 0]);
+                }
+                if (STATS && BNB) {
+                  // dv = dy * act'(a*scale + shift) on the STORED (bf16) dy, as the stand-alone reduction reads it
+                  const uint4 a4 = rr[RES ? u : 0][h8];
+                  const uint32_t aw = i == 0 ? a4.x : i == 1 ? a4.y : i == 2 ? a4.z : a4.w;
+                  const int c = 8 * h8 + 2 * i;
+                  const float a_lo = __uint_as_float(aw << 16), a_hi = __uint_as_float(aw & 0xffff0000u);
+                  const float p_lo = fmaf(a_lo, sVec[2 * NT + c0 + c], sVec[3 * NT + c0 + c]);
+                  const float p_hi = fmaf(a_hi, sVec[2 * NT + c0 + c + 1], sVec[3 * NT + c0 + c + 1]);
+                  const float neg = p.bnb_act == CTL_ACT_LRELU ? 0.2f : (p.bnb_act == CTL_ACT_RELU ? 0.0f : 1.0f);
+                  const float lo = __uint_as_float(o[i] << 16) * (p_lo > 0.0f ? 1.0f : neg);
+                  const float hi = __uint_as_float(o[i] & 0xffff0000u) * (p_hi > 0.0f ? 1.0f : neg);
+                  st_s[STATS ? c : 0] += lo;      st_q[STATS ? c : 0] = fmaf(lo, a_lo, st_q[STATS ? c : 0]);
+                  st_s[STATS ? c + 1 : 0] += hi;  st_q[STATS ? c + 1 : 0] = fmaf(hi, a_hi, st_q[STATS ? c + 1 : 0]);
                 }
               }
               if (SAL) {
@@ -362,7 +386,7 @@ __device__ __forceinline__ void conv_epilogue(const ConvParams& p, const uint32_
     }
     if (++acc == kAccStages) { acc = 0; acc_phase ^= 1; }
     geo = geo_next;
-    if (RES) {
+    if (RES && !BNB) {
 #pragma unroll
       for (int u = 0; u < kPer; ++u) { rr[u][0] = rr_next[u][0]; rr[u][1] = rr_next[u][1]; }
     }
@@ -525,11 +549,15 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap, const ConvParams p) {
     float4* xbuf = reinterpret_cast<float4*>(smem + Cfg::kOffX);
 #define CTL_EPI(RES_, STATS_, GEN_, SAL_) \
     conv_epilogue<CIN, NT, TAPS, MT, STAGES, VP, RES_, STATS_, GEN_, SAL_>(p, tmem_base, sVec, acc_full, acc_empty, n0, stat_smem, xbuf)
+#define CTL_EPI_BNB() \
+    conv_epilogue<CIN, NT, TAPS, MT, STAGES, VP, true, true, false, false, true>(p, tmem_base, sVec, acc_full, acc_empty, n0, stat_smem, xbuf)
     if constexpr (TAPS == 9 && !VP && CIN == 128) {
       CTL_EPI(true, false, true, false);           // unpacked 3x3 with 128 input channels: only the stride-2 form runs here
     } else {
       if (p.up2x || p.subsample != 1) {
         if constexpr (!VP) CTL_EPI(true, false, true, false);
+      } else if (p.bnb_act != 0) {
+        if constexpr (TAPS == 9 && !VP && NT <= 32 && CIN <= 64) CTL_EPI_BNB();
       } else if (p.res != nullptr && p.sal != nullptr) {
         if constexpr ((CIN == 64 || CIN == 128) && TAPS == 1)   // the last input-gradient convolution of a decoder (up1: 1x1)
           CTL_EPI(true, false, false, true);
@@ -542,6 +570,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmap, const ConvParams p) {
       }
     }
 #undef CTL_EPI
+#undef CTL_EPI_BNB
   }
 
   tc_fence_before();
@@ -672,7 +701,8 @@ extern "C" int ctl_conv2d_n_tile(int Cin, int Cout, int taps) {
 static int conv2d_c8_impl(const void* x, int64_t N, int64_t H, int64_t W, int64_t Cin, const void* w_packed,
                           int64_t Cout, int taps, int subsample, int up2x, const float* scale,
                           const float* shift, const void* res, const float* res_scale, const float* res_shift,
-                          int act, void* out, double* stats, double* sal, int sal_mode, int store_out, void* stream) {
+                          int act, void* out, double* stats, double* sal, int sal_mode, int store_out, void* stream,
+                          int bnb_act = 0) {
   CTL_REQUIRE(x && w_packed && (out || (sal && !store_out)), CTL_ERR_INVALID, "ctl_conv2d_c8_bf16: NULL pointer");
   CTL_REQUIRE(!up2x || (taps == 1 && subsample == 1 && Cout % 32 == 0), CTL_ERR_INVALID,
               "up2x (ConvTranspose2d k2 s2) needs taps == 1, subsample == 1 and Cout = 4 * out_channels, out_channels %% 8 == 0");
@@ -685,8 +715,11 @@ static int conv2d_c8_impl(const void* x, int64_t N, int64_t H, int64_t W, int64_
   const int nt = ctl_conv2d_n_tile((int)Cin, (int)Cout, taps);
   CTL_REQUIRE(stats == nullptr || (nt > 0 && nt <= 32 && !up2x), CTL_ERR_UNSUPPORTED,
               "fused output statistics need an N tile <= 32 (Cout %% 64 != 0 or 3x3 with Cin 128) and no up2x");
-  CTL_REQUIRE(stats == nullptr || res == nullptr, CTL_ERR_UNSUPPORTED,
+  CTL_REQUIRE(stats == nullptr || res == nullptr || bnb_act != 0, CTL_ERR_UNSUPPORTED,
               "ctl_conv2d_c8_bf16: fused output statistics and a residual input cannot be combined");
+  CTL_REQUIRE(bnb_act == 0 || (taps == 9 && subsample == 1 && !up2x && Cin <= 64 && stats && res && res_scale && res_shift &&
+                               (bnb_act == CTL_ACT_LRELU || bnb_act == CTL_ACT_RELU)),
+              CTL_ERR_UNSUPPORTED, "fused BatchNorm-backward statistics: 3x3 stride-1 convolutions with Cin <= 64 and an N tile <= 32");
   CTL_REQUIRE(N * ((H + 13) / 14) * ((W + 7) / 8) < (int64_t)1 << 31, CTL_ERR_INVALID, "ctl_conv2d_c8_bf16: too many tiles");
   CTL_REQUIRE(nt > 0, CTL_ERR_UNSUPPORTED,
               "ctl_conv2d_c8_bf16 handles Cin in {16,32,64,128} and Cout %% 16 == 0 (got Cin=%lld Cout=%lld)",
@@ -700,6 +733,7 @@ static int conv2d_c8_impl(const void* x, int64_t N, int64_t H, int64_t W, int64_
   p.scale = scale; p.shift = shift;
   p.res = (const __nv_bfloat16*)res; p.res_scale = res_scale; p.res_shift = res_shift;
   p.out = (__nv_bfloat16*)out; p.act = act; p.subsample = subsample; p.up2x = up2x; p.stats = stats;
+  p.bnb_act = bnb_act;
   if (sal != nullptr) {
     CTL_REQUIRE((Cin == 64 || Cin == 128) && taps == 1 && res != nullptr && stats == nullptr && subsample == 1 && !up2x,
                 CTL_ERR_UNSUPPORTED,
@@ -740,4 +774,12 @@ extern "C" int ctl_conv2d_c8_bf16_saliency(const void* x, int64_t N, int64_t H, 
   CTL_REQUIRE(sal_sums != nullptr, CTL_ERR_INVALID, "ctl_conv2d_c8_bf16_saliency: NULL saliency buffer");
   return conv2d_c8_impl(x, N, H, W, Cin, w_packed, Cout, 1, 1, 0, nullptr, nullptr, res, nullptr, nullptr, CTL_ACT_NONE, out,
                         nullptr, sal_sums, sal_mode, store_out, stream);
+}
+
+extern "C" int ctl_conv2d_c8_bf16_bnbwd(const void* x, int64_t N, int64_t H, int64_t W, int64_t Cin, const void* w_packed,
+                                        int64_t Cout, const void* bn_a, const float* bn_scale, const float* bn_shift,
+                                        int bn_act, void* out, double* totals, void* stream) {
+  CTL_REQUIRE(bn_a && bn_scale && bn_shift && totals, CTL_ERR_INVALID, "ctl_conv2d_c8_bf16_bnbwd: NULL pointer");
+  return conv2d_c8_impl(x, N, H, W, Cin, w_packed, Cout, 9, 1, 0, nullptr, nullptr, bn_a, bn_scale, bn_shift, CTL_ACT_NONE, out,
+                        totals, nullptr, 0, 1, stream, bn_act);
 }

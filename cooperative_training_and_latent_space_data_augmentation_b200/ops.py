@@ -999,3 +999,45 @@ def sse_grad(pred, target, scale):
     with torch.cuda.device(x.device):
         _lib.check(_lib.load().ctl_sse_bwd(x.data_ptr(), t.data_ptr(), x.numel(), float(scale), 0, dx.data_ptr(), _stream()))
     return dx
+
+
+# ------------------------------------------------------------------------------------------------ BN-backward reduction in the dgrad
+def conv_bnbwd_fusable(cin, cout):
+    """True when the 3x3 stride-1 convolution cin -> cout (packed-view channels of an input-gradient convolution) can
+    accumulate the BatchNorm-backward sums of the layer its output flows into (ctl_conv2d_c8_bf16_bnbwd)."""
+    lib = _lib.load()
+    return (cin <= 64 and not lib.ctl_conv2d_vpacked(int(cin), int(cout), 9, 1)
+            and 0 < lib.ctl_conv2d_n_tile(int(cin), int(cout), 9) <= 32)
+
+
+def conv2d_c8_bnbwd(x, w_packed, cout, bn_a, bn_scale, bn_shift, bn_act, totals):
+    """out = conv3x3(x) (an activation gradient) + the BatchNorm-backward sums of h = act(BN(bn_a)) accumulated into
+    `totals` (zeroed float64 [2*cout]) by the epilogue."""
+    _need_cuda(x, w_packed, bn_a, bn_scale, bn_shift, totals)
+    N, cin, H, W = _c8_dims(x)
+    if tuple(bn_a.shape) != (N, cout // 8, H, W, 8):
+        raise ValueError("bn_a must be the C8 tensor of the output's shape")
+    sc, sh = _vec(bn_scale, cout), _vec(bn_shift, cout)
+    out = torch.empty((N, cout // 8, H, W, 8), device=x.device, dtype=torch.bfloat16)
+    with torch.cuda.device(x.device):
+        _lib.check(_lib.load().ctl_conv2d_c8_bf16_bnbwd(x.data_ptr(), N, H, W, cin, w_packed.data_ptr(), cout, bn_a.data_ptr(),
+                                                        sc.data_ptr(), sh.data_ptr(), int(bn_act), out.data_ptr(),
+                                                        totals.data_ptr(), _stream()))
+    return out
+
+
+def bn_bwd_apply_totals_c8(dy, a, act, mean, var, eps, gamma, totals, act_affine, want_param_grads=True):
+    """The apply pass of the BatchNorm + activation backward from per-channel totals (sum dv | sum dv*a) that a
+    convolution epilogue (conv2d_c8_bnbwd) or the stand-alone reduction left in `totals`.  Returns (da, dgamma, dbeta)."""
+    _need_cuda(dy, a, mean, var, gamma, totals)
+    N, C, H, W = _c8_dims(a)
+    sc, sh = _vec(act_affine[0], C), _vec(act_affine[1], C)
+    pg = torch.empty((2, C), device=a.device, dtype=torch.float32) if want_param_grads else None
+    g = _vec(gamma, C)
+    da = torch.empty_like(a)
+    with torch.cuda.device(a.device):
+        _lib.check(_lib.load().ctl_bn_bwd_apply_totals_c8(
+            dy.data_ptr(), a.data_ptr(), N, C, H, W, act, mean.data_ptr(), var.data_ptr(), float(eps), _ptr(g),
+            totals.data_ptr(), da.data_ptr(), pg[0].data_ptr() if pg is not None else 0,
+            pg[1].data_ptr() if pg is not None else 0, sc.data_ptr(), sh.data_ptr(), _stream()))
+    return da, (pg[0] if pg is not None else None), (pg[1] if pg is not None else None)

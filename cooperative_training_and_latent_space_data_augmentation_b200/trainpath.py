@@ -103,6 +103,20 @@ def _dgrad(conv, dy, res=None):
     return ops.conv2d_c8(dy, wp, conv.in_channels, k * k, res=res)
 
 
+def _dgrad_into_bn(grads, conv, dy, bn_saved, act):
+    """Input gradient of the stride-1 3x3 `conv` whose result flows into the backward of act(BatchNorm(a)) of the layer
+    in front of it (`bn_saved` = that layer's forward record).  Where the kernel allows it the BatchNorm-backward sums
+    are accumulated by the convolution's epilogue (no reduction pass over dy and a): returns (dh, totals or None)."""
+    a, scale, shift = bn_saved[1], bn_saved[5], bn_saved[6]
+    if (conv.kernel_size[0] == 3 and act in (ops.ACT_LRELU, ops.ACT_RELU)
+            and ops.conv_bnbwd_fusable(conv.out_channels, conv.in_channels)):
+        totals = grads.bn_totals(conv.in_channels)
+        if totals is not None:
+            wp = _packed(conv.weight, ops.pack_conv_weight_dgrad, tag='dgrad')
+            return ops.conv2d_c8_bnbwd(dy, wp, conv.in_channels, a, scale, shift, act, totals), totals
+    return _dgrad(conv, dy), None
+
+
 def _wgrad(grads, conv, x, dy):
     """K3w straight into nn.Conv2d's [Cout][Cin][k][k] layout, accumulated into a slice of the backward's zero arena."""
     k = conv.kernel_size[0]
@@ -288,15 +302,30 @@ def conv_bn_act_fwd(fw, conv, bn, x, act):
     return h, (x, a, h, mean, var, scale, shift)
 
 
-def conv_bn_act_bwd(conv, bn, act, saved, dh, grads, need_dx=True):
+def _bn_act_bwd(bn, act, saved, dh, grads, totals=None):
+    """da, with the BatchNorm parameter gradients recorded; `totals`: the sums already accumulated by the convolution
+    that produced dh (then only the apply pass runs)."""
     x, a, h, mean, var, scale, shift = saved
-    # act'(h) from sign(a*scale + shift): the backward never reads h (it stays alive only as the next layer's input)
-    da, dg, db, _ = ops.bn_act_bwd_c8(dh, h, a, act, mean, var, bn.eps, bn.weight, act_affine=(scale, shift),
-                                      totals=grads.bn_totals(a.shape[1] * 8))
+    if totals is not None:
+        da, dg, db = ops.bn_bwd_apply_totals_c8(dh, a, act, mean, var, bn.eps, bn.weight, totals, (scale, shift))
+    else:
+        # act'(h) from sign(a*scale + shift): the backward never reads h (it stays alive only as the next layer's input)
+        da, dg, db, _ = ops.bn_act_bwd_c8(dh, h, a, act, mean, var, bn.eps, bn.weight, act_affine=(scale, shift),
+                                          totals=grads.bn_totals(a.shape[1] * 8))
     grads.add(bn.weight, dg)
     grads.add(bn.bias, db)
+    return da
+
+
+def conv_bn_act_bwd(conv, bn, act, saved, dh, grads, need_dx=True, totals=None, next_bn=None):
+    """next_bn = (forward record, activation) of the conv-BN-act layer in FRONT of this one: its BatchNorm-backward sums
+    are then accumulated by this layer's input-gradient convolution; returns (dx, totals for that layer) in that case."""
+    x = saved[0]
+    da = _bn_act_bwd(bn, act, saved, dh, grads, totals)
     if grads.wants(conv.weight):
         grads.add(conv.weight, _wgrad(grads, conv, x, da))
+    if next_bn is not None:
+        return _dgrad_into_bn(grads, conv, da, next_bn[0], next_bn[1]) if need_dx else (None, None)
     return _dgrad(conv, da) if need_dx else None
 
 
@@ -346,13 +375,9 @@ def residual_bwd(block, saved, dout, grads, x_low=None):
     # conv2
     if grads.wants(seq[3].weight):
         grads.add(seq[3].weight, _wgrad(grads, seq[3], h1, da2))
-    dh1 = _dgrad(seq[3], da2)
+    dh1, totals1 = _dgrad_into_bn(grads, seq[3], da2, s1, LRELU)
     # BN1 + LReLU + conv1
-    x, a1, h1_, mean1, var1, scale1, shift1 = s1
-    da1, dg1, db1, _ = ops.bn_act_bwd_c8(dh1, h1_, a1, LRELU, mean1, var1, seq[1].eps, seq[1].weight,
-                                         act_affine=(scale1, shift1), totals=grads.bn_totals(a1.shape[1] * 8))
-    grads.add(seq[1].weight, dg1)
-    grads.add(seq[1].bias, db1)
+    da1 = _bn_act_bwd(seq[1], LRELU, s1, dh1, grads, totals1)
     if grads.wants(seq[0].weight):
         grads.add(seq[0].weight, _wgrad(grads, seq[0], xr, da1))
     return _dgrad(seq[0], da1, res=dxr), dc
@@ -365,17 +390,20 @@ def down_fwd(fw, block, x):
     return out, (x, s)
 
 
-def down_bwd(block, saved, dout, grads, need_dx=True):
+def down_bwd(block, saved, dout, grads, need_dx=True, next_bn=None):
+    """next_bn: see conv_bn_act_bwd (the block's input is the output of a conv-BN-act layer); returns (dx, totals) then."""
     x, s = saved
     dxd, _ = residual_bwd(block, s, dout, grads)
     down = block.down
     want_w = grads.wants(down.weight)
     if not (want_w or need_dx):
-        return None
+        return (None, None) if next_bn is not None else None
     dyz = ops.zero_stuff2x_c8(dxd)                          # the stride-2 output gradient seen at full resolution
     if want_w:
         grads.add(down.weight, _wgrad(grads, down, x, dyz))
         grads.add(down.bias, ops.channel_sum_c8(dxd))
+    if next_bn is not None:
+        return _dgrad_into_bn(grads, down, dyz, next_bn[0], next_bn[1]) if need_dx else (None, None)
     return _dgrad(down, dyz) if need_dx else None
 
 
@@ -475,14 +503,14 @@ def encoder_fwd(enc, x, in_mode, temperature):
 def encoder_bwd(enc, tape, dz, grads, x, in_mode, temperature, need_dx):
     inc = enc.inc
     d = conv_bn_act_bwd(enc.final_conv[0], enc.final_conv[1], _act_code(enc.act), tape[6], dz, grads)
-    for i, blk in zip((5, 4, 3, 2), (enc.down4, enc.down3, enc.down2, enc.down1)):
+    for i, blk in zip((5, 4, 3), (enc.down4, enc.down3, enc.down2)):
         d = down_bwd(blk, tape[i], d, grads)
-    dh0 = conv_bn_act_bwd(inc[3], inc[4], LRELU, tape[1], d, grads)
+    # the 224^2 level: every input-gradient convolution accumulates the BatchNorm-backward sums of the layer in front
+    d, t4 = down_bwd(enc.down1, tape[2], d, grads, next_bn=(tape[1], LRELU))
     a0, h0, mean0, var0, scale0, shift0, xin = tape[0]
-    da0, dg0, db0, _ = ops.bn_act_bwd_c8(dh0, h0, a0, LRELU, mean0, var0, inc[1].eps, inc[1].weight,
-                                         act_affine=(scale0, shift0), totals=grads.bn_totals(a0.shape[1] * 8))
-    grads.add(inc[1].weight, dg0)
-    grads.add(inc[1].bias, db0)
+    rec0 = (xin, a0, h0, mean0, var0, scale0, shift0)
+    dh0, t1 = conv_bn_act_bwd(inc[3], inc[4], LRELU, tape[1], d, grads, totals=t4, next_bn=(rec0, LRELU))
+    da0 = _bn_act_bwd(inc[1], LRELU, rec0, dh0, grads, t1)
     if grads.wants(inc[0].weight):
         # K3w on the 16-channel stem input; the gradient of the real input channels is the leading slice
         dW16 = ops.conv_wgrad_c8(xin, da0, 9, layout='conv')

@@ -244,6 +244,18 @@ int ctl_bn_bwd_apply_c8(const void* dy, const void* h, const void* a, int64_t N,
 int ctl_bn_bwd_c8(const void* dy, const void* h, const void* a, int64_t N, int64_t C, int64_t H, int64_t W, int act,
                   const float* mean, const float* var, float eps, const float* gamma, double* totals, void* dv_out, void* da,
                   float* dgamma, float* dbeta, const float* act_scale, const float* act_shift, void* stream);
+/* The BatchNorm-backward REDUCTION fused into the convolution that produces dy (3x3, stride 1, Cin <= 64, N tile <= 32,
+ * vertically-unpacked layers): out = conv(x) is an activation gradient that flows into the backward of
+ * h = act(BatchNorm(bn_a)); the epilogue reads bn_a at the output's pixels and accumulates totals[0][c] += sum dv,
+ * totals[1][c] += sum dv * bn_a with dv = out * act'(bn_a * bn_scale + bn_shift) (double [2][Cout], zeroed by the caller;
+ * bn_act = CTL_ACT_LRELU | CTL_ACT_RELU).  ctl_bn_bwd_apply_totals_c8 is the apply pass of ctl_bn_bwd_c8 alone. */
+int ctl_conv2d_c8_bf16_bnbwd(const void* x, int64_t N, int64_t H, int64_t W, int64_t Cin, const void* w_packed, int64_t Cout,
+                             const void* bn_a, const float* bn_scale, const float* bn_shift, int bn_act, void* out,
+                             double* totals, void* stream);
+int ctl_bn_bwd_apply_totals_c8(const void* dy, const void* a, int64_t N, int64_t C, int64_t H, int64_t W, int act,
+                               const float* mean, const float* var, float eps, const float* gamma, const double* totals,
+                               void* da, float* dgamma, float* dbeta, const float* act_scale, const float* act_shift,
+                               void* stream);
 /* dv = dy * act'(h) */
 int ctl_act_bwd_c8(const void* dy, const void* h, int64_t N, int64_t C, int64_t H, int64_t W, int act, void* dv,
                    void* stream);

@@ -271,3 +271,31 @@ def test_bn_backward_totals_form_equals_the_three_launch_form(ops, C, H, W, want
         torch.testing.assert_close(g_.float(), w_.float(), rtol=1e-4, atol=1e-5 * float(w_.float().abs().max()) + 1e-9)
     if want_dv:
         assert torch.equal(got[3], want[3])
+
+
+@pytest.mark.parametrize("cin,cout,H,W,act", [(16, 16, 42, 40, 1), (32, 32, 28, 24, 1), (64, 32, 14, 16, 2), (16, 32, 30, 8, 1)])
+def test_dgrad_epilogue_accumulates_the_bn_backward_sums(ops, cin, cout, H, W, act):
+    """ctl_conv2d_c8_bf16_bnbwd: the convolution's output is bit-identical to the plain kernel's, and the totals its
+    epilogue leaves (sum dv | sum dv*a, dv = dy * act'(a*scale + shift)) equal the stand-alone reduction's on that output;
+    the apply pass from those totals reproduces the three-launch backward."""
+    assert ops.conv_bnbwd_fusable(cin, cout)
+    g = torch.Generator(device="cuda").manual_seed(cin + cout + H)
+    N = 3
+    x = ops.nchw_to_c8(torch.randn(N, cin, H, W, device="cuda", generator=g) * 0.1)
+    wp = ops.pack_conv_weight(torch.randn(cout, cin, 3, 3, device="cuda", generator=g) * 0.1)
+    a = ops.nchw_to_c8(torch.randn(N, cout, H, W, device="cuda", generator=g))
+    gamma = 1 + 0.2 * torch.randn(cout, device="cuda", generator=g)
+    beta = 0.3 * torch.randn(cout, device="cuda", generator=g)
+    scale, shift, mean, var = ops.bn_batch_affine_c8(a, gamma, beta, 1e-5, want_stats=True)
+    dy_plain = ops.conv2d_c8(x, wp, cout, 9)
+    totals = torch.zeros(2 * cout, device="cuda", dtype=torch.float64)
+    dy = ops.conv2d_c8_bnbwd(x, wp, cout, a, scale, shift, act, totals)
+    assert torch.equal(dy, dy_plain)
+    want_tot = torch.zeros(2 * cout, device="cuda", dtype=torch.float64)
+    want = ops.bn_act_bwd_c8(dy_plain, None, a, act, mean, var, 1e-5, gamma, act_affine=(scale, shift), totals=want_tot)
+    torch.testing.assert_close(totals, want_tot, rtol=1e-5, atol=1e-7 * float(want_tot.abs().max()))
+    da, dg, db = ops.bn_bwd_apply_totals_c8(dy, a, act, mean, var, 1e-5, gamma, totals, (scale, shift))
+    torch.testing.assert_close(da.float(), want[0].float(), rtol=8e-3, atol=1e-5 * float(want[0].float().abs().max()))
+    torch.testing.assert_close(dg, want[1], rtol=1e-4, atol=1e-5 * float(want[1].abs().max()))
+    torch.testing.assert_close(db, want[2], rtol=1e-4, atol=1e-5 * float(want[2].abs().max()))
+    assert not ops.conv_bnbwd_fusable(128, 16) and not ops.conv_bnbwd_fusable(16, 64)
