@@ -152,28 +152,56 @@ struct SelectArgs {
 // fp64 accumulation in four independent chains, shuffle reduction.  No barriers, no fences.
 // ------------------------------------------------------------------------------------------------
 template <typename T, int VEC, int L>
-__global__ void __launch_bounds__(kThreads, 4)
+__global__ void __launch_bounds__(kThreads, 2)
 saliency_channel_kernel(const T* __restrict__ g, float* __restrict__ s, int64_t rows, int HW, int nv) {
   pdl_launch_dependents();
   const int lane = threadIdx.x & (L - 1);
   const unsigned gmask = group_mask<L>();
-  const int64_t row = (int64_t)blockIdx.x * (kThreads / L) + threadIdx.x / L;
-  if (row >= rows) return;                             // group-uniform
-  const T* __restrict__ p = g + row * HW;
-  double acc[4] = {0.0, 0.0, 0.0, 0.0};
-  for (int base = 0; base < nv; base += kU * L) {
-    float a[kU][VEC];
-    load_batch<T, VEC, L>(p, base, lane, nv, a);
+  const int64_t ngroups = (int64_t)gridDim.x * (kThreads / L);
+  int64_t row = (int64_t)blockIdx.x * (kThreads / L) + threadIdx.x / L;
+  auto reduce_store = [&](const float (&a)[kU][VEC], double (&acc)[4], int64_t r, bool last) {
 #pragma unroll
     for (int j = 0; j < kU; ++j) {
 #pragma unroll
       for (int i = 0; i < VEC; ++i) acc[(j * VEC + i) & 3] += (double)a[j][i];
     }
-  }
-  double t = (acc[0] + acc[1]) + (acc[2] + acc[3]);
+    if (!last) return;
+    double t = (acc[0] + acc[1]) + (acc[2] + acc[3]);
 #pragma unroll
-  for (int o = L / 2; o > 0; o >>= 1) t += __shfl_xor_sync(gmask, t, o);
-  if (lane == 0) s[row] = (float)(t / (double)HW);
+    for (int o = L / 2; o > 0; o >>= 1) t += __shfl_xor_sync(gmask, t, o);
+    if (lane == 0) s[r] = (float)(t / (double)HW);
+  };
+  if (nv <= kU * L) {
+    // a row is one batch (the latent shapes of the model: 14x14, 16x16, 28x28): persistent groups stride over the rows
+    // with the NEXT row's 128-bit loads issued before the current row is reduced -- short-lived CTAs (one row per group)
+    // left the kernel at 3.8 TB/s
+    float cur[kU][VEC], nxt[kU][VEC];
+    if (row < rows) load_batch<T, VEC, L>(g + row * HW, 0, lane, nv, cur);
+    for (; row < rows; row += ngroups) {               // group-uniform
+      const int64_t rn = row + ngroups;
+      const bool more = rn < rows;
+      if (more) load_batch<T, VEC, L>(g + rn * HW, 0, lane, nv, nxt);
+      double acc[4] = {0.0, 0.0, 0.0, 0.0};
+      reduce_store(cur, acc, row, true);
+      if (more) {
+#pragma unroll
+        for (int j = 0; j < kU; ++j) {
+#pragma unroll
+          for (int i = 0; i < VEC; ++i) cur[j][i] = nxt[j][i];
+        }
+      }
+    }
+    return;
+  }
+  for (; row < rows; row += ngroups) {
+    const T* __restrict__ p = g + row * HW;
+    double acc[4] = {0.0, 0.0, 0.0, 0.0};
+    for (int base = 0; base < nv; base += kU * L) {
+      float a[kU][VEC];
+      load_batch<T, VEC, L>(p, base, lane, nv, a);
+      reduce_store(a, acc, row, base + kU * L >= nv);
+    }
+  }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -406,9 +434,8 @@ int launch_saliency_channel(const T* g, float* s, int64_t N, int C, int HW, cuda
   const int nv = HW / VEC;
   const int L = pick_lanes(nv);
   const int64_t rows = N * C;
-  const int64_t grid64 = ceil_div(rows, kThreads / L);
-  CTL_REQUIRE(grid64 <= 0x7fffffff, CTL_ERR_UNSUPPORTED, "too many rows for one launch");
-  const unsigned grid = (unsigned)grid64;
+  // persistent groups: two CTAs per SM stride over the rows (fewer when there are not that many rows)
+  const unsigned grid = (unsigned)std::max<int64_t>(1, std::min<int64_t>(ceil_div(rows, kThreads / L), (int64_t)sm_count() * 2));
   switch (L) {
     case 32: saliency_channel_kernel<T, VEC, 32><<<grid, kThreads, 0, st>>>(g, s, rows, HW, nv); break;
     case 16: saliency_channel_kernel<T, VEC, 16><<<grid, kThreads, 0, st>>>(g, s, rows, HW, nv); break;
