@@ -410,7 +410,9 @@ sums_select_apply_kernel(const double* __restrict__ sums, const float* __restric
   const float* __restrict__ zs = z + sample * (int64_t)C * HW;
   float* __restrict__ zo = z_out + sample * (int64_t)C * HW;
   const int groups = C >> 3;                                  // C % 8 == 0 (checked on the host)
-  for (int idx = threadIdx.x; idx < groups * HW; idx += blockDim.x) {
+  // gridDim.y CTAs share a sample: each repeats the (tiny, deterministic) selection -- they write identical s / mask / thr
+  // values -- and applies its share of the code; one CTA per sample left 84 of 148 SMs idle and took 34 us at [64,128,14,14]
+  for (int idx = blockIdx.y * blockDim.x + threadIdx.x; idx < groups * HW; idx += gridDim.y * blockDim.x) {
     const int gq = idx / HW, pix = idx - gq * HW;
     float v[8];
 #pragma unroll
@@ -675,12 +677,17 @@ extern "C" int ctl_saliency_sums_mask_apply(const double* sums, const float* z, 
   if (sm_count() < 0) return CTL_ERR_CUDA;
   cudaStream_t st = (cudaStream_t)stream;
   SelectArgs sa = {mask_out, thr_out, rand, PhiloxKey{seed, offset}, first_sample, (int)k, soft != 0, step_params};
+  // CTAs per sample: enough to put ~4 CTAs on every SM, at least ~2 apply iterations per thread
+  const int64_t work = (C / 8) * HW;
+  const unsigned parts = (unsigned)std::max<int64_t>(1, std::min<int64_t>(std::min<int64_t>(ceil_div((int64_t)sm_count() * 4, N),
+                                                                                         ceil_div(work, 2 * kThreads)), 32));
+  const dim3 grid((unsigned)N, parts);
   if (mode == CTL_MODE_CHANNEL)
-    sums_select_apply_kernel<CTL_MODE_CHANNEL><<<(unsigned)N, kThreads, 0, st>>>(sums, z, (int)C, (int)HW, sa, s_out, z_out,
-                                                                                 (__nv_bfloat16*)z_c8_out);
+    sums_select_apply_kernel<CTL_MODE_CHANNEL><<<grid, kThreads, 0, st>>>(sums, z, (int)C, (int)HW, sa, s_out, z_out,
+                                                                          (__nv_bfloat16*)z_c8_out);
   else
-    sums_select_apply_kernel<CTL_MODE_SPATIAL><<<(unsigned)N, kThreads, 0, st>>>(sums, z, (int)C, (int)HW, sa, s_out, z_out,
-                                                                                 (__nv_bfloat16*)z_c8_out);
+    sums_select_apply_kernel<CTL_MODE_SPATIAL><<<grid, kThreads, 0, st>>>(sums, z, (int)C, (int)HW, sa, s_out, z_out,
+                                                                          (__nv_bfloat16*)z_c8_out);
   CTL_CUDA_OK(cudaGetLastError(), "sums_select_apply launch");
   return CTL_OK;
 }
