@@ -61,6 +61,8 @@ SIGNATURES = {
     "ctl_conv2d_c8_bf16_bnbwd": (_i, [_vp, _i64, _i64, _i64, _i64, _vp, _i64, _vp, _vp, _vp, _i, _vp, _vp, _vp]),
     "ctl_bn_bwd_apply_totals_c8": (_i, [_vp, _vp, _i64, _i64, _i64, _i64, _i, _vp, _vp, _f, _vp, _vp, _vp, _vp, _vp, _vp, _vp,
                                         _vp]),
+    "ctl_bn_apply_from_sums_c8": (_i, [_vp, _i64, _i64, _i64, _i64, _vp, _vp, _vp, _f, _vp, _i, _vp, _vp, _vp, _vp, _vp, _vp,
+                                       _vp, _f, _vp]),
     "ctl_act_bwd_c8": (_i, [_vp, _vp, _i64, _i64, _i64, _i64, _i, _vp, _vp]),
     "ctl_downsample2x_sum_c8": (_i, [_vp, _i64, _i64, _i64, _i64, _vp, _vp]),
     "ctl_zero_stuff2x_c8": (_i, [_vp, _i64, _i64, _i64, _i64, _vp, _vp]),
@@ -96,7 +98,7 @@ KERNELS_PER_CALL = {"ctl_saliency_reduce": 1, "ctl_topp_mask_apply": 2, "ctl_sal
                     "ctl_stem_wgrad_c8": 1, "ctl_stem_dgrad_c8": 1, "ctl_ce2d_fwd": 1, "ctl_ce2d_bwd": 1, "ctl_scale_shift_upadd_act_c8": 1, "ctl_pack_conv_weights_batched": 1, "ctl_stem_input_c8": 1,
                     "ctl_adam_flat": 2, "ctl_sse_fwd": 1, "ctl_sse_bwd": 1, "ctl_confusion_update": 1,
                     "ctl_confusion_scores": 1, "ctl_conv2d_c8_bf16_saliency": 1, "ctl_saliency_sums_mask_apply": 1,
-                    "ctl_bn_bwd_c8": 2, "ctl_conv2d_c8_bf16_bnbwd": 1, "ctl_bn_bwd_apply_totals_c8": 1}
+                    "ctl_bn_bwd_c8": 2, "ctl_conv2d_c8_bf16_bnbwd": 1, "ctl_bn_bwd_apply_totals_c8": 1, "ctl_bn_apply_from_sums_c8": 1}
 LAUNCHES = {"count": 0}
 
 

@@ -218,17 +218,68 @@ upsample2x_c8_kernel(const uint4* __restrict__ x, uint4* __restrict__ y, int64_t
   }
 }
 
+// Train-mode BatchNorm finalisation folded into the kernel that applies it: when `sums` is given, every CTA forms
+// scale = gamma * rsqrt(var + eps), shift = beta - mean * scale for all C <= kMaxBnC channels in its prologue from the
+// per-channel fp64 sums the convolution epilogue accumulated (sum x | sum x^2) -- fp64 only for mean / variance (no fp64
+// division or square root) -- and CTA 0 also publishes scale / shift / mean / var for the backward and updates the
+// running statistics exactly like bn_fwd_from_sums_kernel.  No finalisation launch between the convolution and the apply.
+constexpr int kMaxBnC = 256;
+struct BnFwdSums {
+  const double* sums;          // [2][C] or nullptr (then scale / shift are read from global memory)
+  double inv_count, unbias;    // 1 / count, count / (count - 1)
+  const float* gamma;
+  const float* beta;
+  float* scale_out;
+  float* shift_out;
+  float* mean_out;
+  float* var_out;
+  float* running_mean;         // may be nullptr
+  float* running_var;
+  float eps, momentum;
+};
+
+__device__ __forceinline__ void bn_fwd_prologue(const BnFwdSums& bn, int C, float* s_scale, float* s_shift) {
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    const double mean = bn.sums[c] * bn.inv_count;
+    double var = bn.sums[C + c] * bn.inv_count - mean * mean;
+    if (var < 0.0) var = 0.0;
+    const float inv = 1.0f / sqrtf((float)var + bn.eps);
+    const float g = bn.gamma ? bn.gamma[c] : 1.0f, b = bn.beta ? bn.beta[c] : 0.0f;
+    const float sc = g * inv, sh = b - (float)mean * sc;
+    s_scale[c] = sc;
+    s_shift[c] = sh;
+    if (blockIdx.x == 0) {
+      bn.scale_out[c] = sc;
+      bn.shift_out[c] = sh;
+      if (bn.mean_out) bn.mean_out[c] = (float)mean;
+      if (bn.var_out) bn.var_out[c] = (float)var;
+      if (bn.running_mean) {
+        bn.running_mean[c] = (1.0f - bn.momentum) * bn.running_mean[c] + bn.momentum * (float)mean;
+        bn.running_var[c] = (1.0f - bn.momentum) * bn.running_var[c] + bn.momentum * (float)(var * bn.unbias);
+      }
+    }
+  }
+  __syncthreads();
+}
+
 // y = act(x*scale[c] + shift[c]), blocked -> blocked
 __global__ void __launch_bounds__(kT)
 scale_shift_act_c8_kernel(const uint4* __restrict__ x, uint4* __restrict__ y, const float* __restrict__ scale,
-                          const float* __restrict__ shift, int64_t total /*N*C8*HW*/, int C8, int64_t HW, int act) {
+                          const float* __restrict__ shift, int64_t total /*N*C8*HW*/, int C8, int64_t HW, int act,
+                          const BnFwdSums bn) {
   pdl_entry();
+  __shared__ float s_scale[kMaxBnC], s_shift[kMaxBnC];
+  if (bn.sums != nullptr) {
+    bn_fwd_prologue(bn, C8 * 8, s_scale, s_shift);
+    scale = s_scale;
+    shift = s_shift;
+  }
   for (int64_t i = (int64_t)blockIdx.x * kT + threadIdx.x; i < total; i += (int64_t)gridDim.x * kT) {
     const int c8 = (int)((i / HW) % C8);
     float f[8];
     unpack8(__ldcs(x + i), f);
 #pragma unroll
-    for (int j = 0; j < 8; ++j) f[j] = act_fn(f[j] * __ldg(scale + c8 * 8 + j) + __ldg(shift + c8 * 8 + j), act);
+    for (int j = 0; j < 8; ++j) f[j] = act_fn(f[j] * scale[c8 * 8 + j] + shift[c8 * 8 + j], act);
     y[i] = pack8(f);
   }
 }
@@ -239,8 +290,14 @@ scale_shift_act_c8_kernel(const uint4* __restrict__ x, uint4* __restrict__ y, co
 __global__ void __launch_bounds__(kT)
 scale_shift_upadd_act_c8_kernel(const uint4* __restrict__ x, const uint4* __restrict__ low, uint4* __restrict__ y,
                                 const float* __restrict__ scale, const float* __restrict__ shift, int64_t planes, int C8,
-                                int Hl, int Wl, int act) {
+                                int Hl, int Wl, int act, const BnFwdSums bn) {
   pdl_entry();
+  __shared__ float s_scale[kMaxBnC], s_shift[kMaxBnC];
+  if (bn.sums != nullptr) {
+    bn_fwd_prologue(bn, C8 * 8, s_scale, s_shift);
+    scale = s_scale;
+    shift = s_shift;
+  }
   const int64_t total = planes * Hl * Wl;
   for (int64_t i = (int64_t)blockIdx.x * kT + threadIdx.x; i < total; i += (int64_t)gridDim.x * kT) {
     const int64_t pl = i / ((int64_t)Hl * Wl);
@@ -251,8 +308,8 @@ scale_shift_upadd_act_c8_kernel(const uint4* __restrict__ x, const uint4* __rest
     unpack8(__ldg(low + i), lo);
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
-      sc[j] = scale ? __ldg(scale + c0 + j) : 1.0f;
-      sh[j] = (shift ? __ldg(shift + c0 + j) : 0.0f) + lo[j];
+      sc[j] = scale ? scale[c0 + j] : 1.0f;
+      sh[j] = (shift ? shift[c0 + j] : 0.0f) + lo[j];
     }
     const int64_t base = pl * 4 * Hl * Wl + (int64_t)(2 * yy) * (2 * Wl) + 2 * xx;
     const int64_t offs[4] = {base, base + 1, base + 2 * Wl, base + 2 * Wl + 1};
@@ -451,8 +508,42 @@ extern "C" int ctl_scale_shift_upadd_act_c8(const void* x, int64_t N, int64_t C,
   if (sm_count() < 0) return CTL_ERR_CUDA;
   const int64_t planes = N * (C / 8);
   launch_chained(scale_shift_upadd_act_c8_kernel, grid_for(planes * (H / 2) * (W / 2)), kT, 0, (cudaStream_t)stream)(
-      (const uint4*)x, (const uint4*)low, (uint4*)y, scale, shift, planes, (int)(C / 8), (int)(H / 2), (int)(W / 2), act);
+      (const uint4*)x, (const uint4*)low, (uint4*)y, scale, shift, planes, (int)(C / 8), (int)(H / 2), (int)(W / 2), act,
+      BnFwdSums{});
   CTL_CUDA_OK(cudaGetLastError(), "scale_shift_upadd_act launch");
+  return CTL_OK;
+}
+
+extern "C" int ctl_bn_apply_from_sums_c8(const void* x, int64_t N, int64_t C, int64_t H, int64_t W, const double* sums,
+                                         const float* gamma, const float* beta, float eps, const void* low, int act,
+                                         void* y, float* scale_out, float* shift_out, float* mean_out, float* var_out,
+                                         float* running_mean, float* running_var, float momentum, void* stream) {
+  CTL_REQUIRE(x && y && sums && scale_out && shift_out && N > 0 && C > 0 && C % 8 == 0 && C <= kMaxBnC && H > 0 && W > 0,
+              CTL_ERR_INVALID, "ctl_bn_apply_from_sums_c8: bad arguments (C a multiple of 8, at most %d)", kMaxBnC);
+  CTL_REQUIRE(!low || (H % 2 == 0 && W % 2 == 0), CTL_ERR_INVALID, "ctl_bn_apply_from_sums_c8: H and W must be even with `low`");
+  CTL_REQUIRE((running_mean == nullptr) == (running_var == nullptr), CTL_ERR_INVALID,
+              "running_mean and running_var must be given together");
+  CTL_REQUIRE(act >= CTL_ACT_NONE && act <= CTL_ACT_SIGMOID, CTL_ERR_INVALID, "unknown activation %d", act);
+  if (sm_count() < 0) return CTL_ERR_CUDA;
+  const double count = (double)(N * H * W);
+  const BnFwdSums bn = {sums, 1.0 / count, count > 1.0 ? count / (count - 1.0) : 1.0, gamma, beta, scale_out, shift_out,
+                        mean_out, var_out, running_mean, running_var, eps, momentum};
+  cudaStream_t st = (cudaStream_t)stream;
+  const int64_t planes = N * (C / 8);
+  // every CTA pays the per-channel prologue: a few CTAs per SM striding over the tensor amortise it
+  if (low) {
+    const int64_t work = planes * (H / 2) * (W / 2);
+    const unsigned grid = (unsigned)std::max<int64_t>(1, std::min<int64_t>(ceil_div(work, kT), (int64_t)sm_count() * 8));
+    launch_chained(scale_shift_upadd_act_c8_kernel, grid, kT, 0, st)((const uint4*)x, (const uint4*)low, (uint4*)y, nullptr,
+                                                                    nullptr, planes, (int)(C / 8), (int)(H / 2), (int)(W / 2),
+                                                                    act, bn);
+  } else {
+    const int64_t total = planes * H * W;
+    const unsigned grid = (unsigned)std::max<int64_t>(1, std::min<int64_t>(ceil_div(total, kT), (int64_t)sm_count() * 8));
+    launch_chained(scale_shift_act_c8_kernel, grid, kT, 0, st)((const uint4*)x, (uint4*)y, nullptr, nullptr, total,
+                                                               (int)(C / 8), H * W, act, bn);
+  }
+  CTL_CUDA_OK(cudaGetLastError(), "bn_apply_from_sums launch");
   return CTL_OK;
 }
 
@@ -463,7 +554,7 @@ extern "C" int ctl_scale_shift_act_c8(const void* x, int64_t N, int64_t C, int64
   if (sm_count() < 0) return CTL_ERR_CUDA;
   const int64_t total = N * (C / 8) * H * W;
   launch_chained(scale_shift_act_c8_kernel, grid_for(total), kT, 0, (cudaStream_t)stream)((const uint4*)x, (uint4*)y, scale, shift,
-                                                                            total, (int)(C / 8), H * W, act);
+                                                                            total, (int)(C / 8), H * W, act, BnFwdSums{});
   CTL_CUDA_OK(cudaGetLastError(), "scale_shift_act launch");
   return CTL_OK;
 }

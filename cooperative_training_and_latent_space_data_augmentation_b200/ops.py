@@ -1041,3 +1041,23 @@ def bn_bwd_apply_totals_c8(dy, a, act, mean, var, eps, gamma, totals, act_affine
             totals.data_ptr(), da.data_ptr(), pg[0].data_ptr() if pg is not None else 0,
             pg[1].data_ptr() if pg is not None else 0, sc.data_ptr(), sh.data_ptr(), _stream()))
     return da, (pg[0] if pg is not None else None), (pg[1] if pg is not None else None)
+
+
+# ------------------------------------------------------------------------------------------------ BN finalisation in the apply pass
+def bn_apply_from_sums_c8(x, sums, gamma, beta, eps, act, running_mean=None, running_var=None, momentum=0.1, low=None):
+    """h = act(BatchNorm_train(x) [+ nearest_up2(low)]) from the per-channel sums (float64 [2, C]) the convolution that
+    produced x accumulated: the finalisation (scale / shift / batch mean / variance, running-statistics update) runs in
+    the prologue of the apply kernel.  Returns (h, scale, shift, mean, var)."""
+    _need_cuda(x, sums, gamma, beta, running_mean, running_var, low)
+    N, C, H, W = _c8_dims(x)
+    if low is not None and (tuple(low.shape) != (N, C // 8, H // 2, W // 2, 8) or H % 2 or W % 2):
+        raise ValueError("low must be C8 %s for x %s" % ((N, C // 8, H // 2, W // 2, 8), tuple(x.shape)))
+    out = torch.empty((4, C), device=x.device, dtype=torch.float32)
+    y = torch.empty_like(x)
+    g, b = _vec(gamma, C), _vec(beta, C)
+    with torch.cuda.device(x.device):
+        _lib.check(_lib.load().ctl_bn_apply_from_sums_c8(
+            x.data_ptr(), N, C, H, W, sums.data_ptr(), _ptr(g), _ptr(b), float(eps), _ptr(low), act, y.data_ptr(),
+            out[0].data_ptr(), out[1].data_ptr(), out[2].data_ptr(), out[3].data_ptr(), _ptr(running_mean),
+            _ptr(running_var), float(momentum), _stream()))
+    return y, out[0], out[1], out[2], out[3]

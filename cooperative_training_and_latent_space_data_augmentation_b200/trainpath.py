@@ -86,6 +86,28 @@ def _conv_bn(fw, conv, bn, x):
     return (a,) + stats
 
 
+def _conv_bn_apply(fw, conv, bn, x, act, low=None, packed=None):
+    """h = act(BatchNorm_train(conv(x)) [+ up2(low)]) -> (a, h, scale, shift, mean, var).  With the statistics accumulated
+    by the conv epilogue the BatchNorm finalisation runs in the prologue of the apply kernel: conv + ONE streaming launch."""
+    k = conv.kernel_size[0]
+    if conv.stride[0] != 1 or conv.out_channels > 256 or \
+            not ops.conv_stats_fusable(conv.in_channels, conv.out_channels, k * k):
+        a, scale, shift, mean, var = _conv_bn(fw, conv, bn, x)
+        h = ops.scale_shift_act_c8(a, scale, shift, act) if low is None else \
+            ops.scale_shift_upadd_act_c8(a, scale, shift, low, act)
+        return a, h, scale, shift, mean, var
+    sums = fw.sums(conv.out_channels)
+    wp = packed if packed is not None else _packed(conv.weight, ops.pack_conv_weight)
+    a = ops.conv2d_c8(x, wp, conv.out_channels, k * k, shift=conv.bias, stats=sums)
+    track = bn.track_running_stats and bn.running_mean is not None
+    h, scale, shift, mean, var = ops.bn_apply_from_sums_c8(
+        a, sums, bn.weight, bn.bias, bn.eps, act, bn.running_mean if track else None,
+        bn.running_var if track else None, bn.momentum if bn.momentum is not None else 0.1, low=low)
+    if track:
+        fw.tracked.append(bn.num_batches_tracked)
+    return a, h, scale, shift, mean, var
+
+
 def _pack_stem_weight(weight):
     return ops.pack_conv_weight(ops.pad_stem_weight(weight))
 
@@ -297,8 +319,7 @@ class _Grads(dict):
 
 # ------------------------------------------------------------------------------------------------ conv + BN + act
 def conv_bn_act_fwd(fw, conv, bn, x, act):
-    a, scale, shift, mean, var = _conv_bn(fw, conv, bn, x)
-    h = ops.scale_shift_act_c8(a, scale, shift, act)
+    a, h, scale, shift, mean, var = _conv_bn_apply(fw, conv, bn, x, act)
     return h, (x, a, h, mean, var, scale, shift)
 
 
@@ -337,13 +358,13 @@ def residual_fwd(fw, block, xr, x_low=None):
     the fly, by the kernel that applies BN2 + LReLU."""
     seq = block.conv
     h1, s1 = conv_bn_act_fwd(fw, seq[0], seq[1], xr, LRELU)
-    a2, scale2, shift2, mean2, var2 = _conv_bn(fw, seq[3], seq[4], h1)
     ci = block.conv_input
     wp = _packed(ci.weight, ops.pack_conv_weight)
     if x_low is not None:
         c = ops.conv2d_c8(x_low, wp, ci.out_channels, 1, shift=ci.bias)
-        out = ops.scale_shift_upadd_act_c8(a2, scale2, shift2, c, LRELU)
+        a2, out, scale2, shift2, mean2, var2 = _conv_bn_apply(fw, seq[3], seq[4], h1, LRELU, low=c)
     else:
+        a2, scale2, shift2, mean2, var2 = _conv_bn(fw, seq[3], seq[4], h1)
         out = ops.conv2d_c8(xr, wp, ci.out_channels, 1, shift=ci.bias, res=a2, res_scale=scale2, res_shift=shift2,
                             act=LRELU)
     return out, (s1, a2, mean2, var2, out)
@@ -483,12 +504,11 @@ def encoder_fwd(enc, x, in_mode, temperature):
     a0 = ops.conv2d_c8(xin, wp, inc[0].out_channels, 9, shift=inc[0].bias, stats=sums)
     bn0 = inc[1]
     track = bn0.track_running_stats and bn0.running_mean is not None
-    scale0, shift0, mean0, var0 = ops.bn_affine_from_sums(
-        sums, a0.shape[0] * a0.shape[2] * a0.shape[3], bn0.weight, bn0.bias, bn0.eps, bn0.running_mean if track else None,
+    h0, scale0, shift0, mean0, var0 = ops.bn_apply_from_sums_c8(
+        a0, sums, bn0.weight, bn0.bias, bn0.eps, LRELU, bn0.running_mean if track else None,
         bn0.running_var if track else None, bn0.momentum if bn0.momentum is not None else 0.1)
     if track:
         fw.tracked.append(bn0.num_batches_tracked)
-    h0 = ops.scale_shift_act_c8(a0, scale0, shift0, LRELU)
     h, s_inc = conv_bn_act_fwd(fw, inc[3], inc[4], h0, LRELU)   # BN then F.leaky_relu (encoder_decoder.py:405)
     tape = [(a0, h0, mean0, var0, scale0, shift0, xin), s_inc]
     for blk in (enc.down1, enc.down2, enc.down3, enc.down4):

@@ -256,6 +256,16 @@ int ctl_bn_bwd_apply_totals_c8(const void* dy, const void* a, int64_t N, int64_t
                                const float* mean, const float* var, float eps, const float* gamma, const double* totals,
                                void* da, float* dgamma, float* dbeta, const float* act_scale, const float* act_shift,
                                void* stream);
+/* Train-mode BatchNorm finalisation + apply in ONE launch: y = act(x * scale + shift [+ nearest_up2(low)]) where scale / shift
+ * are formed in every CTA's prologue from the per-channel sums a convolution epilogue accumulated (sums: double [2][C] =
+ * sum x | sum x^2 over N*H*W values); the first CTA also writes scale / shift / mean / var (for the backward) and applies
+ * the running-statistics update of nn.BatchNorm2d (running_* may be NULL).  low: NULL, or the C8 tensor
+ * [N][C/8][H/2][W/2][8] of ctl_scale_shift_upadd_act_c8.  Replaces ctl_bn_affine_from_sums + ctl_scale_shift[_upadd]_act_c8.
+ * C <= 256. */
+int ctl_bn_apply_from_sums_c8(const void* x, int64_t N, int64_t C, int64_t H, int64_t W, const double* sums,
+                              const float* gamma, const float* beta, float eps, const void* low, int act, void* y,
+                              float* scale_out, float* shift_out, float* mean_out, float* var_out, float* running_mean,
+                              float* running_var, float momentum, void* stream);
 /* dv = dy * act'(h) */
 int ctl_act_bwd_c8(const void* dy, const void* h, int64_t N, int64_t C, int64_t H, int64_t W, int act, void* dv,
                    void* stream);

@@ -299,3 +299,37 @@ def test_dgrad_epilogue_accumulates_the_bn_backward_sums(ops, cin, cout, H, W, a
     torch.testing.assert_close(dg, want[1], rtol=1e-4, atol=1e-5 * float(want[1].abs().max()))
     torch.testing.assert_close(db, want[2], rtol=1e-4, atol=1e-5 * float(want[2].abs().max()))
     assert not ops.conv_bnbwd_fusable(128, 16) and not ops.conv_bnbwd_fusable(16, 64)
+
+
+@pytest.mark.parametrize("C,H,W,with_low,act", [(16, 42, 40, False, 1), (32, 28, 24, True, 1), (64, 14, 16, True, 1),
+                                                 (128, 14, 14, False, 2), (16, 224, 224, True, 1), (256, 6, 8, False, 0)])
+def test_bn_finalisation_in_the_apply_prologue(ops, C, H, W, with_low, act):
+    """ctl_bn_apply_from_sums_c8 against ctl_bn_affine_from_sums + ctl_scale_shift[_upadd]_act_c8 on the same sums:
+    scale / shift / mean / var and the running statistics to 1e-6 relative (fp32 rsqrt instead of an fp64 one), the
+    bf16 result equal up to isolated neighbouring roundings."""
+    g = torch.Generator(device="cuda").manual_seed(C + H)
+    N = 3
+    a = ops.nchw_to_c8(torch.randn(N, C, H, W, device="cuda", generator=g) * 1.3 + 0.2)
+    af = ops.c8_to_nchw(a).double()
+    sums = torch.stack([af.sum((0, 2, 3)), (af * af).sum((0, 2, 3))]).contiguous()
+    gamma = 1 + 0.2 * torch.randn(C, device="cuda", generator=g)
+    beta = 0.3 * torch.randn(C, device="cuda", generator=g)
+    low = ops.nchw_to_c8(torch.randn(N, C, H // 2, W // 2, device="cuda", generator=g)) if with_low else None
+    rm0, rv0 = torch.randn(C, device="cuda", generator=g), torch.rand(C, device="cuda", generator=g) + 0.5
+    rm_w, rv_w, rm_g, rv_g = rm0.clone(), rv0.clone(), rm0.clone(), rv0.clone()
+    want = ops.bn_affine_from_sums(sums, N * H * W, gamma, beta, 1e-5, rm_w, rv_w, 0.1)
+    h_want = ops.scale_shift_act_c8(a, want[0], want[1], act) if low is None else \
+        ops.scale_shift_upadd_act_c8(a, want[0], want[1], low, act)
+    got = ops.bn_apply_from_sums_c8(a, sums, gamma, beta, 1e-5, act, rm_g, rv_g, 0.1, low=low)
+    for w_, g_, what in zip(want, got[1:], ("scale", "shift", "mean", "var")):
+        torch.testing.assert_close(g_, w_, rtol=2e-6, atol=2e-6, msg=lambda m: what + ": " + m)
+    torch.testing.assert_close(rm_g, rm_w, rtol=2e-6, atol=2e-6)
+    torch.testing.assert_close(rv_g, rv_w, rtol=2e-6, atol=2e-6)
+    torch.testing.assert_close(got[0].float(), h_want.float(), rtol=8e-3, atol=1e-5)
+    assert float((got[0].float() != h_want.float()).float().mean()) < 1e-3
+    # and against torch's own train-mode BatchNorm
+    v = F.batch_norm(af.float(), None, None, gamma, beta, True, 0.1, 1e-5)
+    if low is not None:
+        v = v + F.interpolate(ops.c8_to_nchw(low).float(), scale_factor=2, mode="nearest")
+    v = F.leaky_relu(v, 0.2) if act == 1 else F.relu(v) if act == 2 else v
+    _cmp(ops.c8_to_nchw(got[0]), v, 1e-2, "against F.batch_norm")
