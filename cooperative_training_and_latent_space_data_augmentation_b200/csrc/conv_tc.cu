@@ -37,6 +37,8 @@
 // the 224^2 configuration (224, 112, 56, 28, 14) is a multiple of 14.  Rows meet through a small shared-memory exchange
 // between the four epilogue warps that share an item.
 #include <algorithm>
+#include <cstdio>
+#include <cstdlib>
 
 #include "ctl_common.cuh"
 #include "ctl_tcgen05.cuh"
@@ -74,6 +76,8 @@ struct ConvParams {
                                       // its forward affine, bnb_act its activation; stats receives sum dv | sum dv*a
   int diag;                           // profiling only (env CTL_DIAG_SKIP): 1 no MMA, 2 no TMA loads, 4 no epilogue memory traffic, 8 no epilogue
 };
+
+#include "conv_small.cuh"   // K3s: the 16 -> 16 channel 3x3 layers on the warp-level tensor path
 
 template <int CIN, int NT, int TAPS, int MT, int STAGES, bool VP = false>
 struct ConvCfg {
@@ -742,6 +746,7 @@ static int conv2d_c8_impl(const void* x, int64_t N, int64_t H, int64_t W, int64_
     p.sal = sal; p.sal_mode = sal_mode; p.no_store = store_out ? 0 : 1;
   }
   cudaStream_t st = (cudaStream_t)stream;
+  if (conv_small_handles((int)Cin, (int)Cout, taps, p) && conv_small_enabled()) return launch_conv_small(x, p, st);
   if (ctl_conv2d_vpacked((int)Cin, (int)Cout, taps, subsample))   // w_packed in the vertically packed layout
     return dispatch_vp<128>(x, p, nt, st);
   if (taps == 9) {                             // tap-major weights
