@@ -453,7 +453,7 @@ def run_predict_arm(args, world, rank, local_rank, dist):
                 "api": "GraphedPredictor.predict_chunk on pinned host tensors (fp32 image + uint8 ground truth H2D, graph "
                        "replay, uint8 label map D2H, stream synchronised every chunk)"},
         "gpu_launches": kernels_per_step * steps,
-        "roofline": {"kernel": "conv_tc_kernel 16->16 3x3 @%d^2, batch %d (dominant kernel class of the inference pass)"
+        "roofline": {"kernel": "conv_small_kernel (K3s) 16->16 3x3 @%d^2, batch %d (dominant kernel class of the inference pass)"
                                % (size, S), "bound": "hbm", "achieved": top["GBps"], "peak": peaks["hbm_gbs"], "unit": "GB/s",
                      "frac": top["hbm_frac"], "traffic": None, "avg_launch_us": top["us"],
                      "peak_source": peaks["source"] + " (burst copy)"},
@@ -621,7 +621,7 @@ def run_gpu_arm(args):
         "gpu_launches": launches,
         "roofline": roofline,
         # the dominant kernel of the STEP (not of the metric's masking half): HBM-bound 16-channel 3x3 conv class
-        "roofline_conv": {"kernel": "conv_tc_kernel 16->16 3x3 @%d^2, batch %d (largest share of the step's device time)"
+        "roofline_conv": {"kernel": "conv_small_kernel (K3s, warp-level tensor path) 16->16 3x3 @%d^2, batch %d (largest share of the step's device time)"
                                     % (args.size, args.batch), "bound": "hbm", "achieved": top.get("GBps"),
                           "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": top.get("hbm_frac"),
                           "tensor_frac_of_burst_peak": top.get("tensor_frac"), "avg_launch_us": top.get("us")},

@@ -66,7 +66,9 @@ inline int plane_splits(int64_t planes, int64_t HW, int ctas_per_sm) {
 // Stage 1 of every per-channel reduction.  MODE 0: sum x, sum x^2 (forward statistics / bias gradients).
 // MODE 1: dv = dy * act'(h); sum dv, sum dv*a (BatchNorm backward); optionally materialises dv.
 // partial: double [(split*planes + plane)*8 + j][2]
-template <int MODE>
+// WITH_H = false (h is never read: MODE 0, or MODE 1 with the activation input recomputed from a): the loop is
+// double-buffered -- the next four positions' loads are in flight while the current four are reduced.
+template <int MODE, bool WITH_H = (MODE == 1)>
 __global__ void __launch_bounds__(kT, 2)
 plane_reduce_kernel(const uint4* __restrict__ x, const uint4* __restrict__ h, const uint4* __restrict__ a,
                     uint4* __restrict__ dv_out, double* __restrict__ partial, int64_t planes, int64_t HW, int splits,
@@ -119,6 +121,32 @@ plane_reduce_kernel(const uint4* __restrict__ x, const uint4* __restrict__ h, co
   // (~100 KB in flight per SM with three resident CTAs) -- two positions left the HBM pipe at 3.0 TB/s
   const uint4 zero = make_uint4(0, 0, 0, 0);
   constexpr int kP = 4;
+  if constexpr (!WITH_H) {
+    auto load = [&](const int64_t i, uint4 (&xv)[kP], uint4 (&av)[MODE == 1 ? kP : 1]) {
+#pragma unroll
+      for (int u = 0; u < kP; ++u) {
+        const int64_t idx = plane * HW + i + u * kT;
+        const bool ok = i + u * kT < hi;
+        xv[u] = ok ? __ldcs(x + idx) : zero;
+        if (MODE == 1) av[MODE == 1 ? u : 0] = ok ? __ldg(a + idx) : zero;
+      }
+    };
+    auto consume = [&](const int64_t i, const uint4 (&xv)[kP], const uint4 (&av)[MODE == 1 ? kP : 1]) {
+#pragma unroll
+      for (int u = 0; u < kP; ++u)
+        if (i + u * kT < hi) accumulate(plane * HW + i + u * kT, xv[u], av[MODE == 1 ? u : 0], zero);
+    };
+    uint4 xa[kP], xb[kP], aa[MODE == 1 ? kP : 1], ab[MODE == 1 ? kP : 1];
+    int64_t i = lo + threadIdx.x;
+    if (i < hi) load(i, xa, aa);
+    for (; i < hi; i += 2 * kP * kT) {
+      const int64_t i2 = i + kP * kT, i3 = i + 2 * kP * kT;
+      if (i2 < hi) load(i2, xb, ab);
+      consume(i, xa, aa);
+      if (i3 < hi) load(i3, xa, aa);
+      if (i2 < hi) consume(i2, xb, ab);
+    }
+  } else
   for (int64_t i = lo + threadIdx.x; i < hi; i += kP * kT) {
     uint4 xv[kP], av[kP], hv[kP];
 #pragma unroll
@@ -161,12 +189,12 @@ plane_reduce_kernel(const uint4* __restrict__ x, const uint4* __restrict__ h, co
 }
 
 // resident CTAs of the reduction per SM (register-limited; queried once per variant)
-template <int MODE>
+template <int MODE, bool WITH_H = (MODE == 1)>
 int reduce_ctas_per_sm() {
   static int cached = 0;
   if (cached <= 0) {
     int n = 0;
-    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, plane_reduce_kernel<MODE>, kT, 0) != cudaSuccess || n <= 0) n = 3;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, plane_reduce_kernel<MODE, WITH_H>, kT, 0) != cudaSuccess || n <= 0) n = 3;
     cached = n;
   }
   return cached;
@@ -818,10 +846,17 @@ extern "C" int ctl_bn_bwd_reduce_c8(const void* dy, const void* h, const void* a
   if (sm_count() < 0) return CTL_ERR_CUDA;
   cudaStream_t st = (cudaStream_t)stream;
   const int64_t planes = N * (C / 8), HW = H * W;
-  const int splits = plane_splits(planes, HW, reduce_ctas_per_sm<1>());
-  launch_chained(plane_reduce_kernel<1>, dim3((unsigned)planes, (unsigned)splits), kT, 0, st)(
-      (const uint4*)dy, (const uint4*)h, (const uint4*)a, (uint4*)dv_out, (double*)workspace, planes, HW, splits, act,
-      act_scale, act_shift, (int)(C / 8), nullptr);
+  if (h != nullptr) {
+    const int splits = plane_splits(planes, HW, reduce_ctas_per_sm<1, true>());
+    launch_chained(plane_reduce_kernel<1, true>, dim3((unsigned)planes, (unsigned)splits), kT, 0, st)(
+        (const uint4*)dy, (const uint4*)h, (const uint4*)a, (uint4*)dv_out, (double*)workspace, planes, HW, splits, act,
+        act_scale, act_shift, (int)(C / 8), nullptr);
+  }
+  const int splits = plane_splits(planes, HW, h != nullptr ? reduce_ctas_per_sm<1, true>() : reduce_ctas_per_sm<1, false>());
+  if (h == nullptr)
+    launch_chained(plane_reduce_kernel<1, false>, dim3((unsigned)planes, (unsigned)splits), kT, 0, st)(
+        (const uint4*)dy, nullptr, (const uint4*)a, nullptr, (double*)workspace, planes, HW, splits, act,
+        act_scale, act_shift, (int)(C / 8), nullptr);
   CTL_CUDA_OK(cudaGetLastError(), "bn_bwd_reduce launch");
   launch_chained(bn_bwd_finalize_kernel, (unsigned)ceil_div(C, 4), 128, 0, st)((const double*)workspace, planes, splits, (int)N, (int)C,
                                                                    (double)(N * HW), mean, var, eps, gamma, coef, dgamma,
@@ -860,10 +895,17 @@ extern "C" int ctl_bn_bwd_c8(const void* dy, const void* h, const void* a, int64
   if (sm_count() < 0) return CTL_ERR_CUDA;
   cudaStream_t st = (cudaStream_t)stream;
   const int64_t planes = N * (C / 8), HW = H * W, total = planes * HW;
-  const int splits = plane_splits(planes, HW, reduce_ctas_per_sm<1>());
-  launch_chained(plane_reduce_kernel<1>, dim3((unsigned)planes, (unsigned)splits), kT, 0, st)(
-      (const uint4*)dy, (const uint4*)h, (const uint4*)a, (uint4*)dv_out, nullptr, planes, HW, splits, act, act_scale,
-      act_shift, (int)(C / 8), totals);
+  if (h != nullptr) {
+    const int splits = plane_splits(planes, HW, reduce_ctas_per_sm<1, true>());
+    launch_chained(plane_reduce_kernel<1, true>, dim3((unsigned)planes, (unsigned)splits), kT, 0, st)(
+        (const uint4*)dy, (const uint4*)h, (const uint4*)a, (uint4*)dv_out, nullptr, planes, HW, splits, act, act_scale,
+        act_shift, (int)(C / 8), totals);
+  } else {
+    const int splits = plane_splits(planes, HW, reduce_ctas_per_sm<1, false>());
+    launch_chained(plane_reduce_kernel<1, false>, dim3((unsigned)planes, (unsigned)splits), kT, 0, st)(
+        (const uint4*)dy, nullptr, (const uint4*)a, nullptr, nullptr, planes, HW, splits, act, act_scale,
+        act_shift, (int)(C / 8), totals);
+  }
   CTL_CUDA_OK(cudaGetLastError(), "bn_bwd reduce launch");
   const BnBwdTotals bt = {totals, mean, var, gamma, dgamma, dbeta, (double)(N * HW), eps};
   // every CTA pays the coefficient prologue: a grid of a few CTAs per SM striding over the tensor amortises it

@@ -51,11 +51,13 @@ __device__ __forceinline__ void hmma_16816(float (&d)[4], const uint32_t (&a)[4]
                : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b[0]), "r"(b[1]));
 }
 
-// first product of an accumulator chain: C = 0 (no zeroing of the destination registers)
-__device__ __forceinline__ void hmma_16816_first(float (&d)[4], const uint32_t (&a)[4], const uint32_t (&b)[2]) {
-  asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%10,%10,%10,%10};"
+// first product of an accumulator chain: C = the per-channel shift of this thread's two columns (no zeroing of the
+// destination registers, no shift arithmetic in the epilogue)
+__device__ __forceinline__ void hmma_16816_first(float (&d)[4], const uint32_t (&a)[4], const uint32_t (&b)[2], float c0,
+                                                 float c1) {
+  asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%10,%11,%10,%11};"
                : "=f"(d[0]), "=f"(d[1]), "=f"(d[2]), "=f"(d[3])
-               : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b[0]), "r"(b[1]), "f"(0.0f));
+               : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b[0]), "r"(b[1]), "f"(c0), "f"(c1));
 }
 
 // 4-D tiled store shared -> global (elements outside the tensor are not written), bulk-group completion
@@ -129,20 +131,25 @@ conv_small_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constan
       }
   }
   // this thread's four channels: 8*jn + 2*tq + e
-  float sc[2][2], sh[2][2], rs[RES ? 2 : 1][2], rb[RES ? 2 : 1][2];
+  // without a per-channel scale the shift is the accumulators' initial value (no epilogue arithmetic); with one
+  // (inference: folded BatchNorm) the accumulators start at zero and the epilogue applies acc*scale + shift
+  const bool has_scale = p.scale != nullptr;
+  float sc[2][2], sh[2][2], c_init[2][2], rs[RES ? 2 : 1][2], rb[RES ? 2 : 1][2];
 #pragma unroll
   for (int jn = 0; jn < 2; ++jn)
 #pragma unroll
     for (int e = 0; e < 2; ++e) {
       const int c = 8 * jn + 2 * tq + e;
-      sc[jn][e] = p.scale ? __ldg(p.scale + c) : 1.0f;
+      sc[jn][e] = has_scale ? __ldg(p.scale + c) : 1.0f;
       sh[jn][e] = p.shift ? __ldg(p.shift + c) : 0.0f;
+      c_init[jn][e] = has_scale ? 0.0f : sh[jn][e];
       if (RES) {
         rs[RES ? jn : 0][e] = p.res_scale ? __ldg(p.res_scale + c) : 1.0f;
         rb[RES ? jn : 0][e] = p.res_shift ? __ldg(p.res_shift + c) : 0.0f;
       }
     }
   const bool has_res = RES && p.res != nullptr;
+  const bool res_identity = p.res_scale == nullptr && p.res_shift == nullptr;
   const int act = p.act;
   const float slope = act == CTL_ACT_LRELU ? 0.2f : 1.0f;
   const float act_floor = act == CTL_ACT_RELU ? 0.0f : -INFINITY;
@@ -178,6 +185,7 @@ conv_small_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constan
     const int x = tx * kSmTile + sx * 16 + g;                // this thread's pixels: x and x + 8
     const bool x_ok0 = x < p.W, x_ok1 = x + 8 < p.W;
     const int rows_ok = p.H - y0;                            // output rows of this band inside the image
+    const bool inside = rows_ok >= kSmBandRows && tx * kSmTile + sx * 16 + 16 <= p.W;   // warp-uniform
 
     mbar_wait(&full[stage], phase);
     if (CTL_DIAGF(p, 8)) {                                   // profiling: no compute at all
@@ -213,7 +221,7 @@ conv_small_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constan
 #pragma unroll
           for (int jn = 0; jn < 2; ++jn) {
             if (CTL_DIAGF(p, 1)) continue;
-            if (r == 0 && s == 0) hmma_16816_first(acc[j % 3][jn], a[s], wb[r * 3 + s][jn]);
+            if (r == 0 && s == 0) hmma_16816_first(acc[j % 3][jn], a[s], wb[r * 3 + s][jn], c_init[jn][0], c_init[jn][1]);
             else hmma_16816(acc[j % 3][jn], a[s], wb[r * 3 + s][jn]);
           }
         }
@@ -230,59 +238,73 @@ conv_small_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constan
       if (i >= 2) {
         // ---- output row j = i - 2 is complete: f[jn][2*hp + e] = channel 8*jn + 2*tq + e of pixel x + 8*hp
         const int j = i - 2;
-        float f[2][4];
-        uint32_t rw4[RES ? 4 : 1];
-        if constexpr (RES) {
+        // `masked`: the block crosses the image border -- pixels outside must not enter the statistics (the bulk store
+        // clips them by itself); interior blocks skip the per-value selects
+        auto finish_row = [&](auto masked) {
+          constexpr bool kMasked = decltype(masked)::value;
+          float f[2][4];
+          uint32_t rw4[RES ? 4 : 1];
+          if constexpr (RES) {
 #pragma unroll
-          for (int q = 0; q < 4; ++q) rw4[q] = has_res ? o_warp[((q >> 1) * kSmBandRows + j) * 64 + (q & 1) * 32] : 0u;
-        }
+            for (int q = 0; q < 4; ++q) rw4[q] = o_warp[((q >> 1) * kSmBandRows + j) * 64 + (q & 1) * 32];
+          }
 #pragma unroll
-        for (int jn = 0; jn < 2; ++jn)
+          for (int jn = 0; jn < 2; ++jn)
 #pragma unroll
-          for (int v = 0; v < 4; ++v) f[jn][v] = fmaf(acc[j % 3][jn][v], sc[jn][v & 1], sh[jn][v & 1]);
-        if constexpr (RES && !BNB) {
-          if (has_res) {
+            for (int v = 0; v < 4; ++v) f[jn][v] = acc[j % 3][jn][v];
+          if (has_scale) {                                   // warp-uniform
 #pragma unroll
             for (int jn = 0; jn < 2; ++jn)
 #pragma unroll
-              for (int hp = 0; hp < 2; ++hp) {
-                const uint32_t rw = rw4[RES ? 2 * jn + hp : 0];
-                f[jn][2 * hp] += fmaf(bf_lo(rw), rs[RES ? jn : 0][0], rb[RES ? jn : 0][0]);
-                f[jn][2 * hp + 1] += fmaf(bf_hi(rw), rs[RES ? jn : 0][1], rb[RES ? jn : 0][1]);
+              for (int v = 0; v < 4; ++v) f[jn][v] = fmaf(f[jn][v], sc[jn][v & 1], sh[jn][v & 1]);
+          }
+          if constexpr (RES && !BNB) {
+            if (res_identity) {
+#pragma unroll
+              for (int q = 0; q < 4; ++q) { f[q >> 1][2 * (q & 1)] += bf_lo(rw4[RES ? q : 0]); f[q >> 1][2 * (q & 1) + 1] += bf_hi(rw4[RES ? q : 0]); }
+            } else {
+#pragma unroll
+              for (int q = 0; q < 4; ++q) {
+                f[q >> 1][2 * (q & 1)] += fmaf(bf_lo(rw4[RES ? q : 0]), rs[RES ? q >> 1 : 0][0], rb[RES ? q >> 1 : 0][0]);
+                f[q >> 1][2 * (q & 1) + 1] += fmaf(bf_hi(rw4[RES ? q : 0]), rs[RES ? q >> 1 : 0][1], rb[RES ? q >> 1 : 0][1]);
               }
-          }
-        }
-        // none (slope 1) | leaky ReLU (slope 0.2) | ReLU (slope 1, floor 0) without branches; sigmoid layers stay on K3
-#pragma unroll
-        for (int jn = 0; jn < 2; ++jn)
-#pragma unroll
-          for (int v = 0; v < 4; ++v) f[jn][v] = fmaxf(fmaxf(f[jn][v], slope * f[jn][v]), act_floor);
-        const bool y_ok = j < rows_ok;
-#pragma unroll
-        for (int jn = 0; jn < 2; ++jn)
-#pragma unroll
-          for (int hp = 0; hp < 2; ++hp) {
-            const __nv_bfloat162 hh = __floats2bfloat162_rn(f[jn][2 * hp], f[jn][2 * hp + 1]);
-            const uint32_t ow = *reinterpret_cast<const uint32_t*>(&hh);
-            const bool ok = y_ok && (hp == 0 ? x_ok0 : x_ok1);
-            if constexpr (STATS && !BNB) {
-              const float lo = ok ? bf_lo(ow) : 0.0f, hi = ok ? bf_hi(ow) : 0.0f;
-              st_s[STATS ? jn : 0][0] += lo; st_q[STATS ? jn : 0][0] = fmaf(lo, lo, st_q[STATS ? jn : 0][0]);
-              st_s[STATS ? jn : 0][1] += hi; st_q[STATS ? jn : 0][1] = fmaf(hi, hi, st_q[STATS ? jn : 0][1]);
             }
-            if constexpr (BNB) {
-              // dv = dy * act'(a*scale + shift) on the STORED (bf16) dy, as the stand-alone reduction reads it
-              const uint32_t rw = rw4[RES ? 2 * jn + hp : 0];
-              const float a_lo = bf_lo(rw), a_hi = bf_hi(rw);
-              const float p_lo = fmaf(a_lo, rs[RES ? jn : 0][0], rb[RES ? jn : 0][0]);
-              const float p_hi = fmaf(a_hi, rs[RES ? jn : 0][1], rb[RES ? jn : 0][1]);
-              const float lo = ok ? bf_lo(ow) * (p_lo > 0.0f ? 1.0f : bnb_neg) : 0.0f;
-              const float hi = ok ? bf_hi(ow) * (p_hi > 0.0f ? 1.0f : bnb_neg) : 0.0f;
-              st_s[STATS ? jn : 0][0] += lo; st_q[STATS ? jn : 0][0] = fmaf(lo, a_lo, st_q[STATS ? jn : 0][0]);
-              st_s[STATS ? jn : 0][1] += hi; st_q[STATS ? jn : 0][1] = fmaf(hi, a_hi, st_q[STATS ? jn : 0][1]);
-            }
-            o_warp[(jn * kSmBandRows + j) * 64 + hp * 32] = ow;
           }
+          if (act != CTL_ACT_NONE) {                         // warp-uniform; leaky ReLU (slope 0.2) | ReLU (slope 1, floor 0)
+#pragma unroll
+            for (int jn = 0; jn < 2; ++jn)
+#pragma unroll
+              for (int v = 0; v < 4; ++v) f[jn][v] = fmaxf(fmaxf(f[jn][v], slope * f[jn][v]), act_floor);
+          }
+          const bool y_ok = j < rows_ok;
+#pragma unroll
+          for (int jn = 0; jn < 2; ++jn)
+#pragma unroll
+            for (int hp = 0; hp < 2; ++hp) {
+              const __nv_bfloat162 hh = __floats2bfloat162_rn(f[jn][2 * hp], f[jn][2 * hp + 1]);
+              const uint32_t ow = *reinterpret_cast<const uint32_t*>(&hh);
+              const bool ok = !kMasked || (y_ok && (hp == 0 ? x_ok0 : x_ok1));
+              if constexpr (STATS && !BNB) {
+                const float lo = ok ? bf_lo(ow) : 0.0f, hi = ok ? bf_hi(ow) : 0.0f;
+                st_s[STATS ? jn : 0][0] += lo; st_q[STATS ? jn : 0][0] = fmaf(lo, lo, st_q[STATS ? jn : 0][0]);
+                st_s[STATS ? jn : 0][1] += hi; st_q[STATS ? jn : 0][1] = fmaf(hi, hi, st_q[STATS ? jn : 0][1]);
+              }
+              if constexpr (BNB) {
+                // dv = dy * act'(a*scale + shift) on the STORED (bf16) dy, as the stand-alone reduction reads it
+                const uint32_t rw = rw4[RES ? 2 * jn + hp : 0];
+                const float a_lo = bf_lo(rw), a_hi = bf_hi(rw);
+                const float p_lo = fmaf(a_lo, rs[RES ? jn : 0][0], rb[RES ? jn : 0][0]);
+                const float p_hi = fmaf(a_hi, rs[RES ? jn : 0][1], rb[RES ? jn : 0][1]);
+                const float lo = ok ? bf_lo(ow) * (p_lo > 0.0f ? 1.0f : bnb_neg) : 0.0f;
+                const float hi = ok ? bf_hi(ow) * (p_hi > 0.0f ? 1.0f : bnb_neg) : 0.0f;
+                st_s[STATS ? jn : 0][0] += lo; st_q[STATS ? jn : 0][0] = fmaf(lo, a_lo, st_q[STATS ? jn : 0][0]);
+                st_s[STATS ? jn : 0][1] += hi; st_q[STATS ? jn : 0][1] = fmaf(hi, a_hi, st_q[STATS ? jn : 0][1]);
+              }
+              o_warp[(jn * kSmBandRows + j) * 64 + hp * 32] = ow;
+            }
+        };
+        if (STATS && !inside) finish_row(std::true_type{});
+        else finish_row(std::false_type{});
       }
     }
     // the warp's 16 px x 8 rows x 2 planes leave as ONE bulk tensor store (clipped at the image border by the TMA unit):

@@ -171,3 +171,43 @@ def test_pack_kernel_matches_torch_statement(ops, cout, cin, k):
         assert torch.equal(ops._pack_kernel(w, False, tap_major=False), ops.pack_conv_weight_torch(w, tap_major=False).reshape(-1))
     want = ops.pack_conv_weight_torch(w.flip(2, 3).transpose(0, 1)).reshape(-1)
     assert torch.equal(ops.pack_conv_weight_dgrad(w), want)
+
+
+@pytest.mark.parametrize("N,H,W", [(1, 1, 1), (2, 7, 5), (1, 8, 16), (3, 33, 31), (2, 32, 32), (1, 40, 72), (2, 65, 17), (5, 9, 100)])
+@pytest.mark.parametrize("variant", ["plain", "scale", "res", "res_affine", "stats", "relu"])
+def test_small_channel_kernel_geometries_and_epilogues(ops, N, H, W, variant):
+    """K3s (16 -> 16 channel 3x3, warp-level tensor path, csrc/conv_small.cuh): its 32 x 32 pixel tiles, 16 x 8 pixel warp
+    blocks (bulk tensor stores clipped at the image border, residual blocks loaded into the output staging buffer) and
+    every epilogue form against fp32 torch on the same bf16 operands, at sizes that are not multiples of the tile."""
+    g = torch.Generator(device="cuda").manual_seed(N * 1000 + H * 10 + W)
+    x = torch.randn(N, 16, H, W, device="cuda", generator=g).to(torch.bfloat16)
+    w = torch.randn(16, 16, 3, 3, device="cuda", generator=g) * (2.0 / 144) ** 0.5
+    shift = 0.3 * torch.randn(16, device="cuda", generator=g)
+    scale = 1 + 0.2 * torch.randn(16, device="cuda", generator=g)
+    res = torch.randn(N, 16, H, W, device="cuda", generator=g).to(torch.bfloat16)
+    rs = 1 + 0.2 * torch.randn(16, device="cuda", generator=g)
+    rb = 0.3 * torch.randn(16, device="cuda", generator=g)
+    xc, wp = ops.nchw_to_c8(x), ops.pack_conv_weight(w)
+    if variant == "plain":
+        got = ops.conv2d_c8(xc, wp, 16, 9, shift=shift, act=1)
+        want = _ref(x, w, 3, 1, None, shift, None, None, None, 1)
+    elif variant == "scale":
+        got = ops.conv2d_c8(xc, wp, 16, 9, scale=scale, shift=shift, act=1)
+        want = _ref(x, w, 3, 1, scale, shift, None, None, None, 1)
+    elif variant == "relu":
+        got = ops.conv2d_c8(xc, wp, 16, 9, shift=shift, act=2)
+        want = _ref(x, w, 3, 1, None, shift, None, None, None, 2)
+    elif variant == "res":
+        got = ops.conv2d_c8(xc, wp, 16, 9, res=ops.nchw_to_c8(res))
+        want = _ref(x, w, 3, 1, None, None, res, None, None, 0)
+    elif variant == "res_affine":
+        got = ops.conv2d_c8(xc, wp, 16, 9, shift=shift, res=ops.nchw_to_c8(res), res_scale=rs, res_shift=rb, act=1)
+        want = _ref(x, w, 3, 1, None, shift, res, rs, rb, 1)
+    else:
+        stats = torch.zeros(2, 16, device="cuda", dtype=torch.float64)
+        got = ops.conv2d_c8(xc, wp, 16, 9, shift=shift, stats=stats)
+        want = _ref(x, w, 3, 1, None, shift, None, None, None, 0)
+        stored = ops.c8_to_nchw(got).double()
+        torch.testing.assert_close(stats[0], stored.sum((0, 2, 3)), rtol=1e-5, atol=1e-4)
+        torch.testing.assert_close(stats[1], (stored * stored).sum((0, 2, 3)), rtol=1e-5, atol=1e-4)
+    _check(got, want)

@@ -14,7 +14,8 @@ ops = pkg.ops
 
 
 def main():
-    B, C, S = 64, 16, int(sys.argv[1]) if len(sys.argv) > 1 else 224
+    C, S = 16, int(sys.argv[1]) if len(sys.argv) > 1 else 224
+    B = int(sys.argv[2]) if len(sys.argv) > 2 else 64
     sets = []
     for _ in range(3):
         sets.append(dict(x=ops.nchw_to_c8(torch.randn(B, C, S, S, device="cuda")),
@@ -32,7 +33,7 @@ def main():
     only = os.environ.get("ONLY")
     if only:
         variants = {k: v for k, v in variants.items() if k in only.split(",")}
-    out = {"size": S, "small": os.environ.get("CTL_CONV_SMALL", "1"), "diag": os.environ.get("CTL_DIAG_SKIP", "0")}
+    out = {"size": S, "batch": B, "small": os.environ.get("CTL_CONV_SMALL", "1"), "diag": os.environ.get("CTL_DIAG_SKIP", "0")}
     st = torch.cuda.Stream()
     for name, fn in variants.items():
         with torch.cuda.stream(st):
