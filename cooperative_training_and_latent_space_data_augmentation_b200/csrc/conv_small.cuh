@@ -71,6 +71,11 @@ __device__ __forceinline__ void tma_store_wait_read() { asm volatile("cp.async.b
 __device__ __forceinline__ void tma_store_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
+// n / d for 0 <= n < 2^31 and 1 <= d < 2^13 with magic = ceil(2^44 / d) (exact: n * (magic*d - 2^44) < 2^44): one wide
+// multiply and a shift instead of the ~40-instruction generic division, twice per tile and warp
+__device__ __forceinline__ int small_div(int n, uint64_t magic) { return (int)(((uint64_t)(uint32_t)n * magic) >> 44); }
+inline uint64_t small_div_magic(int d) { return (((uint64_t)1 << 44) + (uint64_t)d - 1) / (uint64_t)d; }
+
 __device__ __forceinline__ float bf_lo(uint32_t w) { return __uint_as_float(w << 16); }
 __device__ __forceinline__ float bf_hi(uint32_t w) { return __uint_as_float(w & 0xffff0000u); }
 
@@ -102,9 +107,9 @@ conv_small_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constan
   // TMA producer duty (one elected lane of warp 0): tile k + kSmStages - 1 is requested at the top of iteration k into the
   // stage iteration k - 1 consumed, so two tiles are always in flight behind the one being computed
   auto issue_load = [&](int t, int stage) {
-    const int img = t / tiles_per_img;
+    const int img = small_div(t, p.magic_img);
     const int rem = t - img * tiles_per_img;
-    const int ty = rem / p.tiles_x, tx = rem - ty * p.tiles_x;
+    const int ty = small_div(rem, p.magic_x), tx = rem - ty * p.tiles_x;
     if (CTL_DIAGF(p, 2)) { mbar_arrive(&full[stage]); return; }
     mbar_arrive_expect_tx(&full[stage], kSmStageBytes);
     tma_load_4d(smem + stage * kSmStageBytes, &tmap, &full[stage], (tx * kSmTile - 1) * 2, ty * kSmTile - 1, 0, img);
@@ -178,9 +183,9 @@ conv_small_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constan
       }
       __syncwarp();
     }
-    const int img = t / tiles_per_img;
+    const int img = small_div(t, p.magic_img);
     const int rem = t - img * tiles_per_img;
-    const int ty = rem / p.tiles_x, tx = rem - ty * p.tiles_x;
+    const int ty = small_div(rem, p.magic_x), tx = rem - ty * p.tiles_x;
     const int y0 = ty * kSmTile + band * kSmBandRows;
     const int x = tx * kSmTile + sx * 16 + g;                // this thread's pixels: x and x + 8
     const bool x_ok0 = x < p.W, x_ok1 = x + 8 < p.W;
@@ -352,6 +357,7 @@ conv_small_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constan
 // true when this layer / epilogue combination runs on K3s
 inline bool conv_small_handles(int Cin, int Cout, int taps, const ConvParams& p) {
   return Cin == 16 && Cout == 16 && taps == 9 && p.subsample == 1 && !p.up2x && p.sal == nullptr && p.act != CTL_ACT_SIGMOID &&
+         ceil_div(p.H, kSmTile) * ceil_div(p.W, kSmTile) < 8192 &&
          !(p.stats != nullptr && p.res != nullptr && p.bnb_act == 0);
 }
 
@@ -389,6 +395,8 @@ int launch_conv_small(const void* x, const ConvParams& p0, cudaStream_t st) {
   p.tiles_x = (int)ceil_div(p.W, kSmTile);
   p.tiles_y = (int)ceil_div(p.H, kSmTile);
   p.num_tiles = (int64_t)p.N * p.tiles_x * p.tiles_y;
+  p.magic_img = small_div_magic(p.tiles_x * p.tiles_y);
+  p.magic_x = small_div_magic(p.tiles_x);
   CUtensorMap tmap;
   CUtensorMap tmap_out;                                      // a warp's output block: 16 px x 8 rows x 2 planes
   if (int rc = make_act_tmap(&tmap, x, p.N, p.H, p.W, 16, kSmHalo, kSmHalo)) return rc;

@@ -74,6 +74,7 @@ struct ConvParams {
   int bnb_act;                        // != 0: BatchNorm-backward statistics mode (see conv_epilogue<.., BNB>): `res` is the
                                       // BatchNorm INPUT a of the layer this output gradient flows into, res_scale / res_shift
                                       // its forward affine, bnb_act its activation; stats receives sum dv | sum dv*a
+  uint64_t magic_img, magic_x;        // K3s: small_div magics of tiles per image / tiles per row
   int diag;                           // profiling only (env CTL_DIAG_SKIP): 1 no MMA, 2 no TMA loads, 4 no epilogue memory traffic, 8 no epilogue
 };
 
