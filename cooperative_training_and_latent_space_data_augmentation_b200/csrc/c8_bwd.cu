@@ -11,6 +11,7 @@
 //   MyDecoder.final_conv (+Sigmoid)         medseg/models/ebm/encoder_decoder.py:439-452
 //   MyEncoder.inc[0] + construct_input      medseg/models/ebm/encoder_decoder.py:370-371, medseg/common_utils/basic_operations.py:110-158
 #include <algorithm>
+#include <cstdlib>
 #include <cmath>
 
 #include "ctl_common.cuh"
@@ -322,17 +323,10 @@ struct BnBwdTotals {          // coefficients computed in the kernel's prologue 
 };
 constexpr int kMaxBnC = 256;
 
-__global__ void __launch_bounds__(kT)
-bn_bwd_apply_kernel(const uint4* __restrict__ dy, const uint4* __restrict__ h, const uint4* __restrict__ a,
-                    const float* __restrict__ coef_in, uint4* __restrict__ da, int64_t total, int C8, int64_t HW, int act,
-                    const float* __restrict__ act_scale, const float* __restrict__ act_shift, const BnBwdTotals bt) {
-  pdl_entry();
-  const int C = C8 * 8;
-  __shared__ float s_coef[3 * kMaxBnC];
-  const float* coef = coef_in;
-  if (bt.totals != nullptr) {
-    // same arithmetic as bn_bwd_finalize_kernel, once per CTA (C <= 256 values): no finalisation launch
-    for (int c = threadIdx.x; c < C; c += kT) {
+// BatchNorm-backward coefficients from the per-channel totals (same arithmetic as bn_bwd_finalize_kernel), once per CTA
+// (C <= 256 values): no finalisation launch.  s_coef: c1 | c2 | c3, [3][C]
+__device__ __forceinline__ void bn_bwd_coef_prologue(const BnBwdTotals& bt, int C, float* s_coef) {
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
       // fp64 only where it matters (the cancellation in S2 - mean*S1); 1/sqrt and the divisions in fp32 -- this
       // runs in every CTA's prologue, and fp64 division / square root are ~100-instruction sequences
       const double S1 = bt.totals[c], S2 = bt.totals[C + c];
@@ -350,7 +344,19 @@ bn_bwd_apply_kernel(const uint4* __restrict__ dy, const uint4* __restrict__ h, c
         if (bt.dbeta) bt.dbeta[c] = s1;
       }
     }
-    __syncthreads();
+  __syncthreads();
+}
+
+__global__ void __launch_bounds__(kT)
+bn_bwd_apply_kernel(const uint4* __restrict__ dy, const uint4* __restrict__ h, const uint4* __restrict__ a,
+                    const float* __restrict__ coef_in, uint4* __restrict__ da, int64_t total, int C8, int64_t HW, int act,
+                    const float* __restrict__ act_scale, const float* __restrict__ act_shift, const BnBwdTotals bt) {
+  pdl_entry();
+  const int C = C8 * 8;
+  __shared__ float s_coef[3 * kMaxBnC];
+  const float* coef = coef_in;
+  if (bt.totals != nullptr) {
+    bn_bwd_coef_prologue(bt, C, s_coef);
     coef = s_coef;
   }
   for (int64_t i = (int64_t)blockIdx.x * kT + threadIdx.x; i < total; i += (int64_t)gridDim.x * kT) {
@@ -373,6 +379,104 @@ bn_bwd_apply_kernel(const uint4* __restrict__ dy, const uint4* __restrict__ h, c
     da[i] = pack8(f);
   }
 }
+
+// The same pass for large planes (HW >= 2048), structured by plane: a work item is U*kT consecutive positions of ONE
+// 8-channel plane, so the 24 coefficients (+16 activation-affine values) of its channels sit in registers -- the
+// generic form pays a 64-bit division and ~40 shared / constant-cache loads per 16-byte position, enough to hold it at
+// 0.76 of the HBM peak -- and all 2*U loads of an item are issued before the first use.
+template <int U>
+__global__ void __launch_bounds__(kT, 3)
+bn_bwd_apply_planes_kernel(const uint4* __restrict__ dy, const uint4* __restrict__ a, const float* __restrict__ coef_in,
+                           uint4* __restrict__ da, int64_t planes, int C8, int HW, int items_per_plane, int act,
+                           const float* __restrict__ act_scale, const float* __restrict__ act_shift, const BnBwdTotals bt) {
+  pdl_entry();
+  const int C = C8 * 8;
+  __shared__ float s_coef[5 * kMaxBnC];                  // c1 | c2 | c3 | act scale | act shift
+  if (bt.totals != nullptr) {
+    bn_bwd_coef_prologue(bt, C, s_coef);
+  } else {
+    for (int c = threadIdx.x; c < 3 * C; c += kT) s_coef[c] = coef_in[c];
+  }
+  const bool with_act = act_scale != nullptr && act != CTL_ACT_NONE;
+  for (int c = threadIdx.x; c < C; c += kT) {
+    s_coef[3 * C + c] = with_act ? act_scale[c] : 1.0f;
+    s_coef[4 * C + c] = with_act ? act_shift[c] : 0.0f;
+  }
+  __syncthreads();
+  const float neg = !with_act ? 1.0f : (act == CTL_ACT_LRELU ? 0.2f : 0.0f);   // act'(p) for p <= 0 (LReLU | ReLU)
+  const int64_t items = planes * items_per_plane;
+  float c1[8], c2[8], c3[8], asc[8], ash[8];
+  int cur_c0 = -1;
+  for (int64_t item = blockIdx.x; item < items; item += gridDim.x) {
+    const int64_t plane = item / items_per_plane;
+    const int chunk = (int)(item - plane * items_per_plane);
+    const int c0 = (int)(plane % C8) * 8;
+    if (c0 != cur_c0) {                                   // block-uniform
+      cur_c0 = c0;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        c1[j] = s_coef[c0 + j]; c2[j] = s_coef[C + c0 + j]; c3[j] = s_coef[2 * C + c0 + j];
+        asc[j] = s_coef[3 * C + c0 + j]; ash[j] = s_coef[4 * C + c0 + j];
+      }
+    }
+    const int p0 = chunk * (U * kT) + threadIdx.x;
+    const int64_t base = plane * HW;
+    uint4 xv[U], av4[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const bool ok = p0 + u * kT < HW;
+      xv[u] = ok ? __ldcs(dy + base + p0 + u * kT) : make_uint4(0, 0, 0, 0);
+      av4[u] = ok ? __ldcs(a + base + p0 + u * kT) : make_uint4(0, 0, 0, 0);
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      if (p0 + u * kT < HW) {
+        float f[8], av[8];
+        unpack8(xv[u], f);
+        unpack8(av4[u], av);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const float dv = f[j] * (fmaf(av[j], asc[j], ash[j]) > 0.0f ? 1.0f : neg);
+          f[j] = fmaf(c1[j], dv, fmaf(c2[j], av[j], c3[j]));
+        }
+        da[base + p0 + u * kT] = pack8(f);
+      }
+    }
+  }
+}
+
+// launches the plane-structured form where it applies (no h tensor, planes of >= 2048 positions), else the generic one
+int launch_bn_bwd_apply(const uint4* dy, const uint4* h, const uint4* a, const float* coef, uint4* da, int64_t N, int C8,
+                        int64_t HW, int act, const float* act_scale, const float* act_shift, const BnBwdTotals& bt,
+                        cudaStream_t st) {
+  const int64_t planes = N * C8, total = planes * HW;
+  static const bool planes_on = [] { const char* e = getenv("CTL_BN_APPLY_PLANES"); return !(e && e[0] == '0'); }();
+  if (planes_on && h == nullptr && HW >= 2048 && HW < ((int64_t)1 << 30) && (act == CTL_ACT_NONE || act == CTL_ACT_LRELU || act == CTL_ACT_RELU)) {
+    const int U = HW >= 8192 ? 4 : 2;
+    const int ipp = (int)ceil_div(HW, (int64_t)U * kT);
+    static int resident[2] = {0, 0};                      // CTAs per SM of the U = 2 / U = 4 forms
+    int& res = resident[U == 4];
+    if (res == 0) {
+      if (U == 4) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&res, bn_bwd_apply_planes_kernel<4>, kT, 0);
+      else cudaOccupancyMaxActiveBlocksPerMultiprocessor(&res, bn_bwd_apply_planes_kernel<2>, kT, 0);
+      if (res <= 0) res = 3;
+    }
+    const unsigned grid = (unsigned)std::min<int64_t>(planes * ipp, (int64_t)sm_count() * res);
+    if (U == 4)
+      launch_chained(bn_bwd_apply_planes_kernel<4>, grid, kT, 0, st)(dy, a, coef, da, planes, C8, (int)HW, ipp, act, act_scale,
+                                                                     act_shift, bt);
+    else
+      launch_chained(bn_bwd_apply_planes_kernel<2>, grid, kT, 0, st)(dy, a, coef, da, planes, C8, (int)HW, ipp, act, act_scale,
+                                                                     act_shift, bt);
+  } else {
+    // every CTA pays the coefficient prologue when the totals are given: a few CTAs per SM striding over the tensor
+    const unsigned grid = (unsigned)std::min<int64_t>(ceil_div(total, kT), (int64_t)sm_count() * (bt.totals != nullptr ? 6 : 16));
+    launch_chained(bn_bwd_apply_kernel, grid, kT, 0, st)(dy, h, a, coef, da, total, C8, HW, act, act_scale, act_shift, bt);
+  }
+  CTL_CUDA_OK(cudaGetLastError(), "bn_bwd apply launch");
+  return CTL_OK;
+}
+
 
 // dv = dy * act'(h) only (activation backward without a BatchNorm in front)
 __global__ void __launch_bounds__(kT)
@@ -874,11 +978,9 @@ extern "C" int ctl_bn_bwd_apply_c8(const void* dy, const void* h, const void* a,
               "ctl_bn_bwd_apply_c8: give either h or (act_scale, act_shift)");
   if (sm_count() < 0) return CTL_ERR_CUDA;
   const int64_t total = N * (C / 8) * H * W;
-  launch_chained(bn_bwd_apply_kernel, grid_for(total), kT, 0, (cudaStream_t)stream)((const uint4*)dy, (const uint4*)h, (const uint4*)a,
-                                                                      coef, (uint4*)da, total, (int)(C / 8), H * W, act,
-                                                                      act_scale, act_shift, BnBwdTotals{});
-  CTL_CUDA_OK(cudaGetLastError(), "bn_bwd_apply launch");
-  return CTL_OK;
+  (void)total;
+  return launch_bn_bwd_apply((const uint4*)dy, (const uint4*)h, (const uint4*)a, coef, (uint4*)da, N, (int)(C / 8), H * W, act,
+                             act_scale, act_shift, BnBwdTotals{}, (cudaStream_t)stream);
 }
 
 extern "C" int ctl_bn_bwd_c8(const void* dy, const void* h, const void* a, int64_t N, int64_t C, int64_t H, int64_t W,
@@ -908,19 +1010,13 @@ extern "C" int ctl_bn_bwd_c8(const void* dy, const void* h, const void* a, int64
   }
   CTL_CUDA_OK(cudaGetLastError(), "bn_bwd reduce launch");
   const BnBwdTotals bt = {totals, mean, var, gamma, dgamma, dbeta, (double)(N * HW), eps};
-  // every CTA pays the coefficient prologue: a grid of a few CTAs per SM striding over the tensor amortises it
-  const unsigned apply_grid = (unsigned)std::min<int64_t>(ceil_div(total, kT), (int64_t)sm_count() * 6);
+  (void)total;
   // dv materialised (the residual tail feeds it to the shortcut branch too): the apply pass reads it, activation done
   if (dv_out != nullptr)
-    launch_chained(bn_bwd_apply_kernel, apply_grid, kT, 0, st)((const uint4*)dv_out, nullptr, (const uint4*)a, nullptr,
-                                                                    (uint4*)da, total, (int)(C / 8), HW, act, nullptr,
-                                                                    nullptr, bt);
-  else
-    launch_chained(bn_bwd_apply_kernel, apply_grid, kT, 0, st)((const uint4*)dy, (const uint4*)h, (const uint4*)a, nullptr,
-                                                               (uint4*)da, total, (int)(C / 8), HW, act, act_scale,
-                                                               act_shift, bt);
-  CTL_CUDA_OK(cudaGetLastError(), "bn_bwd apply launch");
-  return CTL_OK;
+    return launch_bn_bwd_apply((const uint4*)dv_out, nullptr, (const uint4*)a, nullptr, (uint4*)da, N, (int)(C / 8), HW, act,
+                               nullptr, nullptr, bt, st);
+  return launch_bn_bwd_apply((const uint4*)dy, (const uint4*)h, (const uint4*)a, nullptr, (uint4*)da, N, (int)(C / 8), HW, act,
+                             act_scale, act_shift, bt, st);
 }
 
 extern "C" int ctl_act_bwd_c8(const void* dy, const void* h, int64_t N, int64_t C, int64_t H, int64_t W, int act,
@@ -1051,10 +1147,7 @@ extern "C" int ctl_bn_bwd_apply_totals_c8(const void* dy, const void* a, int64_t
   if (sm_count() < 0) return CTL_ERR_CUDA;
   const int64_t HW = H * W, total = N * (C / 8) * HW;
   const BnBwdTotals bt = {totals, mean, var, gamma, dgamma, dbeta, (double)(N * HW), eps};
-  const unsigned apply_grid = (unsigned)std::min<int64_t>(ceil_div(total, kT), (int64_t)sm_count() * 6);
-  launch_chained(bn_bwd_apply_kernel, apply_grid, kT, 0, (cudaStream_t)stream)((const uint4*)dy, nullptr, (const uint4*)a, nullptr,
-                                                                              (uint4*)da, total, (int)(C / 8), HW, act,
-                                                                              act_scale, act_shift, bt);
-  CTL_CUDA_OK(cudaGetLastError(), "bn_bwd apply launch");
-  return CTL_OK;
+  (void)total;
+  return launch_bn_bwd_apply((const uint4*)dy, nullptr, (const uint4*)a, nullptr, (uint4*)da, N, (int)(C / 8), HW, act, act_scale,
+                             act_shift, bt, (cudaStream_t)stream);
 }

@@ -51,23 +51,43 @@ class _PackRegistry:
         self.table_keys = []
         self.max_elements = 0
         self.retired = []
+        self.sources = []
         self.dirty = False          # entries were added since the table was built
 
     def _rebuild_table(self):
-        rows, keys, biggest = [], [], 0
-        for key, e in self.entries.items():
+        rows, keys, sources, biggest = [], [], [], 0
+        for key, e in list(self.entries.items()):
             p = e["param"]()
             if p is None:
+                del self.entries[key]                       # a dead model's weight: its packed copy goes with it
                 continue
-            rows.append(ops.pack_job(p.detach(), e["transposed"], e["out"], e["tap_major"]))
+            src = p.detach()
+            rows.append(ops.pack_job(src, e["transposed"], e["out"], e["tap_major"]))
             keys.append(key)
+            sources.append(src)
+            e["table_ptr"] = src.data_ptr()
             biggest = max(biggest, p.numel())
-        dev = next(iter(self.entries.values()))["out"].device
         if self.table is not None:
-            self.retired.append(self.table)                 # a captured CUDA graph may still read the old table
+            # a captured CUDA graph may still read the old table AND the weights it points at: both stay alive
+            self.retired.append((self.table, self.sources))
+            del self.retired[:-8]
+        self.sources = sources                              # the rows hold raw pointers: pin the storages they name
+        if not rows:
+            self.table, self.table_keys, self.max_elements, self.dirty = None, [], 0, False
+            return
+        dev = sources[0].device
         self.table = torch.tensor(rows, dtype=torch.int64).to(dev)
         self.table_keys, self.max_elements = keys, biggest
         self.dirty = False
+
+    def _table_is_current(self):
+        """False when a registered weight died or its storage moved since the table was built (the rows are raw pointers)."""
+        for k in self.table_keys:
+            e = self.entries.get(k)
+            p = e["param"]() if e is not None else None
+            if p is None or p.data_ptr() != e.get("table_ptr"):
+                return False
+        return True
 
     def get(self, param, transposed, tag, tap_major=None):
         import weakref
@@ -87,8 +107,9 @@ class _PackRegistry:
             self.dirty = True
             return out
         if e["epoch"] != epoch or e["version"] != param._version:
-            if self.table is None or self.dirty:
-                if torch.cuda.is_current_stream_capturing():
+            capturing = torch.cuda.is_current_stream_capturing()
+            if self.table is None or self.dirty or (not capturing and not self._table_is_current()):
+                if capturing:
                     raise RuntimeError("the weight-packing table must be built before a CUDA-graph capture "
                                        "(fastpath.prepare_packing())")
                 self._rebuild_table()
@@ -109,7 +130,7 @@ _REGISTRY = _PackRegistry()
 def prepare_packing():
     """Builds the device job table of the batched weight packing now (host -> device copy): call before capturing a
     CUDA graph of a step, after at least one eager step has registered the networks' weights."""
-    if _REGISTRY.entries and (_REGISTRY.table is None or _REGISTRY.dirty):
+    if _REGISTRY.entries and (_REGISTRY.table is None or _REGISTRY.dirty or not _REGISTRY._table_is_current()):
         _REGISTRY._rebuild_table()
 
 

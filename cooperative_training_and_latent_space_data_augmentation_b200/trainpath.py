@@ -178,7 +178,9 @@ def saliency_fusable(decoder, code):
 # decoded with the same weights in the same BatchNorm mode (advanced...model.py:440-447 then :497-523): the forward the
 # reference computes a second time is bit-for-bit the one already on tape.  model_util reuses it for the saliency pass
 # (only the backward runs; the BatchNorm running-stat side effect of the skipped forward is replayed).
-_FORWARD_CACHE = {}
+import weakref as _weakref
+
+_FORWARD_CACHE = _weakref.WeakKeyDictionary()      # keyed by the decoder module itself: a dead model's tape goes with it
 
 
 def forget_forwards():
@@ -188,8 +190,8 @@ def forget_forwards():
 def cached_forward(dec, code):
     """The tape of decoder(code) when that exact forward is the decoder's most recent one, else None."""
     from . import fastpath
-    hit = _FORWARD_CACHE.get(id(dec))
-    if hit is None or hit["dec"] is not dec:
+    hit = _FORWARD_CACHE.get(dec)
+    if hit is None:
         return None
     z = hit["z"]
     tracked = bool(dec.training and all(m.track_running_stats for m in dec.modules() if isinstance(m, nn.BatchNorm2d)))
@@ -601,8 +603,8 @@ class _DecoderFn(torch.autograd.Function):
         ctx.dec, ctx.tape, ctx.params = dec, tape, params
         ctx.z_shape = tuple(z.shape)
         from . import fastpath
-        _FORWARD_CACHE[id(dec)] = {
-            "dec": dec, "z": z, "version": z._version, "epoch": fastpath._WEIGHTS_EPOCH[0], "out": out, "tape": tape,
+        _FORWARD_CACHE[dec] = {
+            "z": z, "version": z._version, "epoch": fastpath._WEIGHTS_EPOCH[0], "out": out, "tape": tape,
             "tracked": all(m.track_running_stats for m in dec.modules() if isinstance(m, nn.BatchNorm2d))}
         return out
 

@@ -114,3 +114,36 @@ def test_packed_weights_follow_optimizer_updates(env):
         dec.up1.conv[0].weight.div_(1.5)
     assert not torch.equal(a, b)
     _close(b, want)
+
+
+def test_pack_registry_outlives_dead_models_and_moved_weights():
+    """The batched weight packing reads raw pointers from a device job table: a model that died (its memory returned to
+    the driver) or a parameter whose storage moved must not leave stale rows behind -- this used to surface as an illegal
+    memory access in a LATER test's graph replay.  The table pins the storages it names and is rebuilt when a registered
+    weight died or moved."""
+    import gc
+    import cooperative_training_and_latent_space_data_augmentation_b200 as pkg
+    from cooperative_training_and_latent_space_data_augmentation_b200 import fastpath
+    ops = pkg.ops
+    reg = fastpath._REGISTRY
+    a = torch.nn.Conv2d(16, 16, 3, padding=1).cuda()
+    fastpath._packed(a.weight, ops.pack_conv_weight)
+    fastpath.prepare_packing()
+    assert any(e["param"]() is a.weight for e in reg.entries.values())
+    del a
+    gc.collect()
+    torch.cuda.empty_cache()
+    b = torch.nn.Conv2d(32, 16, 3, padding=1).cuda()
+    fastpath._packed(b.weight, ops.pack_conv_weight)                    # registers b: the table is stale now
+    fastpath.weights_changed()
+    got = fastpath._packed(b.weight, ops.pack_conv_weight)              # refresh through a rebuilt table
+    torch.cuda.synchronize()
+    assert all(e["param"]() is not None for k, e in reg.entries.items() if k in reg.table_keys)
+    assert torch.equal(got, ops.pack_conv_weight(b.weight))
+    with torch.no_grad():
+        b.weight.data = (b.weight.data * 2).clone()                     # storage replaced behind the registry's back
+    fastpath.weights_changed()
+    got = fastpath._packed(b.weight, ops.pack_conv_weight)
+    torch.cuda.synchronize()
+    assert torch.equal(got, ops.pack_conv_weight(b.weight))
+    assert reg._table_is_current()
