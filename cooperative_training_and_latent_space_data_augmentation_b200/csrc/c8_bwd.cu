@@ -189,6 +189,85 @@ plane_reduce_kernel(const uint4* __restrict__ x, const uint4* __restrict__ h, co
   }
 }
 
+// The BatchNorm-backward reduction for large planes (HW >= 2048, activation input recomputed from a), persistent and
+// structured like bn_bwd_apply_planes_kernel: a work item is U*kT consecutive positions of one 8-channel plane, items
+// are visited CHANNEL-GROUP-major (all planes of channels 0-7 first, ...), so a CTA's running sums stay valid across
+// items and are flushed -- warp shuffles, shared memory, ONE fp64 atomic per statistic -- only when its channel group
+// changes (at most C/8 times) instead of once per short-lived CTA; the activation affine sits in registers.
+template <int U>
+__global__ void __launch_bounds__(kT, 3)
+bn_bwd_reduce_items_kernel(const uint4* __restrict__ dy, const uint4* __restrict__ a, int N, int C8, int HW,
+                           int items_per_plane, int act, const float* __restrict__ act_scale,
+                           const float* __restrict__ act_shift, double* __restrict__ totals) {
+  pdl_entry();
+  __shared__ double red[kT / 32][16];
+  const bool with_act = act_scale != nullptr && act != CTL_ACT_NONE;
+  const float neg = !with_act ? 1.0f : (act == CTL_ACT_LRELU ? 0.2f : 0.0f);
+  const int64_t per_group = (int64_t)N * items_per_plane, items = per_group * C8;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  float s[8], q[8], asc[8], ash[8];
+  int cur = -1;
+  auto flush = [&]() {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        s[j] += __shfl_xor_sync(0xffffffffu, s[j], o);
+        q[j] += __shfl_xor_sync(0xffffffffu, q[j], o);
+      }
+    }
+    __syncthreads();                                      // the previous flush's readers are done with `red`
+    if (lane == 0) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) { red[warp][j] = (double)s[j]; red[warp][8 + j] = (double)q[j]; }
+    }
+    __syncthreads();
+    if (threadIdx.x < 16) {
+      double t = 0.0;
+      for (int w = 0; w < kT / 32; ++w) t += red[w][threadIdx.x];
+      const int j = threadIdx.x & 7, second = threadIdx.x >> 3;
+      atomicAdd(totals + second * (C8 * 8) + cur * 8 + j, t);
+    }
+  };
+  for (int64_t item = blockIdx.x; item < items; item += gridDim.x) {
+    const int c8 = (int)(item / per_group);
+    const int64_t r = item - (int64_t)c8 * per_group;
+    const int n = (int)(r / items_per_plane), chunk = (int)(r - (int64_t)n * items_per_plane);
+    if (c8 != cur) {                                      // block-uniform
+      if (cur >= 0) flush();
+      cur = c8;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        s[j] = 0.0f; q[j] = 0.0f;
+        asc[j] = with_act ? __ldg(act_scale + c8 * 8 + j) : 1.0f;
+        ash[j] = with_act ? __ldg(act_shift + c8 * 8 + j) : 0.0f;
+      }
+    }
+    const int p0 = chunk * (U * kT) + threadIdx.x;
+    const int64_t base = ((int64_t)n * C8 + c8) * HW;
+    uint4 xv[U], av4[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const bool ok = p0 + u * kT < HW;
+      xv[u] = ok ? __ldcs(dy + base + p0 + u * kT) : make_uint4(0, 0, 0, 0);
+      av4[u] = ok ? __ldg(a + base + p0 + u * kT) : make_uint4(0, 0, 0, 0);
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {                          // positions past the plane were loaded as zeros: dv = 0
+      float f[8], av[8];
+      unpack8(xv[u], f);
+      unpack8(av4[u], av);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float dv = f[j] * (fmaf(av[j], asc[j], ash[j]) > 0.0f ? 1.0f : neg);
+        s[j] += dv;
+        q[j] = fmaf(dv, av[j], q[j]);
+      }
+    }
+  }
+  if (cur >= 0) flush();
+}
+
 // resident CTAs of the reduction per SM (register-limited; queried once per variant)
 template <int MODE, bool WITH_H = (MODE == 1)>
 int reduce_ctas_per_sm() {
@@ -1002,6 +1081,23 @@ extern "C" int ctl_bn_bwd_c8(const void* dy, const void* h, const void* a, int64
     launch_chained(plane_reduce_kernel<1, true>, dim3((unsigned)planes, (unsigned)splits), kT, 0, st)(
         (const uint4*)dy, (const uint4*)h, (const uint4*)a, (uint4*)dv_out, nullptr, planes, HW, splits, act, act_scale,
         act_shift, (int)(C / 8), totals);
+  } else if (HW >= 2048 && HW < ((int64_t)1 << 30) && N < ((int64_t)1 << 20)) {
+    static int resident[2] = {0, 0};                      // CTAs per SM of the U = 2 / U = 4 forms
+    const int U = HW >= 8192 ? 4 : 2;
+    int& res = resident[U == 4];
+    if (res == 0) {
+      if (U == 4) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&res, bn_bwd_reduce_items_kernel<4>, kT, 0);
+      else cudaOccupancyMaxActiveBlocksPerMultiprocessor(&res, bn_bwd_reduce_items_kernel<2>, kT, 0);
+      if (res <= 0) res = 3;
+    }
+    const int ipp = (int)ceil_div(HW, (int64_t)U * kT);
+    const unsigned grid = (unsigned)std::min<int64_t>(planes * ipp, (int64_t)sm_count() * res);
+    if (U == 4)
+      launch_chained(bn_bwd_reduce_items_kernel<4>, grid, kT, 0, st)((const uint4*)dy, (const uint4*)a, (int)N, (int)(C / 8),
+                                                                     (int)HW, ipp, act, act_scale, act_shift, totals);
+    else
+      launch_chained(bn_bwd_reduce_items_kernel<2>, grid, kT, 0, st)((const uint4*)dy, (const uint4*)a, (int)N, (int)(C / 8),
+                                                                     (int)HW, ipp, act, act_scale, act_shift, totals);
   } else {
     const int splits = plane_splits(planes, HW, reduce_ctas_per_sm<1, false>());
     launch_chained(plane_reduce_kernel<1, false>, dim3((unsigned)planes, (unsigned)splits), kT, 0, st)(

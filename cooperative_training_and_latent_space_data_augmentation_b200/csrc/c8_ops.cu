@@ -284,6 +284,78 @@ scale_shift_act_c8_kernel(const uint4* __restrict__ x, uint4* __restrict__ y, co
   }
 }
 
+// The same pass for large planes (HW >= 2048), structured by plane: a work item is U*kT consecutive positions of one
+// 8-channel plane -- scale / shift of its channels in registers, no 64-bit division and no per-position parameter
+// loads, all U loads of an item in flight before the first use.
+template <int U>
+__global__ void __launch_bounds__(kT, 4)
+scale_shift_act_planes_kernel(const uint4* __restrict__ x, uint4* __restrict__ y, const float* __restrict__ scale,
+                              const float* __restrict__ shift, int64_t planes, int C8, int HW, int items_per_plane, int act,
+                              const BnFwdSums bn) {
+  pdl_entry();
+  __shared__ float s_scale[kMaxBnC], s_shift[kMaxBnC];
+  if (bn.sums != nullptr) {
+    bn_fwd_prologue(bn, C8 * 8, s_scale, s_shift);
+    scale = s_scale;
+    shift = s_shift;
+  }
+  const int64_t items = planes * items_per_plane;
+  float sc[8], sh[8];
+  int cur_c0 = -1;
+  for (int64_t item = blockIdx.x; item < items; item += gridDim.x) {
+    const int64_t plane = item / items_per_plane;
+    const int chunk = (int)(item - plane * items_per_plane);
+    const int c0 = (int)(plane % C8) * 8;
+    if (c0 != cur_c0) {                                   // block-uniform
+      cur_c0 = c0;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) { sc[j] = scale ? scale[c0 + j] : 1.0f; sh[j] = shift ? shift[c0 + j] : 0.0f; }
+    }
+    const int p0 = chunk * (U * kT) + threadIdx.x;
+    const int64_t base = plane * HW;
+    uint4 xv[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) xv[u] = p0 + u * kT < HW ? __ldcs(x + base + p0 + u * kT) : make_uint4(0, 0, 0, 0);
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      if (p0 + u * kT < HW) {
+        float f[8];
+        unpack8(xv[u], f);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) f[j] = act_fn(fmaf(f[j], sc[j], sh[j]), act);
+        y[base + p0 + u * kT] = pack8(f);
+      }
+    }
+  }
+}
+
+// launches the plane-structured form for planes of >= 2048 positions, else the generic one
+int launch_scale_shift_act(const uint4* x, uint4* y, const float* scale, const float* shift, int64_t planes, int C8,
+                           int64_t HW, int act, const BnFwdSums& bn, cudaStream_t st) {
+  const int64_t total = planes * HW;
+  if (HW >= 2048 && HW < ((int64_t)1 << 30)) {
+    static int resident[2] = {0, 0};
+    const int U = HW >= 8192 ? 4 : 2;
+    int& res = resident[U == 4];
+    if (res == 0) {
+      if (U == 4) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&res, scale_shift_act_planes_kernel<4>, kT, 0);
+      else cudaOccupancyMaxActiveBlocksPerMultiprocessor(&res, scale_shift_act_planes_kernel<2>, kT, 0);
+      if (res <= 0) res = 4;
+    }
+    const int ipp = (int)ceil_div(HW, (int64_t)U * kT);
+    const unsigned grid = (unsigned)std::min<int64_t>(planes * ipp, (int64_t)sm_count() * res);
+    if (U == 4) launch_chained(scale_shift_act_planes_kernel<4>, grid, kT, 0, st)(x, y, scale, shift, planes, C8, (int)HW, ipp, act, bn);
+    else launch_chained(scale_shift_act_planes_kernel<2>, grid, kT, 0, st)(x, y, scale, shift, planes, C8, (int)HW, ipp, act, bn);
+  } else {
+    const unsigned grid = bn.sums != nullptr
+                              ? (unsigned)std::max<int64_t>(1, std::min<int64_t>(ceil_div(total, kT), (int64_t)sm_count() * 8))
+                              : (unsigned)std::min<int64_t>(ceil_div(total, kT), (int64_t)sm_count() * 16);
+    launch_chained(scale_shift_act_c8_kernel, grid, kT, 0, st)(x, y, scale, shift, total, C8, HW, act, bn);
+  }
+  CTL_CUDA_OK(cudaGetLastError(), "scale_shift_act launch");
+  return CTL_OK;
+}
+
 // y = act(x*scale[c] + shift[c] + low[.., h/2, w/2]): the tail of a nearest-x2 residual up block whose 1x1 shortcut was
 // evaluated BEFORE the up-sampling (conv1x1(up(x)) == up(conv1x1(x))).  One thread per LOW-resolution pixel: 16 B of
 // `low`, a 2x2 block of x in, a 2x2 block of y out.  scale / shift may be NULL (1 / 0).
@@ -538,10 +610,7 @@ extern "C" int ctl_bn_apply_from_sums_c8(const void* x, int64_t N, int64_t C, in
                                                                     nullptr, planes, (int)(C / 8), (int)(H / 2), (int)(W / 2),
                                                                     act, bn);
   } else {
-    const int64_t total = planes * H * W;
-    const unsigned grid = (unsigned)std::max<int64_t>(1, std::min<int64_t>(ceil_div(total, kT), (int64_t)sm_count() * 8));
-    launch_chained(scale_shift_act_c8_kernel, grid, kT, 0, st)((const uint4*)x, (uint4*)y, nullptr, nullptr, total,
-                                                               (int)(C / 8), H * W, act, bn);
+    return launch_scale_shift_act((const uint4*)x, (uint4*)y, nullptr, nullptr, planes, (int)(C / 8), H * W, act, bn, st);
   }
   CTL_CUDA_OK(cudaGetLastError(), "bn_apply_from_sums launch");
   return CTL_OK;
@@ -552,9 +621,6 @@ extern "C" int ctl_scale_shift_act_c8(const void* x, int64_t N, int64_t C, int64
   CTL_REQUIRE(x && y && scale && shift && N > 0 && C > 0 && C % 8 == 0 && H > 0 && W > 0, CTL_ERR_INVALID,
               "ctl_scale_shift_act_c8: bad arguments");
   if (sm_count() < 0) return CTL_ERR_CUDA;
-  const int64_t total = N * (C / 8) * H * W;
-  launch_chained(scale_shift_act_c8_kernel, grid_for(total), kT, 0, (cudaStream_t)stream)((const uint4*)x, (uint4*)y, scale, shift,
-                                                                            total, (int)(C / 8), H * W, act, BnFwdSums{});
-  CTL_CUDA_OK(cudaGetLastError(), "scale_shift_act launch");
-  return CTL_OK;
+  return launch_scale_shift_act((const uint4*)x, (uint4*)y, scale, shift, N * (C / 8), (int)(C / 8), H * W, act, BnFwdSums{},
+                                (cudaStream_t)stream);
 }

@@ -146,4 +146,5 @@ def test_pack_registry_outlives_dead_models_and_moved_weights():
     got = fastpath._packed(b.weight, ops.pack_conv_weight)
     torch.cuda.synchronize()
     assert torch.equal(got, ops.pack_conv_weight(b.weight))
-    assert reg._table_is_current()
+    fastpath.prepare_packing()                                          # the re-registered weight made the table dirty
+    assert reg._table_is_current() and not reg.dirty

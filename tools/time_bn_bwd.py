@@ -18,4 +18,5 @@ for C, S in ((16, 224), (32, 112)):
     for _ in range(3):
         totals = torch.zeros(2 * C, device="cuda", dtype=torch.float64)
         ops.bn_act_bwd_c8(dy, None, a, ops.ACT_LRELU, mean, var, 1e-5, gamma, act_affine=(scale, shift), totals=totals)
+        ops.scale_shift_act_c8(a, scale, shift, ops.ACT_LRELU)
 torch.cuda.synchronize()
