@@ -194,14 +194,17 @@ plane_reduce_kernel(const uint4* __restrict__ x, const uint4* __restrict__ h, co
 // are visited CHANNEL-GROUP-major (all planes of channels 0-7 first, ...), so a CTA's running sums stay valid across
 // items and are flushed -- warp shuffles, shared memory, ONE fp64 atomic per statistic -- only when its channel group
 // changes (at most C/8 times) instead of once per short-lived CTA; the activation affine sits in registers.
-template <int U>
+// WITH_H: the activation slope comes from the layer output h (residual tails: h = act(BN(a) + shortcut) cannot be
+// recomputed from a), and dv may be materialised (bf16; the sums are then taken over the rounded values the consumers read).
+template <int U, bool WITH_H>
 __global__ void __launch_bounds__(kT, 3)
-bn_bwd_reduce_items_kernel(const uint4* __restrict__ dy, const uint4* __restrict__ a, int N, int C8, int HW,
-                           int items_per_plane, int act, const float* __restrict__ act_scale,
-                           const float* __restrict__ act_shift, double* __restrict__ totals) {
+bn_bwd_reduce_items_kernel(const uint4* __restrict__ dy, const uint4* __restrict__ h, const uint4* __restrict__ a,
+                           uint4* __restrict__ dv_out, int N, int C8, int HW, int items_per_plane, int act,
+                           const float* __restrict__ act_scale, const float* __restrict__ act_shift,
+                           double* __restrict__ totals) {
   pdl_entry();
   __shared__ double red[kT / 32][16];
-  const bool with_act = act_scale != nullptr && act != CTL_ACT_NONE;
+  const bool with_act = (WITH_H || act_scale != nullptr) && act != CTL_ACT_NONE;
   const float neg = !with_act ? 1.0f : (act == CTL_ACT_LRELU ? 0.2f : 0.0f);
   const int64_t per_group = (int64_t)N * items_per_plane, items = per_group * C8;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -239,29 +242,43 @@ bn_bwd_reduce_items_kernel(const uint4* __restrict__ dy, const uint4* __restrict
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
         s[j] = 0.0f; q[j] = 0.0f;
-        asc[j] = with_act ? __ldg(act_scale + c8 * 8 + j) : 1.0f;
-        ash[j] = with_act ? __ldg(act_shift + c8 * 8 + j) : 0.0f;
+        asc[j] = (!WITH_H && with_act) ? __ldg(act_scale + c8 * 8 + j) : 1.0f;
+        ash[j] = (!WITH_H && with_act) ? __ldg(act_shift + c8 * 8 + j) : 0.0f;
       }
     }
     const int p0 = chunk * (U * kT) + threadIdx.x;
     const int64_t base = ((int64_t)n * C8 + c8) * HW;
-    uint4 xv[U], av4[U];
+    uint4 xv[U], av4[U], hv4[WITH_H ? U : 1];
 #pragma unroll
     for (int u = 0; u < U; ++u) {
       const bool ok = p0 + u * kT < HW;
       xv[u] = ok ? __ldcs(dy + base + p0 + u * kT) : make_uint4(0, 0, 0, 0);
       av4[u] = ok ? __ldg(a + base + p0 + u * kT) : make_uint4(0, 0, 0, 0);
+      if (WITH_H) hv4[WITH_H ? u : 0] = ok ? __ldg(h + base + p0 + u * kT) : make_uint4(0, 0, 0, 0);
     }
 #pragma unroll
     for (int u = 0; u < U; ++u) {                          // positions past the plane were loaded as zeros: dv = 0
       float f[8], av[8];
       unpack8(xv[u], f);
       unpack8(av4[u], av);
+      if constexpr (WITH_H) {
+        float hv[8];
+        unpack8(hv4[WITH_H ? u : 0], hv);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) f[j] *= hv[j] > 0.0f ? 1.0f : neg;
+        if (dv_out != nullptr) {
+          const uint4 packed = pack8(f);
+          if (p0 + u * kT < HW) dv_out[base + p0 + u * kT] = packed;
+          unpack8(packed, f);                               // reduce what the consumers will read (bf16-rounded)
+        }
+      } else {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) f[j] *= fmaf(av[j], asc[j], ash[j]) > 0.0f ? 1.0f : neg;
+      }
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
-        const float dv = f[j] * (fmaf(av[j], asc[j], ash[j]) > 0.0f ? 1.0f : neg);
-        s[j] += dv;
-        q[j] = fmaf(dv, av[j], q[j]);
+        s[j] += f[j];
+        q[j] = fmaf(f[j], av[j], q[j]);
       }
     }
   }
@@ -1076,28 +1093,36 @@ extern "C" int ctl_bn_bwd_c8(const void* dy, const void* h, const void* a, int64
   if (sm_count() < 0) return CTL_ERR_CUDA;
   cudaStream_t st = (cudaStream_t)stream;
   const int64_t planes = N * (C / 8), HW = H * W, total = planes * HW;
-  if (h != nullptr) {
-    const int splits = plane_splits(planes, HW, reduce_ctas_per_sm<1, true>());
-    launch_chained(plane_reduce_kernel<1, true>, dim3((unsigned)planes, (unsigned)splits), kT, 0, st)(
-        (const uint4*)dy, (const uint4*)h, (const uint4*)a, (uint4*)dv_out, nullptr, planes, HW, splits, act, act_scale,
-        act_shift, (int)(C / 8), totals);
-  } else if (HW >= 2048 && HW < ((int64_t)1 << 30) && N < ((int64_t)1 << 20)) {
-    static int resident[2] = {0, 0};                      // CTAs per SM of the U = 2 / U = 4 forms
-    const int U = HW >= 8192 ? 4 : 2;
-    int& res = resident[U == 4];
+  const bool items_form = HW >= 2048 && HW < ((int64_t)1 << 30) && N < ((int64_t)1 << 20) &&
+                          (act == CTL_ACT_NONE || act == CTL_ACT_LRELU || act == CTL_ACT_RELU);
+  if (items_form) {
+    // [with h][U = 4]: CTAs per SM of each form
+    static int resident[2][2] = {{0, 0}, {0, 0}};
+    const int U = (HW >= 8192 && h == nullptr) ? 4 : 2;     // three tensors per position with h: two positions in flight
+    int& res = resident[h != nullptr][U == 4];
     if (res == 0) {
-      if (U == 4) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&res, bn_bwd_reduce_items_kernel<4>, kT, 0);
-      else cudaOccupancyMaxActiveBlocksPerMultiprocessor(&res, bn_bwd_reduce_items_kernel<2>, kT, 0);
+      if (h != nullptr) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&res, bn_bwd_reduce_items_kernel<2, true>, kT, 0);
+      else if (U == 4) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&res, bn_bwd_reduce_items_kernel<4, false>, kT, 0);
+      else cudaOccupancyMaxActiveBlocksPerMultiprocessor(&res, bn_bwd_reduce_items_kernel<2, false>, kT, 0);
       if (res <= 0) res = 3;
     }
     const int ipp = (int)ceil_div(HW, (int64_t)U * kT);
     const unsigned grid = (unsigned)std::min<int64_t>(planes * ipp, (int64_t)sm_count() * res);
-    if (U == 4)
-      launch_chained(bn_bwd_reduce_items_kernel<4>, grid, kT, 0, st)((const uint4*)dy, (const uint4*)a, (int)N, (int)(C / 8),
-                                                                     (int)HW, ipp, act, act_scale, act_shift, totals);
+    if (h != nullptr)
+      launch_chained(bn_bwd_reduce_items_kernel<2, true>, grid, kT, 0, st)(
+          (const uint4*)dy, (const uint4*)h, (const uint4*)a, (uint4*)dv_out, (int)N, (int)(C / 8), (int)HW, ipp, act, act_scale,
+          act_shift, totals);
+    else if (U == 4)
+      launch_chained(bn_bwd_reduce_items_kernel<4, false>, grid, kT, 0, st)(
+          (const uint4*)dy, nullptr, (const uint4*)a, nullptr, (int)N, (int)(C / 8), (int)HW, ipp, act, act_scale, act_shift, totals);
     else
-      launch_chained(bn_bwd_reduce_items_kernel<2>, grid, kT, 0, st)((const uint4*)dy, (const uint4*)a, (int)N, (int)(C / 8),
-                                                                     (int)HW, ipp, act, act_scale, act_shift, totals);
+      launch_chained(bn_bwd_reduce_items_kernel<2, false>, grid, kT, 0, st)(
+          (const uint4*)dy, nullptr, (const uint4*)a, nullptr, (int)N, (int)(C / 8), (int)HW, ipp, act, act_scale, act_shift, totals);
+  } else if (h != nullptr) {
+    const int splits = plane_splits(planes, HW, reduce_ctas_per_sm<1, true>());
+    launch_chained(plane_reduce_kernel<1, true>, dim3((unsigned)planes, (unsigned)splits), kT, 0, st)(
+        (const uint4*)dy, (const uint4*)h, (const uint4*)a, (uint4*)dv_out, nullptr, planes, HW, splits, act, act_scale,
+        act_shift, (int)(C / 8), totals);
   } else {
     const int splits = plane_splits(planes, HW, reduce_ctas_per_sm<1, false>());
     launch_chained(plane_reduce_kernel<1, false>, dim3((unsigned)planes, (unsigned)splits), kT, 0, st)(

@@ -354,10 +354,194 @@ conv_small_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constan
   }
 }
 
+// ---- stride 2 (3x3 pad 1, 16 -> 16 channels): the encoder's first down-sampling convolution.  K3 computes it at full
+// resolution and keeps the even pixels (4x the MMA work, 71 us at 224^2); here the A fragment's eight row addresses are
+// simply every second pixel of the halo row (ldmatrix takes one address per row).  Output tile 16 x 16 from the same
+// 34 x 34 input box; a warp owns 16 output columns x 2 output rows (9 ldmatrix.x4 + 18 mma.sync per row, no row reuse
+// between output rows at this stride) and its 1 KB output block leaves as one bulk tensor store.
+constexpr int kSm2Tile = 16;
+constexpr int kSm2Rows = 2;                                  // output rows per warp
+constexpr int kSm2OutWarpBytes = 2 * kSm2Rows * 16 * 16;     // [2 planes][2 rows][16 px][8 ch]
+
+template <bool STATS>
+__global__ void __launch_bounds__(kSmThreads, 2)
+conv_small_s2_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ CUtensorMap tmap_out, const ConvParams p) {
+  pdl_entry();
+  extern __shared__ __align__(1024) uint8_t smem[];
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem + kSmOffBar);
+  uint64_t* empty = full + kSmStages;
+  float* stat_smem = reinterpret_cast<float*>(smem + kSmOffStat);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (threadIdx.x == 0) {
+    tma_prefetch_desc(&tmap);
+    tma_prefetch_desc(&tmap_out);
+    for (int i = 0; i < kSmStages; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], kSmWarps); }
+    mbar_fence_init();
+  }
+  __syncthreads();
+  const int tiles_per_img = p.tiles_x * p.tiles_y;
+  const int num_tiles = (int)p.num_tiles;
+  const int Ho = p.H >> 1, Wo = p.W >> 1;
+  auto issue_load = [&](int t, int stage) {
+    const int img = small_div(t, p.magic_img);
+    const int rem = t - img * tiles_per_img;
+    const int ty = small_div(rem, p.magic_x), tx = rem - ty * p.tiles_x;
+    mbar_arrive_expect_tx(&full[stage], kSmStageBytes);
+    tma_load_4d(smem + stage * kSmStageBytes, &tmap, &full[stage], (2 * tx * kSm2Tile - 1) * 2, 2 * ty * kSm2Tile - 1, 0, img);
+  };
+  if (warp == 0 && elect_one()) {
+#pragma unroll
+    for (int k = 0; k < kSmStages - 1; ++k)
+      if (blockIdx.x + k * gridDim.x < num_tiles) issue_load(blockIdx.x + k * gridDim.x, k);
+  }
+  const int g = lane >> 2, tq = lane & 3;
+  uint32_t wb[9][2][2];
+  {
+    const uint32_t* w32 = reinterpret_cast<const uint32_t*>(p.w_packed);
+#pragma unroll
+    for (int tap = 0; tap < 9; ++tap)
+#pragma unroll
+      for (int jn = 0; jn < 2; ++jn) {
+        wb[tap][jn][0] = __ldg(w32 + ((tap * 2 + 0) * 16 + 8 * jn + g) * 4 + tq);
+        wb[tap][jn][1] = __ldg(w32 + ((tap * 2 + 1) * 16 + 8 * jn + g) * 4 + tq);
+      }
+  }
+  const bool has_scale = p.scale != nullptr;
+  float sc[2][2], sh[2][2], c_init[2][2];
+#pragma unroll
+  for (int jn = 0; jn < 2; ++jn)
+#pragma unroll
+    for (int e = 0; e < 2; ++e) {
+      const int c = 8 * jn + 2 * tq + e;
+      sc[jn][e] = has_scale ? __ldg(p.scale + c) : 1.0f;
+      sh[jn][e] = p.shift ? __ldg(p.shift + c) : 0.0f;
+      c_init[jn][e] = has_scale ? 0.0f : sh[jn][e];
+    }
+  const int act = p.act;
+  const float slope = act == CTL_ACT_LRELU ? 0.2f : 1.0f;
+  const float act_floor = act == CTL_ACT_RELU ? 0.0f : -INFINITY;
+  float st_s[STATS ? 2 : 1][2], st_q[STATS ? 2 : 1][2];
+#pragma unroll
+  for (int jn = 0; jn < (STATS ? 2 : 1); ++jn) { st_s[jn][0] = st_s[jn][1] = 0.0f; st_q[jn][0] = st_q[jn][1] = 0.0f; }
+  // ldmatrix row address: output pixel px of the strip reads halo column 2*px + s of halo row 2*j + r
+  const int mat = lane >> 3;
+  const uint32_t lane_off = (uint32_t)((mat >> 1) * kSmChunk +
+                                       ((2 * kSm2Rows * warp) * kSmHalo + 2 * ((lane & 7) + 8 * (mat & 1))) * 16);
+  const uint32_t smem_base = smem_u32(smem);
+  uint32_t* const o_warp = reinterpret_cast<uint32_t*>(smem + kSmOffOut + warp * kSm2OutWarpBytes) + lane;
+
+  int stage = 0, prev_stage = kSmStages - 1;
+  uint32_t phase = 0, prev_phase = 1;
+  for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
+    if (warp == 0) {
+      const int t_ahead = t + (kSmStages - 1) * gridDim.x;
+      if (t_ahead < num_tiles && elect_one()) {
+        if (t != (int)blockIdx.x) mbar_wait(&empty[prev_stage], prev_phase);
+        issue_load(t_ahead, prev_stage);
+      }
+      __syncwarp();
+    }
+    const int img = small_div(t, p.magic_img);
+    const int rem = t - img * tiles_per_img;
+    const int ty = small_div(rem, p.magic_x), tx = rem - ty * p.tiles_x;
+    const int y0 = ty * kSm2Tile + kSm2Rows * warp;           // first output row of this warp
+    const int x = tx * kSm2Tile + g;
+    const bool x_ok0 = x < Wo, x_ok1 = x + 8 < Wo;
+    const int rows_ok = Ho - y0;
+    mbar_wait(&full[stage], phase);
+    const uint32_t a_base = smem_base + (uint32_t)(stage * kSmStageBytes) + lane_off;
+    if (t != (int)blockIdx.x) {
+      if (lane == 0) tma_store_wait_read();
+      __syncwarp();
+    }
+#pragma unroll
+    for (int j = 0; j < kSm2Rows; ++j) {
+      float acc[2][4];
+#pragma unroll
+      for (int r = 0; r < 3; ++r) {
+        uint32_t a[3][4];
+#pragma unroll
+        for (int s3 = 0; s3 < 3; ++s3) ldmatrix_x4(a[s3], a_base + (uint32_t)(((2 * j + r) * kSmHalo + s3) * 16));
+#pragma unroll
+        for (int s3 = 0; s3 < 3; ++s3)
+#pragma unroll
+          for (int jn = 0; jn < 2; ++jn) {
+            if (r == 0 && s3 == 0) hmma_16816_first(acc[jn], a[s3], wb[r * 3 + s3][jn], c_init[jn][0], c_init[jn][1]);
+            else hmma_16816(acc[jn], a[s3], wb[r * 3 + s3][jn]);
+          }
+      }
+      if (j == kSm2Rows - 1) {                               // the stage has been read
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&empty[stage]);
+      }
+      float f[2][4];
+#pragma unroll
+      for (int jn = 0; jn < 2; ++jn)
+#pragma unroll
+        for (int v = 0; v < 4; ++v) f[jn][v] = has_scale ? fmaf(acc[jn][v], sc[jn][v & 1], sh[jn][v & 1]) : acc[jn][v];
+      if (act != CTL_ACT_NONE) {
+#pragma unroll
+        for (int jn = 0; jn < 2; ++jn)
+#pragma unroll
+          for (int v = 0; v < 4; ++v) f[jn][v] = fmaxf(fmaxf(f[jn][v], slope * f[jn][v]), act_floor);
+      }
+      const bool y_ok = j < rows_ok;
+#pragma unroll
+      for (int jn = 0; jn < 2; ++jn)
+#pragma unroll
+        for (int hp = 0; hp < 2; ++hp) {
+          const __nv_bfloat162 hh = __floats2bfloat162_rn(f[jn][2 * hp], f[jn][2 * hp + 1]);
+          const uint32_t ow = *reinterpret_cast<const uint32_t*>(&hh);
+          if constexpr (STATS) {
+            const bool ok = y_ok && (hp == 0 ? x_ok0 : x_ok1);
+            const float lo = ok ? bf_lo(ow) : 0.0f, hi = ok ? bf_hi(ow) : 0.0f;
+            st_s[STATS ? jn : 0][0] += lo; st_q[STATS ? jn : 0][0] = fmaf(lo, lo, st_q[STATS ? jn : 0][0]);
+            st_s[STATS ? jn : 0][1] += hi; st_q[STATS ? jn : 0][1] = fmaf(hi, hi, st_q[STATS ? jn : 0][1]);
+          }
+          o_warp[(jn * kSm2Rows + j) * 64 + hp * 32] = ow;
+        }
+    }
+    fence_async_smem();
+    __syncwarp();
+    if (lane == 0) tma_store_4d(&tmap_out, o_warp, (tx * kSm2Tile) * 2, y0, 0, img);
+    prev_stage = stage;
+    prev_phase = phase;
+    if (++stage == kSmStages) { stage = 0; phase ^= 1; }
+  }
+  if (lane == 0) tma_store_wait_all();
+  if constexpr (STATS) {
+#pragma unroll
+    for (int jn = 0; jn < 2; ++jn)
+#pragma unroll
+      for (int e = 0; e < 2; ++e) {
+        float s1 = st_s[jn][e], s2 = st_q[jn][e];
+#pragma unroll
+        for (int o = 4; o < 32; o <<= 1) {
+          s1 += __shfl_xor_sync(0xffffffffu, s1, o);
+          s2 += __shfl_xor_sync(0xffffffffu, s2, o);
+        }
+        if (g == 0) {
+          stat_smem[warp * 32 + 8 * jn + 2 * tq + e] = s1;
+          stat_smem[warp * 32 + 16 + 8 * jn + 2 * tq + e] = s2;
+        }
+      }
+    __syncthreads();
+    if (threadIdx.x < 32) {
+      const int which = threadIdx.x >> 4, c = threadIdx.x & 15;
+      double total = 0.0;
+#pragma unroll
+      for (int w = 0; w < kSmWarps; ++w) total += (double)stat_smem[w * 32 + which * 16 + c];
+      atomicAdd(p.stats + which * p.Cout + c, total);
+    }
+  }
+}
+
 // true when this layer / epilogue combination runs on K3s
 inline bool conv_small_handles(int Cin, int Cout, int taps, const ConvParams& p) {
-  return Cin == 16 && Cout == 16 && taps == 9 && p.subsample == 1 && !p.up2x && p.sal == nullptr && p.act != CTL_ACT_SIGMOID &&
-         ceil_div(p.H, kSmTile) * ceil_div(p.W, kSmTile) < 8192 &&
+  if (!(Cin == 16 && Cout == 16 && taps == 9 && !p.up2x && p.sal == nullptr && p.act != CTL_ACT_SIGMOID)) return false;
+  if (p.subsample == 2)                                      // forward only: no residual / BatchNorm-backward form
+    return p.res == nullptr && p.bnb_act == 0 && ceil_div(p.H / 2, kSm2Tile) * ceil_div(p.W / 2, kSm2Tile) < 8192;
+  return p.subsample == 1 && ceil_div(p.H, kSmTile) * ceil_div(p.W, kSmTile) < 8192 &&
          !(p.stats != nullptr && p.res != nullptr && p.bnb_act == 0);
 }
 
@@ -389,9 +573,38 @@ inline bool conv_small_enabled() {
   return on;
 }
 
+template <bool STATS>
+int launch_conv_small_s2_variant(const CUtensorMap& tmap, const CUtensorMap& tmap_out, const ConvParams& p, cudaStream_t st) {
+  auto kern = conv_small_s2_kernel<STATS>;
+  static int resident = 0;
+  if (resident == 0) {
+    CTL_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmSmemBytes), "conv_small_s2 smem attribute");
+    CTL_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared),
+                "conv_small_s2 carve-out attribute");
+    CTL_CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&resident, kern, kSmThreads, kSmSmemBytes), "conv_small_s2 occupancy");
+    if (resident < 1) resident = 1;
+  }
+  const int ctas = (int)std::min<int64_t>(p.num_tiles, (int64_t)std::min(resident, 2) * sm_count());
+  launch_chained(kern, (unsigned)ctas, kSmThreads, kSmSmemBytes, st)(tmap, tmap_out, p);
+  CTL_CUDA_OK(cudaGetLastError(), "conv_small_s2 launch");
+  return CTL_OK;
+}
+
 int launch_conv_small(const void* x, const ConvParams& p0, cudaStream_t st) {
   ConvParams p = p0;
   p.diag = diag_flags();
+  if (p.subsample == 2) {
+    p.tiles_x = (int)ceil_div(p.W / 2, kSm2Tile);
+    p.tiles_y = (int)ceil_div(p.H / 2, kSm2Tile);
+    p.num_tiles = (int64_t)p.N * p.tiles_x * p.tiles_y;
+    p.magic_img = small_div_magic(p.tiles_x * p.tiles_y);
+    p.magic_x = small_div_magic(p.tiles_x);
+    CUtensorMap tmap, tmap_out;
+    if (int rc = make_act_tmap(&tmap, x, p.N, p.H, p.W, 16, kSmHalo, kSmHalo)) return rc;
+    if (int rc = make_act_tmap(&tmap_out, p.out, p.N, p.H / 2, p.W / 2, 16, 16, kSm2Rows)) return rc;
+    return p.stats != nullptr ? launch_conv_small_s2_variant<true>(tmap, tmap_out, p, st)
+                              : launch_conv_small_s2_variant<false>(tmap, tmap_out, p, st);
+  }
   p.tiles_x = (int)ceil_div(p.W, kSmTile);
   p.tiles_y = (int)ceil_div(p.H, kSmTile);
   p.num_tiles = (int64_t)p.N * p.tiles_x * p.tiles_y;

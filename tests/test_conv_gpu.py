@@ -211,3 +211,22 @@ def test_small_channel_kernel_geometries_and_epilogues(ops, N, H, W, variant):
         torch.testing.assert_close(stats[0], stored.sum((0, 2, 3)), rtol=1e-5, atol=1e-4)
         torch.testing.assert_close(stats[1], (stored * stored).sum((0, 2, 3)), rtol=1e-5, atol=1e-4)
     _check(got, want)
+
+
+@pytest.mark.parametrize("N,H,W", [(1, 2, 2), (2, 34, 30), (1, 64, 64), (3, 18, 66), (2, 224, 224)])
+@pytest.mark.parametrize("with_stats", [False, True])
+def test_small_channel_kernel_stride2(ops, N, H, W, with_stats):
+    """K3s stride-2 form (16 -> 16 channel 3x3 pad 1, the encoder's first down-sampling convolution): 16 x 16 output
+    tiles, every second halo pixel as the A fragment's rows, against fp32 torch; optional statistics of the stored values."""
+    g = torch.Generator(device="cuda").manual_seed(N * 1000 + H * 10 + W)
+    x = torch.randn(N, 16, H, W, device="cuda", generator=g).to(torch.bfloat16)
+    w = torch.randn(16, 16, 3, 3, device="cuda", generator=g) * (2.0 / 144) ** 0.5
+    shift = 0.3 * torch.randn(16, device="cuda", generator=g)
+    stats = torch.zeros(2, 16, device="cuda", dtype=torch.float64) if with_stats else None
+    got = ops.conv2d_c8(ops.nchw_to_c8(x), ops.pack_conv_weight_s2(w), 16, 9, subsample=2, shift=shift, act=1, stats=stats)
+    assert tuple(got.shape) == (N, 2, H // 2, W // 2, 8)
+    _check(got, _ref(x, w, 3, 2, None, shift, None, None, None, 1))
+    if with_stats:
+        stored = ops.c8_to_nchw(got).double()
+        torch.testing.assert_close(stats[0], stored.sum((0, 2, 3)), rtol=1e-5, atol=1e-4)
+        torch.testing.assert_close(stats[1], (stored * stored).sum((0, 2, 3)), rtol=1e-5, atol=1e-4)
