@@ -78,6 +78,7 @@ struct ConvParams {
   int diag;                           // profiling only (env CTL_DIAG_SKIP): 1 no MMA, 2 no TMA loads, 4 no epilogue memory traffic, 8 no epilogue
 };
 
+#include "ctl_hmma.cuh"
 #include "conv_small.cuh"   // K3s: the 16 -> 16 channel 3x3 layers on the warp-level tensor path
 
 template <int CIN, int NT, int TAPS, int MT, int STAGES, bool VP = false>
