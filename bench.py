@@ -624,7 +624,12 @@ def run_gpu_arm(args):
         "roofline_conv": {"kernel": "conv_small_kernel (K3s, warp-level tensor path) 16->16 3x3 @%d^2, batch %d (largest share of the step's device time)"
                                     % (args.size, args.batch), "bound": "hbm", "achieved": top.get("GBps"),
                           "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": top.get("hbm_frac"),
-                          "tensor_frac_of_burst_peak": top.get("tensor_frac"), "avg_launch_us": top.get("us")},
+                          "tensor_frac_of_burst_peak": top.get("tensor_frac"), "avg_launch_us": top.get("us"),
+                          # one ncu --set full capture of this kernel at this shape (dram read 102.8 MB + write 55.8 MB: part of
+                          # the 103 MB output is still in L2 when the kernel ends); algorithmic bytes are 2 x 102.8 MB
+                          "traffic": 158626048.0 if (args.size == 224 and args.batch == 64) else None,
+                          "traffic_source": "profiles/r2_k3s_ncu_summary.csv (plain variant)",
+                          "algorithmic_bytes_per_launch": 2.0 * args.batch * 16 * args.size * args.size * 2},
         "peak_convention": "kernels timed alone (roofline, roofline_conv, conv_blocks, masking_*) are divided by the BURST "
                            "peaks of MEASURED_PEAKS.json (hbm_gbs %.1f GB/s, bf16_tflops %.1f); the whole step "
                            "(step_tensor_frac) by the SUSTAINED bf16 peak (%.1f)"

@@ -24,7 +24,7 @@
 extern "C" {
 #endif
 
-#define CTL_B200_VERSION 200 /* 0.2.0 */
+#define CTL_B200_VERSION 201 /* 0.2.1: + ctl_bn_apply_from_sums_c8 */
 
 enum ctl_status {
   CTL_OK = 0,

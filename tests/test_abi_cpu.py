@@ -31,7 +31,7 @@ def test_library_exports_every_declared_symbol():
         assert hasattr(lib, name), "libctl_b200.so does not export %s" % name
     # the ctypes table binds exactly the declared set
     assert sorted(_lib.SIGNATURES) == names
-    assert _lib.load().ctl_version() == 200
+    assert _lib.load().ctl_version() == 201
 
 
 def test_host_side_validation_without_gpu():
