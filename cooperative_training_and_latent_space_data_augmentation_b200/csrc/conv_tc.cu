@@ -6,6 +6,8 @@
 //   3x3 stride-1 pad-1 (TAPS = 9), 1x1 (TAPS = 1), and 3x3 stride-2 pad-1 as "compute at full
 //   resolution, keep even pixels" (the MMA is far from the bottleneck on these HBM-bound layers),
 //   Cin in {16,32,64,128}, Cout a multiple of 16.
+// The 16 -> 16 channel 3x3 layers (stride 1 and 2) are dispatched to K3s (conv_small.cuh, warp-level tensor path) by
+// the same entry points: with N = 16 this kernel is bound by its shared-memory operand fetch (see there).
 //
 // Data layout in HBM ("blocked", C8): activations are bf16 [N][C/8][H][W][8] -- channels in groups of eight,
 // each group a dense H x W plane of 16-byte pixels.  This is the layout the tensor core consumes: ONE TMA box
