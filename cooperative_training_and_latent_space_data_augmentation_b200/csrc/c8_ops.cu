@@ -399,6 +399,96 @@ scale_shift_upadd_act_c8_kernel(const uint4* __restrict__ x, const uint4* __rest
   }
 }
 
+// The same pass for large planes (>= 2048 low-resolution positions), structured by plane like
+// scale_shift_act_planes_kernel: per-channel values in registers, one multiply-shift instead of two divisions per
+// low-resolution pixel, the 2 * (1 + 4) loads of an item in flight before the first use.
+__device__ __forceinline__ int div44(int n, uint64_t magic) { return (int)(((uint64_t)(uint32_t)n * magic) >> 44); }
+template <int U>
+__global__ void __launch_bounds__(kT, 2)
+scale_shift_upadd_act_planes_kernel(const uint4* __restrict__ x, const uint4* __restrict__ low, uint4* __restrict__ y,
+                                    const float* __restrict__ scale, const float* __restrict__ shift, int64_t planes, int C8,
+                                    int Hl, int Wl, int items_per_plane, int act, const BnFwdSums bn, uint64_t magic_w) {
+  pdl_entry();
+  __shared__ float s_scale[kMaxBnC], s_shift[kMaxBnC];
+  if (bn.sums != nullptr) {
+    bn_fwd_prologue(bn, C8 * 8, s_scale, s_shift);
+    scale = s_scale;
+    shift = s_shift;
+  }
+  const int HWl = Hl * Wl;
+  const int64_t items = planes * items_per_plane;
+  float sc[8], sh[8];
+  int cur_c0 = -1;
+  for (int64_t item = blockIdx.x; item < items; item += gridDim.x) {
+    const int64_t plane = item / items_per_plane;
+    const int chunk = (int)(item - plane * items_per_plane);
+    const int c0 = (int)(plane % C8) * 8;
+    if (c0 != cur_c0) {                                   // block-uniform
+      cur_c0 = c0;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) { sc[j] = scale ? scale[c0 + j] : 1.0f; sh[j] = shift ? shift[c0 + j] : 0.0f; }
+    }
+    const int p0 = chunk * (U * kT) + threadIdx.x;
+    uint4 lo4[U], in[U][4];
+    int64_t base[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int p = p0 + u * kT;
+      const bool ok = p < HWl;
+      const int yy = div44(ok ? p : 0, magic_w), xx = (ok ? p : 0) - yy * Wl;
+      base[u] = plane * 4 * HWl + (int64_t)(2 * yy) * (2 * Wl) + 2 * xx;
+      lo4[u] = ok ? __ldg(low + plane * HWl + p) : make_uint4(0, 0, 0, 0);
+      in[u][0] = ok ? __ldcs(x + base[u]) : make_uint4(0, 0, 0, 0);
+      in[u][1] = ok ? __ldcs(x + base[u] + 1) : make_uint4(0, 0, 0, 0);
+      in[u][2] = ok ? __ldcs(x + base[u] + 2 * Wl) : make_uint4(0, 0, 0, 0);
+      in[u][3] = ok ? __ldcs(x + base[u] + 2 * Wl + 1) : make_uint4(0, 0, 0, 0);
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      if (p0 + u * kT < HWl) {
+        float lo[8], sl[8];
+        unpack8(lo4[u], lo);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) sl[j] = sh[j] + lo[j];
+        const int64_t offs[4] = {base[u], base[u] + 1, base[u] + 2 * Wl, base[u] + 2 * Wl + 1};
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          float f[8];
+          unpack8(in[u][q], f);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) f[j] = act_fn(f[j] * sc[j] + sl[j], act);
+          y[offs[q]] = pack8(f);
+        }
+      }
+    }
+  }
+}
+
+int launch_scale_shift_upadd_act(const uint4* x, const uint4* low, uint4* y, const float* scale, const float* shift,
+                                 int64_t planes, int C8, int Hl, int Wl, int act, const BnFwdSums& bn, cudaStream_t st) {
+  const int64_t HWl = (int64_t)Hl * Wl, work = planes * HWl;
+  if (HWl >= 2048 && HWl < ((int64_t)1 << 28) && Wl < 8192) {
+    constexpr int U = 2;
+    static int res = 0;
+    if (res == 0) {
+      cudaOccupancyMaxActiveBlocksPerMultiprocessor(&res, scale_shift_upadd_act_planes_kernel<U>, kT, 0);
+      if (res <= 0) res = 3;
+    }
+    const int ipp = (int)ceil_div(HWl, (int64_t)U * kT);
+    const unsigned grid = (unsigned)std::min<int64_t>(planes * ipp, (int64_t)sm_count() * res);
+    const uint64_t magic_w = (((uint64_t)1 << 44) + (uint64_t)Wl - 1) / (uint64_t)Wl;
+    launch_chained(scale_shift_upadd_act_planes_kernel<U>, grid, kT, 0, st)(x, low, y, scale, shift, planes, C8, Hl, Wl, ipp, act,
+                                                                           bn, magic_w);
+  } else {
+    const unsigned grid = bn.sums != nullptr
+                              ? (unsigned)std::max<int64_t>(1, std::min<int64_t>(ceil_div(work, kT), (int64_t)sm_count() * 8))
+                              : (unsigned)std::min<int64_t>(ceil_div(work, kT), (int64_t)sm_count() * 16);
+    launch_chained(scale_shift_upadd_act_c8_kernel, grid, kT, 0, st)(x, low, y, scale, shift, planes, C8, Hl, Wl, act, bn);
+  }
+  CTL_CUDA_OK(cudaGetLastError(), "scale_shift_upadd_act launch");
+  return CTL_OK;
+}
+
 // ------------------------------------------------------------------------------------------------ weight packing
 // fp32 nn.Conv2d weight [Cout][Cin][k][k] -> bf16 [Cout'/NT][taps][Cin'/8][NT][8] (the K-major core-matrix order of
 // conv_tc.cu).  transposed == 0: the forward weight (Cout' = Cout, Cin' = Cin).  transposed == 1: the weight of the
@@ -579,11 +669,8 @@ extern "C" int ctl_scale_shift_upadd_act_c8(const void* x, int64_t N, int64_t C,
   CTL_REQUIRE(act >= CTL_ACT_NONE && act <= CTL_ACT_SIGMOID, CTL_ERR_INVALID, "unknown activation %d", act);
   if (sm_count() < 0) return CTL_ERR_CUDA;
   const int64_t planes = N * (C / 8);
-  launch_chained(scale_shift_upadd_act_c8_kernel, grid_for(planes * (H / 2) * (W / 2)), kT, 0, (cudaStream_t)stream)(
-      (const uint4*)x, (const uint4*)low, (uint4*)y, scale, shift, planes, (int)(C / 8), (int)(H / 2), (int)(W / 2), act,
-      BnFwdSums{});
-  CTL_CUDA_OK(cudaGetLastError(), "scale_shift_upadd_act launch");
-  return CTL_OK;
+  return launch_scale_shift_upadd_act((const uint4*)x, (const uint4*)low, (uint4*)y, scale, shift, planes, (int)(C / 8),
+                                      (int)(H / 2), (int)(W / 2), act, BnFwdSums{}, (cudaStream_t)stream);
 }
 
 extern "C" int ctl_bn_apply_from_sums_c8(const void* x, int64_t N, int64_t C, int64_t H, int64_t W, const double* sums,
@@ -604,16 +691,11 @@ extern "C" int ctl_bn_apply_from_sums_c8(const void* x, int64_t N, int64_t C, in
   const int64_t planes = N * (C / 8);
   // every CTA pays the per-channel prologue: a few CTAs per SM striding over the tensor amortise it
   if (low) {
-    const int64_t work = planes * (H / 2) * (W / 2);
-    const unsigned grid = (unsigned)std::max<int64_t>(1, std::min<int64_t>(ceil_div(work, kT), (int64_t)sm_count() * 8));
-    launch_chained(scale_shift_upadd_act_c8_kernel, grid, kT, 0, st)((const uint4*)x, (const uint4*)low, (uint4*)y, nullptr,
-                                                                    nullptr, planes, (int)(C / 8), (int)(H / 2), (int)(W / 2),
-                                                                    act, bn);
+    return launch_scale_shift_upadd_act((const uint4*)x, (const uint4*)low, (uint4*)y, nullptr, nullptr, planes, (int)(C / 8),
+                                        (int)(H / 2), (int)(W / 2), act, bn, st);
   } else {
     return launch_scale_shift_act((const uint4*)x, (uint4*)y, nullptr, nullptr, planes, (int)(C / 8), H * W, act, bn, st);
   }
-  CTL_CUDA_OK(cudaGetLastError(), "bn_apply_from_sums launch");
-  return CTL_OK;
 }
 
 extern "C" int ctl_scale_shift_act_c8(const void* x, int64_t N, int64_t C, int64_t H, int64_t W, const float* scale,
