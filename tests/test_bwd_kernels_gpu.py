@@ -333,3 +333,61 @@ def test_bn_finalisation_in_the_apply_prologue(ops, C, H, W, with_low, act):
         v = v + F.interpolate(ops.c8_to_nchw(low).float(), scale_factor=2, mode="nearest")
     v = F.leaky_relu(v, 0.2) if act == 1 else F.relu(v) if act == 2 else v
     _cmp(ops.c8_to_nchw(got[0]), v, 1e-2, "against F.batch_norm")
+
+
+@pytest.mark.parametrize("C,H,W", [(16, 47, 53), (16, 97, 101), (32, 64, 64), (64, 46, 46)])
+@pytest.mark.parametrize("form", ["from_a", "with_h_dv"])
+def test_plane_structured_bn_backward(ops, C, H, W, form):
+    """The persistent, plane-structured BatchNorm-backward kernels (planes of >= 2048 positions: U = 2 below 8192, U = 4
+    above; odd sizes leave ragged last items) against torch autograd in fp32 on the same bf16 operands: the reduction
+    with the activation recomputed from a, and the residual-tail form (slope from h, dv materialised)."""
+    g = torch.Generator(device="cuda").manual_seed(C + H)
+    N = 3
+    a = _bf(N, C, H, W, gen=g) * 1.5 + 0.3
+    dy = _bf(N, C, H, W, gen=g, scale=0.1)
+    gamma = 1 + 0.2 * torch.randn(C, device="cuda", generator=g)
+    beta = 0.3 * torch.randn(C, device="cuda", generator=g)
+    ac = ops.nchw_to_c8(a)
+    scale, shift, mean, var = ops.bn_batch_affine_c8(ac, gamma, beta, 1e-5, want_stats=True)
+    h = ops.scale_shift_act_c8(ac, scale, shift, ops.ACT_LRELU)
+    af = a.float().requires_grad_(True)
+    gf, bf_ = gamma.clone().requires_grad_(True), beta.clone().requires_grad_(True)
+    v = F.batch_norm(af, None, None, gf, bf_, True, 0.1, 1e-5)
+    _cmp(ops.c8_to_nchw(h), F.leaky_relu(v, 0.2).detach(), 1.5e-2, "forward apply")
+    hk = ops.c8_to_nchw(h)
+    slope = torch.where(hk > 0, 1.0, 0.2)
+    v.backward(dy.float() * slope)
+    totals = torch.zeros(2 * C, device="cuda", dtype=torch.float64)
+    if form == "from_a":
+        da, dg, db, _ = ops.bn_act_bwd_c8(ops.nchw_to_c8(dy), None, ac, ops.ACT_LRELU, mean, var, 1e-5, gamma,
+                                          act_affine=(scale, shift), totals=totals)
+    else:
+        da, dg, db, dv = ops.bn_act_bwd_c8(ops.nchw_to_c8(dy), h, ac, ops.ACT_LRELU, mean, var, 1e-5, gamma, want_dv=True,
+                                           totals=totals)
+        _cmp(ops.c8_to_nchw(dv), dy.float() * slope, 1e-2, "dv")
+    _cmp(dg, gf.grad, 3e-3, "dgamma")
+    _cmp(db, bf_.grad, 3e-3, "dbeta")
+    _cmp(ops.c8_to_nchw(da), af.grad, 2e-2, "da")
+
+
+@pytest.mark.parametrize("C,Hl,Wl", [(16, 47, 53), (32, 48, 48), (16, 112, 112)])
+def test_plane_structured_up_block_tail(ops, C, Hl, Wl):
+    """ctl_scale_shift_upadd_act_c8 / ctl_bn_apply_from_sums_c8 with `low` on planes of >= 2048 low-resolution positions."""
+    g = torch.Generator(device="cuda").manual_seed(C + Hl)
+    N = 2
+    x = _bf(N, C, 2 * Hl, 2 * Wl, gen=g)
+    low = _bf(N, C, Hl, Wl, gen=g)
+    scale = 1 + 0.2 * torch.randn(C, device="cuda", generator=g)
+    shift = 0.3 * torch.randn(C, device="cuda", generator=g)
+    got = ops.scale_shift_upadd_act_c8(ops.nchw_to_c8(x), scale, shift, ops.nchw_to_c8(low), ops.ACT_LRELU)
+    want = F.leaky_relu(x.float() * scale.view(1, C, 1, 1) + shift.view(1, C, 1, 1) +
+                        F.interpolate(low.float(), scale_factor=2, mode="nearest"), 0.2)
+    _cmp(ops.c8_to_nchw(got), want, 1e-2, "scale/shift + up-sampled shortcut + LReLU")
+    xf = x.double()
+    sums = torch.stack([xf.sum((0, 2, 3)), (xf * xf).sum((0, 2, 3))]).contiguous()
+    gamma = 1 + 0.2 * torch.randn(C, device="cuda", generator=g)
+    beta = 0.3 * torch.randn(C, device="cuda", generator=g)
+    got2 = ops.bn_apply_from_sums_c8(ops.nchw_to_c8(x), sums, gamma, beta, 1e-5, ops.ACT_LRELU, low=ops.nchw_to_c8(low))[0]
+    want2 = F.leaky_relu(F.batch_norm(x.float(), None, None, gamma, beta, True, 0.1, 1e-5) +
+                         F.interpolate(low.float(), scale_factor=2, mode="nearest"), 0.2)
+    _cmp(ops.c8_to_nchw(got2), want2, 1e-2, "BatchNorm from sums + up-sampled shortcut + LReLU")
