@@ -1249,6 +1249,8 @@ extern "C" int ctl_stem_dgrad_c8(const void* dy, const float* x, int in_mode, fl
   CTL_REQUIRE(temperature > 0.0f, CTL_ERR_INVALID, "temperature must be positive");
   if (sm_count() < 0) return CTL_ERR_CUDA;
   cudaStream_t st = (cudaStream_t)stream;
+  if (aligned16(dy) && N <= 65535 && stem_dgrad_tensor_path_handles(H, W))
+    return stem_dgrad_tensor_path(dy, x, in_mode, 1.0f / temperature, (int)N, (int)Cin, (int)H, (int)W, weight, dx, st);
   const unsigned grid = grid_for(N * H * W);
   if (Cin == 1)
     launch_chained(stem_dgrad_kernel<1>, grid, kT, 0, st)((const __nv_bfloat16*)dy, x, weight, in_mode, 1.0f / temperature, (int)N, (int)H, (int)W, dx);

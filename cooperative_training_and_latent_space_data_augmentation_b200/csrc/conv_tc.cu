@@ -683,7 +683,22 @@ int dispatch_vp(const void* x, const ConvParams& p, int nt, cudaStream_t st) {
   return CTL_ERR_UNSUPPORTED;
 }
 
+#include "stem_dgrad_small.cuh"   // the stem's input gradient on the K3s pattern (called from c8_bwd.cu through the bridge below)
+
 }  // namespace
+
+// CTL_STEM_DGRAD_SMALL=0 (diagnostic): keep the CUDA-core stem_dgrad_kernel
+bool stem_dgrad_tensor_path_handles(int64_t H, int64_t W) {
+  static const bool on = [] { const char* e = getenv("CTL_STEM_DGRAD_SMALL"); return !(e && e[0] == '0'); }();
+  return on && ceil_div(H, (int64_t)kSmTile) * ceil_div(W, (int64_t)kSmTile) < 8192;
+}
+
+int stem_dgrad_tensor_path(const void* dy, const float* x, int in_mode, float inv_temp, int N, int Cin, int H, int W,
+                           const float* w, float* dx, cudaStream_t st) {
+  StemDgradParams p = {};
+  p.x = x; p.w = w; p.dx = dx; p.N = N; p.H = H; p.W = W; p.in_mode = in_mode; p.inv_temp = inv_temp;
+  return Cin == 1 ? launch_stem_dgrad_small<1>(dy, p, st) : launch_stem_dgrad_small<4>(dy, p, st);
+}
 }  // namespace ctl
 
 using namespace ctl;

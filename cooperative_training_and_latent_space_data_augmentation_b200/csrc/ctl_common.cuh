@@ -12,7 +12,11 @@ namespace ctl {
 void set_error(const char* fmt, ...);
 int cuda_fail(cudaError_t e, const char* what);   // records the message, returns CTL_ERR_CUDA
 int sm_count();                                   // cached per device; <0 on error
-int diag_flags();                                 // env CTL_DIAG_SKIP; always 0 unless the library is built with -DCTL_DIAG
+int diag_flags();
+// the stem's input gradient on the warp-level tensor path (conv_tc.cu / stem_dgrad_small.cuh)
+bool stem_dgrad_tensor_path_handles(int64_t H, int64_t W);
+int stem_dgrad_tensor_path(const void* dy, const float* x, int in_mode, float inv_temp, int N, int Cin, int H, int W,
+                           const float* w, float* dx, cudaStream_t st);                                 // env CTL_DIAG_SKIP; always 0 unless the library is built with -DCTL_DIAG
 
 // Profiling by elimination (tools/diag_conv.py) exists only in a -DCTL_DIAG build (make DIAG=1): the shipped kernels
 // contain no work-skipping switch.

@@ -179,10 +179,12 @@ def test_head_backward(ops, cout, act):
     _cmp(ops.c8_to_nchw(dx), xf.grad, 1e-2, "head dx")
 
 
-@pytest.mark.parametrize("cin,in_mode", [(1, 0), (4, 0), (4, 1), (4, 2)])
-def test_stem_backward(ops, cin, in_mode):
+@pytest.mark.parametrize("N,H,W", [(3, 37, 50), (2, 64, 96)])
+@pytest.mark.parametrize("cin,in_mode", [(1, 0), (1, 1), (4, 0), (4, 1), (4, 2)])
+def test_stem_backward(ops, cin, in_mode, N, H, W):
+    """Stem weight gradient (CUDA-core kernel) and input gradient (warp-level tensor path, csrc/stem_dgrad_small.cuh: dy
+    tiles by TMA, fp32 weights as a bf16 hi | lo fragment pair, softmax chain in registers) against torch autograd."""
     g = torch.Generator(device="cuda").manual_seed(cin * 10 + in_mode)
-    N, H, W = 3, 37, 50
     w = torch.randn(16, cin, 3, 3, device="cuda", generator=g) * 0.3
     dy = _bf(N, 16, H, W, gen=g, scale=0.1)
     wf = w.clone().requires_grad_(True)
