@@ -159,10 +159,11 @@ def test_downsample_sum(ops):
     _cmp(got, want, 1e-2, "downsample2x_sum")
 
 
+@pytest.mark.parametrize("N,H,W", [(3, 30, 44), (2, 64, 96), (1, 33, 20), (2, 9, 30)])
 @pytest.mark.parametrize("cout,act", [(4, 0), (1, 3)])
-def test_head_backward(ops, cout, act):
+def test_head_backward(ops, cout, act, N, H, W):
+    """Head backward (logits head without activation, sigmoid reconstruction head) against torch autograd."""
     g = torch.Generator(device="cuda").manual_seed(cout)
-    N, H, W = 3, 30, 44
     x = _bf(N, 16, H, W, gen=g)
     w = torch.randn(cout, 16, 1, 1, device="cuda", generator=g) * 0.3
     b = torch.randn(cout, device="cuda", generator=g)
