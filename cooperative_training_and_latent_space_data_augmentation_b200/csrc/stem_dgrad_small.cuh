@@ -98,11 +98,25 @@ stem_dgrad_small_kernel(const __grid_constant__ CUtensorMap tmap, const StemDgra
     mbar_wait(&full[stage], phase);
     const uint32_t a_base = smem_base + (uint32_t)(stage * kSmStageBytes) + lane_off;
     float acc[3][4];
+    float xin[3][4];                                         // forward input of output row j (in_mode 1), two rows ahead of use
 #pragma unroll
     for (int i = 0; i < kSmBandRows + 2; ++i) {
       uint32_t a[3][4];
 #pragma unroll
       for (int s = 0; s < 3; ++s) ldmatrix_x4(a[s], a_base + (uint32_t)((i * kSmHalo + s) * 16));
+      if constexpr (CIN == 4) {
+        if (p.in_mode == 1 && i < kSmBandRows) {
+          // this lane's channel pair (2tq, 2tq+1) of pixels x0 / x0 + 8 in row y0 + i: consumed when that row completes
+#pragma unroll
+          for (int hp = 0; hp < 2; ++hp) {
+            const int xx = x0 + 8 * hp;
+            const bool ok = y0 + i < p.H && xx < p.W && owner;
+            const int64_t q = (int64_t)(y0 + i) * p.W + xx;
+            xin[i % 3][2 * hp] = ok ? __ldg(p.x + ((int64_t)img * CIN + 2 * tq) * HW + q) : 0.0f;
+            xin[i % 3][2 * hp + 1] = ok ? __ldg(p.x + ((int64_t)img * CIN + 2 * tq + 1) * HW + q) : 0.0f;
+          }
+        }
+      }
 #pragma unroll
       for (int s = 0; s < 3; ++s)
 #pragma unroll
@@ -126,11 +140,7 @@ stem_dgrad_small_kernel(const __grid_constant__ CUtensorMap tmap, const StemDgra
           if constexpr (CIN == 4) {
 #pragma unroll
             for (int hp = 0; hp < 2; ++hp) {
-              const int xx = x0 + 8 * hp;
-              const bool ok = y < p.H && xx < p.W && owner;
-              const int64_t q = (int64_t)y * p.W + xx;
-              float v0 = ok ? __ldg(p.x + ((int64_t)img * CIN + 2 * tq) * HW + q) : 0.0f;
-              float v1 = ok ? __ldg(p.x + ((int64_t)img * CIN + 2 * tq + 1) * HW + q) : 0.0f;
+              float v0 = xin[j % 3][2 * hp], v1 = xin[j % 3][2 * hp + 1];
               // the other channel pair of this pixel lives in the neighbouring lane (tq ^ 1); lanes tq >= 2 idle along
               const float o0 = __shfl_xor_sync(0xffffffffu, v0, 1), o1 = __shfl_xor_sync(0xffffffffu, v1, 1);
               const float mx = fmaxf(fmaxf(v0, v1), fmaxf(o0, o1));
