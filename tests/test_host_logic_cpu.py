@@ -101,6 +101,46 @@ def test_batched_pack_registry_refreshes_every_weight_in_one_launch(monkeypatch)
     assert raised
 
 
+def test_pack_registry_table_never_names_dead_or_moved_weights(monkeypatch):
+    """The job table holds RAW pointers: (1) it pins the storages it names (a model that dies while the table -- or a
+    retired table a captured graph still reads -- is alive cannot leave dangling rows), (2) a rebuild drops the entries of
+    dead parameters together with their packed buffers, (3) a refresh outside a capture notices a registered weight that
+    died or moved since the table was built and rebuilds first."""
+    import gc
+    from cooperative_training_and_latent_space_data_augmentation_b200 import fastpath, ops
+    batched = []
+    monkeypatch.setattr(ops, "_pack_kernel", lambda param, transposed, tap_major=None: param.detach().clone().reshape(-1))
+    monkeypatch.setattr(ops, "pack_job", lambda weight, transposed, out, tap_major=None:
+                        [weight.data_ptr(), out.data_ptr(), weight.shape[0], weight.shape[1], 9, 16, int(transposed), 0])
+    monkeypatch.setattr(ops, "pack_conv_weights_batched", lambda table, n, m: batched.append(table.clone()))
+    monkeypatch.setattr(torch.cuda, "is_current_stream_capturing", lambda: False)
+    reg = fastpath._PackRegistry()
+    w1 = torch.nn.Parameter(torch.randn(16, 16, 3, 3))
+    w2 = torch.nn.Parameter(torch.randn(16, 16, 3, 3))
+    reg.get(w1, False, 'fwd')
+    reg.get(w2, False, 'fwd')
+    reg._rebuild_table()
+    assert reg._table_is_current() and len(reg.sources) == 2
+    p1 = w1.data_ptr()
+    assert any(src.data_ptr() == p1 for src in reg.sources)                      # (1) the storage is pinned by the table
+    del w1
+    gc.collect()
+    assert not reg._table_is_current()                                           # (3) a dead weight makes the table stale
+    fastpath.weights_changed()
+    reg.get(w2, False, 'fwd')                                                    # refresh: rebuilds first, then ONE launch
+    assert len(batched) == 1 and batched[0].shape[0] == 1 and int(batched[0][0, 0]) == w2.data_ptr()
+    assert len(reg.entries) == 1 and reg._table_is_current()                     # (2) the dead entry is gone
+    assert reg.retired and any(src.data_ptr() == p1 for src in reg.retired[-1][1])   # the retired table keeps ITS sources
+    w2.data = torch.randn(16, 16, 3, 3)                                          # storage moved behind the registry's back
+    assert not reg._table_is_current()
+    fastpath.prepare_packing.__globals__['_REGISTRY'], saved = reg, fastpath.prepare_packing.__globals__['_REGISTRY']
+    try:
+        fastpath.prepare_packing()                                               # what a trainer calls before a capture
+        assert reg._table_is_current() and int(reg.table[0, 0]) == w2.data_ptr()
+    finally:
+        fastpath.prepare_packing.__globals__['_REGISTRY'] = saved
+
+
 def test_grads_direct_mode_accumulates_in_place_and_returns_none():
     """trainpath._Grads: inside accumulate_into_grads() parameters that own a .grad receive their gradients in place
     (kernel-accumulated buffers are the .grad itself, small vectors go through one foreach add, a second contribution
